@@ -1,0 +1,308 @@
+"""Headline benchmark: descriptor-extraction throughput (voxels/s) on 50 k-voxel / 640x480 synthetic 3DMatch fragments
+(BASELINE.json configs[1], "C2"), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one full ResUNetBN2C.forward(x, image) on ONE fragment, coordinate maps rebuilt (what the reference does for every
+new SparseTensor), inputs already resident in HBM.  Steps rotate over 8 distinct fragments per rank and the L2 is flushed
+between steps (a 256 MiB write), outside the per-step CUDA events.  Multi-GPU: fragments are independent, each rank runs
+its own (weak scaling); the only collective is the all-gather of per-rank timings.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "descriptor-extraction throughput: voxels/sec/GPU on 50k-voxel fragments"
+N_FRAGMENTS = 8
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(cfg: str, rank: int):
+    from imfnet_b200 import synthetic
+    target, voxel, W, H = synthetic.CONFIGS[cfg]
+    frags = []
+    for i in range(N_FRAGMENTS):
+        seed = rank * N_FRAGMENTS + i
+        coords, _ = synthetic.make_fragment(target, voxel, seed)
+        frags.append((torch.from_numpy(coords), torch.ones((len(coords), 1)), synthetic.make_image(W, H, seed)))
+    return frags, (target, voxel, W, H)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path = the oracle port (the reference is pure Python over MinkowskiEngine,
+    which is not installable here; oracle/ restates it and is pinned to the unmodified model files by tests/golden)."""
+    if rank != 0:
+        return
+    from imfnet_b200 import synthetic
+    from oracle import imfnet_oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    frags, (target, voxel, W, H) = make_inputs(args.config, 0)
+    sd = synthetic.make_state_dict(0)
+    times = []
+    for i in range(args.warmup + args.steps):
+        c, f, im = frags[i % N_FRAGMENTS]
+        t0 = time.perf_counter()
+        imfnet_oracle.forward(sd, c, f, im)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    value = target * len(times) / total
+    sample = f"{len(times)} cold forwards (coordinate maps rebuilt) of one {target}-voxel fragment each, fp32, torch CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {target}-voxel synthetic 3DMatch fragment + {W}x{H} image, ResUNetBN2C 32-D descriptors",
+                   "fragments_per_step": 1, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def dominant_kernel_roofline(model, frag, flush):
+    """block2_tr-shaped convolution (64->64, 3^3, stride-1 level): the largest single launch of the forward
+    (179.6 MB algorithmic bytes at C2).  Timed live with CUDA events, L2 flushed between launches."""
+    from imfnet_b200 import _lib
+    from imfnet_b200.sparse import CoordinateManager
+    L = _lib.lib()
+    coords = frag[0].cuda()
+    cm = CoordinateManager(coords)
+    nbr = cm.table(1, 1, 3, False)
+    n = len(coords)
+    conv = model.block2_tr.conv1
+    cin, cout = conv.in_channels, conv.out_channels
+    X = torch.randn(n, cin, device="cuda")
+    Y = torch.empty(n, cout, device="cuda")
+    sc, sh = model.block2_tr.norm1.folded()
+    pairs = int((nbr >= 0).sum())
+    alg_bytes = 4 * pairs * cin + 8 * pairs + 4 * 27 * cin * cout + 4 * n * cout
+    s = torch.cuda.current_stream().cuda_stream
+    times = []
+    for i in range(13):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(L.imf_sparse_conv_fwd(X.data_ptr(), cin, conv.kernel.data_ptr(), nbr.data_ptr(), None, n, 27, cin, cout,
+                                         sc.data_ptr(), sh.data_ptr(), None, 0, 1, Y.data_ptr(), cout, s))
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.mean(times))
+    peak, how = load_peaks()
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": f"k_sparse_conv 3x3x3 {cin}->{cout} @ {n} voxels ({pairs} pairs)", "achieved": achieved,
+            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "alg_bytes_per_launch": alg_bytes,
+            "ms_per_launch": ms, "peak_source": how}
+
+
+def run_ours(args, rank, world, local_rank):
+    import imfnet_b200.me as ME
+    from imfnet_b200 import _lib, load_model, synthetic
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = _lib.lib()       # raises if the CUDA extension is missing
+    frags, (target, voxel, W, H) = make_inputs(args.config, rank)
+    sd = synthetic.make_state_dict(0)
+    model = load_model("ResUNetBN2C")(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3, config=None)
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().to(dev)
+    dev_frags = [(c.to(dev), f.to(dev), im.to(dev)) for c, f, im in frags]
+    pin_frags = [(c.pin_memory(), f.pin_memory(), im.pin_memory()) for c, f, im in frags]
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush():
+        flush_buf.fill_(1)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        c, f, im = dev_frags[i % N_FRAGMENTS]
+        return model(ME.SparseTensor(f, coordinates=c), im).F
+
+    host_out = torch.empty((target, 32), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        c, f, im = pin_frags[i % N_FRAGMENTS]
+        x = ME.SparseTensor(f.to(dev, non_blocking=True), coordinates=c.to(dev, non_blocking=True))
+        out = model(x, im.to(dev, non_blocking=True)).F
+        host_out.copy_(out, non_blocking=True)
+        return out
+
+    def timed(step_fn, count_launches=False):
+        for i in range(args.warmup):
+            step_fn(i)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        l0 = L.imf_launch_count()
+        ms = 0.0
+        wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn(args.warmup + i)
+            e1.record()
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+        barrier()
+        wall = time.perf_counter() - wall0
+        launches = L.imf_launch_count() - l0
+        clocks = sampler.stop()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item()), launches, clocks, wall
+
+    if args.profile:      # under ncu: just the resident steps, nothing else
+        with torch.no_grad():
+            for i in range(args.warmup + args.steps):
+                step_resident(i)
+            torch.cuda.synchronize()
+        return
+    with torch.no_grad():
+        ms_total, launches, clocks, wall = timed(step_resident)
+        ms_e2e, _, _, _ = timed(step_e2e)
+        roof = dominant_kernel_roofline(model, frags[0], flush) if rank == 0 else None
+
+    # per-fragment timing records: the one collective of this path
+    rec = torch.tensor([rank, target * args.steps, ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        allrec = [torch.zeros_like(rec) for _ in range(world)]
+        torch.distributed.all_gather(allrec, rec)
+    if rank != 0:
+        return
+
+    cpu = None
+    if world == 1:
+        from oracle import imfnet_oracle
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        c, f, im = frags[0]
+        ts = []
+        t_budget = time.perf_counter()
+        while len(ts) < 5 and time.perf_counter() - t_budget < 25:
+            t0 = time.perf_counter()
+            imfnet_oracle.forward(sd, c, f, im)
+            ts.append(time.perf_counter() - t0)
+        cpu = {"value": target / float(np.median(ts)), "unit": "voxels/s", "cores": cores, "kind": "port",
+               "sample": f"median of {len(ts)} cold oracle forwards of one {target}-voxel fragment (same weights), fp32 torch CPU"}
+
+    value = target * args.steps * world / (ms_total * 1e-3)
+    e2e_v = target * args.steps * world / (ms_e2e * 1e-3)
+    h2d = target * 16 + target * 4 + 3 * H * W * 4
+    d2h = target * 32 * 4
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {target}-voxel synthetic 3DMatch fragment + {W}x{H} image, ResUNetBN2C 32-D descriptors",
+                   "fragments_per_step": 1, "distinct_fragments_per_rank": N_FRAGMENTS,
+                   "l2": "flushed between steps (256 MiB write, outside the per-step CUDA events)",
+                   "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
+                   "coordinate_maps": "rebuilt every step (cold), as the reference does per SparseTensor",
+                   "parallelism": f"fragments sharded over {world} GPU(s), no data-path collective"},
+        "e2e": {"value": e2e_v, "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "wall_s_timed_region": wall,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--profile", action="store_true", help="run only warm-up + steps (for ncu launch lists)")
+    args = ap.parse_args()
+    if args.impl == "ours" and not args.profile:
+        args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

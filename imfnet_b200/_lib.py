@@ -1,0 +1,79 @@
+"""ctypes binding of include/imfnet_b200.h (the in-tree libimfnet_b200.so).  No fallbacks: if the library
+is missing or a call fails, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libimfnet_b200.so")
+
+_p, _i32, _i64, _sz, _f32, _f64 = C.c_void_p, C.c_int32, C.c_longlong, C.c_size_t, C.c_float, C.c_double
+
+
+class AttnWeights(C.Structure):
+    _fields_ = [(n, _p) for n in ("ln_q_w", "ln_q_b", "ln_c_w", "ln_c_b", "wq", "wkv", "wo", "bo", "ln_f_w", "ln_f_b",
+                                  "w1", "b1", "w2", "b2")] + [("latent", _i32), ("dim", _i32), ("inner", _i32)]
+
+
+# name -> (restype, argtypes); mirrors include/imfnet_b200.h one to one (tests/test_abi.py checks the header).
+SIGNATURES = {
+    "imf_last_error": (C.c_char_p, []),
+    "imf_version": (C.c_int, []),
+    "imf_launch_count": (_i64, []),
+    "imf_hash_capacity": (_i64, [_i64]),
+    "imf_hash_bytes": (_sz, [_i64]),
+    "imf_hash_clear": (C.c_int, [_p, _i64, _p]),
+    "imf_hash_build": (C.c_int, [_p, _p, _i32, _p, _i64, _p, _p]),
+    "imf_stride_map_workspace_bytes": (_sz, [_i32]),
+    "imf_stride_map": (C.c_int, [_p, _p, _i32, _i32, _p, _i64, _p, _p, _p, _p, _sz, _p, _p]),
+    "imf_kernel_map": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _i32, _p, _p]),
+    "imf_quantize_points": (C.c_int, [_p, _i32, _f64, _i32, _p, _p]),
+    "imf_batch_segments": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
+    "imf_sparse_conv_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _i32, _p]),
+    "imf_conv_first_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _p]),
+    "imf_pointwise_tail_fwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _i32, _p]),
+    "imf_linear_fwd": (C.c_int, [_p, _i32, _p, _p, _i32, _i32, _i32, _p, _i32, _p]),
+    "imf_attention_kv_workspace_bytes": (_sz, [_i32, _i32]),
+    "imf_attention_kv": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _p, _sz, _p]),
+    "imf_attention_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "imf_attention_fusion_fwd": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _i32, _p, _i32, _p, _sz, _p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Raises if it has not been built (python -m imfnet_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m imfnet_b200.build` "
+                               "(the CUDA extension is required; there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError(f"imfnet_b200 C-ABI call failed ({rc}): {lib().imf_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def cur_stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must live on a CUDA device (got {t.device}); imfnet_b200 has no CPU path")

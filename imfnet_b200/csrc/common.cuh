@@ -1,0 +1,102 @@
+// imfnet_b200 -- shared device/host helpers for the sm_100a kernels behind include/imfnet_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define IMF_OK 0
+#define IMF_ERR_BAD_ARG (-1)
+#define IMF_ERR_CUDA (-2)
+#define IMF_ERR_UNSUPPORTED (-3)
+
+// status word bits written by the coordinate kernels (device int32, read back by the host mirror)
+#define IMF_STATUS_COORD_RANGE 1      // |x|,|y|,|z| >= 2^15 or batch index outside [0, 65534]
+#define IMF_STATUS_DUPLICATE 2        // duplicate coordinate handed to imf_hash_build (rows must be unique)
+#define IMF_STATUS_TABLE_FULL 4       // probe sequence exhausted (capacity too small)
+
+void imf_set_error(const char* fmt, ...);
+void imf_note_launch();   // bumps the process-wide kernel-launch counter reported by imf_launch_count()
+
+#define IMF_CHECK_ARG(cond)                                                              \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      imf_set_error("%s:%d: bad argument: %s", __FILE__, __LINE__, #cond);               \
+      return IMF_ERR_BAD_ARG;                                                            \
+    }                                                                                    \
+  } while (0)
+
+#define IMF_CHECK_LAUNCH()                                                               \
+  do {                                                                                   \
+    imf_note_launch();                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) {                                                            \
+      imf_set_error("%s:%d: CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return IMF_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define IMF_CHECK_CUDA(expr)                                                             \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      imf_set_error("%s:%d: CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return IMF_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+// ---- coordinate keys + open-addressing hash table ------------------------------------------------
+// One slot = 16 bytes so that a probe is a single 128-bit load.
+struct __align__(16) ImfSlot {
+  unsigned long long key;
+  int val;
+  int pad;
+};
+static_assert(sizeof(ImfSlot) == 16, "slot must be 16 bytes");
+
+#define IMF_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+__host__ __device__ __forceinline__ bool imf_coord_in_range(int b, int x, int y, int z) {
+  return (unsigned)b < 65535u && (unsigned)(x + 32768) < 65536u && (unsigned)(y + 32768) < 65536u &&
+         (unsigned)(z + 32768) < 65536u;
+}
+
+__host__ __device__ __forceinline__ unsigned long long imf_pack_key(int b, int x, int y, int z) {
+  return ((unsigned long long)(unsigned)b << 48) | ((unsigned long long)(unsigned)(x + 32768) << 32) |
+         ((unsigned long long)(unsigned)(y + 32768) << 16) | (unsigned long long)(unsigned)(z + 32768);
+}
+
+__host__ __device__ __forceinline__ unsigned long long imf_hash64(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+
+#ifdef __CUDACC__
+// Look a key up; returns the stored value or -1.  `mask` = capacity-1 (capacity is a power of two).
+__device__ __forceinline__ int imf_table_lookup(const ImfSlot* __restrict__ table, unsigned long long mask,
+                                                unsigned long long key) {
+  unsigned long long slot = imf_hash64(key) & mask;
+  for (unsigned long long probes = 0; probes <= mask; ++probes) {
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(table + slot));
+    const unsigned long long k = ((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x;
+    if (k == key) return raw.z;
+    if (k == IMF_EMPTY_KEY) return -1;
+    slot = (slot + 1) & mask;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ float imf_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float imf_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+#endif

@@ -1,0 +1,328 @@
+// imfnet_b200 -- coordinate kernels: voxel hash, first-occurrence unique / stride maps, neighbour tables.
+//
+// Replaces (for the IMFNet descriptor path) what MinkowskiEngine 0.5.4's CoordinateManager does beneath
+//   ME.SparseTensor(feats, coordinates=...)          /root/reference/util/misc.py:95
+//   every stride-2 MinkowskiConvolution             /root/reference/model/resunet.py:54-85
+//   kernel-map generation of every convolution      /root/reference/model/resunet.py:168-226
+//   ME.utils.sparse_quantize(..., return_index=True) /root/reference/util/misc.py:83
+// Semantics are those of oracle/sparse_ops.py (unique_first, stride_coords, neighbour_table); all results
+// here are integers and must be bit-exact against it.
+//
+// Layout: a hash table is `capacity` 16-byte slots {u64 key, i32 val, i32 pad}; key = packed (b,x,y,z),
+// val = row index in the coordinate set.  Coordinate sets are int32 [N,4] row-major.
+#include "common.cuh"
+#include <stdarg.h>
+#include <atomic>
+
+// ------------------------------------------------------------------------------------------------
+// error string (thread-local so concurrent host threads do not clobber each other)
+static thread_local char g_err[512] = "";
+void imf_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* imf_last_error(void) { return g_err; }
+extern "C" int imf_version(void) { return 100; }
+
+static std::atomic<long long> g_launches{0};
+void imf_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long imf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int imf_floor_div(int a, int s) { return (a >= 0) ? (a / s) : -((-a + s - 1) / s); }
+
+__device__ __forceinline__ int imf_count(const int* n_ptr, int n_max) {
+  if (n_ptr == nullptr) return n_max;
+  int n = *n_ptr;
+  return n < n_max ? n : n_max;
+}
+
+// Insert unique rows: val = row index.  Duplicates / out-of-range rows raise status bits.
+__global__ void k_hash_insert_unique(const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max,
+                                     ImfSlot* table, unsigned long long mask, int* status) {
+  const int n = imf_count(n_ptr, n_max);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int4 c = coords[i];
+  if (!imf_coord_in_range(c.x, c.y, c.z, c.w)) {
+    atomicOr(status, IMF_STATUS_COORD_RANGE);
+    return;
+  }
+  const unsigned long long key = imf_pack_key(c.x, c.y, c.z, c.w);
+  unsigned long long slot = imf_hash64(key) & mask;
+  for (unsigned long long probes = 0; probes <= mask; ++probes) {
+    const unsigned long long prev = atomicCAS(&table[slot].key, IMF_EMPTY_KEY, key);
+    if (prev == IMF_EMPTY_KEY) {
+      table[slot].val = i;
+      return;
+    }
+    if (prev == key) {
+      atomicOr(status, IMF_STATUS_DUPLICATE);
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+  atomicOr(status, IMF_STATUS_TABLE_FULL);
+}
+
+// Insert floor(c/stride)*stride keys, keeping the MINIMUM source row per key (first occurrence).
+// slot_of[i] remembers where row i's key lives so later passes do not probe again.
+__global__ void k_stride_insert_min(const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max, int stride,
+                                    ImfSlot* table, unsigned long long mask, int* __restrict__ slot_of, int* status) {
+  const int n = imf_count(n_ptr, n_max);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 c = coords[i];
+  c.y = imf_floor_div(c.y, stride) * stride;
+  c.z = imf_floor_div(c.z, stride) * stride;
+  c.w = imf_floor_div(c.w, stride) * stride;
+  slot_of[i] = -1;
+  if (!imf_coord_in_range(c.x, c.y, c.z, c.w)) {
+    atomicOr(status, IMF_STATUS_COORD_RANGE);
+    return;
+  }
+  const unsigned long long key = imf_pack_key(c.x, c.y, c.z, c.w);
+  unsigned long long slot = imf_hash64(key) & mask;
+  for (unsigned long long probes = 0; probes <= mask; ++probes) {
+    const unsigned long long prev = atomicCAS(&table[slot].key, IMF_EMPTY_KEY, key);
+    if (prev == IMF_EMPTY_KEY || prev == key) {
+      atomicMin(reinterpret_cast<unsigned int*>(&table[slot].val), (unsigned int)i);   // val starts at 0xFFFFFFFF
+      slot_of[i] = (int)slot;
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+  atomicOr(status, IMF_STATUS_TABLE_FULL);
+}
+
+// flag[i] = 1 iff row i is the first occurrence of its key; block_count[b] = number of flags in block b.
+__global__ void __launch_bounds__(1024) k_flag_first(const int* __restrict__ slot_of, const ImfSlot* __restrict__ table,
+                                                     const int* __restrict__ n_ptr, int n_max,
+                                                     unsigned char* __restrict__ flag, int* __restrict__ block_count) {
+  __shared__ int warp_cnt[32];
+  const int n = imf_count(n_ptr, n_max);
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  bool first = false;
+  if (i < n) {
+    const int s = slot_of[i];
+    first = (s >= 0) && (table[s].val == i);
+    flag[i] = first ? 1 : 0;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, first);
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = warp_cnt[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = v;
+  }
+}
+
+// Ordered compaction: rank(i) = #flags before i.  Writes the strided coordinates of each first row at its
+// rank, rewrites the table value to that rank, and (optionally) first_idx[rank] = i.  The last block
+// publishes the total.
+__global__ void __launch_bounds__(1024) k_compact_first(const int4* __restrict__ coords, const int* __restrict__ slot_of,
+                                                        const unsigned char* __restrict__ flag,
+                                                        const int* __restrict__ block_count, const int* __restrict__ n_ptr,
+                                                        int n_max, int stride, ImfSlot* table, int4* __restrict__ coords_out,
+                                                        int* __restrict__ first_idx, int* __restrict__ n_out) {
+  __shared__ int warp_cnt[32];
+  __shared__ int red[32];
+  __shared__ int block_base;
+  const int n = imf_count(n_ptr, n_max);
+  // base = sum of counts of all preceding blocks
+  int part = 0;
+  for (int j = threadIdx.x; j < (int)blockIdx.x; j += 1024) part += block_count[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const bool first = (i < n) && flag[i];
+  const unsigned b = __ballot_sync(0xffffffffu, first);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_cnt[warp] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    // exclusive scan of warp counts
+    int c = warp_cnt[threadIdx.x];
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (threadIdx.x >= o) incl += t;
+    }
+    warp_cnt[threadIdx.x] = incl - c;
+    if (threadIdx.x == 31) {
+      // incl = total flags in this block
+      if (blockIdx.x == gridDim.x - 1) *n_out = v + incl;
+    }
+    if (threadIdx.x == 0) block_base = v;
+  }
+  __syncthreads();
+  if (first) {
+    const int rank = block_base + warp_cnt[warp] + __popc(b & ((1u << lane) - 1u));
+    int4 c = coords[i];
+    c.y = imf_floor_div(c.y, stride) * stride;
+    c.z = imf_floor_div(c.z, stride) * stride;
+    c.w = imf_floor_div(c.w, stride) * stride;
+    coords_out[rank] = c;
+    table[slot_of[i]].val = rank;
+    if (first_idx) first_idx[rank] = i;
+  }
+}
+
+// nbr[o*K3 + k] = row of the IN set at C_out[o] + off_k * scale (scale may be negative: transposed conv), or -1.
+// k = kx + K*ky + K*K*kz, off = (kx,ky,kz) - K/2  (x fastest; oracle/sparse_ops.py::kernel_offsets).
+__global__ void k_kernel_map(const int4* __restrict__ out_coords, const int* __restrict__ n_ptr, int n_max,
+                             const ImfSlot* __restrict__ table, unsigned long long mask, int K, int scale,
+                             int* __restrict__ nbr) {
+  const int n = imf_count(n_ptr, n_max);
+  const int K3 = K * K * K;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * K3) return;
+  const int o = (int)(idx / K3), k = (int)(idx % K3);
+  const int h = K / 2;
+  const int kx = k % K - h, ky = (k / K) % K - h, kz = k / (K * K) - h;
+  const int4 c = out_coords[o];
+  const int x = c.y + kx * scale, y = c.z + ky * scale, z = c.w + kz * scale;
+  int r = -1;
+  if (imf_coord_in_range(c.x, x, y, z)) r = imf_table_lookup(table, mask, imf_pack_key(c.x, x, y, z));
+  nbr[idx] = r;
+}
+
+// xyz (float64 [N,3]) -> int32 (b, floor(x/voxel), floor(y/voxel), floor(z/voxel)).  IEEE double division and
+// floor are exact, so this equals numpy's np.floor(xyz / voxel_size) (/root/reference/util/misc.py:82).
+__global__ void k_quantize_points(const double* __restrict__ xyz, int n, double voxel, int batch, int4* __restrict__ coords) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = floor(xyz[3 * (size_t)i + 0] / voxel), y = floor(xyz[3 * (size_t)i + 1] / voxel),
+               z = floor(xyz[3 * (size_t)i + 2] / voxel);
+  coords[i] = make_int4(batch, (int)x, (int)y, (int)z);
+}
+
+// seg[b] = first row whose batch index is >= b (rows are batch-sorted); seg[B] = n.
+__global__ void k_batch_segments(const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max, int B,
+                                 int* __restrict__ seg) {
+  const int n = imf_count(n_ptr, n_max);
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > B) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (coords[mid].x < b) lo = mid + 1; else hi = mid;
+  }
+  seg[b] = lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+static bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+
+extern "C" long long imf_hash_capacity(long long n) {
+  long long c = 1024;
+  while (c < 2 * n) c <<= 1;
+  return c;
+}
+extern "C" size_t imf_hash_bytes(long long capacity) { return (size_t)capacity * sizeof(ImfSlot); }
+
+extern "C" int imf_hash_clear(void* table, long long capacity, cudaStream_t stream) {
+  IMF_CHECK_ARG(table != nullptr && is_pow2(capacity));
+  IMF_CHECK_CUDA(cudaMemsetAsync(table, 0xFF, imf_hash_bytes(capacity), stream));
+  return IMF_OK;
+}
+
+extern "C" int imf_hash_build(const int32_t* coords, const int32_t* n_dev, int32_t n_max, void* table, long long capacity,
+                              int32_t* status, cudaStream_t stream) {
+  IMF_CHECK_ARG(table != nullptr && status != nullptr && is_pow2(capacity) && n_max >= 0 && capacity >= 2LL * n_max);
+  IMF_CHECK_CUDA(cudaMemsetAsync(table, 0xFF, imf_hash_bytes(capacity), stream));
+  if (n_max == 0) return IMF_OK;
+  IMF_CHECK_ARG(coords != nullptr);
+  k_hash_insert_unique<<<(n_max + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const int4*>(coords), n_dev, n_max,
+                                                                reinterpret_cast<ImfSlot*>(table),
+                                                                (unsigned long long)capacity - 1, status);
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
+}
+
+extern "C" size_t imf_stride_map_workspace_bytes(int32_t n_in_max) {
+  const size_t n = (size_t)(n_in_max > 0 ? n_in_max : 1);
+  const size_t blocks = (n + 1023) / 1024;
+  // slot_of[int n] + block_count[int blocks] + flag[u8 n], each rounded to 256 B
+  auto r = [](size_t b) { return (b + 255) / 256 * 256; };
+  return r(n * 4) + r(blocks * 4) + r(n);
+}
+
+extern "C" int imf_stride_map(const int32_t* coords_in, const int32_t* n_in_dev, int32_t n_in_max, int32_t stride,
+                              void* table_out, long long capacity, int32_t* coords_out, int32_t* n_out_dev,
+                              int32_t* first_idx, void* workspace, size_t workspace_bytes, int32_t* status,
+                              cudaStream_t stream) {
+  IMF_CHECK_ARG(table_out != nullptr && status != nullptr && n_out_dev != nullptr && coords_out != nullptr);
+  IMF_CHECK_ARG(is_pow2(capacity) && n_in_max >= 0 && capacity >= 2LL * n_in_max && stride >= 1);
+  IMF_CHECK_ARG(workspace_bytes >= imf_stride_map_workspace_bytes(n_in_max));
+  IMF_CHECK_CUDA(cudaMemsetAsync(table_out, 0xFF, imf_hash_bytes(capacity), stream));
+  if (n_in_max == 0) {
+    IMF_CHECK_CUDA(cudaMemsetAsync(n_out_dev, 0, sizeof(int32_t), stream));
+    return IMF_OK;
+  }
+  IMF_CHECK_ARG(coords_in != nullptr && workspace != nullptr);
+  const size_t n = (size_t)n_in_max;
+  const int blocks = (int)((n + 1023) / 1024);
+  auto r = [](size_t b) { return (b + 255) / 256 * 256; };
+  char* ws = reinterpret_cast<char*>(workspace);
+  int* slot_of = reinterpret_cast<int*>(ws);
+  int* block_count = reinterpret_cast<int*>(ws + r(n * 4));
+  unsigned char* flag = reinterpret_cast<unsigned char*>(ws + r(n * 4) + r((size_t)blocks * 4));
+  ImfSlot* table = reinterpret_cast<ImfSlot*>(table_out);
+  const unsigned long long mask = (unsigned long long)capacity - 1;
+  const int4* cin = reinterpret_cast<const int4*>(coords_in);
+  k_stride_insert_min<<<(n_in_max + 255) / 256, 256, 0, stream>>>(cin, n_in_dev, n_in_max, stride, table, mask, slot_of, status);
+  IMF_CHECK_LAUNCH();
+  k_flag_first<<<blocks, 1024, 0, stream>>>(slot_of, table, n_in_dev, n_in_max, flag, block_count);
+  IMF_CHECK_LAUNCH();
+  k_compact_first<<<blocks, 1024, 0, stream>>>(cin, slot_of, flag, block_count, n_in_dev, n_in_max, stride, table,
+                                               reinterpret_cast<int4*>(coords_out), first_idx, n_out_dev);
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
+}
+
+extern "C" int imf_kernel_map(const int32_t* out_coords, const int32_t* n_out_dev, int32_t n_out_max, const void* table_in,
+                              long long capacity, int32_t kernel_size, int32_t scale, int32_t* nbr, cudaStream_t stream) {
+  IMF_CHECK_ARG(is_pow2(capacity) && table_in != nullptr && n_out_max >= 0);
+  IMF_CHECK_ARG(kernel_size >= 1 && (kernel_size & 1) == 1 && kernel_size <= 7);
+  if (n_out_max == 0) return IMF_OK;
+  IMF_CHECK_ARG(out_coords != nullptr && nbr != nullptr);
+  const long long total = (long long)n_out_max * kernel_size * kernel_size * kernel_size;
+  const long long blocks = (total + 255) / 256;
+  IMF_CHECK_ARG(blocks < 0x7FFFFFFFLL);
+  k_kernel_map<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const int4*>(out_coords), n_out_dev, n_out_max,
+                                                     reinterpret_cast<const ImfSlot*>(table_in),
+                                                     (unsigned long long)capacity - 1, kernel_size, scale, nbr);
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
+}
+
+extern "C" int imf_quantize_points(const double* xyz, int32_t n, double voxel_size, int32_t batch_index, int32_t* coords,
+                                   cudaStream_t stream) {
+  IMF_CHECK_ARG(n >= 0 && voxel_size > 0.0);
+  if (n == 0) return IMF_OK;
+  IMF_CHECK_ARG(xyz != nullptr && coords != nullptr);
+  k_quantize_points<<<(n + 255) / 256, 256, 0, stream>>>(xyz, n, voxel_size, batch_index, reinterpret_cast<int4*>(coords));
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
+}
+
+extern "C" int imf_batch_segments(const int32_t* coords, const int32_t* n_dev, int32_t n_max, int32_t num_batches,
+                                  int32_t* seg, cudaStream_t stream) {
+  IMF_CHECK_ARG(seg != nullptr && num_batches >= 0 && n_max >= 0);
+  IMF_CHECK_ARG(coords != nullptr || n_max == 0);
+  k_batch_segments<<<(num_batches + 1 + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const int4*>(coords), n_dev, n_max,
+                                                                      num_batches, seg);
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
+}

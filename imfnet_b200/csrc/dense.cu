@@ -1,0 +1,294 @@
+// imfnet_b200 -- attention-fusion dense path, fp32 SIMT tier (LayerNorm, GEMM with fused epilogues, softmax).
+//
+// Replaces, for the IMFNet descriptor path, AttentionFusion.forward with depth=0, one cross head, mask=None:
+//   /root/reference/model/attention_fusion.py:132-154 (PreNorm :32-46, Attention :65-95, FeedForward :53-63, GEGLU :48-51)
+// as called per batch item from ResUNet2.transformer (/root/reference/model/resunet.py:237-273):
+//   x = P;  q = LN(x) Wq^T;  [k|v] = LN_c(I) Wkv^T;  A = softmax(q k^T / sqrt(d));  x = (A v) Wo^T + bo + x;
+//   x = W2 . geglu(W1 . LN(x) + b1) + b2 + x
+// Image tokens I arrive channel-major ([C, H*W], the NCHW feature map of the image encoder), so the context
+// LayerNorm also performs the [C,L] -> [L,C] transposition of resunet.py:259-261.
+#include "common.cuh"
+
+namespace {
+
+// ---- LayerNorm over the last dim of row-major rows; one warp per row, C <= 1024, C % 32 == 0 ----
+__global__ void __launch_bounds__(256) k_layernorm_rows(const float* __restrict__ X, int ldx, int M, int C,
+                                                        const float* __restrict__ g, const float* __restrict__ b, float eps,
+                                                        float* __restrict__ Y, int ldy) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* x = X + (size_t)row * ldx;
+  float v[32];
+  const int per = C / 32;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < per) { v[i] = x[i * 32 + lane]; s += v[i]; }
+  const float mean = imf_warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < per) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = 1.0f / sqrtf(imf_warp_sum(q) / (float)C + eps);
+  float* y = Y + (size_t)row * ldy;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (i < per) { const int c = i * 32 + lane; y[c] = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c); }
+}
+
+// ---- LayerNorm of image tokens stored channel-major: X[C][L] -> Y[L][C] (C == 128) ----------------
+__global__ void __launch_bounds__(256) k_layernorm_tokens_chw(const float* __restrict__ X, int L, const float* __restrict__ g,
+                                                              const float* __restrict__ b, float eps, float* __restrict__ Y) {
+  constexpr int C = 128;
+  __shared__ float t[C][33];
+  const int l0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < C; c += 8) {
+    const int l = l0 + lane;
+    t[c][lane] = (l < L) ? X[(size_t)c * L + l] : 0.f;
+  }
+  __syncthreads();
+  for (int tok = warp; tok < 32; tok += 8) {
+    const int l = l0 + tok;
+    if (l >= L) break;
+    float v[4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = t[i * 32 + lane][tok]; s += v[i]; }
+    const float mean = imf_warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float d = v[i] - mean; q += d * d; }
+    const float rstd = 1.0f / sqrtf(imf_warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = i * 32 + lane;
+      Y[(size_t)l * C + c] = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+    }
+  }
+}
+
+// ---- row softmax in place, one CTA per row ---------------------------------------------------------
+__global__ void __launch_bounds__(256) k_softmax_rows(float* __restrict__ S, int lds, int M, int L) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const int row = blockIdx.x;
+  if (row >= M) return;
+  float* s = S + (size_t)row * lds;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mx = -INFINITY;
+  for (int i = tid; i < L; i += 256) mx = fmaxf(mx, s[i]);
+  mx = imf_warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (tid == 0) { float m = red[0]; for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]); bcast = m; }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.f;
+  for (int i = tid; i < L; i += 256) { const float e = expf(s[i] - mx); s[i] = e; sum += e; }
+  sum = imf_warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (tid == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; bcast = t; }
+  __syncthreads();
+  const float inv = 1.0f / bcast;
+  for (int i = tid; i < L; i += 256) s[i] *= inv;
+  for (int i = L + tid; i < lds; i += 256) s[i] = 0.f;   // padding columns feed the PV GEMM as zeros
+}
+
+// ---- SGEMM: C[M,N] = alpha * A[M,K] . op(B) (+ bias[n]) (+ R[m,n]);  op(B) = B^T for B [N,K] (weights) or B for [K,N] ----
+// GEGLU mode: B has 2N rows ([N,K] layout); C[m,n] = (acc_n + bias[n]) * gelu(acc_{n+N} + bias[n+N])  (exact erf GELU).
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <bool B_KN, bool GEGLU>
+__global__ void __launch_bounds__(256) k_sgemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                               float* __restrict__ C, int ldc, int M, int N, int K, float alpha,
+                                               const float* __restrict__ bias, const float* __restrict__ R, int ldr) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[GEGLU ? 2 : 1][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[4][4], acc2[GEGLU ? 4 : 1][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; if (GEGLU) acc2[i][j] = 0.f; }
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    {   // A tile: 64 rows x 16 k; thread -> (row = tid/4, k4 = (tid%4)*4)
+      const int r = tid >> 2, kk = (tid & 3) * 4;
+      const int m = m0 + r;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = k0 + kk + i;
+        As[kk + i][r] = (m < M && k < K) ? A[(size_t)m * lda + k] : 0.f;
+      }
+    }
+    if (!B_KN) {
+      const int r = tid >> 2, kk = (tid & 3) * 4;
+      const int n = n0 + r;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = k0 + kk + i;
+        Bs[0][kk + i][r] = (n < N && k < K) ? B[(size_t)n * ldb + k] : 0.f;
+        if (GEGLU) Bs[GEGLU ? 1 : 0][kk + i][r] = (n < N && k < K) ? B[(size_t)(n + N) * ldb + k] : 0.f;
+      }
+    } else {   // B [K,N]: thread -> (k = tid/16, n4 = (tid%16)*4)
+      const int kk = tid >> 4, nn = (tid & 15) * 4;
+      const int k = k0 + kk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = n0 + nn + i;
+        Bs[0][kk][nn + i] = (n < N && k < K) ? B[(size_t)k * ldb + n] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[0][kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      if (GEGLU) {
+        const float4 b2 = *reinterpret_cast<const float4*>(&Bs[GEGLU ? 1 : 0][kk][tx * 4]);
+        const float b2v[4] = {b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc2[GEGLU ? i : 0][j] = fmaf(av[i], b2v[j], acc2[GEGLU ? i : 0][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = alpha * acc[i][j];
+      if (bias) v += __ldg(bias + n);
+      if (GEGLU) {
+        float gt = alpha * acc2[GEGLU ? i : 0][j];
+        if (bias) gt += __ldg(bias + n + N);
+        v = v * gelu_erf(gt);
+      }
+      if (R) v += R[(size_t)m * ldr + n];
+      C[(size_t)m * ldc + n] = v;
+    }
+  }
+}
+
+template <bool B_KN, bool GEGLU>
+int sgemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, float alpha,
+          const float* bias, const float* R, int ldr, cudaStream_t stream) {
+  if (M == 0 || N == 0) return IMF_OK;
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  k_sgemm<B_KN, GEGLU><<<grid, 256, 0, stream>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, R, ldr);
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
+}
+
+inline size_t r256(size_t b) { return (b + 255) / 256 * 256; }
+
+}  // namespace
+
+struct imf_attn_weights_t {
+  const float *ln_q_w, *ln_q_b;   // cross_attend_blocks.0.norm            [latent]
+  const float *ln_c_w, *ln_c_b;   // cross_attend_blocks.0.norm_context    [dim]
+  const float* wq;                // cross_attend_blocks.0.fn.to_q.weight  [inner, latent]
+  const float* wkv;               // cross_attend_blocks.0.fn.to_kv.weight [2*inner, dim]
+  const float *wo, *bo;           // cross_attend_blocks.0.fn.to_out       [latent, inner], [latent]
+  const float *ln_f_w, *ln_f_b;   // cross_attend_blocks.1.norm            [latent]
+  const float *w1, *b1;           // cross_attend_blocks.1.fn.net.0        [8*latent, latent], [8*latent]
+  const float *w2, *b2;           // cross_attend_blocks.1.fn.net.2        [latent, 4*latent], [latent]
+  int32_t latent, dim, inner;
+};
+
+extern "C" size_t imf_attention_kv_workspace_bytes(int32_t L, int32_t dim) { return r256((size_t)L * dim * 4); }
+
+// kv[L, 2*inner] = LN_c(tokens) . Wkv^T; tokens are channel-major [dim][L] (channel_major != 0) or row-major [L][dim].
+extern "C" int imf_attention_kv(const imf_attn_weights_t* w, const float* tokens, int32_t L, int32_t channel_major, float* kv,
+                                void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const float* img_chw = tokens;
+  IMF_CHECK_ARG(w != nullptr && L >= 0 && w->dim == 128);
+  if (L == 0) return IMF_OK;
+  IMF_CHECK_ARG(img_chw != nullptr && kv != nullptr && workspace != nullptr);
+  IMF_CHECK_ARG(workspace_bytes >= imf_attention_kv_workspace_bytes(L, w->dim));
+  float* cn = reinterpret_cast<float*>(workspace);
+  if (channel_major)
+    k_layernorm_tokens_chw<<<(L + 31) / 32, 256, 0, stream>>>(img_chw, L, w->ln_c_w, w->ln_c_b, 1e-5f, cn);
+  else
+    k_layernorm_rows<<<(L + 7) / 8, 256, 0, stream>>>(tokens, w->dim, L, w->dim, w->ln_c_w, w->ln_c_b, 1e-5f, cn, w->dim);
+  IMF_CHECK_LAUNCH();
+  return sgemm<false, false>(cn, w->dim, w->wkv, w->dim, kv, 2 * w->inner, L, 2 * w->inner, w->dim, 1.f, nullptr, nullptr, 0,
+                             stream);
+}
+
+extern "C" size_t imf_attention_workspace_bytes(int32_t M, int32_t L, int32_t latent, int32_t inner) {
+  const size_t Lp = ((size_t)L + 3) / 4 * 4;
+  return r256((size_t)M * latent * 4)      // xn / reused for LN before FFN
+         + r256((size_t)M * inner * 4)     // q
+         + r256((size_t)M * Lp * 4)        // scores
+         + r256((size_t)M * inner * 4)     // attention output
+         + r256((size_t)M * latent * 4)    // x after attention residual
+         + r256((size_t)M * latent * 4 * 4);  // GEGLU hidden [M, 4*latent]
+}
+
+// out[M, latent] = AttentionFusion(data = image tokens (through kv), queries_encoder = P[M, latent]).
+extern "C" int imf_attention_fusion_fwd(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const float* kv,
+                                        int32_t L, float* out, int32_t ldo, void* workspace, size_t workspace_bytes,
+                                        cudaStream_t stream) {
+  IMF_CHECK_ARG(w != nullptr && M >= 0 && L >= 1);
+  IMF_CHECK_ARG(w->latent % 32 == 0 && w->latent <= 1024 && w->inner % 4 == 0);
+  if (M == 0) return IMF_OK;
+  IMF_CHECK_ARG(P != nullptr && kv != nullptr && out != nullptr && workspace != nullptr && ldp >= w->latent && ldo >= w->latent);
+  IMF_CHECK_ARG(workspace_bytes >= imf_attention_workspace_bytes(M, L, w->latent, w->inner));
+  const int latent = w->latent, inner = w->inner;
+  const int Lp = (L + 3) / 4 * 4;
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* xn = reinterpret_cast<float*>(ws);  ws += r256((size_t)M * latent * 4);
+  float* q = reinterpret_cast<float*>(ws);   ws += r256((size_t)M * inner * 4);
+  float* S = reinterpret_cast<float*>(ws);   ws += r256((size_t)M * Lp * 4);
+  float* o = reinterpret_cast<float*>(ws);   ws += r256((size_t)M * inner * 4);
+  float* x1 = reinterpret_cast<float*>(ws);  ws += r256((size_t)M * latent * 4);
+  float* hid = reinterpret_cast<float*>(ws);
+  const float sm_scale = 1.0f / sqrtf((float)inner);
+  int rc;
+  k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(P, ldp, M, latent, w->ln_q_w, w->ln_q_b, 1e-5f, xn, latent);
+  IMF_CHECK_LAUNCH();
+  if ((rc = sgemm<false, false>(xn, latent, w->wq, latent, q, inner, M, inner, latent, 1.f, nullptr, nullptr, 0, stream))) return rc;
+  // S = (q . k^T) * scale ; k = kv[:, :inner]
+  if ((rc = sgemm<false, false>(q, inner, kv, 2 * inner, S, Lp, M, L, inner, sm_scale, nullptr, nullptr, 0, stream))) return rc;
+  k_softmax_rows<<<M, 256, 0, stream>>>(S, Lp, M, L);
+  IMF_CHECK_LAUNCH();
+  // o = A . v ; v = kv[:, inner:]
+  if ((rc = sgemm<true, false>(S, Lp, kv + inner, 2 * inner, o, inner, M, inner, L, 1.f, nullptr, nullptr, 0, stream))) return rc;
+  // x1 = o . Wo^T + bo + P
+  if ((rc = sgemm<false, false>(o, inner, w->wo, inner, x1, latent, M, latent, inner, 1.f, w->bo, P, ldp, stream))) return rc;
+  k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(x1, latent, M, latent, w->ln_f_w, w->ln_f_b, 1e-5f, xn, latent);
+  IMF_CHECK_LAUNCH();
+  // hid = geglu(xn . W1^T + b1)   [M, 4*latent]
+  if ((rc = sgemm<false, true>(xn, latent, w->w1, latent, hid, 4 * latent, M, 4 * latent, latent, 1.f, w->b1, nullptr, 0, stream))) return rc;
+  // out = hid . W2^T + b2 + x1
+  if ((rc = sgemm<false, false>(hid, 4 * latent, w->w2, 4 * latent, out, ldo, M, latent, 4 * latent, 1.f, w->b2, x1, latent, stream))) return rc;
+  return IMF_OK;
+}
+
+// Plain dense helper for the 1x1 MinkowskiConvolution module path (kernel [Cin,Cout], optional bias [Cout]).
+extern "C" int imf_linear_fwd(const float* X, int32_t ldx, const float* W_kn, const float* bias, int32_t M, int32_t Cin,
+                              int32_t Cout, float* Y, int32_t ldy, cudaStream_t stream) {
+  IMF_CHECK_ARG(M >= 0 && Cin > 0 && Cout > 0 && ldx >= Cin && ldy >= Cout);
+  if (M == 0) return IMF_OK;
+  IMF_CHECK_ARG(X != nullptr && W_kn != nullptr && Y != nullptr);
+  return sgemm<true, false>(X, ldx, W_kn, Cout, Y, ldy, M, Cout, Cin, 1.f, bias, nullptr, 0, stream);
+}

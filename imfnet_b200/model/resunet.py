@@ -1,0 +1,136 @@
+"""ResUNet2 family with the reference's constructor, attribute names and forward(x, image) signature
+(/root/reference/model/resunet.py:14-326).  Sub-modules only hold parameters under the reference's names (so
+`load_state_dict` of a reference checkpoint is strict-clean); `forward` hands the whole graph to the fused CUDA
+plan in imfnet_b200/engine.py.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import me as ME
+from ..engine import FusedPlan
+from .attention_fusion import AttentionFusion
+from .common import get_norm
+from .Img_Encoder import ImageEncoder
+from .residual_block import get_block
+
+
+class ResUNet2(ME.MinkowskiNetwork):
+    NORM_TYPE = None
+    BLOCK_NORM_TYPE = 'BN'
+    CHANNELS = [None, 32, 64, 128, 256]
+    TR_CHANNELS = [None, 32, 64, 64, 128]
+    IMG_CHANNELS = [None, 0, 0, 0, 0]
+
+    def __init__(self, in_channels=3, out_channels=32, bn_momentum=0.1, normalize_feature=None, conv1_kernel_size=None,
+                 D=3, config=None):
+        super().__init__(D)
+        if self.NORM_TYPE != 'BN' or self.BLOCK_NORM_TYPE != 'BN':
+            raise NotImplementedError(f"{type(self).__name__}: only the batch-norm variants (ResUNetBN2*) are implemented; "
+                                      "the configured IMFNet model is ResUNetBN2C (config_3dmatch.py:66)")
+        CH, TR, IMG = self.CHANNELS, self.TR_CHANNELS, self.IMG_CHANNELS
+        self.normalize_feature = normalize_feature
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.conv1_kernel_size = conv1_kernel_size
+
+        def conv(cin, cout, k, s, tr=False, bias=False):
+            cls = ME.MinkowskiConvolutionTranspose if tr else ME.MinkowskiConvolution
+            return cls(in_channels=cin, out_channels=cout, kernel_size=k, stride=s, dilation=1, bias=bias, dimension=D)
+
+        def norm(c):
+            return get_norm(self.NORM_TYPE, c, bn_momentum=bn_momentum, D=D)
+
+        def block(c):
+            return get_block(self.BLOCK_NORM_TYPE, c, c, bn_momentum=bn_momentum, D=D)
+
+        # encoder (reference lines 42-89)
+        self.conv1, self.norm1, self.block1 = conv(in_channels, CH[1], conv1_kernel_size, 1), norm(CH[1]), block(CH[1])
+        self.conv2, self.norm2, self.block2 = conv(CH[1], CH[2], 3, 2), norm(CH[2]), block(CH[2])
+        self.conv3, self.norm3, self.block3 = conv(CH[2], CH[3], 3, 2), norm(CH[3]), block(CH[3])
+        self.conv4, self.norm4, self.block4 = conv(CH[3], CH[4], 3, 2), norm(CH[4]), block(CH[4])
+        # fusion (91-99): Q from stride-8 point tokens, K/V from 128-channel image tokens, one head of CH[4]/2
+        self.attention_fusion = AttentionFusion(dim=128, depth=0, latent_dim=CH[4], cross_heads=1, latent_heads=8,
+                                                cross_dim_head=int(CH[4] / 2), latent_dim_head=int(CH[4] / 2))
+        # decoder (101-158)
+        self.conv4_tr, self.norm4_tr, self.block4_tr = conv(CH[4], TR[4], 3, 2, tr=True), norm(TR[4]), block(TR[4])
+        self.conv3_tr, self.norm3_tr, self.block3_tr = conv(CH[3] + TR[4] + IMG[1], TR[3], 3, 2, tr=True), norm(TR[3]), block(TR[3])
+        self.conv2_tr, self.norm2_tr, self.block2_tr = conv(CH[2] + TR[3] + IMG[2], TR[2], 3, 2, tr=True), norm(TR[2]), block(TR[2])
+        self.conv1_tr = conv(CH[1] + TR[2] + IMG[3], TR[1], 1, 1)
+        self.final = conv(TR[1], out_channels, 1, 1, bias=True)
+        self.img_encoder = ImageEncoder()
+        self._plan = None
+
+    def _apply(self, fn, *a, **k):
+        self._plan = None                      # weights moved / cast: re-pack lazily
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._plan = None
+        return super().load_state_dict(*a, **k)
+
+    def forward(self, x, image):
+        """x: sparse tensor exposing .F [N,Cin] fp32, .C [N,4] int32 (batch,x,y,z); image: [B,3,H,W] fp32.
+        Returns a SparseTensor on x's coordinate map with .F = [N,out_channels] (L2-normalised rows if
+        normalize_feature), rows in x's order (reference lines 163-235)."""
+        if self.training:
+            raise NotImplementedError("imfnet_b200 implements the eval-mode forward (BatchNorm running statistics); "
+                                      "call model.eval() as util/misc.py:44-45 does")
+        if self._plan is None:
+            self._plan = FusedPlan(self)
+        if not isinstance(x, ME.SparseTensor):       # duck-typed foreign container (.F / .C), e.g. a real ME tensor
+            x = ME.SparseTensor(x.F, coordinates=x.C)
+        F = self._plan.run(x, torch.as_tensor(image))
+        return ME.SparseTensor(F, coordinate_map_key=x.coordinate_map_key, coordinate_manager=x.coordinate_manager)
+
+
+class ResUNetBN2(ResUNet2):
+    NORM_TYPE = 'BN'
+
+
+class ResUNetBN2B(ResUNet2):
+    NORM_TYPE = 'BN'
+    CHANNELS = [None, 32, 64, 128, 256]
+    TR_CHANNELS = [None, 64, 64, 64, 64]
+
+
+class ResUNetBN2C(ResUNet2):
+    NORM_TYPE = 'BN'
+    CHANNELS = [None, 32, 64, 128, 256]
+    TR_CHANNELS = [None, 64, 64, 64, 128]
+
+
+class ResUNetBN2D(ResUNet2):
+    NORM_TYPE = 'BN'
+    CHANNELS = [None, 32, 64, 128, 256]
+    TR_CHANNELS = [None, 64, 64, 128, 128]
+
+
+class ResUNetBN2E(ResUNet2):
+    NORM_TYPE = 'BN'
+    CHANNELS = [None, 128, 128, 128, 256]
+    TR_CHANNELS = [None, 64, 128, 128, 128]
+
+
+class ResUNetIN2(ResUNet2):
+    NORM_TYPE = 'BN'
+    BLOCK_NORM_TYPE = 'IN'
+
+
+class ResUNetIN2B(ResUNetBN2B):
+    NORM_TYPE = 'BN'
+    BLOCK_NORM_TYPE = 'IN'
+
+
+class ResUNetIN2C(ResUNetBN2C):
+    NORM_TYPE = 'BN'
+    BLOCK_NORM_TYPE = 'IN'
+
+
+class ResUNetIN2D(ResUNetBN2D):
+    NORM_TYPE = 'BN'
+    BLOCK_NORM_TYPE = 'IN'
+
+
+class ResUNetIN2E(ResUNetBN2E):
+    NORM_TYPE = 'BN'
+    BLOCK_NORM_TYPE = 'IN'

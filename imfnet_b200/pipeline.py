@@ -1,0 +1,69 @@
+"""Caller-side pipeline with the reference's `extract_features` signature (/root/reference/util/misc.py:21-104),
+plus fragment sharding over the GPUs of one box."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import me as ME
+from .voxelize import voxelize
+
+
+def extract_features(model, xyz, rgb=None, normal=None, voxel_size=0.05, device=None, skip_check=False, is_eval=True,
+                     image=None):
+    """xyz [N,3] -> (xyz of the kept points [U,3], descriptors [U,C] on the device).
+
+    Same steps as util/misc.py:44-104; the voxelisation (floor, first-occurrence unique, batching) runs on the GPU
+    and gives bit-identical indices to np.floor + ME.utils.sparse_quantize(return_index=True)."""
+    if is_eval:
+        model.eval()
+    xyz = np.asarray(xyz)
+    if not skip_check:
+        assert xyz.shape[1] == 3
+        n = xyz.shape[0]
+        if rgb is not None:
+            assert n == len(rgb) and rgb.shape[1] == 3
+            if np.any(rgb > 1):
+                raise ValueError('Invalid color. Color must range from [0, 1]')
+        if normal is not None:
+            assert n == len(normal) and normal.shape[1] == 3
+            if np.any(normal > 1):
+                raise ValueError('Invalid normal. Normal must range from [-1, 1]')
+    if device is None:
+        device = torch.device("cuda:0")
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("imfnet_b200 runs on CUDA devices only (no CPU fallback)")
+
+    feats = []
+    if rgb is not None:
+        feats.append(np.asarray(rgb) - 0.5)
+    if normal is not None:
+        feats.append(np.asarray(normal) / 2)
+    if rgb is None and normal is None:
+        feats.append(np.ones((len(xyz), 1)))
+    feats = np.hstack(feats)
+
+    pts = torch.as_tensor(xyz, dtype=torch.float64).to(device, non_blocking=True)
+    coords, inds = voxelize(pts, voxel_size, batch_index=0)          # util/misc.py:82-86 on the GPU
+    inds_host = inds.cpu().numpy()
+    return_coords = xyz[inds_host]
+    f = torch.as_tensor(feats[inds_host], dtype=torch.float32).to(device, non_blocking=True)
+    stensor = ME.SparseTensor(f, coordinates=coords, device=device)
+    image = torch.as_tensor(image, dtype=torch.float32, device=device)
+    return return_coords, model(stensor, image).F
+
+
+def shard_indices(num_items: int, rank: int, world_size: int, weights=None):
+    """Fragment indices handled by `rank`.  Fragments are independent (scripts/generate_desc.py:65-123), so the only
+    partitioning decision is balance: round-robin, or greedy longest-first when per-fragment weights are given."""
+    if weights is None:
+        return list(range(rank, num_items, world_size))
+    order = sorted(range(num_items), key=lambda i: (-weights[i], i))
+    loads, mine = [0.0] * world_size, []
+    for i in order:
+        r = min(range(world_size), key=lambda j: (loads[j], j))
+        loads[r] += weights[i]
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)

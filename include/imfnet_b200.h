@@ -1,0 +1,133 @@
+/* imfnet_b200 -- C ABI of the B200 (sm_100a) descriptor-extraction kernels.
+ *
+ * The reference (XiaoshuiHuang/IMFNet) has no FFI of its own: its boundary for this path is the Python
+ * nn.Module API of model/ over the MinkowskiEngine Python API.  The host-side mirror
+ * in imfnet_b200/ keeps that Python API; everything below it goes through these entry points, which are
+ * what a MinkowskiEngine-style backend would bind.  Each entry cites the reference call site it serves.
+ *
+ * Conventions
+ *   - plain pointers + sizes; all pointers are DEVICE pointers unless stated; no allocation inside, the
+ *     caller passes workspaces (size queries are provided); work is enqueued on `stream` and not synchronised;
+ *   - return 0 on success, negative on failure (-1 bad argument, -2 CUDA error, -3 unsupported shape);
+ *     imf_last_error() returns a thread-local message for the last failure;
+ *   - coordinates are int32 [N,4] rows (batch, x, y, z), 16-byte aligned; features are fp32 row-major with an
+ *     explicit leading dimension (elements) so concatenations are column windows of one buffer;
+ *   - `*_dev` row counts are optional device int32 scalars: when non-NULL the kernels use
+ *     min(*n_dev, n_max) rows, so a caller can chain levels without reading sizes back to the host;
+ *   - coordinate range: batch in [0, 65534], |x|,|y|,|z| < 32768 (packed into one 64-bit key); violations,
+ *     duplicate rows and hash overflow set bits in a device `status` word (IMF_STATUS_*).
+ */
+#ifndef IMFNET_B200_H_
+#define IMFNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* imf_stream_t; /* == cudaStream_t */
+
+#define IMF_STATUS_COORD_RANGE 1
+#define IMF_STATUS_DUPLICATE 2
+#define IMF_STATUS_TABLE_FULL 4
+
+const char* imf_last_error(void);
+int imf_version(void);
+/* Number of kernels this library has launched in the calling process so far (bench.py's gpu_launches). */
+long long imf_launch_count(void);
+
+/* ---- coordinates: ME CoordinateManager work behind ME.SparseTensor(...) (util/misc.py:95) ------------- */
+
+/* Slots (power of two, >= 2n) and bytes of a hash table for n coordinates. */
+long long imf_hash_capacity(long long n);
+size_t imf_hash_bytes(long long capacity);
+int imf_hash_clear(void* table, long long capacity, imf_stream_t stream);
+
+/* Build the coordinate -> row table of a set of UNIQUE coordinates (value = row index). */
+int imf_hash_build(const int32_t* coords, const int32_t* n_dev, int32_t n_max, void* table, long long capacity,
+                   int32_t* status, imf_stream_t stream);
+
+/* Coarser coordinate set of a stride-2 convolution (model/resunet.py:54-85), or, with stride 1, the
+ * first-occurrence de-duplication of ME.utils.sparse_quantize (util/misc.py:83):
+ *   coords_out = unique_first(floor(coords_in / stride) * stride), rows in order of first appearance;
+ *   table_out maps those coordinates to their row; *n_out_dev = number of rows;
+ *   first_idx (optional, [n_in_max]) receives the source row of every output row. */
+size_t imf_stride_map_workspace_bytes(int32_t n_in_max);
+int imf_stride_map(const int32_t* coords_in, const int32_t* n_in_dev, int32_t n_in_max, int32_t stride, void* table_out,
+                   long long capacity, int32_t* coords_out, int32_t* n_out_dev, int32_t* first_idx, void* workspace,
+                   size_t workspace_bytes, int32_t* status, imf_stream_t stream);
+
+/* Neighbour table of one convolution (ME kernel map, output-stationary form):
+ *   nbr[o*K^3 + k] = row of the input set at out_coords[o] + off_k*scale, or -1;
+ *   k = kx + K*ky + K^2*kz, off = (kx,ky,kz) - K/2.  Forward conv: scale = input tensor stride.
+ *   Transposed conv (model/resunet.py:101-134): out = fine set, table = coarse set, scale = -(fine stride). */
+int imf_kernel_map(const int32_t* out_coords, const int32_t* n_out_dev, int32_t n_out_max, const void* table_in,
+                   long long capacity, int32_t kernel_size, int32_t scale, int32_t* nbr, imf_stream_t stream);
+
+/* coords[i] = (batch_index, floor(xyz[i]/voxel_size)) in float64, as util/misc.py:82 computes on the host. */
+int imf_quantize_points(const double* xyz, int32_t n, double voxel_size, int32_t batch_index, int32_t* coords,
+                        imf_stream_t stream);
+
+/* seg[b] = first row with batch index >= b, seg[num_batches] = n (rows are batch-sorted; resunet.py:240-255). */
+int imf_batch_segments(const int32_t* coords, const int32_t* n_dev, int32_t n_max, int32_t num_batches, int32_t* seg,
+                       imf_stream_t stream);
+
+/* ---- sparse convolution: ME.MinkowskiConvolution(+Transpose).forward (model/resunet.py:168-213,
+ *      model/residual_block.py:40,44) with BatchNorm(eval)/residual/ReLU fused ------------------------- */
+
+/* Y[o, :Cout] = act( (sum_k X[nbr[o,k], :Cin] . W[k]) * scale + shift (+ residual[o]) ), W = [K^3, Cin, Cout].
+ * scale/shift (per output channel, both or neither) and residual are optional; relu != 0 applies max(.,0).
+ * Requires Cin % 32 == 0, Cout % 32 == 0, K^3 <= 27, ldx % 4 == 0, X and W 16-byte aligned. */
+int imf_sparse_conv_fwd(const float* X, int32_t ldx, const float* W, const int32_t* nbr, const int32_t* n_out_dev,
+                        int32_t n_out_max, int32_t kernel_volume, int32_t Cin, int32_t Cout, const float* scale,
+                        const float* shift, const float* residual, int32_t ldr, int32_t relu, float* Y, int32_t ldy,
+                        imf_stream_t stream);
+
+/* First layer (conv1, model/resunet.py:42-49,168): K in {1,3,5}, Cin <= 8, Cout in {32,64,128}; neighbours are
+ * probed from the hash table of the same coordinate set, no neighbour table needed. */
+int imf_conv_first_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords, const int32_t* n_dev,
+                       int32_t n_max, const void* table, long long capacity, int32_t kernel_size, int32_t tensor_stride,
+                       int32_t Cout, const float* scale, const float* shift, int32_t relu, float* Y, int32_t ldy,
+                       imf_stream_t stream);
+
+/* conv1_tr (1x1, no bias) -> ReLU -> final (1x1 + bias) -> optional row L2 normalisation
+ * (model/resunet.py:224-233).  W1 = [C0, C1], W2 = [C1, C2], b2 = [C2] or NULL; C1 in {32,64,128}, C2 <= 32. */
+int imf_pointwise_tail_fwd(const float* X, int32_t ldx, int32_t C0, const float* W1, int32_t C1, const float* W2,
+                           const float* b2, int32_t C2, const int32_t* n_dev, int32_t n_max, int32_t normalize, float* Y,
+                           int32_t ldy, imf_stream_t stream);
+
+/* Y = X . W (+ bias): a 1x1 ME.MinkowskiConvolution as a module (kernel [Cin, Cout]). */
+int imf_linear_fwd(const float* X, int32_t ldx, const float* W_kn, const float* bias, int32_t M, int32_t Cin, int32_t Cout,
+                   float* Y, int32_t ldy, imf_stream_t stream);
+
+/* ---- attention fusion: AttentionFusion.forward (model/attention_fusion.py:132-154), depth 0, 1 head ---- */
+typedef struct {
+  const float *ln_q_w, *ln_q_b; /* cross_attend_blocks.0.norm            [latent]                   */
+  const float *ln_c_w, *ln_c_b; /* cross_attend_blocks.0.norm_context    [dim]                      */
+  const float* wq;              /* cross_attend_blocks.0.fn.to_q.weight  [inner, latent]            */
+  const float* wkv;             /* cross_attend_blocks.0.fn.to_kv.weight [2*inner, dim]             */
+  const float *wo, *bo;         /* cross_attend_blocks.0.fn.to_out       [latent, inner], [latent]  */
+  const float *ln_f_w, *ln_f_b; /* cross_attend_blocks.1.norm            [latent]                   */
+  const float *w1, *b1;         /* cross_attend_blocks.1.fn.net.0        [8*latent, latent], [8*latent] */
+  const float *w2, *b2;         /* cross_attend_blocks.1.fn.net.2        [latent, 4*latent], [latent]   */
+  int32_t latent, dim, inner;
+} imf_attn_weights_t; /* HOST struct of DEVICE pointers */
+
+/* kv[L, 2*inner] = LayerNorm_c(tokens) . Wkv^T for one image.  channel_major != 0: tokens are the encoder's
+ * feature map [dim][L] (NCHW, L = H'*W'), i.e. the view/permute of model/resunet.py:259-261 is folded in;
+ * channel_major == 0: tokens are row-major [L][dim] (AttentionFusion.forward's `data` argument). */
+size_t imf_attention_kv_workspace_bytes(int32_t L, int32_t dim);
+int imf_attention_kv(const imf_attn_weights_t* w, const float* tokens, int32_t L, int32_t channel_major, float* kv,
+                     void* workspace, size_t workspace_bytes, imf_stream_t stream);
+
+/* out[M, latent] = cross-attention + GEGLU feed-forward of M point tokens P[M, latent] against kv. */
+size_t imf_attention_workspace_bytes(int32_t M, int32_t L, int32_t latent, int32_t inner);
+int imf_attention_fusion_fwd(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const float* kv, int32_t L,
+                             float* out, int32_t ldo, void* workspace, size_t workspace_bytes, imf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMFNET_B200_H_ */

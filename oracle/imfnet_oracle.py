@@ -114,12 +114,16 @@ def transformer(sd, images, Fs8, C8):
 # ----------------------------------------------------------------------------------------------
 # sparse ResUNet
 # ----------------------------------------------------------------------------------------------
+def _conv(cm, x, W, t_in, t_out, K, transposed=False):
+    """ME.MinkowskiConvolution(+Transpose).forward on the cached kernel map of (t_in -> t_out)."""
+    return ops.conv_forward(x, W, cm.table(t_in, t_out, K, transposed), pairs=cm.pairs(t_in, t_out, K, transposed))
+
+
 def _block(sd, cm, t, x, p):
     """model/residual_block.py:37-53 BasicBlockBN.forward (conv3 -> BN -> ReLU -> conv3 -> BN -> +x -> ReLU)."""
-    nbr = cm.table(t, t, 3, False)
-    out = ops.conv_forward(x, sd[p + ".conv1.kernel"], nbr)
+    out = _conv(cm, x, sd[p + ".conv1.kernel"], t, t, 3)
     out = torch.relu(_bn(out, sd, p + ".norm1.bn"))
-    out = ops.conv_forward(out, sd[p + ".conv2.kernel"], nbr)
+    out = _conv(cm, out, sd[p + ".conv2.kernel"], t, t, 3)
     out = _bn(out, sd, p + ".norm2.bn")
     return torch.relu(out + x)
 
@@ -136,40 +140,40 @@ def forward(sd, coords, feats, image, normalize_feature=True, conv1_kernel_size=
         img = image_encoder(sd, image.detach().float().cpu())                       # :166
         acts["image"] = img
 
-        out = ops.conv_forward(x, sd["conv1.kernel"], cm.table(1, 1, conv1_kernel_size, False))   # :168
+        out = _conv(cm, x, sd["conv1.kernel"], 1, 1, conv1_kernel_size)   # :168
         out = _bn(out, sd, "norm1.bn")                                               # :169
         out_s1 = _block(sd, cm, 1, out, "block1")                                    # :170 (relu :171 idempotent)
         acts["out_s1"] = out_s1
 
         cm.stride(1, 2)
-        out = ops.conv_forward(out_s1, sd["conv2.kernel"], cm.table(1, 2, 3, False))  # :173
+        out = _conv(cm, out_s1, sd["conv2.kernel"], 1, 2, 3)  # :173
         out_s2 = _block(sd, cm, 2, _bn(out, sd, "norm2.bn"), "block2")               # :174-175
         acts["out_s2"] = out_s2
 
         cm.stride(2, 2)
-        out = ops.conv_forward(out_s2, sd["conv3.kernel"], cm.table(2, 4, 3, False))  # :178
+        out = _conv(cm, out_s2, sd["conv3.kernel"], 2, 4, 3)  # :178
         out_s4 = _block(sd, cm, 4, _bn(out, sd, "norm3.bn"), "block3")               # :179-180
         acts["out_s4"] = out_s4
 
         cm.stride(4, 2)
-        out = ops.conv_forward(out_s4, sd["conv4.kernel"], cm.table(4, 8, 3, False))  # :183
+        out = _conv(cm, out_s4, sd["conv4.kernel"], 4, 8, 3)  # :183
         out_s8 = _block(sd, cm, 8, _bn(out, sd, "norm4.bn"), "block4")               # :184-185
         acts["out_s8"] = out_s8
 
         fused = transformer(sd, img, out_s8, cm.get(8).C)                            # :189
         acts["fused"] = fused
 
-        out = ops.conv_forward(fused, sd["conv4_tr.kernel"], cm.table(8, 4, 3, True))  # :191
+        out = _conv(cm, fused, sd["conv4_tr.kernel"], 8, 4, 3, True)  # :191
         out = _block(sd, cm, 4, _bn(out, sd, "norm4_tr.bn"), "block4_tr")            # :192-194
         acts["out_s4_tr"] = out
         out = torch.cat([out, out_s4], dim=1)                                        # :197
 
-        out = ops.conv_forward(out, sd["conv3_tr.kernel"], cm.table(4, 2, 3, True))  # :202
+        out = _conv(cm, out, sd["conv3_tr.kernel"], 4, 2, 3, True)  # :202
         out = _block(sd, cm, 2, _bn(out, sd, "norm3_tr.bn"), "block3_tr")            # :203-205
         acts["out_s2_tr"] = out
         out = torch.cat([out, out_s2], dim=1)                                        # :208
 
-        out = ops.conv_forward(out, sd["conv2_tr.kernel"], cm.table(2, 1, 3, True))  # :213
+        out = _conv(cm, out, sd["conv2_tr.kernel"], 2, 1, 3, True)  # :213
         out = _block(sd, cm, 1, _bn(out, sd, "norm2_tr.bn"), "block2_tr")            # :214-216
         acts["out_s1_tr"] = out
         out = torch.cat([out, out_s1], dim=1)                                        # :219

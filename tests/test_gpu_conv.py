@@ -1,0 +1,133 @@
+"""GPU: sparse convolution kernels vs the oracle (fp32, tolerance 1e-4 relative as the north star states)."""
+import numpy as np
+import pytest
+import torch
+
+from imfnet_b200 import _lib, synthetic
+from oracle import sparse_ops
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4      # north-star tolerance; observed error is ~1e-6 (fp32 accumulation-order noise)
+
+
+def close(a, b, rtol=RTOL):
+    scale = float(b.abs().max()) + 1e-30
+    err = float((a - b).abs().max()) / scale
+    assert err < rtol, f"max abs err / max|ref| = {err:.3e}"
+
+
+@pytest.fixture(scope="module")
+def frag():
+    coords, _ = synthetic.make_fragment(6000, 0.05, seed=4)
+    ocm = sparse_ops.CoordinateManager(coords)
+    for t in (1, 2, 4):
+        ocm.stride(t, 2)
+    from imfnet_b200.sparse import CoordinateManager
+    cm = CoordinateManager(torch.from_numpy(coords).cuda())
+    cm.build_pyramid([2, 4, 8])
+    return coords, ocm, cm
+
+
+def run_conv(X, W, nbr, n_out, scale=None, shift=None, R=None, relu=False):
+    L = _lib.lib()
+    Y = torch.full((n_out, W.shape[-1]), float("nan"), device="cuda")
+    _lib.check(L.imf_sparse_conv_fwd(X.data_ptr(), X.stride(0), W.data_ptr(), nbr.data_ptr(), None, n_out, W.shape[0],
+                                     W.shape[1], W.shape[2], _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(R),
+                                     0 if R is None else R.stride(0), int(relu), Y.data_ptr(), Y.stride(0), _lib.cur_stream()))
+    torch.cuda.synchronize()
+    return Y.cpu()
+
+
+@pytest.mark.parametrize("t_in,t_out,tr,cin,cout", [
+    (1, 1, False, 32, 32), (1, 1, False, 64, 64), (1, 2, False, 32, 64), (2, 2, False, 64, 64), (2, 4, False, 64, 128),
+    (4, 4, False, 128, 128), (4, 8, False, 128, 256), (8, 8, False, 256, 256), (8, 4, True, 256, 128), (4, 2, True, 256, 64),
+    (2, 1, True, 128, 64)])
+def test_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout):
+    coords, ocm, cm = frag
+    g = torch.Generator().manual_seed(cin * 1000 + cout + t_in)
+    n_in, n_out = len(ocm.get(t_in)), len(ocm.get(t_out))
+    X = torch.randn(n_in, cin, generator=g)
+    W = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+    onbr = ocm.table(t_in, t_out, 3, tr)
+    ref = sparse_ops.conv_forward(X, W, onbr)
+    nbr = cm.table(t_in, t_out, 3, tr)
+    assert np.array_equal(nbr.cpu().numpy(), onbr)
+    close(run_conv(X.cuda(), W.cuda(), nbr, n_out), ref)
+
+
+def test_conv_fused_epilogue_and_strided_operands(frag):
+    """BatchNorm affine + residual + ReLU, reading a column window of a wider buffer and writing into another."""
+    coords, ocm, cm = frag
+    g = torch.Generator().manual_seed(7)
+    n = len(coords)
+    wide = torch.randn(n, 96, generator=g)
+    W = torch.randn(27, 32, 64, generator=g) / 30
+    scale, shift = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+    R = torch.randn(n, 80, generator=g)
+    onbr = ocm.table(1, 1, 3, False)
+    ref = torch.relu(sparse_ops.conv_forward(wide[:, 64:96].contiguous(), W, onbr) * scale + shift + R[:, 16:80])
+    wide_d, R_d = wide.cuda(), R.cuda()
+    out = torch.zeros(n, 128, device="cuda")
+    L = _lib.lib()
+    _lib.check(L.imf_sparse_conv_fwd(wide_d.data_ptr() + 64 * 4, 96, W.cuda().data_ptr(), cm.table(1, 1, 3, False).data_ptr(),
+                                     None, n, 27, 32, 64, scale.cuda().data_ptr(), shift.cuda().data_ptr(),
+                                     R_d.data_ptr() + 16 * 4, 80, 1, out.data_ptr() + 64 * 4, 128, _lib.cur_stream()))
+    torch.cuda.synchronize()
+    close(out[:, 64:].cpu(), ref)
+    assert float(out[:, :64].abs().max()) == 0.0          # neighbouring columns untouched
+
+
+@pytest.mark.parametrize("cin,cout,K", [(1, 32, 5), (3, 32, 5), (1, 32, 3), (1, 64, 5)])
+def test_first_conv_matches_oracle(frag, cin, cout, K):
+    coords, ocm, cm = frag
+    g = torch.Generator().manual_seed(cin + cout + K)
+    n = len(coords)
+    X = torch.rand(n, cin, generator=g) + 0.5
+    W = torch.randn(K ** 3, cin, cout, generator=g) / np.sqrt(K ** 3 * cin)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ref = sparse_ops.conv_forward(X, W, ocm.table(1, 1, K, False)) * scale + shift
+    L = _lib.lib()
+    lvl = cm.level(1)
+    Y = torch.empty(n, cout, device="cuda")
+    _lib.check(L.imf_conv_first_fwd(X.cuda().data_ptr(), cin, cin, W.cuda().data_ptr(), lvl.coords.data_ptr(), None, n,
+                                    lvl.table.data_ptr(), lvl.capacity, K, 1, cout, scale.cuda().data_ptr(),
+                                    shift.cuda().data_ptr(), 0, Y.data_ptr(), cout, _lib.cur_stream()))
+    torch.cuda.synchronize()
+    close(Y.cpu(), ref)
+
+
+@pytest.mark.parametrize("normalize", [True, False])
+def test_pointwise_tail_matches_oracle(normalize):
+    g = torch.Generator().manual_seed(5)
+    n = 3001
+    X = torch.randn(n, 96, generator=g)
+    W1, W2, b2 = torch.randn(96, 64, generator=g) / 10, torch.randn(64, 32, generator=g) / 8, torch.randn(32, generator=g)
+    ref = torch.relu(X @ W1) @ W2 + b2
+    if normalize:
+        ref = ref / torch.norm(ref, p=2, dim=1, keepdim=True)
+    L = _lib.lib()
+    Y = torch.empty(n, 32, device="cuda")
+    _lib.check(L.imf_pointwise_tail_fwd(X.cuda().data_ptr(), 96, 96, W1.cuda().data_ptr(), 64, W2.cuda().data_ptr(),
+                                        b2.cuda().data_ptr(), 32, None, n, int(normalize), Y.data_ptr(), 32, _lib.cur_stream()))
+    torch.cuda.synchronize()
+    close(Y.cpu(), ref)
+
+
+def test_module_level_layers_match_standin(frag):
+    """imfnet_b200.me layers used one by one (the un-fused route) give the oracle's numbers."""
+    import imfnet_b200.me as ME
+    coords, ocm, cm = frag
+    g = torch.Generator().manual_seed(9)
+    X = torch.randn(len(coords), 32, generator=g)
+    conv = ME.MinkowskiConvolution(32, 64, kernel_size=3, stride=2, dimension=3).cuda()
+    tr = ME.MinkowskiConvolutionTranspose(64, 32, kernel_size=3, stride=2, dimension=3).cuda()
+    pw = ME.MinkowskiConvolution(32, 32, kernel_size=1, stride=1, bias=True, dimension=3).cuda()
+    x = ME.SparseTensor(X.cuda(), coordinates=torch.from_numpy(coords).cuda())
+    y = conv(x)
+    z = pw(tr(y))
+    ref_y = sparse_ops.conv_forward(X, conv.kernel.detach().cpu(), ocm.table(1, 2, 3, False))
+    ref_z = sparse_ops.conv_forward(ref_y, tr.kernel.detach().cpu(), ocm.table(2, 1, 3, True)) @ pw.kernel.detach().cpu() + pw.bias.detach().cpu()
+    close(y.F.cpu(), ref_y)
+    close(z.F.cpu(), ref_z)
+    assert z.coordinate_map_key == x.coordinate_map_key and len(z) == len(x)
+    assert ME.cat(x, z).F.shape == (len(coords), 64)

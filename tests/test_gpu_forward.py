@@ -1,0 +1,131 @@
+"""GPU: attention fusion and the full descriptor forward vs golden vectors (generated from the unmodified reference)
+and vs the oracle.  Tolerance: row-wise ||d - d_ref|| / ||d_ref|| <= 1e-4 (BASELINE.json north star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from imfnet_b200 import synthetic
+from oracle import imfnet_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def rel_rows(a, b):
+    return float((torch.linalg.norm(a - b, dim=1) / torch.linalg.norm(b, dim=1)).max())
+
+
+def test_attention_fusion_matches_reference_golden(golden_dir, cuda_model):
+    g = np.load(os.path.join(golden_dir, "attention.npz"))
+    af = cuda_model.attention_fusion
+    out = af(torch.from_numpy(g["data"]).cuda(), queries_encoder=torch.from_numpy(g["queries"]).cuda())
+    assert out.shape == (1, 333, 256)
+    assert rel_rows(out[0].cpu(), torch.from_numpy(g["out"])[0]) < TOL
+
+
+def test_attention_ragged_sizes_vs_oracle(state_dict, cuda_model):
+    """M and L that are not multiples of any tile size (C3's 154x47 = 7238 tokens is such a case)."""
+    rng = np.random.default_rng(2)
+    for M, Lt in ((1, 7), (65, 302), (130, 1001)):
+        P = torch.from_numpy(rng.normal(0, 1, (1, M, 256)).astype(np.float32))
+        I = torch.from_numpy(rng.normal(0, 1, (1, Lt, 128)).astype(np.float32))
+        ref = imfnet_oracle.attention_fusion(state_dict, I, P)
+        out = cuda_model.attention_fusion(I.cuda(), queries_encoder=P.cuda())
+        assert rel_rows(out[0].cpu(), ref[0]) < TOL, (M, Lt)
+
+
+def test_image_encoder_vs_oracle(state_dict, cuda_model):
+    img = synthetic.make_image(160, 120, seed=1)
+    ref = imfnet_oracle.image_encoder(state_dict, img)
+    out = cuda_model.img_encoder(img.cuda()).cpu()
+    assert out.shape == ref.shape == (1, 128, 15, 20)
+    assert float((out - ref).abs().max()) / float(ref.abs().max()) < TOL
+
+
+def test_forward_c1_real_fragment_matches_reference_golden(golden_dir, state_dict, cuda_model):
+    """BASELINE config 0: files/cloud_bin_0.ply @ 5 cm + 160x120 image, output of the reference's own model files."""
+    import imfnet_b200.me as ME
+    g = np.load(os.path.join(golden_dir, "c1_real.npz"))
+    coords = torch.from_numpy(g["coords"])
+    image = torch.from_numpy(g["image"].astype(np.float32))
+    x = ME.SparseTensor(torch.ones((len(coords), 1)), coordinates=coords, device="cuda")
+    cuda_model._plan = None
+    out = cuda_model(x, image.cuda())
+    plan = cuda_model._plan
+    assert out.F.shape == (len(coords), 32) and out.coordinate_map_key == x.coordinate_map_key
+    assert torch.equal(out.C.cpu(), coords)
+    d = out.F.cpu()
+    ref = torch.from_numpy(g["desc"])
+    err = rel_rows(d, ref)
+    # layer-wise diagnosis against the oracle when the end-to-end check fails
+    if not err < TOL:
+        plan.debug = {}
+        cuda_model(x, image.cuda())
+        _, acts = imfnet_oracle.forward(state_dict, coords, torch.ones((len(coords), 1)), image, return_intermediates=True)
+        report = {k: float((plan.debug[k].cpu() - acts[k]).abs().max() / acts[k].abs().max())
+                  for k in ("image", "out_s1", "out_s2", "out_s4", "out_s8", "fused", "out_s4_tr", "out_s2_tr", "out_s1_tr")}
+        plan.debug = None
+        pytest.fail(f"row-wise rel err {err:.3e}; per-layer {report}")
+    assert torch.allclose(torch.linalg.norm(d, dim=1), torch.ones(len(d)), atol=1e-5)
+
+
+def test_forward_intermediates_vs_oracle(golden_dir, state_dict, cuda_model):
+    import imfnet_b200.me as ME
+    g = np.load(os.path.join(golden_dir, "c1_real.npz"))
+    coords = torch.from_numpy(g["coords"])
+    image = torch.from_numpy(g["image"].astype(np.float32))
+    x = ME.SparseTensor(torch.ones((len(coords), 1)), coordinates=coords, device="cuda")
+    cuda_model(x, image.cuda())
+    cuda_model._plan.debug = {}
+    cuda_model(x, image.cuda())
+    dbg, cuda_model._plan.debug = cuda_model._plan.debug, None
+    _, acts = imfnet_oracle.forward(state_dict, coords, torch.ones((len(coords), 1)), image, return_intermediates=True)
+    assert np.array_equal(dbg["levels"][8].cpu().numpy(), g["s8_coords"])
+    assert rel_rows(dbg["fused"].cpu(), torch.from_numpy(g["fused"])) < TOL
+    for k in ("image", "out_s1", "out_s2", "out_s4", "out_s8", "fused", "out_s4_tr", "out_s2_tr", "out_s1_tr"):
+        a, b = dbg[k].cpu(), acts[k]
+        assert float((a - b).abs().max()) / float(b.abs().max()) < TOL, k
+
+
+def test_forward_batch_of_two_matches_reference_golden(golden_dir, cuda_model):
+    import imfnet_b200.me as ME
+    g = np.load(os.path.join(golden_dir, "batch2.npz"))
+    x = ME.SparseTensor(torch.from_numpy(g["feats"]), coordinates=torch.from_numpy(g["coords"]), device="cuda")
+    d = cuda_model(x, torch.from_numpy(g["image"].astype(np.float32)).cuda()).F.cpu()
+    assert rel_rows(d, torch.from_numpy(g["desc"])) < TOL
+
+
+def test_forward_c2_full_size_properties(state_dict, cuda_model):
+    """BASELINE config 1 (50 k voxels + 640x480): unit norms, determinism, row-permutation equivariance,
+    and a 2 000-row spot check against the oracle run on a spatial crop is replaced by: oracle on the whole fragment
+    is affordable once (~1 s), so compare everything."""
+    import imfnet_b200.me as ME
+    coords, feats, image = synthetic.make_config("C2", seed=0)
+    x = ME.SparseTensor(feats, coordinates=coords, device="cuda")
+    d1 = cuda_model(x, image.cuda()).F
+    d2 = cuda_model(ME.SparseTensor(feats, coordinates=coords, device="cuda"), image.cuda()).F
+    assert torch.equal(d1, d2), "forward must be deterministic"
+    assert torch.allclose(torch.linalg.norm(d1, dim=1), torch.ones(len(d1), device="cuda"), atol=1e-5)
+    perm = torch.from_numpy(np.random.default_rng(0).permutation(len(coords)))
+    dp = cuda_model(ME.SparseTensor(feats[perm], coordinates=coords[perm], device="cuda"), image.cuda()).F
+    assert rel_rows(dp.cpu(), d1.cpu()[perm]) < 1e-5, "descriptors must not depend on the input row order"
+    ref = imfnet_oracle.forward(state_dict, coords, feats, image)
+    assert rel_rows(d1.cpu(), ref) < TOL
+
+
+def test_extract_features_pipeline(golden_dir, state_dict, cuda_model):
+    """Caller-level API (util/misc.py:21-104): raw points in, (kept xyz, descriptors) out, GPU voxelisation inside."""
+    from imfnet_b200 import extract_features
+    g = np.load(os.path.join(golden_dir, "quantize_prefix.npz"))
+    xyz = g["xyz"].astype(np.float64)
+    image = synthetic.make_image(160, 120, seed=2).numpy()
+    pts, F = extract_features(cuda_model, xyz, voxel_size=0.05, device="cuda:0", skip_check=True, image=image)
+    from oracle import sparse_ops
+    q = np.floor(xyz / 0.05)
+    idx = sparse_ops.unique_first(q.astype(np.int32))
+    assert np.array_equal(pts, xyz[idx])
+    coords = torch.from_numpy(np.concatenate([np.zeros((len(idx), 1)), q[idx]], 1).astype(np.int32))
+    ref = imfnet_oracle.forward(state_dict, coords, torch.ones((len(idx), 1)), torch.from_numpy(image))
+    assert rel_rows(F.cpu(), ref) < TOL
