@@ -66,11 +66,11 @@ def test_conv_fused_epilogue_and_strided_operands(frag):
     R = torch.randn(n, 80, generator=g)
     onbr = ocm.table(1, 1, 3, False)
     ref = torch.relu(sparse_ops.conv_forward(wide[:, 64:96].contiguous(), W, onbr) * scale + shift + R[:, 16:80])
-    wide_d, R_d = wide.cuda(), R.cuda()
+    wide_d, R_d, W_d, sc_d, sh_d = wide.cuda(), R.cuda(), W.cuda(), scale.cuda(), shift.cuda()   # keep device copies alive
     out = torch.zeros(n, 128, device="cuda")
     L = _lib.lib()
-    _lib.check(L.imf_sparse_conv_fwd(wide_d.data_ptr() + 64 * 4, 96, W.cuda().data_ptr(), cm.table(1, 1, 3, False).data_ptr(),
-                                     None, n, 27, 32, 64, scale.cuda().data_ptr(), shift.cuda().data_ptr(),
+    _lib.check(L.imf_sparse_conv_fwd(wide_d.data_ptr() + 64 * 4, 96, W_d.data_ptr(), cm.table(1, 1, 3, False).data_ptr(),
+                                     None, n, 27, 32, 64, sc_d.data_ptr(), sh_d.data_ptr(),
                                      R_d.data_ptr() + 16 * 4, 80, 1, out.data_ptr() + 64 * 4, 128, _lib.cur_stream()))
     torch.cuda.synchronize()
     close(out[:, 64:].cpu(), ref)
@@ -89,9 +89,10 @@ def test_first_conv_matches_oracle(frag, cin, cout, K):
     L = _lib.lib()
     lvl = cm.level(1)
     Y = torch.empty(n, cout, device="cuda")
-    _lib.check(L.imf_conv_first_fwd(X.cuda().data_ptr(), cin, cin, W.cuda().data_ptr(), lvl.coords.data_ptr(), None, n,
-                                    lvl.table.data_ptr(), lvl.capacity, K, 1, cout, scale.cuda().data_ptr(),
-                                    shift.cuda().data_ptr(), 0, Y.data_ptr(), cout, _lib.cur_stream()))
+    X_d, W_d, sc_d, sh_d = X.cuda(), W.cuda(), scale.cuda(), shift.cuda()      # keep device copies alive across the call
+    _lib.check(L.imf_conv_first_fwd(X_d.data_ptr(), cin, cin, W_d.data_ptr(), lvl.coords.data_ptr(), None, n,
+                                    lvl.table.data_ptr(), lvl.capacity, K, 1, cout, sc_d.data_ptr(),
+                                    sh_d.data_ptr(), 0, Y.data_ptr(), cout, _lib.cur_stream()))
     torch.cuda.synchronize()
     close(Y.cpu(), ref)
 
@@ -107,8 +108,9 @@ def test_pointwise_tail_matches_oracle(normalize):
         ref = ref / torch.norm(ref, p=2, dim=1, keepdim=True)
     L = _lib.lib()
     Y = torch.empty(n, 32, device="cuda")
-    _lib.check(L.imf_pointwise_tail_fwd(X.cuda().data_ptr(), 96, 96, W1.cuda().data_ptr(), 64, W2.cuda().data_ptr(),
-                                        b2.cuda().data_ptr(), 32, None, n, int(normalize), Y.data_ptr(), 32, _lib.cur_stream()))
+    X_d, W1_d, W2_d, b2_d = X.cuda(), W1.cuda(), W2.cuda(), b2.cuda()          # keep device copies alive across the call
+    _lib.check(L.imf_pointwise_tail_fwd(X_d.data_ptr(), 96, 96, W1_d.data_ptr(), 64, W2_d.data_ptr(),
+                                        b2_d.data_ptr(), 32, None, n, int(normalize), Y.data_ptr(), 32, _lib.cur_stream()))
     torch.cuda.synchronize()
     close(Y.cpu(), ref)
 

@@ -39,7 +39,7 @@ def test_attention_ragged_sizes_vs_oracle(state_dict, cuda_model):
 def test_image_encoder_vs_oracle(state_dict, cuda_model):
     img = synthetic.make_image(160, 120, seed=1)
     ref = imfnet_oracle.image_encoder(state_dict, img)
-    out = cuda_model.img_encoder(img.cuda()).cpu()
+    out = cuda_model.img_encoder(img.cuda()).detach().cpu()
     assert out.shape == ref.shape == (1, 128, 15, 20)
     assert float((out - ref).abs().max()) / float(ref.abs().max()) < TOL
 
