@@ -102,6 +102,18 @@ int imf_pointwise_tail_fwd(const float* X, int32_t ldx, int32_t C0, const float*
 int imf_linear_fwd(const float* X, int32_t ldx, const float* W_kn, const float* bias, int32_t M, int32_t Cin, int32_t Cout,
                    float* Y, int32_t ldy, imf_stream_t stream);
 
+/* ---- dense GEMM on the tcgen05 tensor cores (3xTF32, fp32-class accuracy): every nn.Linear / einsum of
+ *      model/attention_fusion.py:57-59,79-95 --------------------------------------------------------- */
+
+/* C[M,N] = alpha * A[M,K] . B[N,K]^T (+ bias[n]) (+ R[m,n]); A and B row-major (K contiguous).
+ * geglu != 0: B holds 2N rows (value rows then gate rows, bias likewise) and C[m,n] = (.)_n * gelu((.)_{n+N}).
+ * workspace (optional, imf_tc_gemm_workspace_bytes) lets small tile grids split K over more SMs.
+ * err (optional device int) receives a non-zero code if an in-kernel barrier wait times out (the kernel traps). */
+size_t imf_tc_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K);
+int imf_tc_gemm(const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc, int32_t M, int32_t N, int32_t K,
+                float alpha, const float* bias, const float* R, int32_t ldr, int32_t geglu, void* workspace,
+                size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+
 /* ---- attention fusion: AttentionFusion.forward (model/attention_fusion.py:132-154), depth 0, 1 head ---- */
 typedef struct {
   const float *ln_q_w, *ln_q_b; /* cross_attend_blocks.0.norm            [latent]                   */
