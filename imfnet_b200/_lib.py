@@ -33,11 +33,16 @@ SIGNATURES = {
     "imf_quantize_points": (C.c_int, [_p, _i32, _f64, _i32, _p, _p]),
     "imf_batch_segments": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
     "imf_sparse_conv_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _i32, _p]),
+    "imf_sparse_conv_tc_packed_bytes": (_sz, [_i32, _i32, _i32]),
+    "imf_sparse_conv_tc_pack": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
+    "imf_sparse_conv_tc_workspace_bytes": (_sz, [_i32, _i32]),
+    "imf_sparse_conv_tc_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _i32, _p, _sz, _p, _p]),
     "imf_conv_first_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _p]),
     "imf_pointwise_tail_fwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _i32, _p]),
     "imf_linear_fwd": (C.c_int, [_p, _i32, _p, _p, _i32, _i32, _i32, _p, _i32, _p]),
     "imf_tc_gemm_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "imf_tc_gemm": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _i32, _i32, _i32, _f32, _p, _p, _i32, _i32, _p, _sz, _p, _p]),
+    "imf_attention_kv_bytes": (_sz, [_i32, _i32]),
     "imf_attention_kv_workspace_bytes": (_sz, [_i32, _i32]),
     "imf_attention_kv": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _p, _sz, _p]),
     "imf_attention_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),

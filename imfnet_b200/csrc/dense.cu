@@ -214,37 +214,49 @@ struct imf_attn_weights_t {
   int32_t latent, dim, inner;
 };
 
+static inline int round4(int v) { return (v + 3) / 4 * 4; }
+
+// Layout of the projected context of one image ("kv" buffers): K [L, inner] row-major, then V^T [inner, Lp] (Lp = L rounded
+// up to 4) so that both attention GEMMs read K-major operands.
+extern "C" size_t imf_attention_kv_bytes(int32_t L, int32_t inner) {
+  return r256((size_t)L * inner * 4) + r256((size_t)inner * round4(L) * 4);
+}
 extern "C" size_t imf_attention_kv_workspace_bytes(int32_t L, int32_t dim) { return r256((size_t)L * dim * 4); }
 
-// kv[L, 2*inner] = LN_c(tokens) . Wkv^T; tokens are channel-major [dim][L] (channel_major != 0) or row-major [L][dim].
+// kv = { K = LN_c(tokens) . Wk^T,  V^T = Wv . LN_c(tokens)^T }; tokens are channel-major [dim][L] (channel_major != 0)
+// or row-major [L][dim].  (to_kv.weight rows [0,inner) are Wk, rows [inner,2*inner) are Wv: attention_fusion.py:81-82.)
 extern "C" int imf_attention_kv(const imf_attn_weights_t* w, const float* tokens, int32_t L, int32_t channel_major, float* kv,
                                 void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  const float* img_chw = tokens;
-  IMF_CHECK_ARG(w != nullptr && L >= 0 && w->dim == 128);
+  IMF_CHECK_ARG(w != nullptr && L >= 0 && w->dim % 32 == 0 && w->dim <= 1024 && (!channel_major || w->dim == 128));
   if (L == 0) return IMF_OK;
-  IMF_CHECK_ARG(img_chw != nullptr && kv != nullptr && workspace != nullptr);
+  IMF_CHECK_ARG(tokens != nullptr && kv != nullptr && workspace != nullptr);
   IMF_CHECK_ARG(workspace_bytes >= imf_attention_kv_workspace_bytes(L, w->dim));
   float* cn = reinterpret_cast<float*>(workspace);
   if (channel_major)
-    k_layernorm_tokens_chw<<<(L + 31) / 32, 256, 0, stream>>>(img_chw, L, w->ln_c_w, w->ln_c_b, 1e-5f, cn);
+    k_layernorm_tokens_chw<<<(L + 31) / 32, 256, 0, stream>>>(tokens, L, w->ln_c_w, w->ln_c_b, 1e-5f, cn);
   else
     k_layernorm_rows<<<(L + 7) / 8, 256, 0, stream>>>(tokens, w->dim, L, w->dim, w->ln_c_w, w->ln_c_b, 1e-5f, cn, w->dim);
   IMF_CHECK_LAUNCH();
-  return sgemm<false, false>(cn, w->dim, w->wkv, w->dim, kv, 2 * w->inner, L, 2 * w->inner, w->dim, 1.f, nullptr, nullptr, 0,
-                             stream);
+  const int inner = w->inner, dim = w->dim, Lp = round4(L);
+  float* Kmat = kv;
+  float* Vt = reinterpret_cast<float*>(reinterpret_cast<char*>(kv) + r256((size_t)L * inner * 4));
+  int rc;
+  if ((rc = imf_tc_gemm(cn, dim, w->wkv, dim, Kmat, inner, L, inner, dim, 1.f, nullptr, nullptr, 0, 0, nullptr, 0, nullptr, stream))) return rc;
+  return imf_tc_gemm(w->wkv + (size_t)inner * dim, dim, cn, dim, Vt, Lp, inner, L, dim, 1.f, nullptr, nullptr, 0, 0, nullptr, 0, nullptr, stream);
 }
 
 extern "C" size_t imf_attention_workspace_bytes(int32_t M, int32_t L, int32_t latent, int32_t inner) {
-  const size_t Lp = ((size_t)L + 3) / 4 * 4;
+  const size_t Lp = (size_t)round4(L);
   return r256((size_t)M * latent * 4)      // xn / reused for LN before FFN
          + r256((size_t)M * inner * 4)     // q
          + r256((size_t)M * Lp * 4)        // scores
          + r256((size_t)M * inner * 4)     // attention output
          + r256((size_t)M * latent * 4)    // x after attention residual
-         + r256((size_t)M * latent * 4 * 4);  // GEGLU hidden [M, 4*latent]
+         + r256((size_t)M * latent * 4 * 4)   // GEGLU hidden [M, 4*latent]
+         + r256(imf_tc_gemm_workspace_bytes(M, latent, 0));   // split-K partials (largest N used with split-K = latent)
 }
 
-// out[M, latent] = AttentionFusion(data = image tokens (through kv), queries_encoder = P[M, latent]).
+// out[M, latent] = cross-attention + GEGLU feed-forward of M point tokens P[M, latent] against kv (imf_attention_kv).
 extern "C" int imf_attention_fusion_fwd(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const float* kv,
                                         int32_t L, float* out, int32_t ldo, void* workspace, size_t workspace_bytes,
                                         cudaStream_t stream) {
@@ -254,33 +266,38 @@ extern "C" int imf_attention_fusion_fwd(const imf_attn_weights_t* w, const float
   IMF_CHECK_ARG(P != nullptr && kv != nullptr && out != nullptr && workspace != nullptr && ldp >= w->latent && ldo >= w->latent);
   IMF_CHECK_ARG(workspace_bytes >= imf_attention_workspace_bytes(M, L, w->latent, w->inner));
   const int latent = w->latent, inner = w->inner;
-  const int Lp = (L + 3) / 4 * 4;
+  const int Lp = round4(L);
   char* ws = reinterpret_cast<char*>(workspace);
   float* xn = reinterpret_cast<float*>(ws);  ws += r256((size_t)M * latent * 4);
   float* q = reinterpret_cast<float*>(ws);   ws += r256((size_t)M * inner * 4);
   float* S = reinterpret_cast<float*>(ws);   ws += r256((size_t)M * Lp * 4);
   float* o = reinterpret_cast<float*>(ws);   ws += r256((size_t)M * inner * 4);
   float* x1 = reinterpret_cast<float*>(ws);  ws += r256((size_t)M * latent * 4);
-  float* hid = reinterpret_cast<float*>(ws);
+  float* hid = reinterpret_cast<float*>(ws); ws += r256((size_t)M * latent * 4 * 4);
+  void* gws = ws;
+  const size_t gws_bytes = imf_tc_gemm_workspace_bytes(M, latent, 0);
+  const float* Kmat = kv;
+  const float* Vt = reinterpret_cast<const float*>(reinterpret_cast<const char*>(kv) + r256((size_t)L * inner * 4));
   const float sm_scale = 1.0f / sqrtf((float)inner);
   int rc;
   k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(P, ldp, M, latent, w->ln_q_w, w->ln_q_b, 1e-5f, xn, latent);
   IMF_CHECK_LAUNCH();
-  if ((rc = sgemm<false, false>(xn, latent, w->wq, latent, q, inner, M, inner, latent, 1.f, nullptr, nullptr, 0, stream))) return rc;
-  // S = (q . k^T) * scale ; k = kv[:, :inner]
-  if ((rc = sgemm<false, false>(q, inner, kv, 2 * inner, S, Lp, M, L, inner, sm_scale, nullptr, nullptr, 0, stream))) return rc;
+  // q = LN(P) . Wq^T
+  if ((rc = imf_tc_gemm(xn, latent, w->wq, latent, q, inner, M, inner, latent, 1.f, nullptr, nullptr, 0, 0, gws, gws_bytes, nullptr, stream))) return rc;
+  // S = (q . K^T) * scale
+  if ((rc = imf_tc_gemm(q, inner, Kmat, inner, S, Lp, M, L, inner, sm_scale, nullptr, nullptr, 0, 0, nullptr, 0, nullptr, stream))) return rc;
   k_softmax_rows<<<M, 256, 0, stream>>>(S, Lp, M, L);
   IMF_CHECK_LAUNCH();
-  // o = A . v ; v = kv[:, inner:]
-  if ((rc = sgemm<true, false>(S, Lp, kv + inner, 2 * inner, o, inner, M, inner, L, 1.f, nullptr, nullptr, 0, stream))) return rc;
+  // o = A . V   (as A . (V^T)^T, split over the L tokens)
+  if ((rc = imf_tc_gemm(S, Lp, Vt, Lp, o, inner, M, inner, L, 1.f, nullptr, nullptr, 0, 0, gws, gws_bytes, nullptr, stream))) return rc;
   // x1 = o . Wo^T + bo + P
-  if ((rc = sgemm<false, false>(o, inner, w->wo, inner, x1, latent, M, latent, inner, 1.f, w->bo, P, ldp, stream))) return rc;
+  if ((rc = imf_tc_gemm(o, inner, w->wo, inner, x1, latent, M, latent, inner, 1.f, w->bo, P, ldp, 0, gws, gws_bytes, nullptr, stream))) return rc;
   k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(x1, latent, M, latent, w->ln_f_w, w->ln_f_b, 1e-5f, xn, latent);
   IMF_CHECK_LAUNCH();
-  // hid = geglu(xn . W1^T + b1)   [M, 4*latent]
-  if ((rc = sgemm<false, true>(xn, latent, w->w1, latent, hid, 4 * latent, M, 4 * latent, latent, 1.f, w->b1, nullptr, 0, stream))) return rc;
+  // hid = geglu(LN(x1) . W1^T + b1)   [M, 4*latent]
+  if ((rc = imf_tc_gemm(xn, latent, w->w1, latent, hid, 4 * latent, M, 4 * latent, latent, 1.f, w->b1, nullptr, 0, 1, nullptr, 0, nullptr, stream))) return rc;
   // out = hid . W2^T + b2 + x1
-  if ((rc = sgemm<false, false>(hid, 4 * latent, w->w2, 4 * latent, out, ldo, M, latent, 4 * latent, 1.f, w->b2, x1, latent, stream))) return rc;
+  if ((rc = imf_tc_gemm(hid, 4 * latent, w->w2, 4 * latent, out, ldo, M, latent, 4 * latent, 1.f, w->b2, x1, latent, 0, gws, gws_bytes, nullptr, stream))) return rc;
   return IMF_OK;
 }
 

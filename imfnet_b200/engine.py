@@ -25,6 +25,7 @@ class FusedPlan:
         self.CH, self.TR = model.CHANNELS, model.TR_CHANNELS
         self._key = None
         self.debug = None      # set to a dict to capture intermediate activations (tests only)
+        self.conv_impl = "tc"  # "tc" = tcgen05 3xTF32 implicit GEMM; "simt" = fp32 SIMT tier
         self.pack()
 
     # -- weights -------------------------------------------------------------------------------
@@ -44,15 +45,37 @@ class FusedPlan:
             self.bn[b + ".norm1"] = blk.norm1.folded()
             self.bn[b + ".norm2"] = blk.norm2.folded()
         self.final_bias = None if m.final.bias is None else m.final.bias.detach().reshape(-1).contiguous()
+        # tensor-core weight slabs (hi/lo TF32 split, swizzled) for every 3x3x3 convolution
+        L = _lib.lib()
+        self.packed = {}
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream().cuda_stream
+            for name, mod in m.named_modules():
+                if hasattr(mod, "kernel") and getattr(mod, "kernel_volume", 1) == 27 and mod.in_channels % 32 == 0:
+                    nbytes = int(L.imf_sparse_conv_tc_packed_bytes(27, mod.in_channels, mod.out_channels))
+                    buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                    _lib.check(L.imf_sparse_conv_tc_pack(mod.kernel.detach().contiguous().data_ptr(), 27, mod.in_channels,
+                                                         mod.out_channels, buf.data_ptr(), s))
+                    self.packed[id(mod)] = buf
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._key = self._weights_key()
 
     # -- launch helpers ------------------------------------------------------------------------
     def _conv(self, L, X, ldx, conv, nbr, n_out, bn, R, ldr, relu, Y, ldy, stream):
         scale, shift = (None, None) if bn is None else self.bn[bn]
-        W = conv.kernel.detach()
-        _lib.check(L.imf_sparse_conv_fwd(X, ldx, W.data_ptr(), nbr.data_ptr(), None, n_out, conv.kernel_volume,
-                                         conv.in_channels, conv.out_channels, _lib.ptr(scale), _lib.ptr(shift), R, ldr,
-                                         1 if relu else 0, Y, ldy, stream))
+        if self.conv_impl == "simt":          # fp32 SIMT tier (kept for A/B measurements)
+            _lib.check(L.imf_sparse_conv_fwd(X, ldx, conv.kernel.data_ptr(), nbr.data_ptr(), None, n_out, conv.kernel_volume,
+                                             conv.in_channels, conv.out_channels, _lib.ptr(scale), _lib.ptr(shift), R, ldr,
+                                             1 if relu else 0, Y, ldy, stream))
+            return
+        ws, ws_bytes = None, 0
+        if n_out < 12800:                     # few row tiles: let the kernel split a tile's offsets over several CTAs
+            ws_bytes = int(L.imf_sparse_conv_tc_workspace_bytes(n_out, conv.out_channels))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        _lib.check(L.imf_sparse_conv_tc_fwd(X, ldx, self.packed[id(conv)].data_ptr(), nbr.data_ptr(), None, n_out,
+                                            conv.kernel_volume, conv.in_channels, conv.out_channels, _lib.ptr(scale),
+                                            _lib.ptr(shift), R, ldr, 1 if relu else 0, Y, ldy, _lib.ptr(ws), ws_bytes,
+                                            self.err.data_ptr(), stream))
 
     def _block(self, L, name, X, ldx, nbr, n, C, tmp, Y, ldy, stream):
         """BasicBlockBN (model/residual_block.py:37-53): X -> tmp = relu(bn1(conv1 X)) -> Y = relu(bn2(conv2 tmp) + X)."""

@@ -81,12 +81,13 @@ class AttentionFusion(nn.Module):
 
     # -- kernels ---------------------------------------------------------------------------------
     def project_context(self, tokens: torch.Tensor, channel_major: bool) -> torch.Tensor:
-        """kv [L, 2*inner] of one image: tokens [dim, L] (channel_major) or [L, dim]."""
+        """Projected context of one image (opaque kv buffer: K then V^T): tokens [dim, L] (channel_major) or [L, dim]."""
         L = _lib.lib()
         w = self.packed()
         tokens = tokens.contiguous()
         n_tok = tokens.shape[1] if channel_major else tokens.shape[0]
-        kv = torch.empty((n_tok, 2 * self.inner), dtype=torch.float32, device=tokens.device)
+        kv = torch.empty(int(L.imf_attention_kv_bytes(n_tok, self.inner)), dtype=torch.uint8, device=tokens.device)
+        kv.n_tokens = n_tok
         ws_bytes = int(L.imf_attention_kv_workspace_bytes(n_tok, self.dim))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=tokens.device)
         with torch.cuda.device(tokens.device):
@@ -95,10 +96,10 @@ class AttentionFusion(nn.Module):
         return kv
 
     def fuse(self, queries: torch.Tensor, kv: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-        """queries [M, latent] (row stride = queries.stride(0)) x kv [L, 2*inner] -> [M, latent]."""
+        """queries [M, latent] (row stride = queries.stride(0)) x kv (from project_context) -> [M, latent]."""
         L = _lib.lib()
         w = self.packed()
-        M, n_tok = queries.shape[0], kv.shape[0]
+        M, n_tok = queries.shape[0], kv.n_tokens
         if queries.stride(1) != 1:
             queries = queries.contiguous()
         if out is None:

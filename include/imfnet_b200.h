@@ -85,6 +85,19 @@ int imf_sparse_conv_fwd(const float* X, int32_t ldx, const float* W, const int32
                         const float* shift, const float* residual, int32_t ldr, int32_t relu, float* Y, int32_t ldy,
                         imf_stream_t stream);
 
+/* Tensor-core path of the same operation (tcgen05.mma kind::tf32 with a 3-way hi/lo split = fp32-class accuracy,
+ * accumulators in TMEM, weights staged by bulk/TMA copies).  Weights are packed once with imf_sparse_conv_tc_pack
+ * (hi/lo split, 128-byte-swizzled K-major slabs per (offset, 32-channel chunk)).  Cout in {32,64,128,256}.
+ * workspace (optional, imf_sparse_conv_tc_workspace_bytes) lets the small deep levels split a tile's offsets over
+ * several CTAs; err (optional device int) gets a non-zero code if an in-kernel barrier wait times out. */
+size_t imf_sparse_conv_tc_packed_bytes(int32_t kernel_volume, int32_t Cin, int32_t Cout);
+int imf_sparse_conv_tc_pack(const float* W, int32_t kernel_volume, int32_t Cin, int32_t Cout, void* packed, imf_stream_t stream);
+size_t imf_sparse_conv_tc_workspace_bytes(int32_t n_out_max, int32_t Cout);
+int imf_sparse_conv_tc_fwd(const float* X, int32_t ldx, const void* packed, const int32_t* nbr, const int32_t* n_out_dev,
+                           int32_t n_out_max, int32_t kernel_volume, int32_t Cin, int32_t Cout, const float* scale,
+                           const float* shift, const float* residual, int32_t ldr, int32_t relu, float* Y, int32_t ldy,
+                           void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+
 /* First layer (conv1, model/resunet.py:42-49,168): K in {1,3,5}, Cin <= 8, Cout in {32,64,128}; neighbours are
  * probed from the hash table of the same coordinate set, no neighbour table needed. */
 int imf_conv_first_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords, const int32_t* n_dev,
@@ -127,9 +140,10 @@ typedef struct {
   int32_t latent, dim, inner;
 } imf_attn_weights_t; /* HOST struct of DEVICE pointers */
 
-/* kv[L, 2*inner] = LayerNorm_c(tokens) . Wkv^T for one image.  channel_major != 0: tokens are the encoder's
+/* kv = { K = LayerNorm_c(tokens) . Wk^T, V^T } for one image (opaque buffer of imf_attention_kv_bytes).  channel_major != 0: tokens are the encoder's
  * feature map [dim][L] (NCHW, L = H'*W'), i.e. the view/permute of model/resunet.py:259-261 is folded in;
  * channel_major == 0: tokens are row-major [L][dim] (AttentionFusion.forward's `data` argument). */
+size_t imf_attention_kv_bytes(int32_t L, int32_t inner); /* size of a kv buffer: K [L,inner] then V^T [inner, roundup4(L)] */
 size_t imf_attention_kv_workspace_bytes(int32_t L, int32_t dim);
 int imf_attention_kv(const imf_attn_weights_t* w, const float* tokens, int32_t L, int32_t channel_major, float* kv,
                      void* workspace, size_t workspace_bytes, imf_stream_t stream);
