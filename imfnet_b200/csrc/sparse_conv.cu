@@ -190,8 +190,8 @@ int launch_conv(const float* X, int ldx, const float* W, const int* nbr, const i
 // A warp owns one output voxel at a time: lanes probe the hash table for the K^3 neighbours (no neighbour table is
 // materialised -- 125 int32 per voxel would be 25 MB at 50 k voxels), then lane <-> output channel accumulates
 // the present offsets in ascending k.  Weights (K^3*Cin*Cout fp32, 16 KB for 125x1x32) sit in shared memory.
-template <int TN>
-__global__ void __launch_bounds__(256) k_conv_first(const float* __restrict__ X, int ldx, int Cin, const float* __restrict__ W,
+template <int TN, int CIN>
+__global__ void __launch_bounds__(256) k_conv_first(const float* __restrict__ X, int ldx, const float* __restrict__ W,
                                                     const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max,
                                                     const ImfSlot* __restrict__ table, unsigned long long mask, int K,
                                                     int tstride, const float* __restrict__ scale,
@@ -206,23 +206,40 @@ __global__ void __launch_bounds__(256) k_conv_first(const float* __restrict__ X,
   if (n_ptr) { int v = *n_ptr; n = v < n_max ? v : n_max; }
   const int row_begin = blockIdx.x * rows_per_cta;
   if (row_begin >= n) return;
-  for (int i = tid; i < K3 * Cin * Cout; i += 256) W_s[i] = __ldg(W + i);
+  for (int i = tid; i < K3 * CIN * Cout; i += 256) W_s[i] = __ldg(W + i);
   __syncthreads();
   const int row_end = min(n, row_begin + rows_per_cta);
   const int h = K / 2;
+  // per-lane offsets of the (up to) 4 probe rounds, computed once
+  int ox[4], oy[4], oz[4];
+#pragma unroll
+  for (int rd = 0; rd < 4; ++rd) {
+    const int k = rd * 32 + lane;
+    ox[rd] = (k % K - h) * tstride;
+    oy[rd] = ((k / K) % K - h) * tstride;
+    oz[rd] = (k / (K * K) - h) * tstride;
+  }
   for (int row = row_begin + warp; row < row_end; row += 8) {
     const int4 c = __ldg(coords + row);
     int found[4];
+    float xv[4][CIN];
+    // phase 1: all probes and all feature loads of the neighbourhood are independent -> issued back to back
 #pragma unroll
     for (int rd = 0; rd < 4; ++rd) {
       const int k = rd * 32 + lane;
       int r = -1;
       if (k < K3) {
-        const int x = c.y + (k % K - h) * tstride, y = c.z + ((k / K) % K - h) * tstride, z = c.w + (k / (K * K) - h) * tstride;
+        const int x = c.y + ox[rd], y = c.z + oy[rd], z = c.w + oz[rd];
         if (imf_coord_in_range(c.x, x, y, z)) r = imf_table_lookup(table, mask, imf_pack_key(c.x, x, y, z));
       }
       found[rd] = r;
     }
+#pragma unroll
+    for (int rd = 0; rd < 4; ++rd) {
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) xv[rd][ci] = (found[rd] >= 0) ? __ldg(X + (size_t)found[rd] * ldx + ci) : 0.f;
+    }
+    // phase 2: lane <-> output channel; present offsets accumulated in ascending k
     float acc[TN];
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[j] = 0.f;
@@ -232,12 +249,10 @@ __global__ void __launch_bounds__(256) k_conv_first(const float* __restrict__ X,
       while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
-        const int src = __shfl_sync(0xffffffffu, found[rd], b);
-        const int k = rd * 32 + b;
-        const float* xr = X + (size_t)src * ldx;
-        const float* wr = W_s + (size_t)k * Cin * Cout + lane;
-        for (int ci = 0; ci < Cin; ++ci) {
-          const float x = __ldg(xr + ci);
+        const float* wr = W_s + (size_t)(rd * 32 + b) * CIN * Cout + lane;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float x = __shfl_sync(0xffffffffu, xv[rd][ci], b);
 #pragma unroll
           for (int j = 0; j < TN; ++j) acc[j] = fmaf(x, wr[ci * Cout + j * 32], acc[j]);
         }
@@ -384,32 +399,47 @@ extern "C" int imf_sparse_conv_fwd(const float* X, int32_t ldx, const float* W, 
 #undef IMF_GO
 }
 
+template <int TN, int CIN>
+static int launch_first(const float* X, int ldx, const float* W, const int32_t* coords, const int32_t* n_dev, int n_max, const void* table,
+                        long long capacity, int K, int tstride, const float* scale, const float* shift, int relu, float* Y, int ldy,
+                        cudaStream_t stream) {
+  const int K3 = K * K * K;
+  const size_t smem = (size_t)K3 * CIN * 32 * TN * sizeof(float);
+  IMF_CHECK_ARG(smem <= 200 * 1024);
+  const int rows_per_cta = 64;
+  const int grid = (n_max + rows_per_cta - 1) / rows_per_cta;
+  IMF_CHECK_CUDA(cudaFuncSetAttribute(k_conv_first<TN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  k_conv_first<TN, CIN><<<grid, 256, smem, stream>>>(X, ldx, W, reinterpret_cast<const int4*>(coords), n_dev, n_max,
+                                                     reinterpret_cast<const ImfSlot*>(table), (unsigned long long)capacity - 1, K, tstride,
+                                                     scale, shift, relu, Y, ldy, rows_per_cta);
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
+}
+
 extern "C" int imf_conv_first_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords,
                                   const int32_t* n_dev, int32_t n_max, const void* table, long long capacity,
                                   int32_t kernel_size, int32_t tensor_stride, int32_t Cout, const float* scale,
                                   const float* shift, int32_t relu, float* Y, int32_t ldy, cudaStream_t stream) {
   IMF_CHECK_ARG(n_max >= 0 && kernel_size >= 1 && (kernel_size & 1) && kernel_size <= 5);
-  IMF_CHECK_ARG(Cin >= 1 && Cin <= 8 && (Cout == 32 || Cout == 64 || Cout == 128));
+  IMF_CHECK_ARG((Cin == 1 || Cin == 3 || Cin == 6) && (Cout == 32 || Cout == 64 || Cout == 128));
   IMF_CHECK_ARG((scale == nullptr) == (shift == nullptr) && ldx >= Cin && ldy >= Cout);
   IMF_CHECK_ARG(capacity > 0 && (capacity & (capacity - 1)) == 0);
   if (n_max == 0) return IMF_OK;
   IMF_CHECK_ARG(X != nullptr && W != nullptr && coords != nullptr && table != nullptr && Y != nullptr);
-  const int K3 = kernel_size * kernel_size * kernel_size;
-  const size_t smem = (size_t)K3 * Cin * Cout * sizeof(float);
-  IMF_CHECK_ARG(smem <= 200 * 1024);
-  const int rows_per_cta = 64;
-  const int grid = (n_max + rows_per_cta - 1) / rows_per_cta;
-#define IMF_GO(TN)                                                                                                      \
-  do {                                                                                                                  \
-    IMF_CHECK_CUDA(cudaFuncSetAttribute(k_conv_first<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));    \
-    k_conv_first<TN><<<grid, 256, smem, stream>>>(X, ldx, Cin, W, reinterpret_cast<const int4*>(coords), n_dev, n_max,  \
-                                                  reinterpret_cast<const ImfSlot*>(table), (unsigned long long)capacity - 1, \
-                                                  kernel_size, tensor_stride, scale, shift, relu, Y, ldy, rows_per_cta); \
+#define IMF_GO(TN, CIN)                                                                                                  \
+  return launch_first<TN, CIN>(X, ldx, W, coords, n_dev, n_max, table, capacity, kernel_size, tensor_stride, scale, shift, relu, Y, \
+                               ldy, stream)
+#define IMF_GO_C(TN)            \
+  do {                          \
+    if (Cin == 1) IMF_GO(TN, 1); \
+    if (Cin == 3) IMF_GO(TN, 3); \
+    IMF_GO(TN, 6);              \
   } while (0)
-  if (Cout == 32) IMF_GO(1); else if (Cout == 64) IMF_GO(2); else IMF_GO(4);
+  if (Cout == 32) IMF_GO_C(1);
+  if (Cout == 64) IMF_GO_C(2);
+  IMF_GO_C(4);
+#undef IMF_GO_C
 #undef IMF_GO
-  IMF_CHECK_LAUNCH();
-  return IMF_OK;
 }
 
 extern "C" int imf_pointwise_tail_fwd(const float* X, int32_t ldx, int32_t C0, const float* W1, int32_t C1, const float* W2,

@@ -13,6 +13,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
+from .arena import Arena
 
 
 class FusedPlan:
@@ -26,6 +27,7 @@ class FusedPlan:
         self._key = None
         self.debug = None      # set to a dict to capture intermediate activations (tests only)
         self.conv_impl = "tc"  # "tc" = tcgen05 3xTF32 implicit GEMM; "simt" = fp32 SIMT tier
+        self.arena = Arena(self.device)
         self.pack()
 
     # -- weights -------------------------------------------------------------------------------
@@ -71,7 +73,7 @@ class FusedPlan:
         ws, ws_bytes = None, 0
         if n_out < 12800:                     # few row tiles: let the kernel split a tile's offsets over several CTAs
             ws_bytes = int(L.imf_sparse_conv_tc_workspace_bytes(n_out, conv.out_channels))
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+            ws = self.arena.take(ws_bytes)
         _lib.check(L.imf_sparse_conv_tc_fwd(X, ldx, self.packed[id(conv)].data_ptr(), nbr.data_ptr(), None, n_out,
                                             conv.kernel_volume, conv.in_channels, conv.out_channels, _lib.ptr(scale),
                                             _lib.ptr(shift), R, ldr, 1 if relu else 0, Y, ldy, _lib.ptr(ws), ws_bytes,
@@ -124,8 +126,8 @@ class FusedPlan:
             dn = {(1, 2): cm.table(1, 2, 3, False), (2, 4): cm.table(2, 4, 3, False), (4, 8): cm.table(4, 8, 3, False)}
             up = {(8, 4): cm.table(8, 4, 3, True), (4, 2): cm.table(4, 2, 3, True), (2, 1): cm.table(2, 1, 3, True)}
 
-            def buf(n, c):
-                return torch.empty((max(n, 1), c), dtype=torch.float32, device=dev)
+            self.arena.reset()
+            buf = self.arena.floats
 
             # concat buffers: [decoder half | encoder skip half]
             cat1, cat2, cat4 = buf(n1, TR[2] + CH[1]), buf(n2, TR[3] + CH[2]), buf(n4, TR[4] + CH[3])
@@ -160,7 +162,7 @@ class FusedPlan:
             for b in range(B):
                 lo, hi = seg[b], seg[b + 1]
                 if hi > lo:
-                    m.attention_fusion.fuse(d2[lo:hi], kvs[b], out=fused[lo:hi])
+                    m.attention_fusion.fuse(d2[lo:hi], kvs[b], out=fused[lo:hi], arena=self.arena)
             if seg[B] != n8:
                 raise ValueError("coordinates reference more batch items than images were given")
             if self.debug is not None:

@@ -79,8 +79,9 @@ class _ConvBase(nn.Module):
             Y = torch.empty((n_out, self.out_channels), dtype=torch.float32, device=X.device)
             W = self.kernel.detach()
             if self.in_channels % 32 != 0:
-                if self.is_transpose or self.stride != 1:
-                    raise NotImplementedError("Cin not a multiple of 32 is supported for stride-1 convolutions only")
+                if self.is_transpose or self.stride != 1 or self.in_channels not in (1, 3, 6):
+                    raise NotImplementedError("Cin not a multiple of 32: only stride-1 convolutions with 1, 3 or 6 input "
+                                              "channels (ones / rgb / rgb+normal, util/misc.py:66-77) are implemented")
                 lvl = cm.level(t)
                 _lib.check(L.imf_conv_first_fwd(_lib.ptr(X), X.shape[1], self.in_channels, _lib.ptr(W), _lib.ptr(lvl.coords),
                                                 None, lvl.n, _lib.ptr(lvl.table), lvl.capacity, self.kernel_size, t,

@@ -95,7 +95,7 @@ class AttentionFusion(nn.Module):
                                           ws_bytes, _lib.cur_stream()))
         return kv
 
-    def fuse(self, queries: torch.Tensor, kv: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    def fuse(self, queries: torch.Tensor, kv: torch.Tensor, out: torch.Tensor | None = None, arena=None) -> torch.Tensor:
         """queries [M, latent] (row stride = queries.stride(0)) x kv (from project_context) -> [M, latent]."""
         L = _lib.lib()
         w = self.packed()
@@ -105,7 +105,7 @@ class AttentionFusion(nn.Module):
         if out is None:
             out = torch.empty((M, self.latent_dim), dtype=torch.float32, device=queries.device)
         ws_bytes = int(L.imf_attention_workspace_bytes(M, n_tok, self.latent_dim, self.inner))
-        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=queries.device)
+        ws = arena.take(ws_bytes) if arena is not None else torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=queries.device)
         with torch.cuda.device(queries.device):
             _lib.check(L.imf_attention_fusion_fwd(w, _lib.ptr(queries), queries.stride(0) if M > 0 else self.latent_dim, M,
                                                   _lib.ptr(kv), n_tok, _lib.ptr(out), out.stride(0) if M > 0 else self.latent_dim,

@@ -141,7 +141,9 @@ class CoordinateManager:
             L = _lib.lib()
             src, dst = self.levels[t_in], self.levels[t_out]
             scale = -t_out if transposed else t_in
-            nbr = torch.empty((dst.n, K ** 3), dtype=torch.int32, device=self.device)
+            # allocated at the stride-1 row count (an upper bound for every level) so that fragments of one size class reuse
+            # the same allocator blocks whatever their level sizes turn out to be
+            nbr = torch.empty((max(self.levels[1].n, dst.n), K ** 3), dtype=torch.int32, device=self.device)[: dst.n]
             with torch.cuda.device(self.device):
                 _lib.check(L.imf_kernel_map(_lib.ptr(dst.coords), None, dst.n, _lib.ptr(src.table), src.capacity, K, scale,
                                             _lib.ptr(nbr), _lib.cur_stream()))

@@ -98,7 +98,8 @@ int imf_sparse_conv_tc_fwd(const float* X, int32_t ldx, const void* packed, cons
                            const float* shift, const float* residual, int32_t ldr, int32_t relu, float* Y, int32_t ldy,
                            void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
 
-/* First layer (conv1, model/resunet.py:42-49,168): K in {1,3,5}, Cin <= 8, Cout in {32,64,128}; neighbours are
+/* First layer (conv1, model/resunet.py:42-49,168): K in {1,3,5}, Cin in {1,3,6} (ones / rgb / rgb+normal,
+ * util/misc.py:66-77), Cout in {32,64,128}; neighbours are
  * probed from the hash table of the same coordinate set, no neighbour table needed. */
 int imf_conv_first_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords, const int32_t* n_dev,
                        int32_t n_max, const void* table, long long capacity, int32_t kernel_size, int32_t tensor_stride,

@@ -89,7 +89,7 @@ def test_tensor_core_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout, split
     R = torch.randn(n_out, cout, generator=g)
     ref = torch.relu(sparse_ops.conv_forward(X, W, ocm.table(t_in, t_out, 3, tr)) * scale + shift + R)
     out = run_conv_tc(X.cuda(), W.cuda(), cm.table(t_in, t_out, 3, tr), n_out, scale.cuda(), shift.cuda(), R.cuda(), True, split)
-    close(out, ref, 1e-5)
+    close(out, ref)
 
 
 def test_tensor_core_conv_equals_simt_conv_c2_size():
@@ -103,7 +103,7 @@ def test_tensor_core_conv_equals_simt_conv_c2_size():
     W = torch.randn(27, 64, 64, device="cuda", generator=g) / 40
     a = run_conv(X, W, nbr, 50000)
     b = run_conv_tc(X, W, nbr, 50000, split=False)
-    close(b, a, 1e-5)
+    close(b, a)
 
 
 def test_conv_fused_epilogue_and_strided_operands(frag):
