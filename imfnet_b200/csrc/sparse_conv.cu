@@ -13,6 +13,8 @@
 // present for row r" is warp-uniform and absent neighbours cost nothing.  Stages of (offset k, 32 input
 // channels) are streamed with cp.async into a 3-deep shared-memory ring: gathered rows (16-byte vector
 // copies, one 128 B line per row and stage) and the matching weight slab.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -190,13 +192,13 @@ int launch_conv(const float* X, int ldx, const float* W, const int* nbr, const i
 // A warp owns one output voxel at a time: lanes probe the hash table for the K^3 neighbours (no neighbour table is
 // materialised -- 125 int32 per voxel would be 25 MB at 50 k voxels), then lane <-> output channel accumulates
 // the present offsets in ascending k.  Weights (K^3*Cin*Cout fp32, 16 KB for 125x1x32) sit in shared memory.
-template <int TN, int CIN>
+template <int TN, int CIN, bool H2>
 __global__ void __launch_bounds__(256) k_conv_first(const float* __restrict__ X, int ldx, const float* __restrict__ W,
                                                     const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max,
                                                     const ImfSlot* __restrict__ table, unsigned long long mask, int K,
                                                     int tstride, const float* __restrict__ scale,
                                                     const float* __restrict__ shift, int relu, float* __restrict__ Y, int ldy,
-                                                    int rows_per_cta) {
+                                                    int rows_per_cta, int kc_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* W_s = reinterpret_cast<float*>(smem_raw);
   constexpr int Cout = 32 * TN;
@@ -264,7 +266,14 @@ __global__ void __launch_bounds__(256) k_conv_first(const float* __restrict__ X,
       float v = acc[j];
       if (scale) v = fmaf(v, __ldg(scale + cch), __ldg(shift + cch));
       if (relu) v = fmaxf(v, 0.f);
-      Y[(size_t)row * ldy + cch] = v;
+      if (H2) {   // fp16 hi/lo output for the tensor-core tier (layout: sparse_conv_h2.cu); ldy counts halves
+        __half* yp = reinterpret_cast<__half*>(Y) + (size_t)row * ldy + (cch / kc_out) * 2 * kc_out + (cch % kc_out);
+        const __half h = __float2half_rn(v);
+        yp[0] = h;
+        yp[kc_out] = __float2half_rn(v - __half2float(h));
+      } else {
+        Y[(size_t)row * ldy + cch] = v;
+      }
     }
   }
 }
@@ -272,11 +281,12 @@ __global__ void __launch_bounds__(256) k_conv_first(const float* __restrict__ X,
 // ------------------------------------------------------------------------------------------------
 // Tail: conv1_tr (1x1, C0->C1, no bias) -> ReLU -> final (1x1, C1->C2, bias) -> row-wise L2 normalisation
 //   /root/reference/model/resunet.py:224-233.  One warp owns RM rows; lane <-> channel; hidden row stays in smem.
-template <int TN1>
+template <int TN1, bool H2>
 __global__ void __launch_bounds__(256) k_pointwise_tail(const float* __restrict__ X, int ldx, int C0, const float* __restrict__ W1,
                                                         const float* __restrict__ W2, const float* __restrict__ b2, int C2,
                                                         const int* __restrict__ n_ptr, int n_max, int normalize,
-                                                        float* __restrict__ Y, int ldy) {
+                                                        float* __restrict__ Y, int ldy, int Ca, int kca, int kcb,
+                                                        const int* __restrict__ out_row) {
   constexpr int RM = 8, C1 = 32 * TN1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* W1_s = reinterpret_cast<float*>(smem_raw);       // [C0][C1]
@@ -294,11 +304,39 @@ __global__ void __launch_bounds__(256) k_pointwise_tail(const float* __restrict_
     W2_s[i] = (c < C2) ? __ldg(W2 + r * C2 + c) : 0.f;
   }
   const int rows = min(64, n - row0);
-  for (int i = tid; i < 64 * (C0 / 4); i += 256) {
-    const int r = i / (C0 / 4), ch = i % (C0 / 4);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < rows) v = *reinterpret_cast<const float4*>(X + (size_t)(row0 + r) * ldx + ch * 4);
-    *reinterpret_cast<float4*>(X_s + r * C0 + ch * 4) = v;
+  if (H2) {
+    // X is an h2 matrix of two sections: channels [0,Ca) with chunk width kca, then [Ca,C0) with chunk width kcb
+    const __half* Xh = reinterpret_cast<const __half*>(X);
+    for (int i = tid; i < 64 * (C0 / 8); i += 256) {
+      const int r = i / (C0 / 8), c = (i % (C0 / 8)) * 8;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (r < rows) {
+        int off, kc;
+        if (c < Ca) { kc = kca; off = (c / kca) * 2 * kca + (c % kca); }
+        else { kc = kcb; const int c2 = c - Ca; off = 2 * Ca + (c2 / kcb) * 2 * kcb + (c2 % kcb); }
+        const __half* p = Xh + (size_t)(row0 + r) * ldx + off;
+        const uint4 hq = *reinterpret_cast<const uint4*>(p), lq = *reinterpret_cast<const uint4*>(p + kc);
+        const __half2* hh = reinterpret_cast<const __half2*>(&hq);
+        const __half2* ll = reinterpret_cast<const __half2*>(&lq);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = __half22float2(hh[e]), b = __half22float2(ll[e]);
+          v[2 * e] = a.x + b.x;
+          v[2 * e + 1] = a.y + b.y;
+        }
+      }
+      *reinterpret_cast<float4*>(X_s + r * C0 + c) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(X_s + r * C0 + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  } else {
+    for (int i = tid; i < 64 * (C0 / 4); i += 256) {
+      const int r = i / (C0 / 4), ch = i % (C0 / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) v = *reinterpret_cast<const float4*>(X + (size_t)(row0 + r) * ldx + ch * 4);
+      *reinterpret_cast<float4*>(X_s + r * C0 + ch * 4) = v;
+    }
   }
   __syncthreads();
 
@@ -361,7 +399,10 @@ __global__ void __launch_bounds__(256) k_pointwise_tail(const float* __restrict_
       const float ss = imf_warp_sum(v * v);
       v = v / sqrtf(ss);
     }
-    if (row < n && lane < C2) Y[(size_t)row * ldy + lane] = v;
+    if (row < n && lane < C2) {
+      const int orow = out_row ? __ldg(out_row + row) : row;     // optional scatter back to the caller's row order
+      Y[(size_t)orow * ldy + lane] = v;
+    }
   }
 }
 
@@ -399,36 +440,38 @@ extern "C" int imf_sparse_conv_fwd(const float* X, int32_t ldx, const float* W, 
 #undef IMF_GO
 }
 
-template <int TN, int CIN>
+template <int TN, int CIN, bool H2>
 static int launch_first(const float* X, int ldx, const float* W, const int32_t* coords, const int32_t* n_dev, int n_max, const void* table,
                         long long capacity, int K, int tstride, const float* scale, const float* shift, int relu, float* Y, int ldy,
-                        cudaStream_t stream) {
+                        int kc_out, cudaStream_t stream) {
   const int K3 = K * K * K;
   const size_t smem = (size_t)K3 * CIN * 32 * TN * sizeof(float);
   IMF_CHECK_ARG(smem <= 200 * 1024);
   const int rows_per_cta = 64;
   const int grid = (n_max + rows_per_cta - 1) / rows_per_cta;
-  IMF_CHECK_CUDA(cudaFuncSetAttribute(k_conv_first<TN, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  k_conv_first<TN, CIN><<<grid, 256, smem, stream>>>(X, ldx, W, reinterpret_cast<const int4*>(coords), n_dev, n_max,
-                                                     reinterpret_cast<const ImfSlot*>(table), (unsigned long long)capacity - 1, K, tstride,
-                                                     scale, shift, relu, Y, ldy, rows_per_cta);
+  IMF_CHECK_CUDA(cudaFuncSetAttribute(k_conv_first<TN, CIN, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  k_conv_first<TN, CIN, H2><<<grid, 256, smem, stream>>>(X, ldx, W, reinterpret_cast<const int4*>(coords), n_dev, n_max,
+                                                         reinterpret_cast<const ImfSlot*>(table), (unsigned long long)capacity - 1, K,
+                                                         tstride, scale, shift, relu, Y, ldy, rows_per_cta, kc_out);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }
 
-extern "C" int imf_conv_first_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords,
-                                  const int32_t* n_dev, int32_t n_max, const void* table, long long capacity,
-                                  int32_t kernel_size, int32_t tensor_stride, int32_t Cout, const float* scale,
-                                  const float* shift, int32_t relu, float* Y, int32_t ldy, cudaStream_t stream) {
+template <bool H2>
+static int conv_first_dispatch(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords, const int32_t* n_dev,
+                               int32_t n_max, const void* table, long long capacity, int32_t kernel_size, int32_t tensor_stride,
+                               int32_t Cout, const float* scale, const float* shift, int32_t relu, float* Y, int32_t ldy, int32_t kc_out,
+                               cudaStream_t stream) {
   IMF_CHECK_ARG(n_max >= 0 && kernel_size >= 1 && (kernel_size & 1) && kernel_size <= 5);
   IMF_CHECK_ARG((Cin == 1 || Cin == 3 || Cin == 6) && (Cout == 32 || Cout == 64 || Cout == 128));
-  IMF_CHECK_ARG((scale == nullptr) == (shift == nullptr) && ldx >= Cin && ldy >= Cout);
+  IMF_CHECK_ARG((scale == nullptr) == (shift == nullptr) && ldx >= Cin && ldy >= (H2 ? 2 : 1) * Cout);
+  IMF_CHECK_ARG(!H2 || ((kc_out == 32 || kc_out == 64) && Cout % kc_out == 0));
   IMF_CHECK_ARG(capacity > 0 && (capacity & (capacity - 1)) == 0);
   if (n_max == 0) return IMF_OK;
   IMF_CHECK_ARG(X != nullptr && W != nullptr && coords != nullptr && table != nullptr && Y != nullptr);
-#define IMF_GO(TN, CIN)                                                                                                  \
-  return launch_first<TN, CIN>(X, ldx, W, coords, n_dev, n_max, table, capacity, kernel_size, tensor_stride, scale, shift, relu, Y, \
-                               ldy, stream)
+#define IMF_GO(TN, CIN)                                                                                                       \
+  return launch_first<TN, CIN, H2>(X, ldx, W, coords, n_dev, n_max, table, capacity, kernel_size, tensor_stride, scale, shift, relu, \
+                                   Y, ldy, kc_out, stream)
 #define IMF_GO_C(TN)            \
   do {                          \
     if (Cin == 1) IMF_GO(TN, 1); \
@@ -442,23 +485,61 @@ extern "C" int imf_conv_first_fwd(const float* X, int32_t ldx, int32_t Cin, cons
 #undef IMF_GO
 }
 
-extern "C" int imf_pointwise_tail_fwd(const float* X, int32_t ldx, int32_t C0, const float* W1, int32_t C1, const float* W2,
-                                      const float* b2, int32_t C2, const int32_t* n_dev, int32_t n_max, int32_t normalize,
-                                      float* Y, int32_t ldy, cudaStream_t stream) {
-  IMF_CHECK_ARG(n_max >= 0 && C0 > 0 && C0 % 4 == 0 && ldx % 4 == 0 && ldx >= C0 && C2 >= 1 && C2 <= 32 && ldy >= C2);
+extern "C" int imf_conv_first_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords,
+                                  const int32_t* n_dev, int32_t n_max, const void* table, long long capacity,
+                                  int32_t kernel_size, int32_t tensor_stride, int32_t Cout, const float* scale,
+                                  const float* shift, int32_t relu, float* Y, int32_t ldy, cudaStream_t stream) {
+  return conv_first_dispatch<false>(X, ldx, Cin, W, coords, n_dev, n_max, table, capacity, kernel_size, tensor_stride, Cout, scale,
+                                    shift, relu, Y, ldy, 0, stream);
+}
+
+// Same, writing the fp16 hi/lo ("h2", sparse_conv_h2.cu) layout; ldy counts halves.
+extern "C" int imf_conv_first_h2_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords,
+                                     const int32_t* n_dev, int32_t n_max, const void* table, long long capacity,
+                                     int32_t kernel_size, int32_t tensor_stride, int32_t Cout, const float* scale,
+                                     const float* shift, int32_t relu, void* Y, int32_t ldy, int32_t kc_out, cudaStream_t stream) {
+  return conv_first_dispatch<true>(X, ldx, Cin, W, coords, n_dev, n_max, table, capacity, kernel_size, tensor_stride, Cout, scale,
+                                   shift, relu, reinterpret_cast<float*>(Y), ldy, kc_out, stream);
+}
+
+template <bool H2>
+static int tail_dispatch(const float* X, int32_t ldx, int32_t C0, const float* W1, int32_t C1, const float* W2, const float* b2,
+                         int32_t C2, const int32_t* n_dev, int32_t n_max, int32_t normalize, float* Y, int32_t ldy, int32_t Ca,
+                         int32_t kca, int32_t kcb, const int32_t* out_row, cudaStream_t stream) {
+  IMF_CHECK_ARG(n_max >= 0 && C0 > 0 && C0 % (H2 ? 8 : 4) == 0 && ldx % (H2 ? 8 : 4) == 0 && ldx >= (H2 ? 2 : 1) * C0);
+  IMF_CHECK_ARG(C2 >= 1 && C2 <= 32 && ldy >= C2);
   IMF_CHECK_ARG(C1 == 32 || C1 == 64 || C1 == 128);
+  if (H2) {
+    IMF_CHECK_ARG(Ca >= 0 && Ca <= C0 && (kca == 32 || kca == 64) && (kcb == 32 || kcb == 64) && Ca % kca == 0 && (C0 - Ca) % kcb == 0);
+  }
   if (n_max == 0) return IMF_OK;
   IMF_CHECK_ARG(X != nullptr && W1 != nullptr && W2 != nullptr && Y != nullptr && ((uintptr_t)X % 16) == 0);
   const size_t smem = ((size_t)C0 * C1 + (size_t)C1 * 32 + 64 * (size_t)C0 + 64 * (size_t)C1) * sizeof(float);
   IMF_CHECK_ARG(smem <= 200 * 1024);
   const int grid = (n_max + 63) / 64;
-#define IMF_GO(TN1)                                                                                                     \
-  do {                                                                                                                  \
-    IMF_CHECK_CUDA(cudaFuncSetAttribute(k_pointwise_tail<TN1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-    k_pointwise_tail<TN1><<<grid, 256, smem, stream>>>(X, ldx, C0, W1, W2, b2, C2, n_dev, n_max, normalize, Y, ldy);    \
+#define IMF_GO(TN1)                                                                                                         \
+  do {                                                                                                                      \
+    IMF_CHECK_CUDA(cudaFuncSetAttribute(k_pointwise_tail<TN1, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+    k_pointwise_tail<TN1, H2><<<grid, 256, smem, stream>>>(X, ldx, C0, W1, W2, b2, C2, n_dev, n_max, normalize, Y, ldy, Ca, kca, kcb, \
+                                                           out_row);                                                         \
   } while (0)
   if (C1 == 32) IMF_GO(1); else if (C1 == 64) IMF_GO(2); else IMF_GO(4);
 #undef IMF_GO
   IMF_CHECK_LAUNCH();
   return IMF_OK;
+}
+
+extern "C" int imf_pointwise_tail_fwd(const float* X, int32_t ldx, int32_t C0, const float* W1, int32_t C1, const float* W2,
+                                      const float* b2, int32_t C2, const int32_t* n_dev, int32_t n_max, int32_t normalize,
+                                      float* Y, int32_t ldy, cudaStream_t stream) {
+  return tail_dispatch<false>(X, ldx, C0, W1, C1, W2, b2, C2, n_dev, n_max, normalize, Y, ldy, 0, 0, 0, nullptr, stream);
+}
+
+// Same on an h2 input made of two sections (channels [0,Ca) with chunk width kca, [Ca,C0) with kcb; ldx counts halves);
+// out_row (optional, int32 [n]) scatters result row i to Y[out_row[i]] (internal -> caller row order).
+extern "C" int imf_pointwise_tail_h2_fwd(const void* X, int32_t ldx, int32_t C0, int32_t Ca, int32_t kca, int32_t kcb, const float* W1,
+                                         int32_t C1, const float* W2, const float* b2, int32_t C2, const int32_t* n_dev, int32_t n_max,
+                                         int32_t normalize, const int32_t* out_row, float* Y, int32_t ldy, cudaStream_t stream) {
+  return tail_dispatch<true>(reinterpret_cast<const float*>(X), ldx, C0, W1, C1, W2, b2, C2, n_dev, n_max, normalize, Y, ldy, Ca, kca,
+                             kcb, out_row, stream);
 }

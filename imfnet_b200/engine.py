@@ -10,13 +10,26 @@ half writes straight into it, so no concat kernel and no extra copy exists.
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 from . import _lib
 from .arena import Arena
 
 
+def _kc(*channels) -> int:
+    """Chunk width of an h2 buffer section holding these channel counts (see csrc/sparse_conv_h2.cu)."""
+    return 64 if all(c % 64 == 0 for c in channels) else 32
+
+
 class FusedPlan:
+    # (convolution, the BatchNorm folded into its epilogue) for every 3x3x3 layer of the graph
+    CONV_BN = [("conv2", "norm2"), ("conv3", "norm3"), ("conv4", "norm4"), ("conv4_tr", "norm4_tr"), ("conv3_tr", "norm3_tr"),
+               ("conv2_tr", "norm2_tr")] + [(f"{b}.conv{i}", f"{b}.norm{i}") for b in
+                                            ("block1", "block2", "block3", "block4", "block4_tr", "block3_tr", "block2_tr")
+                                            for i in (1, 2)]
+
     def __init__(self, model):
         self.m = model
         p = next(model.parameters())
@@ -26,7 +39,6 @@ class FusedPlan:
         self.CH, self.TR = model.CHANNELS, model.TR_CHANNELS
         self._key = None
         self.debug = None      # set to a dict to capture intermediate activations (tests only)
-        self.conv_impl = "tc"  # "tc" = tcgen05 3xTF32 implicit GEMM; "simt" = fp32 SIMT tier
         self.arena = Arena(self.device)
         self.pack()
 
@@ -35,55 +47,62 @@ class FusedPlan:
         return tuple((t.data_ptr(), t._version) for t in list(self.m.parameters()) + list(self.m.buffers()))
 
     def pack(self):
+        """Fold every BatchNorm into (scale, shift), split + swizzle the 3x3x3 kernels for the fp16 hi/lo tensor-core tier."""
         m = self.m
         for t in m.parameters():
             if t.dtype != torch.float32:
                 raise TypeError("imfnet_b200 computes in float32; cast the model with .float()")
-        self.bn = {}
-        for name in ("norm1", "norm2", "norm3", "norm4", "norm4_tr", "norm3_tr", "norm2_tr"):
-            self.bn[name] = getattr(m, name).folded()
-        for b in ("block1", "block2", "block3", "block4", "block4_tr", "block3_tr", "block2_tr"):
-            blk = getattr(m, b)
-            self.bn[b + ".norm1"] = blk.norm1.folded()
-            self.bn[b + ".norm2"] = blk.norm2.folded()
-        self.final_bias = None if m.final.bias is None else m.final.bias.detach().reshape(-1).contiguous()
-        # tensor-core weight slabs (hi/lo TF32 split, swizzled) for every 3x3x3 convolution
+        mods = dict(m.named_modules())
+        CH, TR = self.CH, self.TR
+        # chunk width of the buffer each convolution reads
+        kc_in = {"conv2": _kc(CH[1]), "conv3": _kc(TR[3], CH[2]), "conv4": _kc(TR[4], CH[3]), "conv4_tr": _kc(CH[4]),
+                 "conv3_tr": _kc(TR[4], CH[3]), "conv2_tr": _kc(TR[3], CH[2])}
         L = _lib.lib()
-        self.packed = {}
+        self.conv = {}
         with torch.cuda.device(self.device):
             s = torch.cuda.current_stream().cuda_stream
-            for name, mod in m.named_modules():
-                if hasattr(mod, "kernel") and getattr(mod, "kernel_volume", 1) == 27 and mod.in_channels % 32 == 0:
-                    nbytes = int(L.imf_sparse_conv_tc_packed_bytes(27, mod.in_channels, mod.out_channels))
-                    buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-                    _lib.check(L.imf_sparse_conv_tc_pack(mod.kernel.detach().contiguous().data_ptr(), 27, mod.in_channels,
-                                                         mod.out_channels, buf.data_ptr(), s))
-                    self.packed[id(mod)] = buf
+            for cname, bname in self.CONV_BN:
+                conv, bn = mods[cname], mods[bname]
+                if conv.kernel_volume != 27 or conv.in_channels % 32 or conv.out_channels not in (32, 64, 128, 256):
+                    raise NotImplementedError(f"{cname}: unsupported shape for the tensor-core tier")
+                kci = kc_in.get(cname, _kc(conv.in_channels))
+                wmax = float(conv.kernel.detach().abs().max())
+                wmul = 2.0 ** math.floor(math.log2(2048.0 / wmax)) if wmax > 0 else 1.0
+                nbytes = int(L.imf_sparse_conv_h2_packed_bytes(27, conv.in_channels, conv.out_channels, kci))
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                _lib.check(L.imf_sparse_conv_h2_pack(conv.kernel.detach().contiguous().data_ptr(), 27, conv.in_channels,
+                                                     conv.out_channels, kci, wmul, buf.data_ptr(), s))
+                scale, shift = bn.folded()
+                self.conv[cname] = (conv, buf, (scale / wmul).contiguous(), shift, kci)
+        sc, sh = m.norm1.folded()
+        self.norm1 = (sc, sh)
+        self.final_bias = None if m.final.bias is None else m.final.bias.detach().reshape(-1).contiguous()
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._key = self._weights_key()
 
     # -- launch helpers ------------------------------------------------------------------------
-    def _conv(self, L, X, ldx, conv, nbr, n_out, bn, R, ldr, relu, Y, ldy, stream):
-        scale, shift = (None, None) if bn is None else self.bn[bn]
-        if self.conv_impl == "simt":          # fp32 SIMT tier (kept for A/B measurements)
-            _lib.check(L.imf_sparse_conv_fwd(X, ldx, conv.kernel.data_ptr(), nbr.data_ptr(), None, n_out, conv.kernel_volume,
-                                             conv.in_channels, conv.out_channels, _lib.ptr(scale), _lib.ptr(shift), R, ldr,
-                                             1 if relu else 0, Y, ldy, stream))
-            return
+    def _conv(self, L, cname, X, ldx, nbr, n_out, R, ldr, kc_r, relu, Y, ldy, kc_out, stream):
+        """One 3x3x3 convolution + folded BatchNorm (+ residual) (+ ReLU); X, R, Y are h2 matrices (ld in halves)."""
+        conv, packed, scale, shift, kci = self.conv[cname]
         ws, ws_bytes = None, 0
         if n_out < 12800:                     # few row tiles: let the kernel split a tile's offsets over several CTAs
-            ws_bytes = int(L.imf_sparse_conv_tc_workspace_bytes(n_out, conv.out_channels))
+            ws_bytes = int(L.imf_sparse_conv_h2_workspace_bytes(n_out, conv.out_channels))
             ws = self.arena.take(ws_bytes)
-        _lib.check(L.imf_sparse_conv_tc_fwd(X, ldx, self.packed[id(conv)].data_ptr(), nbr.data_ptr(), None, n_out,
-                                            conv.kernel_volume, conv.in_channels, conv.out_channels, _lib.ptr(scale),
-                                            _lib.ptr(shift), R, ldr, 1 if relu else 0, Y, ldy, _lib.ptr(ws), ws_bytes,
-                                            self.err.data_ptr(), stream))
+        _lib.check(L.imf_sparse_conv_h2_fwd(X, ldx, kci, packed.data_ptr(), nbr.data_ptr(), None, n_out, 27, conv.in_channels,
+                                            conv.out_channels, scale.data_ptr(), shift.data_ptr(), R, ldr, kc_r, 1 if relu else 0,
+                                            Y, ldy, kc_out, _lib.ptr(ws), ws_bytes, self.err.data_ptr(), stream))
 
-    def _block(self, L, name, X, ldx, nbr, n, C, tmp, Y, ldy, stream):
+    def _block(self, L, name, X, ldx, kc_x, nbr, n, C, tmp, Y, ldy, kc_y, stream):
         """BasicBlockBN (model/residual_block.py:37-53): X -> tmp = relu(bn1(conv1 X)) -> Y = relu(bn2(conv2 tmp) + X)."""
-        blk = getattr(self.m, name)
-        self._conv(L, X, ldx, blk.conv1, nbr, n, name + ".norm1", None, 0, True, tmp.data_ptr(), C, stream)
-        self._conv(L, tmp.data_ptr(), C, blk.conv2, nbr, n, name + ".norm2", X, ldx, True, Y, ldy, stream)
+        kt = _kc(C)
+        self._conv(L, name + ".conv1", X, ldx, nbr, n, None, 0, 0, True, tmp.data_ptr(), 2 * C, kt, stream)
+        self._conv(L, name + ".conv2", tmp.data_ptr(), 2 * C, nbr, n, X, ldx, kc_x, True, Y, ldy, kc_y, stream)
+
+    def _unpack(self, ptr, ldh, n, C, kc):
+        out = torch.empty((n, C), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().imf_h2_unpack(ptr, ldh, n, C, kc, out.data_ptr(), C, torch.cuda.current_stream().cuda_stream))
+        return out
 
     # -- forward -------------------------------------------------------------------------------
     @torch.no_grad()
@@ -104,7 +123,6 @@ class FusedPlan:
         if t0 != 1:
             raise NotImplementedError("the fused plan expects an input at tensor stride 1")
         N0 = len(F0)
-        f4 = 4  # bytes per float
 
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream()
@@ -120,6 +138,7 @@ class FusedPlan:
 
             # ---- coordinates ----
             cm.build_pyramid([2, 4, 8])
+            self._raise_on_status(int(self.err_host[0]))   # status of earlier forwards (build_pyramid synchronised the stream)
             lv = {t: cm.level(t) for t in (1, 2, 4, 8)}
             n1, n2, n4, n8 = lv[1].n, lv[2].n, lv[4].n, lv[8].n
             nb = {t: cm.table(t, t, 3, False) for t in (1, 2, 4, 8)}
@@ -127,47 +146,56 @@ class FusedPlan:
             up = {(8, 4): cm.table(8, 4, 3, True), (4, 2): cm.table(4, 2, 3, True), (2, 1): cm.table(2, 1, 3, True)}
 
             self.arena.reset()
-            buf = self.arena.floats
+            buf = self.arena.floats        # an h2 matrix of C channels occupies exactly the bytes of an fp32 [n, C] matrix
 
-            # concat buffers: [decoder half | encoder skip half]
+            # concat buffers: [decoder half | encoder skip half]; ld in halves; byte offset of the skip half = 4*TR
             cat1, cat2, cat4 = buf(n1, TR[2] + CH[1]), buf(n2, TR[3] + CH[2]), buf(n4, TR[4] + CH[3])
-            ld1, ld2, ld4 = cat1.shape[1], cat2.shape[1], cat4.shape[1]
-            s1_ptr, s2_ptr, s4_ptr = cat1.data_ptr() + TR[2] * f4, cat2.data_ptr() + TR[3] * f4, cat4.data_ptr() + TR[4] * f4
+            ld1, ld2, ld4 = 2 * cat1.shape[1], 2 * cat2.shape[1], 2 * cat4.shape[1]
+            s1_ptr, s2_ptr, s4_ptr = cat1.data_ptr() + TR[2] * 4, cat2.data_ptr() + TR[3] * 4, cat4.data_ptr() + TR[4] * 4
+            kc1a, kc1b = _kc(TR[2]), _kc(CH[1])
+            kc2, kc4 = _kc(TR[3], CH[2]), _kc(TR[4], CH[3])
 
             # ---- encoder ----
             a0, a1 = buf(n1, CH[1]), buf(n1, CH[1])
-            sc, sh = self.bn["norm1"]
-            _lib.check(L.imf_conv_first_fwd(F0.data_ptr(), F0.shape[1], m.conv1.in_channels, m.conv1.kernel.data_ptr(),
-                                            lv[1].coords.data_ptr(), None, n1, lv[1].table.data_ptr(), lv[1].capacity,
-                                            m.conv1.kernel_size, 1, CH[1], sc.data_ptr(), sh.data_ptr(), 0, a0.data_ptr(),
-                                            CH[1], s))                                         # conv1 + norm1   :168-169
-            self._block(L, "block1", a0.data_ptr(), CH[1], nb[1], n1, CH[1], a1, s1_ptr, ld1, s)   # out_s1 -> cat1[:, TR2:]
+            sc, sh = self.norm1
+            _lib.check(L.imf_conv_first_h2_fwd(F0.data_ptr(), F0.shape[1], m.conv1.in_channels, m.conv1.kernel.data_ptr(),
+                                               lv[1].coords.data_ptr(), None, n1, lv[1].table.data_ptr(), lv[1].capacity,
+                                               m.conv1.kernel_size, 1, CH[1], sc.data_ptr(), sh.data_ptr(), 0, a0.data_ptr(),
+                                               2 * CH[1], _kc(CH[1]), s))                          # conv1 + norm1   :168-169
+            self._block(L, "block1", a0.data_ptr(), 2 * CH[1], _kc(CH[1]), nb[1], n1, CH[1], a1, s1_ptr, ld1, kc1b, s)   # out_s1
 
             b0, b1 = buf(n2, CH[2]), buf(n2, CH[2])
-            self._conv(L, s1_ptr, ld1, m.conv2, dn[(1, 2)], n2, "norm2", None, 0, False, b0.data_ptr(), CH[2], s)   # :173-174
-            self._block(L, "block2", b0.data_ptr(), CH[2], nb[2], n2, CH[2], b1, s2_ptr, ld2, s)   # out_s2 -> cat2[:, TR3:]
+            self._conv(L, "conv2", s1_ptr, ld1, dn[(1, 2)], n2, None, 0, 0, False, b0.data_ptr(), 2 * CH[2], _kc(CH[2]), s)   # :173-174
+            self._block(L, "block2", b0.data_ptr(), 2 * CH[2], _kc(CH[2]), nb[2], n2, CH[2], b1, s2_ptr, ld2, kc2, s)        # out_s2
 
             c0, c1 = buf(n4, CH[3]), buf(n4, CH[3])
-            self._conv(L, s2_ptr, ld2, m.conv3, dn[(2, 4)], n4, "norm3", None, 0, False, c0.data_ptr(), CH[3], s)   # :178-179
-            self._block(L, "block3", c0.data_ptr(), CH[3], nb[4], n4, CH[3], c1, s4_ptr, ld4, s)   # out_s4 -> cat4[:, TR4:]
+            self._conv(L, "conv3", s2_ptr, ld2, dn[(2, 4)], n4, None, 0, 0, False, c0.data_ptr(), 2 * CH[3], _kc(CH[3]), s)   # :178-179
+            self._block(L, "block3", c0.data_ptr(), 2 * CH[3], _kc(CH[3]), nb[4], n4, CH[3], c1, s4_ptr, ld4, kc4, s)        # out_s4
 
             d0, d1, d2 = buf(n8, CH[4]), buf(n8, CH[4]), buf(n8, CH[4])
-            self._conv(L, s4_ptr, ld4, m.conv4, dn[(4, 8)], n8, "norm4", None, 0, False, d0.data_ptr(), CH[4], s)   # :183-184
-            self._block(L, "block4", d0.data_ptr(), CH[4], nb[8], n8, CH[4], d1, d2.data_ptr(), CH[4], s)          # out_s8
+            k8 = _kc(CH[4])
+            self._conv(L, "conv4", s4_ptr, ld4, dn[(4, 8)], n8, None, 0, 0, False, d0.data_ptr(), 2 * CH[4], k8, s)          # :183-184
+            self._block(L, "block4", d0.data_ptr(), 2 * CH[4], k8, nb[8], n8, CH[4], d1, d2.data_ptr(), 2 * CH[4], k8, s)    # out_s8
 
-            # ---- attention fusion at stride 8 (resunet.py:189, 237-273) ----
+            # ---- attention fusion at stride 8 (resunet.py:189, 237-273), fp32 tokens ----
+            P8 = buf(n8, CH[4])
+            _lib.check(L.imf_h2_unpack(d2.data_ptr(), 2 * CH[4], n8, CH[4], k8, P8.data_ptr(), CH[4], s))
             main.wait_event(ev_img)
-            fused = buf(n8, CH[4])
+            fused32 = buf(n8, CH[4])
             seg = cm.batch_segments(8, B) if B > 1 else [0, n8]
             for b in range(B):
                 lo, hi = seg[b], seg[b + 1]
                 if hi > lo:
-                    m.attention_fusion.fuse(d2[lo:hi], kvs[b], out=fused[lo:hi], arena=self.arena)
+                    m.attention_fusion.fuse(P8[lo:hi], kvs[b], out=fused32[lo:hi], arena=self.arena)
             if seg[B] != n8:
                 raise ValueError("coordinates reference more batch items than images were given")
+            fused = buf(n8, CH[4])
+            _lib.check(L.imf_h2_pack(fused32.data_ptr(), CH[4], n8, CH[4], k8, fused.data_ptr(), 2 * CH[4], self.err.data_ptr(), s))
             if self.debug is not None:
-                self.debug.update(image=img.clone(), out_s1=cat1[:, TR[2]:].clone(), out_s2=cat2[:, TR[3]:].clone(),
-                                  out_s4=cat4[:, TR[4]:].clone(), out_s8=d2.clone(), fused=fused.clone(), conv1=a0.clone(),
+                self.debug.update(image=img.clone(), out_s1=self._unpack(s1_ptr, ld1, n1, CH[1], kc1b),
+                                  out_s2=self._unpack(s2_ptr, ld2, n2, CH[2], kc2), out_s4=self._unpack(s4_ptr, ld4, n4, CH[3], kc4),
+                                  out_s8=P8.clone(), fused=fused32.clone(),
+                                  conv1=self._unpack(a0.data_ptr(), 2 * CH[1], n1, CH[1], _kc(CH[1])),
                                   levels={t: lv[t].coords.clone() for t in (1, 2, 4, 8)})
             for kv in kvs:
                 kv.record_stream(main)
@@ -175,23 +203,38 @@ class FusedPlan:
 
             # ---- decoder ----
             e0, e1 = buf(n4, TR[4]), buf(n4, TR[4])
-            self._conv(L, fused.data_ptr(), CH[4], m.conv4_tr, up[(8, 4)], n4, "norm4_tr", None, 0, False, e0.data_ptr(), TR[4], s)
-            self._block(L, "block4_tr", e0.data_ptr(), TR[4], nb[4], n4, TR[4], e1, cat4.data_ptr(), ld4, s)   # -> cat4[:, :TR4]
+            self._conv(L, "conv4_tr", fused.data_ptr(), 2 * CH[4], up[(8, 4)], n4, None, 0, 0, False, e0.data_ptr(), 2 * TR[4],
+                       _kc(TR[4]), s)
+            self._block(L, "block4_tr", e0.data_ptr(), 2 * TR[4], _kc(TR[4]), nb[4], n4, TR[4], e1, cat4.data_ptr(), ld4, kc4, s)
 
             g0, g1 = buf(n2, TR[3]), buf(n2, TR[3])
-            self._conv(L, cat4.data_ptr(), ld4, m.conv3_tr, up[(4, 2)], n2, "norm3_tr", None, 0, False, g0.data_ptr(), TR[3], s)
-            self._block(L, "block3_tr", g0.data_ptr(), TR[3], nb[2], n2, TR[3], g1, cat2.data_ptr(), ld2, s)   # -> cat2[:, :TR3]
+            self._conv(L, "conv3_tr", cat4.data_ptr(), ld4, up[(4, 2)], n2, None, 0, 0, False, g0.data_ptr(), 2 * TR[3], _kc(TR[3]), s)
+            self._block(L, "block3_tr", g0.data_ptr(), 2 * TR[3], _kc(TR[3]), nb[2], n2, TR[3], g1, cat2.data_ptr(), ld2, kc2, s)
 
             h0, h1 = buf(n1, TR[2]), buf(n1, TR[2])
-            self._conv(L, cat2.data_ptr(), ld2, m.conv2_tr, up[(2, 1)], n1, "norm2_tr", None, 0, False, h0.data_ptr(), TR[2], s)
-            self._block(L, "block2_tr", h0.data_ptr(), TR[2], nb[1], n1, TR[2], h1, cat1.data_ptr(), ld1, s)   # -> cat1[:, :TR2]
+            self._conv(L, "conv2_tr", cat2.data_ptr(), ld2, up[(2, 1)], n1, None, 0, 0, False, h0.data_ptr(), 2 * TR[2], _kc(TR[2]), s)
+            self._block(L, "block2_tr", h0.data_ptr(), 2 * TR[2], _kc(TR[2]), nb[1], n1, TR[2], h1, cat1.data_ptr(), ld1, kc1a, s)
 
             # ---- tail: conv1_tr -> ReLU -> final(+bias) -> L2 norm (resunet.py:224-233) ----
             out = torch.empty((n1, m.out_channels), dtype=torch.float32, device=dev)
-            _lib.check(L.imf_pointwise_tail_fwd(cat1.data_ptr(), ld1, ld1, m.conv1_tr.kernel.data_ptr(), TR[1],
-                                                m.final.kernel.data_ptr(), _lib.ptr(self.final_bias), m.out_channels, None,
-                                                n1, 1 if m.normalize_feature else 0, out.data_ptr(), m.out_channels, s))
+            _lib.check(L.imf_pointwise_tail_h2_fwd(cat1.data_ptr(), ld1, TR[2] + CH[1], TR[2], kc1a, kc1b,
+                                                   m.conv1_tr.kernel.data_ptr(), TR[1], m.final.kernel.data_ptr(),
+                                                   _lib.ptr(self.final_bias), m.out_channels, None, n1,
+                                                   1 if m.normalize_feature else 0, None, out.data_ptr(), m.out_channels, s))
             if self.debug is not None:
-                self.debug.update(out_s4_tr=cat4[:, :TR[4]].clone(), out_s2_tr=cat2[:, :TR[3]].clone(),
-                                  out_s1_tr=cat1[:, :TR[2]].clone())
+                self.debug.update(out_s4_tr=self._unpack(cat4.data_ptr(), ld4, n4, TR[4], kc4),
+                                  out_s2_tr=self._unpack(cat2.data_ptr(), ld2, n2, TR[3], kc2),
+                                  out_s1_tr=self._unpack(cat1.data_ptr(), ld1, n1, TR[2], kc1a))
+            self.err_host.copy_(self.err, non_blocking=True)
         return out
+
+    @staticmethod
+    def _raise_on_status(v: int):
+        if v & 0x10000:
+            raise FloatingPointError("an activation left the fp16 hi/lo range (|v| > 60000) in the tensor-core tier")
+        if v & 0xFFFF:
+            raise RuntimeError(f"in-kernel pipeline watchdog fired (code {v & 0xFFFF})")
+
+    def check_numeric_status(self):
+        """Raises if any kernel of earlier forwards reported an fp16-range overflow or a pipeline watchdog (one host sync)."""
+        self._raise_on_status(int(self.err.item()))

@@ -98,6 +98,25 @@ int imf_sparse_conv_tc_fwd(const float* X, int32_t ldx, const void* packed, cons
                            const float* shift, const float* residual, int32_t ldr, int32_t relu, float* Y, int32_t ldy,
                            void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
 
+/* ---- "h2" tier: activations stored as two fp16 halves (v = hi + lo), products accumulated as lo*Whi + hi*Wlo + hi*Whi by
+ *      kind::f16 tcgen05 MMAs into fp32 TMEM (fp32-class accuracy at twice the TF32 MMA rate and a copy-only gather).
+ * h2 matrix of C channels with chunk width KC in {32,64} (C % KC == 0), row stride ld in HALVES (>= 2C, multiple of 8):
+ *   channel c = q*KC + j  ->  hi at row*ld + q*2*KC + j, lo at row*ld + q*2*KC + KC + j.
+ * `err` (optional device int): bit 16 is set if a stored value left the fp16 range (|v| > 60000); codes 1..3 = watchdog. */
+int imf_h2_pack(const float* X, int32_t ldx, int32_t n, int32_t C, int32_t KC, void* H, int32_t ldh, int32_t* err, imf_stream_t stream);
+int imf_h2_unpack(const void* H, int32_t ldh, int32_t n, int32_t C, int32_t KC, float* X, int32_t ldx, imf_stream_t stream);
+
+/* Weights W[K^3,Cin,Cout] * wmul (a power of two that brings max|W| near 2^11; fold 1/wmul into `scale`) packed for the
+ * input chunk width kc_in.  Same operation and epilogue as imf_sparse_conv_fwd; scale and shift are required. */
+size_t imf_sparse_conv_h2_packed_bytes(int32_t kernel_volume, int32_t Cin, int32_t Cout, int32_t kc_in);
+int imf_sparse_conv_h2_pack(const float* W, int32_t kernel_volume, int32_t Cin, int32_t Cout, int32_t kc_in, float wmul, void* packed,
+                            imf_stream_t stream);
+size_t imf_sparse_conv_h2_workspace_bytes(int32_t n_out_max, int32_t Cout);
+int imf_sparse_conv_h2_fwd(const void* X, int32_t ldx, int32_t kc_in, const void* packed, const int32_t* nbr, const int32_t* n_out_dev,
+                           int32_t n_out_max, int32_t kernel_volume, int32_t Cin, int32_t Cout, const float* scale, const float* shift,
+                           const void* residual, int32_t ldr, int32_t kc_r, int32_t relu, void* Y, int32_t ldy, int32_t kc_out,
+                           void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+
 /* First layer (conv1, model/resunet.py:42-49,168): K in {1,3,5}, Cin in {1,3,6} (ones / rgb / rgb+normal,
  * util/misc.py:66-77), Cout in {32,64,128}; neighbours are
  * probed from the hash table of the same coordinate set, no neighbour table needed. */
@@ -106,11 +125,24 @@ int imf_conv_first_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W,
                        int32_t Cout, const float* scale, const float* shift, int32_t relu, float* Y, int32_t ldy,
                        imf_stream_t stream);
 
+/* imf_conv_first_fwd writing an h2 matrix (ldy in halves, chunk width kc_out). */
+int imf_conv_first_h2_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords, const int32_t* n_dev,
+                          int32_t n_max, const void* table, long long capacity, int32_t kernel_size, int32_t tensor_stride,
+                          int32_t Cout, const float* scale, const float* shift, int32_t relu, void* Y, int32_t ldy, int32_t kc_out,
+                          imf_stream_t stream);
+
 /* conv1_tr (1x1, no bias) -> ReLU -> final (1x1 + bias) -> optional row L2 normalisation
  * (model/resunet.py:224-233).  W1 = [C0, C1], W2 = [C1, C2], b2 = [C2] or NULL; C1 in {32,64,128}, C2 <= 32. */
 int imf_pointwise_tail_fwd(const float* X, int32_t ldx, int32_t C0, const float* W1, int32_t C1, const float* W2,
                            const float* b2, int32_t C2, const int32_t* n_dev, int32_t n_max, int32_t normalize, float* Y,
                            int32_t ldy, imf_stream_t stream);
+
+/* imf_pointwise_tail_fwd reading an h2 matrix made of two sections (model/resunet.py:219 concatenation): channels [0,Ca)
+ * with chunk width kca, then [Ca,C0) with chunk width kcb; ldx in halves.  out_row (optional int32 [n]) writes result
+ * row i to Y[out_row[i]] (internal row order -> caller row order). */
+int imf_pointwise_tail_h2_fwd(const void* X, int32_t ldx, int32_t C0, int32_t Ca, int32_t kca, int32_t kcb, const float* W1, int32_t C1,
+                              const float* W2, const float* b2, int32_t C2, const int32_t* n_dev, int32_t n_max, int32_t normalize,
+                              const int32_t* out_row, float* Y, int32_t ldy, imf_stream_t stream);
 
 /* Y = X . W (+ bias): a 1x1 ME.MinkowskiConvolution as a module (kernel [Cin, Cout]). */
 int imf_linear_fwd(const float* X, int32_t ldx, const float* W_kn, const float* bias, int32_t M, int32_t Cin, int32_t Cout,

@@ -8,6 +8,9 @@ from oracle import sparse_ops
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-4      # north-star tolerance; observed error is ~1e-6 (fp32 accumulation-order noise)
+# tensor-core tiers: the operands carry 22 mantissa bits, but the MMA unit adds into its fp32 accumulator with truncation, so the
+# error grows with the number of accumulation steps (27 offsets x Cin/16 x 3 products): observed up to 8e-6 at Cin = 128-256
+H2_RTOL = 3e-5
 
 
 def close(a, b, rtol=RTOL):
@@ -90,6 +93,129 @@ def test_tensor_core_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout, split
     ref = torch.relu(sparse_ops.conv_forward(X, W, ocm.table(t_in, t_out, 3, tr)) * scale + shift + R)
     out = run_conv_tc(X.cuda(), W.cuda(), cm.table(t_in, t_out, 3, tr), n_out, scale.cuda(), shift.cuda(), R.cuda(), True, split)
     close(out, ref)
+
+
+def h2_pack(X, kc, ld_extra=0):
+    L = _lib.lib()
+    n, C = X.shape
+    H = torch.zeros((n, 2 * C + ld_extra), dtype=torch.float16, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(L.imf_h2_pack(X.data_ptr(), X.stride(0), n, C, kc, H.data_ptr(), H.stride(0), err.data_ptr(), _lib.cur_stream()))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    return H
+
+
+def h2_unpack(H, C, kc):
+    L = _lib.lib()
+    n = H.shape[0]
+    X = torch.empty((n, C), dtype=torch.float32, device="cuda")
+    _lib.check(L.imf_h2_unpack(H.data_ptr(), H.stride(0), n, C, kc, X.data_ptr(), C, _lib.cur_stream()))
+    torch.cuda.synchronize()
+    return X
+
+
+def run_conv_h2(X, W, nbr, n_out, scale, shift, R=None, relu=False, split=True, kc_out=None):
+    """fp32 in/out wrapper of the fp16 hi/lo tensor-core tier: pack -> conv -> unpack."""
+    L = _lib.lib()
+    K3, cin, cout = W.shape
+    kc_in = 64 if cin % 64 == 0 else 32
+    kc_out = kc_out or (64 if cout % 64 == 0 else 32)
+    wmul = 2.0 ** np.floor(np.log2(2048.0 / float(W.abs().max())))
+    packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(K3, cin, cout, kc_in)), dtype=torch.uint8, device="cuda")
+    _lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), K3, cin, cout, kc_in, wmul, packed.data_ptr(), _lib.cur_stream()))
+    Xh = h2_pack(X, kc_in)
+    Rh = None if R is None else h2_pack(R, kc_out, ld_extra=16)
+    Yh = torch.full((n_out, 2 * cout + 8), float("nan"), dtype=torch.float16, device="cuda")
+    ws_bytes = int(L.imf_sparse_conv_h2_workspace_bytes(n_out, cout)) if split else 0
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    sc = (scale / wmul).contiguous()
+    _lib.check(L.imf_sparse_conv_h2_fwd(Xh.data_ptr(), Xh.stride(0), kc_in, packed.data_ptr(), nbr.data_ptr(), None, n_out, K3, cin,
+                                        cout, sc.data_ptr(), shift.data_ptr(), _lib.ptr(Rh), 0 if Rh is None else Rh.stride(0), kc_out,
+                                        int(relu), Yh.data_ptr(), Yh.stride(0), kc_out, ws.data_ptr() if split else None, ws_bytes,
+                                        err.data_ptr(), _lib.cur_stream()))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    return h2_unpack(Yh, cout, kc_out).cpu()
+
+
+def test_h2_pack_unpack_roundtrip_keeps_22_bits():
+    g = torch.Generator().manual_seed(3)
+    X = (torch.randn(1000, 96, generator=g) * torch.logspace(-3, 3, 96)).cuda()
+    for kc in (32,):
+        back = h2_unpack(h2_pack(X, kc), 96, kc)
+        assert bool(((back - X).abs() <= torch.maximum(X.abs() * 2.0 ** -21, torch.tensor(6.1e-8, device="cuda"))).all())
+    X = torch.randn(777, 128, generator=g).cuda()
+    back = h2_unpack(h2_pack(X, 64, ld_extra=24), 128, 64)
+    assert bool(((back - X).abs() <= torch.maximum(X.abs() * 2.0 ** -21, torch.tensor(6.1e-8, device="cuda"))).all())
+
+
+@pytest.mark.parametrize("t_in,t_out,tr,cin,cout", [
+    (1, 1, False, 32, 32), (1, 1, False, 64, 64), (1, 2, False, 32, 64), (2, 2, False, 64, 64), (2, 4, False, 64, 128),
+    (4, 4, False, 128, 128), (4, 8, False, 128, 256), (8, 8, False, 256, 256), (8, 4, True, 256, 128), (4, 2, True, 256, 64),
+    (2, 1, True, 128, 64)])
+@pytest.mark.parametrize("split", [False, True])
+def test_h2_tensor_core_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout, split):
+    """tcgen05 kind::f16 implicit GEMM on fp16 hi/lo operands (3 products): fp32-class accuracy, tolerance 1e-4 as above."""
+    coords, ocm, cm = frag
+    g = torch.Generator().manual_seed(cin * 1000 + cout + t_in)
+    n_in, n_out = len(ocm.get(t_in)), len(ocm.get(t_out))
+    X = torch.randn(n_in, cin, generator=g)
+    W = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    R = torch.randn(n_out, cout, generator=g)
+    ref = torch.relu(sparse_ops.conv_forward(X, W, ocm.table(t_in, t_out, 3, tr)) * scale + shift + R)
+    out = run_conv_h2(X.cuda(), W.cuda(), cm.table(t_in, t_out, 3, tr), n_out, scale.cuda(), shift.cuda(), R.cuda(), True, split)
+    close(out, ref, H2_RTOL)
+
+
+def test_h2_conv_equals_simt_conv_c2_size():
+    coords, _ = synthetic.make_fragment(50000, 0.025, 0)
+    from imfnet_b200.sparse import CoordinateManager
+    cm = CoordinateManager(torch.from_numpy(coords).cuda())
+    nbr = cm.table(1, 1, 3, False)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.randn(50000, 64, device="cuda", generator=g)
+    W = torch.randn(27, 64, 64, device="cuda", generator=g) / 40
+    a = run_conv(X, W, nbr, 50000)
+    one, zero = torch.ones(64, device="cuda"), torch.zeros(64, device="cuda")
+    b = run_conv_h2(X, W, nbr, 50000, one, zero, split=False)
+    close(b, a, H2_RTOL)
+
+
+def test_h2_first_conv_and_tail(frag):
+    coords, ocm, cm = frag
+    g = torch.Generator().manual_seed(11)
+    n = len(coords)
+    L = _lib.lib()
+    X = torch.rand(n, 1, generator=g) + 0.5
+    W = torch.randn(125, 1, 32, generator=g) / 11
+    scale, shift = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.1
+    ref = sparse_ops.conv_forward(X, W, ocm.table(1, 1, 5, False)) * scale + shift
+    lvl = cm.level(1)
+    Yh = torch.zeros(n, 64, dtype=torch.float16, device="cuda")
+    X_d, W_d, sc_d, sh_d = X.cuda(), W.cuda(), scale.cuda(), shift.cuda()
+    _lib.check(L.imf_conv_first_h2_fwd(X_d.data_ptr(), 1, 1, W_d.data_ptr(), lvl.coords.data_ptr(), None, n, lvl.table.data_ptr(),
+                                       lvl.capacity, 5, 1, 32, sc_d.data_ptr(), sh_d.data_ptr(), 0, Yh.data_ptr(), 64, 32,
+                                       _lib.cur_stream()))
+    close(h2_unpack(Yh, 32, 32).cpu(), ref, H2_RTOL)
+    # tail on a two-section h2 matrix [64 | 32], scattered through out_row
+    Xt = torch.randn(n, 96, generator=g)
+    W1, W2, b2 = torch.randn(96, 64, generator=g) / 10, torch.randn(64, 32, generator=g) / 8, torch.randn(32, generator=g)
+    ref = torch.relu(Xt @ W1) @ W2 + b2
+    ref = ref / torch.norm(ref, p=2, dim=1, keepdim=True)
+    Ha, Hb = h2_pack(Xt[:, :64].contiguous().cuda(), 64), h2_pack(Xt[:, 64:].contiguous().cuda(), 32)
+    H = torch.cat([Ha, Hb], dim=1).contiguous()
+    perm = torch.randperm(n, generator=g).to(torch.int32)
+    Y = torch.empty(n, 32, device="cuda")
+    W1_d, W2_d, b2_d, perm_d = W1.cuda(), W2.cuda(), b2.cuda(), perm.cuda()
+    _lib.check(L.imf_pointwise_tail_h2_fwd(H.data_ptr(), 192, 96, 64, 64, 32, W1_d.data_ptr(), 64, W2_d.data_ptr(), b2_d.data_ptr(),
+                                           32, None, n, 1, perm_d.data_ptr(), Y.data_ptr(), 32, _lib.cur_stream()))
+    torch.cuda.synchronize()
+    out = torch.empty_like(ref)
+    out[:] = Y.cpu()
+    close(out[perm.long()], ref, H2_RTOL)
 
 
 def test_tensor_core_conv_equals_simt_conv_c2_size():

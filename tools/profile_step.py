@@ -33,7 +33,6 @@ with torch.no_grad():
     for i in range(10):
         c, f, im = frags[i % 8]
         model(ME.SparseTensor(f, coordinates=c), im)
-    model._plan.conv_impl = args.impl
     torch.cuda.synchronize()
     host, dev = [], []
     for i in range(args.iters):
