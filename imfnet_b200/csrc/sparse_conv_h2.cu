@@ -40,12 +40,25 @@ struct H2Cfg {
   static constexpr int NS = NS_FIT > 6 ? 6 : NS_FIT;
 };
 
-__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+// 16-byte asynchronous copy global -> shared; a negative `row` writes zeros instead (ignore-src form: no address fix-ups).
+__device__ __forceinline__ void cp_async16_row(uint32_t smem_dst, const void* gmem_src, int row) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.lt.s32 p, %2, 0;\n"
+      "cp.async.cg.shared.global [%0], [%1], 16, p;\n"
+      "}\n" ::"r"(smem_dst),
+      "l"(gmem_src), "r"(row)
+      : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ int lds_s32(uint32_t smem_addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(smem_addr));
+  return v;
+}
 
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
   return (1u << 4) /*D = f32*/ | (0u << 7) /*A = f16*/ | (0u << 10) /*B = f16*/ | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -105,7 +118,7 @@ __global__ void __launch_bounds__(288, 1) k_sparse_conv_h2(const __half* __restr
                                                            int K3, int nchunks, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, const __half* __restrict__ R, int ldr,
                                                            int kc_r, int relu, __half* __restrict__ Y, int ldy, int kc_out,
-                                                           float* __restrict__ P, int cout_total, int* err) {
+                                                           float* __restrict__ P, int cout_total, int* err, int dbg, long long* __restrict__ trace) {
   using Cfg = H2Cfg<BN, KC>;
   constexpr int NS = Cfg::NS;
   extern __shared__ unsigned char smem_dyn[];
@@ -123,15 +136,19 @@ __global__ void __launch_bounds__(288, 1) k_sparse_conv_h2(const __half* __restr
   if (row0 >= n_out) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntn = gridDim.z, zt = blockIdx.z;
+  if (blockIdx.x | blockIdx.y | blockIdx.z) trace = nullptr;            // profiling hook: CTA 0 only
+#define H2_TRACE(slot) do { if (trace) trace[slot] = clock64(); } while (0)
+  if (tid == 0) H2_TRACE(0);
 
   if (tid == 0) {
     kmask_s = 0u;
-    for (int s = 0; s < NS; ++s) { tc::mbar_init(&full_bar[s], 257); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NS; ++s) { tc::mbar_init(&full_bar[s], 9); tc::mbar_init(&empty_bar[s], 1); }   // full: 8 producer warps + expect_tx
     tc::mbar_init(&acc_bar, 1);
     tc::fence_barrier_init();
   }
   if (warp == 8) { tc::tmem_alloc(&tmem_base_s, BN < 32 ? 32 : BN); tc::tmem_relinquish(); }
   __syncthreads();
+  if (tid == 0) H2_TRACE(1);
   {
     unsigned local = 0u;
     const int total = kBM * K3;
@@ -147,6 +164,7 @@ __global__ void __launch_bounds__(288, 1) k_sparse_conv_h2(const __half* __restr
     if (lane == 0 && local) atomicOr(&kmask_s, local);
   }
   __syncthreads();
+  if (tid == 0) H2_TRACE(2);
   if (tid == 0) {
     unsigned m = kmask_s;
     int c = 0;
@@ -157,6 +175,7 @@ __global__ void __launch_bounds__(288, 1) k_sparse_conv_h2(const __half* __restr
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem_d = tmem_base_s;
+  if (tid == 0) H2_TRACE(3);
   const int nst_tile = nk_s * nchunks;
   const int per = (nst_tile + (int)gridDim.y - 1) / (int)gridDim.y;
   const int st_begin = min(nst_tile, (int)blockIdx.y * per);
@@ -164,53 +183,61 @@ __global__ void __launch_bounds__(288, 1) k_sparse_conv_h2(const __half* __restr
 
   if (warp < 8) {
     // ------------------------------ gather producers ------------------------------
+    // Thread constants: KC=64: 16 lanes per row (hi 8 x 16 B | lo 8 x 16 B), rows r0 + 16*it; KC=32: 8 lanes per row, rows r0 + 32*it.
+    constexpr int NIT = (KC == 64) ? 8 : 4;
+    constexpr int RSTEP = (KC == 64) ? 16 : 32;
+    const int r0 = (KC == 64) ? (tid >> 4) : (tid >> 3);
+    const int c = tid & 7, part = (KC == 64) ? ((tid >> 3) & 1) : 0;
     const uint32_t smem_base = tc::smem_u32(smem);
+    const uint32_t dst0 = part * kImg + tc::sw128_offset(r0, c);            // + it * RSTEP * 128 (r0 & 7 is unchanged by +16 / +32)
+    const uint32_t nbr_addr0 = tc::smem_u32(nbr_s) + (uint32_t)(r0 * K3) * 4u;
+    const char* xthr = reinterpret_cast<const char*>(X + part * 64 + c * 8);
+    const unsigned ldx_bytes = (unsigned)ldx * 2u;
+    int kidx = st_begin / nchunks, chunk = st_begin % nchunks;
     for (int i = 0; i < nst + kLook; ++i) {
       if (i < nst) {
         const int s = i % NS;
         const uint32_t ph = (uint32_t)(i / NS) & 1u;
-        const int st = st_begin + i;
-        const int k = klist_s[st / nchunks];
-        const int chunk = st % nchunks;
+        const int k = klist_s[kidx];
+        int src[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) src[it] = lds_s32(nbr_addr0 + (uint32_t)((it * RSTEP * K3 + k) * 4));
         tc::mbar_wait(&empty_bar[s], ph ^ 1u, err, 1);
+        if (tid == 0) H2_TRACE(16 + 4 * i);
         const uint32_t stg = smem_base + s * Cfg::STAGE_BYTES;
         if (tid == 0) {
-          tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::W_BYTES);
-          tc::bulk_g2s(smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES,
-                       Wp + (((size_t)k * nchunks + chunk) * ntn + zt) * Cfg::W_BYTES, Cfg::W_BYTES, &full_bar[s]);
-        }
-        if (KC == 64) {
-          const __half* xc = X + chunk * 128;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int id = it * 256 + tid, r = id >> 4, l = id & 15, part = l >> 3, c = l & 7;
-            const int src = nbr_s[r * K3 + k];
-            const __half* g = (src >= 0) ? xc + (size_t)src * ldx + part * 64 + c * 8 : X;
-            cp_async16_zfill(stg + part * kImg + tc::sw128_offset(r, c), g, src >= 0 ? 16u : 0u);
-          }
-        } else {
-          const __half* xc = X + chunk * 64;
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int id = it * 256 + tid, r = id >> 3, c = id & 7;
-            const int src = nbr_s[r * K3 + k];
-            const __half* g = (src >= 0) ? xc + (size_t)src * ldx + c * 8 : X;
-            cp_async16_zfill(stg + tc::sw128_offset(r, c), g, src >= 0 ? 16u : 0u);
+          if (dbg & 1) {
+            tc::mbar_arrive(&full_bar[s]);
+          } else {
+            tc::mbar_arrive_expect_tx(&full_bar[s], Cfg::W_BYTES);
+            tc::bulk_g2s(smem + s * Cfg::STAGE_BYTES + Cfg::A_BYTES,
+                         Wp + (((size_t)k * nchunks + chunk) * ntn + zt) * Cfg::W_BYTES, Cfg::W_BYTES, &full_bar[s]);
           }
         }
+        const char* xc = xthr + chunk * (4 * KC);
+        if (!(dbg & 2))
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)      // absent neighbour: the (valid) address of row 0 is passed but ignored
+          cp_async16_row(stg + dst0 + it * (RSTEP * 128), xc + (unsigned long long)((unsigned)max(src[it], 0)) * ldx_bytes, src[it]);
+        if (++chunk == nchunks) { chunk = 0; ++kidx; }
+        if (tid == 0) H2_TRACE(16 + 4 * i + 1);
       }
       cp_async_commit();
       if (i >= kLook) {
         cp_async_wait<kLook>();            // this thread's copies of stage i-kLook have landed
+        if (tid == 0) H2_TRACE(16 + 4 * (i - kLook) + 2);
         tc::fence_proxy_async();
-        tc::mbar_arrive(&full_bar[(i - kLook) % NS]);
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&full_bar[(i - kLook) % NS]);
       }
     }
     // ------------------------------ epilogue ------------------------------
+    if (tid == 0) H2_TRACE(4);
     if (nst > 0) {
       tc::mbar_wait(&acc_bar, 0u, err, 3);
       tc::tc_fence_after_sync();
     }
+    if (tid == 0) H2_TRACE(5);
     const int lane_base = (warp & 3) * 32;
     const int row = row0 + lane_base + lane;
     constexpr int CW = BN / 2;                               // columns per warp-group half
@@ -250,6 +277,7 @@ __global__ void __launch_bounds__(288, 1) k_sparse_conv_h2(const __half* __restr
       }
     }
     if (big && err) atomicOr(err, 0x10000);
+    if (tid == 0) H2_TRACE(6);
   } else {
     // ------------------------------ MMA issuer ------------------------------
     constexpr uint32_t idesc = idesc_f16(kBM, BN);
@@ -258,7 +286,11 @@ __global__ void __launch_bounds__(288, 1) k_sparse_conv_h2(const __half* __restr
       const uint32_t ph = (uint32_t)(i / NS) & 1u;
       tc::mbar_wait(&full_bar[s], ph, err, 2);
       tc::tc_fence_after_sync();
-      if (lane == 0) {
+      if (lane == 0) H2_TRACE(16 + 4 * i + 3);
+      if (lane == 0 && (dbg & 4)) {
+        tc::mma_commit(&empty_bar[s]);
+        if (i == nst - 1) tc::mma_commit(&acc_bar);
+      } else if (lane == 0) {
         const uint32_t a0 = tc::smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t w0 = a0 + Cfg::A_BYTES, w1 = w0 + Cfg::W_IMG;
         if (KC == 64) {
@@ -288,6 +320,8 @@ __global__ void __launch_bounds__(288, 1) k_sparse_conv_h2(const __half* __restr
   tc::tc_fence_before_sync();
   __syncthreads();
   if (warp == 8) tc::tmem_dealloc(tmem_d, BN < 32 ? 32 : BN);
+  if (tid == 0) H2_TRACE(7);
+#undef H2_TRACE
 }
 
 // Y(h2) = act( (sum_z P[z]) * scale + shift (+ R) ) for the split variant; one thread per (row, 16 channels).
@@ -380,6 +414,8 @@ __global__ void __launch_bounds__(256) k_h2_unpack(const __half* __restrict__ H,
   X[(size_t)row * ldx + c] = __half2float(p[0]) + __half2float(p[KC]);
 }
 
+extern int g_h2_debug_fwd;
+extern long long* g_h2_trace;
 template <int BN, int KC>
 int launch_h2(const __half* X, int ldx, const void* Wp, const int* nbr, const int* n_ptr, int n_max, int K3, int Cin, int Cout,
               const float* scale, const float* shift, const __half* R, int ldr, int kc_r, int relu, __half* Y, int ldy, int kc_out,
@@ -402,7 +438,7 @@ int launch_h2(const __half* X, int ldx, const void* Wp, const int* nbr, const in
   float* P = splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;
   dim3 grid(tiles, splits, ntn);
   k_sparse_conv_h2<BN, KC><<<grid, 288, smem, stream>>>(X, ldx, reinterpret_cast<const unsigned char*>(Wp), nbr, n_ptr, n_max, K3, nchunks,
-                                                        scale, shift, R, ldr, kc_r, relu, Y, ldy, kc_out, P, Cout, err);
+                                                        scale, shift, R, ldr, kc_r, relu, Y, ldy, kc_out, P, Cout, err, g_h2_debug_fwd, g_h2_trace);
   IMF_CHECK_LAUNCH();
   if (splits > 1) {
     const long long total = (long long)n_max * (Cout / 16);
@@ -415,7 +451,25 @@ int launch_h2(const __half* X, int ldx, const void* Wp, const int* nbr, const in
 
 inline int h2_bn(int Cout) { return Cout > 128 ? 128 : Cout; }
 
+int g_h2_debug_fwd = 0;
+long long* g_h2_trace = nullptr;
+
 }  // namespace
+
+// Profiling hook: bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs of imf_sparse_conv_h2_fwd (results are then
+// meaningless); used by tools/conv_microbench.py to attribute the kernel time.  0 = normal operation.
+extern "C" int imf_debug_conv_flags(int32_t flags) {
+  const int old = g_h2_debug_fwd;
+  g_h2_debug_fwd = flags;
+  return old;
+}
+// Profiling hook: device buffer of >= 16 + 4*stages int64 that CTA (0,0,0) of imf_sparse_conv_h2_fwd fills with clock64() stamps
+// (slots: 0 start, 1 barriers+TMEM ready, 2 neighbour rows staged, 3 stage list ready, 4 producer loop done, 5 accumulator ready,
+// 6 epilogue done, 7 exit; 16+4i+{0 slot acquired, 1 copies issued, 2 copies landed, 3 MMA warp saw full}).  NULL = off.
+extern "C" int imf_debug_conv_trace(long long* trace) {
+  g_h2_trace = trace;
+  return IMF_OK;
+}
 
 extern "C" int imf_h2_pack(const float* X, int32_t ldx, int32_t n, int32_t C, int32_t KC, void* H, int32_t ldh, int32_t* err,
                            cudaStream_t stream) {

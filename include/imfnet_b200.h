@@ -125,6 +125,13 @@ int imf_conv_first_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W,
                        int32_t Cout, const float* scale, const float* shift, int32_t relu, float* Y, int32_t ldy,
                        imf_stream_t stream);
 
+/* Profiling hook (tools/conv_microbench.py): bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs of
+ * imf_sparse_conv_h2_fwd, whose results are then meaningless.  Returns the previous value; 0 = normal operation. */
+int imf_debug_conv_flags(int32_t flags);
+/* Profiling hook: device int64 buffer (>= 16 + 4*stages entries) that CTA 0 of imf_sparse_conv_h2_fwd fills with clock64()
+ * stamps of its pipeline events (slot map in csrc/sparse_conv_h2.cu); NULL switches it off. */
+int imf_debug_conv_trace(long long* trace);
+
 /* imf_conv_first_fwd writing an h2 matrix (ldy in halves, chunk width kc_out). */
 int imf_conv_first_h2_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords, const int32_t* n_dev,
                           int32_t n_max, const void* table, long long capacity, int32_t kernel_size, int32_t tensor_stride,
