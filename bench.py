@@ -124,8 +124,9 @@ def run_reference(args, rank, world):
 
 # ------------------------------------------------------------------------------------------------------------------
 def dominant_kernel_roofline(model, frag, flush):
-    """block2_tr-shaped convolution (64->64, 3^3, stride-1 level): the largest single launch of the forward
-    (179.6 MB algorithmic bytes at C2).  Timed live with CUDA events, L2 flushed between launches."""
+    """block2_tr-shaped convolution (64->64, 3^3, stride-1 level, BatchNorm + ReLU folded): the largest single launch of
+    the forward (179.6 MB algorithmic bytes at C2), run through the same entry point and packed weights the
+    forward uses (imf_sparse_conv_h2_fwd).  Timed live with CUDA events on the launching stream, L2 flushed between launches."""
     from imfnet_b200 import _lib
     from imfnet_b200.sparse import CoordinateManager
     L = _lib.lib()
@@ -133,31 +134,37 @@ def dominant_kernel_roofline(model, frag, flush):
     cm = CoordinateManager(coords)
     nbr = cm.table(1, 1, 3, False)
     n = len(coords)
-    conv = model.block2_tr.conv1
+    conv, packed, scale, shift, kci = model._plan.conv["block2_tr.conv1"]
     cin, cout = conv.in_channels, conv.out_channels
-    X = torch.randn(n, cin, device="cuda")
-    Y = torch.empty(n, cout, device="cuda")
-    sc, sh = model.block2_tr.norm1.folded()
-    pairs = int((nbr >= 0).sum())
-    alg_bytes = 4 * pairs * cin + 8 * pairs + 4 * 27 * cin * cout + 4 * n * cout
+    kco = 64 if cout % 64 == 0 else 32
     s = torch.cuda.current_stream().cuda_stream
+    X = torch.randn(n, cin, device="cuda")
+    Xh = torch.empty(n, 2 * cin, dtype=torch.float16, device="cuda")
+    _lib.check(L.imf_h2_pack(X.data_ptr(), cin, n, cin, kci, Xh.data_ptr(), 2 * cin, None, s))
+    Yh = torch.empty(n, 2 * cout, dtype=torch.float16, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    pairs = int((nbr >= 0).sum())
+    # gathered inputs + in/out indices + weights once + output (activations are 4 bytes/channel: fp16 hi + lo)
+    alg_bytes = 4 * pairs * cin + 8 * pairs + 4 * 27 * cin * cout + 4 * n * cout
     times = []
-    for i in range(13):
+    for i in range(23):
         flush()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(L.imf_sparse_conv_fwd(X.data_ptr(), cin, conv.kernel.data_ptr(), nbr.data_ptr(), None, n, 27, cin, cout,
-                                         sc.data_ptr(), sh.data_ptr(), None, 0, 1, Y.data_ptr(), cout, s))
+        _lib.check(L.imf_sparse_conv_h2_fwd(Xh.data_ptr(), 2 * cin, kci, packed.data_ptr(), nbr.data_ptr(), None, n, 27, cin, cout,
+                                            scale.data_ptr(), shift.data_ptr(), None, 0, 0, 1, Yh.data_ptr(), 2 * cout, kco,
+                                            None, 0, err.data_ptr(), s))
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:
             times.append(e0.elapsed_time(e1))
+    assert int(err.item()) == 0
     ms = float(np.mean(times))
     peak, how = load_peaks()
     achieved = alg_bytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": f"k_sparse_conv 3x3x3 {cin}->{cout} @ {n} voxels ({pairs} pairs)", "achieved": achieved,
+    return {"bound": "hbm", "kernel": f"k_sparse_conv_h2<64,64> 3x3x3 {cin}->{cout} @ {n} voxels ({pairs} pairs)", "achieved": achieved,
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "alg_bytes_per_launch": alg_bytes,
-            "ms_per_launch": ms, "peak_source": how}
+            "ms_per_launch": ms, "flops_per_launch": 2 * pairs * cin * cout, "peak_source": how}
 
 
 def run_ours(args, rank, world, local_rank):

@@ -1,0 +1,18 @@
+#!/bin/bash
+# One GPU-box call: parity tests, bench, step profile, conv microbench, ncu launch list, ncu full capture of the top kernel.
+# Usage (from the repo root on the box): bash tools/gpu_round.sh <tag>
+TAG=${1:-run}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
+timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
+tail -c 3000 $OUT/bench.json
+timeout 300 python tools/profile_step.py > $OUT/profile_step.txt 2>&1; cat $OUT/profile_step.txt
+timeout 300 python tools/conv_microbench.py --flags 0,1,2,4,6,7 > $OUT/conv_microbench_64.txt 2>&1; head -8 $OUT/conv_microbench_64.txt
+timeout 300 python tools/conv_microbench.py --cin 32 --cout 32 --flags 0,2,4 2>&1 | head -4 > $OUT/conv_microbench_32.txt; cat $OUT/conv_microbench_32.txt
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/launches.csv \
+    python bench.py --profile --steps 2 --warmup 2 > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sparse_conv_h2 -s 4 -c 2 -o $OUT/prof_conv_h2 \
+    python tools/conv_microbench.py --flags 0 --reps 3 > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
+ls -la $OUT
