@@ -46,6 +46,7 @@ SIGNATURES = {
                                         _i32, _p, _sz, _p, _p]),
     "imf_debug_conv_flags": (C.c_int, [_i32]),
     "imf_debug_conv_trace": (C.c_int, [_p]),
+    "imf_debug_gather4": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _p, _i32, _i32, _p, _p]),
     "imf_conv_first_h2_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p]),
     "imf_pointwise_tail_h2_fwd": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _p, _i32, _p]),
     "imf_conv_first_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _p]),

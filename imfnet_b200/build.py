@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {s}")
     if jobs or force or _stale(LIB, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

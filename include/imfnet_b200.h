@@ -132,6 +132,12 @@ int imf_debug_conv_flags(int32_t flags);
  * stamps of its pipeline events (slot map in csrc/sparse_conv_h2.cu); NULL switches it off. */
 int imf_debug_conv_trace(long long* trace);
 
+/* Self-test hook of the TMA path (tools/tma_selftest.py): gathers rows idx[0..127] (device int32; negative or >= n_rows gives a zero
+ * row) of the fp16 matrix X [n_rows, ld], columns [col, col+64), into a 128-byte-swizzled shared tile with tile::gather4, copies
+ * the raw tile (16 KB) to `raw`, and stores it with a tiled TMA store to rows [out_row, out_row+128) of O [o_rows, ld] (clipped). */
+int imf_debug_gather4(const void* X, int32_t ld, int32_t n_rows, const int32_t* idx, int32_t col, int32_t box_rows, void* raw, void* O,
+                      int32_t o_rows, int32_t out_row, int32_t* err, imf_stream_t stream);
+
 /* imf_conv_first_fwd writing an h2 matrix (ldy in halves, chunk width kc_out). */
 int imf_conv_first_h2_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords, const int32_t* n_dev,
                           int32_t n_max, const void* table, long long capacity, int32_t kernel_size, int32_t tensor_stride,
