@@ -197,6 +197,29 @@ __global__ void k_kernel_map(const int4* __restrict__ out_coords, const int* __r
   nbr[idx] = r;
 }
 
+// Offset-major neighbour table for the TMA-gather convolution (sparse_conv_g4.cu): nbr_t[k*ld_n + o]; rows o in
+// [n, roundup128(n)) are -1 (they pad the last tile); tile_mask[o/128] gets bit k when any row of that 128-row tile has a
+// neighbour at offset k (the caller zeroes tile_mask).  One CTA = one (tile, offset).
+__global__ void __launch_bounds__(128) k_kernel_map_t(const int4* __restrict__ out_coords, const int* __restrict__ n_ptr, int n_max,
+                                                      const ImfSlot* __restrict__ table, unsigned long long mask, int K, int scale,
+                                                      int* __restrict__ nbr_t, int ld_n, unsigned* __restrict__ tile_mask) {
+  const int n = imf_count(n_ptr, n_max);
+  const int tile = blockIdx.x, k = blockIdx.y;
+  if (tile * 128 >= n) return;
+  const int o = tile * 128 + threadIdx.x;
+  int r = -1;
+  if (o < n) {
+    const int h = K / 2;
+    const int kx = k % K - h, ky = (k / K) % K - h, kz = k / (K * K) - h;
+    const int4 c = out_coords[o];
+    const int x = c.y + kx * scale, y = c.z + ky * scale, z = c.w + kz * scale;
+    if (imf_coord_in_range(c.x, x, y, z)) r = imf_table_lookup(table, mask, imf_pack_key(c.x, x, y, z));
+  }
+  if (o < ld_n) nbr_t[(size_t)k * ld_n + o] = r;
+  const unsigned any = __ballot_sync(0xffffffffu, r >= 0);
+  if ((threadIdx.x & 31) == 0 && any) atomicOr(tile_mask + tile, 1u << k);
+}
+
 // xyz (float64 [N,3]) -> int32 (b, floor(x/voxel), floor(y/voxel), floor(z/voxel)).  IEEE double division and
 // floor are exact, so this equals numpy's np.floor(xyz / voxel_size) (/root/reference/util/misc.py:82).
 __global__ void k_quantize_points(const double* __restrict__ xyz, int n, double voxel, int batch, int4* __restrict__ coords) {
@@ -303,6 +326,24 @@ extern "C" int imf_kernel_map(const int32_t* out_coords, const int32_t* n_out_de
   k_kernel_map<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const int4*>(out_coords), n_out_dev, n_out_max,
                                                      reinterpret_cast<const ImfSlot*>(table_in),
                                                      (unsigned long long)capacity - 1, kernel_size, scale, nbr);
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
+}
+
+extern "C" int imf_kernel_map_t(const int32_t* out_coords, const int32_t* n_out_dev, int32_t n_out_max, const void* table_in,
+                                long long capacity, int32_t kernel_size, int32_t scale, int32_t* nbr_t, int32_t ld_n,
+                                uint32_t* tile_mask, cudaStream_t stream) {
+  IMF_CHECK_ARG(is_pow2(capacity) && table_in != nullptr && n_out_max >= 0);
+  IMF_CHECK_ARG(kernel_size >= 1 && (kernel_size & 1) == 1 && kernel_size <= 3);
+  IMF_CHECK_ARG(ld_n % 4 == 0 && ld_n >= ((n_out_max + 31) & ~31));
+  if (n_out_max == 0) return IMF_OK;
+  IMF_CHECK_ARG(out_coords != nullptr && nbr_t != nullptr && tile_mask != nullptr);
+  const int tiles = (n_out_max + 127) / 128;
+  IMF_CHECK_CUDA(cudaMemsetAsync(tile_mask, 0, (size_t)(tiles + 1) * sizeof(uint32_t), stream));
+  dim3 grid(tiles, kernel_size * kernel_size * kernel_size);
+  k_kernel_map_t<<<grid, 128, 0, stream>>>(reinterpret_cast<const int4*>(out_coords), n_out_dev, n_out_max,
+                                           reinterpret_cast<const ImfSlot*>(table_in), (unsigned long long)capacity - 1, kernel_size,
+                                           scale, nbr_t, ld_n, tile_mask);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }

@@ -150,6 +150,23 @@ class CoordinateManager:
             self._tables[key] = nbr
         return self._tables[key]
 
+    def table_t(self, t_in: int, t_out: int, K: int, transposed: bool):
+        """Offset-major neighbour table for the TMA-gather convolution: (nbr_t int32 [K^3, ld_n], ld_n, tile_mask uint32);
+        see include/imfnet_b200.h::imf_kernel_map_t."""
+        key = ("t", t_in, t_out, K, bool(transposed))
+        if key not in self._tables:
+            L = _lib.lib()
+            src, dst = self.levels[t_in], self.levels[t_out]
+            scale = -t_out if transposed else t_in
+            ld_n = (dst.n + 127) // 128 * 128
+            nbr_t = torch.empty((K ** 3, max(ld_n, 128)), dtype=torch.int32, device=self.device)
+            tile_mask = torch.empty(ld_n // 128 + 1, dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(L.imf_kernel_map_t(_lib.ptr(dst.coords), None, dst.n, _lib.ptr(src.table), src.capacity, K, scale,
+                                              _lib.ptr(nbr_t), nbr_t.stride(0), _lib.ptr(tile_mask), _lib.cur_stream()))
+            self._tables[key] = (nbr_t, nbr_t.stride(0), tile_mask)
+        return self._tables[key]
+
     def batch_segments(self, t: int, num_batches: int):
         """Host list seg[0..B] of row offsets per batch item at tensor stride t (rows are batch-sorted)."""
         key = (t, num_batches)

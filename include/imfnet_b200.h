@@ -66,6 +66,14 @@ int imf_stride_map(const int32_t* coords_in, const int32_t* n_in_dev, int32_t n_
 int imf_kernel_map(const int32_t* out_coords, const int32_t* n_out_dev, int32_t n_out_max, const void* table_in,
                    long long capacity, int32_t kernel_size, int32_t scale, int32_t* nbr, imf_stream_t stream);
 
+/* The same neighbour table in offset-major form for the TMA-gather convolution: nbr_t[k*ld_n + o] (ld_n % 4 == 0,
+ * ld_n >= n_out_max rounded up to 32; rows in [n, roundup128(n)) are written as -1), plus tile_mask[o/128] (uint32, at least
+ * ceil(n_out_max/128)+1 entries, zeroed here) whose bit k says that some row of that 128-row tile has a neighbour at offset k.
+ * kernel_size in {1, 3}. */
+int imf_kernel_map_t(const int32_t* out_coords, const int32_t* n_out_dev, int32_t n_out_max, const void* table_in,
+                     long long capacity, int32_t kernel_size, int32_t scale, int32_t* nbr_t, int32_t ld_n, uint32_t* tile_mask,
+                     imf_stream_t stream);
+
 /* coords[i] = (batch_index, floor(xyz[i]/voxel_size)) in float64, as util/misc.py:82 computes on the host. */
 int imf_quantize_points(const double* xyz, int32_t n, double voxel_size, int32_t batch_index, int32_t* coords,
                         imf_stream_t stream);
@@ -116,6 +124,20 @@ int imf_sparse_conv_h2_fwd(const void* X, int32_t ldx, int32_t kc_in, const void
                            int32_t n_out_max, int32_t kernel_volume, int32_t Cin, int32_t Cout, const float* scale, const float* shift,
                            const void* residual, int32_t ldr, int32_t kc_r, int32_t relu, void* Y, int32_t ldy, int32_t kc_out,
                            void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+
+/* "g4" kernel of the h2 tier (csrc/sparse_conv_g4.cu): same operation, data format and packed weights as imf_sparse_conv_h2_fwd, but
+ * persistent (one CTA per SM, grid independent of the row count), neighbour rows fetched by TMA tile::gather4 from the offset-major
+ * table of imf_kernel_map_t, output written by tiled TMA stores.  n_in_rows / n_y_rows = rows of the X / Y allocations (tensor-map
+ * extents; n_y_rows >= n_out_max).  workspace (optional, imf_sparse_conv_g4_workspace_bytes) enables the split mode of small levels. */
+size_t imf_sparse_conv_g4_workspace_bytes(int32_t Cout);
+int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t n_in_rows, int32_t kc_in, const void* packed, const int32_t* nbr_t,
+                           int32_t ld_n, const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max, int32_t kernel_volume,
+                           int32_t Cin, int32_t Cout, const float* scale, const float* shift, const void* residual, int32_t ldr,
+                           int32_t kc_r, int32_t relu, void* Y, int32_t ldy, int32_t n_y_rows, int32_t kc_out, void* workspace,
+                           size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+/* Profiling hook: device int64 buffer (>= 160 entries) filled by CTA 0 with clock64() stamps (slot map in the source), and an
+ * override of the CTAs per output-channel tile (0 = one per SM).  NULL / 0 switch both off. */
+int imf_debug_conv_g4_trace(long long* trace, int32_t grid);
 
 /* First layer (conv1, model/resunet.py:42-49,168): K in {1,3,5}, Cin in {1,3,6} (ones / rgb / rgb+normal,
  * util/misc.py:66-77), Cout in {32,64,128}; neighbours are

@@ -170,6 +170,113 @@ def test_h2_tensor_core_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout, sp
     close(out, ref, H2_RTOL)
 
 
+def run_conv_g4(X, W, tab, n_out, scale, shift, R=None, relu=False, split=True, kc_out=None, n_dev=None, extra_rows=0):
+    """fp32 in/out wrapper of the TMA-gather kernel: pack -> conv -> unpack.  tab = CoordinateManager.table_t(...)."""
+    L = _lib.lib()
+    nbr_t, ld_n, tile_mask = tab
+    K3, cin, cout = W.shape
+    kc_in = 64 if cin % 64 == 0 else 32
+    kc_out = kc_out or (64 if cout % 64 == 0 else 32)
+    wmul = 2.0 ** np.floor(np.log2(2048.0 / float(W.abs().max())))
+    packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(K3, cin, cout, kc_in)), dtype=torch.uint8, device="cuda")
+    _lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), K3, cin, cout, kc_in, wmul, packed.data_ptr(), _lib.cur_stream()))
+    Xh = h2_pack(X, kc_in, ld_extra=8)
+    Rh = None if R is None else h2_pack(R, kc_out, ld_extra=16)
+    Yh = torch.full((n_out + extra_rows, 2 * cout + 8), float("nan"), dtype=torch.float16, device="cuda")
+    ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(cout)) if split else 0
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    sc = (scale / wmul).contiguous()
+    _lib.check(L.imf_sparse_conv_g4_fwd(Xh.data_ptr(), Xh.stride(0), Xh.shape[0], kc_in, packed.data_ptr(), nbr_t.data_ptr(), ld_n,
+                                        tile_mask.data_ptr(), _lib.ptr(n_dev), n_out, K3, cin, cout, sc.data_ptr(), shift.data_ptr(),
+                                        _lib.ptr(Rh), 0 if Rh is None else Rh.stride(0), kc_out, int(relu), Yh.data_ptr(), Yh.stride(0),
+                                        Yh.shape[0], kc_out, ws.data_ptr() if split else None, ws_bytes, err.data_ptr(),
+                                        _lib.cur_stream()))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    return h2_unpack(Yh, cout, kc_out).cpu()
+
+
+@pytest.mark.parametrize("t_in,t_out,tr", [(1, 1, False), (1, 2, False), (4, 8, False), (8, 4, True), (2, 1, True)])
+def test_offset_major_table_matches_oracle(frag, t_in, t_out, tr):
+    """imf_kernel_map_t = the oracle's neighbour table transposed, -1 padding up to the tile boundary, exact per-tile offset masks."""
+    coords, ocm, cm = frag
+    onbr = ocm.table(t_in, t_out, 3, tr)                      # [n_out, 27]
+    nbr_t, ld_n, tile_mask = cm.table_t(t_in, t_out, 3, tr)
+    n = onbr.shape[0]
+    got = nbr_t.cpu().numpy()
+    assert np.array_equal(got[:, :n], onbr.T)
+    assert np.all(got[:, n:(n + 127) // 128 * 128] == -1)
+    tm = tile_mask.cpu().numpy().astype(np.uint32)
+    for t in range((n + 127) // 128):
+        blk = onbr[t * 128:(t + 1) * 128] >= 0
+        exp = sum(1 << k for k in range(27) if blk[:, k].any())
+        assert int(tm[t]) == exp
+
+
+@pytest.mark.parametrize("t_in,t_out,tr,cin,cout", [
+    (1, 1, False, 32, 32), (1, 1, False, 64, 64), (1, 2, False, 32, 64), (2, 2, False, 64, 64), (2, 4, False, 64, 128),
+    (4, 4, False, 128, 128), (4, 8, False, 128, 256), (8, 8, False, 256, 256), (8, 4, True, 256, 128), (4, 2, True, 256, 64),
+    (2, 1, True, 128, 64)])
+@pytest.mark.parametrize("split", [False, True])
+def test_g4_tma_gather_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout, split):
+    """TMA tile::gather4 + tcgen05 kind::f16 persistent kernel: same contract and tolerance as the h2 kernel."""
+    coords, ocm, cm = frag
+    g = torch.Generator().manual_seed(cin * 1000 + cout + t_in)
+    n_in, n_out = len(ocm.get(t_in)), len(ocm.get(t_out))
+    X = torch.randn(n_in, cin, generator=g)
+    W = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    R = torch.randn(n_out, cout, generator=g)
+    ref = torch.relu(sparse_ops.conv_forward(X, W, ocm.table(t_in, t_out, 3, tr)) * scale + shift + R)
+    out = run_conv_g4(X.cuda(), W.cuda(), cm.table_t(t_in, t_out, 3, tr), n_out, scale.cuda(), shift.cuda(), R.cuda(), True, split)
+    close(out, ref, H2_RTOL)
+
+
+@pytest.mark.parametrize("n,cin,cout", [(50000, 64, 64), (50000, 32, 32), (90000, 32, 128), (19200, 64, 64), (14107, 64, 64), (333, 64, 64)])
+def test_g4_conv_equals_simt_conv_large(n, cin, cout):
+    """Row-mode partition (several sub-tiles per CTA, several passes when the accumulators exceed TMEM) against the fp32 SIMT kernel."""
+    coords, _ = synthetic.make_fragment(n, 0.025, 0)
+    from imfnet_b200.sparse import CoordinateManager
+    cm = CoordinateManager(torch.from_numpy(coords).cuda())
+    g = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.randn(n, cin, device="cuda", generator=g)
+    W = torch.randn(27, cin, cout, device="cuda", generator=g) / 40
+    a = run_conv(X, W, cm.table(1, 1, 3, False), n)
+    one, zero = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
+    b = run_conv_g4(X, W, cm.table_t(1, 1, 3, False), n, one, zero, split=True)
+    close(b, a, H2_RTOL)
+
+
+def test_g4_conv_device_side_row_count(frag):
+    """n_out_dev < n_out_max: only the first n rows are computed (their neighbours all lie below n too), rows >= roundup32(n) stay untouched."""
+    coords, ocm, cm = frag
+    from imfnet_b200.sparse import CoordinateManager
+    n_max = len(coords)
+    n = 2500
+    sub = CoordinateManager(torch.from_numpy(coords[:n].copy()).cuda())
+    L = _lib.lib()
+    # table built with the device-side count on the full-size allocation
+    ld_n = (n_max + 127) // 128 * 128
+    nbr_t = torch.full((27, ld_n), 12345, dtype=torch.int32, device="cuda")
+    tile_mask = torch.empty(ld_n // 128 + 1, dtype=torch.int32, device="cuda")
+    n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
+    lvl = sub.level(1)
+    full = torch.from_numpy(coords).cuda()
+    _lib.check(L.imf_kernel_map_t(full.data_ptr(), n_dev.data_ptr(), n_max, lvl.table.data_ptr(), lvl.capacity, 3, 1, nbr_t.data_ptr(), ld_n,
+                                  tile_mask.data_ptr(), _lib.cur_stream()))
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(n_max, 64, generator=g)
+    W = torch.randn(27, 64, 64, generator=g) / 40
+    scale, shift = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+    ocm_sub = sparse_ops.CoordinateManager(coords[:n])
+    ref = torch.relu(sparse_ops.conv_forward(X[:n], W, ocm_sub.table(1, 1, 3, False)) * scale + shift)
+    for split in (False, True):
+        out = run_conv_g4(X.cuda(), W.cuda(), (nbr_t, ld_n, tile_mask), n_max, scale.cuda(), shift.cuda(), None, True, split, n_dev=n_dev)
+        close(out[:n], ref, H2_RTOL)
+        assert bool(torch.isnan(out[(n + 31) // 32 * 32:]).all())
+
+
 def test_h2_conv_equals_simt_conv_c2_size():
     coords, _ = synthetic.make_fragment(50000, 0.025, 0)
     from imfnet_b200.sparse import CoordinateManager

@@ -1,0 +1,96 @@
+"""Time the TMA-gather sparse convolution (imf_sparse_conv_g4_fwd) on one layer shape with CUDA events (run on the GPU box).
+
+    python tools/conv_g4_bench.py [--n 50000] [--cin 64] [--cout 64] [--reps 20] [--grid 0] [--trace]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+import numpy as np
+import torch
+
+from imfnet_b200 import _lib, synthetic
+from imfnet_b200.sparse import CoordinateManager
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--n", type=int, default=50000)
+ap.add_argument("--cin", type=int, default=64)
+ap.add_argument("--cout", type=int, default=64)
+ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--flush", type=int, default=1)
+ap.add_argument("--grid", type=int, default=0)
+ap.add_argument("--trace", action="store_true")
+ap.add_argument("--old", action="store_true", help="also time imf_sparse_conv_h2_fwd (the cp.async kernel)")
+args = ap.parse_args()
+
+L = _lib.lib()
+coords, _ = synthetic.make_fragment(args.n, 0.025, 0)
+cm = CoordinateManager(torch.from_numpy(coords).cuda())
+nbr_t, ld_n, tile_mask = cm.table_t(1, 1, 3, False)
+n, cin, cout = len(coords), args.cin, args.cout
+kci, kco = (64 if cin % 64 == 0 else 32), (64 if cout % 64 == 0 else 32)
+g = torch.Generator(device="cuda").manual_seed(0)
+X = torch.randn(n, cin, device="cuda", generator=g)
+W = torch.randn(27, cin, cout, device="cuda", generator=g) / np.sqrt(27 * cin)
+s = torch.cuda.current_stream().cuda_stream
+Xh = torch.zeros(n, 2 * cin, dtype=torch.float16, device="cuda")
+_lib.check(L.imf_h2_pack(X.data_ptr(), cin, n, cin, kci, Xh.data_ptr(), 2 * cin, None, s))
+packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(27, cin, cout, kci)), dtype=torch.uint8, device="cuda")
+_lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), 27, cin, cout, kci, 1024.0, packed.data_ptr(), s))
+Yh = torch.zeros(n, 2 * cout, dtype=torch.float16, device="cuda")
+one, zero = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
+err = torch.zeros(1, dtype=torch.int32, device="cuda")
+ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(cout))
+ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+flushbuf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+pairs = int((nbr_t[:, :n] >= 0).sum())
+alg = 4 * pairs * cin + 8 * pairs + 4 * 27 * cin * cout + 4 * n * cout
+
+
+def g4():
+    _lib.check(L.imf_sparse_conv_g4_fwd(Xh.data_ptr(), 2 * cin, n, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(), None, n,
+                                        27, cin, cout, one.data_ptr(), zero.data_ptr(), None, 0, 0, 1, Yh.data_ptr(), 2 * cout, n, kco,
+                                        ws.data_ptr(), ws_bytes, err.data_ptr(), s))
+
+
+def timeit(fn, label):
+    ts = []
+    for i in range(args.reps + 3):
+        if args.flush:
+            flushbuf.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1) * 1e3)
+    print(f"{label}: n={n} {cin}->{cout} pairs={pairs}: median {np.median(ts):.1f} us  min {np.min(ts):.1f} us  alg {alg / 1e6:.1f} MB -> "
+          f"{alg / np.median(ts) / 1e3:.0f} GB/s   {2 * pairs * cin * cout / np.median(ts) / 1e6:.1f} TFLOP/s (algorithmic)", flush=True)
+
+
+L.imf_debug_conv_g4_trace(None, args.grid)
+timeit(g4, f"g4 grid={args.grid or 148}")
+assert int(err.item()) == 0, int(err.item())
+if args.old:
+    nbr = cm.table(1, 1, 3, False)
+
+    def old():
+        _lib.check(L.imf_sparse_conv_h2_fwd(Xh.data_ptr(), 2 * cin, kci, packed.data_ptr(), nbr.data_ptr(), None, n, 27, cin, cout,
+                                            one.data_ptr(), zero.data_ptr(), None, 0, 0, 1, Yh.data_ptr(), 2 * cout, kco, None, 0,
+                                            err.data_ptr(), s))
+    timeit(old, "h2 (cp.async)")
+if args.trace:
+    trace = torch.zeros(160, dtype=torch.int64, device="cuda")
+    L.imf_debug_conv_g4_trace(trace.data_ptr(), args.grid)
+    g4()
+    torch.cuda.synchronize()
+    L.imf_debug_conv_g4_trace(None, 0)
+    t = trace.cpu().numpy()
+    names = ["start", "barriers+TMEM", "masks", "epi wait", "acc ready", "epilogue done", "exit"]
+    print("CTA0 timeline (cycles):", {nm: int(t[i] - t[0]) for i, nm in enumerate(names)})
+    for i in range(64):
+        if t[16 + 2 * i] == 0:
+            break
+        print(f"  stage {i:3d}: issued {int(t[16 + 2 * i] - t[0]):7d}   mma-saw-full {int(t[17 + 2 * i] - t[0]):7d}")
