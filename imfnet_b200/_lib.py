@@ -32,9 +32,9 @@ SIGNATURES = {
     "imf_kernel_map": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _i32, _p, _p]),
     "imf_kernel_map_t": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _i32, _p, _i32, _p, _p]),
     "imf_sparse_conv_g4_workspace_bytes": (_sz, [_i32]),
-    "imf_sparse_conv_g4_fwd": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i32,
+    "imf_sparse_conv_g4_fwd": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i32,
                                         _p, _i32, _i32, _i32, _p, _sz, _p, _p]),
-    "imf_debug_conv_g4_trace": (C.c_int, [_p, _i32]),
+    "imf_debug_conv_g4_trace": (C.c_int, [_p, _i32, _i32, _i32]),
     "imf_quantize_points": (C.c_int, [_p, _i32, _f64, _i32, _p, _p]),
     "imf_batch_segments": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
     "imf_sparse_conv_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _i32, _p]),
@@ -52,6 +52,7 @@ SIGNATURES = {
     "imf_debug_conv_flags": (C.c_int, [_i32]),
     "imf_debug_conv_trace": (C.c_int, [_p]),
     "imf_debug_gather4": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _p, _i32, _i32, _p, _p]),
+    "imf_debug_gather4_rate": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "imf_conv_first_h2_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p]),
     "imf_pointwise_tail_h2_fwd": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _p, _i32, _p]),
     "imf_conv_first_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _p]),

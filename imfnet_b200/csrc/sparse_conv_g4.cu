@@ -10,8 +10,9 @@
 //     accumulator each) and walks offsets OUTER / sub-tiles INNER, so a weight slab is fetched once per CTA, not once per tile;
 //   * neighbour rows are fetched by the TMA engine (cp.async.bulk.tensor tile::gather4: four rows per instruction, absent
 //     neighbours = out-of-range index = zero fill, 128-byte swizzle applied by the hardware) straight into the operand ring;
-//     one warp issues a whole 128-row stage with one or two instructions per lane; completion is counted in bytes on an
-//     mbarrier, so there is no per-thread wait / fence / arrive chain and every ring slot can be in flight;
+//     a gather4 instruction occupies its warp for ~2700 cycles (measured, tools/tma_rate.py) but the rate adds up over warps
+//     (8 warps = 46 B/cycle/SM, the L2 ceiling), so whole 128-row images are dealt round-robin to 8 producer warps; completion is counted
+//     in bytes on an mbarrier, so there is no per-thread wait / fence / arrive chain and every ring slot can be in flight;
 //   * the neighbour table is offset-major (nbr_t[k][row]), so the indices of a stage are one coalesced 512-byte read, and a
 //     per-tile offset mask (built by imf_kernel_map_t) lets (offset, sub-tile) pairs without any neighbour be skipped;
 //   * the epilogue converts TMEM -> BatchNorm affine / residual / ReLU -> fp16 hi/lo in registers, stages the tile in shared
@@ -20,7 +21,8 @@
 //     whole forward be captured in a CUDA graph;
 //   * small levels (fewer tiles than SMs) split a tile's stage list over several CTAs into fp32 partials + a reduce kernel.
 //
-// CTA = 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2-9 = epilogue.
+// CTA = 13 warps: warps 0-7 = gather producers, then the epilogue; warps 8-11 = MMA issuers, one group of sub-tiles each (warp 8
+// also owns the TMEM allocation); warp 12 = weight-slab loader (bulk TMA copies).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -31,9 +33,11 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kImg = kBM * 128;          // one 128-row x 128-byte operand image (16 KB)
-constexpr int kThreads = 320;
+constexpr int kNPW = 8;                  // TMA producer warps (they also run the epilogue)
+constexpr int kNMW = 4;                  // MMA issuing warps
+constexpr int kThreads = (kNPW + kNMW + 1) * 32;   // + the weight-slab loader warp
 constexpr int kNW = 2;                   // weight-slab ring depth
-constexpr int kMaxSubAll = 16;           // 512 TMEM columns / 32
+constexpr int kMaxSubAll = 8;            // 512 TMEM columns / (2 * 32)
 constexpr int kSMs = 148;
 
 template <int BN, int KC>
@@ -44,7 +48,8 @@ struct G4Cfg {
   static constexpr int BUDGET = 200 * 1024;
   static constexpr int NA_FIT = (BUDGET - kNW * W_BYTES) / A_BYTES;
   static constexpr int NA = NA_FIT > 8 ? 8 : NA_FIT;
-  static constexpr int MAXSUB = 512 / BN;
+  static constexpr int ACC_COLS = 2 * BN;               // D1 = hi.Whi + lo.Whi, D2 = hi.Wlo (summed in the epilogue)
+  static constexpr int MAXSUB = 512 / ACC_COLS;
   static constexpr int OUT_BYTES = kBM * BN * 4;       // one staged output sub-tile (BN/32 images)
   static constexpr int RING_BYTES = NA * A_BYTES;
   static_assert(2 * OUT_BYTES <= RING_BYTES, "the epilogue double buffer lives in the operand ring");
@@ -61,6 +66,30 @@ __device__ __forceinline__ void g4_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16-byte asynchronous copy global -> shared; a negative `row` writes zeros instead (ignore-src form)
+__device__ __forceinline__ void g4_cp_async16_row(uint32_t smem_dst, const void* gmem_src, int row) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.lt.s32 p, %2, 0;\n"
+      "cp.async.cg.shared.global [%0], [%1], 16, p;\n"
+      "}\n" ::"r"(smem_dst),
+      "l"(gmem_src), "r"(row)
+      : "memory");
+}
+__device__ __forceinline__ void g4_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void g4_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+// make `bar` receive one (pre-counted) arrival once all cp.async issued so far by this thread have completed
+__device__ __forceinline__ void g4_cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+// zero 16 consecutive TMEM columns of this warp's 32 lanes
+__device__ __forceinline__ void g4_tmem_zero16(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};\n" ::"r"(taddr), "r"(0u)
       : "memory");
 }
 __device__ __forceinline__ void named_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -126,17 +155,23 @@ __device__ __forceinline__ void g4_load16_h2(const __half* hi_src, const __half*
   }
 }
 
-// Position in the (offset-chunk, sub-tile) walk shared by the producer and the MMA warp.
+// Position in the (offset, chunk, sub-tile) walk shared by the producers and the MMA warps.
 struct G4It {
-  int w, j;
+  int w;          // weight step = kk * nchunks + chunk
+  int kk;         // index into the offset list
+  int chunk;      // input-channel chunk
+  int k;          // klist[kk]
+  unsigned jm;    // sub-tiles that have a neighbour at offset k
+  unsigned rem;   // sub-tiles of this weight step still to visit (lowest set bit = current)
+  int j;          // current sub-tile
 };
 
 template <int BN, int KC>
 __global__ void __launch_bounds__(kThreads, 1)
-k_sparse_conv_g4(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const unsigned char* __restrict__ Wp,
+k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ CUtensorMap tmY, const unsigned char* __restrict__ Wp,
                  const int* __restrict__ nbr_t, int ld_n, const unsigned* __restrict__ tile_mask, const int* __restrict__ n_ptr, int n_max,
                  int K3, int nchunks, const float* __restrict__ scale, const float* __restrict__ shift, const __half* __restrict__ R, int ldr,
-                 int kc_r, int relu, int kc_out, float* __restrict__ P, int cout_total, int* err, long long* __restrict__ trace) {
+                 int kc_r, int relu, int kc_out, float* __restrict__ P, int cout_total, int zero_row, int* err, long long* __restrict__ trace, int dbg) {
   using Cfg = G4Cfg<BN, KC>;
   constexpr int NA = Cfg::NA;
   extern __shared__ unsigned char smem_dyn[];
@@ -147,8 +182,11 @@ k_sparse_conv_g4(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __shared__ uint32_t tmem_base_s;
   __shared__ unsigned submask_s[kMaxSubAll];
   __shared__ int klist_s[32];
+  __shared__ unsigned jmask_s[32];
   __shared__ int nk_s;
+  __shared__ int ring_s[5];
   __shared__ float sc_s[BN], sh_s[BN];
+  __shared__ __align__(16) int idx_s[NA][2][kBM];      // neighbour indices of each producer warp's current / next stage
 
   int n = n_max;
   if (n_ptr) { const int v = *n_ptr; n = v < n_max ? v : n_max; }
@@ -177,55 +215,53 @@ k_sparse_conv_g4(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #define G4_TRACE(slot) do { if (trace) trace[slot] = clock64(); } while (0)
   if (tid == 0) G4_TRACE(0);
 
+  uint32_t tmem_cols = 32;
+  {
+    const int nsub_pass = nsub_total < Cfg::MAXSUB ? nsub_total : Cfg::MAXSUB;
+    while ((int)tmem_cols < nsub_pass * Cfg::ACC_COLS) tmem_cols <<= 1;
+  }
   if (tid == 0) {
-    for (int s = 0; s < NA; ++s) { tc::mbar_init(&full_a[s], 1); tc::mbar_init(&empty_a[s], 1); }
-    for (int s = 0; s < kNW; ++s) { tc::mbar_init(&full_w[s], 1); tc::mbar_init(&empty_w[s], 1); }
-    tc::mbar_init(&acc_bar, 1);
+    for (int s = 0; s < NA; ++s) { tc::mbar_init(&full_a[s], 32); tc::mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < kNW; ++s) { tc::mbar_init(&full_w[s], 1); tc::mbar_init(&empty_w[s], kNMW); }
+    tc::mbar_init(&acc_bar, kNMW);
     tc::fence_barrier_init();
-    tma::prefetch_map(&tmX);
     tma::prefetch_map(&tmY);
   }
-  if (warp == 1) {
-    const int nsub_pass = nsub_total < Cfg::MAXSUB ? nsub_total : Cfg::MAXSUB;
-    uint32_t cols = 32;
-    while ((int)cols < nsub_pass * BN) cols <<= 1;
-    tc::tmem_alloc(&tmem_base_s, cols);
-    tc::tmem_relinquish();
-  }
-  if (tid >= 64 && tid < 64 + BN) {
-    sc_s[tid - 64] = __ldg(scale + zt * BN + tid - 64);
-    sh_s[tid - 64] = __ldg(shift + zt * BN + tid - 64);
+  if (warp == kNPW) { tc::tmem_alloc(&tmem_base_s, tmem_cols); tc::tmem_relinquish(); }
+  if (tid < BN) {
+    sc_s[tid] = __ldg(scale + zt * BN + tid);
+    sh_s[tid] = __ldg(shift + zt * BN + tid);
   }
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem_d = tmem_base_s;
-  uint32_t tmem_cols = 32;
-  {
-    const int nsub_pass = nsub_total < Cfg::MAXSUB ? nsub_total : Cfg::MAXSUB;
-    while ((int)tmem_cols < nsub_pass * BN) tmem_cols <<= 1;
-  }
   if (tid == 0) G4_TRACE(1);
 
-  int ac = 0, wc = 0;                     // running stage counters (producer and MMA warp advance them identically)
+  // running ring positions (the producers and the MMA warps advance them identically)
+  int ac = 0, a_slot = 0, w_slot = 0;
+  uint32_t a_phase = 0u, w_phase = 0u;
   const int npass = (nsub_total + Cfg::MAXSUB - 1) / Cfg::MAXSUB;
   for (int pass = 0; pass < npass; ++pass) {
     const int sub0 = pass * Cfg::MAXSUB;
     const int nsub = min(Cfg::MAXSUB, nsub_total - sub0);
     const int prow = row_begin + sub0 * kBM;            // first row of this pass
-    // ---- offset masks of the sub-tiles, offset list of the pass ----
+    // ---- offset masks of the sub-tiles; offset list of the pass with, per offset, the sub-tiles that need it ----
     if (tid < nsub) {
       const int r0 = prow + tid * kBM;
       const int r1 = min(r0 + kBM, row_end) - 1;
       submask_s[tid] = __ldg(tile_mask + r0 / kBM) | __ldg(tile_mask + r1 / kBM);
     }
     __syncthreads();
-    if (tid == 0) {
-      unsigned m = 0;
-      for (int j = 0; j < nsub; ++j) m |= submask_s[j];
-      int c = 0;
-      while (m) { const int b = __ffs(m) - 1; m &= m - 1; klist_s[c++] = b; }
-      nk_s = c;
+    if (warp == 0) {            // lane b = offset b: is it used by any sub-tile, by which ones; compacted in offset order
+      unsigned jm = 0;
+      for (int j = 0; j < nsub; ++j) jm |= ((submask_s[j] >> lane) & 1u) << j;
+      const unsigned used = __ballot_sync(0xffffffffu, jm != 0u);
+      const int pos = __popc(used & ((1u << lane) - 1u));
+      const int cnt = __popc(used);
+      if (jm != 0u) { klist_s[pos] = lane; jmask_s[pos] = jm; }
+      if (lane >= cnt) { klist_s[lane] = 0; jmask_s[lane] = 1u; }      // padding entries (never walked, only prefetched)
+      if (lane == 0) nk_s = cnt;
     }
     __syncthreads();
     if (tid == 0) G4_TRACE(2);
@@ -236,129 +272,204 @@ k_sparse_conv_g4(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       w_begin = min(nw_all, split * per);
       w_end = min(nw_all, w_begin + per);
     }
-    auto active = [&](const G4It& it) { return (submask_s[it.j] >> klist_s[it.w / nchunks]) & 1u; };
+    // The walk: offsets outer, chunks, sub-tiles inner; (offset, sub-tile) pairs without any neighbour are skipped.  No integer
+    // division and no shared-memory read per step (only per offset): a lone issuing warp cannot hide their latency
+    // (measured: ~900 cycles per step with divisions in it).
+    auto first = [&]() {
+      G4It it;
+      it.w = w_begin;
+      it.kk = w_begin / nchunks;
+      it.chunk = w_begin - it.kk * nchunks;
+      it.k = klist_s[it.kk & 31];
+      it.jm = jmask_s[it.kk & 31];
+      it.rem = it.jm;
+      it.j = __ffs(it.rem) - 1;
+      return it;
+    };
     auto advance = [&](G4It& it) {
-      do {
-        if (++it.j == nsub) { it.j = 0; ++it.w; }
-      } while (it.w < w_end && !active(it));
+      it.rem &= it.rem - 1;
+      if (it.rem == 0u) {
+        ++it.w;
+        if (++it.chunk == nchunks) {
+          it.chunk = 0;
+          ++it.kk;
+          it.k = klist_s[it.kk & 31];
+          it.jm = jmask_s[it.kk & 31];
+        }
+        it.rem = it.jm;
+      }
+      it.j = __ffs(it.rem) - 1;
     };
 
-    if (warp == 0) {
-      // =========================== TMA producer ===========================
-      auto load_idx = [&](const G4It& it) {
-        int4 v = make_int4(-1, -1, -1, -1);
+    if (warp < kNPW) {
+      // =========================== gather producers (cp.async), one warp per stage ===========================
+      // Measured on B200 (tools/tma_rate.py, profiles/r01): TMA tile::gather4 of 128-byte rows tops out at ~44 B/cycle/SM with
+      // 8 issuing warps (an instruction holds its warp ~2700 cycles) and drops to ~31 B/cycle inside this kernel; absent rows
+      // cost it as much as present ones (more when zero-filled out of range).  The LSU path (LDGSTS, 16 B per lane) issues
+      // 64 B/cycle/SM and its zero fill of an absent row moves no data, so the row gather uses cp.async; completion is still
+      // tracked by the stage's mbarrier (cp.async.mbarrier.arrive.noinc), i.e. no thread ever waits for its own row copies.
+      // A warp owns one ring slot, i.e. every NA-th stage, and copies all of it (its ~900 cycles of per-stage barrier / walk
+      // latency then overlap the other warps' copies).  The 128 neighbour indices of its NEXT stage are prefetched into shared memory (one
+      // 16-byte cp.async per lane) while it copies the current one.
+      // KC = 64: 16 lanes per row (hi 8 x 16 B | lo 8 x 16 B): instruction i covers rows 4*(2*(i/4) + lane/16) + i%4;
+      // KC = 32:  8 lanes per row: instruction i covers rows 4*(4*(i/4) + lane/8) + i%4  -> whole rows per instruction.
+      constexpr int LPR = (KC == 64) ? 16 : 8;           // lanes per row
+      constexpr int RPI = 32 / LPR;                      // rows per instruction
+      constexpr int NINS = kBM / RPI;                    // copy instructions per stage and lane
+      const int cl = lane & (LPR - 1), hw = lane / LPR;
+      const int part = (KC == 64) ? (cl >> 3) : 0, c16 = cl & 7;
+      const uint32_t ring_base = tc::smem_u32(a_ring) + part * kImg;
+      const char* xthr = reinterpret_cast<const char*>(X) + part * 128 + c16 * 16;
+      const unsigned ldx_bytes = (unsigned)ldx * 2u;
+      int* my_idx = &idx_s[warp][0][0];
+      auto prefetch = [&](const G4It& it, int slot) {    // lane l: neighbour rows of output rows 4l..4l+3 of the stage's sub-tile
         const int row = prow + it.j * kBM + 4 * lane;
-        if (row < row_end) v = __ldg(reinterpret_cast<const int4*>(nbr_t + (size_t)klist_s[it.w / nchunks] * ld_n + row));
-        return v;
+        int* dst = my_idx + slot * kBM + 4 * lane;
+        if (row < row_end) g4_cp_async16_row(tc::smem_u32(dst), nbr_t + (size_t)it.k * ld_n + row, 0);
+        else *reinterpret_cast<int4*>(dst) = make_int4(-1, -1, -1, -1);
       };
-      G4It cur{w_begin, -1};
-      advance(cur);
-      int4 idx = make_int4(-1, -1, -1, -1);
-      if (cur.w < w_end) idx = load_idx(cur);
-      int last_w = -1;
-      while (cur.w < w_end) {
-        G4It nxt = cur;
-        advance(nxt);
-        int4 idx_n = make_int4(-1, -1, -1, -1);
-        if (nxt.w < w_end) idx_n = load_idx(nxt);       // prefetch the next stage's indices
-        const int k = klist_s[cur.w / nchunks], chunk = cur.w % nchunks;
-        if (cur.w != last_w) {
-          const int ws = wc % kNW;
-          tc::mbar_wait(&empty_w[ws], ((uint32_t)(wc / kNW) & 1u) ^ 1u, err, 1);
-          if (lane == 0) {
-            tc::mbar_arrive_expect_tx(&full_w[ws], Cfg::W_BYTES);
-            tc::bulk_g2s(w_ring + ws * Cfg::W_BYTES, Wp + (((size_t)k * nchunks + chunk) * ntn + zt) * Cfg::W_BYTES, Cfg::W_BYTES,
-                         &full_w[ws]);
-          }
-          ++wc;
-          last_w = cur.w;
-        }
-        const int as = ac % NA;
-        tc::mbar_wait(&empty_a[as], ((uint32_t)(ac / NA) & 1u) ^ 1u, err, 2);
-        if (lane == 0) {
-          if (trace && ac < 64) trace[16 + 2 * ac] = clock64();
-          tc::mbar_arrive_expect_tx(&full_a[as], Cfg::A_BYTES);
-        }
+      // Stage s lives in ring slot s % NA and belongs to warp s % NA: one producer per slot, so a warp can never run two phases
+      // ahead of the slot's consumer (which the parity wait could not tell apart from "free").  Warps NA..7 only run the epilogue.
+      G4It it = first();
+      const int first_i = warp >= a_slot ? warp - a_slot : warp - a_slot + NA;     // (the ring may start a pass at any slot)
+      for (int i = 0; i < first_i && it.w < w_end; ++i) advance(it);               // first stage of this warp
+      if (warp >= NA) it.w = w_end;
+      int my_ac = ac + first_i;
+      uint32_t my_phase = warp >= a_slot ? a_phase : a_phase ^ 1u;                 // phase of slot `warp` at its next use
+      int slot = 0;
+      if (it.w < w_end) prefetch(it, 0);
+      g4_cp_async_commit();
+      g4_cp_async_commit();                                               // (empty) keeps the group arithmetic uniform
+      while (it.w < w_end) {
+        G4It nxt = it;
+        for (int i = 0; i < NA && nxt.w < w_end; ++i) advance(nxt);
+        if (nxt.w < w_end) prefetch(nxt, slot ^ 1);
+        g4_cp_async_commit();
+        if (trace && lane == 0 && my_ac < 36) trace[16 + 4 * my_ac] = clock64();
+        tc::mbar_wait(&empty_a[warp], my_phase ^ 1u, err, 2);
+        if (trace && lane == 0 && my_ac < 36) trace[17 + 4 * my_ac] = clock64();
+        g4_cp_async_wait<2>();             // pending at most: the previous stage's rows and the prefetch just issued
         __syncwarp();
-        const uint32_t dst = tc::smem_u32(a_ring + as * Cfg::A_BYTES) + lane * 512;
-        const uint32_t bar = tc::smem_u32(&full_a[as]);
-        if (KC == 64) {
-          tma::gather4(dst, &tmX, bar, chunk * 128, idx.x, idx.y, idx.z, idx.w);               // hi halves of the 64-channel chunk
-          tma::gather4(dst + kImg, &tmX, bar, chunk * 128 + 64, idx.x, idx.y, idx.z, idx.w);   // lo halves
-        } else {
-          tma::gather4(dst, &tmX, bar, chunk * 64, idx.x, idx.y, idx.z, idx.w);                // [hi32 | lo32]
-        }
-        ++ac;
-        cur = nxt;
-        idx = idx_n;
-      }
-      // keep the MMA warp's counters in step (it walks the same sequence)
-    } else if (warp == 1) {
-      // =========================== MMA issuer ===========================
-      constexpr uint32_t idesc = g4_idesc_f16(kBM, BN);
-      G4It cur{w_begin, -1};
-      advance(cur);
-      int last_w = -1, ws = 0;
-      unsigned started = 0u;
-      while (cur.w < w_end) {
-        if (cur.w != last_w) {
-          if (last_w >= 0 && lane == 0) tc::mma_commit(&empty_w[ws]);
-          ws = wc % kNW;
-          tc::mbar_wait(&full_w[ws], (uint32_t)(wc / kNW) & 1u, err, 3);
-          ++wc;
-          last_w = cur.w;
-        }
-        const int as = ac % NA;
-        tc::mbar_wait(&full_a[as], (uint32_t)(ac / NA) & 1u, err, 4);
-        tc::tc_fence_after_sync();
-        if (lane == 0) {
-          if (trace && ac < 64) trace[17 + 2 * ac] = clock64();
-          const uint32_t a0 = tc::smem_u32(a_ring + as * Cfg::A_BYTES);
-          const uint32_t w0 = tc::smem_u32(w_ring + ws * Cfg::W_BYTES), w1 = w0 + Cfg::W_IMG;
-          const uint32_t d = tmem_d + (uint32_t)(cur.j * BN);
-          const uint32_t acc0 = (started >> cur.j) & 1u;
-          if (KC == 64) {
-            const uint32_t a_hi = a0, a_lo = a0 + kImg;
+        const uint32_t stg = ring_base + warp * Cfg::A_BYTES;
+        const char* xc = xthr + it.chunk * (4 * KC);
+        const int4* idx4p = reinterpret_cast<const int4*>(my_idx + slot * kBM);
+        if (!(dbg & 2)) {
+#pragma unroll 4
+          for (int i4 = 0; i4 < NINS / 4; ++i4) {
+            const int m = RPI * i4 + hw;                                  // row group of this lane for these 4 instructions
+            const int4 r = idx4p[m];
+            const int r4[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t o = ks * 32;
-              g4_mma_f16(d, tc::smem_desc_sw128(a_lo + o), tc::smem_desc_sw128(w0 + o), idesc, (acc0 | (uint32_t)ks) ? 1u : 0u);
-              g4_mma_f16(d, tc::smem_desc_sw128(a_hi + o), tc::smem_desc_sw128(w1 + o), idesc, 1u);
-              g4_mma_f16(d, tc::smem_desc_sw128(a_hi + o), tc::smem_desc_sw128(w0 + o), idesc, 1u);
-            }
-          } else {
-            // A row = [hi32 | lo32]; image w0 = [Whi | Whi], image w1 = [Wlo | 0]
-            g4_mma_f16(d, tc::smem_desc_sw128(a0 + 64), tc::smem_desc_sw128(w0 + 64), idesc, acc0);     // lo . Whi
-            g4_mma_f16(d, tc::smem_desc_sw128(a0 + 96), tc::smem_desc_sw128(w0 + 96), idesc, 1u);
-            g4_mma_f16(d, tc::smem_desc_sw128(a0), tc::smem_desc_sw128(w1), idesc, 1u);                 // hi . Wlo
-            g4_mma_f16(d, tc::smem_desc_sw128(a0 + 32), tc::smem_desc_sw128(w1 + 32), idesc, 1u);
-            g4_mma_f16(d, tc::smem_desc_sw128(a0), tc::smem_desc_sw128(w0), idesc, 1u);                 // hi . Whi
-            g4_mma_f16(d, tc::smem_desc_sw128(a0 + 32), tc::smem_desc_sw128(w0 + 32), idesc, 1u);
+            for (int i = 0; i < 4; ++i)      // absent neighbour: the (valid) address of row 0 is passed but ignored (zero fill)
+              g4_cp_async16_row(stg + tc::sw128_offset(4 * m + i, c16), xc + (unsigned long long)((unsigned)max(r4[i], 0)) * ldx_bytes, r4[i]);
           }
-          tc::mma_commit(&empty_a[as]);
         }
-        started |= 1u << cur.j;
+        g4_cp_async_arrive_noinc(&full_a[warp]);                          // fires when this thread's copies have landed
+        g4_cp_async_commit();
+        my_ac += NA;
+        my_phase ^= 1u;
+        it = nxt;
+        slot ^= 1;
+        __syncwarp();                      // every lane is done reading the index slot the next prefetch overwrites
+      }
+      g4_cp_async_wait<0>();
+    } else if (warp == kNPW + kNMW) {
+      // =========================== weight-slab loader ===========================
+      int kk = w_begin / nchunks, chunk = w_begin - kk * nchunks;
+      for (int w = w_begin; w < w_end; ++w) {
+        tc::mbar_wait(&empty_w[w_slot], w_phase ^ 1u, err, 1);
+        if (lane == 0 && (dbg & 1)) tc::mbar_arrive(&full_w[w_slot]);
+        if (lane == 0 && !(dbg & 1)) {
+          tc::mbar_arrive_expect_tx(&full_w[w_slot], Cfg::W_BYTES);
+          tc::bulk_g2s(w_ring + w_slot * Cfg::W_BYTES, Wp + (((size_t)klist_s[kk] * nchunks + chunk) * ntn + zt) * Cfg::W_BYTES,
+                       Cfg::W_BYTES, &full_w[w_slot]);
+        }
+        if (++w_slot == kNW) { w_slot = 0; w_phase ^= 1u; }
+        if (++chunk == nchunks) { chunk = 0; ++kk; }
+      }
+    } else if (warp < kNPW + kNMW) {
+      // =========================== MMA issuers ===========================
+      // An issuing thread is held ~85-95 cycles per tcgen05.mma (any N <= 128, measured) and pays ~300 cycles of barrier / walk
+      // overhead per stage, so the stages are spread over kNMW warps by sub-tile (each accumulator belongs to one warp, which
+      // keeps the accumulate flag and the instruction order per accumulator inside one thread).
+      // Three split products with two instructions per K step:
+      //   D[:, 0:2BN] += a_hi . [Whi | Wlo]^T   (the weight slab is one 2BN-row image: rows [0,BN) = Whi, [BN,2BN) = Wlo)
+      //   D[:, 0:BN]  += a_lo . Whi^T            the epilogue adds the two halves
+      constexpr uint32_t idesc2 = g4_idesc_f16(kBM, 2 * BN), idesc1 = g4_idesc_f16(kBM, BN);
+      const int mw = warp - kNPW;
+      // Stage s (ring slot s % NA) is issued by MMA warp (s % NA) % kNMW: one consumer per slot, which the parity waits need
+      // (a consumer that could skip stages might see a slot two phases off).  An accumulator is therefore fed by several
+      // threads; the tensor pipe executes MMAs one after the other, so only the "first MMA overwrites" flag needs care: the
+      // accumulators are zeroed here (each MMA warp owns one TMEM lane quadrant) and every MMA accumulates.
+      {
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        for (int col = 0; col < nsub * Cfg::ACC_COLS; col += 16) g4_tmem_zero16(tmem_d + lane_base + (uint32_t)col);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc::tc_fence_before_sync();
+        named_barrier(2, kNMW * 32);
+        tc::tc_fence_after_sync();
+      }
+      G4It cur = first();
+      int last_w = -1, ws = 0;
+      while (cur.w < w_end) {
+        if (cur.w != last_w) {
+          if (last_w >= 0 && lane == 0) tc::mma_commit(&empty_w[ws]);      // this warp's MMAs on the previous slab
+          ws = w_slot;
+          tc::mbar_wait(&full_w[ws], w_phase, err, 3);                     // every MMA warp waits: keeps them inside the slab ring
+          if (++w_slot == kNW) { w_slot = 0; w_phase ^= 1u; }
+          last_w = cur.w;
+        }
+        if ((a_slot & (kNMW - 1)) == mw) {
+          tc::mbar_wait(&full_a[a_slot], a_phase, err, 4);
+          if (lane == 0) {
+            if (trace && ac < 36) trace[18 + 4 * ac] = clock64();
+            const uint32_t a0 = tc::smem_u32(a_ring + a_slot * Cfg::A_BYTES);
+            const uint32_t w0 = tc::smem_u32(w_ring + ws * Cfg::W_BYTES);
+            const uint32_t d = tmem_d + (uint32_t)(cur.j * Cfg::ACC_COLS);
+            if (dbg & 4) {
+            } else if (KC == 64) {
+              const uint32_t a_hi = a0, a_lo = a0 + kImg;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t o = ks * 32;
+                g4_mma_f16(d, tc::smem_desc_sw128(a_hi + o), tc::smem_desc_sw128(w0 + o), idesc2, 1u);
+                g4_mma_f16(d, tc::smem_desc_sw128(a_lo + o), tc::smem_desc_sw128(w0 + o), idesc1, 1u);
+              }
+            } else {
+              // A row = [hi32 | lo32]; slab rows [0,BN) = [Whi | Whi], rows [BN,2BN) = [Wlo | 0]
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint32_t o = ks * 32;
+                g4_mma_f16(d, tc::smem_desc_sw128(a0 + o), tc::smem_desc_sw128(w0 + o), idesc2, 1u);               // hi . [Whi | Wlo]
+                g4_mma_f16(d, tc::smem_desc_sw128(a0 + 64 + o), tc::smem_desc_sw128(w0 + 64 + o), idesc1, 1u);     // lo . Whi
+              }
+            }
+            tc::mma_commit(&empty_a[a_slot]);
+            if (trace && ac < 36) trace[19 + 4 * ac] = clock64();
+          }
+          __syncwarp();
+        }
         ++ac;
-        __syncwarp();
+        if (++a_slot == NA) { a_slot = 0; a_phase ^= 1u; }
         advance(cur);
       }
       if (lane == 0) {
         if (last_w >= 0) tc::mma_commit(&empty_w[ws]);
         tc::mma_commit(&acc_bar);
+        if (mw == 0) {                     // ring positions after this pass, for everybody (the producers skip through theirs)
+          ring_s[0] = ac; ring_s[1] = a_slot; ring_s[2] = (int)a_phase; ring_s[3] = w_slot; ring_s[4] = (int)w_phase;
+        }
       }
       __syncwarp();
-    } else {
-      // =========================== epilogue (8 warps) ===========================
-      const int e = warp - 2, q = warp & 3, h = e >> 2;
-      const int etid = tid - 64;
-      if (tid == 64) G4_TRACE(3);
+    }
+    if (warp < 8) {
+      // =========================== epilogue (warps 0-7) ===========================
+      const int q = warp & 3, h = warp >> 2;
+      if (tid == 0) G4_TRACE(3);
       tc::mbar_wait(&acc_bar, (uint32_t)pass & 1u, err, 5);
       tc::tc_fence_after_sync();
-      if (tid == 64) G4_TRACE(4);
-      // sub-tile j has an accumulator iff at least one of its (offset, chunk) stages was walked by this CTA
-      unsigned started = 0u;
-      if (w_end > w_begin)
-        for (int j = 0; j < nsub; ++j) started |= (submask_s[j] != 0u ? 1u : 0u) << j;
+      if (tid == 0) G4_TRACE(4);
+      const unsigned started = 0xFFFFFFFFu;             // the MMA warps zero every accumulator before the first MMA
       constexpr int CW = BN / 2;
       const bool partial = (P != nullptr) && !part.row_mode && part.S > 1;
       bool big = false;
@@ -367,7 +478,7 @@ k_sparse_conv_g4(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int grow = prow + j * kBM + r_in;
         unsigned char* stage = a_ring + (j & 1) * Cfg::OUT_BYTES;
         if (!partial) {
-          if (j >= 2 && etid == 0) tma::store_wait_read<1>();       // the stores that read this buffer two sub-tiles ago
+          if (j >= 2 && tid == 0) tma::store_wait_read<1>();       // the stores that read this buffer two sub-tiles ago
           named_barrier(1, 256);
         }
 #pragma unroll 1
@@ -375,7 +486,11 @@ k_sparse_conv_g4(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int cl = h * CW + cb;                                // column inside this CTA's BN-wide tile
           float a[16];
           if ((started >> j) & 1u) {
-            tc::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * BN + cl), a);
+            float a2[16];
+            tc::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * Cfg::ACC_COLS + cl), a);
+            tc::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * Cfg::ACC_COLS + BN + cl), a2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] += a2[i];
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) a[i] = 0.f;
@@ -422,7 +537,7 @@ k_sparse_conv_g4(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (!partial) {
           tc::fence_proxy_async();
           named_barrier(1, 256);
-          if (etid == 0) {
+          if (tid == 0) {
             const int r0 = prow + j * kBM;
 #pragma unroll 1
             for (int rb = 0; rb < 4; ++rb) {
@@ -435,15 +550,16 @@ k_sparse_conv_g4(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
         }
       }
-      if (!partial && etid == 0) tma::store_wait_read<0>();
+      if (!partial && tid == 0) tma::store_wait_read<0>();
       if (big && err) atomicOr(err, 0x10000);
-      if (tid == 64) G4_TRACE(5);
+      if (tid == 0) G4_TRACE(5);
     }
     tc::tc_fence_before_sync();
     __syncthreads();                       // pass boundary: TMEM drained, staging reads done, ring reusable
     tc::tc_fence_after_sync();
+    ac = ring_s[0]; a_slot = ring_s[1]; a_phase = (uint32_t)ring_s[2]; w_slot = ring_s[3]; w_phase = (uint32_t)ring_s[4];
   }
-  if (warp == 1) tc::tmem_dealloc(tmem_d, tmem_cols);
+  if (warp == kNPW) tc::tmem_dealloc(tmem_d, tmem_cols);
   if (tid == 0) G4_TRACE(6);
 #undef G4_TRACE
 }
@@ -495,12 +611,13 @@ __global__ void __launch_bounds__(256) k_conv_g4_reduce(const float* __restrict_
 }
 
 long long* g_g4_trace = nullptr;
+int g_g4_dbg = 0;       // profiling hook: bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs (results meaningless)
 int g_g4_grid = 0;        // profiling hook: overrides the number of CTAs per output-channel tile (0 = one per SM)
 
 template <int BN, int KC>
-int launch_g4(const CUtensorMap& tmX, const CUtensorMap& tmY, const void* Wp, const int* nbr_t, int ld_n, const unsigned* tile_mask,
+int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, const int* nbr_t, int ld_n, const unsigned* tile_mask,
               const int* n_ptr, int n_max, int K3, int Cin, int Cout, const float* scale, const float* shift, const __half* R, int ldr,
-              int kc_r, int relu, __half* Y, int ldy, int kc_out, void* ws, size_t ws_bytes, int* err, cudaStream_t stream) {
+              int kc_r, int relu, __half* Y, int ldy, int kc_out, int zero_row, void* ws, size_t ws_bytes, int* err, cudaStream_t stream) {
   using Cfg = G4Cfg<BN, KC>;
   const size_t smem = (size_t)Cfg::RING_BYTES + (size_t)kNW * Cfg::W_BYTES + 1024;
   static bool attr_done = false;
@@ -519,9 +636,9 @@ int launch_g4(const CUtensorMap& tmX, const CUtensorMap& tmY, const void* Wp, co
   float* P = nullptr;
   if (ws != nullptr && ws_bytes >= (size_t)kSMs * kBM * Cout * sizeof(float)) P = reinterpret_cast<float*>(ws);
   dim3 grid(gx, 1, ntn);
-  k_sparse_conv_g4<BN, KC><<<grid, kThreads, smem, stream>>>(tmX, tmY, reinterpret_cast<const unsigned char*>(Wp), nbr_t, ld_n, tile_mask,
+  k_sparse_conv_g4<BN, KC><<<grid, kThreads, smem, stream>>>(X, ldx, tmY, reinterpret_cast<const unsigned char*>(Wp), nbr_t, ld_n, tile_mask,
                                                             n_ptr, n_max, K3, nchunks, scale, shift, R, ldr, kc_r, relu, kc_out, P, Cout,
-                                                            err, g_g4_trace);
+                                                            zero_row, err, g_g4_trace, g_g4_dbg);
   IMF_CHECK_LAUNCH();
   if (P != nullptr) {      // split mode is possible for small n: the reduce kernel decides on the device (no-op otherwise)
     const int rows = n_max < gx * kBM ? n_max : gx * kBM;
@@ -535,21 +652,24 @@ int launch_g4(const CUtensorMap& tmX, const CUtensorMap& tmY, const void* Wp, co
 
 }  // namespace
 
-extern "C" int imf_debug_conv_g4_trace(long long* trace, int32_t grid) {
+extern "C" int imf_debug_conv_g4_trace(long long* trace, int32_t grid, int32_t producer_warps, int32_t flags) {
   g_g4_trace = trace;
+  g_g4_dbg = flags;
   g_g4_grid = grid;
+  (void)producer_warps;
   return IMF_OK;
 }
 
 extern "C" size_t imf_sparse_conv_g4_workspace_bytes(int32_t Cout) { return (size_t)kSMs * kBM * (size_t)Cout * sizeof(float); }
 
-extern "C" int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t n_in_rows, int32_t kc_in, const void* packed, const int32_t* nbr_t,
+extern "C" int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t n_in_rows, int32_t zero_row, int32_t kc_in, const void* packed, const int32_t* nbr_t,
                                       int32_t ld_n, const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max,
                                       int32_t kernel_volume, int32_t Cin, int32_t Cout, const float* scale, const float* shift,
                                       const void* residual, int32_t ldr, int32_t kc_r, int32_t relu, void* Y, int32_t ldy,
                                       int32_t n_y_rows, int32_t kc_out, void* workspace, size_t workspace_bytes, int32_t* err,
                                       cudaStream_t stream) {
   IMF_CHECK_ARG(n_out_max >= 0 && kernel_volume >= 1 && kernel_volume <= 27 && n_in_rows >= 0);
+  IMF_CHECK_ARG(zero_row < 0 || zero_row + 64 <= n_in_rows);
   IMF_CHECK_ARG((kc_in == 32 || kc_in == 64) && Cin > 0 && Cin % kc_in == 0 && (Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256));
   IMF_CHECK_ARG((kc_out == 32 || kc_out == 64) && Cout % kc_out == 0);
   IMF_CHECK_ARG(scale != nullptr && shift != nullptr);
@@ -560,16 +680,14 @@ extern "C" int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t n_in_r
   IMF_CHECK_ARG(X != nullptr && packed != nullptr && nbr_t != nullptr && tile_mask != nullptr && Y != nullptr && n_in_rows > 0);
   IMF_CHECK_ARG(((uintptr_t)X % 16) == 0 && ((uintptr_t)packed % 16) == 0 && ((uintptr_t)Y % 16) == 0 && ((uintptr_t)residual % 16) == 0 &&
                 ((uintptr_t)nbr_t % 16) == 0);
-  CUtensorMap tmX, tmY;
-  int rc = tma::encode_2d_u16(&tmX, X, (uint64_t)n_in_rows, (uint64_t)(2 * Cin), (uint64_t)ldx, 64, 1);
-  if (rc) { imf_set_error("cuTensorMapEncodeTiled(X) failed: %d", rc); return IMF_ERR_CUDA; }
-  rc = tma::encode_2d_u16(&tmY, Y, (uint64_t)n_y_rows, (uint64_t)(2 * Cout), (uint64_t)ldy, 64, 32);
+  CUtensorMap tmY;
+  int rc = tma::encode_2d_u16(&tmY, Y, (uint64_t)n_y_rows, (uint64_t)(2 * Cout), (uint64_t)ldy, 64, 32);
   if (rc) { imf_set_error("cuTensorMapEncodeTiled(Y) failed: %d", rc); return IMF_ERR_CUDA; }
   const __half* Rh = reinterpret_cast<const __half*>(residual);
   __half* Yh = reinterpret_cast<__half*>(Y);
 #define IMF_GO(BN, KC)                                                                                                               \
-  return launch_g4<BN, KC>(tmX, tmY, packed, nbr_t, ld_n, tile_mask, n_out_dev, n_out_max, kernel_volume, Cin, Cout, scale, shift, Rh, \
-                           ldr, kc_r, relu, Yh, ldy, kc_out, workspace, workspace_bytes, err, stream)
+  return launch_g4<BN, KC>(reinterpret_cast<const __half*>(X), ldx, tmY, packed, nbr_t, ld_n, tile_mask, n_out_dev, n_out_max, kernel_volume, Cin, Cout, scale, shift, Rh, \
+                           ldr, kc_r, relu, Yh, ldy, kc_out, zero_row, workspace, workspace_bytes, err, stream)
   const int bn = Cout > 128 ? 128 : Cout;
   if (kc_in == 64) {
     if (bn == 32) IMF_GO(32, 64);

@@ -48,3 +48,48 @@ extern "C" int imf_debug_gather4(const void* X, int32_t ld, int32_t n_rows, cons
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }
+
+// ---- throughput probe: `nwarps` warps each issue `iters` rounds of one gather4 per lane (4 rows x 128 B) into a private
+// 16 KB tile and wait for each round; out[0] = cycles for the whole loop (max over warps), per CTA 0.
+namespace {
+__global__ void __launch_bounds__(256) k_probe_gather4_rate(const __grid_constant__ CUtensorMap map, const int* __restrict__ idx, int n_idx,
+                                                            int iters, int depth, long long* __restrict__ out, int* err) {
+  extern __shared__ unsigned char dsm[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsm) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bars[8][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < 8; ++w) for (int d = 0; d < 4; ++d) tc::mbar_init(&bars[w][d], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  const long long t0 = clock64();
+  // each warp keeps `depth` (<= 4) rounds in flight, tiles of 16 KB each (nwarps * depth * 16 KB <= 192 KB)
+  for (int it = 0; it < iters + depth; ++it) {
+    if (it >= depth) tc::mbar_wait(&bars[warp][(it - depth) % depth], (uint32_t)((it - depth) / depth) & 1u, err, 1);
+    if (it < iters) {
+      const int d = it % depth;
+      const int o = ((blockIdx.x * nwarps + warp) * iters + it) * 128 + lane * 4;
+      const int4 r = *reinterpret_cast<const int4*>(idx + (o % n_idx));
+      if (lane == 0) tc::mbar_arrive_expect_tx(&bars[warp][d], 128 * 128);
+      __syncwarp();
+      tma::gather4(tc::smem_u32(base + (warp * depth + d) * 16384) + lane * 512, &map, tc::smem_u32(&bars[warp][d]), 0, r.x, r.y, r.z, r.w);
+    }
+  }
+  const long long t1 = clock64();
+  if (lane == 0 && blockIdx.x == 0) out[warp] = t1 - t0;
+}
+}  // namespace
+
+extern "C" int imf_debug_gather4_rate(const void* X, int32_t ld, int32_t n_rows, const int32_t* idx, int32_t n_idx, int32_t nwarps,
+                                      int32_t iters, int32_t depth, int32_t nctas, long long* out, int32_t* err, cudaStream_t stream) {
+  IMF_CHECK_ARG(X && idx && out && nwarps >= 1 && nwarps <= 8 && depth >= 1 && depth <= 4 && nwarps * depth <= 12 && n_idx % 128 == 0);
+  CUtensorMap map;
+  int rc = tma::encode_2d_u16(&map, X, (uint64_t)n_rows, (uint64_t)ld, (uint64_t)ld, 64, 1);
+  if (rc) { imf_set_error("cuTensorMapEncodeTiled failed: %d", rc); return IMF_ERR_CUDA; }
+  const size_t smem = (size_t)nwarps * depth * 16384 + 1024;
+  IMF_CHECK_CUDA(cudaFuncSetAttribute(k_probe_gather4_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_probe_gather4_rate<<<nctas, nwarps * 32, smem, stream>>>(map, idx, n_idx, iters, depth, out, err);
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
+}

@@ -128,16 +128,20 @@ int imf_sparse_conv_h2_fwd(const void* X, int32_t ldx, int32_t kc_in, const void
 /* "g4" kernel of the h2 tier (csrc/sparse_conv_g4.cu): same operation, data format and packed weights as imf_sparse_conv_h2_fwd, but
  * persistent (one CTA per SM, grid independent of the row count), neighbour rows fetched by TMA tile::gather4 from the offset-major
  * table of imf_kernel_map_t, output written by tiled TMA stores.  n_in_rows / n_y_rows = rows of the X / Y allocations (tensor-map
- * extents; n_y_rows >= n_out_max).  workspace (optional, imf_sparse_conv_g4_workspace_bytes) enables the split mode of small levels. */
+ * extents; n_y_rows >= n_out_max).  zero_row >= 0: rows [zero_row, zero_row+64) of X (inside n_in_rows) are all zero and stand in
+ * for absent neighbours (an in-range row is ~5x cheaper for the TMA unit than its out-of-range zero fill, which zero_row < 0 uses).
+ * workspace (optional, imf_sparse_conv_g4_workspace_bytes) enables the split mode of small levels. */
 size_t imf_sparse_conv_g4_workspace_bytes(int32_t Cout);
-int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t n_in_rows, int32_t kc_in, const void* packed, const int32_t* nbr_t,
+int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t n_in_rows, int32_t zero_row, int32_t kc_in, const void* packed, const int32_t* nbr_t,
                            int32_t ld_n, const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max, int32_t kernel_volume,
                            int32_t Cin, int32_t Cout, const float* scale, const float* shift, const void* residual, int32_t ldr,
                            int32_t kc_r, int32_t relu, void* Y, int32_t ldy, int32_t n_y_rows, int32_t kc_out, void* workspace,
                            size_t workspace_bytes, int32_t* err, imf_stream_t stream);
 /* Profiling hook: device int64 buffer (>= 160 entries) filled by CTA 0 with clock64() stamps (slot map in the source), and an
- * override of the CTAs per output-channel tile (0 = one per SM).  NULL / 0 switch both off. */
-int imf_debug_conv_g4_trace(long long* trace, int32_t grid);
+ * override of the CTAs per output-channel tile (0 = one per SM) and of the producer warps per CTA (8 or 16; other values keep the
+ * current setting); flags: bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs (results are then meaningless).
+ * NULL / 0 switch everything off. */
+int imf_debug_conv_g4_trace(long long* trace, int32_t grid, int32_t producer_warps, int32_t flags);
 
 /* First layer (conv1, model/resunet.py:42-49,168): K in {1,3,5}, Cin in {1,3,6} (ones / rgb / rgb+normal,
  * util/misc.py:66-77), Cout in {32,64,128}; neighbours are
@@ -159,6 +163,11 @@ int imf_debug_conv_trace(long long* trace);
  * the raw tile (16 KB) to `raw`, and stores it with a tiled TMA store to rows [out_row, out_row+128) of O [o_rows, ld] (clipped). */
 int imf_debug_gather4(const void* X, int32_t ld, int32_t n_rows, const int32_t* idx, int32_t col, int32_t box_rows, void* raw, void* O,
                       int32_t o_rows, int32_t out_row, int32_t* err, imf_stream_t stream);
+
+/* Throughput probe of tile::gather4 (tools/tma_selftest.py --rate): nctas CTAs x nwarps warps, each warp issues `iters` rounds of 32
+ * gather4 (128 rows x 128 B) with `depth` rounds in flight; out[w] = cycles of warp w of CTA 0. */
+int imf_debug_gather4_rate(const void* X, int32_t ld, int32_t n_rows, const int32_t* idx, int32_t n_idx, int32_t nwarps, int32_t iters,
+                           int32_t depth, int32_t nctas, long long* out, int32_t* err, imf_stream_t stream);
 
 /* imf_conv_first_fwd writing an h2 matrix (ldy in halves, chunk width kc_out). */
 int imf_conv_first_h2_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords, const int32_t* n_dev,

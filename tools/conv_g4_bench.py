@@ -21,6 +21,9 @@ ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--flush", type=int, default=1)
 ap.add_argument("--grid", type=int, default=0)
 ap.add_argument("--trace", action="store_true")
+ap.add_argument("--npw", type=int, default=0, help="producer warps per CTA (8 or 16)")
+ap.add_argument("--flags", default="0", help="comma list of profiling flags: 1 no W copies, 2 no gathers, 4 no MMAs")
+ap.add_argument("--oob", action="store_true", help="absent neighbours by TMA out-of-range zero fill instead of zero rows")
 ap.add_argument("--old", action="store_true", help="also time imf_sparse_conv_h2_fwd (the cp.async kernel)")
 args = ap.parse_args()
 
@@ -34,7 +37,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 X = torch.randn(n, cin, device="cuda", generator=g)
 W = torch.randn(27, cin, cout, device="cuda", generator=g) / np.sqrt(27 * cin)
 s = torch.cuda.current_stream().cuda_stream
-Xh = torch.zeros(n, 2 * cin, dtype=torch.float16, device="cuda")
+Xh = torch.zeros(n + 64, 2 * cin, dtype=torch.float16, device="cuda")      # 64 trailing zero rows = absent neighbours
 _lib.check(L.imf_h2_pack(X.data_ptr(), cin, n, cin, kci, Xh.data_ptr(), 2 * cin, None, s))
 packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(27, cin, cout, kci)), dtype=torch.uint8, device="cuda")
 _lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), 27, cin, cout, kci, 1024.0, packed.data_ptr(), s))
@@ -49,7 +52,7 @@ alg = 4 * pairs * cin + 8 * pairs + 4 * 27 * cin * cout + 4 * n * cout
 
 
 def g4():
-    _lib.check(L.imf_sparse_conv_g4_fwd(Xh.data_ptr(), 2 * cin, n, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(), None, n,
+    _lib.check(L.imf_sparse_conv_g4_fwd(Xh.data_ptr(), 2 * cin, n + 64, -1 if args.oob else n, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(), None, n,
                                         27, cin, cout, one.data_ptr(), zero.data_ptr(), None, 0, 0, 1, Yh.data_ptr(), 2 * cout, n, kco,
                                         ws.data_ptr(), ws_bytes, err.data_ptr(), s))
 
@@ -70,8 +73,10 @@ def timeit(fn, label):
           f"{alg / np.median(ts) / 1e3:.0f} GB/s   {2 * pairs * cin * cout / np.median(ts) / 1e6:.1f} TFLOP/s (algorithmic)", flush=True)
 
 
-L.imf_debug_conv_g4_trace(None, args.grid)
-timeit(g4, f"g4 grid={args.grid or 148}")
+for fl in [int(f) for f in args.flags.split(",")]:
+    L.imf_debug_conv_g4_trace(None, args.grid, args.npw, fl)
+    timeit(g4, f"g4 grid={args.grid or 148} npw={args.npw or 8} flags={fl}")
+L.imf_debug_conv_g4_trace(None, args.grid, args.npw, 0)
 assert int(err.item()) == 0, int(err.item())
 if args.old:
     nbr = cm.table(1, 1, 3, False)
@@ -82,15 +87,16 @@ if args.old:
                                             err.data_ptr(), s))
     timeit(old, "h2 (cp.async)")
 if args.trace:
-    trace = torch.zeros(160, dtype=torch.int64, device="cuda")
-    L.imf_debug_conv_g4_trace(trace.data_ptr(), args.grid)
+    trace = torch.zeros(512, dtype=torch.int64, device="cuda")
+    L.imf_debug_conv_g4_trace(trace.data_ptr(), args.grid, args.npw, int(args.flags.split(",")[-1]))
     g4()
     torch.cuda.synchronize()
-    L.imf_debug_conv_g4_trace(None, 0)
+    L.imf_debug_conv_g4_trace(None, 0, 0, 0)
     t = trace.cpu().numpy()
     names = ["start", "barriers+TMEM", "masks", "epi wait", "acc ready", "epilogue done", "exit"]
     print("CTA0 timeline (cycles):", {nm: int(t[i] - t[0]) for i, nm in enumerate(names)})
-    for i in range(64):
-        if t[16 + 2 * i] == 0:
+    for i in range(36):
+        r = t[16 + 4 * i: 20 + 4 * i]
+        if r[2] == 0:
             break
-        print(f"  stage {i:3d}: issued {int(t[16 + 2 * i] - t[0]):7d}   mma-saw-full {int(t[17 + 2 * i] - t[0]):7d}")
+        print(f"  stage {i:3d}: producer at wait {int(r[0] - t[0]):7d}  slot free {int(r[1] - t[0]):7d}   mma saw full {int(r[2] - t[0]):7d}  committed {int(r[3] - t[0]):7d}")
