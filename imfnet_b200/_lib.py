@@ -32,7 +32,7 @@ SIGNATURES = {
     "imf_kernel_map": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _i32, _p, _p]),
     "imf_kernel_map_t": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _i32, _p, _i32, _p, _p]),
     "imf_sparse_conv_g4_workspace_bytes": (_sz, [_i32]),
-    "imf_sparse_conv_g4_fwd": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i32,
+    "imf_sparse_conv_g4_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i32,
                                         _p, _i32, _i32, _i32, _p, _sz, _p, _p]),
     "imf_debug_conv_g4_trace": (C.c_int, [_p, _i32, _i32, _i32]),
     "imf_quantize_points": (C.c_int, [_p, _i32, _f64, _i32, _p, _p]),

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ CUtensorMap tmY, const unsigned char* __restrict__ Wp,
                  const int* __restrict__ nbr_t, int ld_n, const unsigned* __restrict__ tile_mask, const int* __restrict__ n_ptr, int n_max,
                  int K3, int nchunks, const float* __restrict__ scale, const float* __restrict__ shift, const __half* __restrict__ R, int ldr,
-                 int kc_r, int relu, int kc_out, float* __restrict__ P, int cout_total, int zero_row, int* err, long long* __restrict__ trace, int dbg) {
+                 int kc_r, int relu, int kc_out, float* __restrict__ P, int cout_total, int* err, long long* __restrict__ trace, int dbg) {
   using Cfg = G4Cfg<BN, KC>;
   constexpr int NA = Cfg::NA;
   extern __shared__ unsigned char smem_dyn[];
@@ -185,6 +185,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   __shared__ unsigned jmask_s[32];
   __shared__ int nk_s;
   __shared__ int ring_s[5];
+  __shared__ int turn_s;                                 // next stage (running count) whose MMAs may be issued
   __shared__ float sc_s[BN], sh_s[BN];
   __shared__ __align__(16) int idx_s[NA][2][kBM];      // neighbour indices of each producer warp's current / next stage
 
@@ -224,6 +225,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
     for (int s = 0; s < NA; ++s) { tc::mbar_init(&full_a[s], 32); tc::mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < kNW; ++s) { tc::mbar_init(&full_w[s], 1); tc::mbar_init(&empty_w[s], kNMW); }
     tc::mbar_init(&acc_bar, kNMW);
+    turn_s = 0;
     tc::fence_barrier_init();
     tma::prefetch_map(&tmY);
   }
@@ -422,6 +424,9 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
         if ((a_slot & (kNMW - 1)) == mw) {
           tc::mbar_wait(&full_a[a_slot], a_phase, err, 4);
           if (lane == 0) {
+            // stages are ISSUED in walk order whichever warp owns them (a turn counter in shared memory), so every accumulator
+            // receives its products in the same order on every run: bit-reproducible results
+            while (*reinterpret_cast<volatile int*>(&turn_s) != ac) {}
             if (trace && ac < 36) trace[18 + 4 * ac] = clock64();
             const uint32_t a0 = tc::smem_u32(a_ring + a_slot * Cfg::A_BYTES);
             const uint32_t w0 = tc::smem_u32(w_ring + ws * Cfg::W_BYTES);
@@ -444,6 +449,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
                 g4_mma_f16(d, tc::smem_desc_sw128(a0 + 64 + o), tc::smem_desc_sw128(w0 + 64 + o), idesc1, 1u);     // lo . Whi
               }
             }
+            *reinterpret_cast<volatile int*>(&turn_s) = ac + 1;
             tc::mma_commit(&empty_a[a_slot]);
             if (trace && ac < 36) trace[19 + 4 * ac] = clock64();
           }
@@ -617,7 +623,7 @@ int g_g4_grid = 0;        // profiling hook: overrides the number of CTAs per ou
 template <int BN, int KC>
 int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, const int* nbr_t, int ld_n, const unsigned* tile_mask,
               const int* n_ptr, int n_max, int K3, int Cin, int Cout, const float* scale, const float* shift, const __half* R, int ldr,
-              int kc_r, int relu, __half* Y, int ldy, int kc_out, int zero_row, void* ws, size_t ws_bytes, int* err, cudaStream_t stream) {
+              int kc_r, int relu, __half* Y, int ldy, int kc_out, void* ws, size_t ws_bytes, int* err, cudaStream_t stream) {
   using Cfg = G4Cfg<BN, KC>;
   const size_t smem = (size_t)Cfg::RING_BYTES + (size_t)kNW * Cfg::W_BYTES + 1024;
   static bool attr_done = false;
@@ -638,7 +644,7 @@ int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, 
   dim3 grid(gx, 1, ntn);
   k_sparse_conv_g4<BN, KC><<<grid, kThreads, smem, stream>>>(X, ldx, tmY, reinterpret_cast<const unsigned char*>(Wp), nbr_t, ld_n, tile_mask,
                                                             n_ptr, n_max, K3, nchunks, scale, shift, R, ldr, kc_r, relu, kc_out, P, Cout,
-                                                            zero_row, err, g_g4_trace, g_g4_dbg);
+                                                            err, g_g4_trace, g_g4_dbg);
   IMF_CHECK_LAUNCH();
   if (P != nullptr) {      // split mode is possible for small n: the reduce kernel decides on the device (no-op otherwise)
     const int rows = n_max < gx * kBM ? n_max : gx * kBM;
@@ -662,14 +668,13 @@ extern "C" int imf_debug_conv_g4_trace(long long* trace, int32_t grid, int32_t p
 
 extern "C" size_t imf_sparse_conv_g4_workspace_bytes(int32_t Cout) { return (size_t)kSMs * kBM * (size_t)Cout * sizeof(float); }
 
-extern "C" int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t n_in_rows, int32_t zero_row, int32_t kc_in, const void* packed, const int32_t* nbr_t,
+extern "C" int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t kc_in, const void* packed, const int32_t* nbr_t,
                                       int32_t ld_n, const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max,
                                       int32_t kernel_volume, int32_t Cin, int32_t Cout, const float* scale, const float* shift,
                                       const void* residual, int32_t ldr, int32_t kc_r, int32_t relu, void* Y, int32_t ldy,
                                       int32_t n_y_rows, int32_t kc_out, void* workspace, size_t workspace_bytes, int32_t* err,
                                       cudaStream_t stream) {
-  IMF_CHECK_ARG(n_out_max >= 0 && kernel_volume >= 1 && kernel_volume <= 27 && n_in_rows >= 0);
-  IMF_CHECK_ARG(zero_row < 0 || zero_row + 64 <= n_in_rows);
+  IMF_CHECK_ARG(n_out_max >= 0 && kernel_volume >= 1 && kernel_volume <= 27);
   IMF_CHECK_ARG((kc_in == 32 || kc_in == 64) && Cin > 0 && Cin % kc_in == 0 && (Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256));
   IMF_CHECK_ARG((kc_out == 32 || kc_out == 64) && Cout % kc_out == 0);
   IMF_CHECK_ARG(scale != nullptr && shift != nullptr);
@@ -677,7 +682,7 @@ extern "C" int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t n_in_r
   IMF_CHECK_ARG(residual == nullptr || ((kc_r == 32 || kc_r == 64) && Cout % kc_r == 0 && ldr % 8 == 0 && ldr >= 2 * Cout));
   IMF_CHECK_ARG(ld_n % 4 == 0 && ld_n >= ((n_out_max + 31) & ~31));
   if (n_out_max == 0) return IMF_OK;
-  IMF_CHECK_ARG(X != nullptr && packed != nullptr && nbr_t != nullptr && tile_mask != nullptr && Y != nullptr && n_in_rows > 0);
+  IMF_CHECK_ARG(X != nullptr && packed != nullptr && nbr_t != nullptr && tile_mask != nullptr && Y != nullptr);
   IMF_CHECK_ARG(((uintptr_t)X % 16) == 0 && ((uintptr_t)packed % 16) == 0 && ((uintptr_t)Y % 16) == 0 && ((uintptr_t)residual % 16) == 0 &&
                 ((uintptr_t)nbr_t % 16) == 0);
   CUtensorMap tmY;
@@ -687,7 +692,7 @@ extern "C" int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t n_in_r
   __half* Yh = reinterpret_cast<__half*>(Y);
 #define IMF_GO(BN, KC)                                                                                                               \
   return launch_g4<BN, KC>(reinterpret_cast<const __half*>(X), ldx, tmY, packed, nbr_t, ld_n, tile_mask, n_out_dev, n_out_max, kernel_volume, Cin, Cout, scale, shift, Rh, \
-                           ldr, kc_r, relu, Yh, ldy, kc_out, zero_row, workspace, workspace_bytes, err, stream)
+                           ldr, kc_r, relu, Yh, ldy, kc_out, workspace, workspace_bytes, err, stream)
   const int bn = Cout > 128 ? 128 : Cout;
   if (kc_in == 64) {
     if (bn == 32) IMF_GO(32, 64);

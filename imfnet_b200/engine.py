@@ -82,16 +82,19 @@ class FusedPlan:
         self._key = self._weights_key()
 
     # -- launch helpers ------------------------------------------------------------------------
-    def _conv(self, L, cname, X, ldx, nbr, n_out, R, ldr, kc_r, relu, Y, ldy, kc_out, stream):
-        """One 3x3x3 convolution + folded BatchNorm (+ residual) (+ ReLU); X, R, Y are h2 matrices (ld in halves)."""
+    def _conv(self, L, cname, X, ldx, tab, n_out, R, ldr, kc_r, relu, Y, ldy, kc_out, stream):
+        """One 3x3x3 convolution + folded BatchNorm (+ residual) (+ ReLU); X, R, Y are h2 matrices (ld in halves);
+        tab = CoordinateManager.table_t(...) (offset-major neighbour table, its row stride, tile masks)."""
         conv, packed, scale, shift, kci = self.conv[cname]
+        nbr_t, ld_n, tile_mask = tab
         ws, ws_bytes = None, 0
-        if n_out < 12800:                     # few row tiles: let the kernel split a tile's offsets over several CTAs
-            ws_bytes = int(L.imf_sparse_conv_h2_workspace_bytes(n_out, conv.out_channels))
+        if n_out < 128 * 148:                 # fewer row tiles than SMs: let the kernel split a tile's offsets over several CTAs
+            ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(conv.out_channels))
             ws = self.arena.take(ws_bytes)
-        _lib.check(L.imf_sparse_conv_h2_fwd(X, ldx, kci, packed.data_ptr(), nbr.data_ptr(), None, n_out, 27, conv.in_channels,
-                                            conv.out_channels, scale.data_ptr(), shift.data_ptr(), R, ldr, kc_r, 1 if relu else 0,
-                                            Y, ldy, kc_out, _lib.ptr(ws), ws_bytes, self.err.data_ptr(), stream))
+        _lib.check(L.imf_sparse_conv_g4_fwd(X, ldx, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(), None, n_out,
+                                            27, conv.in_channels, conv.out_channels, scale.data_ptr(), shift.data_ptr(), R, ldr, kc_r,
+                                            1 if relu else 0, Y, ldy, n_out, kc_out, _lib.ptr(ws), ws_bytes, self.err.data_ptr(),
+                                            stream))
 
     def _block(self, L, name, X, ldx, kc_x, nbr, n, C, tmp, Y, ldy, kc_y, stream):
         """BasicBlockBN (model/residual_block.py:37-53): X -> tmp = relu(bn1(conv1 X)) -> Y = relu(bn2(conv2 tmp) + X)."""
@@ -141,9 +144,9 @@ class FusedPlan:
             self._raise_on_status(int(self.err_host[0]))   # status of earlier forwards (build_pyramid synchronised the stream)
             lv = {t: cm.level(t) for t in (1, 2, 4, 8)}
             n1, n2, n4, n8 = lv[1].n, lv[2].n, lv[4].n, lv[8].n
-            nb = {t: cm.table(t, t, 3, False) for t in (1, 2, 4, 8)}
-            dn = {(1, 2): cm.table(1, 2, 3, False), (2, 4): cm.table(2, 4, 3, False), (4, 8): cm.table(4, 8, 3, False)}
-            up = {(8, 4): cm.table(8, 4, 3, True), (4, 2): cm.table(4, 2, 3, True), (2, 1): cm.table(2, 1, 3, True)}
+            nb = {t: cm.table_t(t, t, 3, False) for t in (1, 2, 4, 8)}
+            dn = {(1, 2): cm.table_t(1, 2, 3, False), (2, 4): cm.table_t(2, 4, 3, False), (4, 8): cm.table_t(4, 8, 3, False)}
+            up = {(8, 4): cm.table_t(8, 4, 3, True), (4, 2): cm.table_t(4, 2, 3, True), (2, 1): cm.table_t(2, 1, 3, True)}
 
             self.arena.reset()
             buf = self.arena.floats        # an h2 matrix of C channels occupies exactly the bytes of an fp32 [n, C] matrix

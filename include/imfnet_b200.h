@@ -126,18 +126,17 @@ int imf_sparse_conv_h2_fwd(const void* X, int32_t ldx, int32_t kc_in, const void
                            void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
 
 /* "g4" kernel of the h2 tier (csrc/sparse_conv_g4.cu): same operation, data format and packed weights as imf_sparse_conv_h2_fwd, but
- * persistent (one CTA per SM, grid independent of the row count), neighbour rows fetched by TMA tile::gather4 from the offset-major
- * table of imf_kernel_map_t, output written by tiled TMA stores.  n_in_rows / n_y_rows = rows of the X / Y allocations (tensor-map
- * extents; n_y_rows >= n_out_max).  zero_row >= 0: rows [zero_row, zero_row+64) of X (inside n_in_rows) are all zero and stand in
- * for absent neighbours (an in-range row is ~5x cheaper for the TMA unit than its out-of-range zero fill, which zero_row < 0 uses).
- * workspace (optional, imf_sparse_conv_g4_workspace_bytes) enables the split mode of small levels. */
+ * persistent (one CTA per SM, launch shape independent of the row count, all sizes read from n_out_dev on the device), reading the
+ * offset-major table + tile masks of imf_kernel_map_t, sharing each weight slab between the sub-tiles of a CTA, and writing the output
+ * with tiled TMA stores.  n_y_rows = rows of the Y allocation (tensor-map extent, >= n_out_max; rows in [n, roundup32(n)) that exist
+ * may be overwritten).  workspace (optional, imf_sparse_conv_g4_workspace_bytes) enables the split mode used when n < 128 * #SMs. */
 size_t imf_sparse_conv_g4_workspace_bytes(int32_t Cout);
-int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t n_in_rows, int32_t zero_row, int32_t kc_in, const void* packed, const int32_t* nbr_t,
-                           int32_t ld_n, const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max, int32_t kernel_volume,
-                           int32_t Cin, int32_t Cout, const float* scale, const float* shift, const void* residual, int32_t ldr,
-                           int32_t kc_r, int32_t relu, void* Y, int32_t ldy, int32_t n_y_rows, int32_t kc_out, void* workspace,
-                           size_t workspace_bytes, int32_t* err, imf_stream_t stream);
-/* Profiling hook: device int64 buffer (>= 160 entries) filled by CTA 0 with clock64() stamps (slot map in the source), and an
+int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t kc_in, const void* packed, const int32_t* nbr_t, int32_t ld_n,
+                           const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max, int32_t kernel_volume, int32_t Cin,
+                           int32_t Cout, const float* scale, const float* shift, const void* residual, int32_t ldr, int32_t kc_r,
+                           int32_t relu, void* Y, int32_t ldy, int32_t n_y_rows, int32_t kc_out, void* workspace, size_t workspace_bytes,
+                           int32_t* err, imf_stream_t stream);
+/* Profiling hook: device int64 buffer (>= 512 entries) filled by CTA 0 with clock64() stamps (slot map in the source), and an
  * override of the CTAs per output-channel tile (0 = one per SM) and of the producer warps per CTA (8 or 16; other values keep the
  * current setting); flags: bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs (results are then meaningless).
  * NULL / 0 switch everything off. */

@@ -170,7 +170,7 @@ def test_h2_tensor_core_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout, sp
     close(out, ref, H2_RTOL)
 
 
-def run_conv_g4(X, W, tab, n_out, scale, shift, R=None, relu=False, split=True, kc_out=None, n_dev=None, extra_rows=0, zero_rows=True):
+def run_conv_g4(X, W, tab, n_out, scale, shift, R=None, relu=False, split=True, kc_out=None, n_dev=None, extra_rows=0):
     """fp32 in/out wrapper of the TMA-gather kernel: pack -> conv -> unpack.  tab = CoordinateManager.table_t(...)."""
     L = _lib.lib()
     nbr_t, ld_n, tile_mask = tab
@@ -181,16 +181,13 @@ def run_conv_g4(X, W, tab, n_out, scale, shift, R=None, relu=False, split=True, 
     packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(K3, cin, cout, kc_in)), dtype=torch.uint8, device="cuda")
     _lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), K3, cin, cout, kc_in, wmul, packed.data_ptr(), _lib.cur_stream()))
     Xh = h2_pack(X, kc_in, ld_extra=8)
-    n_x = Xh.shape[0]
-    if zero_rows:                                        # 64 all-zero rows after the data stand in for absent neighbours
-        Xh = torch.cat([Xh, torch.zeros((64, Xh.shape[1]), dtype=torch.float16, device="cuda")], dim=0).contiguous()
     Rh = None if R is None else h2_pack(R, kc_out, ld_extra=16)
     Yh = torch.full((n_out + extra_rows, 2 * cout + 8), float("nan"), dtype=torch.float16, device="cuda")
     ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(cout)) if split else 0
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     sc = (scale / wmul).contiguous()
-    _lib.check(L.imf_sparse_conv_g4_fwd(Xh.data_ptr(), Xh.stride(0), Xh.shape[0], n_x if zero_rows else -1, kc_in, packed.data_ptr(), nbr_t.data_ptr(), ld_n,
+    _lib.check(L.imf_sparse_conv_g4_fwd(Xh.data_ptr(), Xh.stride(0), kc_in, packed.data_ptr(), nbr_t.data_ptr(), ld_n,
                                         tile_mask.data_ptr(), _lib.ptr(n_dev), n_out, K3, cin, cout, sc.data_ptr(), shift.data_ptr(),
                                         _lib.ptr(Rh), 0 if Rh is None else Rh.stride(0), kc_out, int(relu), Yh.data_ptr(), Yh.stride(0),
                                         Yh.shape[0], kc_out, ws.data_ptr() if split else None, ws_bytes, err.data_ptr(),
@@ -221,9 +218,10 @@ def test_offset_major_table_matches_oracle(frag, t_in, t_out, tr):
     (1, 1, False, 32, 32), (1, 1, False, 64, 64), (1, 2, False, 32, 64), (2, 2, False, 64, 64), (2, 4, False, 64, 128),
     (4, 4, False, 128, 128), (4, 8, False, 128, 256), (8, 8, False, 256, 256), (8, 4, True, 256, 128), (4, 2, True, 256, 64),
     (2, 1, True, 128, 64)])
-@pytest.mark.parametrize("split,zero_rows", [(False, True), (True, True), (True, False)])
-def test_g4_tma_gather_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout, split, zero_rows):
-    """TMA tile::gather4 + tcgen05 kind::f16 persistent kernel: same contract and tolerance as the h2 kernel."""
+@pytest.mark.parametrize("split", [False, True])
+def test_g4_persistent_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout, split):
+    """Persistent tcgen05 kind::f16 kernel (offset-major table, shared weight slabs, TMA-store epilogue): same contract and tolerance
+    as the h2 kernel."""
     coords, ocm, cm = frag
     g = torch.Generator().manual_seed(cin * 1000 + cout + t_in)
     n_in, n_out = len(ocm.get(t_in)), len(ocm.get(t_out))
@@ -232,8 +230,7 @@ def test_g4_tma_gather_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout, spl
     scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
     R = torch.randn(n_out, cout, generator=g)
     ref = torch.relu(sparse_ops.conv_forward(X, W, ocm.table(t_in, t_out, 3, tr)) * scale + shift + R)
-    out = run_conv_g4(X.cuda(), W.cuda(), cm.table_t(t_in, t_out, 3, tr), n_out, scale.cuda(), shift.cuda(), R.cuda(), True, split,
-                      zero_rows=zero_rows)
+    out = run_conv_g4(X.cuda(), W.cuda(), cm.table_t(t_in, t_out, 3, tr), n_out, scale.cuda(), shift.cuda(), R.cuda(), True, split)
     close(out, ref, H2_RTOL)
 
 

@@ -23,7 +23,6 @@ ap.add_argument("--grid", type=int, default=0)
 ap.add_argument("--trace", action="store_true")
 ap.add_argument("--npw", type=int, default=0, help="producer warps per CTA (8 or 16)")
 ap.add_argument("--flags", default="0", help="comma list of profiling flags: 1 no W copies, 2 no gathers, 4 no MMAs")
-ap.add_argument("--oob", action="store_true", help="absent neighbours by TMA out-of-range zero fill instead of zero rows")
 ap.add_argument("--old", action="store_true", help="also time imf_sparse_conv_h2_fwd (the cp.async kernel)")
 args = ap.parse_args()
 
@@ -37,7 +36,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 X = torch.randn(n, cin, device="cuda", generator=g)
 W = torch.randn(27, cin, cout, device="cuda", generator=g) / np.sqrt(27 * cin)
 s = torch.cuda.current_stream().cuda_stream
-Xh = torch.zeros(n + 64, 2 * cin, dtype=torch.float16, device="cuda")      # 64 trailing zero rows = absent neighbours
+Xh = torch.zeros(n, 2 * cin, dtype=torch.float16, device="cuda")
 _lib.check(L.imf_h2_pack(X.data_ptr(), cin, n, cin, kci, Xh.data_ptr(), 2 * cin, None, s))
 packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(27, cin, cout, kci)), dtype=torch.uint8, device="cuda")
 _lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), 27, cin, cout, kci, 1024.0, packed.data_ptr(), s))
@@ -52,7 +51,7 @@ alg = 4 * pairs * cin + 8 * pairs + 4 * 27 * cin * cout + 4 * n * cout
 
 
 def g4():
-    _lib.check(L.imf_sparse_conv_g4_fwd(Xh.data_ptr(), 2 * cin, n + 64, -1 if args.oob else n, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(), None, n,
+    _lib.check(L.imf_sparse_conv_g4_fwd(Xh.data_ptr(), 2 * cin, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(), None, n,
                                         27, cin, cout, one.data_ptr(), zero.data_ptr(), None, 0, 0, 1, Yh.data_ptr(), 2 * cout, n, kco,
                                         ws.data_ptr(), ws_bytes, err.data_ptr(), s))
 
