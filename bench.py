@@ -126,13 +126,13 @@ def run_reference(args, rank, world):
 def dominant_kernel_roofline(model, frag, flush):
     """block2_tr-shaped convolution (64->64, 3^3, stride-1 level, BatchNorm + ReLU folded): the largest single launch of
     the forward (179.6 MB algorithmic bytes at C2), run through the same entry point and packed weights the
-    forward uses (imf_sparse_conv_h2_fwd).  Timed live with CUDA events on the launching stream, L2 flushed between launches."""
+    forward uses (imf_sparse_conv_g4_fwd).  Timed live with CUDA events on the launching stream, L2 flushed between launches."""
     from imfnet_b200 import _lib
     from imfnet_b200.sparse import CoordinateManager
     L = _lib.lib()
     coords = frag[0].cuda()
     cm = CoordinateManager(coords)
-    nbr = cm.table(1, 1, 3, False)
+    nbr_t, ld_n, tile_mask = cm.table_t(1, 1, 3, False)
     n = len(coords)
     conv, packed, scale, shift, kci = model._plan.conv["block2_tr.conv1"]
     cin, cout = conv.in_channels, conv.out_channels
@@ -143,7 +143,9 @@ def dominant_kernel_roofline(model, frag, flush):
     _lib.check(L.imf_h2_pack(X.data_ptr(), cin, n, cin, kci, Xh.data_ptr(), 2 * cin, None, s))
     Yh = torch.empty(n, 2 * cout, dtype=torch.float16, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
-    pairs = int((nbr >= 0).sum())
+    ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(cout))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    pairs = int((nbr_t[:, :n] >= 0).sum())
     # gathered inputs + in/out indices + weights once + output (activations are 4 bytes/channel: fp16 hi + lo)
     alg_bytes = 4 * pairs * cin + 8 * pairs + 4 * 27 * cin * cout + 4 * n * cout
     times = []
@@ -151,9 +153,9 @@ def dominant_kernel_roofline(model, frag, flush):
         flush()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(L.imf_sparse_conv_h2_fwd(Xh.data_ptr(), 2 * cin, kci, packed.data_ptr(), nbr.data_ptr(), None, n, 27, cin, cout,
-                                            scale.data_ptr(), shift.data_ptr(), None, 0, 0, 1, Yh.data_ptr(), 2 * cout, kco,
-                                            None, 0, err.data_ptr(), s))
+        _lib.check(L.imf_sparse_conv_g4_fwd(Xh.data_ptr(), 2 * cin, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(),
+                                            None, n, 27, cin, cout, scale.data_ptr(), shift.data_ptr(), None, 0, 0, 1, Yh.data_ptr(),
+                                            2 * cout, n, kco, ws.data_ptr(), ws_bytes, err.data_ptr(), s))
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:
@@ -162,7 +164,7 @@ def dominant_kernel_roofline(model, frag, flush):
     ms = float(np.mean(times))
     peak, how = load_peaks()
     achieved = alg_bytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": f"k_sparse_conv_h2<64,64> 3x3x3 {cin}->{cout} @ {n} voxels ({pairs} pairs)", "achieved": achieved,
+    return {"bound": "hbm", "kernel": f"k_sparse_conv_g4<64,64> 3x3x3 {cin}->{cout} @ {n} voxels ({pairs} pairs)", "achieved": achieved,
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "alg_bytes_per_launch": alg_bytes,
             "ms_per_launch": ms, "flops_per_launch": 2 * pairs * cin * cout, "peak_source": how}
 
@@ -209,7 +211,8 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        l0 = L.imf_launch_count()
+        from imfnet_b200.engine import GraphPlan
+        l0 = L.imf_launch_count() + GraphPlan.replayed_launches
         ms = 0.0
         wall0 = time.perf_counter()
         for i in range(args.steps):
@@ -222,7 +225,7 @@ def run_ours(args, rank, world, local_rank):
             ms += e0.elapsed_time(e1)
         barrier()
         wall = time.perf_counter() - wall0
-        launches = L.imf_launch_count() - l0
+        launches = L.imf_launch_count() + GraphPlan.replayed_launches - l0
         clocks = sampler.stop()
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -276,6 +279,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "flushed between steps (256 MiB write, outside the per-step CUDA events)",
                    "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
                    "coordinate_maps": "rebuilt every step (cold), as the reference does per SparseTensor",
+                   "execution": "one captured CUDA graph replay per fragment (device-side sizes)" if model.use_cuda_graph else "eager launches",
                    "parallelism": f"fragments sharded over {world} GPU(s), no data-path collective"},
         "e2e": {"value": e2e_v, "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},

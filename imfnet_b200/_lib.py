@@ -44,6 +44,10 @@ SIGNATURES = {
     "imf_sparse_conv_tc_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _i32, _p, _sz, _p, _p]),
     "imf_h2_pack": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p, _p]),
     "imf_h2_unpack": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p]),
+    "imf_h2_pack_n": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p, _p]),
+    "imf_h2_unpack_n": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p]),
+    "imf_tc_gemm_m": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _i32, _p, _i32, _i32, _f32, _p, _p, _i32, _i32, _p, _sz, _p, _p]),
+    "imf_attention_fusion_fwd_m": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _p, _i32, _p, _i32, _p, _sz, _p]),
     "imf_sparse_conv_h2_packed_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "imf_sparse_conv_h2_pack": (C.c_int, [_p, _i32, _i32, _i32, _i32, _f32, _p, _p]),
     "imf_sparse_conv_h2_workspace_bytes": (_sz, [_i32, _i32]),
@@ -57,6 +61,10 @@ SIGNATURES = {
     "imf_pointwise_tail_h2_fwd": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _p, _i32, _p]),
     "imf_conv_first_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _p]),
     "imf_pointwise_tail_fwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _i32, _p]),
+    "imf_image_conv_table": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p]),
+    "imf_image_im2col_h2": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p]),
+    "imf_image_maxpool_h2": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p]),
+    "imf_transpose_tokens": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "imf_linear_fwd": (C.c_int, [_p, _i32, _p, _p, _i32, _i32, _i32, _p, _i32, _p]),
     "imf_tc_gemm_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "imf_tc_gemm": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _i32, _i32, _i32, _f32, _p, _p, _i32, _i32, _p, _sz, _p, _p]),

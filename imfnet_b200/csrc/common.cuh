@@ -50,6 +50,10 @@ extern "C" int imf_tc_gemm(const float* A, int32_t lda, const float* B, int32_t 
                            int32_t K, float alpha, const float* bias, const float* R, int32_t ldr, int32_t geglu, void* workspace,
                            size_t workspace_bytes, int32_t* err, cudaStream_t stream);
 
+extern "C" int imf_tc_gemm_m(const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc, int32_t M,
+                             const int32_t* m_dev, int32_t N, int32_t K, float alpha, const float* bias, const float* R, int32_t ldr,
+                             int32_t geglu, void* workspace, size_t workspace_bytes, int32_t* err, cudaStream_t stream);
+
 // ---- coordinate keys + open-addressing hash table ------------------------------------------------
 // One slot = 16 bytes so that a probe is a single 128-bit load.
 struct __align__(16) ImfSlot {

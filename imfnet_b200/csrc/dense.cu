@@ -14,8 +14,9 @@ namespace {
 // ---- LayerNorm over the last dim of row-major rows; one warp per row, C <= 1024, C % 32 == 0 ----
 __global__ void __launch_bounds__(256) k_layernorm_rows(const float* __restrict__ X, int ldx, int M, int C,
                                                         const float* __restrict__ g, const float* __restrict__ b, float eps,
-                                                        float* __restrict__ Y, int ldy) {
+                                                        float* __restrict__ Y, int ldy, const int* __restrict__ m_ptr) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m_ptr) { const int v = *m_ptr; M = v < M ? v : M; }
   if (row >= M) return;
   const float* x = X + (size_t)row * ldx;
   float v[32];
@@ -69,10 +70,11 @@ __global__ void __launch_bounds__(256) k_layernorm_tokens_chw(const float* __res
 }
 
 // ---- row softmax in place, one CTA per row ---------------------------------------------------------
-__global__ void __launch_bounds__(256) k_softmax_rows(float* __restrict__ S, int lds, int M, int L) {
+__global__ void __launch_bounds__(256) k_softmax_rows(float* __restrict__ S, int lds, int M, int L, const int* __restrict__ m_ptr) {
   __shared__ float red[8];
   __shared__ float bcast;
   const int row = blockIdx.x;
+  if (m_ptr) { const int v = *m_ptr; M = v < M ? v : M; }
   if (row >= M) return;
   float* s = S + (size_t)row * lds;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -235,7 +237,7 @@ extern "C" int imf_attention_kv(const imf_attn_weights_t* w, const float* tokens
   if (channel_major)
     k_layernorm_tokens_chw<<<(L + 31) / 32, 256, 0, stream>>>(tokens, L, w->ln_c_w, w->ln_c_b, 1e-5f, cn);
   else
-    k_layernorm_rows<<<(L + 7) / 8, 256, 0, stream>>>(tokens, w->dim, L, w->dim, w->ln_c_w, w->ln_c_b, 1e-5f, cn, w->dim);
+    k_layernorm_rows<<<(L + 7) / 8, 256, 0, stream>>>(tokens, w->dim, L, w->dim, w->ln_c_w, w->ln_c_b, 1e-5f, cn, w->dim, nullptr);
   IMF_CHECK_LAUNCH();
   const int inner = w->inner, dim = w->dim, Lp = round4(L);
   float* Kmat = kv;
@@ -257,9 +259,19 @@ extern "C" size_t imf_attention_workspace_bytes(int32_t M, int32_t L, int32_t la
 }
 
 // out[M, latent] = cross-attention + GEGLU feed-forward of M point tokens P[M, latent] against kv (imf_attention_kv).
+extern "C" int imf_attention_fusion_fwd_m(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const int32_t* m_dev,
+                                          const float* kv, int32_t L, float* out, int32_t ldo, void* workspace, size_t workspace_bytes,
+                                          cudaStream_t stream);
 extern "C" int imf_attention_fusion_fwd(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const float* kv,
                                         int32_t L, float* out, int32_t ldo, void* workspace, size_t workspace_bytes,
                                         cudaStream_t stream) {
+  return imf_attention_fusion_fwd_m(w, P, ldp, M, nullptr, kv, L, out, ldo, workspace, workspace_bytes, stream);
+}
+
+// Same with an optional device-side token count: only min(*m_dev, M) rows are computed (M sizes launches and workspace).
+extern "C" int imf_attention_fusion_fwd_m(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const int32_t* m_dev,
+                                          const float* kv, int32_t L, float* out, int32_t ldo, void* workspace, size_t workspace_bytes,
+                                          cudaStream_t stream) {
   IMF_CHECK_ARG(w != nullptr && M >= 0 && L >= 1);
   IMF_CHECK_ARG(w->latent % 32 == 0 && w->latent <= 1024 && w->inner % 4 == 0);
   if (M == 0) return IMF_OK;
@@ -280,24 +292,24 @@ extern "C" int imf_attention_fusion_fwd(const imf_attn_weights_t* w, const float
   const float* Vt = reinterpret_cast<const float*>(reinterpret_cast<const char*>(kv) + r256((size_t)L * inner * 4));
   const float sm_scale = 1.0f / sqrtf((float)inner);
   int rc;
-  k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(P, ldp, M, latent, w->ln_q_w, w->ln_q_b, 1e-5f, xn, latent);
+  k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(P, ldp, M, latent, w->ln_q_w, w->ln_q_b, 1e-5f, xn, latent, m_dev);
   IMF_CHECK_LAUNCH();
   // q = LN(P) . Wq^T
-  if ((rc = imf_tc_gemm(xn, latent, w->wq, latent, q, inner, M, inner, latent, 1.f, nullptr, nullptr, 0, 0, gws, gws_bytes, nullptr, stream))) return rc;
+  if ((rc = imf_tc_gemm_m(xn, latent, w->wq, latent, q, inner, M, m_dev, inner, latent, 1.f, nullptr, nullptr, 0, 0, gws, gws_bytes, nullptr, stream))) return rc;
   // S = (q . K^T) * scale
-  if ((rc = imf_tc_gemm(q, inner, Kmat, inner, S, Lp, M, L, inner, sm_scale, nullptr, nullptr, 0, 0, nullptr, 0, nullptr, stream))) return rc;
-  k_softmax_rows<<<M, 256, 0, stream>>>(S, Lp, M, L);
+  if ((rc = imf_tc_gemm_m(q, inner, Kmat, inner, S, Lp, M, m_dev, L, inner, sm_scale, nullptr, nullptr, 0, 0, nullptr, 0, nullptr, stream))) return rc;
+  k_softmax_rows<<<M, 256, 0, stream>>>(S, Lp, M, L, m_dev);
   IMF_CHECK_LAUNCH();
   // o = A . V   (as A . (V^T)^T, split over the L tokens)
-  if ((rc = imf_tc_gemm(S, Lp, Vt, Lp, o, inner, M, inner, L, 1.f, nullptr, nullptr, 0, 0, gws, gws_bytes, nullptr, stream))) return rc;
+  if ((rc = imf_tc_gemm_m(S, Lp, Vt, Lp, o, inner, M, m_dev, inner, L, 1.f, nullptr, nullptr, 0, 0, gws, gws_bytes, nullptr, stream))) return rc;
   // x1 = o . Wo^T + bo + P
-  if ((rc = imf_tc_gemm(o, inner, w->wo, inner, x1, latent, M, latent, inner, 1.f, w->bo, P, ldp, 0, gws, gws_bytes, nullptr, stream))) return rc;
-  k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(x1, latent, M, latent, w->ln_f_w, w->ln_f_b, 1e-5f, xn, latent);
+  if ((rc = imf_tc_gemm_m(o, inner, w->wo, inner, x1, latent, M, m_dev, latent, inner, 1.f, w->bo, P, ldp, 0, gws, gws_bytes, nullptr, stream))) return rc;
+  k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(x1, latent, M, latent, w->ln_f_w, w->ln_f_b, 1e-5f, xn, latent, m_dev);
   IMF_CHECK_LAUNCH();
   // hid = geglu(LN(x1) . W1^T + b1)   [M, 4*latent]
-  if ((rc = imf_tc_gemm(xn, latent, w->w1, latent, hid, 4 * latent, M, 4 * latent, latent, 1.f, w->b1, nullptr, 0, 1, nullptr, 0, nullptr, stream))) return rc;
+  if ((rc = imf_tc_gemm_m(xn, latent, w->w1, latent, hid, 4 * latent, M, m_dev, 4 * latent, latent, 1.f, w->b1, nullptr, 0, 1, nullptr, 0, nullptr, stream))) return rc;
   // out = hid . W2^T + b2 + x1
-  if ((rc = imf_tc_gemm(hid, 4 * latent, w->w2, 4 * latent, out, ldo, M, latent, 4 * latent, 1.f, w->b2, x1, latent, 0, gws, gws_bytes, nullptr, stream))) return rc;
+  if ((rc = imf_tc_gemm_m(hid, 4 * latent, w->w2, 4 * latent, out, ldo, M, m_dev, latent, 4 * latent, 1.f, w->b2, x1, latent, 0, gws, gws_bytes, nullptr, stream))) return rc;
   return IMF_OK;
 }
 

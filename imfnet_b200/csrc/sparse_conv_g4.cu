@@ -633,12 +633,10 @@ int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, 
   }
   const int ntn = Cout / BN;
   const int nchunks = Cin / KC;
-  int gx = (g_g4_grid > 0 ? g_g4_grid : kSMs) / ntn;
-  const int tiles_max = (n_max + kBM - 1) / kBM;
+  // one CTA per SM and output-channel tile, whatever n_max: the row partition (hence the fp32 summation order of the split mode)
+  // then depends only on the actual row count, so a fragment gives the same bits in an exact-size and in a bucketed launch
+  const int gx = (g_g4_grid > 0 ? g_g4_grid : kSMs) / ntn;
   const int nst_max = K3 * nchunks;
-  // never launch more CTAs than any partition of n <= n_max rows can use
-  int useful = tiles_max >= gx ? gx : tiles_max * (nst_max / 4 > 1 ? (nst_max / 4 > 32 ? 32 : nst_max / 4) : 1);
-  if (useful < gx) gx = useful < 1 ? 1 : useful;
   float* P = nullptr;
   if (ws != nullptr && ws_bytes >= (size_t)kSMs * kBM * Cout * sizeof(float)) P = reinterpret_cast<float*>(ws);
   dim3 grid(gx, 1, ntn);
@@ -647,7 +645,7 @@ int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, 
                                                             err, g_g4_trace, g_g4_dbg);
   IMF_CHECK_LAUNCH();
   if (P != nullptr) {      // split mode is possible for small n: the reduce kernel decides on the device (no-op otherwise)
-    const int rows = n_max < gx * kBM ? n_max : gx * kBM;
+    const int rows = n_max < gx * kBM ? n_max : gx * kBM;      // split mode only exists below gx tiles
     const long long total = (long long)rows * (Cout / 16);
     k_conv_g4_reduce<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, n_ptr, n_max, gx, nst_max, Cout, scale, shift, R, ldr, kc_r,
                                                                          relu, Y, ldy, kc_out, err);

@@ -34,7 +34,7 @@ template <int BN, bool GEGLU>
 __global__ void __launch_bounds__(288, 1) k_tc_gemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                     float* __restrict__ C, int ldc, int M, int N, int K, float alpha,
                                                     const float* __restrict__ bias, const float* __restrict__ R, int ldr,
-                                                    int chunks_per_split, int* err) {
+                                                    int chunks_per_split, int* err, const int* __restrict__ m_ptr) {
   constexpr int A_BYTES = kBM * 128, B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   extern __shared__ unsigned char smem_dyn[];
@@ -44,12 +44,15 @@ __global__ void __launch_bounds__(288, 1) k_tc_gemm(const float* __restrict__ A,
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * kBM;
+  const int M_layout = M;                                  // split-K partial tiles are laid out with the host-side row count
+  if (m_ptr) { const int v = *m_ptr; M = v < M ? v : M; }  // device-side row count: whole tiles beyond it exit before any barrier
+  if (m0 >= M) return;
   const int n0 = blockIdx.x * (GEGLU ? BN / 2 : BN);      // first OUTPUT column of this tile
   // split-K: blockIdx.z owns K chunks [kc_begin, kc_end) and writes its partial tile to C + z*M*ldc (ldc == N there)
   const int nk_total = (K + kBK - 1) / kBK;
   const int kc_begin = blockIdx.z * chunks_per_split;
   const int nk = min(nk_total, kc_begin + chunks_per_split) - kc_begin;
-  C += (size_t)blockIdx.z * (size_t)M * ldc;
+  C += (size_t)blockIdx.z * (size_t)M_layout * ldc;
 
   if (tid == 0) {
     for (int s = 0; s < kNS; ++s) { tc::mbar_init(&full_bar[s], 256); tc::mbar_init(&empty_bar[s], 1); }
@@ -197,23 +200,25 @@ __global__ void __launch_bounds__(288, 1) k_tc_gemm(const float* __restrict__ A,
 
 template <int BN, bool GEGLU>
 int launch(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, float alpha,
-           const float* bias, const float* R, int ldr, int splits, int chunks_per_split, int* err, cudaStream_t stream) {
+           const float* bias, const float* R, int ldr, int splits, int chunks_per_split, int* err, const int* m_ptr, cudaStream_t stream) {
   constexpr int STAGE_BYTES = 2 * kBM * 128 + 2 * BN * 128;
   const size_t smem = (size_t)kNS * STAGE_BYTES + 1024;
   IMF_CHECK_CUDA(cudaFuncSetAttribute(k_tc_gemm<BN, GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int out_per_tile = GEGLU ? BN / 2 : BN;
   dim3 grid((N + out_per_tile - 1) / out_per_tile, (M + kBM - 1) / kBM, splits);
-  k_tc_gemm<BN, GEGLU><<<grid, 288, smem, stream>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, R, ldr, chunks_per_split, err);
+  k_tc_gemm<BN, GEGLU><<<grid, 288, smem, stream>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, R, ldr, chunks_per_split, err, m_ptr);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }
 
 // Sum split-K partials: C[m,n] = sum_z P[z][m][n] (+ bias[n]) (+ R[m,n]).
 __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ P, int splits, int M, int N, const float* __restrict__ bias,
-                                                       const float* __restrict__ R, int ldr, float* __restrict__ C, int ldc) {
+                                                       const float* __restrict__ R, int ldr, float* __restrict__ C, int ldc,
+                                                       const int* __restrict__ m_ptr) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)M * N) return;
   const int m = (int)(idx / N), n = (int)(idx % N);
+  if (m_ptr && m >= *m_ptr) return;
   float v = 0.f;
   for (int z = 0; z < splits; ++z) v += P[(size_t)z * M * N + idx];
   if (bias) v += __ldg(bias + n);
@@ -234,11 +239,18 @@ extern "C" size_t imf_tc_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K) {
 extern "C" int imf_tc_gemm(const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc, int32_t M, int32_t N,
                            int32_t K, float alpha, const float* bias, const float* R, int32_t ldr, int32_t geglu, void* workspace,
                            size_t workspace_bytes, int32_t* err, cudaStream_t stream) {
+  return imf_tc_gemm_m(A, lda, B, ldb, C, ldc, M, nullptr, N, K, alpha, bias, R, ldr, geglu, workspace, workspace_bytes, err, stream);
+}
+
+// Same with an optional device-side row count: only min(*m_dev, M) rows are computed (M sizes the launch and the workspace).
+extern "C" int imf_tc_gemm_m(const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc, int32_t M,
+                             const int32_t* m_dev, int32_t N, int32_t K, float alpha, const float* bias, const float* R, int32_t ldr,
+                             int32_t geglu, void* workspace, size_t workspace_bytes, int32_t* err, cudaStream_t stream) {
   IMF_CHECK_ARG(M >= 0 && N >= 0 && K >= 1 && lda >= K && ldb >= K && ldc >= N);
   if (M == 0 || N == 0) return IMF_OK;
   IMF_CHECK_ARG(A != nullptr && B != nullptr && C != nullptr);
   const int nk = (K + kBK - 1) / kBK;
-  if (geglu) return launch<128, true>(A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, R, ldr, 1, nk, err, stream);
+  if (geglu) return launch<128, true>(A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, R, ldr, 1, nk, err, m_dev, stream);
   // narrow outputs or few row tiles: smaller BN puts more CTAs on the 148 SMs
   const long long tiles128 = (long long)((M + 127) / 128) * ((N + 127) / 128);
   const bool bn64 = (N <= 64 || tiles128 < 74);
@@ -251,18 +263,18 @@ extern "C" int imf_tc_gemm(const float* A, int32_t lda, const float* B, int32_t 
     if (workspace_bytes < (size_t)splits * M * N * sizeof(float)) splits = 1;
   }
   if (splits <= 1) {
-    if (bn64) return launch<64, false>(A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, R, ldr, 1, nk, err, stream);
-    return launch<128, false>(A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, R, ldr, 1, nk, err, stream);
+    if (bn64) return launch<64, false>(A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, R, ldr, 1, nk, err, m_dev, stream);
+    return launch<128, false>(A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, R, ldr, 1, nk, err, m_dev, stream);
   }
   const int cps = (nk + splits - 1) / splits;
   splits = (nk + cps - 1) / cps;                       // no empty split
   float* P = reinterpret_cast<float*>(workspace);
   int rc;
-  if (bn64) rc = launch<64, false>(A, lda, B, ldb, P, N, M, N, K, alpha, nullptr, nullptr, 0, splits, cps, err, stream);
-  else rc = launch<128, false>(A, lda, B, ldb, P, N, M, N, K, alpha, nullptr, nullptr, 0, splits, cps, err, stream);
+  if (bn64) rc = launch<64, false>(A, lda, B, ldb, P, N, M, N, K, alpha, nullptr, nullptr, 0, splits, cps, err, m_dev, stream);
+  else rc = launch<128, false>(A, lda, B, ldb, P, N, M, N, K, alpha, nullptr, nullptr, 0, splits, cps, err, m_dev, stream);
   if (rc) return rc;
   const long long total = (long long)M * N;
-  k_splitk_reduce<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, splits, M, N, bias, R, ldr, C, ldc);
+  k_splitk_reduce<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, splits, M, N, bias, R, ldr, C, ldc, m_dev);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }

@@ -8,7 +8,9 @@ from __future__ import annotations
 import torch
 
 from .. import me as ME
-from ..engine import FusedPlan
+import os
+
+from ..engine import FusedPlan, GraphPlan, PlanCapacityError
 from .attention_fusion import AttentionFusion
 from .common import get_norm
 from .Img_Encoder import ImageEncoder
@@ -61,7 +63,7 @@ class ResUNet2(ME.MinkowskiNetwork):
         self._plan = None
 
     def _apply(self, fn, *a, **k):
-        self._plan = None                      # weights moved / cast: re-pack lazily
+        self._plan = None                      # weights moved / cast: re-pack lazily (and drop the captured graphs)
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
@@ -77,10 +79,47 @@ class ResUNet2(ME.MinkowskiNetwork):
                                       "call model.eval() as util/misc.py:44-45 does")
         if self._plan is None:
             self._plan = FusedPlan(self)
+            self._graphs, self._cap8_scale = {}, {}
         if not isinstance(x, ME.SparseTensor):       # duck-typed foreign container (.F / .C), e.g. a real ME tensor
             x = ME.SparseTensor(x.F, coordinates=x.C)
-        F = self._plan.run(x, torch.as_tensor(image))
+        image = torch.as_tensor(image)
+        F = None
+        if (image.dim() == 4 and image.shape[0] == 1 and self.use_cuda_graph and x.coordinate_map_key.tensor_stride == 1
+                and self._plan.debug is None):
+            F = self._forward_graph(x, image)
+        if F is None:
+            F = self._plan.run(x, image)
         return ME.SparseTensor(F, coordinate_map_key=x.coordinate_map_key, coordinate_manager=x.coordinate_manager)
+
+    # one fragment per call (what util/misc.py:extract_features and scripts/generate_desc.py do): captured CUDA graph per
+    # (row bucket, image size); larger batches and oversized stride-8 levels take the eager plan
+    use_cuda_graph = os.environ.get("IMFNET_B200_GRAPH", "1") != "0"
+    ROW_BUCKET = 4096
+
+    def _forward_graph(self, x, image):
+        plan = self._plan
+        if plan._key != plan._weights_key():
+            plan.pack()
+            self._graphs.clear()
+        N = len(x.F)
+        if N == 0:
+            return None
+        rows = (N + self.ROW_BUCKET - 1) // self.ROW_BUCKET * self.ROW_BUCKET
+        key = (rows, int(image.shape[2]), int(image.shape[3]))
+        scale = self._cap8_scale.get(key, 1)
+        if scale > 16:
+            return None
+        g = self._graphs.get(key)
+        if g is None:
+            cap8 = min(rows, max(1024, (rows // 16 + 511) // 512 * 512) * scale)
+            g = self._graphs[key] = GraphPlan(plan, rows, key[1], key[2], cap8)
+        feats = x.F.to(device=plan.device, dtype=torch.float32)
+        try:
+            return g.run(x.C, feats, image.to(device=plan.device, dtype=torch.float32))
+        except PlanCapacityError:
+            self._cap8_scale[key] = scale * 4          # unusually dense stride-8 level: bigger plan next time, eager now
+            del self._graphs[key]
+            return None
 
 
 class ResUNetBN2(ResUNet2):

@@ -64,19 +64,26 @@ class CoordinateManager:
             raise ValueError("coordinates must be int32 [N,4] rows of (batch, x, y, z)")
         coords = coords.contiguous()
         self.device = coords.device
+        self._l1 = (coords, coords.shape[0])     # the stride-1 table is built on first use (the captured-graph plan never needs it)
+        self.levels = {}
+        self.meta = None
+        self._next_meta = 1
+        self._tables = {}
+        self._checked = not check
+        self._segments = {}
+
+    def _ensure_level1(self):
+        if 1 in self.levels:
+            return
+        coords, n = self._l1
         L = _lib.lib()
-        n = coords.shape[0]
         cap = int(L.imf_hash_capacity(n))
         table = torch.empty(int(L.imf_hash_bytes(cap)), dtype=torch.uint8, device=self.device)
         # meta = [status, n(stride 2), n(stride 4), ... ] device scalars
         self.meta = torch.zeros(16, dtype=torch.int32, device=self.device)
-        self._next_meta = 1
         with torch.cuda.device(self.device):
             _lib.check(L.imf_hash_build(_lib.ptr(coords), None, n, _lib.ptr(table), cap, _lib.ptr(self.meta), _lib.cur_stream()))
-        self.levels = {1: Level(coords, n, table, cap)}
-        self._tables = {}
-        self._checked = not check
-        self._segments = {}
+        self.levels[1] = Level(coords, n, table, cap)
 
     # -- status ---------------------------------------------------------------------------------
     def _check_status(self, meta_host=None):
@@ -88,12 +95,20 @@ class CoordinateManager:
 
     # -- coordinate sets ------------------------------------------------------------------------
     def level(self, t: int) -> Level:
+        self._ensure_level1()
         return self.levels[t]
+
+    def num_rows(self, t: int) -> int:
+        return self._l1[1] if t == 1 else self.level(t).n
+
+    def coords_of(self, t: int) -> torch.Tensor:
+        return self._l1[0] if t == 1 else self.level(t).coords
 
     def build_pyramid(self, strides):
         """Create the coarser sets for every tensor stride in `strides` (ascending, each 2x the previous or any
         integer multiple) with ONE host read-back of the sizes."""
         L = _lib.lib()
+        self._ensure_level1()
         todo = sorted(t for t in strides if t not in self.levels)
         if not todo and self._checked:
             return
@@ -139,6 +154,7 @@ class CoordinateManager:
         key = (t_in, t_out, K, bool(transposed))
         if key not in self._tables:
             L = _lib.lib()
+            self._ensure_level1()
             src, dst = self.levels[t_in], self.levels[t_out]
             scale = -t_out if transposed else t_in
             # allocated at the stride-1 row count (an upper bound for every level) so that fragments of one size class reuse
@@ -156,6 +172,7 @@ class CoordinateManager:
         key = ("t", t_in, t_out, K, bool(transposed))
         if key not in self._tables:
             L = _lib.lib()
+            self._ensure_level1()
             src, dst = self.levels[t_in], self.levels[t_out]
             scale = -t_out if transposed else t_in
             ld_n = (dst.n + 127) // 128 * 128
@@ -172,7 +189,7 @@ class CoordinateManager:
         key = (t, num_batches)
         if key not in self._segments:
             L = _lib.lib()
-            lvl = self.levels[t]
+            lvl = self.level(t)
             seg = torch.empty(num_batches + 1, dtype=torch.int32, device=self.device)
             with torch.cuda.device(self.device):
                 _lib.check(L.imf_batch_segments(_lib.ptr(lvl.coords), None, lvl.n, num_batches, _lib.ptr(seg), _lib.cur_stream()))
@@ -201,7 +218,7 @@ class SparseTensor:
             coordinate_map_key = CoordinateMapKey(1)
         elif coordinate_manager is None or coordinate_map_key is None:
             raise ValueError("coordinates, or coordinate_map_key and coordinate_manager, are required")
-        elif coordinate_manager.level(coordinate_map_key.tensor_stride).n != len(features):
+        elif coordinate_manager.num_rows(coordinate_map_key.tensor_stride) != len(features):
             raise ValueError("feature rows do not match the coordinate map")
         self._F = features
         self.coordinate_manager = coordinate_manager
@@ -215,7 +232,7 @@ class SparseTensor:
 
     @property
     def C(self):
-        return self.coordinate_manager.level(self.coordinate_map_key.tensor_stride).coords
+        return self.coordinate_manager.coords_of(self.coordinate_map_key.tensor_stride)
 
     coordinates = C
 

@@ -113,6 +113,11 @@ int imf_sparse_conv_tc_fwd(const float* X, int32_t ldx, const void* packed, cons
  * `err` (optional device int): bit 16 is set if a stored value left the fp16 range (|v| > 60000); codes 1..3 = watchdog. */
 int imf_h2_pack(const float* X, int32_t ldx, int32_t n, int32_t C, int32_t KC, void* H, int32_t ldh, int32_t* err, imf_stream_t stream);
 int imf_h2_unpack(const void* H, int32_t ldh, int32_t n, int32_t C, int32_t KC, float* X, int32_t ldx, imf_stream_t stream);
+/* The same with an optional device-side row count (min(*n_dev, n) rows are converted; n sizes the launch). */
+int imf_h2_pack_n(const float* X, int32_t ldx, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, void* H, int32_t ldh, int32_t* err,
+                  imf_stream_t stream);
+int imf_h2_unpack_n(const void* H, int32_t ldh, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, float* X, int32_t ldx,
+                    imf_stream_t stream);
 
 /* Weights W[K^3,Cin,Cout] * wmul (a power of two that brings max|W| near 2^11; fold 1/wmul into `scale`) packed for the
  * input chunk width kc_in.  Same operation and epilogue as imf_sparse_conv_fwd; scale and shift are required. */
@@ -191,6 +196,23 @@ int imf_pointwise_tail_h2_fwd(const void* X, int32_t ldx, int32_t C0, int32_t Ca
 int imf_linear_fwd(const float* X, int32_t ldx, const float* W_kn, const float* bias, int32_t M, int32_t Cin, int32_t Cout,
                    float* Y, int32_t ldy, imf_stream_t stream);
 
+/* ---- image branch: ImageEncoder.forward (model/Img_Encoder.py:15-18 -> model/resnet.py:195-216) as pixel-major h2 matrices [H*W, C]
+ *      run through imf_sparse_conv_g4_fwd with closed-form neighbour tables ------------------------------------------------ */
+
+/* Offset-major neighbour table (+ tile masks, as imf_kernel_map_t) of a ksize x ksize / stride / zero-padded 2-D convolution on an
+ * Hin x Win image: nbr_t[k*ld_n + oy*Wout + ox], k = kx + ksize*ky; ld_n >= Hout*Wout rounded up to 128. */
+int imf_image_conv_table(int32_t Hin, int32_t Win, int32_t ksize, int32_t stride, int32_t pad, int32_t* nbr_t, int32_t ld_n,
+                         uint32_t* tile_mask, imf_stream_t stream);
+/* im2col of an fp32 [C,H,W] image for the stem convolution: row = output pixel, column = c + C*(kx + ksize*ky), zero-padded to Kpad
+ * (multiple of 32) columns, written as an h2 matrix with chunk width 32 (ldy in halves). */
+int imf_image_im2col_h2(const float* image, int32_t C, int32_t H, int32_t W, int32_t ksize, int32_t stride, int32_t pad, int32_t Kpad,
+                        void* Y, int32_t ldy, imf_stream_t stream);
+/* Max pooling (torch semantics: padding never wins) on a pixel-major h2 matrix of C channels, chunk width kc. */
+int imf_image_maxpool_h2(const void* X, int32_t ldx, int32_t kc, int32_t C, int32_t Hin, int32_t Win, int32_t ksize, int32_t stride,
+                         int32_t pad, void* Y, int32_t ldy, imf_stream_t stream);
+/* Y[C][L] = X[L][C]^T (fp32): token-major result -> the NCHW feature map ImageEncoder.forward returns. */
+int imf_transpose_tokens(const float* X, int32_t L, int32_t C, float* Y, imf_stream_t stream);
+
 /* ---- dense GEMM on the tcgen05 tensor cores (3xTF32, fp32-class accuracy): every nn.Linear / einsum of
  *      model/attention_fusion.py:57-59,79-95 --------------------------------------------------------- */
 
@@ -202,6 +224,11 @@ size_t imf_tc_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K);
 int imf_tc_gemm(const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc, int32_t M, int32_t N, int32_t K,
                 float alpha, const float* bias, const float* R, int32_t ldr, int32_t geglu, void* workspace,
                 size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+
+/* imf_tc_gemm with an optional device-side row count: only min(*m_dev, M) rows are computed; M sizes the launch and the workspace. */
+int imf_tc_gemm_m(const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc, int32_t M, const int32_t* m_dev, int32_t N,
+                  int32_t K, float alpha, const float* bias, const float* R, int32_t ldr, int32_t geglu, void* workspace,
+                  size_t workspace_bytes, int32_t* err, imf_stream_t stream);
 
 /* ---- attention fusion: AttentionFusion.forward (model/attention_fusion.py:132-154), depth 0, 1 head ---- */
 typedef struct {
@@ -228,6 +255,10 @@ int imf_attention_kv(const imf_attn_weights_t* w, const float* tokens, int32_t L
 size_t imf_attention_workspace_bytes(int32_t M, int32_t L, int32_t latent, int32_t inner);
 int imf_attention_fusion_fwd(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const float* kv, int32_t L,
                              float* out, int32_t ldo, void* workspace, size_t workspace_bytes, imf_stream_t stream);
+
+/* imf_attention_fusion_fwd with an optional device-side token count (min(*m_dev, M) rows; M sizes launches and workspace). */
+int imf_attention_fusion_fwd_m(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const int32_t* m_dev, const float* kv,
+                               int32_t L, float* out, int32_t ldo, void* workspace, size_t workspace_bytes, imf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -139,3 +139,35 @@ def test_extract_features_pipeline(golden_dir, state_dict, cuda_model):
     coords = torch.from_numpy(np.concatenate([np.zeros((len(idx), 1)), q[idx]], 1).astype(np.int32))
     ref = imfnet_oracle.forward(state_dict, coords, torch.ones((len(idx), 1)), torch.from_numpy(image))
     assert note("extract_features_vs_oracle", rel_rows(F.cpu(), ref)) < TOL
+
+
+def test_graph_plan_equals_eager_plan_and_handles_size_changes(state_dict, cuda_model):
+    """The captured-graph path (device-side sizes, bucketed buffers) agrees with the eager path to fp32 rounding (the attention
+    GEMMs pick their split-K factor from the buffer capacity, so the summation order differs), for several fragments that share a
+    bucket, a fragment in another bucket, and repeated replays, which must be bit-identical."""
+    import imfnet_b200.me as ME
+    assert cuda_model.use_cuda_graph
+    outs = {}
+    for n, seed in ((3000, 1), (3500, 2), (3000, 1), (9000, 3), (1, 4), (130, 5)):
+        coords, _ = synthetic.make_fragment(n, 0.05, seed=seed)
+        coords = torch.from_numpy(coords)
+        feats = torch.ones((len(coords), 1))
+        image = synthetic.make_image(160, 120, seed=seed)
+        g = cuda_model(ME.SparseTensor(feats, coordinates=coords, device="cuda"), image.cuda()).F
+        type(cuda_model).use_cuda_graph = False
+        try:
+            e = cuda_model(ME.SparseTensor(feats, coordinates=coords, device="cuda"), image.cuda()).F
+        finally:
+            type(cuda_model).use_cuda_graph = True
+        assert g.shape == (n, 32)
+        assert rel_rows(g.cpu(), e.cpu()) < 5e-6, f"graph and eager plans differ for n={n}"
+        if (n, seed) in outs:
+            assert torch.equal(outs[(n, seed)], g), "replays of the same fragment must be bit-identical"
+        outs[(n, seed)] = g.clone()
+
+
+def test_graph_plan_reports_bad_coordinates(cuda_model):
+    import imfnet_b200.me as ME
+    coords = torch.tensor([[0, 1, 2, 3], [0, 1, 2, 3], [0, 5, 5, 5]], dtype=torch.int32)
+    with pytest.raises(ValueError):
+        cuda_model(ME.SparseTensor(torch.ones((3, 1)), coordinates=coords, device="cuda"), torch.rand(1, 3, 120, 160).cuda())
