@@ -227,10 +227,7 @@ def run_ours(args, rank, world, local_rank):
         wall = time.perf_counter() - wall0
         launches = L.imf_launch_count() + GraphPlan.replayed_launches - l0
         clocks = sampler.stop()
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        return float(t.item()), launches, clocks, wall
+        return ms, launches, clocks, wall
 
     if args.profile:      # under ncu: just the resident steps, nothing else
         with torch.no_grad():
@@ -239,17 +236,19 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
         return
     with torch.no_grad():
-        ms_total, launches, clocks, wall = timed(step_resident)
-        ms_e2e, _, _, _ = timed(step_e2e)
+        ms_rank, launches, clocks, wall = timed(step_resident)
+        ms_rank_e2e, _, _, _ = timed(step_e2e)
         roof = dominant_kernel_roofline(model, frags[0], flush) if rank == 0 else None
 
-    # per-fragment timing records: the one collective of this path
-    rec = torch.tensor([rank, target * args.steps, ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        allrec = [torch.zeros_like(rec) for _ in range(world)]
-        torch.distributed.all_gather(allrec, rec)
+    # per-rank timing records: the one collective of this path
+    from imfnet_b200.pipeline import aggregate_throughput, gather_records
+    rec = torch.tensor([rank, target * args.steps, ms_rank], dtype=torch.float64, device=dev)
+    rec_e2e = torch.tensor([rank, target * args.steps, ms_rank_e2e], dtype=torch.float64, device=dev)
+    allrec, allrec_e2e = gather_records(rec, world), gather_records(rec_e2e, world)
     if rank != 0:
         return
+    value, ms_total = aggregate_throughput(allrec.cpu())
+    e2e_v, ms_e2e = aggregate_throughput(allrec_e2e.cpu())
 
     cpu = None
     if world == 1:
@@ -266,8 +265,6 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": target / float(np.median(ts)), "unit": "voxels/s", "cores": cores, "kind": "port",
                "sample": f"median of {len(ts)} cold oracle forwards of one {target}-voxel fragment (same weights), fp32 torch CPU"}
 
-    value = target * args.steps * world / (ms_total * 1e-3)
-    e2e_v = target * args.steps * world / (ms_e2e * 1e-3)
     h2d = target * 16 + target * 4 + 3 * H * W * 4
     d2h = target * 32 * 4
     print(json.dumps({

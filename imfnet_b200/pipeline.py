@@ -67,3 +67,21 @@ def shard_indices(num_items: int, rank: int, world_size: int, weights=None):
         if r == rank:
             mine.append(i)
     return sorted(mine)
+
+
+def gather_records(rec: torch.Tensor, world_size: int) -> torch.Tensor:
+    """The only collective of this path: all-gather of one small per-rank record (e.g. [rank, voxels, ms])
+    -> [world_size, k] on every rank.  Works on whatever backend the default process group uses (NCCL on GPUs, gloo in tests)."""
+    if world_size == 1:
+        return rec.reshape(1, -1).clone()
+    import torch.distributed as dist
+    out = [torch.zeros_like(rec) for _ in range(world_size)]
+    dist.all_gather(out, rec)
+    return torch.stack(out, dim=0)
+
+
+def aggregate_throughput(records: torch.Tensor):
+    """records [world, 3] = (rank, voxels processed, device milliseconds) -> (whole-job voxels/s, slowest rank's ms):
+    the job's time is the MAX over ranks, its work the SUM."""
+    ms = float(records[:, 2].max())
+    return float(records[:, 1].sum()) / (ms * 1e-3), ms

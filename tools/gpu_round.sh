@@ -5,14 +5,15 @@ TAG=${1:-run}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log; tail -3 $OUT/pytest_gpu.log
 timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
-tail -c 3000 $OUT/bench.json
+tail -c 2500 $OUT/bench.json
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2>> $OUT/bench.err; echo "reference rc=$?"; cat $OUT/bench_reference.json | cut -c1-300
 timeout 300 python tools/profile_step.py > $OUT/profile_step.txt 2>&1; cat $OUT/profile_step.txt
-timeout 300 python tools/conv_microbench.py --flags 0,1,2,4,6,7 > $OUT/conv_microbench_64.txt 2>&1; head -8 $OUT/conv_microbench_64.txt
-timeout 300 python tools/conv_microbench.py --cin 32 --cout 32 --flags 0,2,4 2>&1 | head -4 > $OUT/conv_microbench_32.txt; cat $OUT/conv_microbench_32.txt
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/launches.csv \
-    python bench.py --profile --steps 2 --warmup 2 > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sparse_conv_h2 -s 4 -c 2 -o $OUT/prof_conv_h2 \
-    python tools/conv_microbench.py --flags 0 --reps 3 > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 300 python tools/conv_g4_bench.py --flags 0,3,6,7 --old > $OUT/conv_g4_bench_64.txt 2>&1; cat $OUT/conv_g4_bench_64.txt
+timeout 300 python tools/conv_g4_bench.py --cin 32 --cout 32 > $OUT/conv_g4_bench_32.txt 2>&1; cat $OUT/conv_g4_bench_32.txt
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv \
+    python bench.py --profile --steps 2 --warmup 1 > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sparse_conv_g4 -s 4 -c 2 -o $OUT/prof_conv_g4 \
+    python tools/conv_g4_bench.py --reps 3 > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT
