@@ -145,7 +145,7 @@ def dominant_kernel_roofline(model, frag, flush):
     Yh = torch.empty(n, 2 * cout, dtype=torch.float16, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(cout))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device="cuda")
     pairs = int((nbr_t[:, :n] >= 0).sum())
     # gathered inputs + in/out indices + weights once + output (activations are 4 bytes/channel: fp16 hi + lo)
     alg_bytes = 4 * pairs * cin + 8 * pairs + 4 * 27 * cin * cout + 4 * n * cout

@@ -13,6 +13,10 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libimfnet_b200.so")
 _p, _i32, _i64, _sz, _f32, _f64 = C.c_void_p, C.c_int32, C.c_longlong, C.c_size_t, C.c_float, C.c_double
 
 
+class KmapJob(C.Structure):
+    _fields_ = [("out_coords", _p), ("n_out_dev", _p), ("table_in", _p), ("nbr_t", _p), ("tile_mask", _p), ("scale", _i32)]
+
+
 class AttnWeights(C.Structure):
     _fields_ = [(n, _p) for n in ("ln_q_w", "ln_q_b", "ln_c_w", "ln_c_b", "wq", "wkv", "wo", "bo", "ln_f_w", "ln_f_b",
                                   "w1", "b1", "w2", "b2")] + [("latent", _i32), ("dim", _i32), ("inner", _i32)]
@@ -31,6 +35,7 @@ SIGNATURES = {
     "imf_stride_map": (C.c_int, [_p, _p, _i32, _i32, _p, _i64, _p, _p, _p, _p, _sz, _p, _p]),
     "imf_kernel_map": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _i32, _p, _p]),
     "imf_kernel_map_t": (C.c_int, [_p, _p, _i32, _p, _i64, _i32, _i32, _p, _i32, _p, _p]),
+    "imf_kernel_map_t_batch": (C.c_int, [C.POINTER(KmapJob), _i32, _i32, _i64, _i32, _i32, _p]),
     "imf_sparse_conv_g4_workspace_bytes": (_sz, [_i32]),
     "imf_sparse_conv_g4_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i32,
                                         _p, _i32, _i32, _i32, _p, _sz, _p, _p]),

@@ -197,27 +197,50 @@ __global__ void k_kernel_map(const int4* __restrict__ out_coords, const int* __r
   nbr[idx] = r;
 }
 
-// Offset-major neighbour table for the TMA-gather convolution (sparse_conv_g4.cu): nbr_t[k*ld_n + o]; rows o in
-// [n, roundup128(n)) are -1 (they pad the last tile); tile_mask[o/128] gets bit k when any row of that 128-row tile has a
-// neighbour at offset k (the caller zeroes tile_mask).  One CTA = one (tile, offset).
-__global__ void __launch_bounds__(128) k_kernel_map_t(const int4* __restrict__ out_coords, const int* __restrict__ n_ptr, int n_max,
-                                                      const ImfSlot* __restrict__ table, unsigned long long mask, int K, int scale,
-                                                      int* __restrict__ nbr_t, int ld_n, unsigned* __restrict__ tile_mask) {
-  const int n = imf_count(n_ptr, n_max);
-  const int tile = blockIdx.x, k = blockIdx.y;
-  if (tile * 128 >= n) return;
-  const int o = tile * 128 + threadIdx.x;
-  int r = -1;
-  if (o < n) {
-    const int h = K / 2;
-    const int kx = k % K - h, ky = (k / K) % K - h, kz = k / (K * K) - h;
-    const int4 c = out_coords[o];
-    const int x = c.y + kx * scale, y = c.z + ky * scale, z = c.w + kz * scale;
-    if (imf_coord_in_range(c.x, x, y, z)) r = imf_table_lookup(table, mask, imf_pack_key(c.x, x, y, z));
+// Offset-major neighbour tables for the persistent convolution (sparse_conv_g4.cu): nbr_t[k*ld_n + o]; rows o in
+// [n, roundup128(n)) are -1 (they pad the last tile); tile_mask[o/128] has bit k set when any row of that 128-row tile has a
+// neighbour at offset k.  One CTA = one 128-row tile of one table (blockIdx.y = job): every thread probes the K^3 offsets of
+// its row, so the tile mask is a plain store (no memset, no atomics) and several tables share one launch.
+struct KmapJob {
+  const int4* out_coords;
+  const int* n_ptr;
+  const ImfSlot* table;
+  int* nbr_t;
+  unsigned* tile_mask;
+  int scale;
+  int pad;
+};
+struct KmapJobs {
+  KmapJob j[16];
+};
+__global__ void __launch_bounds__(128) k_kernel_map_t(const __grid_constant__ KmapJobs jobs, int n_max, unsigned long long mask, int K, int ld_n) {
+  __shared__ unsigned wmask[4];
+  const KmapJob& jb = jobs.j[blockIdx.y];
+  const int n = imf_count(jb.n_ptr, n_max);
+  const int tile = blockIdx.x;
+  if (tile * 128 >= n) {
+    if (tile * 128 < n_max + 128 && threadIdx.x == 0) jb.tile_mask[tile] = 0u;     // tiles past the data: empty masks
+    return;
   }
-  if (o < ld_n) nbr_t[(size_t)k * ld_n + o] = r;
-  const unsigned any = __ballot_sync(0xffffffffu, r >= 0);
-  if ((threadIdx.x & 31) == 0 && any) atomicOr(tile_mask + tile, 1u << k);
+  const int o = tile * 128 + threadIdx.x;
+  const int K3 = K * K * K, h = K / 2;
+  int4 c = make_int4(0, 0, 0, 0);
+  if (o < n) c = jb.out_coords[o];
+  unsigned mine = 0u;
+  for (int k = 0; k < K3; ++k) {
+    int r = -1;
+    if (o < n) {
+      const int kx = k % K - h, ky = (k / K) % K - h, kz = k / (K * K) - h;
+      const int x = c.y + kx * jb.scale, y = c.z + ky * jb.scale, z = c.w + kz * jb.scale;
+      if (imf_coord_in_range(c.x, x, y, z)) r = imf_table_lookup(jb.table, mask, imf_pack_key(c.x, x, y, z));
+    }
+    if (o < ld_n) jb.nbr_t[(size_t)k * ld_n + o] = r;
+    mine |= (r >= 0 ? 1u : 0u) << k;
+  }
+  mine = __reduce_or_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0) wmask[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) jb.tile_mask[tile] = wmask[0] | wmask[1] | wmask[2] | wmask[3];
 }
 
 // xyz (float64 [N,3]) -> int32 (b, floor(x/voxel), floor(y/voxel), floor(z/voxel)).  IEEE double division and
@@ -330,22 +353,44 @@ extern "C" int imf_kernel_map(const int32_t* out_coords, const int32_t* n_out_de
   return IMF_OK;
 }
 
-extern "C" int imf_kernel_map_t(const int32_t* out_coords, const int32_t* n_out_dev, int32_t n_out_max, const void* table_in,
-                                long long capacity, int32_t kernel_size, int32_t scale, int32_t* nbr_t, int32_t ld_n,
-                                uint32_t* tile_mask, cudaStream_t stream) {
-  IMF_CHECK_ARG(is_pow2(capacity) && table_in != nullptr && n_out_max >= 0);
+struct imf_kmap_job_t {      // mirrors include/imfnet_b200.h
+  const int32_t* out_coords;
+  const int32_t* n_out_dev;
+  const void* table_in;
+  int32_t* nbr_t;
+  uint32_t* tile_mask;
+  int32_t scale;
+};
+
+extern "C" int imf_kernel_map_t_batch(const imf_kmap_job_t* jobs, int32_t njobs, int32_t n_out_max, long long capacity, int32_t kernel_size,
+                                      int32_t ld_n, cudaStream_t stream) {
+  IMF_CHECK_ARG(jobs != nullptr && njobs >= 1 && njobs <= 16 && is_pow2(capacity) && n_out_max >= 0);
   IMF_CHECK_ARG(kernel_size >= 1 && (kernel_size & 1) == 1 && kernel_size <= 3);
   IMF_CHECK_ARG(ld_n % 4 == 0 && ld_n >= ((n_out_max + 31) & ~31));
   if (n_out_max == 0) return IMF_OK;
-  IMF_CHECK_ARG(out_coords != nullptr && nbr_t != nullptr && tile_mask != nullptr);
+  KmapJobs kj;
+  for (int i = 0; i < njobs; ++i) {
+    IMF_CHECK_ARG(jobs[i].out_coords != nullptr && jobs[i].table_in != nullptr && jobs[i].nbr_t != nullptr && jobs[i].tile_mask != nullptr);
+    kj.j[i].out_coords = reinterpret_cast<const int4*>(jobs[i].out_coords);
+    kj.j[i].n_ptr = jobs[i].n_out_dev;
+    kj.j[i].table = reinterpret_cast<const ImfSlot*>(jobs[i].table_in);
+    kj.j[i].nbr_t = jobs[i].nbr_t;
+    kj.j[i].tile_mask = jobs[i].tile_mask;
+    kj.j[i].scale = jobs[i].scale;
+    kj.j[i].pad = 0;
+  }
   const int tiles = (n_out_max + 127) / 128;
-  IMF_CHECK_CUDA(cudaMemsetAsync(tile_mask, 0, (size_t)(tiles + 1) * sizeof(uint32_t), stream));
-  dim3 grid(tiles, kernel_size * kernel_size * kernel_size);
-  k_kernel_map_t<<<grid, 128, 0, stream>>>(reinterpret_cast<const int4*>(out_coords), n_out_dev, n_out_max,
-                                           reinterpret_cast<const ImfSlot*>(table_in), (unsigned long long)capacity - 1, kernel_size,
-                                           scale, nbr_t, ld_n, tile_mask);
+  dim3 grid(tiles + 1, njobs);          // + 1: the mask entry past the last tile is written (zero) too
+  k_kernel_map_t<<<grid, 128, 0, stream>>>(kj, n_out_max, (unsigned long long)capacity - 1, kernel_size, ld_n);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
+}
+
+extern "C" int imf_kernel_map_t(const int32_t* out_coords, const int32_t* n_out_dev, int32_t n_out_max, const void* table_in,
+                                long long capacity, int32_t kernel_size, int32_t scale, int32_t* nbr_t, int32_t ld_n,
+                                uint32_t* tile_mask, cudaStream_t stream) {
+  imf_kmap_job_t job{out_coords, n_out_dev, table_in, nbr_t, tile_mask, scale};
+  return imf_kernel_map_t_batch(&job, 1, n_out_max, capacity, kernel_size, ld_n, stream);
 }
 
 extern "C" int imf_quantize_points(const double* xyz, int32_t n, double voxel_size, int32_t batch_index, int32_t* coords,

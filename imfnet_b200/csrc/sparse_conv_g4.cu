@@ -212,6 +212,8 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   }
   if (row_begin >= row_end) return;
   const int nsub_total = (row_end - row_begin + kBM - 1) / kBM;
+  long long* cta_trace = (trace && zt == 0) ? trace + 256 : nullptr;      // per-CTA lifetime (profiling hook)
+  const long long t_cta0 = clock64();
   if (bx | zt) trace = nullptr;
 #define G4_TRACE(slot) do { if (trace) trace[slot] = clock64(); } while (0)
   if (tid == 0) G4_TRACE(0);
@@ -567,6 +569,15 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   }
   if (warp == kNPW) tc::tmem_dealloc(tmem_d, tmem_cols);
   if (tid == 0) G4_TRACE(6);
+  if (tid == 0 && cta_trace) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    cta_trace[bx] = clock64() - t_cta0;
+    cta_trace[160 + bx] = (long long)smid;
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    cta_trace[320 + bx] = (long long)gt;
+  }
 #undef G4_TRACE
 }
 

@@ -79,6 +79,9 @@ class FusedPlan:
         self.final_bias = None if m.final.bias is None else m.final.bias.detach().reshape(-1).contiguous()
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        # split-mode workspace of the convolution kernel (its head holds arrival counters that must start, and are left, zero)
+        self.conv_ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(max(max(CH[1:]), max(TR[1:]))))
+        self.conv_ws = torch.zeros(self.conv_ws_bytes, dtype=torch.uint8, device=self.device)
         self._key = self._weights_key()
 
     # -- launch helpers ------------------------------------------------------------------------
@@ -87,14 +90,11 @@ class FusedPlan:
         tab = CoordinateManager.table_t(...) (offset-major neighbour table, its row stride, tile masks)."""
         conv, packed, scale, shift, kci = self.conv[cname]
         nbr_t, ld_n, tile_mask = tab
-        ws, ws_bytes = None, 0
-        if n_out < 128 * 148:                 # fewer row tiles than SMs: let the kernel split a tile's offsets over several CTAs
-            ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(conv.out_channels))
-            ws = self.arena.take(ws_bytes)
+        split = n_out < 128 * 148                # fewer row tiles than SMs: the kernel may split a tile's offsets over several CTAs
         _lib.check(L.imf_sparse_conv_g4_fwd(X, ldx, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(), None, n_out,
                                             27, conv.in_channels, conv.out_channels, scale.data_ptr(), shift.data_ptr(), R, ldr, kc_r,
-                                            1 if relu else 0, Y, ldy, n_out, kc_out, _lib.ptr(ws), ws_bytes, self.err.data_ptr(),
-                                            stream))
+                                            1 if relu else 0, Y, ldy, n_out, kc_out, self.conv_ws.data_ptr() if split else None,
+                                            self.conv_ws_bytes if split else 0, self.err.data_ptr(), stream))
 
     def _block(self, L, name, X, ldx, kc_x, nbr, n, C, tmp, Y, ldy, kc_y, stream):
         """BasicBlockBN (model/residual_block.py:37-53): X -> tmp = relu(bn1(conv1 X)) -> Y = relu(bn2(conv2 tmp) + X)."""
@@ -258,6 +258,7 @@ class GraphPlan:
     which is what bounded the eager plan (2.7 ms of host enqueue for 3.4 ms of device time at 50 k voxels)."""
 
     replayed_launches = 0      # kernels of this library launched through graph replays (bench.py adds it to imf_launch_count)
+    ROW_SLACK = 4096           # a plan of `rows` voxels only ever serves fragments of more than rows - ROW_SLACK voxels
 
     def __init__(self, fused: FusedPlan, rows: int, H: int, W: int, cap8: int):
         self.f, self.rows, self.H, self.W, self.cap8 = fused, int(rows), int(H), int(W), int(cap8)
@@ -305,7 +306,7 @@ class GraphPlan:
         self.att_ws_bytes = int(L.imf_attention_workspace_bytes(self.cap8, self.n_tok, af.latent_dim, af.inner))
         self.att_ws = torch.empty(max(self.att_ws_bytes, 1), **u8)
         self.conv_ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(max(max(CH[1:]), max(TR[1:]))))
-        self.conv_ws = torch.empty(self.conv_ws_bytes, **u8)
+        self.conv_ws = torch.zeros(self.conv_ws_bytes, **u8)          # head = arrival counters, zero on entry / left zero
         self.out = torch.zeros((rows, m.out_channels), **f32)
         self.side = torch.cuda.Stream(device=dev)
         self.graph = None
@@ -318,10 +319,14 @@ class GraphPlan:
     def _conv(self, L, cname, X, ldx, key, t_out, R, ldr, kc_r, relu, Y, ldy, kc_out, s):
         conv, packed, scale, shift, kci = self.f.conv[cname]
         nbr_t, ld_n, tile_mask = self.nbr[key]
+        # a stride-1 level of this bucket always has >= 128 * 148 rows when the bucket is large enough: row mode is certain, so no
+        # split workspace (and no reduce launch) is needed there
+        split = not (t_out == 1 and self.rows - self.ROW_SLACK >= 128 * 148)
         _lib.check(L.imf_sparse_conv_g4_fwd(X, ldx, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(), self._n(t_out),
                                             self.rows, 27, conv.in_channels, conv.out_channels, scale.data_ptr(), shift.data_ptr(), R,
-                                            ldr, kc_r, 1 if relu else 0, Y, ldy, self.rows, kc_out, self.conv_ws.data_ptr(),
-                                            self.conv_ws_bytes, self.err.data_ptr(), s))
+                                            ldr, kc_r, 1 if relu else 0, Y, ldy, self.rows, kc_out,
+                                            self.conv_ws.data_ptr() if split else None, self.conv_ws_bytes if split else 0,
+                                            self.err.data_ptr(), s))
 
     def _block(self, L, name, X, ldx, kc_x, t, C, tmp, Y, ldy, kc_y, s):
         kt = _kc(C)
@@ -347,9 +352,11 @@ class GraphPlan:
             _lib.check(L.imf_stride_map(self.coords[prev].data_ptr(), self._n(prev), rows, t, self.tables[t].data_ptr(), self.cap,
                                         self.coords[t].data_ptr(), self._n(t), None, self.sm_ws.data_ptr(), self.sm_ws_bytes, status, s))
             prev = t
-        for (t_in, t_out, tr), (nbr_t, ld_n, mask) in self.nbr.items():
-            _lib.check(L.imf_kernel_map_t(self.coords[t_out].data_ptr(), self._n(t_out), rows, self.tables[t_in].data_ptr(), self.cap, 3,
-                                          -t_out if tr else t_in, nbr_t.data_ptr(), ld_n, mask.data_ptr(), s))
+        jobs = (_lib.KmapJob * len(self.nbr))()
+        for i, ((t_in, t_out, tr), (nbr_t, ld_n, mask)) in enumerate(self.nbr.items()):
+            jobs[i] = _lib.KmapJob(self.coords[t_out].data_ptr(), self._n(t_out), self.tables[t_in].data_ptr(), nbr_t.data_ptr(),
+                                   mask.data_ptr(), -t_out if tr else t_in)
+        _lib.check(L.imf_kernel_map_t_batch(jobs, len(self.nbr), rows, self.cap, 3, self.ldn, s))       # all 10 tables, one launch
         # ---- encoder ----
         ld1, ld2, ld4 = 2 * self.cat1.shape[1], 2 * self.cat2.shape[1], 2 * self.cat4.shape[1]
         s1, s2, s4 = self.cat1.data_ptr() + TR[2] * 4, self.cat2.data_ptr() + TR[3] * 4, self.cat4.data_ptr() + TR[4] * 4

@@ -98,7 +98,7 @@ class ImagePlan:
             self.l2 = [torch.zeros((self.P2, self.C2), **f32) for _ in range(3)]
             self.tokens = torch.zeros((self.P2, self.C2), **f32)
             self.ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(self.C2))
-            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+            self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)        # head = arrival counters (zero)
             self.err = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def _conv(self, L, c: _Conv, X, tab, n_out, R, relu, Y, s):
@@ -106,7 +106,8 @@ class ImagePlan:
         _lib.check(L.imf_sparse_conv_g4_fwd(X.data_ptr(), 2 * c.cin, c.kc_in, c.packed.data_ptr(), nbr_t.data_ptr(), ld_n, mask.data_ptr(),
                                             None, n_out, c.K, c.cin, c.cout, c.scale.data_ptr(), c.shift.data_ptr(), _lib.ptr(R),
                                             0 if R is None else 2 * c.cout, 64, 1 if relu else 0, Y.data_ptr(), 2 * c.cout, n_out, 64,
-                                            self.ws.data_ptr(), self.ws_bytes, self.err.data_ptr(), s))
+                                            self.ws.data_ptr() if n_out < 128 * 148 else None, self.ws_bytes if n_out < 128 * 148 else 0,
+                                            self.err.data_ptr(), s))
 
     def enqueue(self, image: torch.Tensor) -> torch.Tensor:
         """image fp32 [3,H,W] (contiguous, on the plan's device) -> fp32 tokens [H/8*W/8, 128] (a buffer owned by the plan)."""

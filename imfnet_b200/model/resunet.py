@@ -94,7 +94,7 @@ class ResUNet2(ME.MinkowskiNetwork):
     # one fragment per call (what util/misc.py:extract_features and scripts/generate_desc.py do): captured CUDA graph per
     # (row bucket, image size); larger batches and oversized stride-8 levels take the eager plan
     use_cuda_graph = os.environ.get("IMFNET_B200_GRAPH", "1") != "0"
-    ROW_BUCKET = 4096
+    ROW_BUCKET = GraphPlan.ROW_SLACK
 
     def _forward_graph(self, x, image):
         plan = self._plan

@@ -68,11 +68,23 @@ int imf_kernel_map(const int32_t* out_coords, const int32_t* n_out_dev, int32_t 
 
 /* The same neighbour table in offset-major form for the TMA-gather convolution: nbr_t[k*ld_n + o] (ld_n % 4 == 0,
  * ld_n >= n_out_max rounded up to 32; rows in [n, roundup128(n)) are written as -1), plus tile_mask[o/128] (uint32, at least
- * ceil(n_out_max/128)+1 entries, zeroed here) whose bit k says that some row of that 128-row tile has a neighbour at offset k.
+ * ceil(n_out_max/128)+1 entries, all written here) whose bit k says that some row of that 128-row tile has a neighbour at offset k.
  * kernel_size in {1, 3}. */
 int imf_kernel_map_t(const int32_t* out_coords, const int32_t* n_out_dev, int32_t n_out_max, const void* table_in,
                      long long capacity, int32_t kernel_size, int32_t scale, int32_t* nbr_t, int32_t ld_n, uint32_t* tile_mask,
                      imf_stream_t stream);
+
+/* Several such tables (same n_out_max, capacity, kernel_size, ld_n) in ONE launch; `jobs` is a HOST array of njobs <= 16 entries. */
+typedef struct {
+  const int32_t* out_coords;
+  const int32_t* n_out_dev;
+  const void* table_in;
+  int32_t* nbr_t;
+  uint32_t* tile_mask;
+  int32_t scale;
+} imf_kmap_job_t;
+int imf_kernel_map_t_batch(const imf_kmap_job_t* jobs, int32_t njobs, int32_t n_out_max, long long capacity, int32_t kernel_size,
+                           int32_t ld_n, imf_stream_t stream);
 
 /* coords[i] = (batch_index, floor(xyz[i]/voxel_size)) in float64, as util/misc.py:82 computes on the host. */
 int imf_quantize_points(const double* xyz, int32_t n, double voxel_size, int32_t batch_index, int32_t* coords,
@@ -141,7 +153,7 @@ int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t kc_in, const void
                            int32_t Cout, const float* scale, const float* shift, const void* residual, int32_t ldr, int32_t kc_r,
                            int32_t relu, void* Y, int32_t ldy, int32_t n_y_rows, int32_t kc_out, void* workspace, size_t workspace_bytes,
                            int32_t* err, imf_stream_t stream);
-/* Profiling hook: device int64 buffer (>= 512 entries) filled by CTA 0 with clock64() stamps (slot map in the source), and an
+/* Profiling hook: device int64 buffer (>= 1024 entries) filled by CTA 0 with clock64() stamps (slot map in the source), and an
  * override of the CTAs per output-channel tile (0 = one per SM) and of the producer warps per CTA (8 or 16; other values keep the
  * current setting); flags: bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs (results are then meaningless).
  * NULL / 0 switch everything off. */

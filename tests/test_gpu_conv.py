@@ -184,7 +184,7 @@ def run_conv_g4(X, W, tab, n_out, scale, shift, R=None, relu=False, split=True, 
     Rh = None if R is None else h2_pack(R, kc_out, ld_extra=16)
     Yh = torch.full((n_out + extra_rows, 2 * cout + 8), float("nan"), dtype=torch.float16, device="cuda")
     ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(cout)) if split else 0
-    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
+    ws = torch.zeros(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     sc = (scale / wmul).contiguous()
     _lib.check(L.imf_sparse_conv_g4_fwd(Xh.data_ptr(), Xh.stride(0), kc_in, packed.data_ptr(), nbr_t.data_ptr(), ld_n,

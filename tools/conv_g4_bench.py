@@ -44,7 +44,7 @@ Yh = torch.zeros(n, 2 * cout, dtype=torch.float16, device="cuda")
 one, zero = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
 err = torch.zeros(1, dtype=torch.int32, device="cuda")
 ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(cout))
-ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+ws = torch.zeros(ws_bytes, dtype=torch.uint8, device="cuda")
 flushbuf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 pairs = int((nbr_t[:, :n] >= 0).sum())
 alg = 4 * pairs * cin + 8 * pairs + 4 * 27 * cin * cout + 4 * n * cout
@@ -86,12 +86,17 @@ if args.old:
                                             err.data_ptr(), s))
     timeit(old, "h2 (cp.async)")
 if args.trace:
-    trace = torch.zeros(512, dtype=torch.int64, device="cuda")
+    trace = torch.zeros(1024, dtype=torch.int64, device="cuda")
     L.imf_debug_conv_g4_trace(trace.data_ptr(), args.grid, args.npw, int(args.flags.split(",")[-1]))
     g4()
     torch.cuda.synchronize()
     L.imf_debug_conv_g4_trace(None, 0, 0, 0)
     t = trace.cpu().numpy()
+    life = t[256:256 + 148]
+    ends = t[256 + 320:256 + 320 + 148]
+    busy = life[life > 0]
+    print(f"per-CTA lifetime (cycles): n={len(busy)} min {busy.min()} median {int(np.median(busy))} max {busy.max()}; "
+          f"end-time spread (globaltimer ns): {int(ends[ends > 0].max() - ends[ends > 0].min())}")
     names = ["start", "barriers+TMEM", "masks", "epi wait", "acc ready", "epilogue done", "exit"]
     print("CTA0 timeline (cycles):", {nm: int(t[i] - t[0]) for i, nm in enumerate(names)})
     for i in range(36):
