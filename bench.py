@@ -4,8 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A step = one full ResUNetBN2C.forward(x, image) on ONE fragment, coordinate maps rebuilt (what the reference does for every
-new SparseTensor), inputs already resident in HBM.  Steps rotate over 8 distinct fragments per rank and the L2 is flushed
+A step = full ResUNetBN2C.forward(x, image) on --streams (default 4) independent fragments, each through its own captured
+CUDA-graph plan and stream (fragments are independent units; the single-fragment latency is reported in
+config.single_fragment_latency_ms), coordinate maps rebuilt for every fragment (what the reference does for every new
+SparseTensor), inputs already resident in HBM.  Steps rotate over 8 distinct fragments per rank and the L2 is flushed
 between steps (a 256 MiB write), outside the per-step CUDA events.  Multi-GPU: fragments are independent, each rank runs
 its own (weak scaling); the only collective is the all-gather of per-rank timings.  One JSON line is printed by rank 0.
 """
@@ -194,18 +196,35 @@ def run_ours(args, rank, world, local_rank):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    K = max(1, args.streams)      # independent fragments in flight per step (one captured plan + CUDA stream each)
+
     def step_resident(i):
-        c, f, im = dev_frags[i % N_FRAGMENTS]
-        return model(ME.SparseTensor(f, coordinates=c), im).F
+        if K == 1:
+            c, f, im = dev_frags[i % N_FRAGMENTS]
+            return model(ME.SparseTensor(f, coordinates=c), im).F
+        items = [(ME.SparseTensor(f, coordinates=c), im) for c, f, im in (dev_frags[(i * K + j) % N_FRAGMENTS] for j in range(K))]
+        return [o.F for o in model.forward_many(items, streams=K)]
 
     host_out = torch.empty((target, 32), dtype=torch.float32).pin_memory()
 
+    host_outs = [torch.empty((target, 32), dtype=torch.float32).pin_memory() for _ in range(K)]
+
     def step_e2e(i):
-        c, f, im = pin_frags[i % N_FRAGMENTS]
-        x = ME.SparseTensor(f.to(dev, non_blocking=True), coordinates=c.to(dev, non_blocking=True))
-        out = model(x, im.to(dev, non_blocking=True)).F
-        host_out.copy_(out, non_blocking=True)
-        return out
+        if K == 1:
+            c, f, im = pin_frags[i % N_FRAGMENTS]
+            x = ME.SparseTensor(f.to(dev, non_blocking=True), coordinates=c.to(dev, non_blocking=True))
+            out = model(x, im.to(dev, non_blocking=True)).F
+            host_out.copy_(out, non_blocking=True)
+            return out
+        items = []
+        for j in range(K):
+            c, f, im = pin_frags[(i * K + j) % N_FRAGMENTS]
+            items.append((ME.SparseTensor(f.to(dev, non_blocking=True), coordinates=c.to(dev, non_blocking=True)),
+                          im.to(dev, non_blocking=True)))
+        outs = model.forward_many(items, streams=K)
+        for j, o in enumerate(outs):
+            host_outs[j].copy_(o.F, non_blocking=True)
+        return outs
 
     def timed(step_fn, count_launches=False):
         for i in range(args.warmup):
@@ -241,11 +260,24 @@ def run_ours(args, rank, world, local_rank):
         ms_rank, launches, clocks, wall = timed(step_resident)
         ms_rank_e2e, _, _, _ = timed(step_e2e)
         roof = dominant_kernel_roofline(model, frags[0], flush) if rank == 0 else None
+        # latency of ONE fragment on an otherwise idle GPU (the reference's own usage pattern: scripts/generate_desc.py:65-123)
+        lat = []
+        for i in range(13):
+            c, f, im = dev_frags[i % N_FRAGMENTS]
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model(ME.SparseTensor(f, coordinates=c), im)
+            e1.record()
+            e1.synchronize()
+            if i >= 3:
+                lat.append(e0.elapsed_time(e1))
+        latency_ms = float(np.median(lat))
 
     # per-rank timing records: the one collective of this path
     from imfnet_b200.pipeline import aggregate_throughput, gather_records
-    rec = torch.tensor([rank, target * args.steps, ms_rank], dtype=torch.float64, device=dev)
-    rec_e2e = torch.tensor([rank, target * args.steps, ms_rank_e2e], dtype=torch.float64, device=dev)
+    rec = torch.tensor([rank, target * args.steps * K, ms_rank], dtype=torch.float64, device=dev)
+    rec_e2e = torch.tensor([rank, target * args.steps * K, ms_rank_e2e], dtype=torch.float64, device=dev)
     allrec, allrec_e2e = gather_records(rec, world), gather_records(rec_e2e, world)
     if rank != 0:
         return
@@ -267,18 +299,20 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": target / float(np.median(ts)), "unit": "voxels/s", "cores": cores, "kind": "port",
                "sample": f"median of {len(ts)} cold oracle forwards of one {target}-voxel fragment (same weights), fp32 torch CPU"}
 
-    h2d = target * 16 + target * 4 + 3 * H * W * 4
-    d2h = target * 32 * 4
+    h2d = K * (target * 16 + target * 4 + 3 * H * W * 4)
+    d2h = K * target * 32 * 4
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {target}-voxel synthetic 3DMatch fragment + {W}x{H} image, ResUNetBN2C 32-D descriptors",
-                   "fragments_per_step": 1, "distinct_fragments_per_rank": N_FRAGMENTS,
+                   "fragments_per_step": K, "streams": K, "single_fragment_latency_ms": latency_ms,
+                   "distinct_fragments_per_rank": N_FRAGMENTS,
                    "l2": "flushed between steps (256 MiB write, outside the per-step CUDA events)",
                    "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
                    "coordinate_maps": "rebuilt every step (cold), as the reference does per SparseTensor",
-                   "execution": "one captured CUDA graph replay per fragment (device-side sizes)" if model.use_cuda_graph else "eager launches",
+                   "execution": (f"one captured CUDA graph replay per fragment (device-side sizes), {K} independent fragments in flight on {K} streams"
+                                 if model.use_cuda_graph else "eager launches"),
                    "parallelism": f"fragments sharded over {world} GPU(s), no data-path collective"},
         "e2e": {"value": e2e_v, "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
@@ -294,6 +328,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
+    ap.add_argument("--streams", type=int, default=4, help="independent fragments in flight per step (captured plan + stream each)")
     ap.add_argument("--profile", action="store_true", help="run only warm-up + steps (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "ours" and not args.profile:

@@ -309,6 +309,9 @@ class GraphPlan:
         self.conv_ws = torch.zeros(self.conv_ws_bytes, **u8)          # head = arrival counters, zero on entry / left zero
         self.out = torch.zeros((rows, m.out_channels), **f32)
         self.side = torch.cuda.Stream(device=dev)
+        from .model.Img_Encoder import ImagePlan
+        with torch.cuda.device(dev):
+            self.image_plan = ImagePlan(m.img_encoder.backbone, self.H, self.W)     # private buffers: plans run concurrently
         self.graph = None
         self.launches_per_replay = 0
 
@@ -342,7 +345,7 @@ class GraphPlan:
         # ---- image branch on a forked stream ----
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            self.kv = m.attention_fusion.project_context(m.img_encoder.tokens(self.image[0]), False)
+            self.kv = m.attention_fusion.project_context(self.image_plan.enqueue(self.image[0]), False)
         # ---- coordinates: hash, pyramid, neighbour tables (all sizes stay on the device) ----
         self.meta.zero_()
         self.err.zero_()
@@ -415,23 +418,39 @@ class GraphPlan:
 
     # -- one forward ---------------------------------------------------------------------------
     @torch.no_grad()
-    def run(self, coords: torch.Tensor, feats: torch.Tensor, image: torch.Tensor) -> torch.Tensor:
+    def launch(self, coords: torch.Tensor, feats: torch.Tensor, image: torch.Tensor, stream=None):
+        """Enqueue one forward (input copies, graph replay, result clone, status read-back) on `stream` (default: the current
+        stream) without waiting for it; finish() returns the descriptors.  Plans launched on different streams overlap."""
         N = int(coords.shape[0])
         if N > self.rows:
             raise PlanCapacityError(f"{N} voxels > plan rows {self.rows}")
         with torch.cuda.device(self.device):
             if self.graph is None:
                 self.capture()
-            self.coords[1][:N].copy_(coords, non_blocking=True)
-            self.feats[:N].copy_(feats, non_blocking=True)
-            self.image.copy_(image.reshape(self.image.shape), non_blocking=True)
-            self.n1.fill_(N)
-            self.graph.replay()
-            GraphPlan.replayed_launches += self.launches_per_replay
-            out = self.out[:N].clone()
-            self.meta_host[:16].copy_(self.meta, non_blocking=True)
-            self.meta_host[16:].copy_(self.err, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            cur = torch.cuda.current_stream()
+            st = cur if stream is None else stream
+            if st is not cur:
+                st.wait_stream(cur)                 # the inputs were produced on the caller's stream
+            with torch.cuda.stream(st):
+                self.coords[1][:N].copy_(coords, non_blocking=True)
+                self.feats[:N].copy_(feats, non_blocking=True)
+                self.image.copy_(image.reshape(self.image.shape), non_blocking=True)
+                self.n1.fill_(N)
+                self.graph.replay()
+                GraphPlan.replayed_launches += self.launches_per_replay
+                out = self.out[:N].clone()
+                self.meta_host[:16].copy_(self.meta, non_blocking=True)
+                self.meta_host[16:].copy_(self.err, non_blocking=True)
+                self._done = torch.cuda.Event()
+                self._done.record(st)
+            self._pending = (N, out, st, cur)
+
+    def finish(self) -> torch.Tensor:
+        N, out, st, cur = self._pending
+        self._pending = None
+        self._done.synchronize()
+        if st is not cur:
+            out.record_stream(cur)
         mh = self.meta_host.tolist()
         if mh[0]:
             from .sparse import _raise_status
@@ -441,3 +460,7 @@ class GraphPlan:
         FusedPlan._raise_on_status(mh[16])
         self.levels = {1: N, 2: mh[2], 4: mh[3], 8: mh[4]}
         return out
+
+    def run(self, coords: torch.Tensor, feats: torch.Tensor, image: torch.Tensor) -> torch.Tensor:
+        self.launch(coords, feats, image)
+        return self.finish()

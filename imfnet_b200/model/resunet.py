@@ -96,6 +96,63 @@ class ResUNet2(ME.MinkowskiNetwork):
     use_cuda_graph = os.environ.get("IMFNET_B200_GRAPH", "1") != "0"
     ROW_BUCKET = GraphPlan.ROW_SLACK
 
+    @torch.no_grad()
+    def forward_many(self, items, streams: int = 2):
+        """[(x, image), ...] -> [SparseTensor, ...]: independent fragments (what scripts/generate_desc.py iterates over) run
+        through `streams` captured plans on as many CUDA streams, so the latency-bound parts of one fragment (coordinate
+        pyramid, small deep levels, attention) overlap the others' work.  Results are identical to forward() one by one."""
+        if self.training:
+            raise NotImplementedError("imfnet_b200 implements the eval-mode forward")
+        if self._plan is None:
+            self._plan = FusedPlan(self)
+            self._graphs, self._cap8_scale = {}, {}
+        plan = self._plan
+        if plan._key != plan._weights_key():
+            plan.pack()
+            self._graphs.clear()
+        outs = [None] * len(items)
+        inflight = []                                     # (index, x, GraphPlan)
+
+        def retire():
+            i, xi, g = inflight.pop(0)
+            try:
+                F = g.finish()
+            except PlanCapacityError:
+                F = None
+            if F is None:
+                F = self(xi, items[i][1]).F
+            outs[i] = ME.SparseTensor(F, coordinate_map_key=xi.coordinate_map_key, coordinate_manager=xi.coordinate_manager)
+
+        for i, (x, image) in enumerate(items):
+            if not isinstance(x, ME.SparseTensor):
+                x = ME.SparseTensor(x.F, coordinates=x.C)
+            image = torch.as_tensor(image)
+            N = len(x.F)
+            rows = (max(N, 1) + self.ROW_BUCKET - 1) // self.ROW_BUCKET * self.ROW_BUCKET
+            key = (rows, int(image.shape[2]), int(image.shape[3]))
+            ok = (image.dim() == 4 and image.shape[0] == 1 and self.use_cuda_graph and N > 0 and self._cap8_scale.get(key, 1) == 1
+                  and x.coordinate_map_key.tensor_stride == 1)
+            if not ok:
+                while inflight:
+                    retire()
+                outs[i] = self(x, image)
+                continue
+            pool = self._graphs.setdefault(("pool",) + key, [])
+            slot = i % max(1, streams)
+            while len(pool) <= slot:
+                cap8 = min(rows, max(1024, (rows // 16 + 511) // 512 * 512))
+                g = GraphPlan(plan, rows, key[1], key[2], cap8)
+                g.stream = torch.cuda.Stream(device=plan.device)
+                pool.append(g)
+            g = pool[slot]
+            while any(e[2] is g for e in inflight):
+                retire()
+            g.launch(x.C, x.F.to(device=plan.device, dtype=torch.float32), image.to(device=plan.device, dtype=torch.float32), g.stream)
+            inflight.append((i, x, g))
+        while inflight:
+            retire()
+        return outs
+
     def _forward_graph(self, x, image):
         plan = self._plan
         if plan._key != plan._weights_key():
