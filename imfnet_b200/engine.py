@@ -301,17 +301,17 @@ class GraphPlan:
         self.g0, self.g1 = h2(TR[3]), h2(TR[3])
         self.h0, self.h1 = h2(TR[2]), h2(TR[2])
         self.P8, self.fused32 = torch.zeros((self.cap8, CH[4]), **f32), torch.zeros((self.cap8, CH[4]), **f32)
-        self.n_tok = (self.H // 8) * (self.W // 8)
+        self.side = torch.cuda.Stream(device=dev)
+        from .model.Img_Encoder import ImagePlan
+        with torch.cuda.device(dev):
+            self.image_plan = ImagePlan(m.img_encoder.backbone, self.H, self.W)     # private buffers: plans run concurrently
+        self.n_tok = self.image_plan.P2                     # image tokens: conv arithmetic, not H/8 * W/8, for odd sizes
         af = m.attention_fusion
         self.att_ws_bytes = int(L.imf_attention_workspace_bytes(self.cap8, self.n_tok, af.latent_dim, af.inner))
         self.att_ws = torch.empty(max(self.att_ws_bytes, 1), **u8)
         self.conv_ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(max(max(CH[1:]), max(TR[1:]))))
         self.conv_ws = torch.zeros(self.conv_ws_bytes, **u8)          # head = arrival counters, zero on entry / left zero
         self.out = torch.zeros((rows, m.out_channels), **f32)
-        self.side = torch.cuda.Stream(device=dev)
-        from .model.Img_Encoder import ImagePlan
-        with torch.cuda.device(dev):
-            self.image_plan = ImagePlan(m.img_encoder.backbone, self.H, self.W)     # private buffers: plans run concurrently
         self.graph = None
         self.launches_per_replay = 0
 
