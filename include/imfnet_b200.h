@@ -268,6 +268,13 @@ size_t imf_attention_workspace_bytes(int32_t M, int32_t L, int32_t latent, int32
 int imf_attention_fusion_fwd(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const float* kv, int32_t L,
                              float* out, int32_t ldo, void* workspace, size_t workspace_bytes, imf_stream_t stream);
 
+/* ---- descriptor matching (next row): nearest neighbour in descriptor space, the kernel under the mutual-NN matching of
+ *      scripts/evaluation_3dmatch.py:207-217 (util/uio.py:245-258) and lib/eval.py:18-48 ---------------------------------------------- */
+/* idx[i] = argmin_j ||A[i,:C] - B[j,:C]||^2 (first index wins ties; -1 if nb == 0); d2 (optional) = that squared distance; C in {16,32,64}. */
+size_t imf_nn_search_workspace_bytes(int32_t na);
+int imf_nn_search(const float* A, int32_t lda, int32_t na, const float* B, int32_t ldb, int32_t nb, int32_t C, int32_t* idx, float* d2,
+                  void* workspace, size_t workspace_bytes, imf_stream_t stream);
+
 /* imf_attention_fusion_fwd with an optional device-side token count (min(*m_dev, M) rows; M sizes launches and workspace). */
 int imf_attention_fusion_fwd_m(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const int32_t* m_dev, const float* kv,
                                int32_t L, float* out, int32_t ldo, void* workspace, size_t workspace_bytes, imf_stream_t stream);
