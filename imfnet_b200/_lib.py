@@ -14,7 +14,7 @@ _p, _i32, _i64, _sz, _f32, _f64 = C.c_void_p, C.c_int32, C.c_longlong, C.c_size_
 
 
 class KmapJob(C.Structure):
-    _fields_ = [("out_coords", _p), ("n_out_dev", _p), ("table_in", _p), ("nbr_t", _p), ("tile_mask", _p), ("scale", _i32)]
+    _fields_ = [("out_coords", _p), ("n_out_dev", _p), ("table_in", _p), ("nbr_t", _p), ("tile_mask", _p), ("perm", _p), ("scale", _i32)]
 
 
 class AttnWeights(C.Structure):
@@ -39,6 +39,10 @@ SIGNATURES = {
     "imf_sparse_conv_g4_workspace_bytes": (_sz, [_i32]),
     "imf_sparse_conv_g4_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i32,
                                         _p, _i32, _i32, _i32, _p, _sz, _p, _p]),
+    "imf_sparse_conv_g4_fwd_perm": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i32,
+                                             _p, _i32, _i32, _i32, _p, _p, _sz, _p, _p]),
+    "imf_parity_perm_workspace_bytes": (_sz, [_i32]),
+    "imf_parity_perm": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _sz, _p]),
     "imf_debug_conv_g4_trace": (C.c_int, [_p, _i32, _i32, _i32]),
     "imf_quantize_points": (C.c_int, [_p, _i32, _f64, _i32, _p, _p]),
     "imf_batch_segments": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),

@@ -207,6 +207,7 @@ struct KmapJob {
   const ImfSlot* table;
   int* nbr_t;
   unsigned* tile_mask;
+  const int* perm;       // optional: table row o describes output row perm[o] (parity-grouped transposed convolution)
   int scale;
   int pad;
 };
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(128) k_kernel_map_t(const __grid_constant__ Km
   const int o = tile * 128 + threadIdx.x;
   const int K3 = K * K * K, h = K / 2;
   int4 c = make_int4(0, 0, 0, 0);
-  if (o < n) c = jb.out_coords[o];
+  if (o < n) c = jb.out_coords[jb.perm ? jb.perm[o] : o];
   unsigned mine = 0u;
   for (int k = 0; k < K3; ++k) {
     int r = -1;
@@ -241,6 +242,66 @@ __global__ void __launch_bounds__(128) k_kernel_map_t(const __grid_constant__ Km
   if ((threadIdx.x & 31) == 0) wmask[threadIdx.x >> 5] = mine;
   __syncthreads();
   if (threadIdx.x == 0) jb.tile_mask[tile] = wmask[0] | wmask[1] | wmask[2] | wmask[3];
+}
+
+// ---- parity grouping of a coordinate set (for transposed convolutions) ---------------------------------------------------
+// A voxel f of the fine set (coordinates multiples of t) can only have coarse parents (multiples of 2t) at the offsets whose
+// non-zero components sit exactly on the axes where f/t is odd: 8 parity classes with 1, 2, 2, 2, 4, 4, 4, 8 candidate offsets
+// instead of 27.  perm lists the rows grouped by class (stable inside a class), so a 128-row tile of the permuted order walks
+// 1-8 offsets instead of all 27.  Three small kernels: per-block histogram, scan, stable scatter.
+__device__ __forceinline__ int imf_parity_class(const int4& c, int t) {
+  return (((c.y / t) & 1)) | (((c.z / t) & 1) << 1) | (((c.w / t) & 1) << 2);
+}
+__global__ void __launch_bounds__(256) k_parity_hist(const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max, int t,
+                                                     int* __restrict__ hist /*[blocks][8]*/) {
+  __shared__ int h[8];
+  const int n = imf_count(n_ptr, n_max);
+  if (threadIdx.x < 8) h[threadIdx.x] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) atomicAdd(&h[imf_parity_class(coords[i], t)], 1);
+  __syncthreads();
+  if (threadIdx.x < 8) hist[blockIdx.x * 8 + threadIdx.x] = h[threadIdx.x];
+}
+// offsets[b][c] = rows of classes < c (all blocks) + rows of class c in blocks < b          (one block, 8 warps = 8 classes)
+__global__ void __launch_bounds__(256) k_parity_scan(const int* __restrict__ hist, int blocks, int* __restrict__ offs) {
+  __shared__ int total[8];
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int run = 0;
+  for (int b0 = 0; b0 < blocks; b0 += 32) {
+    const int b = b0 + lane;
+    const int v = b < blocks ? hist[b * 8 + c] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (b < blocks) offs[b * 8 + c] = run + incl - v;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) total[c] = run;
+  __syncthreads();
+  int base = 0;
+  for (int k = 0; k < c; ++k) base += total[k];
+  for (int b = lane; b < blocks; b += 32) offs[b * 8 + c] += base;
+}
+__global__ void __launch_bounds__(256) k_parity_scatter(const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max, int t,
+                                                        const int* __restrict__ offs, int* __restrict__ perm) {
+  __shared__ int wcnt[8][8];      // [warp][class]
+  const int n = imf_count(n_ptr, n_max);
+  const int i = blockIdx.x * 256 + threadIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cls = i < n ? imf_parity_class(coords[i], t) : -1;
+  int rank_in_warp = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+    if (cls == c) rank_in_warp = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) wcnt[warp][c] = __popc(m);
+  }
+  __syncthreads();
+  if (cls >= 0) {
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += wcnt[w][cls];
+    perm[offs[blockIdx.x * 8 + cls] + before + rank_in_warp] = i;
+  }
 }
 
 // xyz (float64 [N,3]) -> int32 (b, floor(x/voxel), floor(y/voxel), floor(z/voxel)).  IEEE double division and
@@ -359,6 +420,7 @@ struct imf_kmap_job_t {      // mirrors include/imfnet_b200.h
   const void* table_in;
   int32_t* nbr_t;
   uint32_t* tile_mask;
+  const int32_t* perm;
   int32_t scale;
 };
 
@@ -376,6 +438,7 @@ extern "C" int imf_kernel_map_t_batch(const imf_kmap_job_t* jobs, int32_t njobs,
     kj.j[i].table = reinterpret_cast<const ImfSlot*>(jobs[i].table_in);
     kj.j[i].nbr_t = jobs[i].nbr_t;
     kj.j[i].tile_mask = jobs[i].tile_mask;
+    kj.j[i].perm = jobs[i].perm;
     kj.j[i].scale = jobs[i].scale;
     kj.j[i].pad = 0;
   }
@@ -389,8 +452,27 @@ extern "C" int imf_kernel_map_t_batch(const imf_kmap_job_t* jobs, int32_t njobs,
 extern "C" int imf_kernel_map_t(const int32_t* out_coords, const int32_t* n_out_dev, int32_t n_out_max, const void* table_in,
                                 long long capacity, int32_t kernel_size, int32_t scale, int32_t* nbr_t, int32_t ld_n,
                                 uint32_t* tile_mask, cudaStream_t stream) {
-  imf_kmap_job_t job{out_coords, n_out_dev, table_in, nbr_t, tile_mask, scale};
+  imf_kmap_job_t job{out_coords, n_out_dev, table_in, nbr_t, tile_mask, nullptr, scale};
   return imf_kernel_map_t_batch(&job, 1, n_out_max, capacity, kernel_size, ld_n, stream);
+}
+
+extern "C" size_t imf_parity_perm_workspace_bytes(int32_t n_max) { return (size_t)((n_max > 0 ? n_max : 1) + 255) / 256 * 8 * 2 * sizeof(int); }
+
+extern "C" int imf_parity_perm(const int32_t* coords, const int32_t* n_dev, int32_t n_max, int32_t tensor_stride, int32_t* perm,
+                               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  IMF_CHECK_ARG(n_max >= 0 && tensor_stride >= 1);
+  if (n_max == 0) return IMF_OK;
+  IMF_CHECK_ARG(coords != nullptr && perm != nullptr && workspace != nullptr && workspace_bytes >= imf_parity_perm_workspace_bytes(n_max));
+  const int blocks = (n_max + 255) / 256;
+  int* hist = reinterpret_cast<int*>(workspace);
+  int* offs = hist + (size_t)blocks * 8;
+  k_parity_hist<<<blocks, 256, 0, stream>>>(reinterpret_cast<const int4*>(coords), n_dev, n_max, tensor_stride, hist);
+  IMF_CHECK_LAUNCH();
+  k_parity_scan<<<1, 256, 0, stream>>>(hist, blocks, offs);
+  IMF_CHECK_LAUNCH();
+  k_parity_scatter<<<blocks, 256, 0, stream>>>(reinterpret_cast<const int4*>(coords), n_dev, n_max, tensor_stride, offs, perm);
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
 }
 
 extern "C" int imf_quantize_points(const double* xyz, int32_t n, double voxel_size, int32_t batch_index, int32_t* coords,

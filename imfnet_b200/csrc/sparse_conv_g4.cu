@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ CUtensorMap tmY, const unsigned char* __restrict__ Wp,
                  const int* __restrict__ nbr_t, int ld_n, const unsigned* __restrict__ tile_mask, const int* __restrict__ n_ptr, int n_max,
                  int K3, int nchunks, const float* __restrict__ scale, const float* __restrict__ shift, const __half* __restrict__ R, int ldr,
-                 int kc_r, int relu, int kc_out, float* __restrict__ P, int cout_total, int* err, long long* __restrict__ trace, int dbg) {
+                 int kc_r, int relu, int kc_out, float* __restrict__ P, int cout_total, const int* __restrict__ out_row, __half* __restrict__ Yp,
+                 int ldy, int* err, long long* __restrict__ trace, int dbg) {
   using Cfg = G4Cfg<BN, KC>;
   constexpr int NA = Cfg::NA;
   extern __shared__ unsigned char smem_dyn[];
@@ -485,7 +486,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
         const int r_in = q * 32 + lane;
         const int grow = prow + j * kBM + r_in;
         unsigned char* stage = a_ring + (j & 1) * Cfg::OUT_BYTES;
-        if (!partial) {
+        if (!partial && !out_row) {
           if (j >= 2 && tid == 0) tma::store_wait_read<1>();       // the stores that read this buffer two sub-tiles ago
           named_barrier(1, 256);
         }
@@ -528,6 +529,16 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
           Half8 hi[2], lo[2];
           const bool b = g4_split16(a, hi, lo);
           big |= b && (grow < n);
+          if (out_row) {        // parity-grouped transposed convolution: table row grow describes output row out_row[grow]
+            if (grow < n && grow < row_end) {      // rows past row_end belong to the next CTA's range
+              __half* yp = Yp + (size_t)__ldg(out_row + grow) * ldy + (c / kc_out) * 2 * kc_out + (c % kc_out);
+              reinterpret_cast<Half8*>(yp)[0] = hi[0];
+              reinterpret_cast<Half8*>(yp)[1] = hi[1];
+              reinterpret_cast<Half8*>(yp + kc_out)[0] = lo[0];
+              reinterpret_cast<Half8*>(yp + kc_out)[1] = lo[1];
+            }
+            continue;
+          }
           // staged layout: image = 64 halves of the h2 row; kc_out = 64: images (hi, lo) per 64 channels; 32: one image [hi32|lo32]
           int img_hi, img_lo, ch_hi, ch_lo;
           if (kc_out == 64) {
@@ -542,7 +553,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
           *reinterpret_cast<Half8*>(pl + tc::sw128_offset(r_in, ch_lo)) = lo[0];
           *reinterpret_cast<Half8*>(pl + tc::sw128_offset(r_in, ch_lo + 1)) = lo[1];
         }
-        if (!partial) {
+        if (!partial && !out_row) {
           tc::fence_proxy_async();
           named_barrier(1, 256);
           if (tid == 0) {
@@ -558,7 +569,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
           }
         }
       }
-      if (!partial && tid == 0) tma::store_wait_read<0>();
+      if (!partial && !out_row && tid == 0) tma::store_wait_read<0>();
       if (big && err) atomicOr(err, 0x10000);
       if (tid == 0) G4_TRACE(5);
     }
@@ -585,7 +596,8 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
 __global__ void __launch_bounds__(256) k_conv_g4_reduce(const float* __restrict__ P, const int* __restrict__ n_ptr, int n_max, int gx,
                                                         int nst_max, int Cout, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, const __half* __restrict__ R, int ldr, int kc_r,
-                                                        int relu, __half* __restrict__ Y, int ldy, int kc_out, int* err) {
+                                                        int relu, __half* __restrict__ Y, int ldy, int kc_out, int* err,
+                                                        const int* __restrict__ out_row) {
   int n = n_max;
   if (n_ptr) { const int v = *n_ptr; n = v < n_max ? v : n_max; }
   const G4Part part = g4_partition(n, gx, nst_max, true);
@@ -619,7 +631,7 @@ __global__ void __launch_bounds__(256) k_conv_g4_reduce(const float* __restrict_
   }
   Half8 hi[2], lo[2];
   const bool big = g4_split16(a, hi, lo);
-  __half* yp = Y + (size_t)row * ldy + (c / kc_out) * 2 * kc_out + (c % kc_out);
+  __half* yp = Y + (size_t)(out_row ? __ldg(out_row + row) : row) * ldy + (c / kc_out) * 2 * kc_out + (c % kc_out);
   reinterpret_cast<Half8*>(yp)[0] = hi[0];
   reinterpret_cast<Half8*>(yp)[1] = hi[1];
   reinterpret_cast<Half8*>(yp + kc_out)[0] = lo[0];
@@ -634,7 +646,8 @@ int g_g4_grid = 0;        // profiling hook: overrides the number of CTAs per ou
 template <int BN, int KC>
 int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, const int* nbr_t, int ld_n, const unsigned* tile_mask,
               const int* n_ptr, int n_max, int K3, int Cin, int Cout, const float* scale, const float* shift, const __half* R, int ldr,
-              int kc_r, int relu, __half* Y, int ldy, int kc_out, void* ws, size_t ws_bytes, int* err, cudaStream_t stream) {
+              int kc_r, int relu, __half* Y, int ldy, int kc_out, const int* out_row, void* ws, size_t ws_bytes, int* err,
+              cudaStream_t stream) {
   using Cfg = G4Cfg<BN, KC>;
   const size_t smem = (size_t)Cfg::RING_BYTES + (size_t)kNW * Cfg::W_BYTES + 1024;
   static bool attr_done = false;
@@ -653,13 +666,13 @@ int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, 
   dim3 grid(gx, 1, ntn);
   k_sparse_conv_g4<BN, KC><<<grid, kThreads, smem, stream>>>(X, ldx, tmY, reinterpret_cast<const unsigned char*>(Wp), nbr_t, ld_n, tile_mask,
                                                             n_ptr, n_max, K3, nchunks, scale, shift, R, ldr, kc_r, relu, kc_out, P, Cout,
-                                                            err, g_g4_trace, g_g4_dbg);
+                                                            out_row, Y, ldy, err, g_g4_trace, g_g4_dbg);
   IMF_CHECK_LAUNCH();
   if (P != nullptr) {      // split mode is possible for small n: the reduce kernel decides on the device (no-op otherwise)
     const int rows = n_max < gx * kBM ? n_max : gx * kBM;      // split mode only exists below gx tiles
     const long long total = (long long)rows * (Cout / 16);
     k_conv_g4_reduce<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, n_ptr, n_max, gx, nst_max, Cout, scale, shift, R, ldr, kc_r,
-                                                                         relu, Y, ldy, kc_out, err);
+                                                                         relu, Y, ldy, kc_out, err, out_row);
     IMF_CHECK_LAUNCH();
   }
   return IMF_OK;
@@ -677,12 +690,34 @@ extern "C" int imf_debug_conv_g4_trace(long long* trace, int32_t grid, int32_t p
 
 extern "C" size_t imf_sparse_conv_g4_workspace_bytes(int32_t Cout) { return (size_t)kSMs * kBM * (size_t)Cout * sizeof(float); }
 
+extern "C" int imf_sparse_conv_g4_fwd_perm(const void* X, int32_t ldx, int32_t kc_in, const void* packed, const int32_t* nbr_t,
+                                           int32_t ld_n, const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max,
+                                           int32_t kernel_volume, int32_t Cin, int32_t Cout, const float* scale, const float* shift,
+                                           const void* residual, int32_t ldr, int32_t kc_r, int32_t relu, void* Y, int32_t ldy,
+                                           int32_t n_y_rows, int32_t kc_out, const int32_t* out_row, void* workspace,
+                                           size_t workspace_bytes, int32_t* err, cudaStream_t stream);
+
 extern "C" int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t kc_in, const void* packed, const int32_t* nbr_t,
                                       int32_t ld_n, const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max,
                                       int32_t kernel_volume, int32_t Cin, int32_t Cout, const float* scale, const float* shift,
                                       const void* residual, int32_t ldr, int32_t kc_r, int32_t relu, void* Y, int32_t ldy,
                                       int32_t n_y_rows, int32_t kc_out, void* workspace, size_t workspace_bytes, int32_t* err,
                                       cudaStream_t stream) {
+  return imf_sparse_conv_g4_fwd_perm(X, ldx, kc_in, packed, nbr_t, ld_n, tile_mask, n_out_dev, n_out_max, kernel_volume, Cin, Cout, scale,
+                                     shift, residual, ldr, kc_r, relu, Y, ldy, n_y_rows, kc_out, nullptr, workspace, workspace_bytes, err,
+                                     stream);
+}
+
+// Same with a row permutation: table row v (and tile masks) describe output row out_row[v]; the result of table row v is written
+// to Y[out_row[v]].  Used with imf_parity_perm for transposed convolutions, whose 128-row tiles then walk 1-8 offsets instead of 27.
+// residual (if any) is read at table-row order, so it must be NULL unless it is permuted the same way.
+extern "C" int imf_sparse_conv_g4_fwd_perm(const void* X, int32_t ldx, int32_t kc_in, const void* packed, const int32_t* nbr_t,
+                                           int32_t ld_n, const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max,
+                                           int32_t kernel_volume, int32_t Cin, int32_t Cout, const float* scale, const float* shift,
+                                           const void* residual, int32_t ldr, int32_t kc_r, int32_t relu, void* Y, int32_t ldy,
+                                           int32_t n_y_rows, int32_t kc_out, const int32_t* out_row, void* workspace,
+                                           size_t workspace_bytes, int32_t* err, cudaStream_t stream) {
+  IMF_CHECK_ARG(out_row == nullptr || residual == nullptr);
   IMF_CHECK_ARG(n_out_max >= 0 && kernel_volume >= 1 && kernel_volume <= 27);
   IMF_CHECK_ARG((kc_in == 32 || kc_in == 64) && Cin > 0 && Cin % kc_in == 0 && (Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256));
   IMF_CHECK_ARG((kc_out == 32 || kc_out == 64) && Cout % kc_out == 0);
@@ -701,7 +736,7 @@ extern "C" int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t kc_in,
   __half* Yh = reinterpret_cast<__half*>(Y);
 #define IMF_GO(BN, KC)                                                                                                               \
   return launch_g4<BN, KC>(reinterpret_cast<const __half*>(X), ldx, tmY, packed, nbr_t, ld_n, tile_mask, n_out_dev, n_out_max, kernel_volume, Cin, Cout, scale, shift, Rh, \
-                           ldr, kc_r, relu, Yh, ldy, kc_out, workspace, workspace_bytes, err, stream)
+                           ldr, kc_r, relu, Yh, ldy, kc_out, out_row, workspace, workspace_bytes, err, stream)
   const int bn = Cout > 128 ? 128 : Cout;
   if (kc_in == 64) {
     if (bn == 32) IMF_GO(32, 64);

@@ -284,6 +284,9 @@ class GraphPlan:
         self.sm_ws_bytes = int(L.imf_stride_map_workspace_bytes(rows))
         self.sm_ws = torch.empty(self.sm_ws_bytes, **u8)
         self.ldn = (rows + 127) // 128 * 128
+        self.perm = {t: torch.zeros(self.ldn, **i32) for t in (1, 2, 4)}
+        self.perm_ws_bytes = int(L.imf_parity_perm_workspace_bytes(rows))
+        self.perm_ws = torch.empty(self.perm_ws_bytes, **u8)
         self.nbr = {}
         for key in [(1, 1, False), (2, 2, False), (4, 4, False), (8, 8, False), (1, 2, False), (2, 4, False), (4, 8, False),
                     (8, 4, True), (4, 2, True), (2, 1, True)]:
@@ -325,11 +328,12 @@ class GraphPlan:
         # a stride-1 level of this bucket always has >= 128 * 148 rows when the bucket is large enough: row mode is certain, so no
         # split workspace (and no reduce launch) is needed there
         split = not (t_out == 1 and self.rows - self.ROW_SLACK >= 128 * 148)
-        _lib.check(L.imf_sparse_conv_g4_fwd(X, ldx, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(), self._n(t_out),
-                                            self.rows, 27, conv.in_channels, conv.out_channels, scale.data_ptr(), shift.data_ptr(), R,
-                                            ldr, kc_r, 1 if relu else 0, Y, ldy, self.rows, kc_out,
-                                            self.conv_ws.data_ptr() if split else None, self.conv_ws_bytes if split else 0,
-                                            self.err.data_ptr(), s))
+        out_row = self.perm[t_out].data_ptr() if key[2] else None          # transposed: the table is in parity-grouped row order
+        _lib.check(L.imf_sparse_conv_g4_fwd_perm(X, ldx, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(),
+                                                 self._n(t_out), self.rows, 27, conv.in_channels, conv.out_channels, scale.data_ptr(),
+                                                 shift.data_ptr(), R, ldr, kc_r, 1 if relu else 0, Y, ldy, self.rows, kc_out, out_row,
+                                                 self.conv_ws.data_ptr() if split else None, self.conv_ws_bytes if split else 0,
+                                                 self.err.data_ptr(), s))
 
     def _block(self, L, name, X, ldx, kc_x, t, C, tmp, Y, ldy, kc_y, s):
         kt = _kc(C)
@@ -355,10 +359,14 @@ class GraphPlan:
             _lib.check(L.imf_stride_map(self.coords[prev].data_ptr(), self._n(prev), rows, t, self.tables[t].data_ptr(), self.cap,
                                         self.coords[t].data_ptr(), self._n(t), None, self.sm_ws.data_ptr(), self.sm_ws_bytes, status, s))
             prev = t
+        # transposed convolutions: output rows grouped by coordinate parity, so a tile walks 1-8 offsets instead of 27
+        for t in (1, 2, 4):
+            _lib.check(L.imf_parity_perm(self.coords[t].data_ptr(), self._n(t), rows, t, self.perm[t].data_ptr(), self.perm_ws.data_ptr(),
+                                         self.perm_ws_bytes, s))
         jobs = (_lib.KmapJob * len(self.nbr))()
         for i, ((t_in, t_out, tr), (nbr_t, ld_n, mask)) in enumerate(self.nbr.items()):
             jobs[i] = _lib.KmapJob(self.coords[t_out].data_ptr(), self._n(t_out), self.tables[t_in].data_ptr(), nbr_t.data_ptr(),
-                                   mask.data_ptr(), -t_out if tr else t_in)
+                                   mask.data_ptr(), self.perm[t_out].data_ptr() if tr else None, -t_out if tr else t_in)
         _lib.check(L.imf_kernel_map_t_batch(jobs, len(self.nbr), rows, self.cap, 3, self.ldn, s))       # all 10 tables, one launch
         # ---- encoder ----
         ld1, ld2, ld4 = 2 * self.cat1.shape[1], 2 * self.cat2.shape[1], 2 * self.cat4.shape[1]

@@ -81,10 +81,18 @@ typedef struct {
   const void* table_in;
   int32_t* nbr_t;
   uint32_t* tile_mask;
+  const int32_t* perm; /* optional: table row o describes output row perm[o] (see imf_parity_perm) */
   int32_t scale;
 } imf_kmap_job_t;
 int imf_kernel_map_t_batch(const imf_kmap_job_t* jobs, int32_t njobs, int32_t n_out_max, long long capacity, int32_t kernel_size,
                            int32_t ld_n, imf_stream_t stream);
+
+/* Rows of a coordinate set at tensor stride t grouped by the parity class of (x/t, y/t, z/t) (stable inside a class): perm[v] = row.
+ * A fine voxel can only have coarse parents at the offsets whose non-zero components sit on its odd axes, so tiles of the permuted
+ * order need 1, 2, 4 or 8 of the 27 offsets of a stride-2 transposed convolution (model/resunet.py:101-134). */
+size_t imf_parity_perm_workspace_bytes(int32_t n_max);
+int imf_parity_perm(const int32_t* coords, const int32_t* n_dev, int32_t n_max, int32_t tensor_stride, int32_t* perm, void* workspace,
+                    size_t workspace_bytes, imf_stream_t stream);
 
 /* coords[i] = (batch_index, floor(xyz[i]/voxel_size)) in float64, as util/misc.py:82 computes on the host. */
 int imf_quantize_points(const double* xyz, int32_t n, double voxel_size, int32_t batch_index, int32_t* coords,
@@ -153,6 +161,14 @@ int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t kc_in, const void
                            int32_t Cout, const float* scale, const float* shift, const void* residual, int32_t ldr, int32_t kc_r,
                            int32_t relu, void* Y, int32_t ldy, int32_t n_y_rows, int32_t kc_out, void* workspace, size_t workspace_bytes,
                            int32_t* err, imf_stream_t stream);
+/* imf_sparse_conv_g4_fwd with a row permutation: table row v (and its tile masks) describe output row out_row[v], whose result is
+ * written to Y[out_row[v]].  With imf_parity_perm this makes the 128-row tiles of a TRANSPOSED convolution walk only the 1-8 offsets
+ * their rows can have instead of all 27.  residual must be NULL. */
+int imf_sparse_conv_g4_fwd_perm(const void* X, int32_t ldx, int32_t kc_in, const void* packed, const int32_t* nbr_t, int32_t ld_n,
+                                const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max, int32_t kernel_volume, int32_t Cin,
+                                int32_t Cout, const float* scale, const float* shift, const void* residual, int32_t ldr, int32_t kc_r,
+                                int32_t relu, void* Y, int32_t ldy, int32_t n_y_rows, int32_t kc_out, const int32_t* out_row,
+                                void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
 /* Profiling hook: device int64 buffer (>= 1024 entries) filled by CTA 0 with clock64() stamps (slot map in the source), and an
  * override of the CTAs per output-channel tile (0 = one per SM) and of the producer warps per CTA (8 or 16; other values keep the
  * current setting); flags: bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs (results are then meaningless).

@@ -418,3 +418,73 @@ def test_module_level_layers_match_standin(frag):
     close(z.F.cpu(), ref_z)
     assert z.coordinate_map_key == x.coordinate_map_key and len(z) == len(x)
     assert ME.cat(x, z).F.shape == (len(coords), 64)
+
+
+@pytest.fixture(scope="module")
+def frag_big():
+    """30 000 voxels: more 128-row tiles than SMs at stride 1, i.e. the row-range mode of the persistent kernel."""
+    coords, _ = synthetic.make_fragment(30000, 0.025, seed=6)
+    ocm = sparse_ops.CoordinateManager(coords)
+    ocm.stride(1, 2)
+    from imfnet_b200.sparse import CoordinateManager
+    cm = CoordinateManager(torch.from_numpy(coords).cuda())
+    cm.build_pyramid([2])
+    return coords, ocm, cm
+
+
+def test_parity_grouped_transposed_conv_row_mode(frag_big):
+    test_parity_grouped_transposed_conv_matches_oracle(frag_big, 2, 1, 128, 64, True)
+
+
+@pytest.mark.parametrize("t_in,t_out,cin,cout", [(2, 1, 128, 64), (4, 2, 256, 64), (8, 4, 256, 128)])
+@pytest.mark.parametrize("split", [False, True])
+def test_parity_grouped_transposed_conv_matches_oracle(frag, t_in, t_out, cin, cout, split):
+    """imf_parity_perm + imf_kernel_map_t_batch(perm) + imf_sparse_conv_g4_fwd_perm: the transposed convolution computed in
+    parity-grouped row order gives the oracle's result in the original row order, and its tiles need few offsets."""
+    coords, ocm, cm = frag
+    L = _lib.lib()
+    fine, coarse = cm.level(t_out), cm.level(t_in)
+    n = fine.n
+    ld_n = (n + 127) // 128 * 128
+    s = _lib.cur_stream()
+    perm = torch.full((ld_n,), -7, dtype=torch.int32, device="cuda")
+    ws_b = int(L.imf_parity_perm_workspace_bytes(n))
+    ws_p = torch.empty(ws_b, dtype=torch.uint8, device="cuda")
+    _lib.check(L.imf_parity_perm(fine.coords.data_ptr(), None, n, t_out, perm.data_ptr(), ws_p.data_ptr(), ws_b, s))
+    p = perm[:n].cpu().numpy()
+    assert sorted(p.tolist()) == list(range(n))                                   # a permutation
+    c = fine.coords.cpu().numpy()
+    cls = ((c[:, 1] // t_out) & 1) | (((c[:, 2] // t_out) & 1) << 1) | (((c[:, 3] // t_out) & 1) << 2)
+    assert np.array_equal(p, np.argsort(cls, kind="stable"))                      # grouped by class, stable inside
+    nbr_t = torch.empty((27, ld_n), dtype=torch.int32, device="cuda")
+    mask = torch.empty(ld_n // 128 + 1, dtype=torch.int32, device="cuda")
+    job = (_lib.KmapJob * 1)(_lib.KmapJob(fine.coords.data_ptr(), None, coarse.table.data_ptr(), nbr_t.data_ptr(), mask.data_ptr(),
+                                          perm.data_ptr(), -t_out))
+    _lib.check(L.imf_kernel_map_t_batch(job, 1, n, coarse.capacity, 3, ld_n, s))
+    onbr = ocm.table(t_in, t_out, 3, True)
+    assert np.array_equal(nbr_t.cpu().numpy()[:, :n], onbr[p].T)
+    offsets_per_tile = [bin(int(m) & 0x7FFFFFF).count("1") for m in mask.cpu().numpy()[: (n + 127) // 128]]
+    assert np.mean(offsets_per_tile) < 14                                          # 27 without the grouping
+    g = torch.Generator().manual_seed(cin + cout)
+    X = torch.randn(coarse.n, cin, generator=g)
+    W = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ref = torch.relu(sparse_ops.conv_forward(X, W, onbr) * scale + shift)
+    kc_in, kc_out = 64, 64
+    wmul = 2.0 ** np.floor(np.log2(2048.0 / float(W.abs().max())))
+    Wd = W.cuda()
+    packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(27, cin, cout, kc_in)), dtype=torch.uint8, device="cuda")
+    _lib.check(L.imf_sparse_conv_h2_pack(Wd.data_ptr(), 27, cin, cout, kc_in, wmul, packed.data_ptr(), s))
+    Xh = h2_pack(X.cuda(), kc_in)
+    Yh = torch.full((n, 2 * cout), float("nan"), dtype=torch.float16, device="cuda")
+    ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(cout)) if split else 0
+    ws = torch.zeros(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    sc, sh = (scale / wmul).cuda().contiguous(), shift.cuda()
+    _lib.check(L.imf_sparse_conv_g4_fwd_perm(Xh.data_ptr(), Xh.stride(0), kc_in, packed.data_ptr(), nbr_t.data_ptr(), ld_n, mask.data_ptr(),
+                                             None, n, 27, cin, cout, sc.data_ptr(), sh.data_ptr(), None, 0, 0, 1, Yh.data_ptr(),
+                                             Yh.stride(0), n, kc_out, perm.data_ptr(), ws.data_ptr() if split else None, ws_bytes,
+                                             err.data_ptr(), s))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    close(h2_unpack(Yh, cout, kc_out).cpu(), ref, H2_RTOL)
