@@ -201,6 +201,10 @@ __global__ void k_kernel_map(const int4* __restrict__ out_coords, const int* __r
 // [n, roundup128(n)) are -1 (they pad the last tile); tile_mask[o/128] has bit k set when any row of that 128-row tile has a
 // neighbour at offset k.  One CTA = one 128-row tile of one table (blockIdx.y = job): every thread probes the K^3 offsets of
 // its row, so the tile mask is a plain store (no memset, no atomics) and several tables share one launch.
+__device__ __forceinline__ int imf_parity_class(const int4& c, int t) {
+  return (((c.y / t) & 1)) | (((c.z / t) & 1) << 1) | (((c.w / t) & 1) << 2);
+}
+
 struct KmapJob {
   const int4* out_coords;
   const int* n_ptr;
@@ -227,13 +231,19 @@ __global__ void __launch_bounds__(128) k_kernel_map_t(const __grid_constant__ Km
   const int K3 = K * K * K, h = K / 2;
   int4 c = make_int4(0, 0, 0, 0);
   if (o < n) c = jb.out_coords[jb.perm ? jb.perm[o] : o];
+  const bool transposed = jb.perm != nullptr && jb.scale < 0 && K == 3;      // parity-grouped tables are stride-2 transposed by contract
+  const int pc = transposed ? imf_parity_class(c, -jb.scale) : 0;
   unsigned mine = 0u;
   for (int k = 0; k < K3; ++k) {
     int r = -1;
     if (o < n) {
       const int kx = k % K - h, ky = (k / K) % K - h, kz = k / (K * K) - h;
-      const int x = c.y + kx * jb.scale, y = c.z + ky * jb.scale, z = c.w + kz * jb.scale;
-      if (imf_coord_in_range(c.x, x, y, z)) r = imf_table_lookup(jb.table, mask, imf_pack_key(c.x, x, y, z));
+      // transposed table (scale < 0, stride-2 parents): a parent can only sit at offsets that are non-zero exactly on the odd axes
+      const bool possible = !transposed || (((kx != 0) == ((pc & 1) != 0)) && ((ky != 0) == ((pc & 2) != 0)) && ((kz != 0) == ((pc & 4) != 0)));
+      if (possible) {
+        const int x = c.y + kx * jb.scale, y = c.z + ky * jb.scale, z = c.w + kz * jb.scale;
+        if (imf_coord_in_range(c.x, x, y, z)) r = imf_table_lookup(jb.table, mask, imf_pack_key(c.x, x, y, z));
+      }
     }
     if (o < ld_n) jb.nbr_t[(size_t)k * ld_n + o] = r;
     mine |= (r >= 0 ? 1u : 0u) << k;
@@ -249,9 +259,6 @@ __global__ void __launch_bounds__(128) k_kernel_map_t(const __grid_constant__ Km
 // non-zero components sit exactly on the axes where f/t is odd: 8 parity classes with 1, 2, 2, 2, 4, 4, 4, 8 candidate offsets
 // instead of 27.  perm lists the rows grouped by class (stable inside a class), so a 128-row tile of the permuted order walks
 // 1-8 offsets instead of all 27.  Three small kernels: per-block histogram, scan, stable scatter.
-__device__ __forceinline__ int imf_parity_class(const int4& c, int t) {
-  return (((c.y / t) & 1)) | (((c.z / t) & 1) << 1) | (((c.w / t) & 1) << 2);
-}
 __global__ void __launch_bounds__(256) k_parity_hist(const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max, int t,
                                                      int* __restrict__ hist /*[blocks][8]*/) {
   __shared__ int h[8];

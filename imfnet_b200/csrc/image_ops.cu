@@ -33,32 +33,44 @@ __global__ void __launch_bounds__(128) k_image_conv_table(int Hin, int Win, int 
 }
 
 // im2col of an NCHW fp32 image for a K x K / stride / pad convolution: row = output pixel, column = c + C*(kx + K*ky),
-// zero-padded to Kpad columns, written as an h2 matrix with chunk width 32.  One thread = (pixel, 8 columns).
+// zero-padded to Kpad columns, written as an h2 matrix with chunk width 32.  One CTA = 32 consecutive output pixels of one
+// image row: the input patch (K rows x (31*stride + K) columns x C channels) is staged in shared memory with coalesced reads,
+// then every thread produces 8 columns of one pixel (two 16-byte stores).
 __global__ void __launch_bounds__(256) k_image_im2col_h2(const float* __restrict__ img, int C, int H, int W, int Hout, int Wout, int K,
                                                          int stride, int pad, int Kpad, __half* __restrict__ Y, int ldy) {
-  const int groups = Kpad >> 3;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= (long long)Hout * Wout * groups) return;
-  const int o = (int)(idx / groups), g = (int)(idx % groups);
-  const int oy = o / Wout, ox = o - oy * Wout;
-  const int ktot = C * K * K;
-  __half hi[8], lo[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int col = g * 8 + i;
-    float v = 0.f;
-    if (col < ktot) {
-      const int c = col % C, t = col / C;
-      const int iy = oy * stride - pad + t / K, ix = ox * stride - pad + t % K;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + ((size_t)c * H + iy) * W + ix);
-    }
-    hi[i] = __float2half_rn(v);
-    lo[i] = __float2half_rn(v - __half2float(hi[i]));
+  extern __shared__ float patch[];                 // [C][K][PW]
+  const int PW = 31 * stride + K;
+  const int xblocks = (Wout + 31) / 32;
+  const int oy = blockIdx.x / xblocks, ox0 = (blockIdx.x % xblocks) * 32;
+  const int iy0 = oy * stride - pad, ix0 = ox0 * stride - pad;
+  for (int t = threadIdx.x; t < C * K * PW; t += 256) {
+    const int px = t % PW, r = (t / PW) % K, c = t / (PW * K);
+    const int iy = iy0 + r, ix = ix0 + px;
+    patch[t] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + ((size_t)c * H + iy) * W + ix) : 0.f;
   }
-  const int col0 = g * 8;
-  __half* p = Y + (size_t)o * ldy + (col0 >> 5) * 64 + (col0 & 31);
-  *reinterpret_cast<int4*>(p) = *reinterpret_cast<const int4*>(hi);
-  *reinterpret_cast<int4*>(p + 32) = *reinterpret_cast<const int4*>(lo);
+  __syncthreads();
+  const int groups = Kpad >> 3, ktot = C * K * K;
+  for (int w = threadIdx.x; w < 32 * groups; w += 256) {
+    const int p = w / groups, g = w % groups;
+    const int ox = ox0 + p;
+    if (ox >= Wout) continue;
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = g * 8 + i;
+      float v = 0.f;
+      if (col < ktot) {
+        const int c = col % C, t = col / C;
+        v = patch[(c * K + t / K) * PW + p * stride + t % K];
+      }
+      hi[i] = __float2half_rn(v);
+      lo[i] = __float2half_rn(v - __half2float(hi[i]));
+    }
+    const int col0 = g * 8;
+    __half* q = Y + (size_t)(oy * Wout + ox) * ldy + (col0 >> 5) * 64 + (col0 & 31);
+    *reinterpret_cast<int4*>(q) = *reinterpret_cast<const int4*>(hi);
+    *reinterpret_cast<int4*>(q + 32) = *reinterpret_cast<const int4*>(lo);
+  }
 }
 
 // 3x3 (K x K) max pooling with stride / padding on a pixel-major h2 matrix; padding never wins (torch semantics).
@@ -137,9 +149,10 @@ extern "C" int imf_image_im2col_h2(const float* image, int32_t C, int32_t H, int
   IMF_CHECK_ARG(Kpad % 32 == 0 && Kpad >= C * ksize * ksize && ldy % 8 == 0 && ldy >= 2 * Kpad && ((uintptr_t)Y % 16) == 0);
   const int Hout = (H + 2 * pad - ksize) / stride + 1, Wout = (W + 2 * pad - ksize) / stride + 1;
   IMF_CHECK_ARG(Hout > 0 && Wout > 0);
-  const long long total = (long long)Hout * Wout * (Kpad / 8);
-  k_image_im2col_h2<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(image, C, H, W, Hout, Wout, ksize, stride, pad, Kpad,
-                                                                       reinterpret_cast<__half*>(Y), ldy);
+  const size_t smem = (size_t)C * ksize * (31 * stride + ksize) * sizeof(float);
+  IMF_CHECK_ARG(smem <= 48 * 1024);
+  k_image_im2col_h2<<<(unsigned)(Hout * ((Wout + 31) / 32)), 256, smem, stream>>>(image, C, H, W, Hout, Wout, ksize, stride, pad, Kpad,
+                                                                                reinterpret_cast<__half*>(Y), ldy);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }

@@ -81,7 +81,8 @@ typedef struct {
   const void* table_in;
   int32_t* nbr_t;
   uint32_t* tile_mask;
-  const int32_t* perm; /* optional: table row o describes output row perm[o] (see imf_parity_perm) */
+  const int32_t* perm; /* optional: table row o describes output row perm[o] (see imf_parity_perm); only for the STRIDE-2 transposed
+                          convolution (scale = -fine stride): offsets impossible for the row's parity class are not probed */
   int32_t scale;
 } imf_kmap_job_t;
 int imf_kernel_map_t_batch(const imf_kmap_job_t* jobs, int32_t njobs, int32_t n_out_max, long long capacity, int32_t kernel_size,
