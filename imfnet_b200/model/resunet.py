@@ -140,7 +140,7 @@ class ResUNet2(ME.MinkowskiNetwork):
             pool = self._graphs.setdefault(("pool",) + key, [])
             slot = i % max(1, streams)
             while len(pool) <= slot:
-                cap8 = min(rows, max(1024, (rows // 16 + 511) // 512 * 512))
+                cap8 = self._cap8(rows, 1)
                 g = GraphPlan(plan, rows, key[1], key[2], cap8)
                 g.stream = torch.cuda.Stream(device=plan.device)
                 pool.append(g)
@@ -152,6 +152,13 @@ class ResUNet2(ME.MinkowskiNetwork):
         while inflight:
             retire()
         return outs
+
+    @staticmethod
+    def _cap8(rows: int, scale: int) -> int:
+        """Token capacity of a plan at stride 8.  Indoor fragments have ~1/46 of their voxels left at stride 8 (real and synthetic
+        3DMatch data); the plan is sized for 1/28 (the dense GEMMs of the fusion module pick their tiling from this
+        capacity, so a loose bound costs time) and a fragment that exceeds it falls back to the eager plan once and gets a 4x plan."""
+        return min(rows, max(512, (rows // 28 + 255) // 256 * 256) * scale)
 
     def _forward_graph(self, x, image):
         plan = self._plan
@@ -168,7 +175,7 @@ class ResUNet2(ME.MinkowskiNetwork):
             return None
         g = self._graphs.get(key)
         if g is None:
-            cap8 = min(rows, max(1024, (rows // 16 + 511) // 512 * 512) * scale)
+            cap8 = self._cap8(rows, scale)
             g = self._graphs[key] = GraphPlan(plan, rows, key[1], key[2], cap8)
         feats = x.F.to(device=plan.device, dtype=torch.float32)
         try:
