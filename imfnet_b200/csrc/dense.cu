@@ -9,6 +9,15 @@
 // LayerNorm also performs the [C,L] -> [L,C] transposition of resunet.py:259-261.
 #include "common.cuh"
 
+// fused attention kernel (flash_fusion.cu), used when the head has 128 channels (the IMFNet configuration)
+size_t imf_flash_kv_h2_bytes(int L);
+size_t imf_flash_workspace_bytes(int M_max, int L);
+int imf_flash_pack_kv(const float* K, const float* Vt, int ldv, int L, void* kvh2, cudaStream_t stream);
+int imf_flash_attention(const void* qh2, int M_max, const int* m_dev, const void* kvh2, int L, float* o, int ldo, void* workspace,
+                        size_t workspace_bytes, int* err, cudaStream_t stream);
+extern "C" int imf_h2_pack_n(const float* X, int32_t ldx, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, void* H, int32_t ldh,
+                             int32_t* err, cudaStream_t stream);
+
 namespace {
 
 // ---- LayerNorm over the last dim of row-major rows; one warp per row, C <= 1024, C % 32 == 0 ----
@@ -221,7 +230,8 @@ static inline int round4(int v) { return (v + 3) / 4 * 4; }
 // Layout of the projected context of one image ("kv" buffers): K [L, inner] row-major, then V^T [inner, Lp] (Lp = L rounded
 // up to 4) so that both attention GEMMs read K-major operands.
 extern "C" size_t imf_attention_kv_bytes(int32_t L, int32_t inner) {
-  return r256((size_t)L * inner * 4) + r256((size_t)inner * round4(L) * 4);
+  // K [L, inner] fp32, V^T [inner, Lp] fp32, then (128-channel head) their fp16 hi/lo copies for the fused attention kernel
+  return r256((size_t)L * inner * 4) + r256((size_t)inner * round4(L) * 4) + (inner == 128 ? r256(imf_flash_kv_h2_bytes(L)) : 0);
 }
 extern "C" size_t imf_attention_kv_workspace_bytes(int32_t L, int32_t dim) { return r256((size_t)L * dim * 4); }
 
@@ -244,7 +254,12 @@ extern "C" int imf_attention_kv(const imf_attn_weights_t* w, const float* tokens
   float* Vt = reinterpret_cast<float*>(reinterpret_cast<char*>(kv) + r256((size_t)L * inner * 4));
   int rc;
   if ((rc = imf_tc_gemm(cn, dim, w->wkv, dim, Kmat, inner, L, inner, dim, 1.f, nullptr, nullptr, 0, 0, nullptr, 0, nullptr, stream))) return rc;
-  return imf_tc_gemm(w->wkv + (size_t)inner * dim, dim, cn, dim, Vt, Lp, inner, L, dim, 1.f, nullptr, nullptr, 0, 0, nullptr, 0, nullptr, stream);
+  if ((rc = imf_tc_gemm(w->wkv + (size_t)inner * dim, dim, cn, dim, Vt, Lp, inner, L, dim, 1.f, nullptr, nullptr, 0, 0, nullptr, 0, nullptr, stream))) return rc;
+  if (inner == 128) {
+    void* kvh2 = reinterpret_cast<char*>(kv) + r256((size_t)L * inner * 4) + r256((size_t)inner * Lp * 4);
+    return imf_flash_pack_kv(Kmat, Vt, Lp, L, kvh2, stream);
+  }
+  return IMF_OK;
 }
 
 extern "C" size_t imf_attention_workspace_bytes(int32_t M, int32_t L, int32_t latent, int32_t inner) {
@@ -255,7 +270,8 @@ extern "C" size_t imf_attention_workspace_bytes(int32_t M, int32_t L, int32_t la
          + r256((size_t)M * inner * 4)     // attention output
          + r256((size_t)M * latent * 4)    // x after attention residual
          + r256((size_t)M * latent * 4 * 4)   // GEGLU hidden [M, 4*latent]
-         + r256(imf_tc_gemm_workspace_bytes(M, latent, 0));   // split-K partials (largest N used with split-K = latent)
+         + r256(imf_tc_gemm_workspace_bytes(M, latent, 0))    // split-K partials (largest N used with split-K = latent)
+         + (inner == 128 ? r256((size_t)M * inner * 4) + r256(imf_flash_workspace_bytes(M, L)) : 0);   // q as h2 + flash partials
 }
 
 // out[M, latent] = cross-attention + GEGLU feed-forward of M point tokens P[M, latent] against kv (imf_attention_kv).
@@ -295,13 +311,24 @@ extern "C" int imf_attention_fusion_fwd_m(const imf_attn_weights_t* w, const flo
   k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(P, ldp, M, latent, w->ln_q_w, w->ln_q_b, 1e-5f, xn, latent, m_dev);
   IMF_CHECK_LAUNCH();
   // q = LN(P) . Wq^T
-  if ((rc = imf_tc_gemm_m(xn, latent, w->wq, latent, q, inner, M, m_dev, inner, latent, 1.f, nullptr, nullptr, 0, 0, gws, gws_bytes, nullptr, stream))) return rc;
+  if ((rc = imf_tc_gemm_m(xn, latent, w->wq, latent, q, inner, M, m_dev, inner, latent, inner == 128 ? sm_scale : 1.f, nullptr, nullptr, 0, 0,
+                          gws, gws_bytes, nullptr, stream))) return rc;
+  if (inner == 128) {
+    // fused attention: q (scaled) -> fp16 hi/lo -> one tcgen05 kernel for q k^T, softmax and .v (flash_fusion.cu)
+    char* ws2 = reinterpret_cast<char*>(gws) + r256(gws_bytes);
+    void* qh2 = ws2;
+    void* fws = ws2 + r256((size_t)M * inner * 4);
+    const void* kvh2 = reinterpret_cast<const char*>(kv) + r256((size_t)L * inner * 4) + r256((size_t)inner * Lp * 4);
+    if ((rc = imf_h2_pack_n(q, inner, M, m_dev, inner, 64, qh2, 2 * inner, nullptr, stream))) return rc;
+    if ((rc = imf_flash_attention(qh2, M, m_dev, kvh2, L, o, inner, fws, imf_flash_workspace_bytes(M, L), nullptr, stream))) return rc;
+  } else {
   // S = (q . K^T) * scale
   if ((rc = imf_tc_gemm_m(q, inner, Kmat, inner, S, Lp, M, m_dev, L, inner, sm_scale, nullptr, nullptr, 0, 0, nullptr, 0, nullptr, stream))) return rc;
   k_softmax_rows<<<M, 256, 0, stream>>>(S, Lp, M, L, m_dev);
   IMF_CHECK_LAUNCH();
   // o = A . V   (as A . (V^T)^T, split over the L tokens)
   if ((rc = imf_tc_gemm_m(S, Lp, Vt, Lp, o, inner, M, m_dev, inner, L, 1.f, nullptr, nullptr, 0, 0, gws, gws_bytes, nullptr, stream))) return rc;
+  }
   // x1 = o . Wo^T + bo + P
   if ((rc = imf_tc_gemm_m(o, inner, w->wo, inner, x1, latent, M, m_dev, latent, inner, 1.f, w->bo, P, ldp, 0, gws, gws_bytes, nullptr, stream))) return rc;
   k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(x1, latent, M, latent, w->ln_f_w, w->ln_f_b, 1e-5f, xn, latent, m_dev);
