@@ -216,15 +216,8 @@ def run_ours(args, rank, world, local_rank):
             out = model(x, im.to(dev, non_blocking=True)).F
             host_out.copy_(out, non_blocking=True)
             return out
-        items = []
-        for j in range(K):
-            c, f, im = pin_frags[(i * K + j) % N_FRAGMENTS]
-            items.append((ME.SparseTensor(f.to(dev, non_blocking=True), coordinates=c.to(dev, non_blocking=True)),
-                          im.to(dev, non_blocking=True)))
-        outs = model.forward_many(items, streams=K)
-        for j, o in enumerate(outs):
-            host_outs[j].copy_(o.F, non_blocking=True)
-        return outs
+        # the public end-to-end call: pinned host fragments in, pinned host descriptors out (copies ride the plans' streams)
+        return model.forward_many_host([pin_frags[(i * K + j) % N_FRAGMENTS] for j in range(K)], streams=K, out=host_outs)
 
     def timed(step_fn, count_launches=False):
         for i in range(args.warmup):

@@ -426,9 +426,11 @@ class GraphPlan:
 
     # -- one forward ---------------------------------------------------------------------------
     @torch.no_grad()
-    def launch(self, coords: torch.Tensor, feats: torch.Tensor, image: torch.Tensor, stream=None):
+    def launch(self, coords: torch.Tensor, feats: torch.Tensor, image: torch.Tensor, stream=None, out_host: torch.Tensor | None = None):
         """Enqueue one forward (input copies, graph replay, result clone, status read-back) on `stream` (default: the current
-        stream) without waiting for it; finish() returns the descriptors.  Plans launched on different streams overlap."""
+        stream) without waiting for it; finish() returns the descriptors.  Plans launched on different streams overlap.
+        The inputs may be pinned host tensors (the copies into the plan's static buffers are then the host->device transfers);
+        with `out_host` (pinned [N, C]) the result goes straight to the host instead of into a device clone."""
         N = int(coords.shape[0])
         if N > self.rows:
             raise PlanCapacityError(f"{N} voxels > plan rows {self.rows}")
@@ -446,7 +448,11 @@ class GraphPlan:
                 self.n1.fill_(N)
                 self.graph.replay()
                 GraphPlan.replayed_launches += self.launches_per_replay
-                out = self.out[:N].clone()
+                if out_host is None:
+                    out = self.out[:N].clone()
+                else:
+                    out = out_host[:N]
+                    out.copy_(self.out[:N], non_blocking=True)
                 self.meta_host[:16].copy_(self.meta, non_blocking=True)
                 self.meta_host[16:].copy_(self.err, non_blocking=True)
                 self._done = torch.cuda.Event()
@@ -457,7 +463,7 @@ class GraphPlan:
         N, out, st, cur = self._pending
         self._pending = None
         self._done.synchronize()
-        if st is not cur:
+        if st is not cur and out.is_cuda:
             out.record_stream(cur)
         mh = self.meta_host.tolist()
         if mh[0]:

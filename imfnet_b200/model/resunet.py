@@ -160,6 +160,65 @@ class ResUNet2(ME.MinkowskiNetwork):
         capacity, so a loose bound costs time) and a fragment that exceeds it falls back to the eager plan once and gets a 4x plan."""
         return min(rows, max(512, (rows // 28 + 255) // 256 * 256) * scale)
 
+    @torch.no_grad()
+    def forward_many_host(self, frags, streams: int = 2, out=None):
+        """End-to-end form of forward_many for host-resident fragments: frags = [(coords int32 [N,4], feats fp32 [N,Cin],
+        image fp32 [1,3,H,W]), ...] as (ideally pinned) CPU tensors; returns pinned CPU tensors [N, out_channels].  Every fragment's
+        host->device copies, graph replay and device->host copy run on its plan's stream, so the transfers of one fragment overlap
+        the compute of the others (the reference does `feature.detach().cpu()` synchronously per fragment,
+        scripts/generate_desc.py:118-123).  `out` may provide the destination tensors."""
+        if self.training:
+            raise NotImplementedError("imfnet_b200 implements the eval-mode forward")
+        if self._plan is None:
+            self._plan = FusedPlan(self)
+            self._graphs, self._cap8_scale = {}, {}
+        plan = self._plan
+        if plan._key != plan._weights_key():
+            plan.pack()
+            self._graphs.clear()
+        outs = [None] * len(frags)
+        inflight = []
+
+        def eager(i):
+            c, f, im = frags[i]
+            x = ME.SparseTensor(f.to(plan.device, non_blocking=True), coordinates=c.to(plan.device, non_blocking=True))
+            F = self(x, im.to(plan.device, non_blocking=True)).F
+            dst = out[i] if out is not None else torch.empty(F.shape, dtype=F.dtype, pin_memory=True)
+            dst[: len(F)].copy_(F)
+            return dst[: len(F)]
+
+        def retire():
+            i, g = inflight.pop(0)
+            try:
+                outs[i] = g.finish()
+            except PlanCapacityError:
+                outs[i] = eager(i)
+
+        for i, (c, f, im) in enumerate(frags):
+            N = int(c.shape[0])
+            rows = (max(N, 1) + self.ROW_BUCKET - 1) // self.ROW_BUCKET * self.ROW_BUCKET
+            key = (rows, int(im.shape[2]), int(im.shape[3]))
+            if not (self.use_cuda_graph and N > 0 and im.shape[0] == 1 and self._cap8_scale.get(key, 1) == 1):
+                while inflight:
+                    retire()
+                outs[i] = eager(i)
+                continue
+            pool = self._graphs.setdefault(("pool",) + key, [])
+            slot = i % max(1, streams)
+            while len(pool) <= slot:
+                g = GraphPlan(plan, rows, key[1], key[2], self._cap8(rows, 1))
+                g.stream = torch.cuda.Stream(device=plan.device)
+                pool.append(g)
+            g = pool[slot]
+            while any(e[1] is g for e in inflight):
+                retire()
+            dst = out[i] if out is not None else torch.empty((N, self.out_channels), dtype=torch.float32, pin_memory=True)
+            g.launch(c, f.float(), im.float(), g.stream, out_host=dst)
+            inflight.append((i, g))
+        while inflight:
+            retire()
+        return outs
+
     def _forward_graph(self, x, image):
         plan = self._plan
         if plan._key != plan._weights_key():

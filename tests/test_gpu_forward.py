@@ -224,3 +224,17 @@ def test_attention_stress_8192x4800_vs_oracle(state_dict, cuda_model):
     ref = imfnet_oracle.attention_fusion(state_dict, I, P)
     out = cuda_model.attention_fusion(I.cuda(), queries_encoder=P.cuda())
     assert note("attention_8192x4800_vs_oracle", rel_rows(out[0].cpu(), ref[0])) < TOL
+
+
+def test_forward_many_host_equals_forward(cuda_model):
+    """Pinned host fragments in, pinned host descriptors out (transfers on the plans' streams): same bits as forward()."""
+    import imfnet_b200.me as ME
+    frags = []
+    for n, seed in ((3000, 21), (3900, 22), (2500, 23)):
+        coords, _ = synthetic.make_fragment(n, 0.05, seed=seed)
+        frags.append((torch.from_numpy(coords).pin_memory(), torch.ones((n, 1)).pin_memory(), synthetic.make_image(160, 120, seed=seed).pin_memory()))
+    seq = [cuda_model(ME.SparseTensor(f, coordinates=c, device="cuda"), im.cuda()).F.cpu() for c, f, im in frags]
+    for streams in (1, 2):
+        outs = cuda_model.forward_many_host(frags, streams=streams)
+        for a, b in zip(seq, outs):
+            assert not b.is_cuda and torch.equal(a, b)
