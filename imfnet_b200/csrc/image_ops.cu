@@ -38,8 +38,14 @@ __global__ void __launch_bounds__(128) k_image_conv_table(int Hin, int Win, int 
 // then every thread produces 8 columns of one pixel (two 16-byte stores).
 __global__ void __launch_bounds__(256) k_image_im2col_h2(const float* __restrict__ img, int C, int H, int W, int Hout, int Wout, int K,
                                                          int stride, int pad, int Kpad, __half* __restrict__ Y, int ldy) {
-  extern __shared__ float patch[];                 // [C][K][PW]
+  extern __shared__ float patch[];                 // [C][K][PW], then the column -> patch offset table [Kpad]
   const int PW = 31 * stride + K;
+  int* off_s = reinterpret_cast<int*>(patch + C * K * PW);
+  for (int col = threadIdx.x; col < Kpad; col += 256) {
+    int o = -1;
+    if (col < C * K * K) { const int c = col % C, t = col / C; o = (c * K + t / K) * PW + t % K; }
+    off_s[col] = o;
+  }
   const int xblocks = (Wout + 31) / 32;
   const int oy = blockIdx.x / xblocks, ox0 = (blockIdx.x % xblocks) * 32;
   const int iy0 = oy * stride - pad, ix0 = ox0 * stride - pad;
@@ -49,7 +55,7 @@ __global__ void __launch_bounds__(256) k_image_im2col_h2(const float* __restrict
     patch[t] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + ((size_t)c * H + iy) * W + ix) : 0.f;
   }
   __syncthreads();
-  const int groups = Kpad >> 3, ktot = C * K * K;
+  const int groups = Kpad >> 3;
   for (int w = threadIdx.x; w < 32 * groups; w += 256) {
     const int p = w / groups, g = w % groups;
     const int ox = ox0 + p;
@@ -57,12 +63,8 @@ __global__ void __launch_bounds__(256) k_image_im2col_h2(const float* __restrict
     __half hi[8], lo[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int col = g * 8 + i;
-      float v = 0.f;
-      if (col < ktot) {
-        const int c = col % C, t = col / C;
-        v = patch[(c * K + t / K) * PW + p * stride + t % K];
-      }
+      const int o = off_s[g * 8 + i];
+      const float v = o >= 0 ? patch[o + p * stride] : 0.f;
       hi[i] = __float2half_rn(v);
       lo[i] = __float2half_rn(v - __half2float(hi[i]));
     }
@@ -149,7 +151,7 @@ extern "C" int imf_image_im2col_h2(const float* image, int32_t C, int32_t H, int
   IMF_CHECK_ARG(Kpad % 32 == 0 && Kpad >= C * ksize * ksize && ldy % 8 == 0 && ldy >= 2 * Kpad && ((uintptr_t)Y % 16) == 0);
   const int Hout = (H + 2 * pad - ksize) / stride + 1, Wout = (W + 2 * pad - ksize) / stride + 1;
   IMF_CHECK_ARG(Hout > 0 && Wout > 0);
-  const size_t smem = (size_t)C * ksize * (31 * stride + ksize) * sizeof(float);
+  const size_t smem = (size_t)C * ksize * (31 * stride + ksize) * sizeof(float) + (size_t)Kpad * sizeof(int);
   IMF_CHECK_ARG(smem <= 48 * 1024);
   k_image_im2col_h2<<<(unsigned)(Hout * ((Wout + 31) / 32)), 256, smem, stream>>>(image, C, H, W, Hout, Wout, ksize, stride, pad, Kpad,
                                                                                 reinterpret_cast<__half*>(Y), ldy);
