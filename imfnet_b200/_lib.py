@@ -47,10 +47,6 @@ SIGNATURES = {
     "imf_quantize_points": (C.c_int, [_p, _i32, _f64, _i32, _p, _p]),
     "imf_batch_segments": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
     "imf_sparse_conv_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _i32, _p]),
-    "imf_sparse_conv_tc_packed_bytes": (_sz, [_i32, _i32, _i32]),
-    "imf_sparse_conv_tc_pack": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
-    "imf_sparse_conv_tc_workspace_bytes": (_sz, [_i32, _i32]),
-    "imf_sparse_conv_tc_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _i32, _p, _sz, _p, _p]),
     "imf_h2_pack": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p, _p]),
     "imf_h2_unpack": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p]),
     "imf_h2_pack_n": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p, _p]),

@@ -114,19 +114,6 @@ int imf_sparse_conv_fwd(const float* X, int32_t ldx, const float* W, const int32
                         const float* shift, const float* residual, int32_t ldr, int32_t relu, float* Y, int32_t ldy,
                         imf_stream_t stream);
 
-/* Tensor-core path of the same operation (tcgen05.mma kind::tf32 with a 3-way hi/lo split = fp32-class accuracy,
- * accumulators in TMEM, weights staged by bulk/TMA copies).  Weights are packed once with imf_sparse_conv_tc_pack
- * (hi/lo split, 128-byte-swizzled K-major slabs per (offset, 32-channel chunk)).  Cout in {32,64,128,256}.
- * workspace (optional, imf_sparse_conv_tc_workspace_bytes) lets the small deep levels split a tile's offsets over
- * several CTAs; err (optional device int) gets a non-zero code if an in-kernel barrier wait times out. */
-size_t imf_sparse_conv_tc_packed_bytes(int32_t kernel_volume, int32_t Cin, int32_t Cout);
-int imf_sparse_conv_tc_pack(const float* W, int32_t kernel_volume, int32_t Cin, int32_t Cout, void* packed, imf_stream_t stream);
-size_t imf_sparse_conv_tc_workspace_bytes(int32_t n_out_max, int32_t Cout);
-int imf_sparse_conv_tc_fwd(const float* X, int32_t ldx, const void* packed, const int32_t* nbr, const int32_t* n_out_dev,
-                           int32_t n_out_max, int32_t kernel_volume, int32_t Cin, int32_t Cout, const float* scale,
-                           const float* shift, const float* residual, int32_t ldr, int32_t relu, float* Y, int32_t ldy,
-                           void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
-
 /* ---- "h2" tier: activations stored as two fp16 halves (v = hi + lo), products accumulated as lo*Whi + hi*Wlo + hi*Whi by
  *      kind::f16 tcgen05 MMAs into fp32 TMEM (fp32-class accuracy at twice the TF32 MMA rate and a copy-only gather).
  * h2 matrix of C channels with chunk width KC in {32,64} (C % KC == 0), row stride ld in HALVES (>= 2C, multiple of 8):

@@ -58,43 +58,6 @@ def test_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout):
     close(run_conv(X.cuda(), W.cuda(), nbr, n_out), ref)
 
 
-def run_conv_tc(X, W, nbr, n_out, scale=None, shift=None, R=None, relu=False, split=True):
-    L = _lib.lib()
-    K3, cin, cout = W.shape
-    packed = torch.empty(int(L.imf_sparse_conv_tc_packed_bytes(K3, cin, cout)), dtype=torch.uint8, device="cuda")
-    _lib.check(L.imf_sparse_conv_tc_pack(W.data_ptr(), K3, cin, cout, packed.data_ptr(), _lib.cur_stream()))
-    Y = torch.full((n_out, cout), float("nan"), device="cuda")
-    ws_bytes = int(L.imf_sparse_conv_tc_workspace_bytes(n_out, cout)) if split else 0
-    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
-    err = torch.zeros(1, dtype=torch.int32, device="cuda")
-    _lib.check(L.imf_sparse_conv_tc_fwd(X.data_ptr(), X.stride(0), packed.data_ptr(), nbr.data_ptr(), None, n_out, K3, cin, cout,
-                                        _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(R), 0 if R is None else R.stride(0), int(relu),
-                                        Y.data_ptr(), Y.stride(0), ws.data_ptr() if split else None, ws_bytes, err.data_ptr(),
-                                        _lib.cur_stream()))
-    torch.cuda.synchronize()
-    assert int(err.item()) == 0
-    return Y.cpu()
-
-
-@pytest.mark.parametrize("t_in,t_out,tr,cin,cout", [
-    (1, 1, False, 32, 32), (1, 1, False, 64, 64), (1, 2, False, 32, 64), (2, 2, False, 64, 64), (2, 4, False, 64, 128),
-    (4, 4, False, 128, 128), (4, 8, False, 128, 256), (8, 8, False, 256, 256), (8, 4, True, 256, 128), (4, 2, True, 256, 64),
-    (2, 1, True, 128, 64)])
-@pytest.mark.parametrize("split", [False, True])
-def test_tensor_core_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout, split):
-    """tcgen05 3xTF32 implicit GEMM: same tolerance as the fp32 kernel (the split keeps fp32-class accuracy)."""
-    coords, ocm, cm = frag
-    g = torch.Generator().manual_seed(cin * 1000 + cout + t_in)
-    n_in, n_out = len(ocm.get(t_in)), len(ocm.get(t_out))
-    X = torch.randn(n_in, cin, generator=g)
-    W = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
-    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
-    R = torch.randn(n_out, cout, generator=g)
-    ref = torch.relu(sparse_ops.conv_forward(X, W, ocm.table(t_in, t_out, 3, tr)) * scale + shift + R)
-    out = run_conv_tc(X.cuda(), W.cuda(), cm.table(t_in, t_out, 3, tr), n_out, scale.cuda(), shift.cuda(), R.cuda(), True, split)
-    close(out, ref)
-
-
 def h2_pack(X, kc, ld_extra=0):
     L = _lib.lib()
     n, C = X.shape
@@ -324,20 +287,6 @@ def test_h2_first_conv_and_tail(frag):
     out = torch.empty_like(ref)
     out[:] = Y.cpu()
     close(out[perm.long()], ref, H2_RTOL)
-
-
-def test_tensor_core_conv_equals_simt_conv_c2_size():
-    """50 k voxels, 64->64: the two CUDA tiers agree to fp32 rounding, and rows without any neighbour give exactly `shift`."""
-    coords, _ = synthetic.make_fragment(50000, 0.025, 0)
-    from imfnet_b200.sparse import CoordinateManager
-    cm = CoordinateManager(torch.from_numpy(coords).cuda())
-    nbr = cm.table(1, 1, 3, False)
-    g = torch.Generator(device="cuda").manual_seed(1)
-    X = torch.randn(50000, 64, device="cuda", generator=g)
-    W = torch.randn(27, 64, 64, device="cuda", generator=g) / 40
-    a = run_conv(X, W, nbr, 50000)
-    b = run_conv_tc(X, W, nbr, 50000, split=False)
-    close(b, a)
 
 
 def test_conv_fused_epilogue_and_strided_operands(frag):
