@@ -334,7 +334,20 @@ def main():
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL may print its version banner on stdout while the communicator is created; stdout must carry exactly one JSON line,
+        # so the descriptor is pointed at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            torch.cuda.set_device(local_rank)
+            torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     try:
         run_ours(args, rank, world, local_rank)
     finally:
