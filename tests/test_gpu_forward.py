@@ -238,3 +238,21 @@ def test_forward_many_host_equals_forward(cuda_model):
         outs = cuda_model.forward_many_host(frags, streams=streams)
         for a, b in zip(seq, outs):
             assert not b.is_cuda and torch.equal(a, b)
+
+
+def test_graph_plan_capacity_fallback_on_scattered_voxels(state_dict, cuda_model):
+    """Isolated voxels: every level keeps ~all rows, so the stride-8 level exceeds the captured plan's token capacity; the forward
+    must fall back to the eager plan (and then re-capture a larger plan) and still match the oracle."""
+    import imfnet_b200.me as ME
+    rng = np.random.default_rng(3)
+    pts = np.unique(rng.integers(-2000, 2000, size=(3000, 3)).astype(np.int32), axis=0)
+    rng.shuffle(pts)
+    coords = torch.from_numpy(np.concatenate([np.zeros((len(pts), 1), np.int32), pts], axis=1))
+    feats = torch.ones((len(coords), 1))
+    image = synthetic.make_image(160, 120, seed=9)
+    ref = imfnet_oracle.forward(state_dict, coords, feats, image)
+    for attempt in range(3):          # 1: overflow -> eager; 2: larger captured plan; 3: replay of it
+        d = cuda_model(ME.SparseTensor(feats, coordinates=coords, device="cuda"), image.cuda()).F.cpu()
+        assert rel_rows(d, ref) < TOL, attempt
+    many = cuda_model.forward_many([(ME.SparseTensor(feats, coordinates=coords, device="cuda"), image.cuda())] * 2, streams=2)
+    assert all(rel_rows(o.F.cpu(), ref) < TOL for o in many)
