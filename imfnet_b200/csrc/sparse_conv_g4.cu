@@ -103,15 +103,18 @@ struct G4Part {
   int S;          // splits per tile (split mode)
   int T;          // 128-row tiles
 };
-__host__ __device__ inline G4Part g4_partition(int n, int gx, int nst_max, bool have_ws) {
+__host__ __device__ inline G4Part g4_partition(int n, int gx, int nst_max, bool have_ws, int stages_per_split) {
   G4Part p;
   p.T = (n + kBM - 1) / kBM;
   p.row_mode = (p.T >= gx) ? 1 : 0;
   p.R = ((((n + gx - 1) / gx) + 31) / 32) * 32;
   int S = 1;
   if (!p.row_mode && have_ws && p.T > 0) {
+    // as many splits as free SMs allow, but not below `stages_per_split` stages per CTA: a split costs a partial-tile round trip
+    // through L2 and a share of the reduce kernel, which only pays when it shortens a long stage list
     S = gx / p.T;
-    if (S > nst_max / 4) S = nst_max / 4;
+    const int smax = (nst_max + stages_per_split - 1) / stages_per_split;
+    if (S > smax) S = smax;
     if (S > 32) S = 32;
     if (S < 1) S = 1;
   }
@@ -172,7 +175,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
                  const int* __restrict__ nbr_t, int ld_n, const unsigned* __restrict__ tile_mask, const int* __restrict__ n_ptr, int n_max,
                  int K3, int nchunks, const float* __restrict__ scale, const float* __restrict__ shift, const __half* __restrict__ R, int ldr,
                  int kc_r, int relu, int kc_out, float* __restrict__ P, int cout_total, const int* __restrict__ out_row, __half* __restrict__ Yp,
-                 int ldy, int* err, long long* __restrict__ trace, int dbg) {
+                 int ldy, int* err, long long* __restrict__ trace, int dbg, int sps) {
   using Cfg = G4Cfg<BN, KC>;
   constexpr int NA = Cfg::NA;
   extern __shared__ unsigned char smem_dyn[];
@@ -196,7 +199,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gx = gridDim.x, bx = blockIdx.x, zt = blockIdx.z, ntn = gridDim.z;
   const int nst_max = K3 * nchunks;
-  const G4Part part = g4_partition(n, gx, nst_max, P != nullptr);
+  const G4Part part = g4_partition(n, gx, nst_max, P != nullptr, sps);
   const int n32 = (n + 31) & ~31;
 
   // rows of this CTA and its sub-tiles
@@ -597,10 +600,10 @@ __global__ void __launch_bounds__(256) k_conv_g4_reduce(const float* __restrict_
                                                         int nst_max, int Cout, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, const __half* __restrict__ R, int ldr, int kc_r,
                                                         int relu, __half* __restrict__ Y, int ldy, int kc_out, int* err,
-                                                        const int* __restrict__ out_row) {
+                                                        const int* __restrict__ out_row, int sps) {
   int n = n_max;
   if (n_ptr) { const int v = *n_ptr; n = v < n_max ? v : n_max; }
-  const G4Part part = g4_partition(n, gx, nst_max, true);
+  const G4Part part = g4_partition(n, gx, nst_max, true, sps);
   if (part.row_mode || part.S <= 1) return;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const int c16 = Cout >> 4;
@@ -641,6 +644,7 @@ __global__ void __launch_bounds__(256) k_conv_g4_reduce(const float* __restrict_
 
 long long* g_g4_trace = nullptr;
 int g_g4_dbg = 0;       // profiling hook: bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs (results meaningless)
+int g_g4_sps = 4;         // stages per split CTA at least (profiling hook can change it)
 int g_g4_grid = 0;        // profiling hook: overrides the number of CTAs per output-channel tile (0 = one per SM)
 
 template <int BN, int KC>
@@ -666,13 +670,13 @@ int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, 
   dim3 grid(gx, 1, ntn);
   k_sparse_conv_g4<BN, KC><<<grid, kThreads, smem, stream>>>(X, ldx, tmY, reinterpret_cast<const unsigned char*>(Wp), nbr_t, ld_n, tile_mask,
                                                             n_ptr, n_max, K3, nchunks, scale, shift, R, ldr, kc_r, relu, kc_out, P, Cout,
-                                                            out_row, Y, ldy, err, g_g4_trace, g_g4_dbg);
+                                                            out_row, Y, ldy, err, g_g4_trace, g_g4_dbg, g_g4_sps);
   IMF_CHECK_LAUNCH();
   if (P != nullptr) {      // split mode is possible for small n: the reduce kernel decides on the device (no-op otherwise)
     const int rows = n_max < gx * kBM ? n_max : gx * kBM;      // split mode only exists below gx tiles
     const long long total = (long long)rows * (Cout / 16);
     k_conv_g4_reduce<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, n_ptr, n_max, gx, nst_max, Cout, scale, shift, R, ldr, kc_r,
-                                                                         relu, Y, ldy, kc_out, err, out_row);
+                                                                         relu, Y, ldy, kc_out, err, out_row, g_g4_sps);
     IMF_CHECK_LAUNCH();
   }
   return IMF_OK;
@@ -684,7 +688,7 @@ extern "C" int imf_debug_conv_g4_trace(long long* trace, int32_t grid, int32_t p
   g_g4_trace = trace;
   g_g4_dbg = flags;
   g_g4_grid = grid;
-  (void)producer_warps;
+  if (producer_warps > 0) g_g4_sps = producer_warps;      // (argument re-used: minimum stages per split CTA)
   return IMF_OK;
 }
 

@@ -21,7 +21,7 @@ ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--flush", type=int, default=1)
 ap.add_argument("--grid", type=int, default=0)
 ap.add_argument("--trace", action="store_true")
-ap.add_argument("--npw", type=int, default=0, help="producer warps per CTA (8 or 16)")
+ap.add_argument("--npw", type=int, default=0, help="minimum stages per split CTA (profiling hook)")
 ap.add_argument("--flags", default="0", help="comma list of profiling flags: 1 no W copies, 2 no gathers, 4 no MMAs")
 ap.add_argument("--old", action="store_true", help="also time imf_sparse_conv_h2_fwd (the cp.async kernel)")
 args = ap.parse_args()
