@@ -85,3 +85,28 @@ def aggregate_throughput(records: torch.Tensor):
     the job's time is the MAX over ranks, its work the SUM."""
     ms = float(records[:, 2].max())
     return float(records[:, 1].sum()) / (ms * 1e-3), ms
+
+
+@torch.no_grad()
+def describe_and_match_pairs(model, pairs, num_keypoints: int = 5000, seed: int = 0, streams: int = 4):
+    """BASELINE config 3 ("fragment pairs ... descriptors + 5000-keypoint L2 feature matching"): for every pair
+    ((x_i, image_i), (x_j, image_j)) extract descriptors of both fragments (independent fragments, `forward_many`), draw
+    `num_keypoints` random rows of each (scripts/evaluation_3dmatch.py:154-174 samples 5000 keypoints per fragment) and match
+    them by mutual nearest neighbour in descriptor space (evaluation_3dmatch.py:207-217).
+    Returns one dict per pair: keypoint rows of both fragments, nn21 (for each keypoint of j its match in i) and the mutual
+    subset (indices into fragment j's keypoints)."""
+    from .matching import nn_search
+    flat = [f for pair in pairs for f in pair]
+    outs = model.forward_many(flat, streams=streams)
+    g = torch.Generator().manual_seed(seed)
+    results = []
+    for p in range(len(pairs)):
+        Fi, Fj = outs[2 * p].F, outs[2 * p + 1].F
+        ki = torch.randperm(len(Fi), generator=g)[:num_keypoints].to(Fi.device)
+        kj = torch.randperm(len(Fj), generator=g)[:num_keypoints].to(Fj.device)
+        di, dj = Fi[ki], Fj[kj]
+        nn21 = nn_search(dj, di)
+        nn12 = nn_search(di, dj)
+        mutual = torch.nonzero(nn12[nn21.long()] == torch.arange(len(dj), device=dj.device, dtype=torch.int32)).flatten()
+        results.append({"kpts_i": ki, "kpts_j": kj, "nn21": nn21, "mutual": mutual})
+    return results

@@ -50,3 +50,26 @@ def test_mutual_nn_5000_keypoints_and_edge_cases():
     assert idx.cpu().tolist() == [0, 3, 6, 9]
     assert nn_search(torch.zeros((0, 32)).cuda(), torch.from_numpy(b).cuda()).numel() == 0
     assert nn_search(torch.from_numpy(b).cuda(), torch.zeros((0, 32)).cuda()).cpu().tolist() == [-1] * 12
+
+
+@pytest.mark.gpu
+def test_describe_and_match_pairs_on_a_fragment_and_its_permuted_copy():
+    """A fragment paired with a row-permuted copy of itself: every sampled keypoint that exists on both sides must match its twin
+    mutually (identical descriptors up to fp32 summation order)."""
+    import imfnet_b200.me as ME
+    from imfnet_b200 import load_model, synthetic
+    from imfnet_b200.pipeline import describe_and_match_pairs
+    model = load_model("ResUNetBN2C")(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3, config=None)
+    model.load_state_dict(synthetic.make_state_dict(0))
+    model = model.eval().cuda()
+    coords, _ = synthetic.make_fragment(4000, 0.05, seed=8)
+    perm = np.random.default_rng(1).permutation(len(coords))
+    image = synthetic.make_image(160, 120, seed=8).cuda()
+    a = (ME.SparseTensor(torch.ones((4000, 1)), coordinates=torch.from_numpy(coords), device="cuda"), image)
+    b = (ME.SparseTensor(torch.ones((4000, 1)), coordinates=torch.from_numpy(coords[perm].copy()), device="cuda"), image)
+    (r,) = describe_and_match_pairs(model, [(a, b)], num_keypoints=4000, seed=0)     # all rows are keypoints
+    ki, kj = r["kpts_i"].cpu().numpy(), r["kpts_j"].cpu().numpy()
+    nn21 = r["nn21"].cpu().numpy()
+    # keypoint t of b is voxel coords[perm[kj[t]]]; its match in a must be the same voxel: ki[nn21[t]] == perm[kj[t]]
+    assert (ki[nn21] == perm[kj]).mean() > 0.999
+    assert len(r["mutual"]) > 0.999 * 4000
