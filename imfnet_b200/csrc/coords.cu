@@ -10,6 +10,10 @@
 //
 // Layout: a hash table is `capacity` 16-byte slots {u64 key, i32 val, i32 pad}; key = packed (b,x,y,z),
 // val = row index in the coordinate set.  Coordinate sets are int32 [N,4] row-major.
+#include <mutex>
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 #include <stdarg.h>
 #include <atomic>
@@ -27,6 +31,20 @@ extern "C" const char* imf_last_error(void) { return g_err; }
 extern "C" int imf_version(void) { return 100; }
 
 static std::atomic<long long> g_launches{0};
+cudaError_t imf_set_max_smem_once(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& kd : done)
+    if (kd.first == kernel && kd.second == dev) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.emplace_back(kernel, dev);
+  return e;
+}
+
 void imf_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" long long imf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

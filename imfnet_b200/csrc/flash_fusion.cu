@@ -340,11 +340,7 @@ int imf_flash_attention(const void* qh2, int M_max, const int* m_dev, const void
   const int bps = (nblocks + nsplit - 1) / nsplit;
   float* Opart = reinterpret_cast<float*>(workspace);
   float* ml = Opart + (size_t)nsplit * M_max * kD;
-  static bool attr_done = false;
-  if (!attr_done) {
-    IMF_CHECK_CUDA(cudaFuncSetAttribute(k_flash_fusion, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem + 1024));
-    attr_done = true;
-  }
+  IMF_CHECK_CUDA(imf_set_max_smem_once(reinterpret_cast<const void*>(&k_flash_fusion), kSmem + 1024));
   dim3 grid((M_max + kTQ - 1) / kTQ, nsplit);
   k_flash_fusion<<<grid, kThreads, kSmem + 1024, stream>>>(tmQ, tmK, tmV, m_dev, M_max, L, bps, Opart, ml, err);
   IMF_CHECK_LAUNCH();

@@ -654,11 +654,7 @@ int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, 
               cudaStream_t stream) {
   using Cfg = G4Cfg<BN, KC>;
   const size_t smem = (size_t)Cfg::RING_BYTES + (size_t)kNW * Cfg::W_BYTES + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    IMF_CHECK_CUDA(cudaFuncSetAttribute(k_sparse_conv_g4<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  IMF_CHECK_CUDA(imf_set_max_smem_once(reinterpret_cast<const void*>(&k_sparse_conv_g4<BN, KC>), (int)smem));
   const int ntn = Cout / BN;
   const int nchunks = Cin / KC;
   // one CTA per SM and output-channel tile, whatever n_max: the row partition (hence the fp32 summation order of the split mode)
