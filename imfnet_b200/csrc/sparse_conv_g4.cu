@@ -33,9 +33,9 @@ namespace {
 
 constexpr int kBM = 128;
 constexpr int kImg = kBM * 128;          // one 128-row x 128-byte operand image (16 KB)
-constexpr int kNPW = 8;                  // TMA producer warps (they also run the epilogue)
-constexpr int kNMW = 4;                  // MMA issuing warps
-constexpr int kThreads = (kNPW + kNMW + 1) * 32;   // + the weight-slab loader warp
+constexpr int kNPW = 8;                  // gather producer warps that also run the epilogue (warps 0-7)
+constexpr int kNMW = 4;                  // MMA issuing warps (8-11)
+constexpr int kNXW = 2;                  // extra gather producer warps (13-14) for the 5-slot configurations
 constexpr int kNW = 2;                   // weight-slab ring depth
 constexpr int kMaxSubAll = 8;            // 512 TMEM columns / (2 * 32)
 constexpr int kSMs = 148;
@@ -48,6 +48,10 @@ struct G4Cfg {
   static constexpr int BUDGET = 200 * 1024;
   static constexpr int NA_FIT = (BUDGET - kNW * W_BYTES) / A_BYTES;
   static constexpr int NA = NA_FIT > 8 ? 8 : NA_FIT;
+  static constexpr int HALVES = NA <= 5 ? 2 : 1;         // producer warps per ring slot (each copies 128 / HALVES rows of a stage)
+  static constexpr int NPROD = NA * HALVES;
+  static_assert(NPROD <= kNPW + kNXW, "not enough producer warps");
+  static constexpr int THREADS = (kNPW + kNMW + 1 + (NPROD > kNPW ? NPROD - kNPW : 0)) * 32;   // warp 12 = weight-slab loader
   static constexpr int ACC_COLS = 2 * BN;               // D1 = hi.Whi + lo.Whi, D2 = hi.Wlo (summed in the epilogue)
   static constexpr int MAXSUB = 512 / ACC_COLS;
   static constexpr int OUT_BYTES = kBM * BN * 4;       // one staged output sub-tile (BN/32 images)
@@ -170,14 +174,14 @@ struct G4It {
 };
 
 template <int BN, int KC>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((G4Cfg<BN, KC>::THREADS), 1)
 k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ CUtensorMap tmY, const unsigned char* __restrict__ Wp,
                  const int* __restrict__ nbr_t, int ld_n, const unsigned* __restrict__ tile_mask, const int* __restrict__ n_ptr, int n_max,
                  int K3, int nchunks, const float* __restrict__ scale, const float* __restrict__ shift, const __half* __restrict__ R, int ldr,
                  int kc_r, int relu, int kc_out, float* __restrict__ P, int cout_total, const int* __restrict__ out_row, __half* __restrict__ Yp,
                  int ldy, int* err, long long* __restrict__ trace, int dbg, int sps) {
   using Cfg = G4Cfg<BN, KC>;
-  constexpr int NA = Cfg::NA;
+  constexpr int NA = Cfg::NA, HALVES = Cfg::HALVES, NPROD = Cfg::NPROD, HROWS = kBM / HALVES;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* a_ring = smem;                          // NA x A_BYTES   (re-used as the epilogue staging double buffer)
@@ -191,12 +195,13 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   __shared__ int ring_s[5];
   __shared__ int turn_s;                                 // next stage (running count) whose MMAs may be issued
   __shared__ float sc_s[BN], sh_s[BN];
-  __shared__ __align__(16) int idx_s[NA][2][kBM];      // neighbour indices of each producer warp's current / next stage
+  __shared__ __align__(16) int idx_s[NPROD][2][HROWS]; // neighbour indices of each producer warp's current / next stage
 
   int n = n_max;
   if (n_ptr) { const int v = *n_ptr; n = v < n_max ? v : n_max; }
   if (n <= 0) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler too (role branches, uniform registers)
   const int gx = gridDim.x, bx = blockIdx.x, zt = blockIdx.z, ntn = gridDim.z;
   const int nst_max = K3 * nchunks;
   const G4Part part = g4_partition(n, gx, nst_max, P != nullptr, sps);
@@ -228,7 +233,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
     while ((int)tmem_cols < nsub_pass * Cfg::ACC_COLS) tmem_cols <<= 1;
   }
   if (tid == 0) {
-    for (int s = 0; s < NA; ++s) { tc::mbar_init(&full_a[s], 32); tc::mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < NA; ++s) { tc::mbar_init(&full_a[s], 32 * HALVES); tc::mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < kNW; ++s) { tc::mbar_init(&full_w[s], 1); tc::mbar_init(&empty_w[s], kNMW); }
     tc::mbar_init(&acc_bar, kNMW);
     turn_s = 0;
@@ -309,41 +314,47 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       it.j = __ffs(it.rem) - 1;
     };
 
-    if (warp < kNPW) {
-      // =========================== gather producers (cp.async), one warp per stage ===========================
+    // producer index: warps 0-7 -> 0-7, warps 13-14 -> 8-9; producer pw copies rows [half * HROWS, +HROWS) of every stage of slot pslot
+    const int pw = warp < kNPW ? warp : warp - (kNMW + 1);
+    const bool is_prod = (warp < kNPW || warp > kNPW + kNMW) && pw < NPROD;
+    if (is_prod) {
+      // =========================== gather producers (cp.async) ===========================
       // Measured on B200 (tools/tma_rate.py, profiles/r01): TMA tile::gather4 of 128-byte rows tops out at ~44 B/cycle/SM with
       // 8 issuing warps (an instruction holds its warp ~2700 cycles) and drops to ~31 B/cycle inside this kernel; absent rows
       // cost it as much as present ones (more when zero-filled out of range).  The LSU path (LDGSTS, 16 B per lane) issues
       // 64 B/cycle/SM and its zero fill of an absent row moves no data, so the row gather uses cp.async; completion is still
       // tracked by the stage's mbarrier (cp.async.mbarrier.arrive.noinc), i.e. no thread ever waits for its own row copies.
-      // A warp owns one ring slot, i.e. every NA-th stage, and copies all of it (its ~900 cycles of per-stage barrier / walk
-      // latency then overlap the other warps' copies).  The 128 neighbour indices of its NEXT stage are prefetched into shared memory (one
-      // 16-byte cp.async per lane) while it copies the current one.
+      // A ring slot (= every NA-th stage) belongs to HALVES warps, each copying 128 / HALVES rows of the stage: their per-stage
+      // barrier / walk / issue time (~1000 cycles for 64 instructions per lane) overlaps the other slots' copies, and with two
+      // warps per slot the slot's turnaround fits the MMA rate.  The neighbour indices of a warp's NEXT stage are prefetched into
+      // shared memory (one 16-byte cp.async per lane) while it copies the current one.
       // KC = 64: 16 lanes per row (hi 8 x 16 B | lo 8 x 16 B): instruction i covers rows 4*(2*(i/4) + lane/16) + i%4;
       // KC = 32:  8 lanes per row: instruction i covers rows 4*(4*(i/4) + lane/8) + i%4  -> whole rows per instruction.
       constexpr int LPR = (KC == 64) ? 16 : 8;           // lanes per row
       constexpr int RPI = 32 / LPR;                      // rows per instruction
-      constexpr int NINS = kBM / RPI;                    // copy instructions per stage and lane
+      constexpr int NINS = HROWS / RPI;                  // copy instructions per stage and lane
+      const int pslot = pw % NA, half = pw / NA;
       const int cl = lane & (LPR - 1), hw = lane / LPR;
       const int part = (KC == 64) ? (cl >> 3) : 0, c16 = cl & 7;
       const uint32_t ring_base = tc::smem_u32(a_ring) + part * kImg;
       const char* xthr = reinterpret_cast<const char*>(X) + part * 128 + c16 * 16;
       const unsigned ldx_bytes = (unsigned)ldx * 2u;
-      int* my_idx = &idx_s[warp][0][0];
-      auto prefetch = [&](const G4It& it, int slot) {    // lane l: neighbour rows of output rows 4l..4l+3 of the stage's sub-tile
-        const int row = prow + it.j * kBM + 4 * lane;
-        int* dst = my_idx + slot * kBM + 4 * lane;
-        if (row < row_end) g4_cp_async16_row(tc::smem_u32(dst), nbr_t + (size_t)it.k * ld_n + row, 0);
-        else *reinterpret_cast<int4*>(dst) = make_int4(-1, -1, -1, -1);
+      int* my_idx = &idx_s[pw][0][0];
+      auto prefetch = [&](const G4It& it, int slot) {    // lane l: neighbour rows of output rows 4l..4l+3 of this warp's half
+        if (lane < HROWS / 4) {
+          const int row = prow + it.j * kBM + half * HROWS + 4 * lane;
+          int* dst = my_idx + slot * HROWS + 4 * lane;
+          if (row < row_end) g4_cp_async16_row(tc::smem_u32(dst), nbr_t + (size_t)it.k * ld_n + row, 0);
+          else *reinterpret_cast<int4*>(dst) = make_int4(-1, -1, -1, -1);
+        }
       };
-      // Stage s lives in ring slot s % NA and belongs to warp s % NA: one producer per slot, so a warp can never run two phases
-      // ahead of the slot's consumer (which the parity wait could not tell apart from "free").  Warps NA..7 only run the epilogue.
+      // Stage s lives in ring slot s % NA: the producers of a slot take part in every use of it, so none can run two phases
+      // ahead of the slot's consumer (which the parity wait could not tell apart from "free").
       G4It it = first();
-      const int first_i = warp >= a_slot ? warp - a_slot : warp - a_slot + NA;     // (the ring may start a pass at any slot)
+      const int first_i = pslot >= a_slot ? pslot - a_slot : pslot - a_slot + NA;  // (the ring may start a pass at any slot)
       for (int i = 0; i < first_i && it.w < w_end; ++i) advance(it);               // first stage of this warp
-      if (warp >= NA) it.w = w_end;
       int my_ac = ac + first_i;
-      uint32_t my_phase = warp >= a_slot ? a_phase : a_phase ^ 1u;                 // phase of slot `warp` at its next use
+      uint32_t my_phase = pslot >= a_slot ? a_phase : a_phase ^ 1u;                // phase of slot `pslot` at its next use
       int slot = 0;
       if (it.w < w_end) prefetch(it, 0);
       g4_cp_async_commit();
@@ -353,26 +364,27 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
         for (int i = 0; i < NA && nxt.w < w_end; ++i) advance(nxt);
         if (nxt.w < w_end) prefetch(nxt, slot ^ 1);
         g4_cp_async_commit();
-        if (trace && lane == 0 && my_ac < 36) trace[16 + 4 * my_ac] = clock64();
-        tc::mbar_wait(&empty_a[warp], my_phase ^ 1u, err, 2);
-        if (trace && lane == 0 && my_ac < 36) trace[17 + 4 * my_ac] = clock64();
+        if (trace && lane == 0 && half == 0 && my_ac < 36) trace[16 + 4 * my_ac] = clock64();
+        tc::mbar_wait(&empty_a[pslot], my_phase ^ 1u, err, 2);
+        if (trace && lane == 0 && half == 0 && my_ac < 36) trace[17 + 4 * my_ac] = clock64();
         g4_cp_async_wait<2>();             // pending at most: the previous stage's rows and the prefetch just issued
         __syncwarp();
-        const uint32_t stg = ring_base + warp * Cfg::A_BYTES;
+        const uint32_t stg = ring_base + pslot * Cfg::A_BYTES;
         const char* xc = xthr + it.chunk * (4 * KC);
-        const int4* idx4p = reinterpret_cast<const int4*>(my_idx + slot * kBM);
+        const int4* idx4p = reinterpret_cast<const int4*>(my_idx + slot * HROWS);
         if (!(dbg & 2)) {
 #pragma unroll 4
           for (int i4 = 0; i4 < NINS / 4; ++i4) {
-            const int m = RPI * i4 + hw;                                  // row group of this lane for these 4 instructions
+            const int m = RPI * i4 + hw;                                  // row group (of this warp's half) for these 4 instructions
             const int4 r = idx4p[m];
             const int r4[4] = {r.x, r.y, r.z, r.w};
+            const int srow = half * HROWS + 4 * m;
 #pragma unroll
             for (int i = 0; i < 4; ++i)      // absent neighbour: the (valid) address of row 0 is passed but ignored (zero fill)
-              g4_cp_async16_row(stg + tc::sw128_offset(4 * m + i, c16), xc + (unsigned long long)((unsigned)max(r4[i], 0)) * ldx_bytes, r4[i]);
+              g4_cp_async16_row(stg + tc::sw128_offset(srow + i, c16), xc + (unsigned long long)((unsigned)max(r4[i], 0)) * ldx_bytes, r4[i]);
           }
         }
-        g4_cp_async_arrive_noinc(&full_a[warp]);                          // fires when this thread's copies have landed
+        g4_cp_async_arrive_noinc(&full_a[pslot]);                         // fires when this thread's copies have landed
         g4_cp_async_commit();
         my_ac += NA;
         my_phase ^= 1u;
@@ -395,7 +407,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
         if (++w_slot == kNW) { w_slot = 0; w_phase ^= 1u; }
         if (++chunk == nchunks) { chunk = 0; ++kk; }
       }
-    } else if (warp < kNPW + kNMW) {
+    } else if (warp >= kNPW && warp < kNPW + kNMW) {
       // =========================== MMA issuers ===========================
       // An issuing thread is held ~85-95 cycles per tcgen05.mma (any N <= 128, measured) and pays ~300 cycles of barrier / walk
       // overhead per stage, so the stages are spread over kNMW warps by sub-tile (each accumulator belongs to one warp, which
@@ -405,10 +417,13 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       //   D[:, 0:BN]  += a_lo . Whi^T            the epilogue adds the two halves
       constexpr uint32_t idesc2 = g4_idesc_f16(kBM, 2 * BN), idesc1 = g4_idesc_f16(kBM, BN);
       const int mw = warp - kNPW;
-      // Stage s (ring slot s % NA) is issued by MMA warp (s % NA) % kNMW: one consumer per slot, which the parity waits need
-      // (a consumer that could skip stages might see a slot two phases off).  An accumulator is therefore fed by several
-      // threads; the tensor pipe executes MMAs one after the other, so only the "first MMA overwrites" flag needs care: the
-      // accumulators are zeroed here (each MMA warp owns one TMEM lane quadrant) and every MMA accumulates.
+      // Stage s is issued by MMA warp s % kNMW, so consecutive stages never fall to the same warp (its ~600 cycles of per-stage
+      // bookkeeping would sit on the issue chain; measured with the slot-based assignment every NA-th stage).  The parity wait
+      // on full_a stays unambiguous because of the turn order below: a warp reaches stage s only after it issued stage s - 4,
+      // i.e. after every earlier stage -- including the previous use of the same ring slot -- was consumed.
+      // An accumulator is fed by several threads; the tensor pipe executes MMAs one after the other, so only the "first MMA
+      // overwrites" flag needs care: the accumulators are zeroed here (each MMA warp owns one TMEM lane quadrant) and every
+      // MMA accumulates.
       {
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         for (int col = 0; col < nsub * Cfg::ACC_COLS; col += 16) g4_tmem_zero16(tmem_d + lane_base + (uint32_t)col);
@@ -421,51 +436,54 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       int last_w = -1, ws = 0;
       while (cur.w < w_end) {
         if (cur.w != last_w) {
-          if (last_w >= 0 && lane == 0) tc::mma_commit(&empty_w[ws]);      // this warp's MMAs on the previous slab
+          if (last_w >= 0 && tc::elect_one()) tc::mma_commit(&empty_w[ws]);      // this warp's MMAs on the previous slab (same elected thread)
           ws = w_slot;
           tc::mbar_wait(&full_w[ws], w_phase, err, 3);                     // every MMA warp waits: keeps them inside the slab ring
           if (++w_slot == kNW) { w_slot = 0; w_phase ^= 1u; }
           last_w = cur.w;
         }
-        if ((a_slot & (kNMW - 1)) == mw) {
+        const int owner = (dbg & 8) ? 0 : (dbg & 16) ? (ac & (kNMW - 1)) : (cur.j & (kNMW - 1));
+        if (owner == mw) {
+          // stages are ISSUED in walk order whichever warp owns them (a turn counter in shared memory).  Waiting for the turn
+          // BEFORE the slot's barrier also keeps the parity wait unambiguous: every earlier stage, hence the previous use of
+          // this ring slot, has been consumed by then.
+          while (*reinterpret_cast<volatile int*>(&turn_s) != ac) {}
           tc::mbar_wait(&full_a[a_slot], a_phase, err, 4);
-          if (lane == 0) {
-            // stages are ISSUED in walk order whichever warp owns them (a turn counter in shared memory), so every accumulator
-            // receives its products in the same order on every run: bit-reproducible results
-            while (*reinterpret_cast<volatile int*>(&turn_s) != ac) {}
-            if (trace && ac < 36) trace[18 + 4 * ac] = clock64();
-            const uint32_t a0 = tc::smem_u32(a_ring + a_slot * Cfg::A_BYTES);
-            const uint32_t w0 = tc::smem_u32(w_ring + ws * Cfg::W_BYTES);
-            const uint32_t d = tmem_d + (uint32_t)(cur.j * Cfg::ACC_COLS);
+          // operand addresses as warp-uniform values (shuffles from lane 0): the compiler then keeps the descriptors in uniform
+          // registers and emits bare UTCHMMA instructions instead of an elect / R2UR / branch loop around each of them
+          const uint32_t a0 = __shfl_sync(0xffffffffu, tc::smem_u32(a_ring + a_slot * Cfg::A_BYTES), 0);
+          const uint32_t w0 = __shfl_sync(0xffffffffu, tc::smem_u32(w_ring + ws * Cfg::W_BYTES), 0);
+          const uint32_t d = __shfl_sync(0xffffffffu, tmem_d + (uint32_t)(cur.j * Cfg::ACC_COLS), 0);
+          const uint64_t da = tc::smem_desc_sw128(a0), dw = tc::smem_desc_sw128(w0);
+          if (trace && lane == 0 && ac < 36) trace[18 + 4 * ac] = clock64();
+          if (tc::elect_one()) {
             if (dbg & 4) {
             } else if (KC == 64) {
-              const uint32_t a_hi = a0, a_lo = a0 + kImg;
+              // (descriptor start-address field = byte address >> 4: the hi image is at +0, the lo image at +kImg)
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t o = ks * 32;
-                g4_mma_f16(d, tc::smem_desc_sw128(a_hi + o), tc::smem_desc_sw128(w0 + o), idesc2, 1u);
-                g4_mma_f16(d, tc::smem_desc_sw128(a_lo + o), tc::smem_desc_sw128(w0 + o), idesc1, 1u);
+                g4_mma_f16(d, da + (uint64_t)(ks * 2), dw + (uint64_t)(ks * 2), idesc2, 1u);
+                g4_mma_f16(d, da + (uint64_t)(kImg / 16 + ks * 2), dw + (uint64_t)(ks * 2), idesc1, 1u);
               }
             } else {
               // A row = [hi32 | lo32]; slab rows [0,BN) = [Whi | Whi], rows [BN,2BN) = [Wlo | 0]
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t o = ks * 32;
-                g4_mma_f16(d, tc::smem_desc_sw128(a0 + o), tc::smem_desc_sw128(w0 + o), idesc2, 1u);               // hi . [Whi | Wlo]
-                g4_mma_f16(d, tc::smem_desc_sw128(a0 + 64 + o), tc::smem_desc_sw128(w0 + 64 + o), idesc1, 1u);     // lo . Whi
+                g4_mma_f16(d, da + (uint64_t)(ks * 2), dw + (uint64_t)(ks * 2), idesc2, 1u);                  // hi . [Whi | Wlo]
+                g4_mma_f16(d, da + (uint64_t)(4 + ks * 2), dw + (uint64_t)(4 + ks * 2), idesc1, 1u);          // lo . Whi
               }
             }
             *reinterpret_cast<volatile int*>(&turn_s) = ac + 1;
             tc::mma_commit(&empty_a[a_slot]);
-            if (trace && ac < 36) trace[19 + 4 * ac] = clock64();
           }
+          if (trace && lane == 0 && ac < 36) trace[19 + 4 * ac] = clock64();
           __syncwarp();
         }
         ++ac;
         if (++a_slot == NA) { a_slot = 0; a_phase ^= 1u; }
         advance(cur);
       }
-      if (lane == 0) {
+      if (tc::elect_one()) {                 // the thread that issued this warp's MMAs (elect.sync is deterministic per mask)
         if (last_w >= 0) tc::mma_commit(&empty_w[ws]);
         tc::mma_commit(&acc_bar);
         if (mw == 0) {                     // ring positions after this pass, for everybody (the producers skip through theirs)
@@ -490,89 +508,104 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
         const int grow = prow + j * kBM + r_in;
         unsigned char* stage = a_ring + (j & 1) * Cfg::OUT_BYTES;
         if (!partial && !out_row) {
-          if (j >= 2 && tid == 0) tma::store_wait_read<1>();       // the stores that read this buffer two sub-tiles ago
+          if (j >= 2 && lane == 0) tma::store_wait_read<1>();      // this thread's stores that read this buffer two sub-tiles ago
           named_barrier(1, 256);
         }
+        // NB 16-column blocks per round: the residual rows (global loads) and all TMEM loads of a round are in flight together
+        constexpr int NB = CW >= 32 ? 2 : 1;
+        const bool has_r = !partial && (R != nullptr) && grow < n;
 #pragma unroll 1
-        for (int cb = 0; cb < CW; cb += 16) {
-          const int cl = h * CW + cb;                                // column inside this CTA's BN-wide tile
-          float a[16];
-          if ((started >> j) & 1u) {
-            float a2[16];
-            tc::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * Cfg::ACC_COLS + cl), a);
-            tc::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * Cfg::ACC_COLS + BN + cl), a2);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) a[i] += a2[i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) a[i] = 0.f;
-          }
-          const int c = zt * BN + cl;                                // absolute output channel of a[0]
-          if (partial) {
-            if (grow < n) {
-              float4* dst = reinterpret_cast<float4*>(P + ((size_t)split * n + grow) * cout_total + c);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dst[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
-            }
-            continue;
-          }
-          float r16[16];
-          const bool has_r = (R != nullptr) && grow < n;
+        for (int cb = 0; cb < CW; cb += 16 * NB) {
+          float r16[NB][16];
           if (has_r) {
-            const __half* rp = R + (size_t)grow * ldr + (c / kc_r) * 2 * kc_r + (c % kc_r);
-            g4_load16_h2(rp, rp + kc_r, r16);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+              const int c = zt * BN + h * CW + cb + 16 * b;
+              const __half* rp = R + (size_t)grow * ldr + (c / kc_r) * 2 * kc_r + (c % kc_r);
+              g4_load16_h2(rp, rp + kc_r, r16[b]);
+            }
+          }
+          uint32_t t1[NB][16], t2[NB][16];
+          if ((started >> j) & 1u) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+              const uint32_t col = (uint32_t)(j * Cfg::ACC_COLS + h * CW + cb + 16 * b);
+              tc::tmem_ld16_issue(tmem_d + ((uint32_t)(q * 32) << 16) + col, t1[b]);
+              tc::tmem_ld16_issue(tmem_d + ((uint32_t)(q * 32) << 16) + col + BN, t2[b]);
+            }
+            tc::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) t1[b][i] = t2[b][i] = 0u;
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = fmaf(a[i], sc_s[cl + i], sh_s[cl + i]);
-            if (has_r) x += r16[i];
-            if (relu) x = fmaxf(x, 0.f);
-            a[i] = x;
-          }
-          Half8 hi[2], lo[2];
-          const bool b = g4_split16(a, hi, lo);
-          big |= b && (grow < n);
-          if (out_row) {        // parity-grouped transposed convolution: table row grow describes output row out_row[grow]
-            if (grow < n && grow < row_end) {      // rows past row_end belong to the next CTA's range
-              __half* yp = Yp + (size_t)__ldg(out_row + grow) * ldy + (c / kc_out) * 2 * kc_out + (c % kc_out);
-              reinterpret_cast<Half8*>(yp)[0] = hi[0];
-              reinterpret_cast<Half8*>(yp)[1] = hi[1];
-              reinterpret_cast<Half8*>(yp + kc_out)[0] = lo[0];
-              reinterpret_cast<Half8*>(yp + kc_out)[1] = lo[1];
+          for (int b = 0; b < NB; ++b) {
+            const int cl = h * CW + cb + 16 * b;                       // column inside this CTA's BN-wide tile
+            const int c = zt * BN + cl;                                // absolute output channel of a[0]
+            float a[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(t1[b][i]) + __uint_as_float(t2[b][i]);
+            if (partial) {
+              if (grow < n) {
+                float4* dst = reinterpret_cast<float4*>(P + ((size_t)split * n + grow) * cout_total + c);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+              }
+              continue;
             }
-            continue;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float x = fmaf(a[i], sc_s[cl + i], sh_s[cl + i]);
+              if (has_r) x += r16[b][i];
+              if (relu) x = fmaxf(x, 0.f);
+              a[i] = x;
+            }
+            Half8 hi[2], lo[2];
+            const bool bg = g4_split16(a, hi, lo);
+            big |= bg && (grow < n);
+            if (out_row) {        // parity-grouped transposed convolution: table row grow describes output row out_row[grow]
+              if (grow < n && grow < row_end) {      // rows past row_end belong to the next CTA's range
+                __half* yp = Yp + (size_t)__ldg(out_row + grow) * ldy + (c / kc_out) * 2 * kc_out + (c % kc_out);
+                reinterpret_cast<Half8*>(yp)[0] = hi[0];
+                reinterpret_cast<Half8*>(yp)[1] = hi[1];
+                reinterpret_cast<Half8*>(yp + kc_out)[0] = lo[0];
+                reinterpret_cast<Half8*>(yp + kc_out)[1] = lo[1];
+              }
+              continue;
+            }
+            // staged layout: image = 64 halves of the h2 row; kc_out = 64: images (hi, lo) per 64 channels; 32: one image [hi32|lo32]
+            int img_hi, img_lo, ch_hi, ch_lo;
+            if (kc_out == 64) {
+              img_hi = (cl >> 6) * 2; img_lo = img_hi + 1; ch_hi = (cl & 63) >> 3; ch_lo = ch_hi;
+            } else {
+              img_hi = cl >> 5; img_lo = img_hi; ch_hi = (cl & 31) >> 3; ch_lo = 4 + ch_hi;
+            }
+            unsigned char* ph = stage + img_hi * kImg;
+            unsigned char* pl = stage + img_lo * kImg;
+            *reinterpret_cast<Half8*>(ph + tc::sw128_offset(r_in, ch_hi)) = hi[0];
+            *reinterpret_cast<Half8*>(ph + tc::sw128_offset(r_in, ch_hi + 1)) = hi[1];
+            *reinterpret_cast<Half8*>(pl + tc::sw128_offset(r_in, ch_lo)) = lo[0];
+            *reinterpret_cast<Half8*>(pl + tc::sw128_offset(r_in, ch_lo + 1)) = lo[1];
           }
-          // staged layout: image = 64 halves of the h2 row; kc_out = 64: images (hi, lo) per 64 channels; 32: one image [hi32|lo32]
-          int img_hi, img_lo, ch_hi, ch_lo;
-          if (kc_out == 64) {
-            img_hi = (cl >> 6) * 2; img_lo = img_hi + 1; ch_hi = (cl & 63) >> 3; ch_lo = ch_hi;
-          } else {
-            img_hi = cl >> 5; img_lo = img_hi; ch_hi = (cl & 31) >> 3; ch_lo = 4 + ch_hi;
-          }
-          unsigned char* ph = stage + img_hi * kImg;
-          unsigned char* pl = stage + img_lo * kImg;
-          *reinterpret_cast<Half8*>(ph + tc::sw128_offset(r_in, ch_hi)) = hi[0];
-          *reinterpret_cast<Half8*>(ph + tc::sw128_offset(r_in, ch_hi + 1)) = hi[1];
-          *reinterpret_cast<Half8*>(pl + tc::sw128_offset(r_in, ch_lo)) = lo[0];
-          *reinterpret_cast<Half8*>(pl + tc::sw128_offset(r_in, ch_lo + 1)) = lo[1];
         }
         if (!partial && !out_row) {
           tc::fence_proxy_async();
           named_barrier(1, 256);
-          if (tid == 0) {
-            const int r0 = prow + j * kBM;
+          // warp (q, h) stores the 32-row box q of images h, h + 2, ...: eight issuing threads instead of one
+          const int r0 = prow + j * kBM + q * 32;
+          if (lane == 0) {
+            if (r0 < row_end) {
 #pragma unroll 1
-            for (int rb = 0; rb < 4; ++rb) {
-              if (r0 + rb * 32 >= row_end) break;
-#pragma unroll 1
-              for (int img = 0; img < BN / 32; ++img)
-                tma::store_2d(&tmY, tc::smem_u32(stage + img * kImg + rb * 4096), zt * BN * 2 + img * 64, r0 + rb * 32);
+              for (int img = h; img < BN / 32; img += 2)
+                tma::store_2d(&tmY, tc::smem_u32(stage + img * kImg + q * 4096), zt * BN * 2 + img * 64, r0);
             }
-            tma::store_commit();
+            tma::store_commit();      // one (possibly empty) group per sub-tile: keeps the wait_read<1> arithmetic exact
           }
         }
       }
-      if (!partial && !out_row && tid == 0) tma::store_wait_read<0>();
+      if (!partial && !out_row && lane == 0) tma::store_wait_read<0>();
       if (big && err) atomicOr(err, 0x10000);
       if (tid == 0) G4_TRACE(5);
     }
@@ -664,7 +697,7 @@ int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, 
   float* P = nullptr;
   if (ws != nullptr && ws_bytes >= (size_t)kSMs * kBM * Cout * sizeof(float)) P = reinterpret_cast<float*>(ws);
   dim3 grid(gx, 1, ntn);
-  k_sparse_conv_g4<BN, KC><<<grid, kThreads, smem, stream>>>(X, ldx, tmY, reinterpret_cast<const unsigned char*>(Wp), nbr_t, ld_n, tile_mask,
+  k_sparse_conv_g4<BN, KC><<<grid, Cfg::THREADS, smem, stream>>>(X, ldx, tmY, reinterpret_cast<const unsigned char*>(Wp), nbr_t, ld_n, tile_mask,
                                                             n_ptr, n_max, K3, nchunks, scale, shift, R, ldr, kc_r, relu, kc_out, P, Cout,
                                                             out_row, Y, ldy, err, g_g4_trace, g_g4_dbg, g_g4_sps);
   IMF_CHECK_LAUNCH();
