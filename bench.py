@@ -266,6 +266,21 @@ def run_ours(args, rank, world, local_rank):
             if i >= 3:
                 lat.append(e0.elapsed_time(e1))
         latency_ms = float(np.median(lat))
+        # the same with the model's low-latency setting (small levels split over more CTAs; plans are rebuilt for it)
+        model.low_latency = True
+        lat = []
+        for i in range(13):
+            c, f, im = dev_frags[i % N_FRAGMENTS]
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model(ME.SparseTensor(f, coordinates=c), im)
+            e1.record()
+            e1.synchronize()
+            if i >= 3:
+                lat.append(e0.elapsed_time(e1))
+        latency_ll_ms = float(np.median(lat))
+        model.low_latency = False
 
     # per-rank timing records: the one collective of this path
     from imfnet_b200.pipeline import aggregate_throughput, gather_records
@@ -300,6 +315,8 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {target}-voxel synthetic 3DMatch fragment + {W}x{H} image, ResUNetBN2C 32-D descriptors",
                    "fragments_per_step": K, "streams": K, "single_fragment_latency_ms": latency_ms,
+                   "single_fragment_latency_ms_low_latency_setting": latency_ll_ms,
+                   "small_level_splits": "off (model.low_latency=False: throughput setting, used for value and e2e)",
                    "distinct_fragments_per_rank": N_FRAGMENTS,
                    "l2": "flushed between steps (256 MiB write, outside the per-step CUDA events)",
                    "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",

@@ -25,6 +25,8 @@
 // also owns the TMEM allocation); warp 12 = weight-slab loader (bulk TMA copies).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tma.cuh"
@@ -116,10 +118,12 @@ __host__ __device__ inline G4Part g4_partition(int n, int gx, int nst_max, bool 
   if (!p.row_mode && have_ws && p.T > 0) {
     // as many splits as free SMs allow, but not below `stages_per_split` stages per CTA: a split costs a partial-tile round trip
     // through L2 and a share of the reduce kernel, which only pays when it shortens a long stage list
+    // (stages_per_split: low 16 bits = minimum stages per split CTA, high 16 bits = upper limit of S, 0 = 32)
+    const int sps = stages_per_split & 0xffff, cap = (stages_per_split >> 16) ? (stages_per_split >> 16) : 32;
     S = gx / p.T;
-    const int smax = (nst_max + stages_per_split - 1) / stages_per_split;
+    const int smax = (nst_max + sps - 1) / sps;
     if (S > smax) S = smax;
-    if (S > 32) S = 32;
+    if (S > cap) S = cap;
     if (S < 1) S = 1;
   }
   p.S = S;
@@ -679,6 +683,10 @@ long long* g_g4_trace = nullptr;
 int g_g4_dbg = 0;       // profiling hook: bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs (results meaningless)
 int g_g4_sps = 4;         // stages per split CTA at least (profiling hook can change it)
 int g_g4_grid = 0;        // profiling hook: overrides the number of CTAs per output-channel tile (0 = one per SM)
+int g4_split_param() {    // experiment knob: IMF_G4_MAX_SPLITS caps the split factor of the small levels (default 32)
+  static const int cap = [] { const char* e = getenv("IMF_G4_MAX_SPLITS"); const int v = e ? atoi(e) : 0; return v > 0 && v < 32 ? v : 0; }();
+  return g_g4_sps | (cap << 16);
+}
 
 template <int BN, int KC>
 int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, const int* nbr_t, int ld_n, const unsigned* tile_mask,
@@ -699,13 +707,13 @@ int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, 
   dim3 grid(gx, 1, ntn);
   k_sparse_conv_g4<BN, KC><<<grid, Cfg::THREADS, smem, stream>>>(X, ldx, tmY, reinterpret_cast<const unsigned char*>(Wp), nbr_t, ld_n, tile_mask,
                                                             n_ptr, n_max, K3, nchunks, scale, shift, R, ldr, kc_r, relu, kc_out, P, Cout,
-                                                            out_row, Y, ldy, err, g_g4_trace, g_g4_dbg, g_g4_sps);
+                                                            out_row, Y, ldy, err, g_g4_trace, g_g4_dbg, g4_split_param());
   IMF_CHECK_LAUNCH();
   if (P != nullptr) {      // split mode is possible for small n: the reduce kernel decides on the device (no-op otherwise)
     const int rows = n_max < gx * kBM ? n_max : gx * kBM;      // split mode only exists below gx tiles
     const long long total = (long long)rows * (Cout / 16);
     k_conv_g4_reduce<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, n_ptr, n_max, gx, nst_max, Cout, scale, shift, R, ldr, kc_r,
-                                                                         relu, Y, ldy, kc_out, err, out_row, g_g4_sps);
+                                                                         relu, Y, ldy, kc_out, err, out_row, g4_split_param());
     IMF_CHECK_LAUNCH();
   }
   return IMF_OK;

@@ -40,6 +40,11 @@ class FusedPlan:
         self._key = None
         self.debug = None      # set to a dict to capture intermediate activations (tests only)
         self.arena = Arena(self.device)
+        # small levels (fewer 128-row tiles than SMs): splitting a tile's offsets over several CTAs + a reduce launch shortens ONE
+        # fragment's latency (1.79 vs 2.05 ms at C2) but costs SM time (every split CTA pays the kernel's fixed cost), i.e.
+        # throughput when several fragments are in flight (43.6 -> 48.2 M voxels/s); off unless the model asks for low latency
+        self.split_small = bool(getattr(model, "low_latency", False))
+        model.img_encoder.low_latency = self.split_small
         self.pack()
 
     # -- weights -------------------------------------------------------------------------------
@@ -90,7 +95,7 @@ class FusedPlan:
         tab = CoordinateManager.table_t(...) (offset-major neighbour table, its row stride, tile masks)."""
         conv, packed, scale, shift, kci = self.conv[cname]
         nbr_t, ld_n, tile_mask = tab
-        split = n_out < 128 * 148                # fewer row tiles than SMs: the kernel may split a tile's offsets over several CTAs
+        split = self.split_small and n_out < 128 * 148      # fewer row tiles than SMs: the kernel may split a tile's offsets over several CTAs
         _lib.check(L.imf_sparse_conv_g4_fwd(X, ldx, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(), None, n_out,
                                             27, conv.in_channels, conv.out_channels, scale.data_ptr(), shift.data_ptr(), R, ldr, kc_r,
                                             1 if relu else 0, Y, ldy, n_out, kc_out, self.conv_ws.data_ptr() if split else None,
@@ -307,7 +312,7 @@ class GraphPlan:
         self.side = torch.cuda.Stream(device=dev)
         from .model.Img_Encoder import ImagePlan
         with torch.cuda.device(dev):
-            self.image_plan = ImagePlan(m.img_encoder.backbone, self.H, self.W)     # private buffers: plans run concurrently
+            self.image_plan = ImagePlan(m.img_encoder.backbone, self.H, self.W, fused.split_small)     # private buffers: plans run concurrently
         self.n_tok = self.image_plan.P2                     # image tokens: conv arithmetic, not H/8 * W/8, for odd sizes
         af = m.attention_fusion
         self.att_ws_bytes = int(L.imf_attention_workspace_bytes(self.cap8, self.n_tok, af.latent_dim, af.inner))
@@ -327,7 +332,7 @@ class GraphPlan:
         nbr_t, ld_n, tile_mask = self.nbr[key]
         # a stride-1 level of this bucket always has >= 128 * 148 rows when the bucket is large enough: row mode is certain, so no
         # split workspace (and no reduce launch) is needed there
-        split = not (t_out == 1 and self.rows - self.ROW_SLACK >= 128 * 148)
+        split = self.f.split_small and not (t_out == 1 and self.rows - self.ROW_SLACK >= 128 * 148)
         out_row = self.perm[t_out].data_ptr() if key[2] else None          # transposed: the table is in parity-grouped row order
         _lib.check(L.imf_sparse_conv_g4_fwd_perm(X, ldx, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(),
                                                  self._n(t_out), self.rows, 27, conv.in_channels, conv.out_channels, scale.data_ptr(),

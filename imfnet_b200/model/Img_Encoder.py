@@ -49,8 +49,9 @@ class ImagePlan:
 
     STEM_K = 160      # 7*7*3 = 147 im2col columns padded to a multiple of 32
 
-    def __init__(self, backbone: resnet.ResNet, H: int, W: int):
+    def __init__(self, backbone: resnet.ResNet, H: int, W: int, split_small: bool = False):
         L = _lib.lib()
+        self.split_small = split_small        # see FusedPlan.split_small (engine.py)
         p = next(backbone.parameters())
         _lib.require_cuda(p, "image-encoder weights")
         dev = self.device = p.device
@@ -103,10 +104,11 @@ class ImagePlan:
 
     def _conv(self, L, c: _Conv, X, tab, n_out, R, relu, Y, s):
         nbr_t, ld_n, mask = tab
+        split = self.split_small and n_out < 128 * 148
         _lib.check(L.imf_sparse_conv_g4_fwd(X.data_ptr(), 2 * c.cin, c.kc_in, c.packed.data_ptr(), nbr_t.data_ptr(), ld_n, mask.data_ptr(),
                                             None, n_out, c.K, c.cin, c.cout, c.scale.data_ptr(), c.shift.data_ptr(), _lib.ptr(R),
                                             0 if R is None else 2 * c.cout, 64, 1 if relu else 0, Y.data_ptr(), 2 * c.cout, n_out, 64,
-                                            self.ws.data_ptr() if n_out < 128 * 148 else None, self.ws_bytes if n_out < 128 * 148 else 0,
+                                            self.ws.data_ptr() if split else None, self.ws_bytes if split else 0,
                                             self.err.data_ptr(), s))
 
     def enqueue(self, image: torch.Tensor) -> torch.Tensor:
@@ -141,6 +143,7 @@ class ImageEncoder(nn.Module):
     def __init__(self):
         super().__init__()
         self.backbone = resnet.resnet34(in_channels=3, pretrained=False, progress=False)
+        self.low_latency = False              # set by the owning model's plan (ResUNet2.low_latency)
         self._plans = {}
 
     def _apply(self, fn, *a, **k):
@@ -156,11 +159,12 @@ class ImageEncoder(nn.Module):
 
     def plan(self, H: int, W: int) -> ImagePlan:
         key = self._weights_key()
+        key = key + (self.low_latency,)
         hit = self._plans.get((H, W))
         if hit is None or hit[0] != key:
             if self.training:
                 raise NotImplementedError("imfnet_b200 implements the eval-mode image encoder (BatchNorm running statistics)")
-            hit = self._plans[(H, W)] = (key, ImagePlan(self.backbone, H, W))
+            hit = self._plans[(H, W)] = (key, ImagePlan(self.backbone, H, W, self.low_latency))
         return hit[1]
 
     def tokens(self, image: torch.Tensor) -> torch.Tensor:

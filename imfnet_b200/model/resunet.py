@@ -77,9 +77,7 @@ class ResUNet2(ME.MinkowskiNetwork):
         if self.training:
             raise NotImplementedError("imfnet_b200 implements the eval-mode forward (BatchNorm running statistics); "
                                       "call model.eval() as util/misc.py:44-45 does")
-        if self._plan is None:
-            self._plan = FusedPlan(self)
-            self._graphs, self._cap8_scale = {}, {}
+        self._ensure_plan()
         if not isinstance(x, ME.SparseTensor):       # duck-typed foreign container (.F / .C), e.g. a real ME tensor
             x = ME.SparseTensor(x.F, coordinates=x.C)
         image = torch.as_tensor(image)
@@ -94,6 +92,15 @@ class ResUNet2(ME.MinkowskiNetwork):
     # one fragment per call (what util/misc.py:extract_features and scripts/generate_desc.py do): captured CUDA graph per
     # (row bucket, image size); larger batches and oversized stride-8 levels take the eager plan
     use_cuda_graph = os.environ.get("IMFNET_B200_GRAPH", "1") != "0"
+    # False (default): tuned for throughput with several fragments in flight (forward_many / forward_many_host); True: small levels
+    # split their work over more CTAs, which shortens a lone forward() by ~13 % and costs ~10 % throughput.  Both settings give the
+    # same descriptors up to fp32 summation order.  Read when the plans are built; changing it rebuilds them.
+    low_latency = os.environ.get("IMFNET_B200_LOW_LATENCY", "0") == "1"
+
+    def _ensure_plan(self):
+        if self._plan is None or self._plan.split_small != bool(self.low_latency):
+            self._plan = FusedPlan(self)
+            self._graphs, self._cap8_scale = {}, {}
     ROW_BUCKET = GraphPlan.ROW_SLACK
 
     @torch.no_grad()
@@ -103,9 +110,7 @@ class ResUNet2(ME.MinkowskiNetwork):
         pyramid, small deep levels, attention) overlap the others' work.  Results are identical to forward() one by one."""
         if self.training:
             raise NotImplementedError("imfnet_b200 implements the eval-mode forward")
-        if self._plan is None:
-            self._plan = FusedPlan(self)
-            self._graphs, self._cap8_scale = {}, {}
+        self._ensure_plan()
         plan = self._plan
         if plan._key != plan._weights_key():
             plan.pack()
@@ -169,9 +174,7 @@ class ResUNet2(ME.MinkowskiNetwork):
         scripts/generate_desc.py:118-123).  `out` may provide the destination tensors."""
         if self.training:
             raise NotImplementedError("imfnet_b200 implements the eval-mode forward")
-        if self._plan is None:
-            self._plan = FusedPlan(self)
-            self._graphs, self._cap8_scale = {}, {}
+        self._ensure_plan()
         plan = self._plan
         if plan._key != plan._weights_key():
             plan.pack()

@@ -256,3 +256,29 @@ def test_graph_plan_capacity_fallback_on_scattered_voxels(state_dict, cuda_model
         assert rel_rows(d, ref) < TOL, attempt
     many = cuda_model.forward_many([(ME.SparseTensor(feats, coordinates=coords, device="cuda"), image.cuda())] * 2, streams=2)
     assert all(rel_rows(o.F.cpu(), ref) < TOL for o in many)
+
+
+def test_low_latency_setting_matches_throughput_setting(state_dict, cuda_model):
+    """model.low_latency only changes how the small levels are scheduled (tile offsets split over several CTAs + a reduce
+    launch): same descriptors up to fp32 summation order, both settings deterministic and within the oracle tolerance; switching
+    the attribute rebuilds the plans."""
+    import imfnet_b200.me as ME
+    coords, _ = synthetic.make_fragment(6000, 0.05, seed=21)
+    c, f, im = torch.from_numpy(coords), torch.ones((6000, 1)), synthetic.make_image(160, 120, seed=21)
+    ref = imfnet_oracle.forward(state_dict, c, f, im)
+    assert not cuda_model.low_latency
+    try:
+        a = cuda_model(ME.SparseTensor(f, coordinates=c, device="cuda"), im.cuda()).F.clone()
+        cuda_model.low_latency = True
+        b = cuda_model(ME.SparseTensor(f, coordinates=c, device="cuda"), im.cuda()).F.clone()
+        b2 = cuda_model(ME.SparseTensor(f, coordinates=c, device="cuda"), im.cuda()).F.clone()
+        assert cuda_model._plan.split_small
+        many = cuda_model.forward_many([(ME.SparseTensor(f, coordinates=c, device="cuda"), im.cuda())] * 3, streams=2)
+    finally:
+        cuda_model.low_latency = False
+    a2 = cuda_model(ME.SparseTensor(f, coordinates=c, device="cuda"), im.cuda()).F
+    assert not cuda_model._plan.split_small
+    assert torch.equal(a, a2) and torch.equal(b, b2) and all(torch.equal(b, m.F) for m in many)
+    assert rel_rows(a, b) < 5e-6
+    assert note("low_latency_vs_oracle", rel_rows(b.cpu(), ref)) < TOL
+    assert note("throughput_setting_vs_oracle", rel_rows(a.cpu(), ref)) < TOL
