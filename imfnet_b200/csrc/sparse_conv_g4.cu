@@ -101,11 +101,10 @@ __device__ __forceinline__ void g4_tmem_zero16(uint32_t taddr) {
 __device__ __forceinline__ void named_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ---- work partition (identical in the convolution and in the reduce kernel) ---------------------------------------------
-// row mode  : CTA x owns output rows [x*R, (x+1)*R) (R a multiple of 32), all offsets;
+// row mode  : CTA x owns T / gx (+1 for the first T % gx CTAs) consecutive 128-row tiles, all offsets;
 // split mode: CTA x owns tile x / S and the x % S -th part of that tile's stage list; partials go to the workspace when S > 1.
 struct G4Part {
   int row_mode;
-  int R;          // rows per CTA (row mode)
   int S;          // splits per tile (split mode)
   int T;          // 128-row tiles
 };
@@ -113,7 +112,6 @@ __host__ __device__ inline G4Part g4_partition(int n, int gx, int nst_max, bool 
   G4Part p;
   p.T = (n + kBM - 1) / kBM;
   p.row_mode = (p.T >= gx) ? 1 : 0;
-  p.R = ((((n + gx - 1) / gx) + 31) / 32) * 32;
   int S = 1;
   if (!p.row_mode && have_ws && p.T > 0) {
     // as many splits as free SMs allow, but not below `stages_per_split` stages per CTA: a split costs a partial-tile round trip
@@ -214,8 +212,13 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   // rows of this CTA and its sub-tiles
   int row_begin, row_end, split = 0;
   if (part.row_mode) {
-    row_begin = bx * part.R;
-    row_end = min(row_begin + part.R, n32);
+    // whole 128-row tiles, the first T % gx CTAs one more than the others: same critical path as equal row counts, but no CTA
+    // carries a mostly empty trailing sub-tile (an MMA costs the same for 32 rows as for 128), and the short CTAs free their SM
+    // early for the other fragments' kernels
+    const int base = part.T / gx, extra = part.T - base * gx;
+    const int t0 = bx * base + min(bx, extra);
+    row_begin = t0 * kBM;
+    row_end = min((t0 + base + (bx < extra ? 1 : 0)) * kBM, n32);
   } else {
     const int tile = bx / part.S;
     split = bx % part.S;
