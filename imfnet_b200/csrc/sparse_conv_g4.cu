@@ -130,23 +130,23 @@ __host__ __device__ inline G4Part g4_partition(int n, int gx, int nst_max, bool 
 
 struct __align__(16) Half8 { __half2 a, b, c, d; };
 
-// 16 floats -> fp16 hi / lo halves (8 + 8 per 16-byte vector)
-__device__ __forceinline__ bool g4_split16(const float* x, Half8* hi, Half8* lo) {
+// 16 floats -> fp16 hi / lo halves (8 + 8 per 16-byte vector), packed conversions (one instruction per pair); returns max |x|
+__device__ __forceinline__ float g4_split16(const float* x, Half8* hi, Half8* lo) {
   __half2 h[8], l[8];
-  bool big = false;
+  float m = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float x0 = x[2 * i], x1 = x[2 * i + 1];
-    big |= (fabsf(x0) > 60000.f) | (fabsf(x1) > 60000.f);
-    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-    h[i] = __halves2half2(h0, h1);
-    l[i] = __halves2half2(__float2half_rn(x0 - __half2float(h0)), __float2half_rn(x1 - __half2float(h1)));
+    m = fmaxf(m, fmaxf(fabsf(x0), fabsf(x1)));
+    h[i] = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h[i]);
+    l[i] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
   }
   hi[0] = Half8{h[0], h[1], h[2], h[3]};
   hi[1] = Half8{h[4], h[5], h[6], h[7]};
   lo[0] = Half8{l[0], l[1], l[2], l[3]};
   lo[1] = Half8{l[4], l[5], l[6], l[7]};
-  return big;
+  return m;
 }
 __device__ __forceinline__ void g4_load16_h2(const __half* hi_src, const __half* lo_src, float* x) {
   const Half8* hs = reinterpret_cast<const Half8*>(hi_src);
@@ -196,7 +196,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   __shared__ int nk_s;
   __shared__ int ring_s[5];
   __shared__ int turn_s;                                 // next stage (running count) whose MMAs may be issued
-  __shared__ float sc_s[BN], sh_s[BN];
+  __shared__ __align__(16) float sc_s[BN], sh_s[BN];
   __shared__ __align__(16) int idx_s[NPROD][2][HROWS]; // neighbour indices of each producer warp's current / next stage
 
   int n = n_max;
@@ -518,9 +518,11 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
           if (j >= 2 && lane == 0) tma::store_wait_read<1>();      // this thread's stores that read this buffer two sub-tiles ago
           named_barrier(1, 256);
         }
+        if (tid == 0 && j < 8) G4_TRACE(160 + 8 * j);
         // NB 16-column blocks per round: the residual rows (global loads) and all TMEM loads of a round are in flight together
         constexpr int NB = CW >= 32 ? 2 : 1;
         const bool has_r = !partial && (R != nullptr) && grow < n;
+        const float act_floor = relu ? 0.f : -INFINITY;
 #pragma unroll 1
         for (int cb = 0; cb < CW; cb += 16 * NB) {
           float r16[NB][16];
@@ -541,6 +543,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
               tc::tmem_ld16_issue(tmem_d + ((uint32_t)(q * 32) << 16) + col + BN, t2[b]);
             }
             tc::tmem_ld_wait();
+            if (tid == 0 && j < 8) G4_TRACE(161 + 8 * j);
           } else {
 #pragma unroll
             for (int b = 0; b < NB; ++b)
@@ -563,15 +566,20 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
               continue;
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float x = fmaf(a[i], sc_s[cl + i], sh_s[cl + i]);
-              if (has_r) x += r16[b][i];
-              if (relu) x = fmaxf(x, 0.f);
-              a[i] = x;
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 sc4 = *reinterpret_cast<const float4*>(&sc_s[cl + 4 * i4]);
+              const float4 sh4 = *reinterpret_cast<const float4*>(&sh_s[cl + 4 * i4]);
+              const float scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, shv[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float x = fmaf(a[4 * i4 + i], scv[i], shv[i]);
+                if (has_r) x += r16[b][4 * i4 + i];
+                a[4 * i4 + i] = fmaxf(x, act_floor);
+              }
             }
             Half8 hi[2], lo[2];
-            const bool bg = g4_split16(a, hi, lo);
-            big |= bg && (grow < n);
+            const float amax = g4_split16(a, hi, lo);
+            big |= !(amax <= 60000.f) && (grow < n);
             if (out_row) {        // parity-grouped transposed convolution: table row grow describes output row out_row[grow]
               if (grow < n && grow < row_end) {      // rows past row_end belong to the next CTA's range
                 __half* yp = Yp + (size_t)__ldg(out_row + grow) * ldy + (c / kc_out) * 2 * kc_out + (c % kc_out);
@@ -597,9 +605,12 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
             *reinterpret_cast<Half8*>(pl + tc::sw128_offset(r_in, ch_lo + 1)) = lo[1];
           }
         }
+        if (tid == 0 && j < 8) G4_TRACE(162 + 8 * j);
         if (!partial && !out_row) {
           tc::fence_proxy_async();
+          if (tid == 0 && j < 8) G4_TRACE(163 + 8 * j);
           named_barrier(1, 256);
+          if (tid == 0 && j < 8) G4_TRACE(164 + 8 * j);
           // warp (q, h) stores the 32-row box q of images h, h + 2, ...: eight issuing threads instead of one
           const int r0 = prow + j * kBM + q * 32;
           if (lane == 0) {
@@ -610,6 +621,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
             }
             tma::store_commit();      // one (possibly empty) group per sub-tile: keeps the wait_read<1> arithmetic exact
           }
+          if (tid == 0 && j < 8) G4_TRACE(165 + 8 * j);
         }
       }
       if (!partial && !out_row && lane == 0) tma::store_wait_read<0>();
@@ -673,7 +685,7 @@ __global__ void __launch_bounds__(256) k_conv_g4_reduce(const float* __restrict_
     a[i] = x;
   }
   Half8 hi[2], lo[2];
-  const bool big = g4_split16(a, hi, lo);
+  const bool big = !(g4_split16(a, hi, lo) <= 60000.f);
   __half* yp = Y + (size_t)(out_row ? __ldg(out_row + row) : row) * ldy + (c / kc_out) * 2 * kc_out + (c % kc_out);
   reinterpret_cast<Half8*>(yp)[0] = hi[0];
   reinterpret_cast<Half8*>(yp)[1] = hi[1];

@@ -99,6 +99,12 @@ if args.trace:
           f"end-time spread (globaltimer ns): {int(ends[ends > 0].max() - ends[ends > 0].min())}")
     names = ["start", "barriers+TMEM", "masks", "epi wait", "acc ready", "epilogue done", "exit"]
     print("CTA0 timeline (cycles):", {nm: int(t[i] - t[0]) for i, nm in enumerate(names)})
+    for j in range(8):
+        r = t[160 + 8 * j: 166 + 8 * j]
+        if r[0] == 0:
+            break
+        print(f"  epilogue sub-tile {j}: buffer free {int(r[0] - t[0])}  TMEM loaded {int(r[1] - t[0])}  staged {int(r[2] - t[0])}  "
+              f"fenced {int(r[3] - t[0])}  all warps staged {int(r[4] - t[0])}  stores issued {int(r[5] - t[0])}")
     for i in range(36):
         r = t[16 + 4 * i: 20 + 4 * i]
         if r[2] == 0:
