@@ -252,6 +252,16 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
     sc_s[tid] = __ldg(scale + zt * BN + tid);
     sh_s[tid] = __ldg(shift + zt * BN + tid);
   }
+  // offset masks of the first pass' sub-tiles: loaded here so that their latency overlaps the TMEM allocation
+  if (tid >= 64 && tid < 64 + kMaxSubAll) {
+    const int j = tid - 64;
+    const int nsub0 = nsub_total < Cfg::MAXSUB ? nsub_total : Cfg::MAXSUB;
+    if (j < nsub0) {
+      const int r0 = row_begin + j * kBM;
+      const int r1 = min(r0 + kBM, row_end) - 1;
+      submask_s[j] = __ldg(tile_mask + r0 / kBM) | __ldg(tile_mask + r1 / kBM);
+    }
+  }
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
@@ -267,12 +277,14 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
     const int nsub = min(Cfg::MAXSUB, nsub_total - sub0);
     const int prow = row_begin + sub0 * kBM;            // first row of this pass
     // ---- offset masks of the sub-tiles; offset list of the pass with, per offset, the sub-tiles that need it ----
-    if (tid < nsub) {
-      const int r0 = prow + tid * kBM;
-      const int r1 = min(r0 + kBM, row_end) - 1;
-      submask_s[tid] = __ldg(tile_mask + r0 / kBM) | __ldg(tile_mask + r1 / kBM);
+    if (pass > 0) {                                      // (pass 0: loaded before the set-up barrier)
+      if (tid < nsub) {
+        const int r0 = prow + tid * kBM;
+        const int r1 = min(r0 + kBM, row_end) - 1;
+        submask_s[tid] = __ldg(tile_mask + r0 / kBM) | __ldg(tile_mask + r1 / kBM);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (warp == 0) {            // lane b = offset b: is it used by any sub-tile, by which ones; compacted in offset order
       unsigned jm = 0;
       for (int j = 0; j < nsub; ++j) jm |= ((submask_s[j] >> lane) & 1u) << j;
