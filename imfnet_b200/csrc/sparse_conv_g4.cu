@@ -1,4 +1,4 @@
-// imfnet_b200 -- sparse 3-D convolution, "g4" kernel: TMA tile::gather4 implicit GEMM on the tcgen05 tensor cores.
+// imfnet_b200 -- sparse 3-D convolution, "g4" kernel: persistent output-stationary implicit GEMM on the tcgen05 tensor cores.
 //
 // Same operation and h2 data format as sparse_conv_h2.cu,
 //   Y[o] = act( (sum_k X[nbr(o,k)] . W[k]) * scale + shift (+ R[o]) )
@@ -6,23 +6,25 @@
 //   /root/reference/model/resunet.py:168-213, model/residual_block.py:37-53,
 // re-designed around what bounded that kernel on B200 (profiles/r01: 110 us for 64->64 at 50 k voxels, 70 % of it pipeline
 // skeleton, 2 % DRAM, every 128-row tile re-reading all 27 weight slabs from L2):
-//   * persistent grid (one CTA per SM); a CTA owns a contiguous range of output rows (several 128-row sub-tiles, one TMEM
-//     accumulator each) and walks offsets OUTER / sub-tiles INNER, so a weight slab is fetched once per CTA, not once per tile;
-//   * neighbour rows are fetched by the TMA engine (cp.async.bulk.tensor tile::gather4: four rows per instruction, absent
-//     neighbours = out-of-range index = zero fill, 128-byte swizzle applied by the hardware) straight into the operand ring;
-//     a gather4 instruction occupies its warp for ~2700 cycles (measured, tools/tma_rate.py) but the rate adds up over warps
-//     (8 warps = 46 B/cycle/SM, the L2 ceiling), so whole 128-row images are dealt round-robin to 8 producer warps; completion is counted
-//     in bytes on an mbarrier, so there is no per-thread wait / fence / arrive chain and every ring slot can be in flight;
+//   * persistent grid (one CTA per SM); a CTA owns consecutive whole 128-row tiles (one TMEM accumulator pair each) and walks
+//     offsets OUTER / sub-tiles INNER, so a weight slab is fetched once per CTA, not once per tile;
+//   * neighbour rows are gathered with 16-byte cp.async (LDGSTS) straight into 128-byte-swizzled operand images, two warps per
+//     ring slot, completion counted on the slot's mbarrier (cp.async.mbarrier.arrive.noinc): no thread waits for its own copies
+//     and every ring slot can be in flight.  (TMA tile::gather4 was measured first -- hence the kernel's name -- and rejected:
+//     84 cycles per instruction and issuing warp, 44 B/cycle/SM at best, zero-filled rows 5x slower; tools/tma_rate.py);
 //   * the neighbour table is offset-major (nbr_t[k][row]), so the indices of a stage are one coalesced 512-byte read, and a
 //     per-tile offset mask (built by imf_kernel_map_t) lets (offset, sub-tile) pairs without any neighbour be skipped;
+//   * MMAs are issued from warp-uniform code (descriptors in uniform registers, bare UTCHMMA back to back), each accumulator by
+//     one thread only, the issuing warps taking turns in walk order: bit-reproducible sums (see the MMA section);
 //   * the epilogue converts TMEM -> BatchNorm affine / residual / ReLU -> fp16 hi/lo in registers, stages the tile in shared
 //     memory (swizzled, conflict-free) and writes it with tiled TMA stores;
 //   * all sizes are read on the device (n_out_dev): the launch shape depends only on the SM count, which is what lets the
 //     whole forward be captured in a CUDA graph;
-//   * small levels (fewer tiles than SMs) split a tile's stage list over several CTAs into fp32 partials + a reduce kernel.
+//   * small levels (fewer tiles than SMs) run one CTA per tile, or -- when the caller passes a workspace -- split a tile's stage
+//     list over several CTAs into fp32 partials + a reduce kernel (shorter latency, more SM time).
 //
-// CTA = 13 warps: warps 0-7 = gather producers, then the epilogue; warps 8-11 = MMA issuers, one group of sub-tiles each (warp 8
-// also owns the TMEM allocation); warp 12 = weight-slab loader (bulk TMA copies).
+// CTA = 13 or 15 warps: warps 0-7 = gather producers, then the epilogue; warps 8-11 = MMA issuers (warp 8 also owns the TMEM
+// allocation); warp 12 = weight-slab loader (bulk TMA copies); warps 13-14 = two more gather producers when the ring has 5 slots.
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -428,21 +430,19 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       }
     } else if (warp >= kNPW && warp < kNPW + kNMW) {
       // =========================== MMA issuers ===========================
-      // An issuing thread is held ~85-95 cycles per tcgen05.mma (any N <= 128, measured) and pays ~300 cycles of barrier / walk
-      // overhead per stage, so the stages are spread over kNMW warps by sub-tile (each accumulator belongs to one warp, which
-      // keeps the accumulate flag and the instruction order per accumulator inside one thread).
       // Three split products with two instructions per K step:
       //   D[:, 0:2BN] += a_hi . [Whi | Wlo]^T   (the weight slab is one 2BN-row image: rows [0,BN) = Whi, [BN,2BN) = Wlo)
       //   D[:, 0:BN]  += a_lo . Whi^T            the epilogue adds the two halves
       constexpr uint32_t idesc2 = g4_idesc_f16(kBM, 2 * BN), idesc1 = g4_idesc_f16(kBM, BN);
       const int mw = warp - kNPW;
-      // Stage s is issued by MMA warp s % kNMW, so consecutive stages never fall to the same warp (its ~600 cycles of per-stage
-      // bookkeeping would sit on the issue chain; measured with the slot-based assignment every NA-th stage).  The parity wait
-      // on full_a stays unambiguous because of the turn order below: a warp reaches stage s only after it issued stage s - 4,
-      // i.e. after every earlier stage -- including the previous use of the same ring slot -- was consumed.
-      // An accumulator is fed by several threads; the tensor pipe executes MMAs one after the other, so only the "first MMA
-      // overwrites" flag needs care: the accumulators are zeroed here (each MMA warp owns one TMEM lane quadrant) and every
-      // MMA accumulates.
+      // A stage is issued by the MMA warp that owns its sub-tile (j % kNMW): every accumulator is fed by ONE thread, whose
+      // tcgen05.mma execute in issue order.  Feeding an accumulator from several threads is not ordered by the tensor pipe even
+      // when the issue order is (measured: last-bit differences from launch to launch, tools/conv_g4_check.py), so this
+      // ownership is what makes the sums bit-reproducible.  With >= 2 sub-tiles consecutive stages fall to different warps, whose
+      // per-stage bookkeeping (~600 cycles) then stays off the issue chain.  The warps take turns in walk order (turn_s): a warp
+      // reaches stage s only after every earlier stage was issued, i.e. after the previous use of the same ring slot was
+      // consumed, which keeps the parity wait on full_a unambiguous.  The accumulators are zeroed here (each MMA warp clears
+      // one TMEM lane quadrant) so that every MMA accumulates.
       {
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         for (int col = 0; col < nsub * Cfg::ACC_COLS; col += 16) g4_tmem_zero16(tmem_d + lane_base + (uint32_t)col);

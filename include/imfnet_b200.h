@@ -142,7 +142,10 @@ int imf_sparse_conv_h2_fwd(const void* X, int32_t ldx, int32_t kc_in, const void
  * persistent (one CTA per SM, launch shape independent of the row count, all sizes read from n_out_dev on the device), reading the
  * offset-major table + tile masks of imf_kernel_map_t, sharing each weight slab between the sub-tiles of a CTA, and writing the output
  * with tiled TMA stores.  n_y_rows = rows of the Y allocation (tensor-map extent, >= n_out_max; rows in [n, roundup32(n)) that exist
- * may be overwritten).  workspace (optional, imf_sparse_conv_g4_workspace_bytes) enables the split mode used when n < 128 * #SMs. */
+ * may be overwritten).  workspace (optional, imf_sparse_conv_g4_workspace_bytes): NULL = one CTA per 128-row tile when n < 128 * #SMs
+ * (least SM time: best throughput with several fragments in flight); non-NULL = such a small level splits each tile's offsets over
+ * several CTAs into fp32 partials in the workspace + a reduce launch (shortest latency of a lone forward).  Same result up to fp32
+ * summation order; each setting is bit-reproducible. */
 size_t imf_sparse_conv_g4_workspace_bytes(int32_t Cout);
 int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t kc_in, const void* packed, const int32_t* nbr_t, int32_t ld_n,
                            const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max, int32_t kernel_volume, int32_t Cin,
@@ -157,10 +160,11 @@ int imf_sparse_conv_g4_fwd_perm(const void* X, int32_t ldx, int32_t kc_in, const
                                 int32_t Cout, const float* scale, const float* shift, const void* residual, int32_t ldr, int32_t kc_r,
                                 int32_t relu, void* Y, int32_t ldy, int32_t n_y_rows, int32_t kc_out, const int32_t* out_row,
                                 void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
-/* Profiling hook: device int64 buffer (>= 1024 entries) filled by CTA 0 with clock64() stamps (slot map in the source), and an
- * override of the CTAs per output-channel tile (0 = one per SM) and of the producer warps per CTA (8 or 16; other values keep the
- * current setting); flags: bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs (results are then meaningless).
- * NULL / 0 switch everything off. */
+/* Profiling hook: device int64 buffer (>= 1024 entries) filled by CTA 0 with clock64() stamps (slot map in the source), an
+ * override of the CTAs per output-channel tile (0 = one per SM) and of the minimum stages per split CTA (`producer_warps`, 0 keeps
+ * the current value); flags: bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs (results are then meaningless),
+ * bit 3 = one MMA-issuing warp, bit 4 = stages dealt to the MMA warps by stage number instead of by accumulator (results correct
+ * but not bit-reproducible: tools/conv_g4_check.py).  NULL / 0 switch everything off. */
 int imf_debug_conv_g4_trace(long long* trace, int32_t grid, int32_t producer_warps, int32_t flags);
 
 /* First layer (conv1, model/resunet.py:42-49,168): K in {1,3,5}, Cin in {1,3,6} (ones / rgb / rgb+normal,
