@@ -29,7 +29,7 @@ import torch  # noqa: E402
 
 METRIC = "descriptor-extraction throughput: voxels/sec/GPU on 50k-voxel fragments"
 N_FRAGMENTS = 8
-NCU_DRAM_BYTES_PER_LAUNCH = 18679808      # k_sparse_conv_g4<64,64>, 64->64 @ 50 000 voxels (profiles/r01/call26_g4_ncu_summary.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = 18674944      # k_sparse_conv_g4<64,64>, 64->64 @ 50 000 voxels (profiles/r01/call55_g4_ncu_summary.txt)
 
 
 def load_peaks():
@@ -170,7 +170,7 @@ def dominant_kernel_roofline(model, frag, flush):
     return {"bound": "hbm", "kernel": f"k_sparse_conv_g4<64,64> 3x3x3 {cin}->{cout} @ {n} voxels ({pairs} pairs)", "achieved": achieved,
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "alg_bytes_per_launch": alg_bytes,
             "ms_per_launch": ms, "flops_per_launch": 2 * pairs * cin * cout, "peak_source": how,
-            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r01/call26_g4_ncu_summary.txt)"}
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r01/call55_g4_ncu_summary.txt)"}
 
 
 def run_ours(args, rank, world, local_rank):
