@@ -198,7 +198,13 @@ def run_ours(args, rank, world, local_rank):
 
     K = max(1, args.streams)      # independent fragments in flight per step (one captured plan + CUDA stream each)
 
+    Bt = max(0, args.batched)     # > 0: groups of Bt fragments per captured-graph replay (imfnet_b200/batched.py), two plans in flight
+    if Bt and K % Bt:
+        raise SystemExit("--streams (fragments per step) must be a multiple of --batched")
+
     def step_resident(i):
+        if Bt:
+            return model.forward_batches([dev_frags[(i * K + j) % N_FRAGMENTS] for j in range(K)], Bt, streams=2)
         if K == 1:
             c, f, im = dev_frags[i % N_FRAGMENTS]
             return model(ME.SparseTensor(f, coordinates=c), im).F
@@ -210,6 +216,8 @@ def run_ours(args, rank, world, local_rank):
     host_outs = [torch.empty((target, 32), dtype=torch.float32).pin_memory() for _ in range(K)]
 
     def step_e2e(i):
+        if Bt:
+            return model.forward_batches([pin_frags[(i * K + j) % N_FRAGMENTS] for j in range(K)], Bt, streams=2, out=host_outs)
         if K == 1:
             c, f, im = pin_frags[i % N_FRAGMENTS]
             x = ME.SparseTensor(f.to(dev, non_blocking=True), coordinates=c.to(dev, non_blocking=True))
@@ -321,7 +329,9 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "flushed between steps (256 MiB write, outside the per-step CUDA events)",
                    "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
                    "coordinate_maps": "rebuilt every step (cold), as the reference does per SparseTensor",
-                   "execution": (f"one captured CUDA graph replay per fragment (device-side sizes), {K} independent fragments in flight on {K} streams"
+                   "execution": (f"one captured CUDA graph replay per batch of {Bt} fragments (device-side sizes), {K // Bt} batches per step, 2 plans in flight"
+                                 if Bt else
+                                 f"one captured CUDA graph replay per fragment (device-side sizes), {K} independent fragments in flight on {K} streams"
                                  if model.use_cuda_graph else "eager launches"),
                    "parallelism": f"fragments sharded over {world} GPU(s), no data-path collective"},
         "e2e": {"value": e2e_v, "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -339,6 +349,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--streams", type=int, default=10, help="independent fragments in flight per step (captured plan + stream each)")
+    ap.add_argument("--batched", type=int, default=0,
+                    help="B > 0: run the step's fragments in groups of B through the batched captured plan (imfnet_b200/batched.py)")
     ap.add_argument("--profile", action="store_true", help="run only warm-up + steps (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "ours" and not args.profile:

@@ -46,6 +46,9 @@ SIGNATURES = {
     "imf_debug_conv_g4_trace": (C.c_int, [_p, _i32, _i32, _i32]),
     "imf_quantize_points": (C.c_int, [_p, _i32, _f64, _i32, _p, _p]),
     "imf_batch_segments": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
+    "imf_batch_segments_n": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
+    "imf_h2_unpack_seg": (C.c_int, [_p, _i32, _p, _p, _i32, _i32, _i32, _p, _i32, _p]),
+    "imf_h2_pack_seg": (C.c_int, [_p, _i32, _p, _p, _i32, _i32, _i32, _p, _i32, _p, _p]),
     "imf_sparse_conv_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _i32, _p]),
     "imf_h2_pack": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p, _p]),
     "imf_h2_unpack": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p]),

@@ -1,0 +1,364 @@
+"""Batched captured plan: B fragments (+ their B images) through ONE CUDA-graph replay.
+
+The reference accepts batches -- `collate_pair_fn` builds batched coordinates (/root/reference/lib/data_loaders.py:28-91) and
+`ResUNet2.forward` / `transformer` split the stride-8 rows per batch item against that item's image
+(/root/reference/model/resunet.py:163-273) -- while `scripts/generate_desc.py:65-123` feeds one fragment per call.  For
+throughput the batched form is the better shape on a B200: every sparse convolution of the forward becomes ONE persistent
+launch over all items' rows, so the per-CTA fixed cost of the convolution kernel (prologue + epilogue, ~13 k cycles, DESIGN.md
+section 4.1) and the under-filled small levels (1-4 k rows per fragment at strides 4 and 8, 4 800 pixels in the image encoder's
+layer2: 9-38 CTAs on 148 SMs) are paid once per batch instead of once per fragment.  `GraphPlan` (engine.py) keeps several
+single-fragment graphs in flight instead; this module is the alternative the bench can switch to (`bench.py --batched B`).
+
+Everything arithmetic runs in the same kernels as the single-fragment plan; per output row the summation order of every
+convolution is unchanged (offset order, chunk order), so the descriptors are expected to be bit-identical to forward() fragment by
+fragment in the throughput setting (tests/test_gpu_batched.py).
+
+What is specific to a batch:
+  * coordinates carry the item index in column 0 (set on the device after the host->device copy);
+  * the image encoder runs once over B*H*W pixel rows with neighbour tables replicated per image (`BatchedImagePlan`);
+  * the fusion module runs per item on forked streams; the per-item row ranges at stride 8 stay on the device
+    (csrc/batched.cu: imf_batch_segments_n, imf_h2_unpack_seg, imf_h2_pack_seg).
+
+STATUS: written against the verified single-fragment plan without GPU access (the round's GPU budget was spent); the GPU test
+is marked `unverified` and `bench.py` only takes this path when asked to.  See DESIGN.md section 7.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .engine import FusedPlan, GraphPlan, PlanCapacityError, _kc
+from .model.Img_Encoder import ImagePlan
+
+
+class BatchedImagePlan(ImagePlan):
+    """ImagePlan over B images of one size: pixel rows of image b are rows [b*P, (b+1)*P) of every matrix."""
+
+    def __init__(self, backbone, H: int, W: int, B: int):
+        super().__init__(backbone, H, W, False)
+        self.B = B = int(B)
+        dev = self.device
+        with torch.cuda.device(dev):
+            self.t_id0 = self._replicate(self.t_id0, self.P0, self.P0)
+            self.t1 = self._replicate(self.t1, self.P1, self.P1)
+            self.t12 = self._replicate(self.t12, self.P1, self.P2)
+            self.t12d = self._replicate(self.t12d, self.P1, self.P2)
+            self.t2 = self._replicate(self.t2, self.P2, self.P2)
+            f32 = dict(dtype=torch.float32, device=dev)
+            self.col = torch.zeros((B * self.P0, self.STEM_K), **f32)
+            self.s0 = torch.zeros((B * self.P0, self.C1), **f32)
+            self.l1 = [torch.zeros((B * self.P1, self.C1), **f32) for _ in range(3)]
+            self.l2 = [torch.zeros((B * self.P2, self.C2), **f32) for _ in range(3)]
+            self.tokens = torch.zeros((B * self.P2, self.C2), **f32)
+
+    def _replicate(self, tab, p_in: int, p_out: int):
+        """Single-image offset-major table [K, ld] -> table of B images (input rows shifted by b*p_in) + its 128-row tile masks."""
+        nbr_t, _ld, _mask = tab
+        B, K = self.B, nbr_t.shape[0]
+        t = nbr_t[:, :p_out]
+        n = B * p_out
+        ld = (n + 127) // 128 * 128
+        out = torch.full((K, ld), -1, dtype=torch.int32, device=nbr_t.device)
+        for b in range(B):
+            out[:, b * p_out:(b + 1) * p_out] = torch.where(t >= 0, t + b * p_in, t)
+        valid = (out >= 0).view(K, ld // 128, 128).any(dim=2).to(torch.int32)                     # [K, tiles]
+        bits = (valid << torch.arange(K, dtype=torch.int32, device=out.device).view(K, 1)).sum(dim=0).to(torch.int32)
+        mask = torch.zeros(ld // 128 + 1, dtype=torch.int32, device=out.device)
+        mask[: ld // 128] = bits
+        return out, ld, mask
+
+    def enqueue(self, images: torch.Tensor) -> torch.Tensor:
+        """images fp32 [B,3,H,W] (contiguous, on the plan's device) -> fp32 tokens [B * H/8*W/8, 128] (plan-owned)."""
+        L = _lib.lib()
+        s = _lib.cur_stream()
+        B = self.B
+        k, st, pd = self.stem_geom
+        for b in range(B):
+            _lib.check(L.imf_image_im2col_h2(images[b].data_ptr(), 3, self.H, self.W, k, st, pd, self.STEM_K,
+                                             self.col.data_ptr() + b * self.P0 * self.STEM_K * 4, 2 * self.STEM_K, s))
+        self._conv(L, self.stem, self.col, self.t_id0, B * self.P0, None, True, self.s0, s)
+        for b in range(B):
+            _lib.check(L.imf_image_maxpool_h2(self.s0.data_ptr() + b * self.P0 * self.C1 * 4, 2 * self.C1, 64, self.C1, self.H1, self.W1,
+                                              3, 2, 1, self.l1[0].data_ptr() + b * self.P1 * self.C1 * 4, 2 * self.C1, s))
+        n1, n2 = B * self.P1, B * self.P2
+        x, tmp, out = self.l1
+        for c1, c2 in self.blocks1:
+            self._conv(L, c1, x, self.t1, n1, None, True, tmp, s)
+            self._conv(L, c2, tmp, self.t1, n1, x, True, out, s)
+            x, out = out, x
+        y, tmp, out = self.l2
+        for c1, c2, down in self.blocks2:
+            if down is not None:
+                self._conv(L, c1, x, self.t12, n2, None, True, tmp, s)
+                self._conv(L, down, x, self.t12d, n2, None, False, out, s)
+                self._conv(L, c2, tmp, self.t2, n2, out, True, y, s)
+            else:
+                self._conv(L, c1, y, self.t2, n2, None, True, tmp, s)
+                self._conv(L, c2, tmp, self.t2, n2, y, True, out, s)
+                y, out = out, y
+        _lib.check(L.imf_h2_unpack(y.data_ptr(), 2 * self.C2, n2, self.C2, 64, self.tokens.data_ptr(), self.C2, s))
+        return self.tokens
+
+
+class BatchGraphPlan(GraphPlan):
+    """GraphPlan for exactly B fragments of at most `rows` voxels in total (each at most `item_cap8` rows at stride 8)."""
+
+    ERR_ITEM_CAPACITY = 0x20000
+    ERR_BATCH_INDEX = 0x40000
+
+    def __init__(self, fused: FusedPlan, rows: int, H: int, W: int, B: int, item_cap8: int):
+        if fused.split_small:
+            raise NotImplementedError("the batched plan implements the throughput setting (model.low_latency = False)")
+        super().__init__(fused, rows, H, W, cap8=256)          # the base plan's stride-8 buffers are replaced below
+        L = _lib.lib()
+        m, dev = self.m, self.device
+        CH = fused.CH
+        self.B, self.item_cap8 = int(B), int(item_cap8)
+        self.cap8 = self.rows                                   # the level itself lives in full-size buffers (d0, d1, d2, fused)
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        self.image = torch.zeros((self.B, 3, self.H, self.W), **f32)
+        with torch.cuda.device(dev):
+            self.image_plan = BatchedImagePlan(m.img_encoder.backbone, self.H, self.W, self.B)
+        self.n_tok = self.image_plan.P2
+        self.P8 = self.fused32 = None
+        self.seg = torch.zeros(self.B + 1, **i32)
+        self.cnt = torch.zeros(self.B, **i32)
+        af = m.attention_fusion
+        self.att_ws_bytes = int(L.imf_attention_workspace_bytes(self.item_cap8, self.n_tok, af.latent_dim, af.inner))
+        self.item = [dict(P8=torch.zeros((self.item_cap8, CH[4]), **f32), fused32=torch.zeros((self.item_cap8, CH[4]), **f32),
+                          ws=torch.empty(max(self.att_ws_bytes, 1), **u8), stream=torch.cuda.Stream(device=dev)) for _ in range(self.B)]
+        self.att_ws = None
+
+    # -- the launch sequence (GraphPlan._enqueue with the image branch and the fusion step per batch item) ------------------
+    def _enqueue(self):
+        m, f, L = self.m, self.f, _lib.lib()
+        CH, TR, rows, B = f.CH, f.TR, self.rows, self.B
+        main = torch.cuda.current_stream()
+        s = main.cuda_stream
+        status = self.meta.data_ptr()
+        # ---- image branch on a forked stream: one encoder pass over all images, then K / V of every item ----
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            tokens = self.image_plan.enqueue(self.image)
+            P2 = self.image_plan.P2
+            self.kvs = [m.attention_fusion.project_context(tokens[b * P2:(b + 1) * P2], False) for b in range(B)]
+        # ---- coordinates: hash, pyramid, neighbour tables (all sizes stay on the device) ----
+        self.meta.zero_()
+        self.err.zero_()
+        _lib.check(L.imf_hash_build(self.coords[1].data_ptr(), self._n(1), rows, self.tables[1].data_ptr(), self.cap, status, s))
+        prev = 1
+        for t in (2, 4, 8):
+            _lib.check(L.imf_stride_map(self.coords[prev].data_ptr(), self._n(prev), rows, t, self.tables[t].data_ptr(), self.cap,
+                                        self.coords[t].data_ptr(), self._n(t), None, self.sm_ws.data_ptr(), self.sm_ws_bytes, status, s))
+            prev = t
+        for t in (1, 2, 4):
+            _lib.check(L.imf_parity_perm(self.coords[t].data_ptr(), self._n(t), rows, t, self.perm[t].data_ptr(), self.perm_ws.data_ptr(),
+                                         self.perm_ws_bytes, s))
+        jobs = (_lib.KmapJob * len(self.nbr))()
+        for i, ((t_in, t_out, tr), (nbr_t, ld_n, mask)) in enumerate(self.nbr.items()):
+            jobs[i] = _lib.KmapJob(self.coords[t_out].data_ptr(), self._n(t_out), self.tables[t_in].data_ptr(), nbr_t.data_ptr(),
+                                   mask.data_ptr(), self.perm[t_out].data_ptr() if tr else None, -t_out if tr else t_in)
+        _lib.check(L.imf_kernel_map_t_batch(jobs, len(self.nbr), rows, self.cap, 3, self.ldn, s))
+        _lib.check(L.imf_batch_segments_n(self.coords[8].data_ptr(), self._n(8), rows, B, self.item_cap8, self.seg.data_ptr(),
+                                          self.cnt.data_ptr(), self.err.data_ptr(), s))
+        # ---- encoder ----
+        ld1, ld2, ld4 = 2 * self.cat1.shape[1], 2 * self.cat2.shape[1], 2 * self.cat4.shape[1]
+        s1, s2, s4 = self.cat1.data_ptr() + TR[2] * 4, self.cat2.data_ptr() + TR[3] * 4, self.cat4.data_ptr() + TR[4] * 4
+        kc1a, kc1b = _kc(TR[2]), _kc(CH[1])
+        kc2, kc4, k8 = _kc(TR[3], CH[2]), _kc(TR[4], CH[3]), _kc(CH[4])
+        sc, sh = f.norm1
+        _lib.check(L.imf_conv_first_h2_fwd(self.feats.data_ptr(), self.feats.shape[1], m.conv1.in_channels, m.conv1.kernel.data_ptr(),
+                                           self.coords[1].data_ptr(), self._n(1), rows, self.tables[1].data_ptr(), self.cap,
+                                           m.conv1.kernel_size, 1, CH[1], sc.data_ptr(), sh.data_ptr(), 0, self.a0.data_ptr(),
+                                           2 * CH[1], _kc(CH[1]), s))
+        self._block(L, "block1", self.a0.data_ptr(), 2 * CH[1], _kc(CH[1]), 1, CH[1], self.a1, s1, ld1, kc1b, s)
+        self._conv(L, "conv2", s1, ld1, (1, 2, False), 2, None, 0, 0, False, self.b0.data_ptr(), 2 * CH[2], _kc(CH[2]), s)
+        self._block(L, "block2", self.b0.data_ptr(), 2 * CH[2], _kc(CH[2]), 2, CH[2], self.b1, s2, ld2, kc2, s)
+        self._conv(L, "conv3", s2, ld2, (2, 4, False), 4, None, 0, 0, False, self.c0.data_ptr(), 2 * CH[3], _kc(CH[3]), s)
+        self._block(L, "block3", self.c0.data_ptr(), 2 * CH[3], _kc(CH[3]), 4, CH[3], self.c1, s4, ld4, kc4, s)
+        self._conv(L, "conv4", s4, ld4, (4, 8, False), 8, None, 0, 0, False, self.d0.data_ptr(), 2 * CH[4], k8, s)
+        self._block(L, "block4", self.d0.data_ptr(), 2 * CH[4], k8, 8, CH[4], self.d1, self.d2.data_ptr(), 2 * CH[4], k8, s)
+        # ---- attention fusion at stride 8, one chain per batch item on its own stream (model/resunet.py:240-271) ----
+        af = m.attention_fusion
+        main.wait_stream(self.side)
+        for b, it in enumerate(self.item):
+            st = it["stream"]
+            st.wait_stream(main)
+            seg_b, cnt_b = self.seg.data_ptr() + 4 * b, self.cnt.data_ptr() + 4 * b
+            with torch.cuda.stream(st):
+                sb = st.cuda_stream
+                _lib.check(L.imf_h2_unpack_seg(self.d2.data_ptr(), 2 * CH[4], seg_b, cnt_b, self.item_cap8, CH[4], k8,
+                                               it["P8"].data_ptr(), CH[4], sb))
+                _lib.check(L.imf_attention_fusion_fwd_m(af.packed(), it["P8"].data_ptr(), CH[4], self.item_cap8, cnt_b,
+                                                        self.kvs[b].data_ptr(), self.n_tok, it["fused32"].data_ptr(), CH[4],
+                                                        it["ws"].data_ptr(), self.att_ws_bytes, sb))
+                _lib.check(L.imf_h2_pack_seg(it["fused32"].data_ptr(), CH[4], seg_b, cnt_b, self.item_cap8, CH[4], k8,
+                                             self.fused.data_ptr(), 2 * CH[4], self.err.data_ptr(), sb))
+        for it in self.item:
+            main.wait_stream(it["stream"])
+        # ---- decoder ----
+        self._conv(L, "conv4_tr", self.fused.data_ptr(), 2 * CH[4], (8, 4, True), 4, None, 0, 0, False, self.e0.data_ptr(), 2 * TR[4],
+                   _kc(TR[4]), s)
+        self._block(L, "block4_tr", self.e0.data_ptr(), 2 * TR[4], _kc(TR[4]), 4, TR[4], self.e1, self.cat4.data_ptr(), ld4, kc4, s)
+        self._conv(L, "conv3_tr", self.cat4.data_ptr(), ld4, (4, 2, True), 2, None, 0, 0, False, self.g0.data_ptr(), 2 * TR[3], _kc(TR[3]), s)
+        self._block(L, "block3_tr", self.g0.data_ptr(), 2 * TR[3], _kc(TR[3]), 2, TR[3], self.g1, self.cat2.data_ptr(), ld2, kc2, s)
+        self._conv(L, "conv2_tr", self.cat2.data_ptr(), ld2, (2, 1, True), 1, None, 0, 0, False, self.h0.data_ptr(), 2 * TR[2], _kc(TR[2]), s)
+        self._block(L, "block2_tr", self.h0.data_ptr(), 2 * TR[2], _kc(TR[2]), 1, TR[2], self.h1, self.cat1.data_ptr(), ld1, kc1a, s)
+        # ---- tail ----
+        _lib.check(L.imf_pointwise_tail_h2_fwd(self.cat1.data_ptr(), ld1, TR[2] + CH[1], TR[2], kc1a, kc1b, m.conv1_tr.kernel.data_ptr(),
+                                               TR[1], m.final.kernel.data_ptr(), _lib.ptr(f.final_bias), m.out_channels, self._n(1), rows,
+                                               1 if m.normalize_feature else 0, None, self.out.data_ptr(), m.out_channels, s))
+
+    # -- one batch ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def launch_batch(self, frags, stream=None, out_hosts=None):
+        """frags = exactly B tuples (coords int32 [N_b,4], feats fp32 [N_b,Cin], image fp32 [1,3,H,W] or [3,H,W]); device or
+        (pinned) host tensors.  Column 0 of the coordinates is overwritten with the item index on the device.  Enqueues the
+        copies, one graph replay and the result copies on `stream` without waiting; finish_batch() returns the descriptors."""
+        if len(frags) != self.B:
+            raise ValueError(f"the plan was built for batches of {self.B} fragments, got {len(frags)}")
+        sizes = [int(c.shape[0]) for c, _f, _im in frags]
+        total = sum(sizes)
+        if total > self.rows:
+            raise PlanCapacityError(f"{total} voxels > plan rows {self.rows}")
+        with torch.cuda.device(self.device):
+            if self.graph is None:
+                self.capture()
+            cur = torch.cuda.current_stream()
+            st = cur if stream is None else stream
+            if st is not cur:
+                st.wait_stream(cur)
+            outs = []
+            with torch.cuda.stream(st):
+                off = 0
+                for b, (c, ft, im) in enumerate(frags):
+                    n = sizes[b]
+                    self.coords[1][off:off + n].copy_(c, non_blocking=True)
+                    self.coords[1][off:off + n, 0].fill_(b)
+                    self.feats[off:off + n].copy_(ft, non_blocking=True)
+                    self.image[b].copy_(im.reshape(self.image.shape[1:]), non_blocking=True)
+                    off += n
+                self.n1.fill_(total)
+                self.graph.replay()
+                GraphPlan.replayed_launches += self.launches_per_replay
+                off = 0
+                for b, n in enumerate(sizes):
+                    if out_hosts is None:
+                        o = self.out[off:off + n].clone()
+                    else:
+                        o = out_hosts[b][:n]
+                        o.copy_(self.out[off:off + n], non_blocking=True)
+                    outs.append(o)
+                    off += n
+                self.meta_host[:16].copy_(self.meta, non_blocking=True)
+                self.meta_host[16:].copy_(self.err, non_blocking=True)
+                self._done = torch.cuda.Event()
+                self._done.record(st)
+            self._pending = (total, outs, st, cur)
+
+    def finish_batch(self):
+        total, outs, st, cur = self._pending
+        self._pending = None
+        self._done.synchronize()
+        if st is not cur:
+            for o in outs:
+                if o.is_cuda:
+                    o.record_stream(cur)
+        mh = self.meta_host.tolist()
+        if mh[0]:
+            from .sparse import _raise_status
+            _raise_status(mh[0])
+        if mh[16] & self.ERR_BATCH_INDEX:
+            raise ValueError("coordinates carry a batch index outside the plan's batch size")
+        if mh[16] & self.ERR_ITEM_CAPACITY:
+            raise PlanCapacityError(f"a fragment has more than {self.item_cap8} voxels at stride 8")
+        FusedPlan._raise_on_status(mh[16])
+        self.levels = {1: total, 2: mh[2], 4: mh[3], 8: mh[4]}
+        return outs
+
+    def launch(self, *a, **k):
+        raise NotImplementedError("use launch_batch / finish_batch")
+
+    run = launch
+
+
+@torch.no_grad()
+def forward_batches(model, frags, batch: int, streams: int = 2, out=None):
+    """frags = [(coords int32 [N,4], feats fp32 [N,Cin], image fp32 [1,3,H,W]), ...], all on the host (ideally pinned) or all on
+    the model's device.  Consecutive groups of `batch` fragments go through one `BatchGraphPlan` replay each, `streams` plans in
+    flight (the copies of one group overlap the compute of the other); a trailing group smaller than `batch`, groups with images
+    of different sizes and groups that overflow a plan's capacity take `forward_many_host` / `forward_many`.
+    Returns the descriptors [N, out_channels] per fragment in order: device tensors for device inputs, pinned host tensors
+    (`out[i]` when given) for host inputs."""
+    from . import me as ME
+    if model.training:
+        raise NotImplementedError("imfnet_b200 implements the eval-mode forward")
+    model._ensure_plan()
+    plan = model._plan
+    if plan._key != plan._weights_key():
+        plan.pack()
+        model._graphs.clear()
+    B = int(batch)
+    if B < 1 or B > 255:
+        raise ValueError("batch must be in [1, 255]")
+    on_device = len(frags) > 0 and frags[0][0].is_cuda
+    outs = [None] * len(frags)
+    inflight = []
+    bucket = model.ROW_BUCKET
+
+    def sequential(idx):
+        if on_device:
+            items = [(ME.SparseTensor(frags[i][1], coordinates=frags[i][0]), frags[i][2]) for i in idx]
+            res = [o.F for o in model.forward_many(items, streams=max(2, streams))]
+        else:
+            res = model.forward_many_host([frags[i] for i in idx], streams=max(2, streams), out=None if out is None else [out[i] for i in idx])
+        for i, r in zip(idx, res):
+            outs[i] = r
+
+    def retire():
+        idx, g = inflight.pop(0)
+        try:
+            res = g.finish_batch()
+        except PlanCapacityError:
+            sequential(idx)
+            return
+        for i, r in zip(idx, res):
+            outs[i] = r
+
+    groups = len(frags) // B
+    for gi in range(groups):
+        idx = list(range(gi * B, (gi + 1) * B))
+        sizes = [int(frags[i][0].shape[0]) for i in idx]
+        shapes = {tuple(frags[i][2].shape[-2:]) for i in idx}
+        if min(sizes) == 0 or len(shapes) != 1 or not model.use_cuda_graph:
+            while inflight:
+                retire()
+            sequential(idx)
+            continue
+        H, W = shapes.pop()
+        rows = (sum(sizes) + bucket - 1) // bucket * bucket
+        item_rows = (max(sizes) + bucket - 1) // bucket * bucket
+        key = ("batch", rows, int(H), int(W), B, item_rows)
+        pool = model._graphs.setdefault(key, [])
+        slot = gi % max(1, streams)
+        while len(pool) <= slot:
+            g = BatchGraphPlan(plan, rows, int(H), int(W), B, model._cap8(item_rows, 1))
+            g.stream = torch.cuda.Stream(device=plan.device)
+            pool.append(g)
+        g = pool[slot]
+        while any(e[1] is g for e in inflight):
+            retire()
+        dsts = None
+        if not on_device:
+            dsts = [out[i] if out is not None else torch.empty((sizes[j], model.out_channels), dtype=torch.float32, pin_memory=True)
+                    for j, i in enumerate(idx)]
+        g.launch_batch([(frags[i][0], frags[i][1].float(), frags[i][2].float()) for i in idx], g.stream, out_hosts=dsts)
+        inflight.append((idx, g))
+    while inflight:
+        retire()
+    tail = list(range(groups * B, len(frags)))
+    if tail:
+        sequential(tail)
+    return outs

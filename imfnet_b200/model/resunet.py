@@ -222,6 +222,11 @@ class ResUNet2(ME.MinkowskiNetwork):
             retire()
         return outs
 
+    def forward_batches(self, frags, batch: int, streams: int = 2, out=None):
+        """Throughput form for many fragments: groups of `batch` fragments per captured-graph replay (imfnet_b200/batched.py)."""
+        from ..batched import forward_batches
+        return forward_batches(self, frags, batch, streams, out)
+
     def _forward_graph(self, x, image):
         plan = self._plan
         if plan._key != plan._weights_key():

@@ -103,6 +103,18 @@ int imf_quantize_points(const double* xyz, int32_t n, double voxel_size, int32_t
 int imf_batch_segments(const int32_t* coords, const int32_t* n_dev, int32_t n_max, int32_t num_batches, int32_t* seg,
                        imf_stream_t stream);
 
+/* Device-side form of the per-item split of ResUNet2.transformer (model/resunet.py:240-255) for the batched captured plan
+ * (imfnet_b200/batched.py): seg[0..num_batches] as above, cnt[b] = min(seg[b+1] - seg[b], cap_item).  *err (optional) gets
+ * bit 17 when an item has more than cap_item rows and bit 18 when rows carry a batch index >= num_batches.  num_batches <= 255. */
+int imf_batch_segments_n(const int32_t* coords, const int32_t* n_dev, int32_t n_max, int32_t num_batches, int32_t cap_item,
+                         int32_t* seg, int32_t* cnt, int32_t* err, imf_stream_t stream);
+/* Rows [*seg_b_dev, *seg_b_dev + min(*cnt_b_dev, cap)) of the h2 matrix H <-> fp32 rows 0.. of X (one batch item's tokens:
+ * the `queries_encoder` / result of AttentionFusion.forward, model/resunet.py:262-266).  cap sizes the launch. */
+int imf_h2_unpack_seg(const void* H, int32_t ldh, const int32_t* seg_b_dev, const int32_t* cnt_b_dev, int32_t cap, int32_t C, int32_t KC,
+                      float* X, int32_t ldx, imf_stream_t stream);
+int imf_h2_pack_seg(const float* X, int32_t ldx, const int32_t* seg_b_dev, const int32_t* cnt_b_dev, int32_t cap, int32_t C, int32_t KC,
+                    void* H, int32_t ldh, int32_t* err, imf_stream_t stream);
+
 /* ---- sparse convolution: ME.MinkowskiConvolution(+Transpose).forward (model/resunet.py:168-213,
  *      model/residual_block.py:40,44) with BatchNorm(eval)/residual/ReLU fused ------------------------- */
 
