@@ -18,6 +18,8 @@ LIB = os.path.join(CSRC, "libimfnet_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+# experiment switches of the kernels (e.g. IMFNET_B200_NVCC_FLAGS="-DIMF_G4_SKIP_CLEAN_ZERO" + --force); empty in the shipped build
+FLAGS += os.environ.get("IMFNET_B200_NVCC_FLAGS", "").split()
 
 
 def sources():

@@ -377,6 +377,10 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       int my_ac = ac + first_i;
       uint32_t my_phase = pslot >= a_slot ? a_phase : a_phase ^ 1u;                // phase of slot `pslot` at its next use
       int slot = 0;
+#if defined(IMF_G4_SKIP_CLEAN_ZERO)
+      unsigned dirty = 0xFFFFFFFFu;
+      static_assert(NINS <= 32, "one dirty bit per copy instruction of a lane");
+#endif
       if (it.w < w_end) prefetch(it, 0);
       g4_cp_async_commit();
       g4_cp_async_commit();                                               // (empty) keeps the group arithmetic uniform
@@ -400,9 +404,24 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
             const int4 r = idx4p[m];
             const int r4[4] = {r.x, r.y, r.z, r.w};
             const int srow = half * HROWS + 4 * m;
+#if defined(IMF_G4_SKIP_CLEAN_ZERO)
+            // EXPERIMENT (off in the default build): an absent neighbour only needs its zero fill when the
+            // row of this ring slot still holds data of an earlier stage; `dirty` tracks that per (lane, instruction), so about
+            // half of the zero-fill wavefronts disappear.  Every row counts as dirty at the start of a pass (uninitialised
+            // shared memory / the epilogue's staging buffers live in the ring).
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const unsigned bit = 1u << (4 * i4 + i);
+              if (r4[i] >= 0 || (dirty & bit)) {
+                g4_cp_async16_row(stg + tc::sw128_offset(srow + i, c16), xc + (unsigned long long)((unsigned)max(r4[i], 0)) * ldx_bytes, r4[i]);
+                dirty = r4[i] >= 0 ? (dirty | bit) : (dirty & ~bit);
+              }
+            }
+#else
 #pragma unroll
             for (int i = 0; i < 4; ++i)      // absent neighbour: the (valid) address of row 0 is passed but ignored (zero fill)
               g4_cp_async16_row(stg + tc::sw128_offset(srow + i, c16), xc + (unsigned long long)((unsigned)max(r4[i], 0)) * ldx_bytes, r4[i]);
+#endif
           }
         }
         g4_cp_async_arrive_noinc(&full_a[pslot]);                         // fires when this thread's copies have landed
