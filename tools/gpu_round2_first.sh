@@ -24,6 +24,7 @@ done
 tail -5 $OUT/bench_batched_10_10.err
 # conv-kernel experiment: rebuild with the switch into a scratch copy of the library, run the microbench and the parity checker
 timeout 300 python tools/conv_g4_bench.py > $OUT/conv_g4_default.txt 2>&1; cat $OUT/conv_g4_default.txt
+timeout 300 python tools/conv_g4_bench.py --cin 32 --cout 32 --trace > $OUT/conv_g4_trace_32.txt 2>&1; head -50 $OUT/conv_g4_trace_32.txt
 IMFNET_B200_NVCC_FLAGS="-DIMF_G4_SKIP_CLEAN_ZERO" timeout 300 python -m imfnet_b200.build --force > $OUT/build_exp.log 2>&1; echo "exp build rc=$?"
 timeout 300 python tools/conv_g4_bench.py > $OUT/conv_g4_skip_clean_zero.txt 2>&1; cat $OUT/conv_g4_skip_clean_zero.txt
 timeout 300 python tools/conv_g4_check.py > $OUT/conv_g4_check_skip_clean_zero.txt 2>&1; tail -5 $OUT/conv_g4_check_skip_clean_zero.txt
