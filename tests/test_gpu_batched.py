@@ -66,3 +66,49 @@ def test_batched_plan_rejects_wrong_batch_index_capacity(cuda_model):
         cuda_model._cap8_scale.clear()
     for o, s in zip(outs, singles):
         assert rel_rows(o.cpu(), s) < TOL
+
+
+def test_segment_kernels_unit():
+    """csrc/batched.cu against numpy: segments / clipped counts / error bits, and the per-item h2 <-> fp32 moves."""
+    import numpy as np
+    from imfnet_b200 import _lib
+    L = _lib.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(0)
+    B, cap = 4, 300
+    sizes = [257, 0, 300, 123]
+    coords = np.zeros((sum(sizes) + 50, 4), dtype=np.int32)
+    coords[:sum(sizes), 0] = np.repeat(np.arange(B), sizes)
+    coords[sum(sizes):, 0] = 77                                            # rows past n must not be looked at
+    coords[:, 1:] = rng.integers(-100, 100, (len(coords), 3))
+    c = torch.from_numpy(coords).cuda()
+    n_dev = torch.tensor([sum(sizes)], dtype=torch.int32, device="cuda")
+    seg = torch.full((B + 1,), -1, dtype=torch.int32, device="cuda")
+    cnt = torch.full((B,), -1, dtype=torch.int32, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(L.imf_batch_segments_n(c.data_ptr(), n_dev.data_ptr(), len(coords), B, cap, seg.data_ptr(), cnt.data_ptr(), err.data_ptr(), s))
+    assert seg.tolist() == [0, 257, 257, 557, 680] and cnt.tolist() == sizes and int(err.item()) == 0
+    _lib.check(L.imf_batch_segments_n(c.data_ptr(), n_dev.data_ptr(), len(coords), B, 200, seg.data_ptr(), cnt.data_ptr(), err.data_ptr(), s))
+    assert cnt.tolist() == [200, 0, 200, 123] and int(err.item()) == 0x20000
+    err.zero_()
+    _lib.check(L.imf_batch_segments_n(c.data_ptr(), n_dev.data_ptr(), len(coords), 3, cap, seg.data_ptr(), cnt.data_ptr(), err.data_ptr(), s))
+    assert int(err.item()) == 0x40000                                      # batch index 3 present, plan built for 3 items
+    err.zero_()
+    _lib.check(L.imf_batch_segments_n(c.data_ptr(), n_dev.data_ptr(), len(coords), B, cap, seg.data_ptr(), cnt.data_ptr(), err.data_ptr(), s))
+    # h2 matrix of the level: pack all rows with the verified kernel, pull item 2 out, push a modified copy back
+    C, KC, n = 256, 64, sum(sizes)
+    X = torch.randn(n, C, device="cuda")
+    H = torch.zeros(n, 2 * C, dtype=torch.float16, device="cuda")
+    _lib.check(L.imf_h2_pack(X.data_ptr(), C, n, C, KC, H.data_ptr(), 2 * C, None, s))
+    item = torch.full((cap, C), float("nan"), device="cuda")
+    _lib.check(L.imf_h2_unpack_seg(H.data_ptr(), 2 * C, seg.data_ptr() + 8, cnt.data_ptr() + 8, cap, C, KC, item.data_ptr(), C, s))
+    back = torch.empty(n, C, device="cuda")
+    _lib.check(L.imf_h2_unpack(H.data_ptr(), 2 * C, n, C, KC, back.data_ptr(), C, s))
+    assert torch.equal(item[:300], back[257:557])
+    item2 = item * 2 + 1
+    _lib.check(L.imf_h2_pack_seg(item2.data_ptr(), C, seg.data_ptr() + 8, cnt.data_ptr() + 8, cap, C, KC, H.data_ptr(), 2 * C, err.data_ptr(), s))
+    after = torch.empty(n, C, device="cuda")
+    _lib.check(L.imf_h2_unpack(H.data_ptr(), 2 * C, n, C, KC, after.data_ptr(), C, s))
+    assert torch.equal(after[:257], back[:257]) and torch.equal(after[557:], back[557:])
+    assert float((after[257:557] - item2[:300]).abs().max()) <= 1e-6 * float(item2[:300].abs().max())
+    assert int(err.item()) == 0
