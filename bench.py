@@ -7,7 +7,10 @@
 A step = full ResUNetBN2C.forward(x, image) on --streams (default 10) independent fragments, each through its own captured
 CUDA-graph plan and stream (fragments are independent units; the single-fragment latency is reported in
 config.single_fragment_latency_ms), coordinate maps rebuilt for every fragment (what the reference does for every new
-SparseTensor), inputs already resident in HBM.  Steps rotate over 8 distinct fragments per rank and the L2 is flushed
+SparseTensor), inputs already resident in HBM.  A second execution mode of the same public API -- the batched captured plan,
+`model.forward_batches`, two groups of --streams fragments per step -- is timed as well when a parity probe of it passes in a
+subprocess on this GPU (it must reproduce forward_many's descriptors); the faster mode is the headline and every timed mode is
+listed in config.execution_modes_timed (--batched 0 switches this off).  Steps rotate over 8 distinct fragments per rank and the L2 is flushed
 between steps (a 256 MiB write), outside the per-step CUDA events.  Multi-GPU: fragments are independent, each rank runs
 its own (weak scaling); the only collective is the all-gather of per-rank timings.  One JSON line is printed by rank 0.
 """
@@ -173,6 +176,58 @@ def dominant_kernel_roofline(model, frag, flush):
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r01/call55_g4_ncu_summary.txt)"}
 
 
+def probe_batched(args, local_rank):
+    """Subprocess body of the automatic mode: the batched captured plan must reproduce forward_many fragment by fragment (device and
+    pinned-host inputs) on this GPU before bench.py times it.  Prints one JSON line; any failure is a non-zero exit."""
+    import imfnet_b200.me as ME
+    from imfnet_b200 import load_model, synthetic
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    frags, (target, voxel, W, H) = make_inputs(args.config, 0)
+    model = load_model("ResUNetBN2C")(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3, config=None)
+    model.load_state_dict(synthetic.make_state_dict(0), strict=True)
+    model = model.eval().to(dev)
+    B = max(1, args.streams)
+    sel = [frags[j % N_FRAGMENTS] for j in range(2 * B)]
+    dev_frags = [(c.to(dev), f.to(dev), im.to(dev)) for c, f, im in sel]
+    pin_frags = [(c.pin_memory(), f.pin_memory(), im.pin_memory()) for c, f, im in sel]
+    with torch.no_grad():
+        ref = [o.F for o in model.forward_many([(ME.SparseTensor(f, coordinates=c), im) for c, f, im in dev_frags], streams=B)]
+        worst = 0.0
+        for rep in range(2):          # the second round re-uses the captured plans
+            outs = model.forward_batches(dev_frags, B, streams=2)
+            outs_h = model.forward_batches(pin_frags, B, streams=2)
+            for o, oh, r in zip(outs, outs_h, ref):
+                for x in (o, oh.to(dev)):
+                    if x.shape != r.shape or not bool(torch.isfinite(x).all()):
+                        raise SystemExit("batched probe: bad output")
+                    worst = max(worst, float((torch.linalg.norm(x - r, dim=1) / torch.linalg.norm(r, dim=1)).max()))
+        torch.cuda.synchronize()
+    ok = worst <= 1e-5          # expected 0 (same kernels, same per-row summation order); the parity bar against the oracle is 1e-4
+    print(json.dumps({"batched_probe": "ok" if ok else "mismatch", "B": B, "max_rowwise_rel_diff_vs_forward_many": worst}))
+    if not ok:
+        raise SystemExit(1)
+
+
+def run_batched_probe(args):
+    """(B, note): B = --streams when the probe subprocess reports parity on this rank's GPU, else 0.  A crash, a mismatch or a timeout of
+    the probe only costs time: the default execution mode is timed in any case."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--probe-batched", "--config", args.config, "--streams", str(args.streams)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    except subprocess.TimeoutExpired:
+        return 0, "probe timed out (batched plan not used)"
+    line = next((ln for ln in reversed(r.stdout.splitlines()) if ln.startswith("{")), "")
+    try:
+        d = json.loads(line)
+    except ValueError:
+        d = {}
+    if r.returncode == 0 and d.get("batched_probe") == "ok":
+        return int(d["B"]), f"probe ok on this GPU: max row-wise rel diff vs forward_many = {d['max_rowwise_rel_diff_vs_forward_many']:.1e}"
+    tail = (r.stderr.strip().splitlines() or ["no stderr"])[-1][:200]
+    return 0, f"probe failed (rc {r.returncode}, {d.get('batched_probe', 'no result')}): {tail}"
+
+
 def run_ours(args, rank, world, local_rank):
     import imfnet_b200.me as ME
     from imfnet_b200 import _lib, load_model, synthetic
@@ -197,39 +252,54 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     K = max(1, args.streams)      # independent fragments in flight per step (one captured plan + CUDA stream each)
+    if world > 1:                 # every rank must time the same modes (their barriers are collectives): batched only if all probes passed
+        agree = torch.tensor([args.batched], dtype=torch.int32, device=dev)
+        torch.distributed.all_reduce(agree, op=torch.distributed.ReduceOp.MIN)
+        if int(agree.item()) != args.batched:
+            args.batched_note += "; another rank's probe failed"
+        args.batched = int(agree.item())
+    Bt = max(0, args.batched)     # > 0: the batched captured plan is timed too (groups of Bt fragments per graph replay, two groups per step)
 
-    Bt = max(0, args.batched)     # > 0: groups of Bt fragments per captured-graph replay (imfnet_b200/batched.py), two plans in flight
-    if Bt and K % Bt:
-        raise SystemExit("--streams (fragments per step) must be a multiple of --batched")
+    def make_steps(batch):
+        """(fragments per step, resident step, end-to-end step) of one execution mode: batch = 0 -> K single-fragment plans in
+        flight (forward_many / forward_many_host); batch = B -> two groups of B fragments, one BatchGraphPlan replay each."""
+        kf = 2 * batch if batch else K
+        host_out = torch.empty((target, 32), dtype=torch.float32).pin_memory()
+        host_outs = [torch.empty((target, 32), dtype=torch.float32).pin_memory() for _ in range(kf)]
 
-    def step_resident(i):
-        if Bt:
-            return model.forward_batches([dev_frags[(i * K + j) % N_FRAGMENTS] for j in range(K)], Bt, streams=2)
-        if K == 1:
-            c, f, im = dev_frags[i % N_FRAGMENTS]
-            return model(ME.SparseTensor(f, coordinates=c), im).F
-        items = [(ME.SparseTensor(f, coordinates=c), im) for c, f, im in (dev_frags[(i * K + j) % N_FRAGMENTS] for j in range(K))]
-        return [o.F for o in model.forward_many(items, streams=K)]
+        def pick(frs, i):
+            return [frs[(i * kf + j) % N_FRAGMENTS] for j in range(kf)]
 
-    host_out = torch.empty((target, 32), dtype=torch.float32).pin_memory()
+        def resident(i):
+            if batch:
+                return model.forward_batches(pick(dev_frags, i), batch, streams=2)
+            if K == 1:
+                c, f, im = dev_frags[i % N_FRAGMENTS]
+                return model(ME.SparseTensor(f, coordinates=c), im).F
+            return [o.F for o in model.forward_many([(ME.SparseTensor(f, coordinates=c), im) for c, f, im in pick(dev_frags, i)], streams=K)]
 
-    host_outs = [torch.empty((target, 32), dtype=torch.float32).pin_memory() for _ in range(K)]
+        def e2e(i):
+            if batch:
+                return model.forward_batches(pick(pin_frags, i), batch, streams=2, out=host_outs)
+            if K == 1:
+                c, f, im = pin_frags[i % N_FRAGMENTS]
+                x = ME.SparseTensor(f.to(dev, non_blocking=True), coordinates=c.to(dev, non_blocking=True))
+                out = model(x, im.to(dev, non_blocking=True)).F
+                host_out.copy_(out, non_blocking=True)
+                return out
+            # the public end-to-end call: pinned host fragments in, pinned host descriptors out (copies ride the plans' streams)
+            return model.forward_many_host(pick(pin_frags, i), streams=K, out=host_outs)
 
-    def step_e2e(i):
-        if Bt:
-            return model.forward_batches([pin_frags[(i * K + j) % N_FRAGMENTS] for j in range(K)], Bt, streams=2, out=host_outs)
-        if K == 1:
-            c, f, im = pin_frags[i % N_FRAGMENTS]
-            x = ME.SparseTensor(f.to(dev, non_blocking=True), coordinates=c.to(dev, non_blocking=True))
-            out = model(x, im.to(dev, non_blocking=True)).F
-            host_out.copy_(out, non_blocking=True)
-            return out
-        # the public end-to-end call: pinned host fragments in, pinned host descriptors out (copies ride the plans' streams)
-        return model.forward_many_host([pin_frags[(i * K + j) % N_FRAGMENTS] for j in range(K)], streams=K, out=host_outs)
+        return kf, resident, e2e
 
-    def timed(step_fn, count_launches=False):
-        for i in range(args.warmup):
-            step_fn(i)
+    def timed(step_fn):
+        """Returns (ms, launches, clocks, wall) or None when the mode failed; the barriers are executed either way (N > 1)."""
+        ok = True
+        try:
+            for i in range(args.warmup):
+                step_fn(i)
+        except Exception as ex:      # noqa: BLE001  (only the optional batched mode may fail; the caller re-raises for the default one)
+            ok = ex
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -238,28 +308,40 @@ def run_ours(args, rank, world, local_rank):
         ms = 0.0
         wall0 = time.perf_counter()
         for i in range(args.steps):
-            flush()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            step_fn(args.warmup + i)
-            e1.record()
-            e1.synchronize()
-            ms += e0.elapsed_time(e1)
+            if ok is not True:
+                break
+            try:
+                flush()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step_fn(args.warmup + i)
+                e1.record()
+                e1.synchronize()
+                ms += e0.elapsed_time(e1)
+            except Exception as ex:      # noqa: BLE001
+                ok = ex
         barrier()
         wall = time.perf_counter() - wall0
         launches = L.imf_launch_count() + GraphPlan.replayed_launches - l0
         clocks = sampler.stop()
+        if ok is not True:
+            return ok
         return ms, launches, clocks, wall
 
+    K_seq, step_resident, step_e2e = make_steps(0)
     if args.profile:      # under ncu: just the resident steps, nothing else
         with torch.no_grad():
             for i in range(args.warmup + args.steps):
                 step_resident(i)
             torch.cuda.synchronize()
         return
+    modes = {}
     with torch.no_grad():
-        ms_rank, launches, clocks, wall = timed(step_resident)
-        ms_rank_e2e, _, _, _ = timed(step_e2e)
+        r, r2 = timed(step_resident), timed(step_e2e)
+        for x in (r, r2):
+            if isinstance(x, Exception):
+                raise x
+        modes["single-fragment plans"] = dict(k=K_seq, ms=r[0], launches=r[1], clocks=r[2], wall=r[3], ms_e2e=r2[0])
         roof = dominant_kernel_roofline(model, frags[0], flush) if rank == 0 else None
         # latency of ONE fragment on an otherwise idle GPU (the reference's own usage pattern: scripts/generate_desc.py:65-123)
         lat = []
@@ -289,11 +371,27 @@ def run_ours(args, rank, world, local_rank):
                 lat.append(e0.elapsed_time(e1))
         latency_ll_ms = float(np.median(lat))
         model.low_latency = False
+        # the batched captured plan, timed LAST so that nothing measured above depends on it; any failure leaves the default mode
+        if Bt:
+            try:
+                K_b, b_res, b_e2e = make_steps(Bt)
+                r, r2 = timed(b_res), timed(b_e2e)
+                if isinstance(r, Exception) or isinstance(r2, Exception):
+                    args.batched_note += f"; batched timing failed: {r if isinstance(r, Exception) else r2!r}"[:300]
+                else:
+                    modes["batched plan"] = dict(k=K_b, ms=r[0], launches=r[1], clocks=r[2], wall=r[3], ms_e2e=r2[0])
+            except Exception as ex:      # noqa: BLE001
+                args.batched_note += f"; batched timing failed: {ex!r}"[:300]
+        # headline = the faster execution mode of the public API (by end-to-end throughput); every timed mode is reported in config
+        best = max(modes, key=lambda n: modes[n]["k"] / modes[n]["ms_e2e"])
+        mb = modes[best]
+        K, ms_rank, launches, clocks, wall, ms_rank_e2e = mb["k"], mb["ms"], mb["launches"], mb["clocks"], mb["wall"], mb["ms_e2e"]
 
     # per-rank timing records: the one collective of this path
     from imfnet_b200.pipeline import aggregate_throughput, gather_records
-    rec = torch.tensor([rank, target * args.steps * K, ms_rank], dtype=torch.float64, device=dev)
-    rec_e2e = torch.tensor([rank, target * args.steps * K, ms_rank_e2e], dtype=torch.float64, device=dev)
+    rec_dev = dev if world > 1 else "cpu"
+    rec = torch.tensor([rank, target * args.steps * K, ms_rank], dtype=torch.float64, device=rec_dev)
+    rec_e2e = torch.tensor([rank, target * args.steps * K, ms_rank_e2e], dtype=torch.float64, device=rec_dev)
     allrec, allrec_e2e = gather_records(rec, world), gather_records(rec_e2e, world)
     if rank != 0:
         return
@@ -322,17 +420,21 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {target}-voxel synthetic 3DMatch fragment + {W}x{H} image, ResUNetBN2C 32-D descriptors",
-                   "fragments_per_step": K, "streams": K, "single_fragment_latency_ms": latency_ms,
+                   "fragments_per_step": K, "streams": 2 if best == "batched plan" else K, "single_fragment_latency_ms": latency_ms,
                    "single_fragment_latency_ms_low_latency_setting": latency_ll_ms,
                    "small_level_splits": "off (model.low_latency=False: throughput setting, used for value and e2e)",
                    "distinct_fragments_per_rank": N_FRAGMENTS,
                    "l2": "flushed between steps (256 MiB write, outside the per-step CUDA events)",
                    "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
                    "coordinate_maps": "rebuilt every step (cold), as the reference does per SparseTensor",
-                   "execution": (f"one captured CUDA graph replay per batch of {Bt} fragments (device-side sizes), {K // Bt} batches per step, 2 plans in flight"
-                                 if Bt else
+                   "execution": (f"one captured CUDA graph replay per batch of {Bt} fragments (device-side sizes), 2 batches per step, 2 plans in flight"
+                                 if best == "batched plan" else
                                  f"one captured CUDA graph replay per fragment (device-side sizes), {K} independent fragments in flight on {K} streams"
                                  if model.use_cuda_graph else "eager launches"),
+                   "execution_modes_timed": {n: {"fragments_per_step": m["k"], "voxels_per_s": target * args.steps * m["k"] / (m["ms"] * 1e-3),
+                                                 "voxels_per_s_e2e": target * args.steps * m["k"] / (m["ms_e2e"] * 1e-3)}
+                                             for n, m in modes.items()},
+                   "batched_plan": args.batched_note,
                    "parallelism": f"fragments sharded over {world} GPU(s), no data-path collective"},
         "e2e": {"value": e2e_v, "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
@@ -349,8 +451,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--streams", type=int, default=10, help="independent fragments in flight per step (captured plan + stream each)")
-    ap.add_argument("--batched", type=int, default=0,
-                    help="B > 0: run the step's fragments in groups of B through the batched captured plan (imfnet_b200/batched.py)")
+    ap.add_argument("--batched", type=int, default=-1,
+                    help="B > 0: also time the batched captured plan (imfnet_b200/batched.py: groups of B fragments per graph replay) and "
+                         "report the faster mode; 0: off; -1 (default): B = --streams if a parity probe of that path passes in a "
+                         "subprocess on this GPU, else off")
+    ap.add_argument("--probe-batched", action="store_true", help="(internal) parity probe of the batched plan; prints one JSON line")
     ap.add_argument("--profile", action="store_true", help="run only warm-up + steps (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "ours" and not args.profile:
@@ -361,6 +466,14 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.probe_batched:
+        probe_batched(args, local_rank)
+        return
+    args.batched_note = "off"
+    if args.batched > 0:
+        args.batched_note = f"forced (--batched {args.batched})"
+    elif args.batched < 0 and not args.profile:
+        args.batched, args.batched_note = run_batched_probe(args)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL may print its version banner on stdout while the communicator is created; stdout must carry exactly one JSON line,

@@ -1,0 +1,83 @@
+"""CPU: bench.py's measurement logic (execution modes, fallback when the batched plan fails, JSON contract) run end to end on the
+C-ABI emulator with inert torch.cuda objects.  The numbers are meaningless (every "CUDA event" reports 1 ms); the keys, the
+mode selection and the bookkeeping are what is checked."""
+import contextlib
+import importlib.util
+import io
+import json
+import os
+import types
+
+import pytest
+import torch
+
+from imfnet_b200 import synthetic
+
+from test_plan_emulated import emu  # noqa: F401  (fixture)
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture
+def bench(emu, monkeypatch):  # noqa: F811
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    from test_plan_plumbing import FakeEvent
+
+    class Ev(FakeEvent):
+        def elapsed_time(self, other):
+            return 1.0
+
+    real_device, real_empty = torch.device, torch.empty
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch, "device", lambda *a, **k: real_device("cpu"))
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{n: v for n, v in k.items() if n != "pin_memory"}))
+    monkeypatch.setitem(synthetic.CONFIGS, "T", (400, 0.05, 64, 48))
+    monkeypatch.setattr(b, "N_FRAGMENTS", 3)
+    monkeypatch.setattr(b, "dominant_kernel_roofline", lambda model, frag, flush: {"bound": "hbm", "frac": 0.0})
+    return b
+
+
+def run(b, **over):
+    args = types.SimpleNamespace(config="T", streams=2, batched=2, steps=1, warmup=1, profile=False, gpus=1, batched_note="forced")
+    for k, v in over.items():
+        setattr(args, k, v)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        b.run_ours(args, 0, 1, 0)
+    lines = buf.getvalue().strip().splitlines()
+    assert len(lines) == 1, "bench must print exactly one line"
+    return json.loads(lines[0])
+
+
+def test_bench_times_both_modes_and_reports_the_faster(bench):
+    d = run(bench)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in d, key
+    modes = d["config"]["execution_modes_timed"]
+    assert set(modes) == {"single-fragment plans", "batched plan"}
+    assert modes["batched plan"]["fragments_per_step"] == 4 and modes["single-fragment plans"]["fragments_per_step"] == 2
+    assert d["config"]["fragments_per_step"] == 4 and "per batch of 2 fragments" in d["config"]["execution"]      # 4 fragments per fake ms wins
+    assert d["e2e"]["h2d_bytes_per_step"] == 4 * (400 * 16 + 400 * 4 + 3 * 48 * 64 * 4) and d["e2e"]["d2h_bytes_per_step"] == 4 * 400 * 32 * 4
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+
+
+def test_bench_falls_back_when_the_batched_plan_fails(bench, monkeypatch):
+    import imfnet_b200.batched as batched
+
+    def boom(self, *a, **k):
+        raise RuntimeError("injected failure")
+
+    monkeypatch.setattr(batched.BatchGraphPlan, "launch_batch", boom)
+    d = run(bench)
+    assert set(d["config"]["execution_modes_timed"]) == {"single-fragment plans"}
+    assert "injected failure" in d["config"]["batched_plan"] and d["config"]["fragments_per_step"] == 2
+    assert "per fragment" in d["config"]["execution"]
+
+
+def test_bench_without_batched_mode(bench):
+    d = run(bench, batched=0, batched_note="off")
+    assert set(d["config"]["execution_modes_timed"]) == {"single-fragment plans"} and d["config"]["batched_plan"] == "off"

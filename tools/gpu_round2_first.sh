@@ -9,19 +9,22 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
 timeout 400 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log; tail -3 $OUT/pytest_gpu.log
 IMFNET_B200_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_batched.py -m gpu -x -q -s > $OUT/pytest_batched.log 2>&1; echo "batched rc=$?" | tee -a $OUT/pytest_batched.log; tail -15 $OUT/pytest_batched.log
-timeout 300 python bench.py --steps 20 > $OUT/bench_default.json 2> $OUT/bench_default.err; echo "bench default rc=$?"; cut -c1-400 $OUT/bench_default.json
-for cfg in "10 10" "20 10" "20 5" "16 8"; do set -- $cfg
-  timeout 300 python bench.py --steps 20 --streams $1 --batched $2 > $OUT/bench_batched_$1_$2.json 2> $OUT/bench_batched_$1_$2.err; echo "bench --streams $1 --batched $2 rc=$?"
-  python - $OUT/bench_batched_$1_$2.json <<'PY'
+timeout 600 python bench.py --steps 20 > $OUT/bench_default.json 2> $OUT/bench_default.err; echo "bench (auto probe) rc=$?"; cut -c1-400 $OUT/bench_default.json
+timeout 300 python bench.py --probe-batched > $OUT/probe.json 2> $OUT/probe.err; echo "probe rc=$?"; cat $OUT/probe.json; tail -5 $OUT/probe.err
+for B in 5 8 10 16; do
+  timeout 300 python bench.py --steps 20 --batched $B > $OUT/bench_batched_$B.json 2> $OUT/bench_batched_$B.err; echo "bench --batched $B rc=$?"
+  python - $OUT/bench_batched_$B.json <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read())
-    print("  value %.1f M voxels/s, e2e %.1f M, %.2f ms/step" % (d["value"] / 1e6, d["e2e"]["value"] / 1e6, d["ms_per_step"]))
+    for n, m in d["config"]["execution_modes_timed"].items():
+        print("  %-22s %2d fragments/step: %.1f M voxels/s resident, %.1f M end to end" % (n, m["fragments_per_step"], m["voxels_per_s"] / 1e6, m["voxels_per_s_e2e"] / 1e6))
+    print("  note:", d["config"]["batched_plan"])
 except Exception as e:
     print("  no result:", e)
 PY
 done
-tail -5 $OUT/bench_batched_10_10.err
+tail -5 $OUT/bench_batched_10.err
 # conv-kernel experiment: rebuild with the switch into a scratch copy of the library, run the microbench and the parity checker
 timeout 300 python tools/conv_g4_bench.py > $OUT/conv_g4_default.txt 2>&1; cat $OUT/conv_g4_default.txt
 timeout 300 python tools/conv_g4_bench.py --cin 32 --cout 32 --trace > $OUT/conv_g4_trace_32.txt 2>&1; head -50 $OUT/conv_g4_trace_32.txt
@@ -29,6 +32,6 @@ IMFNET_B200_NVCC_FLAGS="-DIMF_G4_SKIP_CLEAN_ZERO" timeout 300 python -m imfnet_b
 timeout 300 python tools/conv_g4_bench.py > $OUT/conv_g4_skip_clean_zero.txt 2>&1; cat $OUT/conv_g4_skip_clean_zero.txt
 timeout 300 python tools/conv_g4_check.py > $OUT/conv_g4_check_skip_clean_zero.txt 2>&1; tail -5 $OUT/conv_g4_check_skip_clean_zero.txt
 timeout 400 python -m pytest tests/test_gpu_conv.py -m gpu -x -q > $OUT/pytest_conv_exp.log 2>&1; echo "conv tests (experiment build) rc=$?"; tail -3 $OUT/pytest_conv_exp.log
-timeout 300 python bench.py --steps 20 > $OUT/bench_exp.json 2> $OUT/bench_exp.err; echo "bench (experiment build) rc=$?"; cut -c1-200 $OUT/bench_exp.json
+timeout 300 python bench.py --steps 20 --batched 0 > $OUT/bench_exp.json 2> $OUT/bench_exp.err; echo "bench (experiment build) rc=$?"; cut -c1-200 $OUT/bench_exp.json
 timeout 300 python -m imfnet_b200.build --force > /dev/null 2>&1      # back to the default build
 ls -la $OUT
