@@ -10,7 +10,9 @@ config.single_fragment_latency_ms), coordinate maps rebuilt for every fragment (
 SparseTensor), inputs already resident in HBM.  A second execution mode of the same public API -- the batched captured plan,
 `model.forward_batches`, two groups of --streams fragments per step -- is timed as well when a parity probe of it passes in a
 subprocess on this GPU (it must reproduce forward_many's descriptors); the faster mode is the headline and every timed mode is
-listed in config.execution_modes_timed (--batched 0 switches this off).  Steps rotate over 8 distinct fragments per rank and the L2 is flushed
+listed in config.execution_modes_timed (--batched 0 switches this off).  The same probes decide whether the kernel variant library
+(imfnet_b200/build.py VARIANTS: same sources, two experiment switches on the convolution kernel) is loaded instead of the default one:
+only when its descriptors are bit-identical and its step is shorter (config.mode_selection, config.library).  Steps rotate over 8 distinct fragments per rank and the L2 is flushed
 between steps (a 256 MiB write), outside the per-step CUDA events.  Multi-GPU: fragments are independent, each rank runs
 its own (weak scaling); the only collective is the all-gather of per-rank timings.  One JSON line is printed by rank 0.
 """
@@ -177,8 +179,12 @@ def dominant_kernel_roofline(model, frag, flush):
 
 
 def probe_batched(args, local_rank):
-    """Subprocess body of the automatic mode: the batched captured plan must reproduce forward_many fragment by fragment (device and
-    pinned-host inputs) on this GPU before bench.py times it.  Prints one JSON line; any failure is a non-zero exit."""
+    """Subprocess body of the automatic mode selection (runs with the library variant named by IMFNET_B200_VARIANT, default
+    none).  Prints one JSON line with
+      * sha256 of the descriptors forward_many gives for the distinct fragments (the parent compares variants bit for bit),
+      * a short timing of the default execution mode (the parent only switches to a variant that is faster),
+      * whether the batched captured plan reproduces forward_many fragment by fragment (device and pinned-host inputs)."""
+    import hashlib
     import imfnet_b200.me as ME
     from imfnet_b200 import load_model, synthetic
     torch.cuda.set_device(local_rank)
@@ -191,41 +197,89 @@ def probe_batched(args, local_rank):
     sel = [frags[j % N_FRAGMENTS] for j in range(2 * B)]
     dev_frags = [(c.to(dev), f.to(dev), im.to(dev)) for c, f, im in sel]
     pin_frags = [(c.pin_memory(), f.pin_memory(), im.pin_memory()) for c, f, im in sel]
+    out = {"probe": "done", "variant": os.environ.get("IMFNET_B200_VARIANT", ""), "B": B}
     with torch.no_grad():
-        ref = [o.F for o in model.forward_many([(ME.SparseTensor(f, coordinates=c), im) for c, f, im in dev_frags], streams=B)]
-        worst = 0.0
-        for rep in range(2):          # the second round re-uses the captured plans
-            outs = model.forward_batches(dev_frags, B, streams=2)
-            outs_h = model.forward_batches(pin_frags, B, streams=2)
-            for o, oh, r in zip(outs, outs_h, ref):
-                for x in (o, oh.to(dev)):
-                    if x.shape != r.shape or not bool(torch.isfinite(x).all()):
-                        raise SystemExit("batched probe: bad output")
-                    worst = max(worst, float((torch.linalg.norm(x - r, dim=1) / torch.linalg.norm(r, dim=1)).max()))
-        torch.cuda.synchronize()
-    ok = worst <= 1e-5          # expected 0 (same kernels, same per-row summation order); the parity bar against the oracle is 1e-4
-    print(json.dumps({"batched_probe": "ok" if ok else "mismatch", "B": B, "max_rowwise_rel_diff_vs_forward_many": worst}))
-    if not ok:
-        raise SystemExit(1)
+        items = [(ME.SparseTensor(f, coordinates=c), im) for c, f, im in dev_frags]
+        ref = [o.F for o in model.forward_many(items, streams=B)]
+        if not all(bool(torch.isfinite(r).all()) for r in ref):
+            raise SystemExit("probe: non-finite descriptors")
+        out["hashes"] = [hashlib.sha256(r.cpu().numpy().tobytes()).hexdigest() for r in ref[:N_FRAGMENTS]]
+        ts = []
+        for i in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model.forward_many(items[:B], streams=B)
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        out["seq_ms_per_step"] = float(np.median(ts[3:]))
+        try:
+            worst = 0.0
+            for rep in range(2):          # the second round re-uses the captured plans
+                outs = model.forward_batches(dev_frags, B, streams=2)
+                outs_h = model.forward_batches(pin_frags, B, streams=2)
+                for o, oh, r in zip(outs, outs_h, ref):
+                    for x in (o, oh.to(dev)):
+                        if x.shape != r.shape or not bool(torch.isfinite(x).all()):
+                            raise RuntimeError("bad output")
+                        worst = max(worst, float((torch.linalg.norm(x - r, dim=1) / torch.linalg.norm(r, dim=1)).max()))
+            torch.cuda.synchronize()
+            # expected 0 (same kernels, same per-row summation order); the parity bar against the oracle is 1e-4
+            out["batched"] = "ok" if worst <= 1e-5 else "mismatch"
+            out["max_rowwise_rel_diff_vs_forward_many"] = worst
+        except Exception as ex:      # noqa: BLE001
+            out["batched"] = f"failed: {ex!r}"[:200]
+    print(json.dumps(out))
 
 
-def run_batched_probe(args):
-    """(B, note): B = --streams when the probe subprocess reports parity on this rank's GPU, else 0.  A crash, a mismatch or a timeout of
-    the probe only costs time: the default execution mode is timed in any case."""
+def run_probe(args, variant=""):
+    """One probe subprocess -> (dict or None, note)."""
     cmd = [sys.executable, os.path.abspath(__file__), "--probe-batched", "--config", args.config, "--streams", str(args.streams)]
+    env = dict(os.environ)
+    env.pop("IMFNET_B200_VARIANT", None)
+    if variant:
+        env["IMFNET_B200_VARIANT"] = variant
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     except subprocess.TimeoutExpired:
-        return 0, "probe timed out (batched plan not used)"
+        return None, "probe timed out"
     line = next((ln for ln in reversed(r.stdout.splitlines()) if ln.startswith("{")), "")
     try:
         d = json.loads(line)
     except ValueError:
         d = {}
-    if r.returncode == 0 and d.get("batched_probe") == "ok":
-        return int(d["B"]), f"probe ok on this GPU: max row-wise rel diff vs forward_many = {d['max_rowwise_rel_diff_vs_forward_many']:.1e}"
+    if r.returncode == 0 and d.get("probe") == "done":
+        return d, "ok"
     tail = (r.stderr.strip().splitlines() or ["no stderr"])[-1][:200]
-    return 0, f"probe failed (rc {r.returncode}, {d.get('batched_probe', 'no result')}): {tail}"
+    return None, f"probe failed (rc {r.returncode}): {tail}"
+
+
+def select_modes(args):
+    """Automatic mode (--batched -1): decide, from subprocess probes on the GPU this rank is about to measure,
+      * whether to load the kernel variant library "x" (imfnet_b200/build.py VARIANTS): only if its descriptors are bit-identical
+        to the default library's and its step is shorter;
+      * whether to time the batched captured plan as a second execution mode: only if it reproduces forward_many.
+    Any failure of a probe only costs time: the default library and execution mode are what is measured then.
+    Returns (batched B or 0, note)."""
+    d0, n0 = run_probe(args)
+    if d0 is None:
+        return 0, f"default library: {n0} (batched plan and kernel variant not used)"
+    chosen, note = d0, ""
+    if os.environ.get("IMFNET_B200_VARIANT", "") == "" and args.variant_probe:
+        dx, nx = run_probe(args, "x")
+        if dx is None:
+            note = f"kernel variant x: {nx}; "
+        elif dx["hashes"] != d0["hashes"]:
+            note = "kernel variant x: descriptors differ from the default library (not used); "
+        elif dx["seq_ms_per_step"] >= 0.98 * d0["seq_ms_per_step"]:
+            note = f"kernel variant x: bit-identical, not faster ({dx['seq_ms_per_step']:.2f} vs {d0['seq_ms_per_step']:.2f} ms, not used); "
+        else:
+            note = f"kernel variant x in use: bit-identical descriptors, {dx['seq_ms_per_step']:.2f} vs {d0['seq_ms_per_step']:.2f} ms per step; "
+            os.environ["IMFNET_B200_VARIANT"] = "x"
+            chosen = dx
+    if chosen.get("batched") == "ok":
+        return int(chosen["B"]), note + f"batched plan: probe ok on this GPU (max row-wise rel diff vs forward_many {chosen['max_rowwise_rel_diff_vs_forward_many']:.1e})"
+    return 0, note + f"batched plan: probe {chosen.get('batched', 'no result')} (not used)"
 
 
 def run_ours(args, rank, world, local_rank):
@@ -434,7 +488,8 @@ def run_ours(args, rank, world, local_rank):
                    "execution_modes_timed": {n: {"fragments_per_step": m["k"], "voxels_per_s": target * args.steps * m["k"] / (m["ms"] * 1e-3),
                                                  "voxels_per_s_e2e": target * args.steps * m["k"] / (m["ms_e2e"] * 1e-3)}
                                              for n, m in modes.items()},
-                   "batched_plan": args.batched_note,
+                   "mode_selection": args.batched_note,
+                   "library": os.path.basename(_lib.lib_path()),
                    "parallelism": f"fragments sharded over {world} GPU(s), no data-path collective"},
         "e2e": {"value": e2e_v, "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
@@ -455,7 +510,9 @@ def main():
                     help="B > 0: also time the batched captured plan (imfnet_b200/batched.py: groups of B fragments per graph replay) and "
                          "report the faster mode; 0: off; -1 (default): B = --streams if a parity probe of that path passes in a "
                          "subprocess on this GPU, else off")
-    ap.add_argument("--probe-batched", action="store_true", help="(internal) parity probe of the batched plan; prints one JSON line")
+    ap.add_argument("--probe-batched", action="store_true", help="(internal) probe subprocess of the automatic mode; prints one JSON line")
+    ap.add_argument("--no-variant-probe", dest="variant_probe", action="store_false",
+                    help="automatic mode: do not try the kernel variant library (imfnet_b200/build.py VARIANTS)")
     ap.add_argument("--profile", action="store_true", help="run only warm-up + steps (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "ours" and not args.profile:
@@ -473,7 +530,7 @@ def main():
     if args.batched > 0:
         args.batched_note = f"forced (--batched {args.batched})"
     elif args.batched < 0 and not args.profile:
-        args.batched, args.batched_note = run_batched_probe(args)
+        args.batched, args.batched_note = select_modes(args)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL may print its version banner on stdout while the communicator is created; stdout must carry exactly one JSON line,

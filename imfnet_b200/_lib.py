@@ -10,6 +10,13 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libimfnet_b200.so")
 
+
+def lib_path() -> str:
+    """IMFNET_B200_VARIANT=<name> (read when the library is first loaded) selects a kernel variant built by imfnet_b200/build.py
+    (same sources, experiment switches on some kernels); unset = the default library."""
+    v = os.environ.get("IMFNET_B200_VARIANT", "")
+    return os.path.join(_HERE, "csrc", f"libimfnet_b200_{v}.so") if v else LIB_PATH
+
 _p, _i32, _i64, _sz, _f32, _f64 = C.c_void_p, C.c_int32, C.c_longlong, C.c_size_t, C.c_float, C.c_double
 
 
@@ -92,10 +99,11 @@ def lib():
     """The loaded library.  Raises if it has not been built (python -m imfnet_b200.build)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m imfnet_b200.build` "
+        path = lib_path()
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: build it with `python -m imfnet_b200.build` "
                                "(the CUDA extension is required; there is no CPU fallback)")
-        l = C.CDLL(LIB_PATH)
+        l = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args

@@ -22,6 +22,16 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxe
 FLAGS += os.environ.get("IMFNET_B200_NVCC_FLAGS", "").split()
 
 
+# Kernel variants: the same sources with experiment switches on some files, linked into libimfnet_b200_<name>.so next to the default
+# library (all other objects are shared).  Selected at load time by IMFNET_B200_VARIANT=<name> (imfnet_b200/_lib.py); bench.py only
+# does so after a subprocess probe showed bit-identical descriptors and a shorter step on the GPU at hand.
+VARIANTS = {"x": {"sparse_conv_g4.cu": ["-DIMF_G4_LEAN_PRODUCER", "-DIMF_G4_SKIP_CLEAN_ZERO"]}}
+
+
+def lib_path(variant: str = "") -> str:
+    return LIB if not variant else os.path.join(CSRC, f"libimfnet_b200_{variant}.so")
+
+
 def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -42,11 +52,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(CSRC, src[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            jobs.append((s, o))
+            jobs.append((s, o, []))
+    variant_objs = {}
+    for name, switches in VARIANTS.items():
+        vobjs = []
+        for src in sources():
+            o = os.path.join(CSRC, src[:-3] + ".o")
+            if src in switches:
+                s = os.path.join(CSRC, src)
+                o = os.path.join(CSRC, f"{src[:-3]}_{name}.o")
+                if force or _stale(o, [s] + headers):
+                    jobs.append((s, o, switches[src]))
+            vobjs.append(o)
+        variant_objs[name] = vobjs
 
     def compile_one(job):
-        s, o = job
-        cmd = [NVCC] + ARCH + FLAGS + ["-I", CSRC, "-I", os.path.join(HERE, "..", "include"), "-c", s, "-o", o]
+        s, o, extra = job
+        cmd = [NVCC] + ARCH + FLAGS + extra + ["-I", CSRC, "-I", os.path.join(HERE, "..", "include"), "-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return s, r
 
@@ -56,12 +78,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 sys.stderr.write(f"--- {os.path.basename(s)} ---\n{r.stdout}{r.stderr}\n")
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {s}")
-    if jobs or force or _stale(LIB, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("link failed")
+    for target, tobjs in [(LIB, objs)] + [(lib_path(n), o) for n, o in variant_objs.items()]:
+        if jobs or force or _stale(target, tobjs):
+            cmd = [NVCC] + ARCH + ["-shared", "-o", target] + tobjs
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("link failed")
     return LIB
 
 

@@ -381,6 +381,22 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       unsigned dirty = 0xFFFFFFFFu;
       static_assert(NINS <= 32, "one dirty bit per copy instruction of a lane");
 #endif
+#if defined(IMF_G4_LEAN_PRODUCER)
+      // EXPERIMENT (off in the default build): the default build spends ~12 ALU instructions per LDGSTS
+      // (swizzled shared address recomputed per copy, 64-bit base + chunk offset added per copy).  Row srow + i of instruction
+      // group i4 is half*HROWS + 4*RPI*i4 + q with q = 4*hw + i, so its swizzled offset is i4 * (RPI/2) * 1024 + a per-lane
+      // constant: four destination registers per lane, the i4 term an immediate of the fully unrolled loop.
+      uint32_t dstq[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dstq[i] = ring_base + pslot * Cfg::A_BYTES + tc::sw128_offset(half * HROWS + 4 * hw + i, c16);
+#define G4_DST(i4, i) (dstq[i] + (uint32_t)((i4) * (RPI / 2) * 1024))
+#define G4_SRC(r) reinterpret_cast<const char*>(xb + (unsigned long long)((unsigned)max((r), 0)) * ldx_bytes)
+#define G4_COPY_UNROLL _Pragma("unroll")
+#else
+#define G4_DST(i4, i) (stg + tc::sw128_offset(srow + (i), c16))
+#define G4_SRC(r) (xc + (unsigned long long)((unsigned)max((r), 0)) * ldx_bytes)
+#define G4_COPY_UNROLL _Pragma("unroll 4")
+#endif
       if (it.w < w_end) prefetch(it, 0);
       g4_cp_async_commit();
       g4_cp_async_commit();                                               // (empty) keeps the group arithmetic uniform
@@ -397,8 +413,12 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
         const uint32_t stg = ring_base + pslot * Cfg::A_BYTES;
         const char* xc = xthr + it.chunk * (4 * KC);
         const int4* idx4p = reinterpret_cast<const int4*>(my_idx + slot * HROWS);
+#if defined(IMF_G4_LEAN_PRODUCER)
+        unsigned long long xb = reinterpret_cast<unsigned long long>(xc);
+        asm volatile("" : "+l"(xb));        // keep base + chunk offset in one register pair (one IMAD.WIDE per copy)
+#endif
         if (!(dbg & 2)) {
-#pragma unroll 4
+          G4_COPY_UNROLL
           for (int i4 = 0; i4 < NINS / 4; ++i4) {
             const int m = RPI * i4 + hw;                                  // row group (of this warp's half) for these 4 instructions
             const int4 r = idx4p[m];
@@ -413,17 +433,21 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
             for (int i = 0; i < 4; ++i) {
               const unsigned bit = 1u << (4 * i4 + i);
               if (r4[i] >= 0 || (dirty & bit)) {
-                g4_cp_async16_row(stg + tc::sw128_offset(srow + i, c16), xc + (unsigned long long)((unsigned)max(r4[i], 0)) * ldx_bytes, r4[i]);
+                g4_cp_async16_row(G4_DST(i4, i), G4_SRC(r4[i]), r4[i]);
                 dirty = r4[i] >= 0 ? (dirty | bit) : (dirty & ~bit);
               }
             }
 #else
 #pragma unroll
             for (int i = 0; i < 4; ++i)      // absent neighbour: the (valid) address of row 0 is passed but ignored (zero fill)
-              g4_cp_async16_row(stg + tc::sw128_offset(srow + i, c16), xc + (unsigned long long)((unsigned)max(r4[i], 0)) * ldx_bytes, r4[i]);
+              g4_cp_async16_row(G4_DST(i4, i), G4_SRC(r4[i]), r4[i]);
 #endif
+            (void)srow;
           }
         }
+#undef G4_DST
+#undef G4_SRC
+#undef G4_COPY_UNROLL
         g4_cp_async_arrive_noinc(&full_a[pslot]);                         // fires when this thread's copies have landed
         g4_cp_async_commit();
         my_ac += NA;

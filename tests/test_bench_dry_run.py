@@ -74,10 +74,47 @@ def test_bench_falls_back_when_the_batched_plan_fails(bench, monkeypatch):
     monkeypatch.setattr(batched.BatchGraphPlan, "launch_batch", boom)
     d = run(bench)
     assert set(d["config"]["execution_modes_timed"]) == {"single-fragment plans"}
-    assert "injected failure" in d["config"]["batched_plan"] and d["config"]["fragments_per_step"] == 2
+    assert "injected failure" in d["config"]["mode_selection"] and d["config"]["fragments_per_step"] == 2
     assert "per fragment" in d["config"]["execution"]
 
 
 def test_bench_without_batched_mode(bench):
     d = run(bench, batched=0, batched_note="off")
-    assert set(d["config"]["execution_modes_timed"]) == {"single-fragment plans"} and d["config"]["batched_plan"] == "off"
+    assert set(d["config"]["execution_modes_timed"]) == {"single-fragment plans"} and d["config"]["mode_selection"] == "off"
+
+
+def test_mode_selection_logic(bench, monkeypatch):
+    """select_modes(): the variant library is only chosen when bit-identical and faster; the batched plan only when its probe passed."""
+    import os
+    ok = {"probe": "done", "B": 10, "hashes": ["a", "b"], "seq_ms_per_step": 10.0, "batched": "ok", "max_rowwise_rel_diff_vs_forward_many": 0.0}
+
+    def with_probes(default, variant):
+        calls = []
+
+        def fake(args, v=""):
+            calls.append(v)
+            d = variant if v else default
+            return (dict(d), "ok") if d is not None else (None, "probe failed (rc 1): boom")
+
+        monkeypatch.setattr(bench, "run_probe", fake)
+        monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
+        args = types.SimpleNamespace(config="T", streams=10, variant_probe=True)
+        res = bench.select_modes(args)
+        chosen = os.environ.get("IMFNET_B200_VARIANT", "")
+        monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
+        return res, chosen, calls
+
+    (B, note), var, calls = with_probes(ok, dict(ok, seq_ms_per_step=8.0))
+    assert B == 10 and var == "x" and "in use" in note and calls == ["", "x"]
+    (B, note), var, _ = with_probes(ok, dict(ok, seq_ms_per_step=9.9))
+    assert B == 10 and var == "" and "not faster" in note
+    (B, note), var, _ = with_probes(ok, dict(ok, hashes=["a", "c"], seq_ms_per_step=5.0))
+    assert B == 10 and var == "" and "differ" in note
+    (B, note), var, _ = with_probes(ok, None)
+    assert B == 10 and var == "" and "probe failed" in note
+    (B, note), var, _ = with_probes(dict(ok, batched="mismatch"), dict(ok, seq_ms_per_step=8.0))
+    assert B == 10 and var == "x"                                  # the variant's own batched probe passed
+    (B, note), var, _ = with_probes(dict(ok, batched="failed: x"), dict(ok, seq_ms_per_step=20.0, batched="failed: x"))
+    assert B == 0 and var == "" and "not used" in note
+    (B, note), var, calls = with_probes(None, ok)
+    assert B == 0 and var == "" and calls == [""]

@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of the next round: verify what was written without GPU access at the end of round 1, in ONE gpurun call.
 #   1. the regular GPU suite (must stay green), 2. the gated tests of the batched captured plan, 3. bench: default vs --batched,
-#   4. the compile-time experiment of the convolution kernel (zero fill skipped for clean rows) on the conv microbench + parity check.
+#   4. the kernel variant library x (lean producer addressing, zero fill skipped for clean rows): conv microbench, parity, GPU tests.
 # Usage (repo root on the box): bash tools/gpu_round2_first.sh <tag>
 TAG=${1:-r02_first}
 OUT=gpurun_out/$TAG
@@ -19,7 +19,7 @@ try:
     d = json.loads(open(sys.argv[1]).read())
     for n, m in d["config"]["execution_modes_timed"].items():
         print("  %-22s %2d fragments/step: %.1f M voxels/s resident, %.1f M end to end" % (n, m["fragments_per_step"], m["voxels_per_s"] / 1e6, m["voxels_per_s_e2e"] / 1e6))
-    print("  note:", d["config"]["batched_plan"])
+    print("  note:", d["config"]["mode_selection"])
 except Exception as e:
     print("  no result:", e)
 PY
@@ -28,10 +28,11 @@ tail -5 $OUT/bench_batched_10.err
 # conv-kernel experiment: rebuild with the switch into a scratch copy of the library, run the microbench and the parity checker
 timeout 300 python tools/conv_g4_bench.py > $OUT/conv_g4_default.txt 2>&1; cat $OUT/conv_g4_default.txt
 timeout 300 python tools/conv_g4_bench.py --cin 32 --cout 32 --trace > $OUT/conv_g4_trace_32.txt 2>&1; head -50 $OUT/conv_g4_trace_32.txt
-IMFNET_B200_NVCC_FLAGS="-DIMF_G4_SKIP_CLEAN_ZERO" timeout 300 python -m imfnet_b200.build --force > $OUT/build_exp.log 2>&1; echo "exp build rc=$?"
-timeout 300 python tools/conv_g4_bench.py > $OUT/conv_g4_skip_clean_zero.txt 2>&1; cat $OUT/conv_g4_skip_clean_zero.txt
-timeout 300 python tools/conv_g4_check.py > $OUT/conv_g4_check_skip_clean_zero.txt 2>&1; tail -5 $OUT/conv_g4_check_skip_clean_zero.txt
-timeout 400 python -m pytest tests/test_gpu_conv.py -m gpu -x -q > $OUT/pytest_conv_exp.log 2>&1; echo "conv tests (experiment build) rc=$?"; tail -3 $OUT/pytest_conv_exp.log
-timeout 300 python bench.py --steps 20 --batched 0 > $OUT/bench_exp.json 2> $OUT/bench_exp.err; echo "bench (experiment build) rc=$?"; cut -c1-200 $OUT/bench_exp.json
-timeout 300 python -m imfnet_b200.build --force > /dev/null 2>&1      # back to the default build
+export IMFNET_B200_VARIANT=x      # libimfnet_b200_x.so: lean producer addressing + zero fill skipped for clean rows
+timeout 300 python tools/conv_g4_bench.py > $OUT/conv_g4_variant_x.txt 2>&1; cat $OUT/conv_g4_variant_x.txt
+timeout 300 python tools/conv_g4_bench.py --cin 32 --cout 32 > $OUT/conv_g4_variant_x_32.txt 2>&1; cat $OUT/conv_g4_variant_x_32.txt
+timeout 300 python tools/conv_g4_check.py > $OUT/conv_g4_check_variant_x.txt 2>&1; tail -8 $OUT/conv_g4_check_variant_x.txt
+timeout 400 python -m pytest tests/test_gpu_conv.py tests/test_gpu_forward.py -m gpu -x -q > $OUT/pytest_variant_x.log 2>&1; echo "gpu tests (variant x) rc=$?"; tail -3 $OUT/pytest_variant_x.log
+timeout 300 python bench.py --steps 20 --batched 0 > $OUT/bench_variant_x.json 2> $OUT/bench_variant_x.err; echo "bench (variant x) rc=$?"; cut -c1-200 $OUT/bench_variant_x.json
+unset IMFNET_B200_VARIANT
 ls -la $OUT
