@@ -11,7 +11,7 @@ timeout 400 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo
 IMFNET_B200_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_batched.py -m gpu -x -q -s > $OUT/pytest_batched.log 2>&1; echo "batched rc=$?" | tee -a $OUT/pytest_batched.log; tail -15 $OUT/pytest_batched.log
 timeout 600 python bench.py --steps 20 > $OUT/bench_default.json 2> $OUT/bench_default.err; echo "bench (auto probe) rc=$?"; cut -c1-400 $OUT/bench_default.json
 timeout 300 python bench.py --probe-batched > $OUT/probe.json 2> $OUT/probe.err; echo "probe rc=$?"; cat $OUT/probe.json; tail -5 $OUT/probe.err
-for B in 5 8 10 16; do
+for B in 5 10 16; do
   timeout 300 python bench.py --steps 20 --batched $B > $OUT/bench_batched_$B.json 2> $OUT/bench_batched_$B.err; echo "bench --batched $B rc=$?"
   python - $OUT/bench_batched_$B.json <<'PY'
 import json, sys
