@@ -177,8 +177,17 @@ __global__ void __launch_bounds__(288, 1) k_tc_gemm(const float* __restrict__ A,
       const uint32_t ph = (uint32_t)(kc / kNS) & 1u;
       tc::mbar_wait(&full_bar[s], ph, err, 2);
       tc::tc_fence_after_sync();
+#if defined(IMF_TCGEMM_UNIFORM_ISSUE)
+      // EXPERIMENT (variant library x): warp-uniform operands + elect.sync instead of `if (lane == 0)`, so that
+      // ptxas emits bare UTC*MMA instructions instead of an ELECT / R2UR / BRA.U.ANY loop around each (see sparse_conv_g4.cu)
+      const uint32_t a_hi = __shfl_sync(0xffffffffu, tc::smem_u32(smem + s * STAGE_BYTES), 0), a_lo = a_hi + A_BYTES;
+      const uint32_t tmem_d_u = __shfl_sync(0xffffffffu, tmem_d, 0);
+      if (tc::elect_one()) {
+#define tmem_d tmem_d_u
+#else
       if (lane == 0) {
         const uint32_t a_hi = tc::smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+#endif
         const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -190,6 +199,9 @@ __global__ void __launch_bounds__(288, 1) k_tc_gemm(const float* __restrict__ A,
         tc::mma_commit(&empty_bar[s]);
         if (kc == nk - 1) tc::mma_commit(&acc_bar);
       }
+#if defined(IMF_TCGEMM_UNIFORM_ISSUE)
+#undef tmem_d
+#endif
       __syncwarp();
     }
   }
