@@ -155,7 +155,15 @@ __device__ __forceinline__ void g4_load16_h2(const __half* hi_src, const __half*
   const Half8* ls = reinterpret_cast<const Half8*>(lo_src);
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
+#if defined(IMF_G4_VEC_RESIDUAL)
+    // EXPERIMENT (variant library x): the struct copies below compile to eight 4-byte LDG.E.CONSTANT per 32 bytes; explicit 16-byte loads
+    const int4 h4 = __ldg(reinterpret_cast<const int4*>(hs) + q), l4 = __ldg(reinterpret_cast<const int4*>(ls) + q);
+    Half8 h, l;
+    *reinterpret_cast<int4*>(&h) = h4;
+    *reinterpret_cast<int4*>(&l) = l4;
+#else
     const Half8 h = hs[q], l = ls[q];
+#endif
     const __half2 hv[4] = {h.a, h.b, h.c, h.d}, lv[4] = {l.a, l.b, l.c, l.d};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
