@@ -28,6 +28,8 @@ FLAGS += os.environ.get("IMFNET_B200_NVCC_FLAGS", "").split()
 VARIANTS = {"x": {"sparse_conv_g4.cu": ["-DIMF_G4_LEAN_PRODUCER", "-DIMF_G4_SKIP_CLEAN_ZERO", "-DIMF_G4_VEC_RESIDUAL"],
                   "flash_fusion.cu": ["-DIMF_FLASH_UNIFORM_ISSUE"],
                   "tc_gemm.cu": ["-DIMF_TCGEMM_UNIFORM_ISSUE"]}}
+# y = x + a change of the MMA warps' hand-off protocol in the convolution kernel: for manual experiments only (bench.py never loads it)
+VARIANTS["y"] = dict(VARIANTS["x"], **{"sparse_conv_g4.cu": VARIANTS["x"]["sparse_conv_g4.cu"] + ["-DIMF_G4_EARLY_TURN"]})
 
 
 def lib_path(variant: str = "") -> str:

@@ -517,6 +517,22 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
           // stages are ISSUED in walk order whichever warp owns them (a turn counter in shared memory).  Waiting for the turn
           // BEFORE the slot's barrier also keeps the parity wait unambiguous: every earlier stage, hence the previous use of
           // this ring slot, has been consumed by then.
+#if defined(IMF_G4_EARLY_TURN)
+          // EXPERIMENT (variant library y only, never selected automatically): the hand-off chain between
+          // the MMA warps (turn -> slot barrier -> descriptors -> 8 MMAs -> turn store) is what a stage costs when nothing else
+          // stalls.  The descriptors do not depend on the turn, and the turn only has to order the WAITS on the ring (parity),
+          // not the MMAs (every accumulator has one issuing thread): build the descriptors first and pass the turn on as soon
+          // as this stage's slot has been seen full, before issuing.
+          const uint32_t a0 = __shfl_sync(0xffffffffu, tc::smem_u32(a_ring + a_slot * Cfg::A_BYTES), 0);
+          const uint32_t w0 = __shfl_sync(0xffffffffu, tc::smem_u32(w_ring + ws * Cfg::W_BYTES), 0);
+          const uint32_t d = __shfl_sync(0xffffffffu, tmem_d + (uint32_t)(cur.j * Cfg::ACC_COLS), 0);
+          const uint64_t da = tc::smem_desc_sw128(a0), dw = tc::smem_desc_sw128(w0);
+          while (*reinterpret_cast<volatile int*>(&turn_s) != ac) {}
+          tc::mbar_wait(&full_a[a_slot], a_phase, err, 4);
+          if (trace && lane == 0 && ac < 36) trace[18 + 4 * ac] = clock64();
+          if (tc::elect_one()) {
+            *reinterpret_cast<volatile int*>(&turn_s) = ac + 1;
+#else
           while (*reinterpret_cast<volatile int*>(&turn_s) != ac) {}
           tc::mbar_wait(&full_a[a_slot], a_phase, err, 4);
           // operand addresses as warp-uniform values (shuffles from lane 0): the compiler then keeps the descriptors in uniform
@@ -527,6 +543,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
           const uint64_t da = tc::smem_desc_sw128(a0), dw = tc::smem_desc_sw128(w0);
           if (trace && lane == 0 && ac < 36) trace[18 + 4 * ac] = clock64();
           if (tc::elect_one()) {
+#endif
             if (dbg & 4) {
             } else if (KC == 64) {
               // (descriptor start-address field = byte address >> 4: the hi image is at +0, the lo image at +kImg)
@@ -543,7 +560,9 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
                 g4_mma_f16(d, da + (uint64_t)(4 + ks * 2), dw + (uint64_t)(4 + ks * 2), idesc1, 1u);          // lo . Whi
               }
             }
+#if !defined(IMF_G4_EARLY_TURN)
             *reinterpret_cast<volatile int*>(&turn_s) = ac + 1;
+#endif
             tc::mma_commit(&empty_a[a_slot]);
           }
           if (trace && lane == 0 && ac < 36) trace[19 + 4 * ac] = clock64();

@@ -34,5 +34,9 @@ timeout 300 python tools/conv_g4_bench.py --cin 32 --cout 32 > $OUT/conv_g4_vari
 timeout 300 python tools/conv_g4_check.py > $OUT/conv_g4_check_variant_x.txt 2>&1; tail -8 $OUT/conv_g4_check_variant_x.txt
 timeout 400 python -m pytest tests/test_gpu_conv.py tests/test_gpu_forward.py -m gpu -x -q > $OUT/pytest_variant_x.log 2>&1; echo "gpu tests (variant x) rc=$?"; tail -3 $OUT/pytest_variant_x.log
 timeout 300 python bench.py --steps 20 --batched 0 > $OUT/bench_variant_x.json 2> $OUT/bench_variant_x.err; echo "bench (variant x) rc=$?"; cut -c1-200 $OUT/bench_variant_x.json
+export IMFNET_B200_VARIANT=y      # x + early hand-off of the MMA warps' turn (protocol change: check reproducibility first)
+timeout 300 python tools/conv_g4_check.py > $OUT/conv_g4_check_variant_y.txt 2>&1; tail -8 $OUT/conv_g4_check_variant_y.txt
+timeout 300 python tools/conv_g4_bench.py > $OUT/conv_g4_variant_y.txt 2>&1; cat $OUT/conv_g4_variant_y.txt
+timeout 300 python tools/conv_g4_bench.py --cin 32 --cout 32 > $OUT/conv_g4_variant_y_32.txt 2>&1; cat $OUT/conv_g4_variant_y_32.txt
 unset IMFNET_B200_VARIANT
 ls -la $OUT
