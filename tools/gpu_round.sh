@@ -9,7 +9,7 @@ timeout 400 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo
 timeout 600 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
 tail -c 2500 $OUT/bench.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2>> $OUT/bench.err; echo "reference rc=$?"; cat $OUT/bench_reference.json | cut -c1-300
-for k in 1 6 10; do timeout 200 python bench.py --steps 20 --streams $k 2>/dev/null | python -c "import json,sys;d=json.loads(sys.stdin.read());print(\"streams\",d[\"config\"][\"streams\"],d[\"value\"],d[\"ms_per_step\"],d[\"e2e\"][\"value\"])"; done | tee $OUT/streams_sweep.txt
+for k in 1 6 10; do timeout 200 python bench.py --steps 20 --streams $k --batched 0 2>/dev/null | python -c "import json,sys;d=json.loads(sys.stdin.read());print(\"streams\",d[\"config\"][\"streams\"],d[\"value\"],d[\"ms_per_step\"],d[\"e2e\"][\"value\"])"; done | tee $OUT/streams_sweep.txt
 timeout 300 python tools/profile_step.py > $OUT/profile_step.txt 2>&1; cat $OUT/profile_step.txt
 timeout 300 python tools/conv_g4_bench.py --flags 0,3,6,7 --old > $OUT/conv_g4_bench_64.txt 2>&1; cat $OUT/conv_g4_bench_64.txt
 timeout 300 python tools/conv_g4_bench.py --cin 32 --cout 32 > $OUT/conv_g4_bench_32.txt 2>&1; cat $OUT/conv_g4_bench_32.txt
