@@ -11,7 +11,8 @@ SparseTensor), inputs already resident in HBM.  A second execution mode of the s
 `model.forward_batches`, two groups of --streams fragments per step -- is timed as well when a parity probe of it passes in a
 subprocess on this GPU (it must reproduce forward_many's descriptors); the faster mode is the headline and every timed mode is
 listed in config.execution_modes_timed (--batched 0 switches this off).  The same probes decide whether the kernel variant library
-(imfnet_b200/build.py VARIANTS: same sources, two experiment switches on the convolution kernel) is loaded instead of the default one:
+(imfnet_b200/build.py VARIANTS: same sources, experiment switches on the convolution, attention and GEMM kernels) is loaded instead of the
+default one:
 only when its descriptors are bit-identical and its step is shorter (config.mode_selection, config.library).  Steps rotate over 8 distinct fragments per rank and the L2 is flushed
 between steps (a 256 MiB write), outside the per-step CUDA events.  Multi-GPU: fragments are independent, each rank runs
 its own (weak scaling); the only collective is the all-gather of per-rank timings.  One JSON line is printed by rank 0.
@@ -347,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
         return kf, resident, e2e
 
     def timed(step_fn):
-        """Returns (ms, launches, clocks, wall) or None when the mode failed; the barriers are executed either way (N > 1)."""
+        """Returns (ms, launches, clocks, wall), or the exception when the mode failed; the barriers are executed either way (N > 1)."""
         ok = True
         try:
             for i in range(args.warmup):
