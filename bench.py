@@ -257,27 +257,30 @@ def run_probe(args, variant=""):
 
 def select_modes(args):
     """Automatic mode (--batched -1): decide, from subprocess probes on the GPU this rank is about to measure,
-      * whether to load the kernel variant library "x" (imfnet_b200/build.py VARIANTS): only if its descriptors are bit-identical
-        to the default library's and its step is shorter;
+      * whether to load one of the kernel variant libraries (imfnet_b200/build.py AUTO_VARIANTS): the fastest one whose descriptors
+        are bit-identical to the default library's and whose step is at least 2 % shorter;
       * whether to time the batched captured plan as a second execution mode: only if it reproduces forward_many.
     Any failure of a probe only costs time: the default library and execution mode are what is measured then.
     Returns (batched B or 0, note)."""
+    from imfnet_b200.build import AUTO_VARIANTS
     d0, n0 = run_probe(args)
     if d0 is None:
-        return 0, f"default library: {n0} (batched plan and kernel variant not used)"
-    chosen, note = d0, ""
+        return 0, f"default library: {n0} (batched plan and kernel variants not used)"
+    chosen, best_name, notes = d0, "", []
     if os.environ.get("IMFNET_B200_VARIANT", "") == "" and args.variant_probe:
-        dx, nx = run_probe(args, "x")
-        if dx is None:
-            note = f"kernel variant x: {nx}; "
-        elif dx["hashes"] != d0["hashes"]:
-            note = "kernel variant x: descriptors differ from the default library (not used); "
-        elif dx["seq_ms_per_step"] >= 0.98 * d0["seq_ms_per_step"]:
-            note = f"kernel variant x: bit-identical, not faster ({dx['seq_ms_per_step']:.2f} vs {d0['seq_ms_per_step']:.2f} ms, not used); "
-        else:
-            note = f"kernel variant x in use: bit-identical descriptors, {dx['seq_ms_per_step']:.2f} vs {d0['seq_ms_per_step']:.2f} ms per step; "
-            os.environ["IMFNET_B200_VARIANT"] = "x"
-            chosen = dx
+        for name in AUTO_VARIANTS:
+            dx, nx = run_probe(args, name)
+            if dx is None:
+                notes.append(f"variant {name}: {nx}")
+            elif dx["hashes"] != d0["hashes"]:
+                notes.append(f"variant {name}: descriptors differ from the default library")
+            else:
+                notes.append(f"variant {name}: bit-identical, {dx['seq_ms_per_step']:.2f} ms per step")
+                if dx["seq_ms_per_step"] < 0.98 * d0["seq_ms_per_step"] and dx["seq_ms_per_step"] < chosen["seq_ms_per_step"]:
+                    chosen, best_name = dx, name
+        if best_name:
+            os.environ["IMFNET_B200_VARIANT"] = best_name
+    note = f"default library {d0['seq_ms_per_step']:.2f} ms per step; " + "; ".join(notes) + (f"; variant {best_name} in use; " if best_name else "; default library in use; ")
     if chosen.get("batched") == "ok":
         return int(chosen["B"]), note + f"batched plan: probe ok on this GPU (max row-wise rel diff vs forward_many {chosen['max_rowwise_rel_diff_vs_forward_many']:.1e})"
     return 0, note + f"batched plan: probe {chosen.get('batched', 'no result')} (not used)"

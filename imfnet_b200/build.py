@@ -25,11 +25,14 @@ FLAGS += os.environ.get("IMFNET_B200_NVCC_FLAGS", "").split()
 # Kernel variants: the same sources with experiment switches on some files, linked into libimfnet_b200_<name>.so next to the default
 # library (all other objects are shared).  Selected at load time by IMFNET_B200_VARIANT=<name> (imfnet_b200/_lib.py); bench.py only
 # does so after a subprocess probe showed bit-identical descriptors and a shorter step on the GPU at hand.
-VARIANTS = {"x": {"sparse_conv_g4.cu": ["-DIMF_G4_LEAN_PRODUCER", "-DIMF_G4_SKIP_CLEAN_ZERO", "-DIMF_G4_VEC_RESIDUAL"],
+VARIANTS = {"x": {"sparse_conv_g4.cu": ["-DIMF_G4_LEAN_PRODUCER", "-DIMF_G4_VEC_RESIDUAL"],
                   "flash_fusion.cu": ["-DIMF_FLASH_UNIFORM_ISSUE"],
                   "tc_gemm.cu": ["-DIMF_TCGEMM_UNIFORM_ISSUE"]}}
+# z = x + zero fills of clean ring rows skipped (fewer LDGSTS wavefronts, more producer instructions: which wins is a measurement)
+VARIANTS["z"] = dict(VARIANTS["x"], **{"sparse_conv_g4.cu": VARIANTS["x"]["sparse_conv_g4.cu"] + ["-DIMF_G4_SKIP_CLEAN_ZERO"]})
 # y = x + a change of the MMA warps' hand-off protocol in the convolution kernel: for manual experiments only (bench.py never loads it)
 VARIANTS["y"] = dict(VARIANTS["x"], **{"sparse_conv_g4.cu": VARIANTS["x"]["sparse_conv_g4.cu"] + ["-DIMF_G4_EARLY_TURN"]})
+AUTO_VARIANTS = ["x", "z"]      # what bench.py's automatic mode may load (bit-identical descriptors and a shorter step required)
 
 
 def lib_path(variant: str = "") -> str:

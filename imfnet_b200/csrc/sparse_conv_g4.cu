@@ -425,6 +425,9 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
         unsigned long long xb = reinterpret_cast<unsigned long long>(xc);
         asm volatile("" : "+l"(xb));        // keep base + chunk offset in one register pair (one IMAD.WIDE per copy)
 #endif
+#if defined(IMF_G4_SKIP_CLEAN_ZERO)
+        unsigned dirty_next = 0u;
+#endif
         if (!(dbg & 2)) {
           G4_COPY_UNROLL
           for (int i4 = 0; i4 < NINS / 4; ++i4) {
@@ -437,13 +440,12 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
             // row of this ring slot still holds data of an earlier stage; `dirty` tracks that per (lane, instruction), so about
             // half of the zero-fill wavefronts disappear.  Every row counts as dirty at the start of a pass (uninitialised
             // shared memory / the epilogue's staging buffers live in the ring).
+            // (after this stage a row is dirty exactly when its neighbour was present: an absent one is clean either way)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const unsigned bit = 1u << (4 * i4 + i);
-              if (r4[i] >= 0 || (dirty & bit)) {
-                g4_cp_async16_row(G4_DST(i4, i), G4_SRC(r4[i]), r4[i]);
-                dirty = r4[i] >= 0 ? (dirty | bit) : (dirty & ~bit);
-              }
+              if (r4[i] >= 0 || (dirty & bit)) g4_cp_async16_row(G4_DST(i4, i), G4_SRC(r4[i]), r4[i]);
+              dirty_next |= r4[i] >= 0 ? bit : 0u;
             }
 #else
 #pragma unroll
@@ -452,6 +454,9 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
 #endif
             (void)srow;
           }
+#if defined(IMF_G4_SKIP_CLEAN_ZERO)
+          dirty = dirty_next;
+#endif
         }
 #undef G4_DST
 #undef G4_SRC

@@ -84,16 +84,17 @@ def test_bench_without_batched_mode(bench):
 
 
 def test_mode_selection_logic(bench, monkeypatch):
-    """select_modes(): the variant library is only chosen when bit-identical and faster; the batched plan only when its probe passed."""
+    """select_modes(): a variant library is only chosen when bit-identical and faster (the fastest wins); the batched plan only when
+    the chosen library's probe of it passed."""
     import os
     ok = {"probe": "done", "B": 10, "hashes": ["a", "b"], "seq_ms_per_step": 10.0, "batched": "ok", "max_rowwise_rel_diff_vs_forward_many": 0.0}
 
-    def with_probes(default, variant):
+    def with_probes(default, x, z):
         calls = []
 
         def fake(args, v=""):
             calls.append(v)
-            d = variant if v else default
+            d = {"": default, "x": x, "z": z}[v]
             return (dict(d), "ok") if d is not None else (None, "probe failed (rc 1): boom")
 
         monkeypatch.setattr(bench, "run_probe", fake)
@@ -104,17 +105,17 @@ def test_mode_selection_logic(bench, monkeypatch):
         monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
         return res, chosen, calls
 
-    (B, note), var, calls = with_probes(ok, dict(ok, seq_ms_per_step=8.0))
-    assert B == 10 and var == "x" and "in use" in note and calls == ["", "x"]
-    (B, note), var, _ = with_probes(ok, dict(ok, seq_ms_per_step=9.9))
-    assert B == 10 and var == "" and "not faster" in note
-    (B, note), var, _ = with_probes(ok, dict(ok, hashes=["a", "c"], seq_ms_per_step=5.0))
-    assert B == 10 and var == "" and "differ" in note
-    (B, note), var, _ = with_probes(ok, None)
-    assert B == 10 and var == "" and "probe failed" in note
-    (B, note), var, _ = with_probes(dict(ok, batched="mismatch"), dict(ok, seq_ms_per_step=8.0))
-    assert B == 10 and var == "x"                                  # the variant's own batched probe passed
-    (B, note), var, _ = with_probes(dict(ok, batched="failed: x"), dict(ok, seq_ms_per_step=20.0, batched="failed: x"))
+    (B, note), var, calls = with_probes(ok, dict(ok, seq_ms_per_step=8.0), dict(ok, seq_ms_per_step=9.0))
+    assert B == 10 and var == "x" and "variant x in use" in note and calls == ["", "x", "z"]
+    (B, note), var, _ = with_probes(ok, dict(ok, seq_ms_per_step=8.0), dict(ok, seq_ms_per_step=7.0))
+    assert var == "z"
+    (B, note), var, _ = with_probes(ok, dict(ok, seq_ms_per_step=9.9), dict(ok, seq_ms_per_step=10.5))
+    assert B == 10 and var == "" and "default library in use" in note
+    (B, note), var, _ = with_probes(ok, dict(ok, hashes=["a", "c"], seq_ms_per_step=5.0), None)
+    assert B == 10 and var == "" and "differ" in note and "probe failed" in note
+    (B, note), var, _ = with_probes(dict(ok, batched="mismatch"), dict(ok, seq_ms_per_step=8.0), None)
+    assert B == 10 and var == "x"                                  # the chosen library's own batched probe passed
+    (B, note), var, _ = with_probes(dict(ok, batched="failed: x"), dict(ok, seq_ms_per_step=20.0, batched="failed: x"), None)
     assert B == 0 and var == "" and "not used" in note
-    (B, note), var, calls = with_probes(None, ok)
+    (B, note), var, calls = with_probes(None, ok, ok)
     assert B == 0 and var == "" and calls == [""]

@@ -28,12 +28,15 @@ tail -5 $OUT/bench_batched_10.err
 # conv-kernel experiment: rebuild with the switch into a scratch copy of the library, run the microbench and the parity checker
 timeout 300 python tools/conv_g4_bench.py > $OUT/conv_g4_default.txt 2>&1; cat $OUT/conv_g4_default.txt
 timeout 300 python tools/conv_g4_bench.py --cin 32 --cout 32 --trace > $OUT/conv_g4_trace_32.txt 2>&1; head -50 $OUT/conv_g4_trace_32.txt
-export IMFNET_B200_VARIANT=x      # libimfnet_b200_x.so: lean producer addressing + zero fill skipped for clean rows
-timeout 300 python tools/conv_g4_bench.py > $OUT/conv_g4_variant_x.txt 2>&1; cat $OUT/conv_g4_variant_x.txt
-timeout 300 python tools/conv_g4_bench.py --cin 32 --cout 32 > $OUT/conv_g4_variant_x_32.txt 2>&1; cat $OUT/conv_g4_variant_x_32.txt
-timeout 300 python tools/conv_g4_check.py > $OUT/conv_g4_check_variant_x.txt 2>&1; tail -8 $OUT/conv_g4_check_variant_x.txt
-timeout 400 python -m pytest tests/test_gpu_conv.py tests/test_gpu_forward.py -m gpu -x -q > $OUT/pytest_variant_x.log 2>&1; echo "gpu tests (variant x) rc=$?"; tail -3 $OUT/pytest_variant_x.log
-timeout 300 python bench.py --steps 20 --batched 0 > $OUT/bench_variant_x.json 2> $OUT/bench_variant_x.err; echo "bench (variant x) rc=$?"; cut -c1-200 $OUT/bench_variant_x.json
+for V in x z; do     # x: lean producer addressing, vector residual loads, uniform MMA issue; z: x + zero fill skipped for clean rows
+  export IMFNET_B200_VARIANT=$V
+  timeout 300 python tools/conv_g4_bench.py > $OUT/conv_g4_variant_$V.txt 2>&1; cat $OUT/conv_g4_variant_$V.txt
+  timeout 300 python tools/conv_g4_bench.py --cin 32 --cout 32 > $OUT/conv_g4_variant_${V}_32.txt 2>&1; cat $OUT/conv_g4_variant_${V}_32.txt
+  timeout 300 python tools/conv_g4_check.py > $OUT/conv_g4_check_variant_$V.txt 2>&1; tail -8 $OUT/conv_g4_check_variant_$V.txt
+  timeout 400 python -m pytest tests/test_gpu_conv.py tests/test_gpu_forward.py -m gpu -x -q > $OUT/pytest_variant_$V.log 2>&1; echo "gpu tests (variant $V) rc=$?"; tail -3 $OUT/pytest_variant_$V.log
+  timeout 300 python bench.py --steps 20 --batched 0 > $OUT/bench_variant_$V.json 2> $OUT/bench_variant_$V.err; echo "bench (variant $V) rc=$?"; cut -c1-200 $OUT/bench_variant_$V.json
+done
+timeout 300 python tools/flash_bench.py > $OUT/flash_bench_variant_z.txt 2>&1; cat $OUT/flash_bench_variant_z.txt
 export IMFNET_B200_VARIANT=y      # x + early hand-off of the MMA warps' turn (protocol change: check reproducibility first)
 timeout 300 python tools/conv_g4_check.py > $OUT/conv_g4_check_variant_y.txt 2>&1; tail -8 $OUT/conv_g4_check_variant_y.txt
 timeout 300 python tools/conv_g4_bench.py > $OUT/conv_g4_variant_y.txt 2>&1; cat $OUT/conv_g4_variant_y.txt
