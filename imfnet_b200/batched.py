@@ -27,7 +27,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from .engine import FusedPlan, GraphPlan, PlanCapacityError, _kc
+from .engine import FusedPlan, GraphPlan, PlanCapacityError
 from .model.Img_Encoder import ImagePlan
 
 
@@ -131,57 +131,21 @@ class BatchGraphPlan(GraphPlan):
                           ws=torch.empty(max(self.att_ws_bytes, 1), **u8), stream=torch.cuda.Stream(device=dev)) for _ in range(self.B)]
         self.att_ws = None
 
-    # -- the launch sequence (GraphPlan._enqueue with the image branch and the fusion step per batch item) ------------------
-    def _enqueue(self):
-        m, f, L = self.m, self.f, _lib.lib()
-        CH, TR, rows, B = f.CH, f.TR, self.rows, self.B
-        main = torch.cuda.current_stream()
-        s = main.cuda_stream
-        status = self.meta.data_ptr()
-        # ---- image branch on a forked stream: one encoder pass over all images, then K / V of every item ----
+    # -- the two steps of GraphPlan._enqueue that a batch changes ------------------------------------------------------------
+    def _enqueue_image(self, m, main):
+        """Image branch on a forked stream: ONE encoder pass over all images, then K / V of every item."""
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             tokens = self.image_plan.enqueue(self.image)
             P2 = self.image_plan.P2
-            self.kvs = [m.attention_fusion.project_context(tokens[b * P2:(b + 1) * P2], False) for b in range(B)]
-        # ---- coordinates: hash, pyramid, neighbour tables (all sizes stay on the device) ----
-        self.meta.zero_()
-        self.err.zero_()
-        _lib.check(L.imf_hash_build(self.coords[1].data_ptr(), self._n(1), rows, self.tables[1].data_ptr(), self.cap, status, s))
-        prev = 1
-        for t in (2, 4, 8):
-            _lib.check(L.imf_stride_map(self.coords[prev].data_ptr(), self._n(prev), rows, t, self.tables[t].data_ptr(), self.cap,
-                                        self.coords[t].data_ptr(), self._n(t), None, self.sm_ws.data_ptr(), self.sm_ws_bytes, status, s))
-            prev = t
-        for t in (1, 2, 4):
-            _lib.check(L.imf_parity_perm(self.coords[t].data_ptr(), self._n(t), rows, t, self.perm[t].data_ptr(), self.perm_ws.data_ptr(),
-                                         self.perm_ws_bytes, s))
-        jobs = (_lib.KmapJob * len(self.nbr))()
-        for i, ((t_in, t_out, tr), (nbr_t, ld_n, mask)) in enumerate(self.nbr.items()):
-            jobs[i] = _lib.KmapJob(self.coords[t_out].data_ptr(), self._n(t_out), self.tables[t_in].data_ptr(), nbr_t.data_ptr(),
-                                   mask.data_ptr(), self.perm[t_out].data_ptr() if tr else None, -t_out if tr else t_in)
-        _lib.check(L.imf_kernel_map_t_batch(jobs, len(self.nbr), rows, self.cap, 3, self.ldn, s))
-        _lib.check(L.imf_batch_segments_n(self.coords[8].data_ptr(), self._n(8), rows, B, self.item_cap8, self.seg.data_ptr(),
-                                          self.cnt.data_ptr(), self.err.data_ptr(), s))
-        # ---- encoder ----
-        ld1, ld2, ld4 = 2 * self.cat1.shape[1], 2 * self.cat2.shape[1], 2 * self.cat4.shape[1]
-        s1, s2, s4 = self.cat1.data_ptr() + TR[2] * 4, self.cat2.data_ptr() + TR[3] * 4, self.cat4.data_ptr() + TR[4] * 4
-        kc1a, kc1b = _kc(TR[2]), _kc(CH[1])
-        kc2, kc4, k8 = _kc(TR[3], CH[2]), _kc(TR[4], CH[3]), _kc(CH[4])
-        sc, sh = f.norm1
-        _lib.check(L.imf_conv_first_h2_fwd(self.feats.data_ptr(), self.feats.shape[1], m.conv1.in_channels, m.conv1.kernel.data_ptr(),
-                                           self.coords[1].data_ptr(), self._n(1), rows, self.tables[1].data_ptr(), self.cap,
-                                           m.conv1.kernel_size, 1, CH[1], sc.data_ptr(), sh.data_ptr(), 0, self.a0.data_ptr(),
-                                           2 * CH[1], _kc(CH[1]), s))
-        self._block(L, "block1", self.a0.data_ptr(), 2 * CH[1], _kc(CH[1]), 1, CH[1], self.a1, s1, ld1, kc1b, s)
-        self._conv(L, "conv2", s1, ld1, (1, 2, False), 2, None, 0, 0, False, self.b0.data_ptr(), 2 * CH[2], _kc(CH[2]), s)
-        self._block(L, "block2", self.b0.data_ptr(), 2 * CH[2], _kc(CH[2]), 2, CH[2], self.b1, s2, ld2, kc2, s)
-        self._conv(L, "conv3", s2, ld2, (2, 4, False), 4, None, 0, 0, False, self.c0.data_ptr(), 2 * CH[3], _kc(CH[3]), s)
-        self._block(L, "block3", self.c0.data_ptr(), 2 * CH[3], _kc(CH[3]), 4, CH[3], self.c1, s4, ld4, kc4, s)
-        self._conv(L, "conv4", s4, ld4, (4, 8, False), 8, None, 0, 0, False, self.d0.data_ptr(), 2 * CH[4], k8, s)
-        self._block(L, "block4", self.d0.data_ptr(), 2 * CH[4], k8, 8, CH[4], self.d1, self.d2.data_ptr(), 2 * CH[4], k8, s)
-        # ---- attention fusion at stride 8, one chain per batch item on its own stream (model/resunet.py:240-271) ----
+            self.kvs = [m.attention_fusion.project_context(tokens[b * P2:(b + 1) * P2], False) for b in range(self.B)]
+
+    def _enqueue_fusion(self, L, m, C8, k8, main, s):
+        """Attention fusion at stride 8, one chain per batch item on its own stream (model/resunet.py:240-271): the item's rows
+        [seg[b], seg[b] + cnt[b]) of d2 (h2) -> its private P8 -> fused32 -> the same rows of fused (h2)."""
         af = m.attention_fusion
+        _lib.check(L.imf_batch_segments_n(self.coords[8].data_ptr(), self._n(8), self.rows, self.B, self.item_cap8, self.seg.data_ptr(),
+                                          self.cnt.data_ptr(), self.err.data_ptr(), s))
         main.wait_stream(self.side)
         for b, it in enumerate(self.item):
             st = it["stream"]
@@ -189,27 +153,13 @@ class BatchGraphPlan(GraphPlan):
             seg_b, cnt_b = self.seg.data_ptr() + 4 * b, self.cnt.data_ptr() + 4 * b
             with torch.cuda.stream(st):
                 sb = st.cuda_stream
-                _lib.check(L.imf_h2_unpack_seg(self.d2.data_ptr(), 2 * CH[4], seg_b, cnt_b, self.item_cap8, CH[4], k8,
-                                               it["P8"].data_ptr(), CH[4], sb))
-                _lib.check(L.imf_attention_fusion_fwd_m(af.packed(), it["P8"].data_ptr(), CH[4], self.item_cap8, cnt_b,
-                                                        self.kvs[b].data_ptr(), self.n_tok, it["fused32"].data_ptr(), CH[4],
-                                                        it["ws"].data_ptr(), self.att_ws_bytes, sb))
-                _lib.check(L.imf_h2_pack_seg(it["fused32"].data_ptr(), CH[4], seg_b, cnt_b, self.item_cap8, CH[4], k8,
-                                             self.fused.data_ptr(), 2 * CH[4], self.err.data_ptr(), sb))
+                _lib.check(L.imf_h2_unpack_seg(self.d2.data_ptr(), 2 * C8, seg_b, cnt_b, self.item_cap8, C8, k8, it["P8"].data_ptr(), C8, sb))
+                _lib.check(L.imf_attention_fusion_fwd_m(af.packed(), it["P8"].data_ptr(), C8, self.item_cap8, cnt_b, self.kvs[b].data_ptr(),
+                                                        self.n_tok, it["fused32"].data_ptr(), C8, it["ws"].data_ptr(), self.att_ws_bytes, sb))
+                _lib.check(L.imf_h2_pack_seg(it["fused32"].data_ptr(), C8, seg_b, cnt_b, self.item_cap8, C8, k8, self.fused.data_ptr(), 2 * C8,
+                                             self.err.data_ptr(), sb))
         for it in self.item:
             main.wait_stream(it["stream"])
-        # ---- decoder ----
-        self._conv(L, "conv4_tr", self.fused.data_ptr(), 2 * CH[4], (8, 4, True), 4, None, 0, 0, False, self.e0.data_ptr(), 2 * TR[4],
-                   _kc(TR[4]), s)
-        self._block(L, "block4_tr", self.e0.data_ptr(), 2 * TR[4], _kc(TR[4]), 4, TR[4], self.e1, self.cat4.data_ptr(), ld4, kc4, s)
-        self._conv(L, "conv3_tr", self.cat4.data_ptr(), ld4, (4, 2, True), 2, None, 0, 0, False, self.g0.data_ptr(), 2 * TR[3], _kc(TR[3]), s)
-        self._block(L, "block3_tr", self.g0.data_ptr(), 2 * TR[3], _kc(TR[3]), 2, TR[3], self.g1, self.cat2.data_ptr(), ld2, kc2, s)
-        self._conv(L, "conv2_tr", self.cat2.data_ptr(), ld2, (2, 1, True), 1, None, 0, 0, False, self.h0.data_ptr(), 2 * TR[2], _kc(TR[2]), s)
-        self._block(L, "block2_tr", self.h0.data_ptr(), 2 * TR[2], _kc(TR[2]), 1, TR[2], self.h1, self.cat1.data_ptr(), ld1, kc1a, s)
-        # ---- tail ----
-        _lib.check(L.imf_pointwise_tail_h2_fwd(self.cat1.data_ptr(), ld1, TR[2] + CH[1], TR[2], kc1a, kc1b, m.conv1_tr.kernel.data_ptr(),
-                                               TR[1], m.final.kernel.data_ptr(), _lib.ptr(f.final_bias), m.out_channels, self._n(1), rows,
-                                               1 if m.normalize_feature else 0, None, self.out.data_ptr(), m.out_channels, s))
 
     # -- one batch ---------------------------------------------------------------------------------
     @torch.no_grad()

@@ -351,10 +351,7 @@ class GraphPlan:
         main = torch.cuda.current_stream()
         s = main.cuda_stream
         status = self.meta.data_ptr()
-        # ---- image branch on a forked stream ----
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
-            self.kv = m.attention_fusion.project_context(self.image_plan.enqueue(self.image[0]), False)
+        self._enqueue_image(m, main)
         # ---- coordinates: hash, pyramid, neighbour tables (all sizes stay on the device) ----
         self.meta.zero_()
         self.err.zero_()
@@ -390,14 +387,7 @@ class GraphPlan:
         self._block(L, "block3", self.c0.data_ptr(), 2 * CH[3], _kc(CH[3]), 4, CH[3], self.c1, s4, ld4, kc4, s)
         self._conv(L, "conv4", s4, ld4, (4, 8, False), 8, None, 0, 0, False, self.d0.data_ptr(), 2 * CH[4], k8, s)
         self._block(L, "block4", self.d0.data_ptr(), 2 * CH[4], k8, 8, CH[4], self.d1, self.d2.data_ptr(), 2 * CH[4], k8, s)
-        # ---- attention fusion at stride 8 (fp32 tokens) ----
-        af = m.attention_fusion
-        _lib.check(L.imf_h2_unpack_n(self.d2.data_ptr(), 2 * CH[4], self.cap8, self._n(8), CH[4], k8, self.P8.data_ptr(), CH[4], s))
-        main.wait_stream(self.side)
-        _lib.check(L.imf_attention_fusion_fwd_m(af.packed(), self.P8.data_ptr(), CH[4], self.cap8, self._n(8), self.kv.data_ptr(),
-                                                self.n_tok, self.fused32.data_ptr(), CH[4], self.att_ws.data_ptr(), self.att_ws_bytes, s))
-        _lib.check(L.imf_h2_pack_n(self.fused32.data_ptr(), CH[4], self.cap8, self._n(8), CH[4], k8, self.fused.data_ptr(), 2 * CH[4],
-                                   self.err.data_ptr(), s))
+        self._enqueue_fusion(L, m, CH[4], k8, main, s)
         # ---- decoder ----
         self._conv(L, "conv4_tr", self.fused.data_ptr(), 2 * CH[4], (8, 4, True), 4, None, 0, 0, False, self.e0.data_ptr(), 2 * TR[4],
                    _kc(TR[4]), s)
@@ -410,6 +400,23 @@ class GraphPlan:
         _lib.check(L.imf_pointwise_tail_h2_fwd(self.cat1.data_ptr(), ld1, TR[2] + CH[1], TR[2], kc1a, kc1b, m.conv1_tr.kernel.data_ptr(),
                                                TR[1], m.final.kernel.data_ptr(), _lib.ptr(f.final_bias), m.out_channels, self._n(1), rows,
                                                1 if m.normalize_feature else 0, None, self.out.data_ptr(), m.out_channels, s))
+
+    # the two steps a batch changes (imfnet_b200/batched.py overrides them): the image branch and the fusion at stride 8
+    def _enqueue_image(self, m, main):
+        """Image branch on a forked stream: encoder, then K / V of the image tokens (joined again in _enqueue_fusion)."""
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self.kv = m.attention_fusion.project_context(self.image_plan.enqueue(self.image[0]), False)
+
+    def _enqueue_fusion(self, L, m, C8, k8, main, s):
+        """Attention fusion at stride 8 (fp32 tokens): d2 (h2) -> P8 -> fused32 -> fused (h2)."""
+        af = m.attention_fusion
+        _lib.check(L.imf_h2_unpack_n(self.d2.data_ptr(), 2 * C8, self.cap8, self._n(8), C8, k8, self.P8.data_ptr(), C8, s))
+        main.wait_stream(self.side)
+        _lib.check(L.imf_attention_fusion_fwd_m(af.packed(), self.P8.data_ptr(), C8, self.cap8, self._n(8), self.kv.data_ptr(),
+                                                self.n_tok, self.fused32.data_ptr(), C8, self.att_ws.data_ptr(), self.att_ws_bytes, s))
+        _lib.check(L.imf_h2_pack_n(self.fused32.data_ptr(), C8, self.cap8, self._n(8), C8, k8, self.fused.data_ptr(), 2 * C8,
+                                   self.err.data_ptr(), s))
 
     def capture(self):
         """Warm the sequence up once (lazy initialisation inside torch / cuDNN must not happen during capture), then record it."""
