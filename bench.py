@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+CACHE_DIR = os.path.join(ROOT, ".bench_cache")      # mode decisions of the automatic mode (select_modes), keyed by machine boot id
 METRIC = "descriptor-extraction throughput: voxels/sec/GPU on 50k-voxel fragments"
 N_FRAGMENTS = 8
 NCU_DRAM_BYTES_PER_LAUNCH = 18674944      # k_sparse_conv_g4<64,64>, 64->64 @ 50 000 voxels (profiles/r01/call55_g4_ncu_summary.txt)
@@ -262,7 +263,37 @@ def select_modes(args):
       * whether to time the batched captured plan as a second execution mode: only if it reproduces forward_many.
     Any failure of a probe only costs time: the default library and execution mode are what is measured then.
     Returns (batched B or 0, note)."""
-    from imfnet_b200.build import AUTO_VARIANTS
+    from imfnet_b200.build import AUTO_VARIANTS, lib_path
+    # the decision (not any measurement) is remembered per box, GPU index and build, so that the back-to-back runs of a scaling sweep
+    # (N = 1, 2, 4, 8 on the same box) probe once
+    import hashlib
+    libs = [lib_path(v) for v in [""] + AUTO_VARIANTS] + [os.path.abspath(__file__)]
+    stamp = [(os.path.basename(f), os.path.getsize(f), int(os.path.getmtime(f))) for f in libs if os.path.exists(f)]
+    try:
+        boot = open("/proc/sys/kernel/random/boot_id").read().strip()      # a decision never travels to another machine
+    except OSError:
+        boot = str(os.getpid())
+    key = hashlib.sha1(json.dumps([stamp, boot, args.config, args.streams, os.environ.get("LOCAL_RANK", "0"), args.variant_probe]).encode()).hexdigest()[:16]
+    cache = os.path.join(CACHE_DIR, f"modes_{key}.json")
+    if os.environ.get("IMFNET_B200_VARIANT", "") == "":
+        try:
+            if time.time() - os.path.getmtime(cache) < 3600:
+                c = json.load(open(cache))
+                if c["variant"]:
+                    os.environ["IMFNET_B200_VARIANT"] = c["variant"]
+                return int(c["batched"]), c["note"] + " [decision cached by an earlier bench.py run on this box]"
+        except (OSError, ValueError, KeyError):
+            pass
+
+    def remember(batched, variant, note):
+        try:
+            os.makedirs(CACHE_DIR, exist_ok=True)
+            with open(cache, "w") as f:
+                json.dump({"batched": batched, "variant": variant, "note": note}, f)
+        except OSError:
+            pass
+        return batched, note
+
     d0, n0 = run_probe(args)
     if d0 is None:
         return 0, f"default library: {n0} (batched plan and kernel variants not used)"
@@ -282,8 +313,9 @@ def select_modes(args):
             os.environ["IMFNET_B200_VARIANT"] = best_name
     note = f"default library {d0['seq_ms_per_step']:.2f} ms per step; " + "; ".join(notes) + (f"; variant {best_name} in use; " if best_name else "; default library in use; ")
     if chosen.get("batched") == "ok":
-        return int(chosen["B"]), note + f"batched plan: probe ok on this GPU (max row-wise rel diff vs forward_many {chosen['max_rowwise_rel_diff_vs_forward_many']:.1e})"
-    return 0, note + f"batched plan: probe {chosen.get('batched', 'no result')} (not used)"
+        return remember(int(chosen["B"]), best_name, note + "batched plan: probe ok on this GPU (max row-wise rel diff vs forward_many "
+                        f"{chosen['max_rowwise_rel_diff_vs_forward_many']:.1e})")
+    return remember(0, best_name, note + f"batched plan: probe {chosen.get('batched', 'no result')} (not used)")
 
 
 def run_ours(args, rank, world, local_rank):

@@ -83,7 +83,7 @@ def test_bench_without_batched_mode(bench):
     assert set(d["config"]["execution_modes_timed"]) == {"single-fragment plans"} and d["config"]["mode_selection"] == "off"
 
 
-def test_mode_selection_logic(bench, monkeypatch):
+def test_mode_selection_logic(bench, monkeypatch, tmp_path_factory):
     """select_modes(): a variant library is only chosen when bit-identical and faster (the fastest wins); the batched plan only when
     the chosen library's probe of it passed."""
     import os
@@ -99,6 +99,7 @@ def test_mode_selection_logic(bench, monkeypatch):
 
         monkeypatch.setattr(bench, "run_probe", fake)
         monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
+        monkeypatch.setattr(bench, "CACHE_DIR", str(tmp_path_factory.mktemp("modes")))      # no decision cache between cases
         args = types.SimpleNamespace(config="T", streams=10, variant_probe=True)
         res = bench.select_modes(args)
         chosen = os.environ.get("IMFNET_B200_VARIANT", "")
@@ -119,3 +120,24 @@ def test_mode_selection_logic(bench, monkeypatch):
     assert B == 0 and var == "" and "not used" in note
     (B, note), var, calls = with_probes(None, ok, ok)
     assert B == 0 and var == "" and calls == [""]
+
+
+def test_mode_selection_is_cached_per_box(bench, monkeypatch, tmp_path):
+    import os
+    ok = {"probe": "done", "B": 10, "hashes": ["a"], "seq_ms_per_step": 10.0, "batched": "ok", "max_rowwise_rel_diff_vs_forward_many": 0.0}
+    calls = []
+
+    def fake(args, v=""):
+        calls.append(v)
+        return dict(ok, seq_ms_per_step=10.0 if v == "" else 8.0 if v == "x" else 9.0), "ok"
+
+    monkeypatch.setattr(bench, "run_probe", fake)
+    monkeypatch.setattr(bench, "CACHE_DIR", str(tmp_path / "cache"))
+    monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
+    args = types.SimpleNamespace(config="T", streams=10, variant_probe=True)
+    B1, note1 = bench.select_modes(args)
+    assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B1 == 10 and len(calls) == 3
+    monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
+    B2, note2 = bench.select_modes(args)                      # second run on the same box: no probes, same decision
+    assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B2 == 10 and len(calls) == 3 and "cached" in note2 and note2.startswith(note1)
+    monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
