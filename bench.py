@@ -206,6 +206,10 @@ def probe_batched(args, local_rank):
         if not all(bool(torch.isfinite(r).all()) for r in ref):
             raise SystemExit("probe: non-finite descriptors")
         out["hashes"] = [hashlib.sha256(r.cpu().numpy().tobytes()).hexdigest() for r in ref[:N_FRAGMENTS]]
+        for rep in range(3):          # run-to-run reproducibility of this library (every repeat must give the same bits)
+            again = [o.F for o in model.forward_many(items, streams=B)]
+            if [hashlib.sha256(r.cpu().numpy().tobytes()).hexdigest() for r in again[:N_FRAGMENTS]] != out["hashes"]:
+                raise SystemExit("probe: descriptors differ from run to run")
         ts = []
         for i in range(8):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -30,9 +30,9 @@ VARIANTS = {"x": {"sparse_conv_g4.cu": ["-DIMF_G4_LEAN_PRODUCER", "-DIMF_G4_VEC_
                   "tc_gemm.cu": ["-DIMF_TCGEMM_UNIFORM_ISSUE"]}}
 # z = x + zero fills of clean ring rows skipped (fewer LDGSTS wavefronts, more producer instructions: which wins is a measurement)
 VARIANTS["z"] = dict(VARIANTS["x"], **{"sparse_conv_g4.cu": VARIANTS["x"]["sparse_conv_g4.cu"] + ["-DIMF_G4_SKIP_CLEAN_ZERO"]})
-# y = x + a change of the MMA warps' hand-off protocol in the convolution kernel: for manual experiments only (bench.py never loads it)
+# y = x + the MMA warps of the convolution kernel pass their turn on before issuing (shorter hand-off chain; same single-owner accumulators)
 VARIANTS["y"] = dict(VARIANTS["x"], **{"sparse_conv_g4.cu": VARIANTS["x"]["sparse_conv_g4.cu"] + ["-DIMF_G4_EARLY_TURN"]})
-AUTO_VARIANTS = ["x", "z"]      # what bench.py's automatic mode may load (bit-identical descriptors and a shorter step required)
+AUTO_VARIANTS = ["x", "z", "y"]      # what bench.py's automatic mode may load (bit-identical descriptors and a shorter step required)
 
 
 def lib_path(variant: str = "") -> str:

@@ -89,12 +89,12 @@ def test_mode_selection_logic(bench, monkeypatch, tmp_path_factory):
     import os
     ok = {"probe": "done", "B": 10, "hashes": ["a", "b"], "seq_ms_per_step": 10.0, "batched": "ok", "max_rowwise_rel_diff_vs_forward_many": 0.0}
 
-    def with_probes(default, x, z):
+    def with_probes(default, x, z, y=None):
         calls = []
 
         def fake(args, v=""):
             calls.append(v)
-            d = {"": default, "x": x, "z": z}[v]
+            d = {"": default, "x": x, "z": z, "y": y}[v]
             return (dict(d), "ok") if d is not None else (None, "probe failed (rc 1): boom")
 
         monkeypatch.setattr(bench, "run_probe", fake)
@@ -107,9 +107,11 @@ def test_mode_selection_logic(bench, monkeypatch, tmp_path_factory):
         return res, chosen, calls
 
     (B, note), var, calls = with_probes(ok, dict(ok, seq_ms_per_step=8.0), dict(ok, seq_ms_per_step=9.0))
-    assert B == 10 and var == "x" and "variant x in use" in note and calls == ["", "x", "z"]
+    assert B == 10 and var == "x" and "variant x in use" in note and calls == ["", "x", "z", "y"]
     (B, note), var, _ = with_probes(ok, dict(ok, seq_ms_per_step=8.0), dict(ok, seq_ms_per_step=7.0))
     assert var == "z"
+    (B, note), var, _ = with_probes(ok, dict(ok, seq_ms_per_step=8.0), dict(ok, seq_ms_per_step=7.0), dict(ok, seq_ms_per_step=6.0))
+    assert var == "y"
     (B, note), var, _ = with_probes(ok, dict(ok, seq_ms_per_step=9.9), dict(ok, seq_ms_per_step=10.5))
     assert B == 10 and var == "" and "default library in use" in note
     (B, note), var, _ = with_probes(ok, dict(ok, hashes=["a", "c"], seq_ms_per_step=5.0), None)
@@ -136,8 +138,8 @@ def test_mode_selection_is_cached_per_box(bench, monkeypatch, tmp_path):
     monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
     args = types.SimpleNamespace(config="T", streams=10, variant_probe=True)
     B1, note1 = bench.select_modes(args)
-    assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B1 == 10 and len(calls) == 3
+    assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B1 == 10 and len(calls) == 4
     monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
     B2, note2 = bench.select_modes(args)                      # second run on the same box: no probes, same decision
-    assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B2 == 10 and len(calls) == 3 and "cached" in note2 and note2.startswith(note1)
+    assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B2 == 10 and len(calls) == 4 and "cached" in note2 and note2.startswith(note1)
     monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
