@@ -32,7 +32,8 @@ VARIANTS = {"x": {"sparse_conv_g4.cu": ["-DIMF_G4_LEAN_PRODUCER", "-DIMF_G4_VEC_
 VARIANTS["z"] = dict(VARIANTS["x"], **{"sparse_conv_g4.cu": VARIANTS["x"]["sparse_conv_g4.cu"] + ["-DIMF_G4_SKIP_CLEAN_ZERO"]})
 # y = x + the MMA warps of the convolution kernel pass their turn on before issuing (shorter hand-off chain; same single-owner accumulators)
 VARIANTS["y"] = dict(VARIANTS["x"], **{"sparse_conv_g4.cu": VARIANTS["x"]["sparse_conv_g4.cu"] + ["-DIMF_G4_EARLY_TURN"]})
-AUTO_VARIANTS = ["x", "z", "y"]      # what bench.py's automatic mode may load (bit-identical descriptors and a shorter step required)
+VARIANTS["w"] = dict(VARIANTS["x"], **{"sparse_conv_g4.cu": VARIANTS["z"]["sparse_conv_g4.cu"] + ["-DIMF_G4_EARLY_TURN"]})      # z + y
+AUTO_VARIANTS = ["x", "z", "y", "w"]      # what bench.py's automatic mode may load (bit-identical descriptors and a shorter step required)
 
 
 def lib_path(variant: str = "") -> str:

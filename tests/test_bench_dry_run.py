@@ -89,12 +89,12 @@ def test_mode_selection_logic(bench, monkeypatch, tmp_path_factory):
     import os
     ok = {"probe": "done", "B": 10, "hashes": ["a", "b"], "seq_ms_per_step": 10.0, "batched": "ok", "max_rowwise_rel_diff_vs_forward_many": 0.0}
 
-    def with_probes(default, x, z, y=None):
+    def with_probes(default, x, z, y=None, w=None):
         calls = []
 
         def fake(args, v=""):
             calls.append(v)
-            d = {"": default, "x": x, "z": z, "y": y}[v]
+            d = {"": default, "x": x, "z": z, "y": y, "w": w}[v]
             return (dict(d), "ok") if d is not None else (None, "probe failed (rc 1): boom")
 
         monkeypatch.setattr(bench, "run_probe", fake)
@@ -107,7 +107,7 @@ def test_mode_selection_logic(bench, monkeypatch, tmp_path_factory):
         return res, chosen, calls
 
     (B, note), var, calls = with_probes(ok, dict(ok, seq_ms_per_step=8.0), dict(ok, seq_ms_per_step=9.0))
-    assert B == 10 and var == "x" and "variant x in use" in note and calls == ["", "x", "z", "y"]
+    assert B == 10 and var == "x" and "variant x in use" in note and calls == ["", "x", "z", "y", "w"]
     (B, note), var, _ = with_probes(ok, dict(ok, seq_ms_per_step=8.0), dict(ok, seq_ms_per_step=7.0))
     assert var == "z"
     (B, note), var, _ = with_probes(ok, dict(ok, seq_ms_per_step=8.0), dict(ok, seq_ms_per_step=7.0), dict(ok, seq_ms_per_step=6.0))
@@ -138,8 +138,8 @@ def test_mode_selection_is_cached_per_box(bench, monkeypatch, tmp_path):
     monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
     args = types.SimpleNamespace(config="T", streams=10, variant_probe=True)
     B1, note1 = bench.select_modes(args)
-    assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B1 == 10 and len(calls) == 4
+    assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B1 == 10 and len(calls) == 5
     monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
     B2, note2 = bench.select_modes(args)                      # second run on the same box: no probes, same decision
-    assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B2 == 10 and len(calls) == 4 and "cached" in note2 and note2.startswith(note1)
+    assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B2 == 10 and len(calls) == 5 and "cached" in note2 and note2.startswith(note1)
     monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
