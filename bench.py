@@ -219,6 +219,12 @@ def probe_batched(args, local_rank):
             e1.synchronize()
             ts.append(e0.elapsed_time(e1))
         out["seq_ms_per_step"] = float(np.median(ts[3:]))
+        try:          # the dominant kernel alone with this library (information for the next round; the decision does not use it)
+            fb = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            out["conv64_us_per_launch"] = 1e3 * dominant_kernel_roofline(model, frags[0], lambda: fb.fill_(1))["ms_per_launch"]
+            del fb
+        except Exception as ex:      # noqa: BLE001
+            out["conv64_us_per_launch"] = f"failed: {ex!r}"[:120]
         try:
             worst = 0.0
             for rep in range(2):          # the second round re-uses the captured plans
@@ -233,6 +239,15 @@ def probe_batched(args, local_rank):
             # expected 0 (same kernels, same per-row summation order); the parity bar against the oracle is 1e-4
             out["batched"] = "ok" if worst <= 1e-5 else "mismatch"
             out["max_rowwise_rel_diff_vs_forward_many"] = worst
+            ts = []
+            for i in range(6):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                model.forward_batches(dev_frags, B, streams=2)
+                e1.record()
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            out["batched_ms_per_2B_fragments"] = float(np.median(ts[2:]))
         except Exception as ex:      # noqa: BLE001
             out["batched"] = f"failed: {ex!r}"[:200]
     print(json.dumps(out))
@@ -285,6 +300,7 @@ def select_modes(args):
                 c = json.load(open(cache))
                 if c["variant"]:
                     os.environ["IMFNET_B200_VARIANT"] = c["variant"]
+                args.probe_table = c.get("table")
                 return int(c["batched"]), c["note"] + " [decision cached by an earlier bench.py run on this box]"
         except (OSError, ValueError, KeyError):
             pass
@@ -293,18 +309,23 @@ def select_modes(args):
         try:
             os.makedirs(CACHE_DIR, exist_ok=True)
             with open(cache, "w") as f:
-                json.dump({"batched": batched, "variant": variant, "note": note}, f)
+                json.dump({"batched": batched, "variant": variant, "note": note, "table": getattr(args, "probe_table", None)}, f)
         except OSError:
             pass
         return batched, note
+
+    def row(d):
+        return {k: d.get(k) for k in ("seq_ms_per_step", "conv64_us_per_launch", "batched", "batched_ms_per_2B_fragments", "B")}
 
     d0, n0 = run_probe(args)
     if d0 is None:
         return 0, f"default library: {n0} (batched plan and kernel variants not used)"
     chosen, best_name, notes = d0, "", []
+    args.probe_table = {"default": row(d0)}
     if os.environ.get("IMFNET_B200_VARIANT", "") == "" and args.variant_probe:
         for name in AUTO_VARIANTS:
             dx, nx = run_probe(args, name)
+            args.probe_table[name] = {"probe": nx} if dx is None else dict(row(dx), bit_identical=dx["hashes"] == d0["hashes"])
             if dx is None:
                 notes.append(f"variant {name}: {nx}")
             elif dx["hashes"] != d0["hashes"]:
@@ -529,6 +550,7 @@ def run_ours(args, rank, world, local_rank):
                                                  "voxels_per_s_e2e": target * args.steps * m["k"] / (m["ms_e2e"] * 1e-3)}
                                              for n, m in modes.items()},
                    "mode_selection": args.batched_note,
+                   "mode_probes": getattr(args, "probe_table", None),
                    "library": os.path.basename(_lib.lib_path()),
                    "parallelism": f"fragments sharded over {world} GPU(s), no data-path collective"},
         "e2e": {"value": e2e_v, "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -139,7 +139,12 @@ def test_mode_selection_is_cached_per_box(bench, monkeypatch, tmp_path):
     args = types.SimpleNamespace(config="T", streams=10, variant_probe=True)
     B1, note1 = bench.select_modes(args)
     assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B1 == 10 and len(calls) == 5
+    assert set(args.probe_table) == {"default", "x", "z", "y", "w"} and args.probe_table["x"]["bit_identical"] is True
+    assert args.probe_table["x"]["seq_ms_per_step"] == 8.0
+    table1 = args.probe_table
+    args = types.SimpleNamespace(config="T", streams=10, variant_probe=True)
     monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
     B2, note2 = bench.select_modes(args)                      # second run on the same box: no probes, same decision
     assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B2 == 10 and len(calls) == 5 and "cached" in note2 and note2.startswith(note1)
+    assert args.probe_table == table1
     monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
