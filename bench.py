@@ -133,7 +133,7 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def dominant_kernel_roofline(model, frag, flush):
+def dominant_kernel_roofline(model, frag, flush, layer="block2_tr.conv1"):
     """block2_tr-shaped convolution (64->64, 3^3, stride-1 level, BatchNorm + ReLU folded): the largest single launch of
     the forward (179.6 MB algorithmic bytes at C2), run through the same entry point and packed weights the
     forward uses (imf_sparse_conv_g4_fwd).  Timed live with CUDA events on the launching stream, L2 flushed between launches."""
@@ -144,7 +144,7 @@ def dominant_kernel_roofline(model, frag, flush):
     cm = CoordinateManager(coords)
     nbr_t, ld_n, tile_mask = cm.table_t(1, 1, 3, False)
     n = len(coords)
-    conv, packed, scale, shift, kci = model._plan.conv["block2_tr.conv1"]
+    conv, packed, scale, shift, kci = model._plan.conv[layer]
     cin, cout = conv.in_channels, conv.out_channels
     kco = 64 if cout % 64 == 0 else 32
     s = torch.cuda.current_stream().cuda_stream
@@ -174,7 +174,7 @@ def dominant_kernel_roofline(model, frag, flush):
     ms = float(np.mean(times))
     peak, how = load_peaks()
     achieved = alg_bytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": f"k_sparse_conv_g4<64,64> 3x3x3 {cin}->{cout} @ {n} voxels ({pairs} pairs)", "achieved": achieved,
+    return {"bound": "hbm", "kernel": f"k_sparse_conv_g4<{cout},{kci}> 3x3x3 {cin}->{cout} @ {n} voxels ({pairs} pairs)", "achieved": achieved,
             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "alg_bytes_per_launch": alg_bytes,
             "ms_per_launch": ms, "flops_per_launch": 2 * pairs * cin * cout, "peak_source": how,
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r01/call55_g4_ncu_summary.txt)"}
@@ -222,6 +222,7 @@ def probe_batched(args, local_rank):
         try:          # the dominant kernel alone with this library (information for the next round; the decision does not use it)
             fb = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
             out["conv64_us_per_launch"] = 1e3 * dominant_kernel_roofline(model, frags[0], lambda: fb.fill_(1))["ms_per_launch"]
+            out["conv32_us_per_launch"] = 1e3 * dominant_kernel_roofline(model, frags[0], lambda: fb.fill_(1), "block1.conv1")["ms_per_launch"]
             del fb
         except Exception as ex:      # noqa: BLE001
             out["conv64_us_per_launch"] = f"failed: {ex!r}"[:120]
@@ -315,7 +316,7 @@ def select_modes(args):
         return batched, note
 
     def row(d):
-        return {k: d.get(k) for k in ("seq_ms_per_step", "conv64_us_per_launch", "batched", "batched_ms_per_2B_fragments", "B")}
+        return {k: d.get(k) for k in ("seq_ms_per_step", "conv64_us_per_launch", "conv32_us_per_launch", "batched", "batched_ms_per_2B_fragments", "B")}
 
     d0, n0 = run_probe(args)
     if d0 is None:
