@@ -25,7 +25,7 @@ FLAGS += os.environ.get("IMFNET_B200_NVCC_FLAGS", "").split()
 # Kernel variants: the same sources with experiment switches on some files, linked into libimfnet_b200_<name>.so next to the default
 # library (all other objects are shared).  Selected at load time by IMFNET_B200_VARIANT=<name> (imfnet_b200/_lib.py); bench.py only
 # does so after a subprocess probe showed bit-identical descriptors and a shorter step on the GPU at hand.
-VARIANTS = {"x": {"sparse_conv_g4.cu": ["-DIMF_G4_LEAN_PRODUCER", "-DIMF_G4_VEC_RESIDUAL"],
+VARIANTS = {"x": {"sparse_conv_g4.cu": ["-DIMF_G4_LEAN_PRODUCER", "-DIMF_G4_VEC_RESIDUAL", "-DIMF_G4_NO_TRACE"],
                   "flash_fusion.cu": ["-DIMF_FLASH_UNIFORM_ISSUE"],
                   "tc_gemm.cu": ["-DIMF_TCGEMM_UNIFORM_ISSUE"]}}
 # z = x + zero fills of clean ring rows skipped (fewer LDGSTS wavefronts, more producer instructions: which wins is a measurement)

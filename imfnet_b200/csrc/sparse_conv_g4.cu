@@ -209,6 +209,9 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   __shared__ __align__(16) float sc_s[BN], sh_s[BN];
   __shared__ __align__(16) int idx_s[NPROD][2][HROWS]; // neighbour indices of each producer warp's current / next stage
 
+#if defined(IMF_G4_NO_TRACE)
+  trace = nullptr;      // EXPERIMENT (variant libraries): the clock64 trace hooks compile away (a few predicated instructions per stage)
+#endif
   int n = n_max;
   if (n_ptr) { const int v = *n_ptr; n = v < n_max ? v : n_max; }
   if (n <= 0) return;
