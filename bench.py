@@ -133,7 +133,7 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def dominant_kernel_roofline(model, frag, flush, layer="block2_tr.conv1"):
+def dominant_kernel_roofline(model, frag, flush, layer="block2_tr.conv1", check=True):
     """block2_tr-shaped convolution (64->64, 3^3, stride-1 level, BatchNorm + ReLU folded): the largest single launch of
     the forward (179.6 MB algorithmic bytes at C2), run through the same entry point and packed weights the
     forward uses (imf_sparse_conv_g4_fwd).  Timed live with CUDA events on the launching stream, L2 flushed between launches."""
@@ -170,7 +170,7 @@ def dominant_kernel_roofline(model, frag, flush, layer="block2_tr.conv1"):
         torch.cuda.synchronize()
         if i >= 3:
             times.append(e0.elapsed_time(e1))
-    assert int(err.item()) == 0
+    assert not check or int(err.item()) == 0
     ms = float(np.mean(times))
     peak, how = load_peaks()
     achieved = alg_bytes / (ms * 1e-3) / 1e9
@@ -223,6 +223,19 @@ def probe_batched(args, local_rank):
             fb = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
             out["conv64_us_per_launch"] = 1e3 * dominant_kernel_roofline(model, frags[0], lambda: fb.fill_(1))["ms_per_launch"]
             out["conv32_us_per_launch"] = 1e3 * dominant_kernel_roofline(model, frags[0], lambda: fb.fill_(1), "block1.conv1")["ms_per_launch"]
+            # the kernel's own profiling flags (results meaningless, timing only): 3 = no gathers + no weight copies, 6 = no gathers +
+            # no MMAs, 7 = pipeline skeleton only -- what tools/conv_g4_bench.py --flags prints
+            from imfnet_b200 import _lib
+            out["conv64_us_by_debug_flags"] = {}
+            try:
+                for fl in (3, 6, 7):
+                    _lib.lib().imf_debug_conv_g4_trace(None, 0, 0, fl)
+                    out["conv64_us_by_debug_flags"][str(fl)] = 1e3 * dominant_kernel_roofline(model, frags[0], lambda: fb.fill_(1),
+                                                                                             check=False)["ms_per_launch"]
+            except Exception as ex:      # noqa: BLE001
+                out["conv64_us_by_debug_flags"]["error"] = f"{ex!r}"[:120]
+            finally:
+                _lib.lib().imf_debug_conv_g4_trace(None, 0, 0, 0)
             del fb
         except Exception as ex:      # noqa: BLE001
             out["conv64_us_per_launch"] = f"failed: {ex!r}"[:120]
@@ -316,7 +329,7 @@ def select_modes(args):
         return batched, note
 
     def row(d):
-        return {k: d.get(k) for k in ("seq_ms_per_step", "conv64_us_per_launch", "conv32_us_per_launch", "batched", "batched_ms_per_2B_fragments", "B")}
+        return {k: d.get(k) for k in ("seq_ms_per_step", "conv64_us_per_launch", "conv32_us_per_launch", "conv64_us_by_debug_flags", "batched", "batched_ms_per_2B_fragments", "B")}
 
     d0, n0 = run_probe(args)
     if d0 is None:
