@@ -243,11 +243,12 @@ def probe_batched(args, local_rank):
         # the L2's size: the smaller batch may be the faster one); each must reproduce forward_many before its time counts
         out["batched_by_size"] = {}
         best = None
-        for b in [B] + ([B // 2] if B >= 4 else []):
+        sizes = [int(x) for x in args.probe_sizes.split(",") if x] if args.probe_sizes else [B] + ([B // 2] if B >= 4 else [])
+        for b in sizes:
             rec = {}
             try:
                 worst = 0.0
-                sub_d, sub_p, sub_r = dev_frags[:2 * b], pin_frags[:2 * b], ref[:2 * b]
+                sub_d, sub_p, sub_r = dev_frags[:2 * b], pin_frags[:2 * b], ref[:2 * b]          # (b <= B: 2 B fragments were prepared)
                 for rep in range(2):          # the second round re-uses the captured plans
                     outs = model.forward_batches(sub_d, b, streams=2)
                     outs_h = model.forward_batches(sub_p, b, streams=2)
@@ -287,9 +288,11 @@ def probe_batched(args, local_rank):
     print(json.dumps(out))
 
 
-def run_probe(args, variant=""):
-    """One probe subprocess -> (dict or None, note)."""
+def run_probe(args, variant="", sizes=""):
+    """One probe subprocess -> (dict or None, note).  sizes: batch sizes of the batched plan to probe (default: --streams and half of it)."""
     cmd = [sys.executable, os.path.abspath(__file__), "--probe-batched", "--config", args.config, "--streams", str(args.streams)]
+    if sizes:
+        cmd += ["--probe-sizes", sizes]
     env = dict(os.environ)
     env.pop("IMFNET_B200_VARIANT", None)
     if variant:
@@ -357,8 +360,9 @@ def select_modes(args):
     chosen, best_name, notes = d0, "", []
     args.probe_table = {"default": row(d0)}
     if os.environ.get("IMFNET_B200_VARIANT", "") == "" and args.variant_probe:
+        sizes = str(d0["B"]) if d0.get("batched") == "ok" else ""      # the variants only probe the batch size the default library preferred
         for name in AUTO_VARIANTS:
-            dx, nx = run_probe(args, name)
+            dx, nx = run_probe(args, name, sizes)
             args.probe_table[name] = {"probe": nx} if dx is None else dict(row(dx), bit_identical=dx["hashes"] == d0["hashes"])
             if dx is None:
                 notes.append(f"variant {name}: {nx}")
@@ -607,6 +611,7 @@ def main():
                          "report the faster mode; 0: off; -1 (default): B = --streams if a parity probe of that path passes in a "
                          "subprocess on this GPU, else off")
     ap.add_argument("--probe-batched", action="store_true", help="(internal) probe subprocess of the automatic mode; prints one JSON line")
+    ap.add_argument("--probe-sizes", default="", help="(internal) batch sizes the probe tries for the batched plan, comma separated")
     ap.add_argument("--no-variant-probe", dest="variant_probe", action="store_false",
                     help="automatic mode: do not try the kernel variant library (imfnet_b200/build.py VARIANTS)")
     ap.add_argument("--profile", action="store_true", help="run only warm-up + steps (for ncu launch lists)")

@@ -92,7 +92,7 @@ def test_mode_selection_logic(bench, monkeypatch, tmp_path_factory):
     def with_probes(default, x, z, y=None, w=None):
         calls = []
 
-        def fake(args, v=""):
+        def fake(args, v="", sizes=""):
             calls.append(v)
             d = {"": default, "x": x, "z": z, "y": y, "w": w}[v]
             return (dict(d), "ok") if d is not None else (None, "probe failed (rc 1): boom")
@@ -129,7 +129,7 @@ def test_mode_selection_is_cached_per_box(bench, monkeypatch, tmp_path):
     ok = {"probe": "done", "B": 10, "hashes": ["a"], "seq_ms_per_step": 10.0, "batched": "ok", "max_rowwise_rel_diff_vs_forward_many": 0.0}
     calls = []
 
-    def fake(args, v=""):
+    def fake(args, v="", sizes=""):
         calls.append(v)
         return dict(ok, seq_ms_per_step=10.0 if v == "" else 8.0 if v == "x" else 9.0), "ok"
 
