@@ -12,10 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libimfnet_b200.so")
 
 
 def lib_path() -> str:
-    """IMFNET_B200_VARIANT=<name> (read when the library is first loaded) selects a kernel variant built by imfnet_b200/build.py
-    (same sources, experiment switches on some kernels); unset = the default library."""
-    v = os.environ.get("IMFNET_B200_VARIANT", "")
-    return os.path.join(_HERE, "csrc", f"libimfnet_b200_{v}.so") if v else LIB_PATH
+    return LIB_PATH
 
 _p, _i32, _i64, _sz, _f32, _f64 = C.c_void_p, C.c_int32, C.c_longlong, C.c_size_t, C.c_float, C.c_double
 
@@ -34,6 +31,7 @@ SIGNATURES = {
     "imf_last_error": (C.c_char_p, []),
     "imf_version": (C.c_int, []),
     "imf_launch_count": (_i64, []),
+    "imf_device_sm_count": (C.c_int, []),
     "imf_hash_capacity": (_i64, [_i64]),
     "imf_hash_bytes": (_sz, [_i64]),
     "imf_hash_clear": (C.c_int, [_p, _i64, _p]),
@@ -52,6 +50,7 @@ SIGNATURES = {
     "imf_parity_perm": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _sz, _p]),
     "imf_debug_conv_g4_trace": (C.c_int, [_p, _i32, _i32, _i32]),
     "imf_quantize_points": (C.c_int, [_p, _i32, _f64, _i32, _p, _p]),
+    "imf_quantize_points_f32": (C.c_int, [_p, _i32, _f32, _i32, _p, _p]),
     "imf_batch_segments": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
     "imf_batch_segments_n": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
     "imf_h2_unpack_seg": (C.c_int, [_p, _i32, _p, _p, _i32, _i32, _i32, _p, _i32, _p]),
@@ -65,13 +64,6 @@ SIGNATURES = {
     "imf_attention_fusion_fwd_m": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _p, _i32, _p, _i32, _p, _sz, _p]),
     "imf_sparse_conv_h2_packed_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "imf_sparse_conv_h2_pack": (C.c_int, [_p, _i32, _i32, _i32, _i32, _f32, _p, _p]),
-    "imf_sparse_conv_h2_workspace_bytes": (_sz, [_i32, _i32]),
-    "imf_sparse_conv_h2_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i32, _p, _i32,
-                                        _i32, _p, _sz, _p, _p]),
-    "imf_debug_conv_flags": (C.c_int, [_i32]),
-    "imf_debug_conv_trace": (C.c_int, [_p]),
-    "imf_debug_gather4": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _p, _i32, _i32, _p, _p]),
-    "imf_debug_gather4_rate": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "imf_conv_first_h2_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p]),
     "imf_pointwise_tail_h2_fwd": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _p, _i32, _p]),
     "imf_conv_first_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _p]),
@@ -109,6 +101,11 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = l
     return _lib
+
+
+def sm_count() -> int:
+    """SMs of the current CUDA device (the persistent kernels' grid size)."""
+    return int(lib().imf_device_sm_count())
 
 
 def check(rc: int):

@@ -19,8 +19,8 @@ What is specific to a batch:
   * the fusion module runs per item on forked streams; the per-item row ranges at stride 8 stay on the device
     (csrc/batched.cu: imf_batch_segments_n, imf_h2_unpack_seg, imf_h2_pack_seg).
 
-STATUS: written against the verified single-fragment plan without GPU access (the round's GPU budget was spent); the GPU test
-is marked `unverified` and `bench.py` only takes this path when asked to.  See DESIGN.md section 7.
+This is the execution mode bench.py measures; tests/test_gpu_batched.py checks it against the CPU oracle, the reference's golden
+outputs and forward() (bit-identical) on the GPU, tests/test_plan_emulated.py its host logic on the C-ABI emulator.
 """
 from __future__ import annotations
 
@@ -34,8 +34,8 @@ from .model.Img_Encoder import ImagePlan
 class BatchedImagePlan(ImagePlan):
     """ImagePlan over B images of one size: pixel rows of image b are rows [b*P, (b+1)*P) of every matrix."""
 
-    def __init__(self, backbone, H: int, W: int, B: int):
-        super().__init__(backbone, H, W, False)
+    def __init__(self, backbone, H: int, W: int, B: int, err=None):
+        super().__init__(backbone, H, W, False, err=err)
         self.B = B = int(B)
         dev = self.device
         with torch.cuda.device(dev):
@@ -120,7 +120,7 @@ class BatchGraphPlan(GraphPlan):
         u8 = dict(dtype=torch.uint8, device=dev)
         self.image = torch.zeros((self.B, 3, self.H, self.W), **f32)
         with torch.cuda.device(dev):
-            self.image_plan = BatchedImagePlan(m.img_encoder.backbone, self.H, self.W, self.B)
+            self.image_plan = BatchedImagePlan(m.img_encoder.backbone, self.H, self.W, self.B, err=self.err)
         self.n_tok = self.image_plan.P2
         self.P8 = self.fused32 = None
         self.seg = torch.zeros(self.B + 1, **i32)
@@ -134,8 +134,9 @@ class BatchGraphPlan(GraphPlan):
     # -- the two steps of GraphPlan._enqueue that a batch changes ------------------------------------------------------------
     def _enqueue_image(self, m, main):
         """Image branch on a forked stream: ONE encoder pass over all images, then K / V of every item."""
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
+        side = main if self._tl is not None else self.side          # (layer timing: nothing runs beside the timed kernels)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
             tokens = self.image_plan.enqueue(self.image)
             P2 = self.image_plan.P2
             self.kvs = [m.attention_fusion.project_context(tokens[b * P2:(b + 1) * P2], False) for b in range(self.B)]
@@ -305,6 +306,7 @@ def forward_batches(model, frags, batch: int, streams: int = 2, out=None):
             dsts = [out[i] if out is not None else torch.empty((sizes[j], model.out_channels), dtype=torch.float32, pin_memory=True)
                     for j, i in enumerate(idx)]
         g.launch_batch([(frags[i][0], frags[i][1].float(), frags[i][2].float()) for i in idx], g.stream, out_hosts=dsts)
+        model._last_batch_plan = g          # (bench.py times this plan's layers in place)
         inflight.append((idx, g))
     while inflight:
         retire()

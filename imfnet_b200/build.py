@@ -18,26 +18,8 @@ LIB = os.path.join(CSRC, "libimfnet_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-# experiment switches of the kernels (e.g. IMFNET_B200_NVCC_FLAGS="-DIMF_G4_SKIP_CLEAN_ZERO" + --force); empty in the shipped build
+# extra switches for profiling builds (e.g. IMFNET_B200_NVCC_FLAGS="-DIMF_G4_TRACE" + --force); empty in the shipped build
 FLAGS += os.environ.get("IMFNET_B200_NVCC_FLAGS", "").split()
-
-
-# Kernel variants: the same sources with experiment switches on some files, linked into libimfnet_b200_<name>.so next to the default
-# library (all other objects are shared).  Selected at load time by IMFNET_B200_VARIANT=<name> (imfnet_b200/_lib.py); bench.py only
-# does so after a subprocess probe showed bit-identical descriptors and a shorter step on the GPU at hand.
-VARIANTS = {"x": {"sparse_conv_g4.cu": ["-DIMF_G4_LEAN_PRODUCER", "-DIMF_G4_VEC_RESIDUAL", "-DIMF_G4_NO_TRACE"],
-                  "flash_fusion.cu": ["-DIMF_FLASH_UNIFORM_ISSUE"],
-                  "tc_gemm.cu": ["-DIMF_TCGEMM_UNIFORM_ISSUE"]}}
-# z = x + zero fills of clean ring rows skipped (fewer LDGSTS wavefronts, more producer instructions: which wins is a measurement)
-VARIANTS["z"] = dict(VARIANTS["x"], **{"sparse_conv_g4.cu": VARIANTS["x"]["sparse_conv_g4.cu"] + ["-DIMF_G4_SKIP_CLEAN_ZERO"]})
-# y = x + the MMA warps of the convolution kernel pass their turn on before issuing (shorter hand-off chain; same single-owner accumulators)
-VARIANTS["y"] = dict(VARIANTS["x"], **{"sparse_conv_g4.cu": VARIANTS["x"]["sparse_conv_g4.cu"] + ["-DIMF_G4_EARLY_TURN"]})
-VARIANTS["w"] = dict(VARIANTS["x"], **{"sparse_conv_g4.cu": VARIANTS["z"]["sparse_conv_g4.cu"] + ["-DIMF_G4_EARLY_TURN"]})      # z + y
-AUTO_VARIANTS = ["x", "z", "y", "w"]      # what bench.py's automatic mode may load (bit-identical descriptors and a shorter step required)
-
-
-def lib_path(variant: str = "") -> str:
-    return LIB if not variant else os.path.join(CSRC, f"libimfnet_b200_{variant}.so")
 
 
 def sources():
@@ -61,19 +43,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
         if force or _stale(o, [s] + headers):
             jobs.append((s, o, []))
-    variant_objs = {}
-    for name, switches in VARIANTS.items():
-        vobjs = []
-        for src in sources():
-            o = os.path.join(CSRC, src[:-3] + ".o")
-            if src in switches:
-                s = os.path.join(CSRC, src)
-                o = os.path.join(CSRC, f"{src[:-3]}_{name}.o")
-                if force or _stale(o, [s] + headers):
-                    jobs.append((s, o, switches[src]))
-            vobjs.append(o)
-        variant_objs[name] = vobjs
-
     def compile_one(job):
         s, o, extra = job
         cmd = [NVCC] + ARCH + FLAGS + extra + ["-I", CSRC, "-I", os.path.join(HERE, "..", "include"), "-c", s, "-o", o]
@@ -86,13 +55,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 sys.stderr.write(f"--- {os.path.basename(s)} ---\n{r.stdout}{r.stderr}\n")
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {s}")
-    for target, tobjs in [(LIB, objs)] + [(lib_path(n), o) for n, o in variant_objs.items()]:
-        if jobs or force or _stale(target, tobjs):
-            cmd = [NVCC] + ARCH + ["-shared", "-o", target] + tobjs
-            r = subprocess.run(cmd, capture_output=True, text=True)
-            if r.returncode != 0:
-                sys.stderr.write(r.stdout + r.stderr)
-                raise RuntimeError("link failed")
+    if jobs or force or _stale(LIB, objs):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
     return LIB
 
 

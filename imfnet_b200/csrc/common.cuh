@@ -48,6 +48,9 @@ void imf_note_launch();   // bumps the process-wide kernel-launch counter report
 // few microseconds, too much for every launch of a 150-launch forward.  Defined in coords.cu.
 cudaError_t imf_set_max_smem_once(const void* kernel, int bytes);
 
+// SM count of the current device, cached (coords.cu); 148 when no device is present
+int imf_sm_count();
+
 // tensor-core GEMM (tc_gemm.cu), used by the attention-fusion orchestration in dense.cu
 extern "C" size_t imf_tc_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K);
 extern "C" int imf_tc_gemm(const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc, int32_t M, int32_t N,

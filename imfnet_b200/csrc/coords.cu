@@ -45,6 +45,23 @@ cudaError_t imf_set_max_smem_once(const void* kernel, int bytes) {
   return e;
 }
 
+// Number of SMs of the current device (cached per device): sizes the persistent grids and the split heuristics; 148 on a full B200,
+// fewer on other sm_100 SKUs or MIG slices.  Without a device (the CPU-side ABI tests) it reports the B200 count.
+int imf_sm_count() {
+  static std::mutex mu;
+  static std::vector<std::pair<int, int>> known;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& d : known)
+    if (d.first == dev) return d.second;
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+  known.emplace_back(dev, n);
+  return n;
+}
+extern "C" int imf_device_sm_count(void) { return imf_sm_count(); }
+
 void imf_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" long long imf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -339,6 +356,17 @@ __global__ void k_quantize_points(const double* __restrict__ xyz, int n, double 
   coords[i] = make_int4(batch, (int)x, (int)y, (int)z);
 }
 
+// float32 clouds: numpy computes np.floor(xyz / voxel_size) in the INPUT dtype (float32 array / Python float -> float32 quotient with
+// the divisor rounded to float32), so points next to a voxel boundary can land in another voxel than in float64; __fdiv_rn is the
+// correctly rounded IEEE division numpy performs (plain `/` may compile to an approximate sequence under fast-math flags).
+__global__ void k_quantize_points_f32(const float* __restrict__ xyz, int n, float voxel, int batch, int4* __restrict__ coords) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = floorf(__fdiv_rn(xyz[3 * (size_t)i + 0], voxel)), y = floorf(__fdiv_rn(xyz[3 * (size_t)i + 1], voxel)),
+              z = floorf(__fdiv_rn(xyz[3 * (size_t)i + 2], voxel));
+  coords[i] = make_int4(batch, (int)x, (int)y, (int)z);
+}
+
 // seg[b] = first row whose batch index is >= b (rows are batch-sorted); seg[B] = n.
 __global__ void k_batch_segments(const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max, int B,
                                  int* __restrict__ seg) {
@@ -506,6 +534,16 @@ extern "C" int imf_quantize_points(const double* xyz, int32_t n, double voxel_si
   if (n == 0) return IMF_OK;
   IMF_CHECK_ARG(xyz != nullptr && coords != nullptr);
   k_quantize_points<<<(n + 255) / 256, 256, 0, stream>>>(xyz, n, voxel_size, batch_index, reinterpret_cast<int4*>(coords));
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
+}
+
+extern "C" int imf_quantize_points_f32(const float* xyz, int32_t n, float voxel_size, int32_t batch_index, int32_t* coords,
+                                       cudaStream_t stream) {
+  IMF_CHECK_ARG(n >= 0 && voxel_size > 0.f);
+  if (n == 0) return IMF_OK;
+  IMF_CHECK_ARG(xyz != nullptr && coords != nullptr);
+  k_quantize_points_f32<<<(n + 255) / 256, 256, 0, stream>>>(xyz, n, voxel_size, batch_index, reinterpret_cast<int4*>(coords));
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }

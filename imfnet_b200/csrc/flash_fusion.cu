@@ -154,17 +154,12 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc::mbar_wait(&full[st], ((uint32_t)(it >> 1)) & 1u, err, 3);
         tc::mbar_wait(&s_free, ((uint32_t)it & 1u) ^ 1u, err, 4);            // softmax warps have read the previous S
         tc::tc_fence_after_sync();
-#if defined(IMF_FLASH_UNIFORM_ISSUE)
-        // EXPERIMENT (variant library x): issued from `if (lane == 0)` every tcgen05.mma is wrapped by ptxas in an
-        // ELECT / R2UR / BRA.U.ANY loop (the same finding as in sparse_conv_g4.cu); warp-uniform operands + elect.sync give bare UTCHMMAs
+        // issued from `if (lane == 0)` every tcgen05.mma is wrapped by ptxas in an ELECT / R2UR / BRA.U.ANY loop (the same finding as
+        // in sparse_conv_g4.cu); warp-uniform operands + elect.sync give bare UTCHMMAs
         const uint32_t q0 = __shfl_sync(0xffffffffu, tc::smem_u32(q_s), 0), k0 = __shfl_sync(0xffffffffu, tc::smem_u32(ring + st * kStage), 0);
         const uint32_t tmem_s_u = __shfl_sync(0xffffffffu, tmem_s, 0);
         if (tc::elect_one()) {
 #define tmem_s tmem_s_u
-#else
-        if (lane == 0) {
-          const uint32_t q0 = tc::smem_u32(q_s), k0 = tc::smem_u32(ring + st * kStage);
-#endif
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const uint32_t qhi = q0 + (2 * c) * kQImg, qlo = qhi + kQImg, kb = k0 + (2 * c) * kKImg;     // [Khi_c ; Klo_c] = 128 rows
@@ -178,23 +173,16 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tc::mma_commit(&s_ready);
           if (pass == 0) tc::mma_commit(&empty[st]);
         }
-#if defined(IMF_FLASH_UNIFORM_ISSUE)
 #undef tmem_s
-#endif
         __syncwarp();
         if (pass == 1) {
           tc::mbar_wait(&p_ready, (uint32_t)b & 1u, err, 5);                  // P of this block is in shared memory
           tc::tc_fence_after_sync();
-#if defined(IMF_FLASH_UNIFORM_ISSUE)
           const uint32_t p0 = __shfl_sync(0xffffffffu, tc::smem_u32(p_s), 0);
-          const uint32_t v0 = __shfl_sync(0xffffffffu, tc::smem_u32(ring + st * kStage + kKBytes), 0);
+          const uint32_t v0 = __shfl_sync(0xffffffffu, tc::smem_u32(ring + st * kStage + kKBytes), 0);       // [Vhi ; Vlo] = 256 rows
           const uint32_t tmem_o_u = __shfl_sync(0xffffffffu, tmem_o, 0);
           if (tc::elect_one()) {
 #define tmem_o tmem_o_u
-#else
-          if (lane == 0) {
-            const uint32_t p0 = tc::smem_u32(p_s), v0 = tc::smem_u32(ring + st * kStage + kKBytes);       // [Vhi ; Vlo] = 256 rows
-#endif
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t o = ks * 32;
@@ -204,18 +192,12 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tc::mma_commit(&empty[st]);
             tc::mma_commit(&p_free);
           }
-#if defined(IMF_FLASH_UNIFORM_ISSUE)
 #undef tmem_o
-#endif
           __syncwarp();
         }
       }
     }
-#if defined(IMF_FLASH_UNIFORM_ISSUE)
     if (tc::elect_one()) tc::mma_commit(&o_done);      // same thread as the MMAs above (elect.sync is deterministic per mask)
-#else
-    if (lane == 0) tc::mma_commit(&o_done);
-#endif
     __syncwarp();
   } else {
     // =========================== softmax (4 warps, one query row per thread) ===========================
@@ -325,7 +307,7 @@ __global__ void __launch_bounds__(256) k_flash_combine(const float* __restrict__
 inline int ff_lpad(int L) { return (L + kTB - 1) / kTB * kTB; }
 inline int ff_nsplit(int M_max, int L) {
   const int tiles = (M_max + kTQ - 1) / kTQ, nblocks = (L + kTB - 1) / kTB;
-  int ns = (2 * 148 + tiles - 1) / tiles;          // about two waves of CTAs when every tile is active
+  int ns = (2 * imf_sm_count() + tiles - 1) / tiles;          // about two waves of CTAs when every tile is active
   if (ns > nblocks) ns = nblocks;
   if (ns > 32) ns = 32;
   return ns < 1 ? 1 : ns;

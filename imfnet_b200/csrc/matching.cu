@@ -68,7 +68,7 @@ extern "C" int imf_nn_search(const float* A, int32_t lda, int32_t na, const floa
   IMF_CHECK_CUDA(cudaMemsetAsync(best, 0xFF, (size_t)na * sizeof(unsigned long long), stream));
   if (nb > 0) {
     const int qblocks = (na + kQ - 1) / kQ;
-    int chunks = (2 * 148 + qblocks - 1) / qblocks;                 // about two CTAs per SM
+    int chunks = (2 * imf_sm_count() + qblocks - 1) / qblocks;                 // about two CTAs per SM
     const int max_chunks = (nb + kTB - 1) / kTB;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;

@@ -425,17 +425,18 @@ extern "C" int imf_sparse_conv_fwd(const float* X, int32_t ldx, const float* W, 
                              relu, Y, ldy, stream)
   // Tile choice: widest channel tile that divides Cout; shrink the row tile while the grid would leave SMs idle.
   const long long n = n_out_max;
+  const int sms = imf_sm_count();
   if (Cout % 128 == 0) {
-    if ((n + 63) / 64 * (Cout / 128) >= 148) IMF_GO(8, 4);
-    if ((n + 31) / 32 * (Cout / 64) >= 148 || n <= 32) IMF_GO(4, 2);
+    if ((n + 63) / 64 * (Cout / 128) >= sms) IMF_GO(8, 4);
+    if ((n + 31) / 32 * (Cout / 64) >= sms || n <= 32) IMF_GO(4, 2);
     IMF_GO(2, 2);
   }
   if (Cout % 64 == 0) {
-    if ((n + 127) / 128 * (Cout / 64) >= 148) IMF_GO(16, 2);
-    if ((n + 31) / 32 * (Cout / 64) >= 148 || n <= 32) IMF_GO(4, 2);
+    if ((n + 127) / 128 * (Cout / 64) >= sms) IMF_GO(16, 2);
+    if ((n + 31) / 32 * (Cout / 64) >= sms || n <= 32) IMF_GO(4, 2);
     IMF_GO(2, 2);
   }
-  if ((n + 127) / 128 * (Cout / 32) >= 148) IMF_GO(16, 1);
+  if ((n + 127) / 128 * (Cout / 32) >= sms) IMF_GO(16, 1);
   IMF_GO(4, 1);
 #undef IMF_GO
 }

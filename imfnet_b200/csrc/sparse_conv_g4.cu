@@ -42,7 +42,6 @@ constexpr int kNMW = 4;                  // MMA issuing warps (8-11)
 constexpr int kNXW = 2;                  // extra gather producer warps (13-14) for the 5-slot configurations
 constexpr int kNW = 2;                   // weight-slab ring depth
 constexpr int kMaxSubAll = 8;            // 512 TMEM columns / (2 * 32)
-constexpr int kSMs = 148;
 
 template <int BN, int KC>
 struct G4Cfg {
@@ -155,15 +154,11 @@ __device__ __forceinline__ void g4_load16_h2(const __half* hi_src, const __half*
   const Half8* ls = reinterpret_cast<const Half8*>(lo_src);
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
-#if defined(IMF_G4_VEC_RESIDUAL)
-    // EXPERIMENT (variant library x): the struct copies below compile to eight 4-byte LDG.E.CONSTANT per 32 bytes; explicit 16-byte loads
+    // explicit 16-byte loads (plain struct copies compile to eight 4-byte LDG.E.CONSTANT per 32 bytes)
     const int4 h4 = __ldg(reinterpret_cast<const int4*>(hs) + q), l4 = __ldg(reinterpret_cast<const int4*>(ls) + q);
     Half8 h, l;
     *reinterpret_cast<int4*>(&h) = h4;
     *reinterpret_cast<int4*>(&l) = l4;
-#else
-    const Half8 h = hs[q], l = ls[q];
-#endif
     const __half2 hv[4] = {h.a, h.b, h.c, h.d}, lv[4] = {l.a, l.b, l.c, l.d};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -209,8 +204,8 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   __shared__ __align__(16) float sc_s[BN], sh_s[BN];
   __shared__ __align__(16) int idx_s[NPROD][2][HROWS]; // neighbour indices of each producer warp's current / next stage
 
-#if defined(IMF_G4_NO_TRACE)
-  trace = nullptr;      // EXPERIMENT (variant libraries): the clock64 trace hooks compile away (a few predicated instructions per stage)
+#if !defined(IMF_G4_TRACE)
+  trace = nullptr;      // the clock64 trace hooks only exist in a -DIMF_G4_TRACE build (tools/conv_g4_bench.py --trace)
 #endif
   int n = n_max;
   if (n_ptr) { const int v = *n_ptr; n = v < n_max ? v : n_max; }
@@ -388,26 +383,15 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       int my_ac = ac + first_i;
       uint32_t my_phase = pslot >= a_slot ? a_phase : a_phase ^ 1u;                // phase of slot `pslot` at its next use
       int slot = 0;
-#if defined(IMF_G4_SKIP_CLEAN_ZERO)
-      unsigned dirty = 0xFFFFFFFFu;
-      static_assert(NINS <= 32, "one dirty bit per copy instruction of a lane");
-#endif
-#if defined(IMF_G4_LEAN_PRODUCER)
-      // EXPERIMENT (off in the default build): the default build spends ~12 ALU instructions per LDGSTS
-      // (swizzled shared address recomputed per copy, 64-bit base + chunk offset added per copy).  Row srow + i of instruction
-      // group i4 is half*HROWS + 4*RPI*i4 + q with q = 4*hw + i, so its swizzled offset is i4 * (RPI/2) * 1024 + a per-lane
-      // constant: four destination registers per lane, the i4 term an immediate of the fully unrolled loop.
+      // The swizzled shared-memory address of a copy is not recomputed per LDGSTS (that cost ~12 ALU instructions per copy and made
+      // the producers issue-bound): row half*HROWS + 4*RPI*i4 + q of instruction group i4 (q = 4*hw + i) has the swizzled offset
+      // i4 * (RPI/2) * 1024 + a per-lane constant, so four destination registers per lane are enough and the i4 term is an
+      // immediate of the fully unrolled loop (4.25 instructions per LDGSTS in the SASS).
       uint32_t dstq[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) dstq[i] = ring_base + pslot * Cfg::A_BYTES + tc::sw128_offset(half * HROWS + 4 * hw + i, c16);
 #define G4_DST(i4, i) (dstq[i] + (uint32_t)((i4) * (RPI / 2) * 1024))
 #define G4_SRC(r) reinterpret_cast<const char*>(xb + (unsigned long long)((unsigned)max((r), 0)) * ldx_bytes)
-#define G4_COPY_UNROLL _Pragma("unroll")
-#else
-#define G4_DST(i4, i) (stg + tc::sw128_offset(srow + (i), c16))
-#define G4_SRC(r) (xc + (unsigned long long)((unsigned)max((r), 0)) * ldx_bytes)
-#define G4_COPY_UNROLL _Pragma("unroll 4")
-#endif
       if (it.w < w_end) prefetch(it, 0);
       g4_cp_async_commit();
       g4_cp_async_commit();                                               // (empty) keeps the group arithmetic uniform
@@ -421,49 +405,22 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
         if (trace && lane == 0 && half == 0 && my_ac < 36) trace[17 + 4 * my_ac] = clock64();
         g4_cp_async_wait<2>();             // pending at most: the previous stage's rows and the prefetch just issued
         __syncwarp();
-        const uint32_t stg = ring_base + pslot * Cfg::A_BYTES;
-        const char* xc = xthr + it.chunk * (4 * KC);
         const int4* idx4p = reinterpret_cast<const int4*>(my_idx + slot * HROWS);
-#if defined(IMF_G4_LEAN_PRODUCER)
-        unsigned long long xb = reinterpret_cast<unsigned long long>(xc);
+        unsigned long long xb = reinterpret_cast<unsigned long long>(xthr + it.chunk * (4 * KC));
         asm volatile("" : "+l"(xb));        // keep base + chunk offset in one register pair (one IMAD.WIDE per copy)
-#endif
-#if defined(IMF_G4_SKIP_CLEAN_ZERO)
-        unsigned dirty_next = 0u;
-#endif
         if (!(dbg & 2)) {
-          G4_COPY_UNROLL
+#pragma unroll
           for (int i4 = 0; i4 < NINS / 4; ++i4) {
             const int m = RPI * i4 + hw;                                  // row group (of this warp's half) for these 4 instructions
             const int4 r = idx4p[m];
             const int r4[4] = {r.x, r.y, r.z, r.w};
-            const int srow = half * HROWS + 4 * m;
-#if defined(IMF_G4_SKIP_CLEAN_ZERO)
-            // EXPERIMENT (off in the default build): an absent neighbour only needs its zero fill when the
-            // row of this ring slot still holds data of an earlier stage; `dirty` tracks that per (lane, instruction), so about
-            // half of the zero-fill wavefronts disappear.  Every row counts as dirty at the start of a pass (uninitialised
-            // shared memory / the epilogue's staging buffers live in the ring).
-            // (after this stage a row is dirty exactly when its neighbour was present: an absent one is clean either way)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const unsigned bit = 1u << (4 * i4 + i);
-              if (r4[i] >= 0 || (dirty & bit)) g4_cp_async16_row(G4_DST(i4, i), G4_SRC(r4[i]), r4[i]);
-              dirty_next |= r4[i] >= 0 ? bit : 0u;
-            }
-#else
 #pragma unroll
             for (int i = 0; i < 4; ++i)      // absent neighbour: the (valid) address of row 0 is passed but ignored (zero fill)
               g4_cp_async16_row(G4_DST(i4, i), G4_SRC(r4[i]), r4[i]);
-#endif
-            (void)srow;
           }
-#if defined(IMF_G4_SKIP_CLEAN_ZERO)
-          dirty = dirty_next;
-#endif
         }
 #undef G4_DST
 #undef G4_SRC
-#undef G4_COPY_UNROLL
         g4_cp_async_arrive_noinc(&full_a[pslot]);                         // fires when this thread's copies have landed
         g4_cp_async_commit();
         my_ac += NA;
@@ -522,15 +479,13 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
         }
         const int owner = (dbg & 8) ? 0 : (dbg & 16) ? (ac & (kNMW - 1)) : (cur.j & (kNMW - 1));
         if (owner == mw) {
-          // stages are ISSUED in walk order whichever warp owns them (a turn counter in shared memory).  Waiting for the turn
-          // BEFORE the slot's barrier also keeps the parity wait unambiguous: every earlier stage, hence the previous use of
-          // this ring slot, has been consumed by then.
-#if defined(IMF_G4_EARLY_TURN)
-          // EXPERIMENT (variant library y only, never selected automatically): the hand-off chain between
-          // the MMA warps (turn -> slot barrier -> descriptors -> 8 MMAs -> turn store) is what a stage costs when nothing else
-          // stalls.  The descriptors do not depend on the turn, and the turn only has to order the WAITS on the ring (parity),
-          // not the MMAs (every accumulator has one issuing thread): build the descriptors first and pass the turn on as soon
-          // as this stage's slot has been seen full, before issuing.
+          // The slot barriers are WAITED ON in walk order whichever warp owns the stage (a turn counter in shared memory): every
+          // earlier stage's slot has been seen full by then, so a waiter is never more than one phase off.
+          // The hand-off chain between the MMA warps is what a stage costs when nothing else stalls.  The descriptors do not
+          // depend on the turn, and the turn only has to order the WAITS on the ring (parity), not the MMAs (every accumulator
+          // has one issuing thread): the descriptors are built first (warp-uniform values shuffled from lane 0, so the compiler
+          // keeps them in uniform registers and emits bare UTCHMMA instructions) and the turn is passed on as soon as this
+          // stage's slot has been seen full, before issuing.
           const uint32_t a0 = __shfl_sync(0xffffffffu, tc::smem_u32(a_ring + a_slot * Cfg::A_BYTES), 0);
           const uint32_t w0 = __shfl_sync(0xffffffffu, tc::smem_u32(w_ring + ws * Cfg::W_BYTES), 0);
           const uint32_t d = __shfl_sync(0xffffffffu, tmem_d + (uint32_t)(cur.j * Cfg::ACC_COLS), 0);
@@ -540,18 +495,6 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
           if (trace && lane == 0 && ac < 36) trace[18 + 4 * ac] = clock64();
           if (tc::elect_one()) {
             *reinterpret_cast<volatile int*>(&turn_s) = ac + 1;
-#else
-          while (*reinterpret_cast<volatile int*>(&turn_s) != ac) {}
-          tc::mbar_wait(&full_a[a_slot], a_phase, err, 4);
-          // operand addresses as warp-uniform values (shuffles from lane 0): the compiler then keeps the descriptors in uniform
-          // registers and emits bare UTCHMMA instructions instead of an elect / R2UR / branch loop around each of them
-          const uint32_t a0 = __shfl_sync(0xffffffffu, tc::smem_u32(a_ring + a_slot * Cfg::A_BYTES), 0);
-          const uint32_t w0 = __shfl_sync(0xffffffffu, tc::smem_u32(w_ring + ws * Cfg::W_BYTES), 0);
-          const uint32_t d = __shfl_sync(0xffffffffu, tmem_d + (uint32_t)(cur.j * Cfg::ACC_COLS), 0);
-          const uint64_t da = tc::smem_desc_sw128(a0), dw = tc::smem_desc_sw128(w0);
-          if (trace && lane == 0 && ac < 36) trace[18 + 4 * ac] = clock64();
-          if (tc::elect_one()) {
-#endif
             if (dbg & 4) {
             } else if (KC == 64) {
               // (descriptor start-address field = byte address >> 4: the hi image is at +0, the lo image at +kImg)
@@ -568,9 +511,6 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
                 g4_mma_f16(d, da + (uint64_t)(4 + ks * 2), dw + (uint64_t)(4 + ks * 2), idesc1, 1u);          // lo . Whi
               }
             }
-#if !defined(IMF_G4_EARLY_TURN)
-            *reinterpret_cast<volatile int*>(&turn_s) = ac + 1;
-#endif
             tc::mma_commit(&empty_a[a_slot]);
           }
           if (trace && lane == 0 && ac < 36) trace[19 + 4 * ac] = clock64();
@@ -805,10 +745,11 @@ int launch_g4(const __half* X, int ldx, const CUtensorMap& tmY, const void* Wp, 
   const int nchunks = Cin / KC;
   // one CTA per SM and output-channel tile, whatever n_max: the row partition (hence the fp32 summation order of the split mode)
   // then depends only on the actual row count, so a fragment gives the same bits in an exact-size and in a bucketed launch
-  const int gx = (g_g4_grid > 0 ? g_g4_grid : kSMs) / ntn;
+  const int sms = imf_sm_count();
+  const int gx = (g_g4_grid > 0 ? g_g4_grid : sms) / ntn;
   const int nst_max = K3 * nchunks;
   float* P = nullptr;
-  if (ws != nullptr && ws_bytes >= (size_t)kSMs * kBM * Cout * sizeof(float)) P = reinterpret_cast<float*>(ws);
+  if (ws != nullptr && ws_bytes >= (size_t)sms * kBM * Cout * sizeof(float)) P = reinterpret_cast<float*>(ws);
   dim3 grid(gx, 1, ntn);
   k_sparse_conv_g4<BN, KC><<<grid, Cfg::THREADS, smem, stream>>>(X, ldx, tmY, reinterpret_cast<const unsigned char*>(Wp), nbr_t, ld_n, tile_mask,
                                                             n_ptr, n_max, K3, nchunks, scale, shift, R, ldr, kc_r, relu, kc_out, P, Cout,
@@ -834,7 +775,7 @@ extern "C" int imf_debug_conv_g4_trace(long long* trace, int32_t grid, int32_t p
   return IMF_OK;
 }
 
-extern "C" size_t imf_sparse_conv_g4_workspace_bytes(int32_t Cout) { return (size_t)kSMs * kBM * (size_t)Cout * sizeof(float); }
+extern "C" size_t imf_sparse_conv_g4_workspace_bytes(int32_t Cout) { return (size_t)imf_sm_count() * kBM * (size_t)Cout * sizeof(float); }
 
 extern "C" int imf_sparse_conv_g4_fwd_perm(const void* X, int32_t ldx, int32_t kc_in, const void* packed, const int32_t* nbr_t,
                                            int32_t ld_n, const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max,

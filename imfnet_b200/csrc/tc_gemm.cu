@@ -177,17 +177,12 @@ __global__ void __launch_bounds__(288, 1) k_tc_gemm(const float* __restrict__ A,
       const uint32_t ph = (uint32_t)(kc / kNS) & 1u;
       tc::mbar_wait(&full_bar[s], ph, err, 2);
       tc::tc_fence_after_sync();
-#if defined(IMF_TCGEMM_UNIFORM_ISSUE)
-      // EXPERIMENT (variant library x): warp-uniform operands + elect.sync instead of `if (lane == 0)`, so that
-      // ptxas emits bare UTC*MMA instructions instead of an ELECT / R2UR / BRA.U.ANY loop around each (see sparse_conv_g4.cu)
+      // warp-uniform operands + elect.sync instead of `if (lane == 0)`, so that ptxas emits bare UTC*MMA instructions instead of an
+      // ELECT / R2UR / BRA.U.ANY loop around each (see sparse_conv_g4.cu)
       const uint32_t a_hi = __shfl_sync(0xffffffffu, tc::smem_u32(smem + s * STAGE_BYTES), 0), a_lo = a_hi + A_BYTES;
       const uint32_t tmem_d_u = __shfl_sync(0xffffffffu, tmem_d, 0);
       if (tc::elect_one()) {
 #define tmem_d tmem_d_u
-#else
-      if (lane == 0) {
-        const uint32_t a_hi = tc::smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
-#endif
         const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -199,9 +194,7 @@ __global__ void __launch_bounds__(288, 1) k_tc_gemm(const float* __restrict__ A,
         tc::mma_commit(&empty_bar[s]);
         if (kc == nk - 1) tc::mma_commit(&acc_bar);
       }
-#if defined(IMF_TCGEMM_UNIFORM_ISSUE)
 #undef tmem_d
-#endif
       __syncwarp();
     }
   }
@@ -263,13 +256,14 @@ extern "C" int imf_tc_gemm_m(const float* A, int32_t lda, const float* B, int32_
   IMF_CHECK_ARG(A != nullptr && B != nullptr && C != nullptr);
   const int nk = (K + kBK - 1) / kBK;
   if (geglu) return launch<128, true>(A, lda, B, ldb, C, ldc, M, N, K, alpha, bias, R, ldr, 1, nk, err, m_dev, stream);
-  // narrow outputs or few row tiles: smaller BN puts more CTAs on the 148 SMs
+  // narrow outputs or few row tiles: smaller BN puts more CTAs on the SMs
+  const int sms = imf_sm_count();
   const long long tiles128 = (long long)((M + 127) / 128) * ((N + 127) / 128);
-  const bool bn64 = (N <= 64 || tiles128 < 74);
+  const bool bn64 = (N <= 64 || tiles128 < sms / 2);
   const long long tiles = bn64 ? (long long)((M + 127) / 128) * ((N + 63) / 64) : tiles128;
   int splits = 1;
-  if (workspace != nullptr && tiles < 74 && nk >= 16) {
-    splits = (int)((148 + tiles - 1) / tiles);
+  if (workspace != nullptr && tiles < sms / 2 && nk >= 16) {
+    splits = (int)((sms + tiles - 1) / tiles);
     if (splits > 16) splits = 16;
     if (splits > nk / 4) splits = nk / 4;
     if (workspace_bytes < (size_t)splits * M * N * sizeof(float)) splits = 1;

@@ -95,7 +95,7 @@ class FusedPlan:
         tab = CoordinateManager.table_t(...) (offset-major neighbour table, its row stride, tile masks)."""
         conv, packed, scale, shift, kci = self.conv[cname]
         nbr_t, ld_n, tile_mask = tab
-        split = self.split_small and n_out < 128 * 148      # fewer row tiles than SMs: the kernel may split a tile's offsets over several CTAs
+        split = self.split_small and n_out < 128 * _lib.sm_count()      # fewer row tiles than SMs: the kernel may split a tile's offsets over several CTAs
         _lib.check(L.imf_sparse_conv_g4_fwd(X, ldx, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(), None, n_out,
                                             27, conv.in_channels, conv.out_channels, scale.data_ptr(), shift.data_ptr(), R, ldr, kc_r,
                                             1 if relu else 0, Y, ldy, n_out, kc_out, self.conv_ws.data_ptr() if split else None,
@@ -140,14 +140,16 @@ class FusedPlan:
             with torch.cuda.stream(self.side):
                 # image encoder (resunet.py:166) as pixel-major tokens [H/8*W/8, 128] = the `data` layout of the fusion module
                 B = image.shape[0]
+                img_plan = m.img_encoder.plan(int(image.shape[2]), int(image.shape[3]))
+                img_plan.err.zero_()
                 kvs = [m.attention_fusion.project_context(m.img_encoder.tokens(image[b]), False) for b in range(B)]
                 img = m.img_encoder(image) if self.debug is not None else None
                 ev_img = torch.cuda.Event()
                 ev_img.record(self.side)
 
             # ---- coordinates ----
+            self.err.zero_()
             cm.build_pyramid([2, 4, 8])
-            self._raise_on_status(int(self.err_host[0]))   # status of earlier forwards (build_pyramid synchronised the stream)
             lv = {t: cm.level(t) for t in (1, 2, 4, 8)}
             n1, n2, n4, n8 = lv[1].n, lv[2].n, lv[4].n, lv[8].n
             nb = {t: cm.table_t(t, t, 3, False) for t in (1, 2, 4, 8)}
@@ -233,7 +235,13 @@ class FusedPlan:
                 self.debug.update(out_s4_tr=self._unpack(cat4.data_ptr(), ld4, n4, TR[4], kc4),
                                   out_s2_tr=self._unpack(cat2.data_ptr(), ld2, n2, TR[3], kc2),
                                   out_s1_tr=self._unpack(cat1.data_ptr(), ld1, n1, TR[2], kc1a))
+            # numeric status of THIS forward (fp16-range overflow, pipeline watchdog), including the image branch's convolutions:
+            # checked before the descriptors are handed out -- the eager plan is the slow path (batches, capacity fallback), one
+            # stream synchronisation per forward is not what bounds it
+            self.err.bitwise_or_(img_plan.err)
             self.err_host.copy_(self.err, non_blocking=True)
+            main.synchronize()
+            self._raise_on_status(int(self.err_host[0]))
         return out
 
     @staticmethod
@@ -246,6 +254,89 @@ class FusedPlan:
     def check_numeric_status(self):
         """Raises if any kernel of earlier forwards reported an fp16-range overflow or a pipeline watchdog (one host sync)."""
         self._raise_on_status(int(self.err.item()))
+
+
+class PlanCache:
+    """Captured plans of a model, least-recently-used first, bounded by a byte budget.
+
+    A plan preallocates everything a forward touches (~0.6 GB per 50 k voxels: activations, 10 neighbour tables, 4 hash tables, image
+    plan, attention workspace), and a dataset run meets many (row bucket, image size) keys times `streams` pool slots: without a
+    bound the GPU memory only grows.  Keys map to one plan or to a pool (list) of plans; `trim` drops whole entries, oldest first,
+    never the entry in use.  A dropped plan that is still in flight stays alive through the caller's reference until it is retired.
+    Budget: IMFNET_B200_PLAN_CACHE_GB (default 32 of the B200's 180 GB)."""
+
+    def __init__(self, budget_bytes: int | None = None):
+        import collections
+        import os
+        self._d = collections.OrderedDict()
+        gb = float(os.environ.get("IMFNET_B200_PLAN_CACHE_GB", "32"))
+        self.budget = int(gb * (1 << 30)) if budget_bytes is None else int(budget_bytes)
+        self.evictions = 0
+
+    def _touch(self, key):
+        self._d.move_to_end(key)
+
+    def get(self, key, default=None):
+        if key in self._d:
+            self._touch(key)
+            return self._d[key]
+        return default
+
+    def setdefault(self, key, default):
+        if key not in self._d:
+            self._d[key] = default
+        self._touch(key)
+        return self._d[key]
+
+    def __setitem__(self, key, value):
+        self._d[key] = value
+        self._touch(key)
+
+    def __getitem__(self, key):
+        self._touch(key)
+        return self._d[key]
+
+    def __delitem__(self, key):
+        del self._d[key]
+
+    def __contains__(self, key):
+        return key in self._d
+
+    def __len__(self):
+        return len(self._d)
+
+    def keys(self):
+        return self._d.keys()
+
+    def items(self):
+        return self._d.items()
+
+    def clear(self):
+        self._d.clear()
+
+    @staticmethod
+    def _entry_bytes(entry) -> int:
+        plans = entry if isinstance(entry, list) else [entry]
+        total = 0
+        for g in plans:
+            if getattr(g, "_nbytes", None) is None:
+                g._nbytes = g.nbytes()
+            total += g._nbytes
+        return total
+
+    def nbytes(self) -> int:
+        return sum(self._entry_bytes(e) for e in self._d.values())
+
+    def trim(self, keep=None):
+        """Evict least-recently-used entries until the cache fits its budget (the entry `keep` always stays)."""
+        total = self.nbytes()
+        for key in list(self._d.keys()):
+            if total <= self.budget:
+                break
+            if key == keep:
+                continue
+            total -= self._entry_bytes(self._d.pop(key))
+            self.evictions += 1
 
 
 class PlanCapacityError(RuntimeError):
@@ -312,7 +403,7 @@ class GraphPlan:
         self.side = torch.cuda.Stream(device=dev)
         from .model.Img_Encoder import ImagePlan
         with torch.cuda.device(dev):
-            self.image_plan = ImagePlan(m.img_encoder.backbone, self.H, self.W, fused.split_small)     # private buffers: plans run concurrently
+            self.image_plan = ImagePlan(m.img_encoder.backbone, self.H, self.W, fused.split_small, err=self.err)     # private buffers: plans run concurrently
         self.n_tok = self.image_plan.P2                     # image tokens: conv arithmetic, not H/8 * W/8, for odd sizes
         af = m.attention_fusion
         self.att_ws_bytes = int(L.imf_attention_workspace_bytes(self.cap8, self.n_tok, af.latent_dim, af.inner))
@@ -322,6 +413,59 @@ class GraphPlan:
         self.out = torch.zeros((rows, m.out_channels), **f32)
         self.graph = None
         self.launches_per_replay = 0
+        self._tl = None      # layer-timing records while time_layers() runs, else None
+
+    # -- footprint (the model's plan cache evicts by bytes) ------------------------------------------
+    def nbytes(self) -> int:
+        seen, total = set(), 0
+
+        def walk(o):
+            nonlocal total
+            if isinstance(o, torch.Tensor):
+                st = o.untyped_storage()
+                if st.data_ptr() not in seen:
+                    seen.add(st.data_ptr())
+                    total += st.nbytes()
+            elif isinstance(o, dict):
+                for v in o.values():
+                    walk(v)
+            elif isinstance(o, (list, tuple)):
+                for v in o:
+                    walk(v)
+            elif hasattr(o, "__dict__") and type(o).__name__ in ("ImagePlan", "BatchedImagePlan", "_Conv"):
+                walk(vars(o))
+
+        walk({k: v for k, v in vars(self).items() if k not in ("f", "m")})
+        return total
+
+    # -- layer timing (bench.py's roofline leg) ---------------------------------------------------------
+    def _tl_begin(self, name, **info):
+        if self._tl is None:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return (name, info, e0)
+
+    def _tl_end(self, tok):
+        if tok is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self._tl.append(tok + (e1,))
+
+    def time_layers(self):
+        """Runs the plan's launch sequence ONCE eagerly on the current stream, on whatever inputs the last launch left in the static
+        buffers, with a CUDA-event pair around every sparse-convolution launch (conv1, the 3x3x3 layers, the fused 1x1 tail); the
+        image branch is not forked meanwhile, so nothing else runs beside the timed kernels.  Returns [(layer, info, ms)] in launch
+        order: every kernel is timed in the cache state the previous layer leaves behind, as in a replay."""
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            self._tl = []
+            try:
+                self._enqueue()
+                torch.cuda.synchronize(self.device)
+                return [(name, info, e0.elapsed_time(e1)) for name, info, e0, e1 in self._tl]
+            finally:
+                self._tl = None
 
     # -- the launch sequence -------------------------------------------------------------------
     def _n(self, t):
@@ -330,15 +474,17 @@ class GraphPlan:
     def _conv(self, L, cname, X, ldx, key, t_out, R, ldr, kc_r, relu, Y, ldy, kc_out, s):
         conv, packed, scale, shift, kci = self.f.conv[cname]
         nbr_t, ld_n, tile_mask = self.nbr[key]
-        # a stride-1 level of this bucket always has >= 128 * 148 rows when the bucket is large enough: row mode is certain, so no
+        # a stride-1 level of this bucket always has >= 128 * _lib.sm_count() rows when the bucket is large enough: row mode is certain, so no
         # split workspace (and no reduce launch) is needed there
-        split = self.f.split_small and not (t_out == 1 and self.rows - self.ROW_SLACK >= 128 * 148)
+        split = self.f.split_small and not (t_out == 1 and self.rows - self.ROW_SLACK >= 128 * _lib.sm_count())
         out_row = self.perm[t_out].data_ptr() if key[2] else None          # transposed: the table is in parity-grouped row order
+        tok = self._tl_begin(cname, key=key, t_out=t_out, cin=conv.in_channels, cout=conv.out_channels, K=27, residual=R is not None)
         _lib.check(L.imf_sparse_conv_g4_fwd_perm(X, ldx, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(),
                                                  self._n(t_out), self.rows, 27, conv.in_channels, conv.out_channels, scale.data_ptr(),
                                                  shift.data_ptr(), R, ldr, kc_r, 1 if relu else 0, Y, ldy, self.rows, kc_out, out_row,
                                                  self.conv_ws.data_ptr() if split else None, self.conv_ws_bytes if split else 0,
                                                  self.err.data_ptr(), s))
+        self._tl_end(tok)
 
     def _block(self, L, name, X, ldx, kc_x, t, C, tmp, Y, ldy, kc_y, s):
         kt = _kc(C)
@@ -376,10 +522,12 @@ class GraphPlan:
         kc1a, kc1b = _kc(TR[2]), _kc(CH[1])
         kc2, kc4, k8 = _kc(TR[3], CH[2]), _kc(TR[4], CH[3]), _kc(CH[4])
         sc, sh = f.norm1
+        tok = self._tl_begin("conv1", t_out=1, cin=m.conv1.in_channels, cout=CH[1], K=m.conv1.kernel_size ** 3, residual=False)
         _lib.check(L.imf_conv_first_h2_fwd(self.feats.data_ptr(), self.feats.shape[1], m.conv1.in_channels, m.conv1.kernel.data_ptr(),
                                            self.coords[1].data_ptr(), self._n(1), rows, self.tables[1].data_ptr(), self.cap,
                                            m.conv1.kernel_size, 1, CH[1], sc.data_ptr(), sh.data_ptr(), 0, self.a0.data_ptr(),
                                            2 * CH[1], _kc(CH[1]), s))
+        self._tl_end(tok)
         self._block(L, "block1", self.a0.data_ptr(), 2 * CH[1], _kc(CH[1]), 1, CH[1], self.a1, s1, ld1, kc1b, s)
         self._conv(L, "conv2", s1, ld1, (1, 2, False), 2, None, 0, 0, False, self.b0.data_ptr(), 2 * CH[2], _kc(CH[2]), s)
         self._block(L, "block2", self.b0.data_ptr(), 2 * CH[2], _kc(CH[2]), 2, CH[2], self.b1, s2, ld2, kc2, s)
@@ -397,15 +545,18 @@ class GraphPlan:
         self._conv(L, "conv2_tr", self.cat2.data_ptr(), ld2, (2, 1, True), 1, None, 0, 0, False, self.h0.data_ptr(), 2 * TR[2], _kc(TR[2]), s)
         self._block(L, "block2_tr", self.h0.data_ptr(), 2 * TR[2], _kc(TR[2]), 1, TR[2], self.h1, self.cat1.data_ptr(), ld1, kc1a, s)
         # ---- tail ----
+        tok = self._tl_begin("conv1_tr+final", t_out=1, cin=TR[2] + CH[1], mid=TR[1], cout=m.out_channels, K=1, residual=False)
         _lib.check(L.imf_pointwise_tail_h2_fwd(self.cat1.data_ptr(), ld1, TR[2] + CH[1], TR[2], kc1a, kc1b, m.conv1_tr.kernel.data_ptr(),
                                                TR[1], m.final.kernel.data_ptr(), _lib.ptr(f.final_bias), m.out_channels, self._n(1), rows,
                                                1 if m.normalize_feature else 0, None, self.out.data_ptr(), m.out_channels, s))
+        self._tl_end(tok)
 
     # the two steps a batch changes (imfnet_b200/batched.py overrides them): the image branch and the fusion at stride 8
     def _enqueue_image(self, m, main):
         """Image branch on a forked stream: encoder, then K / V of the image tokens (joined again in _enqueue_fusion)."""
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
+        side = main if self._tl is not None else self.side          # (layer timing: nothing runs beside the timed kernels)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
             self.kv = m.attention_fusion.project_context(self.image_plan.enqueue(self.image[0]), False)
 
     def _enqueue_fusion(self, L, m, C8, k8, main, s):

@@ -58,6 +58,6 @@ def mutual_nn(frag1_descs, frag2_descs, device="cuda:0"):
     d2 = torch.as_tensor(np.asarray(frag2_descs), dtype=torch.float32).to(device)
     nn21 = nn_search(d2, d1)
     nn12 = nn_search(d1, d2)
-    n2 = d2.shape[0]
-    mutual = torch.nonzero(nn12[nn21.long()] == torch.arange(n2, device=d2.device, dtype=torch.int32)).flatten()
+    from .pipeline import mutual_from_nn
+    mutual = mutual_from_nn(nn12, nn21)          # (rows without a match, index -1, are never mutual)
     return nn21.cpu().numpy().astype(np.int32), mutual.cpu().numpy()

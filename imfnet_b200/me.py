@@ -130,7 +130,7 @@ class MinkowskiFunctional:
 
 
 class utils:
-    """ME.utils subset (util/misc.py:83,86; lib/data_loaders.py:68-69)."""
+    """ME.utils subset (util/misc.py:83,86; lib/data_loaders.py:68-69; scripts/evaluation_3dmatch.py:164-168)."""
 
     @staticmethod
     def sparse_quantize(coordinates, features=None, labels=None, ignore_label=-100, return_index=False,
@@ -156,6 +156,22 @@ class utils:
         if return_index:
             res.append(idx)
         return res[0] if len(res) == 1 else tuple(res)
+
+    @staticmethod
+    def fnv_hash_vec(arr):
+        """FNV64-1A over the columns of an integer-valued [N, D] array -> uint64 [N] (ME.utils.fnv_hash_vec as called by
+        scripts/evaluation_3dmatch.py:164-168 on np.floor(points / voxel_size) to intersect keypoints with voxel coordinates).
+        Host numpy arithmetic like the original: it hashes a few thousand keypoints per fragment pair, not a hot path."""
+        a = np.asarray(arr)
+        if a.ndim != 2:
+            raise ValueError("fnv_hash_vec expects a 2-D array [N, D]")
+        a = a.copy().astype(np.uint64, copy=False)
+        h = np.uint64(14695981039346656037) * np.ones(a.shape[0], dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            for j in range(a.shape[1]):
+                h *= np.uint64(1099511628211)
+                h = np.bitwise_xor(h, a[:, j])
+        return h
 
     @staticmethod
     def batched_coordinates(coords, dtype=torch.int32, device=None):

@@ -49,7 +49,10 @@ class ImagePlan:
 
     STEM_K = 160      # 7*7*3 = 147 im2col columns padded to a multiple of 32
 
-    def __init__(self, backbone: resnet.ResNet, H: int, W: int, split_small: bool = False):
+    def __init__(self, backbone: resnet.ResNet, H: int, W: int, split_small: bool = False, err: torch.Tensor | None = None):
+        """err: device int32 status word the convolutions report fp16-range overflows / watchdogs into -- the owning forward plan's, so
+        that a failure in the image branch raises like one in the point branch (the encoder's own plans use a private word that
+        FusedPlan.run merges)."""
         L = _lib.lib()
         self.split_small = split_small        # see FusedPlan.split_small (engine.py)
         p = next(backbone.parameters())
@@ -100,11 +103,11 @@ class ImagePlan:
             self.tokens = torch.zeros((self.P2, self.C2), **f32)
             self.ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(self.C2))
             self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)        # head = arrival counters (zero)
-            self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.err = err if err is not None else torch.zeros(1, dtype=torch.int32, device=dev)
 
     def _conv(self, L, c: _Conv, X, tab, n_out, R, relu, Y, s):
         nbr_t, ld_n, mask = tab
-        split = self.split_small and n_out < 128 * 148
+        split = self.split_small and n_out < 128 * _lib.sm_count()
         _lib.check(L.imf_sparse_conv_g4_fwd(X.data_ptr(), 2 * c.cin, c.kc_in, c.packed.data_ptr(), nbr_t.data_ptr(), ld_n, mask.data_ptr(),
                                             None, n_out, c.K, c.cin, c.cout, c.scale.data_ptr(), c.shift.data_ptr(), _lib.ptr(R),
                                             0 if R is None else 2 * c.cout, 64, 1 if relu else 0, Y.data_ptr(), 2 * c.cout, n_out, 64,

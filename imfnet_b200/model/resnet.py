@@ -1,8 +1,7 @@
-"""ResNet image backbone, truncated after layer2 as the reference runs it
-(/root/reference/model/resnet.py:120-216: conv7x7/2 -> BN -> ReLU -> maxpool/2 -> layer1 -> layer2; layer3/4/fc are
-constructed so checkpoints load strictly, but never executed).  Per the north star the 2-D encoder reuses
-torch's cuDNN path; TF32 is switched off for it because single-pass TF32 breaks the 1e-4 descriptor parity
-(SURVEY.md section 7.3-1)."""
+"""ResNet image backbone: the PARAMETER TREE of the reference's torchvision-style ResNet
+(/root/reference/model/resnet.py:120-216: conv7x7/2 -> BN -> ReLU -> maxpool/2 -> layer1 -> layer2 are what runs; layer3/4/fc are
+constructed so checkpoints load strictly, but never executed).  The arithmetic of the executed prefix lives in
+Img_Encoder.ImagePlan (sm_100a kernels); these modules only hold weights under the reference's names."""
 import torch
 import torch.nn as nn
 
@@ -21,11 +20,6 @@ class BasicBlock(nn.Module):
         self.bn2 = nn.BatchNorm2d(planes)
         self.downsample = downsample
         self.stride = stride
-
-    def forward(self, x):
-        y = self.relu(self.bn1(self.conv1(x)))
-        y = self.bn2(self.conv2(y))
-        return self.relu(y + (x if self.downsample is None else self.downsample(x)))
 
 
 class ResNet(nn.Module):
@@ -57,9 +51,8 @@ class ResNet(nn.Module):
         return nn.Sequential(*mods)
 
     def forward(self, x):
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
-            return self.layer2(self.layer1(x))     # I1: [B, 128, H/8, W/8]
+        raise NotImplementedError("the backbone is a parameter container: run it through imfnet_b200.model.ImageEncoder "
+                                  "(Img_Encoder.ImagePlan executes conv1..layer2 on the sm_100a kernels)")
 
 
 def resnet18(in_channels=3, pretrained=False, progress=True, **kwargs):

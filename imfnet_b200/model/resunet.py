@@ -10,7 +10,7 @@ import torch
 from .. import me as ME
 import os
 
-from ..engine import FusedPlan, GraphPlan, PlanCapacityError
+from ..engine import FusedPlan, GraphPlan, PlanCache, PlanCapacityError
 from .attention_fusion import AttentionFusion
 from .common import get_norm
 from .Img_Encoder import ImageEncoder
@@ -100,7 +100,7 @@ class ResUNet2(ME.MinkowskiNetwork):
     def _ensure_plan(self):
         if self._plan is None or self._plan.split_small != bool(self.low_latency):
             self._plan = FusedPlan(self)
-            self._graphs, self._cap8_scale = {}, {}
+            self._graphs, self._cap8_scale = PlanCache(), {}
     ROW_BUCKET = GraphPlan.ROW_SLACK
 
     @torch.no_grad()
@@ -149,6 +149,7 @@ class ResUNet2(ME.MinkowskiNetwork):
                 g = GraphPlan(plan, rows, key[1], key[2], cap8)
                 g.stream = torch.cuda.Stream(device=plan.device)
                 pool.append(g)
+                self._graphs.trim(keep=("pool",) + key)
             g = pool[slot]
             while any(e[2] is g for e in inflight):
                 retire()
@@ -212,6 +213,7 @@ class ResUNet2(ME.MinkowskiNetwork):
                 g = GraphPlan(plan, rows, key[1], key[2], self._cap8(rows, 1))
                 g.stream = torch.cuda.Stream(device=plan.device)
                 pool.append(g)
+                self._graphs.trim(keep=("pool",) + key)
             g = pool[slot]
             while any(e[1] is g for e in inflight):
                 retire()
@@ -244,6 +246,7 @@ class ResUNet2(ME.MinkowskiNetwork):
         if g is None:
             cap8 = self._cap8(rows, scale)
             g = self._graphs[key] = GraphPlan(plan, rows, key[1], key[2], cap8)
+            self._graphs.trim(keep=key)
         feats = x.F.to(device=plan.device, dtype=torch.float32)
         try:
             return g.run(x.C, feats, image.to(device=plan.device, dtype=torch.float32))

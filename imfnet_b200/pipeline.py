@@ -44,7 +44,7 @@ def extract_features(model, xyz, rgb=None, normal=None, voxel_size=0.05, device=
         feats.append(np.ones((len(xyz), 1)))
     feats = np.hstack(feats)
 
-    pts = torch.as_tensor(xyz, dtype=torch.float64).to(device, non_blocking=True)
+    pts = torch.as_tensor(xyz).to(device, non_blocking=True)          # quantised in the cloud's own dtype, as np.floor(xyz / voxel_size) is
     coords, inds = voxelize(pts, voxel_size, batch_index=0)          # util/misc.py:82-86 on the GPU
     inds_host = inds.cpu().numpy()
     return_coords = xyz[inds_host]
@@ -87,6 +87,16 @@ def aggregate_throughput(records: torch.Tensor):
     return float(records[:, 1].sum()) / (ms * 1e-3), ms
 
 
+def mutual_from_nn(nn12: torch.Tensor, nn21: torch.Tensor) -> torch.Tensor:
+    """Rows j of fragment 2 whose nearest neighbour i = nn21[j] in fragment 1 has j as ITS nearest neighbour (nn12[i] == j).
+    A row without a match (index -1: empty other side, or a NaN descriptor that no distance comparison selects) is never mutual --
+    it must not be used as an index (nn12[-1] would silently wrap to the last row)."""
+    ok = nn21 >= 0
+    back = nn12[nn21.clamp_min(0).long()] if len(nn12) else torch.full_like(nn21, -1)
+    j = torch.arange(len(nn21), device=nn21.device, dtype=nn21.dtype)
+    return torch.nonzero(ok & (back == j)).flatten()
+
+
 @torch.no_grad()
 def describe_and_match_pairs(model, pairs, num_keypoints: int = 5000, seed: int = 0, streams: int = 4):
     """BASELINE config 3 ("fragment pairs ... descriptors + 5000-keypoint L2 feature matching"): for every pair
@@ -107,6 +117,6 @@ def describe_and_match_pairs(model, pairs, num_keypoints: int = 5000, seed: int 
         di, dj = Fi[ki], Fj[kj]
         nn21 = nn_search(dj, di)
         nn12 = nn_search(di, dj)
-        mutual = torch.nonzero(nn12[nn21.long()] == torch.arange(len(dj), device=dj.device, dtype=torch.int32)).flatten()
+        mutual = mutual_from_nn(nn12, nn21)
         results.append({"kpts_i": ki, "kpts_j": kj, "nn21": nn21, "mutual": mutual})
     return results

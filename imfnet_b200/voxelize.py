@@ -1,6 +1,6 @@
 """GPU voxelisation front end: what util/misc.py:82-86 does on the host with numpy + ME.
 
-  coords = floor(xyz / voxel)            util/misc.py:82  -> imf_quantize_points (float64, bit-exact)
+  coords = floor(xyz / voxel)            util/misc.py:82  -> imf_quantize_points / _f32 (in the cloud's dtype, as numpy: bit-exact)
   sparse_quantize(..., return_index)     util/misc.py:83  -> imf_stride_map(stride=1, first_idx)
 Order of the returned rows = first occurrence, ascending source index (pinned by files/3D_head_map.ply).
 """
@@ -41,14 +41,20 @@ def unique_first(coords: torch.Tensor) -> torch.Tensor:
 
 
 def voxelize(xyz: torch.Tensor, voxel_size: float, batch_index: int = 0):
-    """xyz float64 [N,3] on CUDA -> (coords int32 [U,4] (b,x,y,z), idx int32 [U]) exactly as
-    floor(xyz/voxel) -> sparse_quantize(return_index=True) -> batched_coordinates would give."""
+    """xyz float64 or float32 [N,3] on CUDA -> (coords int32 [U,4] (b,x,y,z), idx int32 [U]) exactly as
+    np.floor(xyz/voxel) -> sparse_quantize(return_index=True) -> batched_coordinates would give.  The division runs in the cloud's
+    own dtype, as numpy's does (a float32 cloud is NOT promoted: near voxel boundaries float64 would pick other voxels)."""
     _lib.require_cuda(xyz, "points")
     L = _lib.lib()
-    x = xyz.to(torch.float64).contiguous()
+    if xyz.dtype not in (torch.float32, torch.float64):
+        xyz = xyz.to(torch.float64)          # integer / half clouds: numpy's true division gives float64 (float16 is not a cloud dtype)
+    x = xyz.contiguous()
     n = len(x)
     c = torch.empty((n, 4), dtype=torch.int32, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(L.imf_quantize_points(_lib.ptr(x), n, float(voxel_size), int(batch_index), _lib.ptr(c), _lib.cur_stream()))
+        if x.dtype == torch.float32:
+            _lib.check(L.imf_quantize_points_f32(_lib.ptr(x), n, float(voxel_size), int(batch_index), _lib.ptr(c), _lib.cur_stream()))
+        else:
+            _lib.check(L.imf_quantize_points(_lib.ptr(x), n, float(voxel_size), int(batch_index), _lib.ptr(c), _lib.cur_stream()))
     idx = unique_first(c)
     return c[idx.long()], idx

@@ -37,6 +37,9 @@ const char* imf_last_error(void);
 int imf_version(void);
 /* Number of kernels this library has launched in the calling process so far (bench.py's gpu_launches). */
 long long imf_launch_count(void);
+/* SMs of the current CUDA device (148 on a full B200; 148 is also reported when no device is present).  The persistent kernels size
+ * their grids and split heuristics with it; callers use it for the same thresholds (e.g. "fewer 128-row tiles than SMs"). */
+int imf_device_sm_count(void);
 
 /* ---- coordinates: ME CoordinateManager work behind ME.SparseTensor(...) (util/misc.py:95) ------------- */
 
@@ -98,6 +101,10 @@ int imf_parity_perm(const int32_t* coords, const int32_t* n_dev, int32_t n_max, 
 /* coords[i] = (batch_index, floor(xyz[i]/voxel_size)) in float64, as util/misc.py:82 computes on the host. */
 int imf_quantize_points(const double* xyz, int32_t n, double voxel_size, int32_t batch_index, int32_t* coords,
                         imf_stream_t stream);
+/* The same for float32 clouds: numpy evaluates np.floor(xyz / voxel_size) in the input dtype, i.e. a float32 division by
+ * (float)voxel_size; points next to a voxel boundary may fall into another voxel than in float64. */
+int imf_quantize_points_f32(const float* xyz, int32_t n, float voxel_size, int32_t batch_index, int32_t* coords,
+                            imf_stream_t stream);
 
 /* seg[b] = first row with batch index >= b, seg[num_batches] = n (rows are batch-sorted; resunet.py:240-255). */
 int imf_batch_segments(const int32_t* coords, const int32_t* n_dev, int32_t n_max, int32_t num_batches, int32_t* seg,
@@ -140,17 +147,13 @@ int imf_h2_unpack_n(const void* H, int32_t ldh, int32_t n, const int32_t* n_dev,
                     imf_stream_t stream);
 
 /* Weights W[K^3,Cin,Cout] * wmul (a power of two that brings max|W| near 2^11; fold 1/wmul into `scale`) packed for the
- * input chunk width kc_in.  Same operation and epilogue as imf_sparse_conv_fwd; scale and shift are required. */
+ * input chunk width kc_in (consumed by imf_sparse_conv_g4_fwd). */
 size_t imf_sparse_conv_h2_packed_bytes(int32_t kernel_volume, int32_t Cin, int32_t Cout, int32_t kc_in);
 int imf_sparse_conv_h2_pack(const float* W, int32_t kernel_volume, int32_t Cin, int32_t Cout, int32_t kc_in, float wmul, void* packed,
                             imf_stream_t stream);
-size_t imf_sparse_conv_h2_workspace_bytes(int32_t n_out_max, int32_t Cout);
-int imf_sparse_conv_h2_fwd(const void* X, int32_t ldx, int32_t kc_in, const void* packed, const int32_t* nbr, const int32_t* n_out_dev,
-                           int32_t n_out_max, int32_t kernel_volume, int32_t Cin, int32_t Cout, const float* scale, const float* shift,
-                           const void* residual, int32_t ldr, int32_t kc_r, int32_t relu, void* Y, int32_t ldy, int32_t kc_out,
-                           void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
 
-/* "g4" kernel of the h2 tier (csrc/sparse_conv_g4.cu): same operation, data format and packed weights as imf_sparse_conv_h2_fwd, but
+/* "g4" kernel of the h2 tier (csrc/sparse_conv_g4.cu): same operation and epilogue as imf_sparse_conv_fwd on h2 matrices and
+ * packed weights (scale and shift are required):
  * persistent (one CTA per SM, launch shape independent of the row count, all sizes read from n_out_dev on the device), reading the
  * offset-major table + tile masks of imf_kernel_map_t, sharing each weight slab between the sub-tiles of a CTA, and writing the output
  * with tiled TMA stores.  n_y_rows = rows of the Y allocation (tensor-map extent, >= n_out_max; rows in [n, roundup32(n)) that exist
@@ -186,24 +189,6 @@ int imf_conv_first_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W,
                        int32_t n_max, const void* table, long long capacity, int32_t kernel_size, int32_t tensor_stride,
                        int32_t Cout, const float* scale, const float* shift, int32_t relu, float* Y, int32_t ldy,
                        imf_stream_t stream);
-
-/* Profiling hook (tools/conv_microbench.py): bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs of
- * imf_sparse_conv_h2_fwd, whose results are then meaningless.  Returns the previous value; 0 = normal operation. */
-int imf_debug_conv_flags(int32_t flags);
-/* Profiling hook: device int64 buffer (>= 16 + 4*stages entries) that CTA 0 of imf_sparse_conv_h2_fwd fills with clock64()
- * stamps of its pipeline events (slot map in csrc/sparse_conv_h2.cu); NULL switches it off. */
-int imf_debug_conv_trace(long long* trace);
-
-/* Self-test hook of the TMA path (tools/tma_selftest.py): gathers rows idx[0..127] (device int32; negative or >= n_rows gives a zero
- * row) of the fp16 matrix X [n_rows, ld], columns [col, col+64), into a 128-byte-swizzled shared tile with tile::gather4, copies
- * the raw tile (16 KB) to `raw`, and stores it with a tiled TMA store to rows [out_row, out_row+128) of O [o_rows, ld] (clipped). */
-int imf_debug_gather4(const void* X, int32_t ld, int32_t n_rows, const int32_t* idx, int32_t col, int32_t box_rows, void* raw, void* O,
-                      int32_t o_rows, int32_t out_row, int32_t* err, imf_stream_t stream);
-
-/* Throughput probe of tile::gather4 (tools/tma_selftest.py --rate): nctas CTAs x nwarps warps, each warp issues `iters` rounds of 32
- * gather4 (128 rows x 128 B) with `depth` rounds in flight; out[w] = cycles of warp w of CTA 0. */
-int imf_debug_gather4_rate(const void* X, int32_t ld, int32_t n_rows, const int32_t* idx, int32_t n_idx, int32_t nwarps, int32_t iters,
-                           int32_t depth, int32_t nctas, long long* out, int32_t* err, imf_stream_t stream);
 
 /* imf_conv_first_fwd writing an h2 matrix (ldy in halves, chunk width kc_out). */
 int imf_conv_first_h2_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords, const int32_t* n_dev,

@@ -16,7 +16,7 @@ from numpy.lib.stride_tricks import as_strided
 
 from imfnet_b200 import _lib
 
-HOST_ONLY = {"imf_last_error", "imf_version", "imf_launch_count", "imf_hash_capacity", "imf_hash_bytes"}
+HOST_ONLY = {"imf_last_error", "imf_version", "imf_launch_count", "imf_hash_capacity", "imf_hash_bytes", "imf_device_sm_count"}
 
 
 def vec(ptr, n, dtype=np.float32):
@@ -100,17 +100,19 @@ class Emulator:
         n = count(n_in_dev, n_in_max)
         C = mat(coords_in, n, 4, 4, np.int32).copy()
         C[:, 1:] = np.floor_divide(C[:, 1:], stride) * stride
-        d, rows = {}, []
-        for row in map(tuple, C.tolist()):
+        d, rows, first = {}, [], []
+        for i, row in enumerate(map(tuple, C.tolist())):
             if row not in d:
                 d[row] = len(rows)
                 rows.append(row)
+                first.append(i)
         out = mat(coords_out, len(rows), 4, 4, np.int32)
         if rows:
             out[:] = np.asarray(rows, dtype=np.int32)
         vec(n_out_dev, 1, np.int32)[0] = len(rows)
         self.tables[table_out] = d
-        assert not first_idx
+        if first_idx:          # source row of every kept row (imf_stride_map with stride 1 = ME.utils.sparse_quantize(return_index=True))
+            vec(first_idx, len(first), np.int32)[:] = np.asarray(first, dtype=np.int32)
 
     def do_imf_parity_perm(self, coords, n_dev, n_max, t, perm, ws, ws_bytes):
         n = count(n_dev, n_max)

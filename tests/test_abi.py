@@ -51,15 +51,3 @@ def test_sass_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", build.build()], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
-
-
-def test_kernel_variant_libraries_export_the_same_abi():
-    """build.py VARIANTS: same sources with experiment switches, selected by IMFNET_B200_VARIANT; same exported symbols, sm_100a only."""
-    build.build()
-    for name in build.VARIANTS:
-        path = build.lib_path(name)
-        assert os.path.exists(path), path
-        out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
-        assert sorted(set(re.findall(r"\bT (imf_[a-z0-9_]+)$", out, flags=re.M))) == header_functions()
-        archs = set(re.findall(r"sm_(\d+a?)", subprocess.run(["cuobjdump", "-lelf", path], capture_output=True, text=True).stdout))
-        assert archs == {"100a"}, archs

@@ -1,6 +1,6 @@
-"""CPU: bench.py's measurement logic (execution modes, fallback when the batched plan fails, JSON contract) run end to end on the
-C-ABI emulator with inert torch.cuda objects.  The numbers are meaningless (every "CUDA event" reports 1 ms); the keys, the
-mode selection and the bookkeeping are what is checked."""
+"""CPU: bench.py's measurement logic (the batched execution mode, the per-layer roofline leg, the C4 pair workload, the JSON
+contract) run end to end on the C-ABI emulator with inert torch.cuda objects.  The numbers are meaningless (every "CUDA event"
+reports 1 ms); the keys and the bookkeeping are what is checked."""
 import contextlib
 import importlib.util
 import io
@@ -35,13 +35,23 @@ def bench(emu, monkeypatch):  # noqa: F811
     monkeypatch.setattr(torch, "device", lambda *a, **k: real_device("cpu"))
     monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{n: v for n, v in k.items() if n != "pin_memory"}))
     monkeypatch.setitem(synthetic.CONFIGS, "T", (400, 0.05, 64, 48))
+    monkeypatch.setitem(b.WORKLOADS, "C2", ("T", 2))
+    monkeypatch.setitem(b.WORKLOADS, "C4", ("T", 2))
     monkeypatch.setattr(b, "N_FRAGMENTS", 3)
-    monkeypatch.setattr(b, "dominant_kernel_roofline", lambda model, frag, flush: {"bound": "hbm", "frac": 0.0})
+    monkeypatch.setattr(b, "KEYPOINTS", 50)
+    monkeypatch.setattr(b, "count_conv1_pairs", lambda group, k, device: 40 * sum(len(c) for c, _f, _im in group))
+    import imfnet_b200.matching as matching
+
+    def nn_cpu(A, B, return_distance=False):          # (the matching kernel is not part of the emulator)
+        d = torch.cdist(A.double(), B.double())
+        return d.argmin(dim=1).to(torch.int32)
+
+    monkeypatch.setattr(matching, "nn_search", nn_cpu)
     return b
 
 
 def run(b, **over):
-    args = types.SimpleNamespace(config="T", streams=2, batched=2, steps=1, warmup=1, profile=False, gpus=1, batched_note="forced")
+    args = types.SimpleNamespace(config="C2", batch=0, steps=1, warmup=1, profile=False, gpus=1)
     for k, v in over.items():
         setattr(args, k, v)
     buf = io.StringIO()
@@ -52,99 +62,41 @@ def run(b, **over):
     return json.loads(lines[0])
 
 
-def test_bench_times_both_modes_and_reports_the_faster(bench):
+def test_bench_line_contract_and_roofline_leg(bench):
     d = run(bench)
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
                 "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert key in d, key
-    modes = d["config"]["execution_modes_timed"]
-    assert set(modes) == {"single-fragment plans", "batched plan"}
-    assert modes["batched plan"]["fragments_per_step"] == 4 and modes["single-fragment plans"]["fragments_per_step"] == 2
-    assert d["config"]["fragments_per_step"] == 4 and "per batch of 2 fragments" in d["config"]["execution"]      # 4 fragments per fake ms wins
+    assert d["config"]["fragments_per_step"] == 4 and d["config"]["fragments_per_graph_replay"] == 2
+    assert d["value"] == pytest.approx(400 * 4 / 1e-3) and d["ms_per_step"] == pytest.approx(1.0)          # ms_per_step x steps reproduces value
     assert d["e2e"]["h2d_bytes_per_step"] == 4 * (400 * 16 + 400 * 4 + 3 * 48 * 64 * 4) and d["e2e"]["d2h_bytes_per_step"] == 4 * 400 * 32 * 4
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    r = d["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "sparse_part", "layers"):
+        assert key in r, key
+    names = [x["layer"] for x in r["layers"]]
+    assert names[0] == "conv1" and names[-1] == "conv1_tr+final" and len(names) == 22 and "block2_tr.conv1" in names
+    assert r["frac"] == pytest.approx(r["achieved"] / r["peak"])
+    sp = r["sparse_part"]
+    assert sp["alg_bytes"] == pytest.approx(sum(x["alg_MB"] for x in r["layers"]) * 1e6, rel=1e-6) and sp["ms"] == pytest.approx(22.0)
+    # SURVEY 8(d) accounting of one layer, by hand
+    x = next(x for x in r["layers"] if x["layer"] == "block2_tr.conv2")
+    assert x["alg_MB"] * 1e6 == pytest.approx(4 * x["pairs"] * 64 + 8 * x["pairs"] + 4 * 27 * 64 * 64 + 2 * 4 * x["rows"] * 64)
 
 
-def test_bench_falls_back_when_the_batched_plan_fails(bench, monkeypatch):
-    import imfnet_b200.batched as batched
-
-    def boom(self, *a, **k):
-        raise RuntimeError("injected failure")
-
-    monkeypatch.setattr(batched.BatchGraphPlan, "launch_batch", boom)
-    d = run(bench)
-    assert set(d["config"]["execution_modes_timed"]) == {"single-fragment plans"}
-    assert "injected failure" in d["config"]["mode_selection"] and d["config"]["fragments_per_step"] == 2
-    assert "per fragment" in d["config"]["execution"]
+def test_bench_pairs_workload(bench):
+    d = run(bench, config="C4")
+    c = d["config"]
+    assert c["pairs_per_step"] == 2 and c["fragments_per_step"] == 4 and c["pairs_per_s"] == pytest.approx(2 / 1e-3)
+    assert "mutual-NN" in c["workload"]
+    assert d["e2e"]["d2h_bytes_per_step"] == 4 * 400 * 32 * 4 + 2 * 50 * 4
 
 
-def test_bench_without_batched_mode(bench):
-    d = run(bench, batched=0, batched_note="off")
-    assert set(d["config"]["execution_modes_timed"]) == {"single-fragment plans"} and d["config"]["mode_selection"] == "off"
-
-
-def test_mode_selection_logic(bench, monkeypatch, tmp_path_factory):
-    """select_modes(): a variant library is only chosen when bit-identical and faster (the fastest wins); the batched plan only when
-    the chosen library's probe of it passed."""
-    import os
-    ok = {"probe": "done", "B": 10, "hashes": ["a", "b"], "seq_ms_per_step": 10.0, "batched": "ok", "max_rowwise_rel_diff_vs_forward_many": 0.0}
-
-    def with_probes(default, x, z, y=None, w=None):
-        calls = []
-
-        def fake(args, v="", sizes=""):
-            calls.append(v)
-            d = {"": default, "x": x, "z": z, "y": y, "w": w}[v]
-            return (dict(d), "ok") if d is not None else (None, "probe failed (rc 1): boom")
-
-        monkeypatch.setattr(bench, "run_probe", fake)
-        monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
-        monkeypatch.setattr(bench, "CACHE_DIR", str(tmp_path_factory.mktemp("modes")))      # no decision cache between cases
-        args = types.SimpleNamespace(config="T", streams=10, variant_probe=True)
-        res = bench.select_modes(args)
-        chosen = os.environ.get("IMFNET_B200_VARIANT", "")
-        monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
-        return res, chosen, calls
-
-    (B, note), var, calls = with_probes(ok, dict(ok, seq_ms_per_step=8.0), dict(ok, seq_ms_per_step=9.0))
-    assert B == 10 and var == "x" and "variant x in use" in note and calls == ["", "x", "z", "y", "w"]
-    (B, note), var, _ = with_probes(ok, dict(ok, seq_ms_per_step=8.0), dict(ok, seq_ms_per_step=7.0))
-    assert var == "z"
-    (B, note), var, _ = with_probes(ok, dict(ok, seq_ms_per_step=8.0), dict(ok, seq_ms_per_step=7.0), dict(ok, seq_ms_per_step=6.0))
-    assert var == "y"
-    (B, note), var, _ = with_probes(ok, dict(ok, seq_ms_per_step=9.9), dict(ok, seq_ms_per_step=10.5))
-    assert B == 10 and var == "" and "default library in use" in note
-    (B, note), var, _ = with_probes(ok, dict(ok, hashes=["a", "c"], seq_ms_per_step=5.0), None)
-    assert B == 10 and var == "" and "differ" in note and "probe failed" in note
-    (B, note), var, _ = with_probes(dict(ok, batched="mismatch"), dict(ok, seq_ms_per_step=8.0), None)
-    assert B == 10 and var == "x"                                  # the chosen library's own batched probe passed
-    (B, note), var, _ = with_probes(dict(ok, batched="failed: x"), dict(ok, seq_ms_per_step=20.0, batched="failed: x"), None)
-    assert B == 0 and var == "" and "not used" in note
-    (B, note), var, calls = with_probes(None, ok, ok)
-    assert B == 0 and var == "" and calls == [""]
-
-
-def test_mode_selection_is_cached_per_box(bench, monkeypatch, tmp_path):
-    import os
-    ok = {"probe": "done", "B": 10, "hashes": ["a"], "seq_ms_per_step": 10.0, "batched": "ok", "max_rowwise_rel_diff_vs_forward_many": 0.0}
-    calls = []
-
-    def fake(args, v="", sizes=""):
-        calls.append(v)
-        return dict(ok, seq_ms_per_step=10.0 if v == "" else 8.0 if v == "x" else 9.0), "ok"
-
-    monkeypatch.setattr(bench, "run_probe", fake)
-    monkeypatch.setattr(bench, "CACHE_DIR", str(tmp_path / "cache"))
-    monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
-    args = types.SimpleNamespace(config="T", streams=10, variant_probe=True)
-    B1, note1 = bench.select_modes(args)
-    assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B1 == 10 and len(calls) == 5
-    assert set(args.probe_table) == {"default", "x", "z", "y", "w"} and args.probe_table["x"]["bit_identical"] is True
-    assert args.probe_table["x"]["seq_ms_per_step"] == 8.0
-    table1 = args.probe_table
-    args = types.SimpleNamespace(config="T", streams=10, variant_probe=True)
-    monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
-    B2, note2 = bench.select_modes(args)                      # second run on the same box: no probes, same decision
-    assert os.environ.get("IMFNET_B200_VARIANT") == "x" and B2 == 10 and len(calls) == 5 and "cached" in note2 and note2.startswith(note1)
-    assert args.probe_table == table1
-    monkeypatch.delenv("IMFNET_B200_VARIANT", raising=False)
+def test_reference_arm_line(bench, monkeypatch, capsys):
+    args = types.SimpleNamespace(config="C2", steps=1, warmup=0, gpus=1)
+    bench.run_reference(args, 0, 1)
+    d = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["metric"] == bench.METRIC
+    bench.run_reference(args, 1, 2)                      # other ranks exit without work or output
+    assert capsys.readouterr().out == ""

@@ -41,98 +41,6 @@ def run_conv(X, W, nbr, n_out, scale=None, shift=None, R=None, relu=False):
     return Y.cpu()
 
 
-@pytest.mark.parametrize("t_in,t_out,tr,cin,cout", [
-    (1, 1, False, 32, 32), (1, 1, False, 64, 64), (1, 2, False, 32, 64), (2, 2, False, 64, 64), (2, 4, False, 64, 128),
-    (4, 4, False, 128, 128), (4, 8, False, 128, 256), (8, 8, False, 256, 256), (8, 4, True, 256, 128), (4, 2, True, 256, 64),
-    (2, 1, True, 128, 64)])
-def test_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout):
-    coords, ocm, cm = frag
-    g = torch.Generator().manual_seed(cin * 1000 + cout + t_in)
-    n_in, n_out = len(ocm.get(t_in)), len(ocm.get(t_out))
-    X = torch.randn(n_in, cin, generator=g)
-    W = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
-    onbr = ocm.table(t_in, t_out, 3, tr)
-    ref = sparse_ops.conv_forward(X, W, onbr)
-    nbr = cm.table(t_in, t_out, 3, tr)
-    assert np.array_equal(nbr.cpu().numpy(), onbr)
-    close(run_conv(X.cuda(), W.cuda(), nbr, n_out), ref)
-
-
-def h2_pack(X, kc, ld_extra=0):
-    L = _lib.lib()
-    n, C = X.shape
-    H = torch.zeros((n, 2 * C + ld_extra), dtype=torch.float16, device="cuda")
-    err = torch.zeros(1, dtype=torch.int32, device="cuda")
-    _lib.check(L.imf_h2_pack(X.data_ptr(), X.stride(0), n, C, kc, H.data_ptr(), H.stride(0), err.data_ptr(), _lib.cur_stream()))
-    torch.cuda.synchronize()
-    assert int(err.item()) == 0
-    return H
-
-
-def h2_unpack(H, C, kc):
-    L = _lib.lib()
-    n = H.shape[0]
-    X = torch.empty((n, C), dtype=torch.float32, device="cuda")
-    _lib.check(L.imf_h2_unpack(H.data_ptr(), H.stride(0), n, C, kc, X.data_ptr(), C, _lib.cur_stream()))
-    torch.cuda.synchronize()
-    return X
-
-
-def run_conv_h2(X, W, nbr, n_out, scale, shift, R=None, relu=False, split=True, kc_out=None):
-    """fp32 in/out wrapper of the fp16 hi/lo tensor-core tier: pack -> conv -> unpack."""
-    L = _lib.lib()
-    K3, cin, cout = W.shape
-    kc_in = 64 if cin % 64 == 0 else 32
-    kc_out = kc_out or (64 if cout % 64 == 0 else 32)
-    wmul = 2.0 ** np.floor(np.log2(2048.0 / float(W.abs().max())))
-    packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(K3, cin, cout, kc_in)), dtype=torch.uint8, device="cuda")
-    _lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), K3, cin, cout, kc_in, wmul, packed.data_ptr(), _lib.cur_stream()))
-    Xh = h2_pack(X, kc_in)
-    Rh = None if R is None else h2_pack(R, kc_out, ld_extra=16)
-    Yh = torch.full((n_out, 2 * cout + 8), float("nan"), dtype=torch.float16, device="cuda")
-    ws_bytes = int(L.imf_sparse_conv_h2_workspace_bytes(n_out, cout)) if split else 0
-    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
-    err = torch.zeros(1, dtype=torch.int32, device="cuda")
-    sc = (scale / wmul).contiguous()
-    _lib.check(L.imf_sparse_conv_h2_fwd(Xh.data_ptr(), Xh.stride(0), kc_in, packed.data_ptr(), nbr.data_ptr(), None, n_out, K3, cin,
-                                        cout, sc.data_ptr(), shift.data_ptr(), _lib.ptr(Rh), 0 if Rh is None else Rh.stride(0), kc_out,
-                                        int(relu), Yh.data_ptr(), Yh.stride(0), kc_out, ws.data_ptr() if split else None, ws_bytes,
-                                        err.data_ptr(), _lib.cur_stream()))
-    torch.cuda.synchronize()
-    assert int(err.item()) == 0
-    return h2_unpack(Yh, cout, kc_out).cpu()
-
-
-def test_h2_pack_unpack_roundtrip_keeps_22_bits():
-    g = torch.Generator().manual_seed(3)
-    X = (torch.randn(1000, 96, generator=g) * torch.logspace(-3, 3, 96)).cuda()
-    for kc in (32,):
-        back = h2_unpack(h2_pack(X, kc), 96, kc)
-        assert bool(((back - X).abs() <= torch.maximum(X.abs() * 2.0 ** -21, torch.tensor(6.1e-8, device="cuda"))).all())
-    X = torch.randn(777, 128, generator=g).cuda()
-    back = h2_unpack(h2_pack(X, 64, ld_extra=24), 128, 64)
-    assert bool(((back - X).abs() <= torch.maximum(X.abs() * 2.0 ** -21, torch.tensor(6.1e-8, device="cuda"))).all())
-
-
-@pytest.mark.parametrize("t_in,t_out,tr,cin,cout", [
-    (1, 1, False, 32, 32), (1, 1, False, 64, 64), (1, 2, False, 32, 64), (2, 2, False, 64, 64), (2, 4, False, 64, 128),
-    (4, 4, False, 128, 128), (4, 8, False, 128, 256), (8, 8, False, 256, 256), (8, 4, True, 256, 128), (4, 2, True, 256, 64),
-    (2, 1, True, 128, 64)])
-@pytest.mark.parametrize("split", [False, True])
-def test_h2_tensor_core_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout, split):
-    """tcgen05 kind::f16 implicit GEMM on fp16 hi/lo operands (3 products): fp32-class accuracy, tolerance 1e-4 as above."""
-    coords, ocm, cm = frag
-    g = torch.Generator().manual_seed(cin * 1000 + cout + t_in)
-    n_in, n_out = len(ocm.get(t_in)), len(ocm.get(t_out))
-    X = torch.randn(n_in, cin, generator=g)
-    W = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
-    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
-    R = torch.randn(n_out, cout, generator=g)
-    ref = torch.relu(sparse_ops.conv_forward(X, W, ocm.table(t_in, t_out, 3, tr)) * scale + shift + R)
-    out = run_conv_h2(X.cuda(), W.cuda(), cm.table(t_in, t_out, 3, tr), n_out, scale.cuda(), shift.cuda(), R.cuda(), True, split)
-    close(out, ref, H2_RTOL)
-
-
 def run_conv_g4(X, W, tab, n_out, scale, shift, R=None, relu=False, split=True, kc_out=None, n_dev=None, extra_rows=0):
     """fp32 in/out wrapper of the TMA-gather kernel: pack -> conv -> unpack.  tab = CoordinateManager.table_t(...)."""
     L = _lib.lib()
@@ -239,20 +147,6 @@ def test_g4_conv_device_side_row_count(frag):
         out = run_conv_g4(X.cuda(), W.cuda(), (nbr_t, ld_n, tile_mask), n_max, scale.cuda(), shift.cuda(), None, True, split, n_dev=n_dev)
         close(out[:n], ref, H2_RTOL)
         assert bool(torch.isnan(out[(n + 31) // 32 * 32:]).all())
-
-
-def test_h2_conv_equals_simt_conv_c2_size():
-    coords, _ = synthetic.make_fragment(50000, 0.025, 0)
-    from imfnet_b200.sparse import CoordinateManager
-    cm = CoordinateManager(torch.from_numpy(coords).cuda())
-    nbr = cm.table(1, 1, 3, False)
-    g = torch.Generator(device="cuda").manual_seed(1)
-    X = torch.randn(50000, 64, device="cuda", generator=g)
-    W = torch.randn(27, 64, 64, device="cuda", generator=g) / 40
-    a = run_conv(X, W, nbr, 50000)
-    one, zero = torch.ones(64, device="cuda"), torch.zeros(64, device="cuda")
-    b = run_conv_h2(X, W, nbr, 50000, one, zero, split=False)
-    close(b, a, H2_RTOL)
 
 
 def test_h2_first_conv_and_tail(frag):

@@ -52,6 +52,27 @@ def test_unique_first_matches_head_map_golden(golden_dir):
     assert np.array_equal(unique_first(torch.from_numpy(np.floor(xyz / 0.025).astype(np.int32)).cuda()).cpu().numpy(), oidx)
 
 
+def test_float32_cloud_is_quantised_in_float32_like_numpy():
+    """util/misc.py:82 computes np.floor(xyz / voxel_size) in the cloud's dtype: for a float32 cloud that is a float32 division, which
+    puts points next to a voxel boundary into other voxels than float64 would.  The GPU path must follow the input dtype."""
+    from imfnet_b200.voxelize import voxelize
+    rng = np.random.default_rng(5)
+    k = rng.integers(-400, 400, size=(200000, 3))
+    xyz32 = (k * np.float32(0.025) + rng.normal(0, 1e-7, k.shape)).astype(np.float32)      # points hugging the voxel boundaries
+    for voxel in (0.025, 0.05, 0.3):
+        ref32 = np.floor(xyz32 / voxel)
+        assert ref32.dtype == np.float32
+        ref64 = np.floor(xyz32.astype(np.float64) / voxel)
+        c, idx = voxelize(torch.from_numpy(xyz32).cuda(), voxel)
+        idx = idx.cpu().numpy()
+        assert np.array_equal(c.cpu().numpy()[:, 1:], ref32.astype(np.int32)[idx])
+        assert np.array_equal(idx, sparse_ops.unique_first(ref32.astype(np.int32)))
+        c64, idx64 = voxelize(torch.from_numpy(xyz32.astype(np.float64)).cuda(), voxel)
+        assert np.array_equal(c64.cpu().numpy()[:, 1:], ref64.astype(np.int32)[idx64.cpu().numpy()])
+        if voxel == 0.025:
+            assert (ref32 != ref64).any(), "the test cloud must contain points where the two dtypes disagree"
+
+
 def test_edge_cases_empty_single_duplicates_range():
     from imfnet_b200.sparse import CoordinateManager
     from imfnet_b200.voxelize import unique_first

@@ -282,3 +282,27 @@ def test_low_latency_setting_matches_throughput_setting(state_dict, cuda_model):
     assert rel_rows(a, b) < 5e-6
     assert note("low_latency_vs_oracle", rel_rows(b.cpu(), ref)) < TOL
     assert note("throughput_setting_vs_oracle", rel_rows(a.cpu(), ref)) < TOL
+
+
+def test_reference_call_sequence_on_gpu(state_dict, cuda_model):
+    """The call sequence of the reference's feature extraction (util/misc.py:76-100: np.floor -> ME.utils.sparse_quantize ->
+    ME.utils.batched_coordinates -> torch tensors -> ME.SparseTensor(..., device) -> model(stensor, image).F), restated here against
+    the drop-in module on the real kernels (the reference file itself is run by tests/test_reference_callers.py where it exists)."""
+    import imfnet_b200.me as ME
+    _, pts = synthetic.make_fragment(6000, 0.05, seed=31)
+    xyz = np.concatenate([pts + 0.01, pts[::3] + 0.02])
+    image = synthetic.make_image(160, 120, seed=31).numpy()
+    feats = np.ones((len(xyz), 1))
+    coords = np.floor(xyz / 0.05)
+    coords, inds = ME.utils.sparse_quantize(coords, return_index=True)
+    assert isinstance(coords, np.ndarray) and coords.dtype == np.int32
+    coords = ME.utils.batched_coordinates([coords])
+    stensor = ME.SparseTensor(torch.tensor(feats[inds], dtype=torch.float32), coordinates=torch.as_tensor(coords, dtype=torch.int32), device="cuda:0")
+    F = cuda_model(stensor, torch.as_tensor(image, dtype=torch.float32, device="cuda:0")).F
+    idx = np.sort(np.unique(np.floor(xyz / 0.05).astype(np.int64) @ np.array([1, 1 << 20, 1 << 40]), return_index=True)[1])
+    assert np.array_equal(inds, idx)
+    ref = imfnet_oracle.forward(state_dict, torch.as_tensor(coords, dtype=torch.int32), torch.ones((len(idx), 1)), torch.from_numpy(image))
+    assert note("reference_call_sequence_vs_oracle", rel_rows(F.cpu(), ref)) < TOL
+    # the evaluation script's keypoint/voxel intersection helper (scripts/evaluation_3dmatch.py:164-168)
+    h = ME.utils.fnv_hash_vec(np.floor(xyz[inds] / 0.05))
+    assert h.dtype == np.uint64 and len(np.unique(h)) == len(h)

@@ -68,3 +68,40 @@ def test_shard_indices_cover_everything_once():
     assert sorted(parts[0] + parts[1]) == list(range(6))
     loads = [sum(w[i] for i in p) for p in parts]
     assert abs(loads[0] - loads[1]) <= 1
+
+
+def test_plan_cache_is_lru_and_bounded_by_bytes():
+    """The model's cache of captured plans (engine.PlanCache) evicts least-recently-used entries beyond its byte budget."""
+    from imfnet_b200.engine import PlanCache
+
+    class P:
+        def __init__(self, n):
+            self.n = n
+
+        def nbytes(self):
+            return self.n
+
+    c = PlanCache(budget_bytes=100)
+    c[("a",)] = P(40)
+    pool = c.setdefault(("pool", 1), [])
+    pool.append(P(30))
+    pool.append(P(20))
+    c.trim(keep=("pool", 1))
+    assert len(c) == 2 and c.nbytes() == 90
+    assert c.get(("a",)).n == 40                      # touch: ("a",) is now the most recent entry
+    c[("b",)] = P(50)
+    c.trim(keep=("b",))
+    assert ("pool", 1) not in c and ("a",) in c and ("b",) in c and c.evictions == 1
+    c[("huge",)] = P(500)
+    c.trim(keep=("huge",))                           # the entry in use is never dropped, everything else goes
+    assert list(c.keys()) == [("huge",)]
+    c.clear()
+    assert len(c) == 0
+
+
+def test_mutual_nn_ignores_rows_without_a_match():
+    from imfnet_b200.pipeline import mutual_from_nn
+    nn21 = torch.tensor([2, -1, 0, 1], dtype=torch.int32)          # row 1 of fragment 2 has no match (e.g. NaN descriptor)
+    nn12 = torch.tensor([2, 3, 0], dtype=torch.int32)
+    assert mutual_from_nn(nn12, nn21).tolist() == [0, 2, 3]
+    assert mutual_from_nn(torch.zeros(0, dtype=torch.int32), torch.full((3,), -1, dtype=torch.int32)).tolist() == []

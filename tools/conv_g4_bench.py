@@ -23,11 +23,16 @@ ap.add_argument("--grid", type=int, default=0)
 ap.add_argument("--trace", action="store_true")
 ap.add_argument("--npw", type=int, default=0, help="minimum stages per split CTA (profiling hook)")
 ap.add_argument("--flags", default="0", help="comma list of profiling flags: 1 no W copies, 2 no gathers, 4 no MMAs")
-ap.add_argument("--old", action="store_true", help="also time imf_sparse_conv_h2_fwd (the cp.async kernel)")
+ap.add_argument("--frags", type=int, default=1, help="fragments of --n voxels in one launch (batch index in column 0), as the batched plan runs it")
 args = ap.parse_args()
 
 L = _lib.lib()
-coords, _ = synthetic.make_fragment(args.n, 0.025, 0)
+parts = []
+for b in range(args.frags):
+    c, _ = synthetic.make_fragment(args.n, 0.025, b)
+    c[:, 0] = b
+    parts.append(c)
+coords = np.concatenate(parts)
 cm = CoordinateManager(torch.from_numpy(coords).cuda())
 nbr_t, ld_n, tile_mask = cm.table_t(1, 1, 3, False)
 n, cin, cout = len(coords), args.cin, args.cout
@@ -75,17 +80,11 @@ def timeit(fn, label):
 for fl in [int(f) for f in args.flags.split(",")]:
     L.imf_debug_conv_g4_trace(None, args.grid, args.npw, fl)
     timeit(g4, f"g4 grid={args.grid or 148} npw={args.npw or 8} flags={fl}")
+    if fl == 0:
+        assert int(err.item()) == 0, int(err.item())
+    err.zero_()          # (with profiling flags the results are meaningless and may leave the fp16 range)
 L.imf_debug_conv_g4_trace(None, args.grid, args.npw, 0)
-assert int(err.item()) == 0, int(err.item())
-if args.old:
-    nbr = cm.table(1, 1, 3, False)
-
-    def old():
-        _lib.check(L.imf_sparse_conv_h2_fwd(Xh.data_ptr(), 2 * cin, kci, packed.data_ptr(), nbr.data_ptr(), None, n, 27, cin, cout,
-                                            one.data_ptr(), zero.data_ptr(), None, 0, 0, 1, Yh.data_ptr(), 2 * cout, kco, None, 0,
-                                            err.data_ptr(), s))
-    timeit(old, "h2 (cp.async)")
-if args.trace:
+if args.trace:      # needs a library built with IMFNET_B200_NVCC_FLAGS=-DIMF_G4_TRACE
     trace = torch.zeros(1024, dtype=torch.int64, device="cuda")
     L.imf_debug_conv_g4_trace(trace.data_ptr(), args.grid, args.npw, int(args.flags.split(",")[-1]))
     g4()
