@@ -64,6 +64,9 @@ SIGNATURES = {
     "imf_attention_fusion_fwd_m": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _p, _i32, _p, _i32, _p, _sz, _p]),
     "imf_sparse_conv_h2_packed_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "imf_sparse_conv_h2_pack": (C.c_int, [_p, _i32, _i32, _i32, _i32, _f32, _p, _p]),
+    "imf_conv_first_tc_columns": (_i32, [_i32]),
+    "imf_conv_first_tc_workspace_bytes": (_sz, [_i32, _i32]),
+    "imf_conv_first_tc_h2_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _sz, _p, _p]),
     "imf_conv_first_h2_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p]),
     "imf_pointwise_tail_h2_fwd": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _p, _i32, _p]),
     "imf_conv_first_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _p]),

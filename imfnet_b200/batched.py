@@ -114,6 +114,7 @@ class BatchGraphPlan(GraphPlan):
         m, dev = self.m, self.device
         CH = fused.CH
         self.B, self.item_cap8 = int(B), int(item_cap8)
+        self.num_items = self.B
         self.cap8 = self.rows                                   # the level itself lives in full-size buffers (d0, d1, d2, fused)
         i32 = dict(dtype=torch.int32, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)

@@ -1,0 +1,265 @@
+// imfnet_b200 -- first layer (conv1: K^3 = 5^3 offsets, ONE input channel) on the tensor cores.
+//
+//   conv1 = ME.MinkowskiConvolution(in_channels=1, out_channels=32, kernel_size=5)  + norm1     /root/reference/model/resunet.py:42-49, 168-169
+//   input feature = a column of ones at inference (util/misc.py:76-77), any [N,1] in general.
+//
+// Y[o, :] = sum_k f[nbr(o,k)] * W[k, 0, :] is a dense product E[N, K^3] . W[K^3, Cout] once the K^3 neighbour FEATURES of every voxel
+// are laid out as a row: E[o, k] = f[nbr(o,k)] (0 where the neighbour is absent).  The old kernel (k_conv_first, sparse_conv.cu)
+// probed the hash table 125 times per voxel and then walked the ~40 present offsets serially (shuffle + FMA per offset and lane):
+// 965 us for 10 x 50 k voxels, 23 % of the sparse part of a batched forward.  Here
+//   1. the voxels of every batch item are scattered into a DENSE row-index grid over the item's bounding box (+ a halo of K/2 cells,
+//      so neighbour reads need no range checks): a neighbour lookup becomes one 4-byte load at a computed address (5 consecutive x
+//      offsets share a 32-byte sector) instead of a 64-bit hash + 16-byte probe chain.  The grid lives in the caller's workspace;
+//      when the boxes do not fit its budget (sparse outdoor scans at a fine voxel size) the same kernel probes the hash table;
+//   2. k_cf_expand writes E as an h2 matrix (fp16 hi/lo, K^3 padded to a multiple of 64 columns) + an identity "neighbour table";
+//   3. the persistent tcgen05 convolution kernel (sparse_conv_g4.cu) runs the product as a one-offset convolution over E, with the
+//      BatchNorm affine in its epilogue -- the accumulation over offsets happens in TMEM, not in a per-voxel loop.
+#include <cuda_fp16.h>
+
+#include <climits>
+
+#include "common.cuh"
+
+extern "C" int imf_sparse_conv_g4_fwd(const void* X, int32_t ldx, int32_t kc_in, const void* packed, const int32_t* nbr_t, int32_t ld_n,
+                                      const uint32_t* tile_mask, const int32_t* n_out_dev, int32_t n_out_max, int32_t kernel_volume,
+                                      int32_t Cin, int32_t Cout, const float* scale, const float* shift, const void* residual, int32_t ldr,
+                                      int32_t kc_r, int32_t relu, void* Y, int32_t ldy, int32_t n_y_rows, int32_t kc_out, void* workspace,
+                                      size_t workspace_bytes, int32_t* err, cudaStream_t stream);
+
+namespace {
+
+constexpr int kMaxItems = 256;
+constexpr int kItemInts = 8;          // per item: x0, y0, z0 (box origin incl. halo), DX, DY, DZ, base (two ints: 64-bit cell offset)
+
+struct CfMeta {                        // head of the workspace
+  int use_grid;                        // 1: every item's box fits the grid budget; 0: probe the hash table
+  int pad[7];
+  int bbox[kMaxItems][6];              // running min x,y,z / max x,y,z per item (k_cf_bbox)
+  int item[kMaxItems][kItemInts];
+};
+
+__device__ __forceinline__ int cf_count(const int* n_ptr, int n_max) {
+  if (!n_ptr) return n_max;
+  const int v = *n_ptr;
+  return v < n_max ? v : n_max;
+}
+
+__global__ void k_cf_init(CfMeta* m, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * 6) m->bbox[i / 6][i % 6] = (i % 6) < 3 ? INT_MAX : INT_MIN;
+  if (i == 0) m->use_grid = 0;
+}
+
+// bounding box per batch item: block-level reduction when the block's voxels belong to one item (rows are batch-sorted, so almost
+// every block), per-thread atomics otherwise
+__global__ void __launch_bounds__(256) k_cf_bbox(const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max, int B, CfMeta* m) {
+  __shared__ int red[6][8];
+  __shared__ int same_s;
+  const int n = cf_count(n_ptr, n_max);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int first = blockIdx.x * 256;
+  if (first >= n) return;
+  const int last = min(n, first + 256) - 1;
+  const int b0 = coords[first].x, b1 = coords[last].x;
+  int4 c = make_int4(b0, INT_MAX, INT_MAX, INT_MAX);
+  const bool valid = i < n;
+  if (valid) c = coords[i];
+  if (threadIdx.x == 0) same_s = (b0 == b1) ? 1 : 0;
+  __syncthreads();
+  if (!same_s) {
+    if (valid && (unsigned)c.x < (unsigned)B) {
+      atomicMin(&m->bbox[c.x][0], c.y); atomicMin(&m->bbox[c.x][1], c.z); atomicMin(&m->bbox[c.x][2], c.w);
+      atomicMax(&m->bbox[c.x][3], c.y); atomicMax(&m->bbox[c.x][4], c.z); atomicMax(&m->bbox[c.x][5], c.w);
+    }
+    return;
+  }
+  int v[6] = {valid ? c.y : INT_MAX, valid ? c.z : INT_MAX, valid ? c.w : INT_MAX, valid ? c.y : INT_MIN, valid ? c.z : INT_MIN, valid ? c.w : INT_MIN};
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int t = __shfl_xor_sync(0xffffffffu, v[q], o);
+      v[q] = q < 3 ? min(v[q], t) : max(v[q], t);
+    }
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6 && (unsigned)b0 < (unsigned)B) {
+    const int q = threadIdx.x;
+    int r = red[q][0];
+    for (int w = 1; w < 8; ++w) r = q < 3 ? min(r, red[q][w]) : max(r, red[q][w]);
+    if (q < 3) atomicMin(&m->bbox[b0][q], r); else atomicMax(&m->bbox[b0][q], r);
+  }
+}
+
+// boxes -> grid layout; decides whether the grid path is used (one thread: B <= 256 items)
+__global__ void k_cf_layout(CfMeta* m, int B, int halo, long long budget_cells) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  long long total = 0;
+  bool ok = true;
+  for (int b = 0; b < B; ++b) {
+    int* it = m->item[b];
+    const int* bb = m->bbox[b];
+    if (bb[0] > bb[3]) {                 // empty item
+      it[0] = it[1] = it[2] = 0; it[3] = it[4] = it[5] = 0; it[6] = it[7] = 0;
+      continue;
+    }
+    const long long dx = (long long)bb[3] - bb[0] + 1 + 2 * halo, dy = (long long)bb[4] - bb[1] + 1 + 2 * halo,
+                    dz = (long long)bb[5] - bb[2] + 1 + 2 * halo;
+    it[0] = bb[0] - halo; it[1] = bb[1] - halo; it[2] = bb[2] - halo;
+    it[3] = (int)dx; it[4] = (int)dy; it[5] = (int)dz;
+    it[6] = (int)(total & 0xffffffffll); it[7] = (int)(total >> 32);
+    const long long cells = dx * dy * dz;
+    if (dx > 65536 || dy > 65536 || dz > 65536 || cells > budget_cells) { ok = false; break; }
+    total += cells;
+    if (total > budget_cells) { ok = false; break; }
+  }
+  m->use_grid = ok ? 1 : 0;
+  m->pad[0] = (int)(total & 0xffffffffll);
+  m->pad[1] = (int)(total >> 32);
+}
+
+__global__ void __launch_bounds__(256) k_cf_clear(const CfMeta* __restrict__ m, int4* __restrict__ grid) {
+  if (!m->use_grid) return;
+  const long long total = ((long long)(unsigned)m->pad[0]) | ((long long)m->pad[1] << 32);
+  const long long n4 = (total + 3) / 4;
+  const int4 e = make_int4(-1, -1, -1, -1);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) grid[i] = e;
+}
+
+__device__ __forceinline__ long long cf_cell(const int* it, int x, int y, int z) {
+  const long long base = ((long long)(unsigned)it[6]) | ((long long)it[7] << 32);
+  return base + ((long long)(z - it[2]) * it[4] + (y - it[1])) * it[3] + (x - it[0]);
+}
+
+__global__ void __launch_bounds__(256) k_cf_scatter(const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max, int B,
+                                                    const CfMeta* __restrict__ m, int* __restrict__ grid) {
+  if (!m->use_grid) return;
+  const int n = cf_count(n_ptr, n_max);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int4 c = coords[i];
+  if ((unsigned)c.x >= (unsigned)B) return;          // foreign batch index: reported by the caller's segment kernel
+  grid[cf_cell(m->item[c.x], c.y, c.z, c.w)] = i;
+}
+
+// E[row, k] = f[nbr(row, k)] as an h2 matrix of KP columns (chunk width 64); identity table + tile masks for the one-offset convolution.
+// One warp per voxel; lane l owns the 4 consecutive offsets k = 4 l + i of every 128-column group.
+template <int K>
+__global__ void __launch_bounds__(256) k_cf_expand(const float* __restrict__ X, int ldx, const int4* __restrict__ coords,
+                                                   const int* __restrict__ n_ptr, int n_max, int B, const CfMeta* __restrict__ m,
+                                                   const int* __restrict__ grid, const ImfSlot* __restrict__ table, unsigned long long mask,
+                                                   __half* __restrict__ E, int KP, int* __restrict__ ident, unsigned* __restrict__ tile_mask,
+                                                   int ld_n) {
+  constexpr int K3 = K * K * K, h = K / 2;
+  const int n = cf_count(n_ptr, n_max);
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= ld_n) return;
+  if (row >= n) {                                       // padding rows of the identity table (up to the 128-row boundary the kernel reads)
+    if (lane == 0 && row < (n + 127) / 128 * 128) ident[row] = -1;
+    if (lane == 0 && (row & 127) == 0 && row >= (n + 127) / 128 * 128) tile_mask[row >> 7] = 0u;
+    return;
+  }
+  const int4 c = coords[row];
+  const bool use_grid = m->use_grid != 0 && (unsigned)c.x < (unsigned)B;
+  const int* it = m->item[use_grid ? c.x : 0];
+  if (lane == 0) {
+    ident[row] = row;
+    if ((row & 127) == 0) tile_mask[row >> 7] = 1u;
+  }
+  __half* e_row = E + (size_t)row * (2 * KP);
+  for (int k0 = 4 * lane; k0 < KP; k0 += 128) {        // k0 = first of this lane's 4 offsets in the current 128-column group
+    float f[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + i;
+      int r = -1;
+      if (k < K3) {
+        const int x = c.y + (k % K - h), y = c.z + ((k / K) % K - h), z = c.w + (k / (K * K) - h);
+        if (use_grid) r = __ldg(grid + cf_cell(it, x, y, z));
+        else if (imf_coord_in_range(c.x, x, y, z)) r = imf_table_lookup(table, mask, imf_pack_key(c.x, x, y, z));
+      }
+      f[i] = r >= 0 ? __ldg(X + (size_t)r * ldx) : 0.f;
+    }
+    const __half2 h01 = __floats2half2_rn(f[0], f[1]), h23 = __floats2half2_rn(f[2], f[3]);
+    const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(f[0] - b01.x, f[1] - b01.y), l23 = __floats2half2_rn(f[2] - b23.x, f[3] - b23.y);
+    // chunk q = k0 / 64 holds [hi 64 | lo 64]
+    __half* p = e_row + (k0 / 64) * 128 + (k0 % 64);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const unsigned*>(&h01), *reinterpret_cast<const unsigned*>(&h23));
+    *reinterpret_cast<uint2*>(p + 64) = make_uint2(*reinterpret_cast<const unsigned*>(&l01), *reinterpret_cast<const unsigned*>(&l23));
+  }
+}
+
+inline size_t r256(size_t b) { return (b + 255) / 256 * 256; }
+inline int cf_kp(int K) { return (K * K * K + 63) / 64 * 64; }
+inline long long cf_budget_cells(int n_max) { return 64LL * (n_max > 0 ? n_max : 1) + (1 << 20); }
+
+struct CfLayout {
+  size_t meta, grid, E, ident, mask, conv_ws, total;
+  int ld_n;
+};
+inline CfLayout cf_layout(int n_max, int K) {
+  CfLayout L;
+  const int KP = cf_kp(K);
+  L.ld_n = (n_max + 127) / 128 * 128;
+  size_t off = 0;
+  L.meta = off; off += r256(sizeof(CfMeta));
+  L.grid = off; off += r256((size_t)cf_budget_cells(n_max) * 4 + 16);
+  L.E = off;    off += r256((size_t)L.ld_n * 2 * KP * sizeof(__half));
+  L.ident = off; off += r256((size_t)L.ld_n * 4);
+  L.mask = off; off += r256((size_t)(L.ld_n / 128 + 2) * 4);
+  L.total = off;
+  return L;
+}
+
+}  // namespace
+
+extern "C" int32_t imf_conv_first_tc_columns(int32_t kernel_size) { return cf_kp(kernel_size); }
+extern "C" size_t imf_conv_first_tc_workspace_bytes(int32_t n_max, int32_t kernel_size) { return cf_layout(n_max, kernel_size).total; }
+
+// conv1 (+ folded BatchNorm) for ONE input channel through the tensor-core tier.  packed = imf_sparse_conv_h2_pack of the kernel
+// reshaped to ONE offset with K^3 (zero-padded to imf_conv_first_tc_columns) input channels; scale / shift as for imf_sparse_conv_g4_fwd.
+// coords carry the batch index in column 0 (< num_items); table / capacity = the hash table of the same coordinate set (fallback when
+// the items' bounding boxes exceed the workspace's dense-grid budget of 64 cells per voxel).  Y = h2 matrix (ldy halves, chunk kc_out).
+extern "C" int imf_conv_first_tc_h2_fwd(const float* X, int32_t ldx, const void* packed, const int32_t* coords, const int32_t* n_dev,
+                                        int32_t n_max, int32_t num_items, const void* table, long long capacity, int32_t kernel_size,
+                                        int32_t Cout, const float* scale, const float* shift, int32_t relu, void* Y, int32_t ldy,
+                                        int32_t kc_out, void* workspace, size_t workspace_bytes, int32_t* err, cudaStream_t stream) {
+  IMF_CHECK_ARG(n_max >= 0 && (kernel_size == 1 || kernel_size == 3 || kernel_size == 5) && num_items >= 1 && num_items <= kMaxItems);
+  IMF_CHECK_ARG(ldx >= 1 && (Cout == 32 || Cout == 64 || Cout == 128) && scale != nullptr && shift != nullptr);
+  IMF_CHECK_ARG(capacity > 0 && (capacity & (capacity - 1)) == 0);
+  if (n_max == 0) return IMF_OK;
+  IMF_CHECK_ARG(X != nullptr && packed != nullptr && coords != nullptr && table != nullptr && Y != nullptr && workspace != nullptr);
+  const CfLayout L = cf_layout(n_max, kernel_size);
+  IMF_CHECK_ARG(workspace_bytes >= L.total && ((uintptr_t)workspace % 256) == 0);
+  char* ws = reinterpret_cast<char*>(workspace);
+  CfMeta* meta = reinterpret_cast<CfMeta*>(ws + L.meta);
+  int* grid = reinterpret_cast<int*>(ws + L.grid);
+  __half* E = reinterpret_cast<__half*>(ws + L.E);
+  int* ident = reinterpret_cast<int*>(ws + L.ident);
+  unsigned* tmask = reinterpret_cast<unsigned*>(ws + L.mask);
+  const int4* c4 = reinterpret_cast<const int4*>(coords);
+  const int KP = cf_kp(kernel_size);
+  const int blocks = (n_max + 255) / 256;
+  k_cf_init<<<(num_items * 6 + 255) / 256, 256, 0, stream>>>(meta, num_items);
+  IMF_CHECK_LAUNCH();
+  k_cf_bbox<<<blocks, 256, 0, stream>>>(c4, n_dev, n_max, num_items, meta);
+  IMF_CHECK_LAUNCH();
+  k_cf_layout<<<1, 32, 0, stream>>>(meta, num_items, kernel_size / 2, cf_budget_cells(n_max));
+  IMF_CHECK_LAUNCH();
+  k_cf_clear<<<imf_sm_count() * 8, 256, 0, stream>>>(meta, reinterpret_cast<int4*>(grid));
+  IMF_CHECK_LAUNCH();
+  k_cf_scatter<<<blocks, 256, 0, stream>>>(c4, n_dev, n_max, num_items, meta, grid);
+  IMF_CHECK_LAUNCH();
+  const ImfSlot* tab = reinterpret_cast<const ImfSlot*>(table);
+  const unsigned long long hmask = (unsigned long long)capacity - 1;
+  const int eblocks = (L.ld_n + 7) / 8;
+  if (kernel_size == 5) k_cf_expand<5><<<eblocks, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, E, KP, ident, tmask, L.ld_n);
+  else if (kernel_size == 3) k_cf_expand<3><<<eblocks, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, E, KP, ident, tmask, L.ld_n);
+  else k_cf_expand<1><<<eblocks, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, E, KP, ident, tmask, L.ld_n);
+  IMF_CHECK_LAUNCH();
+  return imf_sparse_conv_g4_fwd(E, 2 * KP, 64, packed, ident, L.ld_n, tmask, n_dev, n_max, 1, KP, Cout, scale, shift, nullptr, 0, 0, relu, Y,
+                                ldy, n_max, kc_out, nullptr, 0, err, stream);
+}

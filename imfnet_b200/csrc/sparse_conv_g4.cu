@@ -217,25 +217,41 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   const G4Part part = g4_partition(n, gx, nst_max, P != nullptr, sps);
   const int n32 = (n + 31) & ~31;
 
-  // rows of this CTA and its sub-tiles
-  int row_begin, row_end, split = 0;
+  // Rows of this CTA, pass by pass.  Row mode: the T tiles are cut into `npass` equal WINDOWS of at most gx * MAXSUB tiles; in pass p
+  // every CTA takes its share of window p -- whole 128-row tiles, the first (window size % gx) CTAs one more than the others (no CTA
+  // carries a mostly empty trailing sub-tile: an MMA costs the same for 32 rows as for 128).  All CTAs therefore work on the same
+  // ~gx * MAXSUB * 128 rows (75 k at BN = 64: about 1.5 fragments of a batched launch) at the same time, and their gathers -- a row's
+  // neighbours are rows of the same fragment -- stay inside the L2 (126 MB) instead of sweeping all rows of a 500 k-row batch
+  // (128 MB of 64-channel activations + 54 MB of indices) concurrently; per CTA the tile count and the number of passes are what a
+  // contiguous partition gives.  Split mode: one tile per CTA, one pass.
+  int split = 0, npass = 1;
   if (part.row_mode) {
-    // whole 128-row tiles, the first T % gx CTAs one more than the others: same critical path as equal row counts, but no CTA
-    // carries a mostly empty trailing sub-tile (an MMA costs the same for 32 rows as for 128), and the short CTAs free their SM
-    // early for the other fragments' kernels
-    const int base = part.T / gx, extra = part.T - base * gx;
-    const int t0 = bx * base + min(bx, extra);
-    row_begin = t0 * kBM;
-    row_end = min((t0 + base + (bx < extra ? 1 : 0)) * kBM, n32);
+    npass = (part.T + gx * Cfg::MAXSUB - 1) / (gx * Cfg::MAXSUB);
   } else {
-    const int tile = bx / part.S;
     split = bx % part.S;
-    if (tile >= part.T) return;
-    row_begin = tile * kBM;
-    row_end = min(row_begin + kBM, n32);
+    if (bx / part.S >= part.T) return;
   }
-  if (row_begin >= row_end) return;
-  const int nsub_total = (row_end - row_begin + kBM - 1) / kBM;
+  auto pass_rows = [&](int pass, int& prow, int& pend) {       // rows [prow, pend) of this CTA in pass `pass`; returns the sub-tiles
+    int t0, cnt;
+    if (part.row_mode) {
+      const int w0 = (int)(((long long)part.T * pass) / npass), w1 = (int)(((long long)part.T * (pass + 1)) / npass);
+      const int wt = w1 - w0, base = wt / gx, extra = wt - base * gx;
+      t0 = w0 + bx * base + min(bx, extra);
+      cnt = base + (bx < extra ? 1 : 0);
+    } else {
+      t0 = bx / part.S;
+      cnt = 1;
+    }
+    prow = t0 * kBM;
+    pend = min((t0 + cnt) * kBM, n32);
+    return pend > prow ? (pend - prow + kBM - 1) / kBM : 0;
+  };
+  int nsub_max = 0;
+  {
+    int a, b;
+    for (int p = 0; p < npass; ++p) nsub_max = max(nsub_max, pass_rows(p, a, b));
+  }
+  if (nsub_max == 0) return;
   long long* cta_trace = (trace && zt == 0) ? trace + 256 : nullptr;      // per-CTA lifetime (profiling hook)
   const long long t_cta0 = clock64();
   if (bx | zt) trace = nullptr;
@@ -243,10 +259,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   if (tid == 0) G4_TRACE(0);
 
   uint32_t tmem_cols = 32;
-  {
-    const int nsub_pass = nsub_total < Cfg::MAXSUB ? nsub_total : Cfg::MAXSUB;
-    while ((int)tmem_cols < nsub_pass * Cfg::ACC_COLS) tmem_cols <<= 1;
-  }
+  while ((int)tmem_cols < nsub_max * Cfg::ACC_COLS) tmem_cols <<= 1;
   if (tid == 0) {
     for (int s = 0; s < NA; ++s) { tc::mbar_init(&full_a[s], 32 * HALVES); tc::mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < kNW; ++s) { tc::mbar_init(&full_w[s], 1); tc::mbar_init(&empty_w[s], kNMW); }
@@ -263,10 +276,11 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   // offset masks of the first pass' sub-tiles: loaded here so that their latency overlaps the TMEM allocation
   if (tid >= 64 && tid < 64 + kMaxSubAll) {
     const int j = tid - 64;
-    const int nsub0 = nsub_total < Cfg::MAXSUB ? nsub_total : Cfg::MAXSUB;
+    int prow0, pend0;
+    const int nsub0 = pass_rows(0, prow0, pend0);
     if (j < nsub0) {
-      const int r0 = row_begin + j * kBM;
-      const int r1 = min(r0 + kBM, row_end) - 1;
+      const int r0 = prow0 + j * kBM;
+      const int r1 = min(r0 + kBM, pend0) - 1;
       submask_s[j] = __ldg(tile_mask + r0 / kBM) | __ldg(tile_mask + r1 / kBM);
     }
   }
@@ -279,11 +293,11 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   // running ring positions (the producers and the MMA warps advance them identically)
   int ac = 0, a_slot = 0, w_slot = 0;
   uint32_t a_phase = 0u, w_phase = 0u;
-  const int npass = (nsub_total + Cfg::MAXSUB - 1) / Cfg::MAXSUB;
+  int passes_done = 0;                                  // executed passes (parity of the accumulator barrier)
   for (int pass = 0; pass < npass; ++pass) {
-    const int sub0 = pass * Cfg::MAXSUB;
-    const int nsub = min(Cfg::MAXSUB, nsub_total - sub0);
-    const int prow = row_begin + sub0 * kBM;            // first row of this pass
+    int prow, row_end;                                  // first row of this pass, end of this CTA's rows in it
+    const int nsub = pass_rows(pass, prow, row_end);
+    if (nsub == 0) continue;                            // (CTA-uniform: a window with fewer tiles than CTAs)
     // ---- offset masks of the sub-tiles; offset list of the pass with, per offset, the sub-tiles that need it ----
     if (pass > 0) {                                      // (pass 0: loaded before the set-up barrier)
       if (tid < nsub) {
@@ -533,7 +547,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       // =========================== epilogue (warps 0-7) ===========================
       const int q = warp & 3, h = warp >> 2;
       if (tid == 0) G4_TRACE(3);
-      tc::mbar_wait(&acc_bar, (uint32_t)pass & 1u, err, 5);
+      tc::mbar_wait(&acc_bar, (uint32_t)passes_done & 1u, err, 5);
       tc::tc_fence_after_sync();
       if (tid == 0) G4_TRACE(4);
       const unsigned started = 0xFFFFFFFFu;             // the MMA warps zero every accumulator before the first MMA
@@ -662,6 +676,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
     __syncthreads();                       // pass boundary: TMEM drained, staging reads done, ring reusable
     tc::tc_fence_after_sync();
     ac = ring_s[0]; a_slot = ring_s[1]; a_phase = (uint32_t)ring_s[2]; w_slot = ring_s[3]; w_phase = (uint32_t)ring_s[4];
+    ++passes_done;
   }
   if (warp == kNPW) tc::tmem_dealloc(tmem_d, tmem_cols);
   if (tid == 0) G4_TRACE(6);

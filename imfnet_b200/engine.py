@@ -81,6 +81,21 @@ class FusedPlan:
                 self.conv[cname] = (conv, buf, (scale / wmul).contiguous(), shift, kci)
         sc, sh = m.norm1.folded()
         self.norm1 = (sc, sh)
+        # conv1 with one input channel (the IMFNet configuration: a column of ones, util/misc.py:76-77) runs on the tensor cores as a
+        # dense product over the K^3 neighbour features (csrc/conv_first_tc.cu): its kernel packed as ONE offset with K^3 "channels"
+        self.conv1_tc = None
+        if m.conv1.in_channels == 1 and m.conv1.kernel_size in (1, 3, 5) and CH[1] in (32, 64, 128):
+            with torch.cuda.device(self.device):
+                K3 = m.conv1.kernel_size ** 3
+                KP = int(L.imf_conv_first_tc_columns(m.conv1.kernel_size))
+                w1 = torch.zeros((1, KP, CH[1]), dtype=torch.float32, device=self.device)
+                w1[0, :K3] = m.conv1.kernel.detach().reshape(K3, CH[1])
+                wmax = float(w1.abs().max())
+                wmul = 2.0 ** math.floor(math.log2(2048.0 / wmax)) if wmax > 0 else 1.0
+                buf = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(1, KP, CH[1], 64)), dtype=torch.uint8, device=self.device)
+                _lib.check(L.imf_sparse_conv_h2_pack(w1.data_ptr(), 1, KP, CH[1], 64, wmul, buf.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                torch.cuda.current_stream().synchronize()          # w1 is a temporary
+                self.conv1_tc = (buf, (sc / wmul).contiguous(), sh)
         self.final_bias = None if m.final.bias is None else m.final.bias.detach().reshape(-1).contiguous()
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -410,6 +425,11 @@ class GraphPlan:
         self.att_ws = torch.empty(max(self.att_ws_bytes, 1), **u8)
         self.conv_ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(max(max(CH[1:]), max(TR[1:]))))
         self.conv_ws = torch.zeros(self.conv_ws_bytes, **u8)          # head = arrival counters, zero on entry / left zero
+        self.num_items = 1                                            # batch items the coordinates may name (BatchGraphPlan: B)
+        self.cf_ws = None
+        if fused.conv1_tc is not None:
+            self.cf_ws_bytes = int(L.imf_conv_first_tc_workspace_bytes(rows, m.conv1.kernel_size))
+            self.cf_ws = torch.empty(self.cf_ws_bytes, **u8)
         self.out = torch.zeros((rows, m.out_channels), **f32)
         self.graph = None
         self.launches_per_replay = 0
@@ -523,10 +543,17 @@ class GraphPlan:
         kc2, kc4, k8 = _kc(TR[3], CH[2]), _kc(TR[4], CH[3]), _kc(CH[4])
         sc, sh = f.norm1
         tok = self._tl_begin("conv1", t_out=1, cin=m.conv1.in_channels, cout=CH[1], K=m.conv1.kernel_size ** 3, residual=False)
-        _lib.check(L.imf_conv_first_h2_fwd(self.feats.data_ptr(), self.feats.shape[1], m.conv1.in_channels, m.conv1.kernel.data_ptr(),
-                                           self.coords[1].data_ptr(), self._n(1), rows, self.tables[1].data_ptr(), self.cap,
-                                           m.conv1.kernel_size, 1, CH[1], sc.data_ptr(), sh.data_ptr(), 0, self.a0.data_ptr(),
-                                           2 * CH[1], _kc(CH[1]), s))
+        if self.cf_ws is not None:
+            packed1, sc1, sh1 = f.conv1_tc
+            _lib.check(L.imf_conv_first_tc_h2_fwd(self.feats.data_ptr(), self.feats.shape[1], packed1.data_ptr(), self.coords[1].data_ptr(),
+                                                  self._n(1), rows, self.num_items, self.tables[1].data_ptr(), self.cap, m.conv1.kernel_size,
+                                                  CH[1], sc1.data_ptr(), sh1.data_ptr(), 0, self.a0.data_ptr(), 2 * CH[1], _kc(CH[1]),
+                                                  self.cf_ws.data_ptr(), self.cf_ws_bytes, self.err.data_ptr(), s))
+        else:
+            _lib.check(L.imf_conv_first_h2_fwd(self.feats.data_ptr(), self.feats.shape[1], m.conv1.in_channels, m.conv1.kernel.data_ptr(),
+                                               self.coords[1].data_ptr(), self._n(1), rows, self.tables[1].data_ptr(), self.cap,
+                                               m.conv1.kernel_size, 1, CH[1], sc.data_ptr(), sh.data_ptr(), 0, self.a0.data_ptr(),
+                                               2 * CH[1], _kc(CH[1]), s))
         self._tl_end(tok)
         self._block(L, "block1", self.a0.data_ptr(), 2 * CH[1], _kc(CH[1]), 1, CH[1], self.a1, s1, ld1, kc1b, s)
         self._conv(L, "conv2", s1, ld1, (1, 2, False), 2, None, 0, 0, False, self.b0.data_ptr(), 2 * CH[2], _kc(CH[2]), s)

@@ -190,6 +190,20 @@ int imf_conv_first_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W,
                        int32_t Cout, const float* scale, const float* shift, int32_t relu, float* Y, int32_t ldy,
                        imf_stream_t stream);
 
+/* conv1 with ONE input channel on the tensor cores (csrc/conv_first_tc.cu): the K^3 neighbour features of every voxel are laid out as
+ * a row of an h2 matrix E[n, KP] (KP = imf_conv_first_tc_columns(K) = K^3 rounded up to 64; neighbours found through a dense row-index
+ * grid over every batch item's bounding box, or through the hash table when the boxes exceed the workspace's budget of 64 cells per
+ * voxel), then Y = act((E . W) * scale + shift) runs as a one-offset convolution in imf_sparse_conv_g4_fwd.
+ * packed = imf_sparse_conv_h2_pack(W', 1, KP, Cout, 64, wmul) with W'[0, k, :] = kernel[k, 0, :] (rows >= K^3 zero); scale already
+ * divided by wmul.  coords column 0 = batch item (< num_items <= 256; other rows fall back to the hash probe).  workspace: 256-byte
+ * aligned, imf_conv_first_tc_workspace_bytes(n_max, K).  Y: h2 matrix with >= n_max rows (ldy halves, chunk width kc_out). */
+int32_t imf_conv_first_tc_columns(int32_t kernel_size);
+size_t imf_conv_first_tc_workspace_bytes(int32_t n_max, int32_t kernel_size);
+int imf_conv_first_tc_h2_fwd(const float* X, int32_t ldx, const void* packed, const int32_t* coords, const int32_t* n_dev, int32_t n_max,
+                             int32_t num_items, const void* table, long long capacity, int32_t kernel_size, int32_t Cout,
+                             const float* scale, const float* shift, int32_t relu, void* Y, int32_t ldy, int32_t kc_out, void* workspace,
+                             size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+
 /* imf_conv_first_fwd writing an h2 matrix (ldy in halves, chunk width kc_out). */
 int imf_conv_first_h2_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords, const int32_t* n_dev,
                           int32_t n_max, const void* table, long long capacity, int32_t kernel_size, int32_t tensor_stride,

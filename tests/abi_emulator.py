@@ -16,7 +16,7 @@ from numpy.lib.stride_tricks import as_strided
 
 from imfnet_b200 import _lib
 
-HOST_ONLY = {"imf_last_error", "imf_version", "imf_launch_count", "imf_hash_capacity", "imf_hash_bytes", "imf_device_sm_count"}
+HOST_ONLY = {"imf_conv_first_tc_columns", "imf_last_error", "imf_version", "imf_launch_count", "imf_hash_capacity", "imf_hash_bytes", "imf_device_sm_count"}
 
 
 def vec(ptr, n, dtype=np.float32):
@@ -214,6 +214,25 @@ class Emulator:
                 acc[ok] += x[idx[ok]] @ Wk[k]
         if scale:
             acc = acc * vec(scale, Cout) + vec(shift, Cout)
+        if relu:
+            acc = np.maximum(acc, 0)
+        mat(Y, n, Cout, ldy // 2)[:] = acc
+
+    def do_imf_conv_first_tc_h2_fwd(self, X, ldx, packed, coords, n_dev, n_max, num_items, table, cap, K, Cout, scale, shift, relu, Y, ldy,
+                                    kc_out, ws, ws_bytes, err):
+        n = count(n_dev, n_max)
+        C = mat(coords, n, 4, 4, np.int32).tolist()
+        x = mat(X, n, 1, ldx)
+        Wk = self.packed[packed]                      # [1, KP, Cout] (already times wmul; scale carries 1 / wmul)
+        assert Wk.shape[0] == 1 and Wk.shape[1] >= K ** 3 and Wk.shape[2] == Cout and not Wk[0, K ** 3:].any()
+        t = self.tables[table]
+        acc = np.zeros((n, Cout), dtype=np.float32)
+        for k, (dx, dy, dz) in enumerate(offsets(K).tolist()):
+            idx = np.fromiter((t.get((b, x_ + dx, y_ + dy, z_ + dz), -1) for b, x_, y_, z_ in C), dtype=np.int64, count=n)
+            ok = idx >= 0
+            if ok.any():
+                acc[ok] += x[idx[ok]] @ Wk[0, k:k + 1]
+        acc = acc * vec(scale, Cout) + vec(shift, Cout)
         if relu:
             acc = np.maximum(acc, 0)
         mat(Y, n, Cout, ldy // 2)[:] = acc

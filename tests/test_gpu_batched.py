@@ -53,13 +53,14 @@ def test_batched_plan_rejects_wrong_batch_index_capacity(cuda_model):
     frags = fragments([3000, 3000], 160, 120)
     import imfnet_b200.me as ME
     singles = [cuda_model(ME.SparseTensor(f.cuda(), coordinates=c.cuda()), im.cuda()).F.cpu() for c, f, im in frags]
-    saved = type(cuda_model).__dict__["_cap8"]          # the staticmethod object itself (attribute access would unwrap it)
+    cls = type(cuda_model)
+    assert "_cap8" not in cls.__dict__          # inherited from ResUNet2: shadow it on the subclass, remove the shadow afterwards
     try:
-        type(cuda_model)._cap8 = staticmethod(lambda rows, scale: 16)          # absurdly small per-item capacity
+        cls._cap8 = staticmethod(lambda rows, scale: 16)          # absurdly small per-item capacity
         cuda_model._graphs.clear()
         outs = cuda_model.forward_batches([(c.cuda(), f.cuda(), im.cuda()) for c, f, im in frags], batch=2)
     finally:
-        type(cuda_model)._cap8 = saved
+        del cls._cap8
         cuda_model._graphs.clear()
         cuda_model._cap8_scale.clear()
     for o, s in zip(outs, singles):

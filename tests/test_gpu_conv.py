@@ -41,6 +41,54 @@ def run_conv(X, W, nbr, n_out, scale=None, shift=None, R=None, relu=False):
     return Y.cpu()
 
 
+@pytest.mark.parametrize("t_in,t_out,tr,cin,cout", [
+    (1, 1, False, 32, 32), (1, 1, False, 64, 64), (1, 2, False, 32, 64), (2, 2, False, 64, 64), (2, 4, False, 64, 128),
+    (4, 4, False, 128, 128), (4, 8, False, 128, 256), (8, 8, False, 256, 256), (8, 4, True, 256, 128), (4, 2, True, 256, 64),
+    (2, 1, True, 128, 64)])
+def test_conv_matches_oracle(frag, t_in, t_out, tr, cin, cout):
+    coords, ocm, cm = frag
+    g = torch.Generator().manual_seed(cin * 1000 + cout + t_in)
+    n_in, n_out = len(ocm.get(t_in)), len(ocm.get(t_out))
+    X = torch.randn(n_in, cin, generator=g)
+    W = torch.randn(27, cin, cout, generator=g) / np.sqrt(27 * cin)
+    onbr = ocm.table(t_in, t_out, 3, tr)
+    ref = sparse_ops.conv_forward(X, W, onbr)
+    nbr = cm.table(t_in, t_out, 3, tr)
+    assert np.array_equal(nbr.cpu().numpy(), onbr)
+    close(run_conv(X.cuda(), W.cuda(), nbr, n_out), ref)
+
+
+def h2_pack(X, kc, ld_extra=0):
+    L = _lib.lib()
+    n, C = X.shape
+    H = torch.zeros((n, 2 * C + ld_extra), dtype=torch.float16, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(L.imf_h2_pack(X.data_ptr(), X.stride(0), n, C, kc, H.data_ptr(), H.stride(0), err.data_ptr(), _lib.cur_stream()))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    return H
+
+
+def h2_unpack(H, C, kc):
+    L = _lib.lib()
+    n = H.shape[0]
+    X = torch.empty((n, C), dtype=torch.float32, device="cuda")
+    _lib.check(L.imf_h2_unpack(H.data_ptr(), H.stride(0), n, C, kc, X.data_ptr(), C, _lib.cur_stream()))
+    torch.cuda.synchronize()
+    return X
+
+
+def test_h2_pack_unpack_roundtrip_keeps_22_bits():
+    g = torch.Generator().manual_seed(3)
+    X = (torch.randn(1000, 96, generator=g) * torch.logspace(-3, 3, 96)).cuda()
+    for kc in (32,):
+        back = h2_unpack(h2_pack(X, kc), 96, kc)
+        assert bool(((back - X).abs() <= torch.maximum(X.abs() * 2.0 ** -21, torch.tensor(6.1e-8, device="cuda"))).all())
+    X = torch.randn(777, 128, generator=g).cuda()
+    back = h2_unpack(h2_pack(X, 64, ld_extra=24), 128, 64)
+    assert bool(((back - X).abs() <= torch.maximum(X.abs() * 2.0 ** -21, torch.tensor(6.1e-8, device="cuda"))).all())
+
+
 def run_conv_g4(X, W, tab, n_out, scale, shift, R=None, relu=False, split=True, kc_out=None, n_dev=None, extra_rows=0):
     """fp32 in/out wrapper of the TMA-gather kernel: pack -> conv -> unpack.  tab = CoordinateManager.table_t(...)."""
     L = _lib.lib()
@@ -223,6 +271,83 @@ def test_first_conv_matches_oracle(frag, cin, cout, K):
                                     sh_d.data_ptr(), 0, Y.data_ptr(), cout, _lib.cur_stream()))
     torch.cuda.synchronize()
     close(Y.cpu(), ref)
+
+
+def run_conv_first_tc(coords_np, X, W, scale, shift, K, num_items, n_dev=None):
+    """imf_conv_first_tc_h2_fwd (dense-grid / hash-probe neighbour expansion + one-offset tensor-core convolution), fp32 in/out."""
+    from imfnet_b200.sparse import CoordinateManager
+    L = _lib.lib()
+    n, cout = len(coords_np), W.shape[2]
+    cm = CoordinateManager(torch.from_numpy(coords_np).cuda(), check=False)
+    lvl = cm.level(1)
+    KP = int(L.imf_conv_first_tc_columns(K))
+    w1 = torch.zeros((1, KP, cout), device="cuda")
+    w1[0, :K ** 3] = W[:, 0, :].cuda()
+    wmul = 2.0 ** np.floor(np.log2(2048.0 / float(w1.abs().max())))
+    packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(1, KP, cout, 64)), dtype=torch.uint8, device="cuda")
+    _lib.check(L.imf_sparse_conv_h2_pack(w1.data_ptr(), 1, KP, cout, 64, wmul, packed.data_ptr(), _lib.cur_stream()))
+    ws_bytes = int(L.imf_conv_first_tc_workspace_bytes(n, K))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    kco = 64 if cout % 64 == 0 else 32
+    Yh = torch.full((n, 2 * cout), float("nan"), dtype=torch.float16, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    X_d, sc_d, sh_d = X.cuda().contiguous(), (scale / wmul).cuda().contiguous(), shift.cuda().contiguous()
+    _lib.check(L.imf_conv_first_tc_h2_fwd(X_d.data_ptr(), X_d.stride(0), packed.data_ptr(), lvl.coords.data_ptr(), _lib.ptr(n_dev), n, num_items,
+                                          lvl.table.data_ptr(), lvl.capacity, K, cout, sc_d.data_ptr(), sh_d.data_ptr(), 0, Yh.data_ptr(),
+                                          2 * cout, kco, ws.data_ptr(), ws_bytes, err.data_ptr(), _lib.cur_stream()))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    use_grid = int(ws[:4].view(torch.int32).item())
+    return h2_unpack(Yh, cout, kco).cpu(), use_grid
+
+
+@pytest.mark.parametrize("cout,K", [(32, 5), (32, 3), (64, 5), (32, 1)])
+def test_first_conv_tensor_core_path_matches_oracle(frag, cout, K):
+    """conv1 with one input channel as neighbour expansion (dense row-index grid) + tcgen05 product, against the oracle's convolution."""
+    coords, ocm, cm = frag
+    g = torch.Generator().manual_seed(cout + K)
+    n = len(coords)
+    X = torch.rand(n, 1, generator=g) + 0.5
+    W = torch.randn(K ** 3, 1, cout, generator=g) / np.sqrt(K ** 3)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ref = sparse_ops.conv_forward(X, W, ocm.table(1, 1, K, False)) * scale + shift
+    out, use_grid = run_conv_first_tc(coords, X, W, scale, shift, K, 1)
+    assert use_grid == 1
+    close(out, ref, H2_RTOL)
+
+
+def test_first_conv_tensor_core_path_batches_fallback_and_device_count():
+    """(a) three batch items with different bounding boxes (one of them empty) share the grid; (b) scattered voxels whose boxes exceed
+    the grid budget take the hash-probe fallback; (c) a foreign batch index falls back per voxel; (d) a device-side row count."""
+    g = torch.Generator().manual_seed(9)
+    rng = np.random.default_rng(9)
+    K, cout = 5, 32
+    W = torch.randn(125, 1, cout, generator=g) / 11
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+
+    def check(coords, num_items, expect_grid, n_dev=None, n_eff=None):
+        n = len(coords)
+        X = torch.rand(n, 1, generator=g) + 0.5
+        m = n if n_eff is None else n_eff
+        ocm = sparse_ops.CoordinateManager(coords[:m])
+        ref = sparse_ops.conv_forward(X[:m], W, ocm.table(1, 1, K, False)) * scale + shift
+        out, use_grid = run_conv_first_tc(coords, X, W, scale, shift, K, num_items, n_dev)
+        assert use_grid == expect_grid
+        close(out[:m], ref, H2_RTOL)
+
+    a, _ = synthetic.make_fragment(3000, 0.05, seed=1)
+    b, _ = synthetic.make_fragment(2000, 0.05, seed=2)
+    b = b.copy(); b[:, 0] = 2; b[:, 1:] += np.array([500, -300, 40], dtype=np.int32)
+    check(np.concatenate([a, b]), 3, 1)                                             # item 1 is empty
+    centres = rng.integers(-20000, 20000, size=(60, 1, 3))
+    far = (centres + rng.integers(-3, 4, size=(60, 50, 3))).reshape(-1, 3).astype(np.int32)          # clusters far apart: neighbours exist
+    far = far[np.sort(np.unique(far, axis=0, return_index=True)[1])]
+    far = np.concatenate([np.zeros((len(far), 1), np.int32), far], axis=1)
+    check(far, 1, 0)
+    c = a.copy(); c[-100:, 0] = 7                                                   # batch index outside num_items for the last rows
+    check(c, 1, 1)
+    n_dev = torch.tensor([2100], dtype=torch.int32, device="cuda")
+    check(a, 1, 1, n_dev=n_dev, n_eff=2100)
 
 
 @pytest.mark.parametrize("normalize", [True, False])

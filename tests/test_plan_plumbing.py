@@ -13,7 +13,7 @@ import torch
 
 from imfnet_b200 import _lib, load_model, synthetic
 
-HOST_ONLY = {"imf_last_error", "imf_version", "imf_launch_count", "imf_hash_capacity", "imf_hash_bytes"}
+HOST_ONLY = {"imf_last_error", "imf_version", "imf_launch_count", "imf_hash_capacity", "imf_hash_bytes", "imf_device_sm_count", "imf_conv_first_tc_columns"}
 
 
 class FakeLib:
