@@ -53,8 +53,6 @@ SIGNATURES = {
     "imf_quantize_points_f32": (C.c_int, [_p, _i32, _f32, _i32, _p, _p]),
     "imf_batch_segments": (C.c_int, [_p, _p, _i32, _i32, _p, _p]),
     "imf_batch_segments_n": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
-    "imf_h2_unpack_seg": (C.c_int, [_p, _i32, _p, _p, _i32, _i32, _i32, _p, _i32, _p]),
-    "imf_h2_pack_seg": (C.c_int, [_p, _i32, _p, _p, _i32, _i32, _i32, _p, _i32, _p, _p]),
     "imf_sparse_conv_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _i32, _p]),
     "imf_h2_pack": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p, _p]),
     "imf_h2_unpack": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p]),
@@ -84,6 +82,11 @@ SIGNATURES = {
     "imf_attention_kv_workspace_bytes": (_sz, [_i32, _i32]),
     "imf_attention_kv": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _p, _sz, _p]),
     "imf_attention_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "imf_attention_kv_batched_bytes": (_sz, [_i32, _i32]),
+    "imf_attention_kv_batched_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "imf_attention_kv_batched": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _p, _sz, _p, _p]),
+    "imf_attention_batched_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+    "imf_attention_fusion_fwd_batched": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _sz, _p, _p]),
     "imf_attention_fusion_fwd": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _i32, _p, _i32, _p, _sz, _p]),
 }
 

@@ -16,8 +16,9 @@ fragment in the throughput setting (tests/test_gpu_batched.py).
 What is specific to a batch:
   * coordinates carry the item index in column 0 (set on the device after the host->device copy);
   * the image encoder runs once over B*H*W pixel rows with neighbour tables replicated per image (`BatchedImagePlan`);
-  * the fusion module runs per item on forked streams; the per-item row ranges at stride 8 stay on the device
-    (csrc/batched.cu: imf_batch_segments_n, imf_h2_unpack_seg, imf_h2_pack_seg).
+  * the fusion module runs ONCE over all items' stride-8 rows (everything but the attention core is row-wise); the attention
+    kernel takes the per-item row ranges, computed on the device (csrc/batched.cu: imf_batch_segments_n), and lets item b attend
+    to image b's tokens (csrc/flash_fusion.cu).  The single-fragment plan is the same code with B = 1 (engine.GraphPlan).
 
 This is the execution mode bench.py measures; tests/test_gpu_batched.py checks it against the CPU oracle, the reference's golden
 outputs and forward() (bit-identical) on the GPU, tests/test_plan_emulated.py its host logic on the C-ABI emulator.
@@ -101,67 +102,17 @@ class BatchedImagePlan(ImagePlan):
 
 
 class BatchGraphPlan(GraphPlan):
-    """GraphPlan for exactly B fragments of at most `rows` voxels in total (each at most `item_cap8` rows at stride 8)."""
-
-    ERR_ITEM_CAPACITY = 0x20000
-    ERR_BATCH_INDEX = 0x40000
+    """GraphPlan for exactly B fragments of at most `rows` voxels in total (each sized for `item_cap8` rows at stride 8: the fusion
+    module's buffers hold B * item_cap8 tokens, shared by the items)."""
 
     def __init__(self, fused: FusedPlan, rows: int, H: int, W: int, B: int, item_cap8: int):
         if fused.split_small:
             raise NotImplementedError("the batched plan implements the throughput setting (model.low_latency = False)")
-        super().__init__(fused, rows, H, W, cap8=256)          # the base plan's stride-8 buffers are replaced below
-        L = _lib.lib()
-        m, dev = self.m, self.device
-        CH = fused.CH
-        self.B, self.item_cap8 = int(B), int(item_cap8)
-        self.num_items = self.B
-        self.cap8 = self.rows                                   # the level itself lives in full-size buffers (d0, d1, d2, fused)
-        i32 = dict(dtype=torch.int32, device=dev)
-        f32 = dict(dtype=torch.float32, device=dev)
-        u8 = dict(dtype=torch.uint8, device=dev)
-        self.image = torch.zeros((self.B, 3, self.H, self.W), **f32)
-        with torch.cuda.device(dev):
-            self.image_plan = BatchedImagePlan(m.img_encoder.backbone, self.H, self.W, self.B, err=self.err)
-        self.n_tok = self.image_plan.P2
-        self.P8 = self.fused32 = None
-        self.seg = torch.zeros(self.B + 1, **i32)
-        self.cnt = torch.zeros(self.B, **i32)
-        af = m.attention_fusion
-        self.att_ws_bytes = int(L.imf_attention_workspace_bytes(self.item_cap8, self.n_tok, af.latent_dim, af.inner))
-        self.item = [dict(P8=torch.zeros((self.item_cap8, CH[4]), **f32), fused32=torch.zeros((self.item_cap8, CH[4]), **f32),
-                          ws=torch.empty(max(self.att_ws_bytes, 1), **u8), stream=torch.cuda.Stream(device=dev)) for _ in range(self.B)]
-        self.att_ws = None
+        self.item_cap8 = int(item_cap8)
+        super().__init__(fused, rows, H, W, cap8=min(int(rows), int(B) * int(item_cap8)), B=B)
 
-    # -- the two steps of GraphPlan._enqueue that a batch changes ------------------------------------------------------------
-    def _enqueue_image(self, m, main):
-        """Image branch on a forked stream: ONE encoder pass over all images, then K / V of every item."""
-        side = main if self._tl is not None else self.side          # (layer timing: nothing runs beside the timed kernels)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            tokens = self.image_plan.enqueue(self.image)
-            P2 = self.image_plan.P2
-            self.kvs = [m.attention_fusion.project_context(tokens[b * P2:(b + 1) * P2], False) for b in range(self.B)]
-
-    def _enqueue_fusion(self, L, m, C8, k8, main, s):
-        """Attention fusion at stride 8, one chain per batch item on its own stream (model/resunet.py:240-271): the item's rows
-        [seg[b], seg[b] + cnt[b]) of d2 (h2) -> its private P8 -> fused32 -> the same rows of fused (h2)."""
-        af = m.attention_fusion
-        _lib.check(L.imf_batch_segments_n(self.coords[8].data_ptr(), self._n(8), self.rows, self.B, self.item_cap8, self.seg.data_ptr(),
-                                          self.cnt.data_ptr(), self.err.data_ptr(), s))
-        main.wait_stream(self.side)
-        for b, it in enumerate(self.item):
-            st = it["stream"]
-            st.wait_stream(main)
-            seg_b, cnt_b = self.seg.data_ptr() + 4 * b, self.cnt.data_ptr() + 4 * b
-            with torch.cuda.stream(st):
-                sb = st.cuda_stream
-                _lib.check(L.imf_h2_unpack_seg(self.d2.data_ptr(), 2 * C8, seg_b, cnt_b, self.item_cap8, C8, k8, it["P8"].data_ptr(), C8, sb))
-                _lib.check(L.imf_attention_fusion_fwd_m(af.packed(), it["P8"].data_ptr(), C8, self.item_cap8, cnt_b, self.kvs[b].data_ptr(),
-                                                        self.n_tok, it["fused32"].data_ptr(), C8, it["ws"].data_ptr(), self.att_ws_bytes, sb))
-                _lib.check(L.imf_h2_pack_seg(it["fused32"].data_ptr(), C8, seg_b, cnt_b, self.item_cap8, C8, k8, self.fused.data_ptr(), 2 * C8,
-                                             self.err.data_ptr(), sb))
-        for it in self.item:
-            main.wait_stream(it["stream"])
+    def _make_image_plan(self, m, fused):
+        return BatchedImagePlan(m.img_encoder.backbone, self.H, self.W, self.B, err=self.err)
 
     # -- one batch ---------------------------------------------------------------------------------
     @torch.no_grad()
@@ -222,11 +173,7 @@ class BatchGraphPlan(GraphPlan):
         if mh[0]:
             from .sparse import _raise_status
             _raise_status(mh[0])
-        if mh[16] & self.ERR_BATCH_INDEX:
-            raise ValueError("coordinates carry a batch index outside the plan's batch size")
-        if mh[16] & self.ERR_ITEM_CAPACITY:
-            raise PlanCapacityError(f"a fragment has more than {self.item_cap8} voxels at stride 8")
-        FusedPlan._raise_on_status(mh[16])
+        self._check_fusion_status(mh)
         self.levels = {1: total, 2: mh[2], 4: mh[3], 8: mh[4]}
         return outs
 

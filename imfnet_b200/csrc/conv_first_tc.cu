@@ -7,10 +7,12 @@
 // are laid out as a row: E[o, k] = f[nbr(o,k)] (0 where the neighbour is absent).  The old kernel (k_conv_first, sparse_conv.cu)
 // probed the hash table 125 times per voxel and then walked the ~40 present offsets serially (shuffle + FMA per offset and lane):
 // 965 us for 10 x 50 k voxels, 23 % of the sparse part of a batched forward.  Here
-//   1. the voxels of every batch item are scattered into a DENSE row-index grid over the item's bounding box (+ a halo of K/2 cells,
-//      so neighbour reads need no range checks): a neighbour lookup becomes one 4-byte load at a computed address (5 consecutive x
-//      offsets share a 32-byte sector) instead of a 64-bit hash + 16-byte probe chain.  The grid lives in the caller's workspace;
-//      when the boxes do not fit its budget (sparse outdoor scans at a fine voxel size) the same kernel probes the hash table;
+//   1. the FEATURES of every batch item's voxels are scattered into a DENSE grid over the item's bounding box (+ a halo of K/2 cells,
+//      so neighbour reads need no range checks; empty cells hold 0, which contributes nothing): a neighbour's feature becomes one
+//      4-byte load at a computed address -- no hash, no probe chain, no second gather through a row index -- and the K cells of an
+//      x-run are contiguous, so one warp instruction covers 32 / K whole runs (6 cache lines instead of 25 for K = 5).  The grid
+//      lives in the caller's workspace; when the boxes do not fit its budget (sparse outdoor scans at a fine voxel size) the same
+//      kernel probes the hash table and gathers the feature through the row index;
 //   2. k_cf_expand writes E as an h2 matrix (fp16 hi/lo, K^3 padded to a multiple of 64 columns) + an identity "neighbour table";
 //   3. the persistent tcgen05 convolution kernel (sparse_conv_g4.cu) runs the product as a one-offset convolution over E, with the
 //      BatchNorm affine in its epilogue -- the accumulation over offsets happens in TMEM, not in a per-voxel loop.
@@ -119,11 +121,11 @@ __global__ void k_cf_layout(CfMeta* m, int B, int halo, long long budget_cells) 
   m->pad[1] = (int)(total >> 32);
 }
 
-__global__ void __launch_bounds__(256) k_cf_clear(const CfMeta* __restrict__ m, int4* __restrict__ grid) {
+__global__ void __launch_bounds__(256) k_cf_clear(const CfMeta* __restrict__ m, float4* __restrict__ grid) {
   if (!m->use_grid) return;
   const long long total = ((long long)(unsigned)m->pad[0]) | ((long long)m->pad[1] << 32);
   const long long n4 = (total + 3) / 4;
-  const int4 e = make_int4(-1, -1, -1, -1);
+  const float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) grid[i] = e;
 }
 
@@ -132,26 +134,28 @@ __device__ __forceinline__ long long cf_cell(const int* it, int x, int y, int z)
   return base + ((long long)(z - it[2]) * it[4] + (y - it[1])) * it[3] + (x - it[0]);
 }
 
-__global__ void __launch_bounds__(256) k_cf_scatter(const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max, int B,
-                                                    const CfMeta* __restrict__ m, int* __restrict__ grid) {
+__global__ void __launch_bounds__(256) k_cf_scatter(const float* __restrict__ X, int ldx, const int4* __restrict__ coords,
+                                                    const int* __restrict__ n_ptr, int n_max, int B, const CfMeta* __restrict__ m,
+                                                    float* __restrict__ grid) {
   if (!m->use_grid) return;
   const int n = cf_count(n_ptr, n_max);
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const int4 c = coords[i];
-  if ((unsigned)c.x >= (unsigned)B) return;          // foreign batch index: reported by the caller's segment kernel
-  grid[cf_cell(m->item[c.x], c.y, c.z, c.w)] = i;
+  if ((unsigned)c.x >= (unsigned)B) return;          // foreign batch index: such rows take the hash probe in k_cf_expand
+  grid[cf_cell(m->item[c.x], c.y, c.z, c.w)] = X[(size_t)i * ldx];
 }
 
 // E[row, k] = f[nbr(row, k)] as an h2 matrix of KP columns (chunk width 64); identity table + tile masks for the one-offset convolution.
-// One warp per voxel; lane l owns the 4 consecutive offsets k = 4 l + i of every 128-column group.
+// One warp per voxel.  Offset k = kx + K ky + K^2 kz (x fastest): the K cells of an x-run are contiguous in the grid, so instruction t
+// lets lane l read offset k = (K * RPI) t + l -- RPI = 32 / K whole runs per instruction.
 template <int K>
 __global__ void __launch_bounds__(256) k_cf_expand(const float* __restrict__ X, int ldx, const int4* __restrict__ coords,
                                                    const int* __restrict__ n_ptr, int n_max, int B, const CfMeta* __restrict__ m,
-                                                   const int* __restrict__ grid, const ImfSlot* __restrict__ table, unsigned long long mask,
+                                                   const float* __restrict__ grid, const ImfSlot* __restrict__ table, unsigned long long mask,
                                                    __half* __restrict__ E, int KP, int* __restrict__ ident, unsigned* __restrict__ tile_mask,
                                                    int ld_n) {
-  constexpr int K3 = K * K * K, h = K / 2;
+  constexpr int K3 = K * K * K, h = K / 2, KR = K * (32 / K);
   const int n = cf_count(n_ptr, n_max);
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -163,32 +167,31 @@ __global__ void __launch_bounds__(256) k_cf_expand(const float* __restrict__ X, 
   }
   const int4 c = coords[row];
   const bool use_grid = m->use_grid != 0 && (unsigned)c.x < (unsigned)B;
-  const int* it = m->item[use_grid ? c.x : 0];
+  int it[kItemInts];
+#pragma unroll
+  for (int i = 0; i < kItemInts; ++i) it[i] = use_grid ? m->item[c.x][i] : 0;
   if (lane == 0) {
     ident[row] = row;
     if ((row & 127) == 0) tile_mask[row >> 7] = 1u;
   }
   __half* e_row = E + (size_t)row * (2 * KP);
-  for (int k0 = 4 * lane; k0 < KP; k0 += 128) {        // k0 = first of this lane's 4 offsets in the current 128-column group
-    float f[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = k0 + i;
-      int r = -1;
+  if (lane < KR) {
+    for (int k = lane; k < KP; k += KR) {
+      float f = 0.f;
       if (k < K3) {
         const int x = c.y + (k % K - h), y = c.z + ((k / K) % K - h), z = c.w + (k / (K * K) - h);
-        if (use_grid) r = __ldg(grid + cf_cell(it, x, y, z));
-        else if (imf_coord_in_range(c.x, x, y, z)) r = imf_table_lookup(table, mask, imf_pack_key(c.x, x, y, z));
+        if (use_grid) {
+          f = __ldg(grid + cf_cell(it, x, y, z));
+        } else if (imf_coord_in_range(c.x, x, y, z)) {
+          const int r = imf_table_lookup(table, mask, imf_pack_key(c.x, x, y, z));
+          if (r >= 0) f = __ldg(X + (size_t)r * ldx);
+        }
       }
-      f[i] = r >= 0 ? __ldg(X + (size_t)r * ldx) : 0.f;
+      const __half hi = __float2half_rn(f);
+      __half* p = e_row + (k >> 6) * 128 + (k & 63);   // chunk k / 64 holds [hi 64 | lo 64]
+      p[0] = hi;
+      p[64] = __float2half_rn(f - __half2float(hi));
     }
-    const __half2 h01 = __floats2half2_rn(f[0], f[1]), h23 = __floats2half2_rn(f[2], f[3]);
-    const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
-    const __half2 l01 = __floats2half2_rn(f[0] - b01.x, f[1] - b01.y), l23 = __floats2half2_rn(f[2] - b23.x, f[3] - b23.y);
-    // chunk q = k0 / 64 holds [hi 64 | lo 64]
-    __half* p = e_row + (k0 / 64) * 128 + (k0 % 64);
-    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const unsigned*>(&h01), *reinterpret_cast<const unsigned*>(&h23));
-    *reinterpret_cast<uint2*>(p + 64) = make_uint2(*reinterpret_cast<const unsigned*>(&l01), *reinterpret_cast<const unsigned*>(&l23));
   }
 }
 
@@ -236,7 +239,7 @@ extern "C" int imf_conv_first_tc_h2_fwd(const float* X, int32_t ldx, const void*
   IMF_CHECK_ARG(workspace_bytes >= L.total && ((uintptr_t)workspace % 256) == 0);
   char* ws = reinterpret_cast<char*>(workspace);
   CfMeta* meta = reinterpret_cast<CfMeta*>(ws + L.meta);
-  int* grid = reinterpret_cast<int*>(ws + L.grid);
+  float* grid = reinterpret_cast<float*>(ws + L.grid);
   __half* E = reinterpret_cast<__half*>(ws + L.E);
   int* ident = reinterpret_cast<int*>(ws + L.ident);
   unsigned* tmask = reinterpret_cast<unsigned*>(ws + L.mask);
@@ -249,9 +252,9 @@ extern "C" int imf_conv_first_tc_h2_fwd(const float* X, int32_t ldx, const void*
   IMF_CHECK_LAUNCH();
   k_cf_layout<<<1, 32, 0, stream>>>(meta, num_items, kernel_size / 2, cf_budget_cells(n_max));
   IMF_CHECK_LAUNCH();
-  k_cf_clear<<<imf_sm_count() * 8, 256, 0, stream>>>(meta, reinterpret_cast<int4*>(grid));
+  k_cf_clear<<<imf_sm_count() * 8, 256, 0, stream>>>(meta, reinterpret_cast<float4*>(grid));
   IMF_CHECK_LAUNCH();
-  k_cf_scatter<<<blocks, 256, 0, stream>>>(c4, n_dev, n_max, num_items, meta, grid);
+  k_cf_scatter<<<blocks, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid);
   IMF_CHECK_LAUNCH();
   const ImfSlot* tab = reinterpret_cast<const ImfSlot*>(table);
   const unsigned long long hmask = (unsigned long long)capacity - 1;

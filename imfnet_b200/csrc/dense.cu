@@ -10,11 +10,11 @@
 #include "common.cuh"
 
 // fused attention kernel (flash_fusion.cu), used when the head has 128 channels (the IMFNet configuration)
-size_t imf_flash_kv_h2_bytes(int L);
-size_t imf_flash_workspace_bytes(int M_max, int L);
-int imf_flash_pack_kv(const float* K, const float* Vt, int ldv, int L, void* kvh2, cudaStream_t stream);
-int imf_flash_attention(const void* qh2, int M_max, const int* m_dev, const void* kvh2, int L, float* o, int ldo, void* workspace,
-                        size_t workspace_bytes, int* err, cudaStream_t stream);
+size_t imf_flash_kv_h2_bytes(int L, int B);
+size_t imf_flash_workspace_bytes(int M_max, int L, int B);
+int imf_flash_pack_kv(const float* K, int ldk, const float* V, int ldv, int v_transposed, int L, int B, void* kvh2, cudaStream_t stream);
+int imf_flash_attention(const void* qh2, int M_max, const int* seg_dev, const int* cnt_dev, const int* m_dev, int B, const void* kvh2, int L,
+                        float* o, int ldo, void* workspace, size_t workspace_bytes, int* err, cudaStream_t stream);
 extern "C" int imf_h2_pack_n(const float* X, int32_t ldx, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, void* H, int32_t ldh,
                              int32_t* err, cudaStream_t stream);
 
@@ -231,7 +231,7 @@ static inline int round4(int v) { return (v + 3) / 4 * 4; }
 // up to 4) so that both attention GEMMs read K-major operands.
 extern "C" size_t imf_attention_kv_bytes(int32_t L, int32_t inner) {
   // K [L, inner] fp32, V^T [inner, Lp] fp32, then (128-channel head) their fp16 hi/lo copies for the fused attention kernel
-  return r256((size_t)L * inner * 4) + r256((size_t)inner * round4(L) * 4) + (inner == 128 ? r256(imf_flash_kv_h2_bytes(L)) : 0);
+  return r256((size_t)L * inner * 4) + r256((size_t)inner * round4(L) * 4) + (inner == 128 ? r256(imf_flash_kv_h2_bytes(L, 1)) : 0);
 }
 extern "C" size_t imf_attention_kv_workspace_bytes(int32_t L, int32_t dim) { return r256((size_t)L * dim * 4); }
 
@@ -257,7 +257,7 @@ extern "C" int imf_attention_kv(const imf_attn_weights_t* w, const float* tokens
   if ((rc = imf_tc_gemm(w->wkv + (size_t)inner * dim, dim, cn, dim, Vt, Lp, inner, L, dim, 1.f, nullptr, nullptr, 0, 0, nullptr, 0, nullptr, stream))) return rc;
   if (inner == 128) {
     void* kvh2 = reinterpret_cast<char*>(kv) + r256((size_t)L * inner * 4) + r256((size_t)inner * Lp * 4);
-    return imf_flash_pack_kv(Kmat, Vt, Lp, L, kvh2, stream);
+    return imf_flash_pack_kv(Kmat, inner, Vt, Lp, 1, L, 1, kvh2, stream);
   }
   return IMF_OK;
 }
@@ -271,7 +271,7 @@ extern "C" size_t imf_attention_workspace_bytes(int32_t M, int32_t L, int32_t la
          + r256((size_t)M * latent * 4)    // x after attention residual
          + r256((size_t)M * latent * 4 * 4)   // GEGLU hidden [M, 4*latent]
          + r256(imf_tc_gemm_workspace_bytes(M, latent, 0))    // split-K partials (largest N used with split-K = latent)
-         + (inner == 128 ? r256((size_t)M * inner * 4) + r256(imf_flash_workspace_bytes(M, L)) : 0);   // q as h2 + flash partials
+         + (inner == 128 ? r256((size_t)M * inner * 4) + r256(imf_flash_workspace_bytes(M, L, 1)) : 0);   // q as h2 + flash partials
 }
 
 // out[M, latent] = cross-attention + GEGLU feed-forward of M point tokens P[M, latent] against kv (imf_attention_kv).
@@ -284,6 +284,65 @@ extern "C" int imf_attention_fusion_fwd(const imf_attn_weights_t* w, const float
   return imf_attention_fusion_fwd_m(w, P, ldp, M, nullptr, kv, L, out, ldo, workspace, workspace_bytes, stream);
 }
 
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+// The module body for M_max rows (min(*m_dev, M_max) of them valid) that belong to B batch items: everything except the attention
+// core is row-wise (LayerNorm, projections, GEGLU feed-forward), so ALL items go through ONE chain of launches; only the attention
+// core needs the item structure (rows [seg[b], seg[b] + cnt[b]) attend to image b's tokens).  kvh2: fp16 hi/lo K / V^T of the B images
+// (imf_flash_pack_kv); kv32 (B == 1, any head width): the fp32 K / V^T of imf_attention_kv for the unfused path.
+int attention_body(const imf_attn_weights_t* w, const float* P, int ldp, int M, const int* m_dev, const int* seg_dev, const int* cnt_dev, int B,
+                   const float* kv32, const void* kvh2, int L, float* out, int ldo, void* workspace, int* err, cudaStream_t stream) {
+  const int latent = w->latent, inner = w->inner;
+  const int Lp = round4(L);
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* xn = reinterpret_cast<float*>(ws);  ws += r256((size_t)M * latent * 4);
+  float* q = reinterpret_cast<float*>(ws);   ws += r256((size_t)M * inner * 4);
+  float* S = reinterpret_cast<float*>(ws);   ws += (kvh2 ? 0 : r256((size_t)M * Lp * 4));
+  float* o = reinterpret_cast<float*>(ws);   ws += r256((size_t)M * inner * 4);
+  float* x1 = reinterpret_cast<float*>(ws);  ws += r256((size_t)M * latent * 4);
+  float* hid = reinterpret_cast<float*>(ws); ws += r256((size_t)M * latent * 4 * 4);
+  void* gws = ws;
+  const size_t gws_bytes = imf_tc_gemm_workspace_bytes(M, latent, 0);
+  const float sm_scale = 1.0f / sqrtf((float)inner);
+  int rc;
+  k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(P, ldp, M, latent, w->ln_q_w, w->ln_q_b, 1e-5f, xn, latent, m_dev);
+  IMF_CHECK_LAUNCH();
+  // q = LN(P) . Wq^T   (fused attention: times log2(e) / sqrt(d), the kernel exponentiates with ex2)
+  if ((rc = imf_tc_gemm_m(xn, latent, w->wq, latent, q, inner, M, m_dev, inner, latent, kvh2 ? sm_scale * kLog2e : 1.f, nullptr, nullptr, 0, 0,
+                          gws, gws_bytes, err, stream))) return rc;
+  if (kvh2) {
+    // fused attention: q -> fp16 hi/lo -> one persistent tcgen05 kernel for q k^T, softmax and .v of every item (flash_fusion.cu)
+    char* ws2 = reinterpret_cast<char*>(gws) + r256(gws_bytes);
+    void* qh2 = ws2;
+    void* fws = ws2 + r256((size_t)M * inner * 4);
+    if ((rc = imf_h2_pack_n(q, inner, M, m_dev, inner, 64, qh2, 2 * inner, err, stream))) return rc;
+    if ((rc = imf_flash_attention(qh2, M, seg_dev, cnt_dev, m_dev, B, kvh2, L, o, inner, fws, imf_flash_workspace_bytes(M, L, B), err, stream)))
+      return rc;
+  } else {
+    const float* Kmat = kv32;
+    const float* Vt = reinterpret_cast<const float*>(reinterpret_cast<const char*>(kv32) + r256((size_t)L * inner * 4));
+    // S = (q . K^T) * scale
+    if ((rc = imf_tc_gemm_m(q, inner, Kmat, inner, S, Lp, M, m_dev, L, inner, sm_scale, nullptr, nullptr, 0, 0, nullptr, 0, err, stream))) return rc;
+    k_softmax_rows<<<M, 256, 0, stream>>>(S, Lp, M, L, m_dev);
+    IMF_CHECK_LAUNCH();
+    // o = A . V   (as A . (V^T)^T, split over the L tokens)
+    if ((rc = imf_tc_gemm_m(S, Lp, Vt, Lp, o, inner, M, m_dev, inner, L, 1.f, nullptr, nullptr, 0, 0, gws, gws_bytes, err, stream))) return rc;
+  }
+  // x1 = o . Wo^T + bo + P
+  if ((rc = imf_tc_gemm_m(o, inner, w->wo, inner, x1, latent, M, m_dev, latent, inner, 1.f, w->bo, P, ldp, 0, gws, gws_bytes, err, stream))) return rc;
+  k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(x1, latent, M, latent, w->ln_f_w, w->ln_f_b, 1e-5f, xn, latent, m_dev);
+  IMF_CHECK_LAUNCH();
+  // hid = geglu(LN(x1) . W1^T + b1)   [M, 4*latent]
+  if ((rc = imf_tc_gemm_m(xn, latent, w->w1, latent, hid, 4 * latent, M, m_dev, 4 * latent, latent, 1.f, w->b1, nullptr, 0, 1, nullptr, 0, err, stream))) return rc;
+  // out = hid . W2^T + b2 + x1
+  if ((rc = imf_tc_gemm_m(hid, 4 * latent, w->w2, 4 * latent, out, ldo, M, m_dev, latent, 4 * latent, 1.f, w->b2, x1, latent, 0, gws, gws_bytes, err, stream))) return rc;
+  return IMF_OK;
+}
+
+}  // namespace
+
 // Same with an optional device-side token count: only min(*m_dev, M) rows are computed (M sizes launches and workspace).
 extern "C" int imf_attention_fusion_fwd_m(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const int32_t* m_dev,
                                           const float* kv, int32_t L, float* out, int32_t ldo, void* workspace, size_t workspace_bytes,
@@ -293,51 +352,54 @@ extern "C" int imf_attention_fusion_fwd_m(const imf_attn_weights_t* w, const flo
   if (M == 0) return IMF_OK;
   IMF_CHECK_ARG(P != nullptr && kv != nullptr && out != nullptr && workspace != nullptr && ldp >= w->latent && ldo >= w->latent);
   IMF_CHECK_ARG(workspace_bytes >= imf_attention_workspace_bytes(M, L, w->latent, w->inner));
-  const int latent = w->latent, inner = w->inner;
-  const int Lp = round4(L);
-  char* ws = reinterpret_cast<char*>(workspace);
-  float* xn = reinterpret_cast<float*>(ws);  ws += r256((size_t)M * latent * 4);
-  float* q = reinterpret_cast<float*>(ws);   ws += r256((size_t)M * inner * 4);
-  float* S = reinterpret_cast<float*>(ws);   ws += r256((size_t)M * Lp * 4);
-  float* o = reinterpret_cast<float*>(ws);   ws += r256((size_t)M * inner * 4);
-  float* x1 = reinterpret_cast<float*>(ws);  ws += r256((size_t)M * latent * 4);
-  float* hid = reinterpret_cast<float*>(ws); ws += r256((size_t)M * latent * 4 * 4);
-  void* gws = ws;
-  const size_t gws_bytes = imf_tc_gemm_workspace_bytes(M, latent, 0);
-  const float* Kmat = kv;
-  const float* Vt = reinterpret_cast<const float*>(reinterpret_cast<const char*>(kv) + r256((size_t)L * inner * 4));
-  const float sm_scale = 1.0f / sqrtf((float)inner);
+  const void* kvh2 = nullptr;
+  if (w->inner == 128)
+    kvh2 = reinterpret_cast<const char*>(kv) + r256((size_t)L * w->inner * 4) + r256((size_t)w->inner * round4(L) * 4);
+  return attention_body(w, P, ldp, M, m_dev, nullptr, nullptr, 1, kv, kvh2, L, out, ldo, workspace, nullptr, stream);
+}
+
+// ---- all batch items in one chain of launches (the batched captured plan; model/resunet.py:237-273 loops over the items) ----------
+// kv of B images with L tokens each: the fp16 hi/lo K / V^T the attention kernel reads.
+extern "C" size_t imf_attention_kv_batched_bytes(int32_t L, int32_t B) { return r256(imf_flash_kv_h2_bytes(L, B)); }
+extern "C" size_t imf_attention_kv_batched_workspace_bytes(int32_t L, int32_t dim, int32_t inner, int32_t B) {
+  return r256((size_t)B * L * dim * 4) + r256((size_t)B * L * 2 * inner * 4);          // LN(tokens), [K | V] fp32
+}
+// tokens [B*L, dim] row-major (image b = rows [b*L, (b+1)*L)) -> kv = fp16 hi/lo {K, V^T} per image, with
+// [K | V] = LN_c(tokens) . Wkv^T as ONE GEMM over all images.  inner must be 128 (the IMFNet head).
+extern "C" int imf_attention_kv_batched(const imf_attn_weights_t* w, const float* tokens, int32_t L, int32_t B, void* kv, void* workspace,
+                                        size_t workspace_bytes, int32_t* err, cudaStream_t stream) {
+  IMF_CHECK_ARG(w != nullptr && L >= 1 && B >= 1 && B <= 256 && w->dim % 32 == 0 && w->dim <= 1024 && w->inner == 128);
+  IMF_CHECK_ARG(tokens != nullptr && kv != nullptr && workspace != nullptr);
+  IMF_CHECK_ARG(workspace_bytes >= imf_attention_kv_batched_workspace_bytes(L, w->dim, w->inner, B));
+  const int n = B * L, dim = w->dim, inner = w->inner;
+  float* cn = reinterpret_cast<float*>(workspace);
+  float* KV = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + r256((size_t)n * dim * 4));
+  k_layernorm_rows<<<(n + 7) / 8, 256, 0, stream>>>(tokens, dim, n, dim, w->ln_c_w, w->ln_c_b, 1e-5f, cn, dim, nullptr);
+  IMF_CHECK_LAUNCH();
   int rc;
-  k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(P, ldp, M, latent, w->ln_q_w, w->ln_q_b, 1e-5f, xn, latent, m_dev);
-  IMF_CHECK_LAUNCH();
-  // q = LN(P) . Wq^T
-  if ((rc = imf_tc_gemm_m(xn, latent, w->wq, latent, q, inner, M, m_dev, inner, latent, inner == 128 ? sm_scale : 1.f, nullptr, nullptr, 0, 0,
-                          gws, gws_bytes, nullptr, stream))) return rc;
-  if (inner == 128) {
-    // fused attention: q (scaled) -> fp16 hi/lo -> one tcgen05 kernel for q k^T, softmax and .v (flash_fusion.cu)
-    char* ws2 = reinterpret_cast<char*>(gws) + r256(gws_bytes);
-    void* qh2 = ws2;
-    void* fws = ws2 + r256((size_t)M * inner * 4);
-    const void* kvh2 = reinterpret_cast<const char*>(kv) + r256((size_t)L * inner * 4) + r256((size_t)inner * Lp * 4);
-    if ((rc = imf_h2_pack_n(q, inner, M, m_dev, inner, 64, qh2, 2 * inner, nullptr, stream))) return rc;
-    if ((rc = imf_flash_attention(qh2, M, m_dev, kvh2, L, o, inner, fws, imf_flash_workspace_bytes(M, L), nullptr, stream))) return rc;
-  } else {
-  // S = (q . K^T) * scale
-  if ((rc = imf_tc_gemm_m(q, inner, Kmat, inner, S, Lp, M, m_dev, L, inner, sm_scale, nullptr, nullptr, 0, 0, nullptr, 0, nullptr, stream))) return rc;
-  k_softmax_rows<<<M, 256, 0, stream>>>(S, Lp, M, L, m_dev);
-  IMF_CHECK_LAUNCH();
-  // o = A . V   (as A . (V^T)^T, split over the L tokens)
-  if ((rc = imf_tc_gemm_m(S, Lp, Vt, Lp, o, inner, M, m_dev, inner, L, 1.f, nullptr, nullptr, 0, 0, gws, gws_bytes, nullptr, stream))) return rc;
-  }
-  // x1 = o . Wo^T + bo + P
-  if ((rc = imf_tc_gemm_m(o, inner, w->wo, inner, x1, latent, M, m_dev, latent, inner, 1.f, w->bo, P, ldp, 0, gws, gws_bytes, nullptr, stream))) return rc;
-  k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(x1, latent, M, latent, w->ln_f_w, w->ln_f_b, 1e-5f, xn, latent, m_dev);
-  IMF_CHECK_LAUNCH();
-  // hid = geglu(LN(x1) . W1^T + b1)   [M, 4*latent]
-  if ((rc = imf_tc_gemm_m(xn, latent, w->w1, latent, hid, 4 * latent, M, m_dev, 4 * latent, latent, 1.f, w->b1, nullptr, 0, 1, nullptr, 0, nullptr, stream))) return rc;
-  // out = hid . W2^T + b2 + x1
-  if ((rc = imf_tc_gemm_m(hid, 4 * latent, w->w2, 4 * latent, out, ldo, M, m_dev, latent, 4 * latent, 1.f, w->b2, x1, latent, 0, gws, gws_bytes, nullptr, stream))) return rc;
-  return IMF_OK;
+  if ((rc = imf_tc_gemm(cn, dim, w->wkv, dim, KV, 2 * inner, n, 2 * inner, dim, 1.f, nullptr, nullptr, 0, 0, nullptr, 0, err, stream))) return rc;
+  return imf_flash_pack_kv(KV, 2 * inner, KV + inner, 2 * inner, 0, L, B, kv, stream);
+}
+
+extern "C" size_t imf_attention_batched_workspace_bytes(int32_t M, int32_t L, int32_t latent, int32_t inner, int32_t B) {
+  return r256((size_t)M * latent * 4) + r256((size_t)M * inner * 4) + r256((size_t)M * inner * 4) + r256((size_t)M * latent * 4) +
+         r256((size_t)M * latent * 4 * 4) + r256(imf_tc_gemm_workspace_bytes(M, latent, 0)) + r256((size_t)M * inner * 4) +
+         r256(imf_flash_workspace_bytes(M, L, B));
+}
+// out[row] for the rows [seg[b], seg[b] + cnt[b]) of every item b < B of P [M, latent] (M = capacity; *m_dev = rows in use = the end of
+// the last item): one LayerNorm / projection / feed-forward chain over all rows + one attention launch over all items.
+// err (optional device int): in-kernel watchdog codes and the fp16-range flag of the query pack (bit 16).
+extern "C" int imf_attention_fusion_fwd_batched(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const int32_t* m_dev,
+                                                const int32_t* seg_dev, const int32_t* cnt_dev, int32_t B, const void* kv, int32_t L,
+                                                float* out, int32_t ldo, void* workspace, size_t workspace_bytes, int32_t* err,
+                                                cudaStream_t stream) {
+  IMF_CHECK_ARG(w != nullptr && M >= 0 && L >= 1 && B >= 1 && B <= 256);
+  IMF_CHECK_ARG(w->latent % 32 == 0 && w->latent <= 1024 && w->inner == 128);
+  if (M == 0) return IMF_OK;
+  IMF_CHECK_ARG(P != nullptr && kv != nullptr && out != nullptr && workspace != nullptr && ldp >= w->latent && ldo >= w->latent);
+  IMF_CHECK_ARG(seg_dev != nullptr && cnt_dev != nullptr);
+  IMF_CHECK_ARG(workspace_bytes >= imf_attention_batched_workspace_bytes(M, L, w->latent, w->inner, B));
+  return attention_body(w, P, ldp, M, m_dev, seg_dev, cnt_dev, B, nullptr, kv, L, out, ldo, workspace, err, stream);
 }
 
 // Plain dense helper for the 1x1 MinkowskiConvolution module path (kernel [Cin,Cout], optional bias [Cout]).

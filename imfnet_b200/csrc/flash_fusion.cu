@@ -1,18 +1,29 @@
-// imfnet_b200 -- attention of the fusion module as ONE tcgen05 kernel: S = q k^T, softmax, o = softmax(S) v
+// imfnet_b200 -- attention of the fusion module as ONE persistent tcgen05 kernel for ALL batch items:
+//   S = q k^T, softmax, o = softmax(S) v
 //   /root/reference/model/attention_fusion.py:84-93 (einsum 'b i d, b j d -> b i j', softmax(dim=-1), einsum 'b i j, b j d -> b i d'),
-// one cross head of 128 channels, M point tokens (queries) against L image tokens (keys / values).
+// one cross head of 128 channels; per batch item b its M_b point tokens (queries, rows [seg[b], seg[b] + cnt[b]) of the stride-8
+// level, model/resunet.py:240-271) against the L image tokens of image b (keys / values).
 //
-// Operands are fp16 hi/lo pairs ("h2", see sparse_conv_h2.cu): q, K and V^T are pre-split once, P = exp(S - m) is split on the fly;
-// every product is accumulated as hi.hi + hi.lo + lo.hi with two tcgen05.mma (kind::f16) per K step by concatenating [hi ; lo]
-// of the B operand along N, exactly as the sparse convolution does.  All operand tiles are dense, so they are fetched with tiled
-// TMA loads (cp.async.bulk.tensor.2d, 128-byte swizzle) -- the [M, L] score matrix never exists in memory.
+// Operands are fp16 hi/lo pairs ("h2", see h2_format.cu): q, K and V^T are pre-split once, P = exp2(S - m) is split on the fly; every
+// product is accumulated as hi.hi + hi.lo + lo.hi with two tcgen05.mma (kind::f16) per K step by concatenating [hi ; lo] of the B
+// operand along N, exactly as the sparse convolution does.  All operand tiles are dense, so they are fetched with tiled TMA loads
+// (cp.async.bulk.tensor.2d, 128-byte swizzle) -- the [M, L] score matrix never exists in memory.
 //
-// CTA = one 128-query tile x one slice of the L tokens (flash-decoding style split, so 9 query tiles still fill the GPU):
-//   warp 0   TMA producer (Q once, then K / V blocks of 64 tokens into a 2-stage ring)
-//   warp 1   MMA issuer + TMEM owner: S (128 x 64, two halves) and O (128 x 128, two halves) live in TMEM
-//   warps 2-5 softmax: one query row per thread; pass 1 finds the row maximum of the slice (S only), pass 2 recomputes S, writes
-//            P = exp(S - m) (hi/lo) into shared memory for the P.V MMAs and sums the row -- no rescaling of O is ever needed.
-// The slices are merged by k_flash_combine (log-sum-exp weights), which also produces the fp32 [M, 128] output.
+// Work decomposition ("stream-K"): the (query tile, 64-token block) pairs of all items form one flat axis, tile-major; every CTA of
+// the persistent grid takes one contiguous range of `per` blocks, whatever tiles it crosses.  A (CTA, tile) intersection is a PIECE:
+// its un-normalised output, row maxima and row sums go to slot `tile + cta` of the workspace and k_flash_combine merges the pieces of
+// a tile (log-sum-exp weights).  Every CTA therefore does the same number of blocks (no wave quantisation, no per-item launches),
+// and all sizes are read on the device (seg / cnt), which keeps the launch capturable.
+//
+// CTA = 10 warps:
+//   warp 0    TMA producer: Q of the piece, then the K (pass 1: its hi halves only) / K + V blocks into a 2-stage ring
+//   warp 1    MMA issuer + TMEM owner: S double-buffered (2 x 128 columns), O (256 columns)
+//   warps 2-9 softmax, two warps per TMEM lane quadrant (32 of a block's 64 tokens each): pass 1 finds the row maximum of the piece
+//             from the CHEAP product q_hi . k_hi^T (any m close to the maximum serves: it only has to keep exp2(S - m) in range, and
+//             the pieces are merged with exact weights exp2(m_piece - m)); pass 2 recomputes S with all three products, writes
+//             P = exp2(S - m) (hi/lo) to shared memory for the P.V MMAs and sums the row -- O is never rescaled.
+//             While the softmax warps work on block j the tensor pipe already computes S of block j + 1 (second S buffer).
+// The queries arrive scaled by log2(e) / sqrt(d) (dense.cu), so the exponentials are bare ex2.approx.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -22,7 +33,7 @@
 namespace {
 
 constexpr int kD = 128;                 // head dimension
-constexpr int kTQ = 128;                // queries per CTA
+constexpr int kTQ = 128;                // queries per tile
 constexpr int kTB = 64;                 // tokens per block
 constexpr int kQImg = kTQ * 128;        // 16 KB: 128 rows x 64 halves
 constexpr int kKImg = kTB * 128;        //  8 KB:  64 rows x 64 halves
@@ -33,7 +44,10 @@ constexpr int kVBytes = 2 * kVImg;      // Vhi Vlo
 constexpr int kStage = kKBytes + kVBytes;
 constexpr int kPBytes = 2 * kQImg;      // Phi Plo (128 rows x 64 tokens)
 constexpr int kSmem = kQBytes + 2 * kStage + kPBytes;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kSoftWarps = 8;
+constexpr int kMaxPieces = 16;          // pieces a CTA may hold (the host sizes the grid so that this suffices)
+constexpr int kMaxItems = 256;
 
 __host__ __device__ constexpr uint32_t ff_idesc(int M, int N) {
   return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -53,226 +67,362 @@ __device__ __forceinline__ void ff_tma_load(uint32_t dst, const CUtensorMap* map
                "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(col), "r"(row)
                : "memory");
 }
+__device__ __forceinline__ float ff_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void ff_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 struct __align__(16) FHalf8 { __half2 a, b, c, d; };
 
-// K [L, 128] fp32 -> h2 [Lpad, 256 halves] (chunk width 64), V^T [128, ldv] fp32 -> h2 [128, 2*Lpad] over the token axis; padding = 0
-__global__ void __launch_bounds__(256) k_flash_pack_kv(const float* __restrict__ K, const float* __restrict__ Vt, int ldv, int L, int Lpad,
-                                                       __half* __restrict__ Kh, __half* __restrict__ Vh) {
+struct FFPiece {
+  int item;        // batch item
+  int row0;        // first query row of the tile (global row of the level matrix)
+  int row_end;     // end of the item's rows
+  int blk0;        // first 64-token block of the piece
+  int nblk;        // blocks of the piece
+  int slot;        // workspace slot of its partial result
+  int pad[2];
+};
+
+// K [B*L, ldk] fp32 (columns 0..127 of row b*L + t) -> h2 [B*Lpad, 256 halves] (chunk width 64); V [B*L, ldv] -> V^T as h2 over the token
+// axis [B*128, 2*Lpad halves]; padding tokens = 0.  v_transposed != 0: V is given as V^T [128, ldv] (single item, the old kv layout).
+__global__ void __launch_bounds__(256) k_flash_pack_kv(const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
+                                                       int v_transposed, int L, int Lpad, int B, __half* __restrict__ Kh,
+                                                       __half* __restrict__ Vh) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long nk = (long long)Lpad * kD;
+  const long long nk = (long long)B * Lpad * kD;
   if (idx < nk) {
-    const int t = (int)(idx / kD), c = (int)(idx % kD);
-    const float v = t < L ? K[(size_t)t * kD + c] : 0.f;
+    const int c = (int)(idx % kD);
+    const long long bt = idx / kD;
+    const int t = (int)(bt % Lpad), b = (int)(bt / Lpad);
+    const float v = t < L ? K[((size_t)b * L + t) * ldk + c] : 0.f;
     const __half h = __float2half_rn(v);
-    __half* p = Kh + (size_t)t * (2 * kD) + (c >> 6) * 128 + (c & 63);
+    __half* p = Kh + (size_t)bt * (2 * kD) + (c >> 6) * 128 + (c & 63);
     p[0] = h;
     p[64] = __float2half_rn(v - __half2float(h));
   } else if (idx < 2 * nk) {
     const long long j = idx - nk;
-    const int d = (int)(j / Lpad), t = (int)(j % Lpad);
-    const float v = t < L ? Vt[(size_t)d * ldv + t] : 0.f;
+    const int t = (int)(j % Lpad);
+    const long long bd = j / Lpad;
+    const int d = (int)(bd % kD), b = (int)(bd / kD);
+    float v = 0.f;
+    if (t < L) v = v_transposed ? V[(size_t)d * ldv + t] : V[((size_t)b * L + t) * ldv + d];
     const __half h = __float2half_rn(v);
-    __half* p = Vh + (size_t)d * (2 * Lpad) + (t >> 6) * 128 + (t & 63);
+    __half* p = Vh + (size_t)bd * (2 * Lpad) + (t >> 6) * 128 + (t & 63);
     p[0] = h;
     p[64] = __float2half_rn(v - __half2float(h));
   }
 }
 
+// rows of item b that lie inside the matrix (an item whose range runs past M_max -- a plan whose token capacity was exceeded; the
+// host then discards the result -- is clipped, so nothing is ever read or written outside the M_max rows);
+// cnt == nullptr: one item with *m_ptr (or M_max) rows starting at row 0
+__device__ __forceinline__ int ff_item_rows(const int* seg, const int* cnt, const int* m_ptr, int M_max, int b) {
+  int v, s0 = 0;
+  if (cnt) { v = cnt[b]; s0 = seg[b]; }
+  else v = m_ptr ? *m_ptr : M_max;
+  if (s0 < 0 || s0 >= M_max) return 0;
+  if (v > M_max - s0) v = M_max - s0;
+  return v < 0 ? 0 : v;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-               const int* __restrict__ m_ptr, int M_max, int L, int blocks_per_split, float* __restrict__ Opart, float* __restrict__ ml,
-               int* err) {
+               const int* __restrict__ seg, const int* __restrict__ cnt, const int* __restrict__ m_ptr, int B, int M_max, int L, int Lpad,
+               float* __restrict__ Opart, float* __restrict__ ml, int* err) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* q_s = smem;
   unsigned char* ring = smem + kQBytes;
   unsigned char* p_s = ring + 2 * kStage;
-  __shared__ __align__(8) uint64_t q_full, full[2], empty[2], s_ready, s_free, p_ready, p_free, o_done;
+  __shared__ __align__(8) uint64_t q_full, full[2], empty[2], s_ready[2], s_free[2], p_ready, p_free, o_done, o_free;
   __shared__ uint32_t tmem_base_s;
+  __shared__ FFPiece piece_s[kMaxPieces];
+  __shared__ int npiece_s;
 
-  int M = M_max;
-  if (m_ptr) { const int v = *m_ptr; M = v < M_max ? v : M_max; }
-  const int m0 = blockIdx.x * kTQ;
-  if (m0 >= M) return;
-  const int split = blockIdx.y;
-  const int nblocks_all = (L + kTB - 1) / kTB;
-  const int b_begin = min(nblocks_all, split * blocks_per_split);
-  const int nb = min(nblocks_all, b_begin + blocks_per_split) - b_begin;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int nb = (L + kTB - 1) / kTB;                 // blocks per tile (every image of the batch has L tokens)
 
   if (tid == 0) {
+    // ---- this CTA's pieces: flat blocks [c * per, (c + 1) * per) of the tile-major (tile, block) axis ----
+    long long T = 0;
+    for (int b = 0; b < B; ++b) T += (ff_item_rows(seg, cnt, m_ptr, M_max, b) + kTQ - 1) / kTQ;
+    const long long total = T * nb;
+    const long long per = (total + gridDim.x - 1) / gridDim.x;
+    long long f0 = per * blockIdx.x;
+    const long long f1 = f0 + per < total ? f0 + per : total;
+    int np = 0;
+    if (per > 0 && f0 < f1) {
+      long long tile = f0 / nb;
+      int b = 0;
+      long long tb = 0;                                // first tile of item b
+      for (;;) {                                       // the item of `tile`
+        const int tiles_b = (ff_item_rows(seg, cnt, m_ptr, M_max, b) + kTQ - 1) / kTQ;
+        if (tile < tb + tiles_b) break;
+        tb += tiles_b;
+        ++b;
+      }
+      while (f0 < f1 && np < kMaxPieces) {
+        const int rows_b = ff_item_rows(seg, cnt, m_ptr, M_max, b);
+        const int s0 = seg ? seg[b] : 0;
+        const long long tend = (tile + 1) * nb;
+        const long long pe = tend < f1 ? tend : f1;
+        FFPiece& p = piece_s[np++];
+        p.item = b;
+        p.row0 = s0 + (int)(tile - tb) * kTQ;
+        p.row_end = s0 + rows_b;
+        p.blk0 = (int)(f0 - tile * nb);
+        p.nblk = (int)(pe - f0);
+        p.slot = (int)tile + (int)blockIdx.x;
+        f0 = pe;
+        if (f0 == tend) {
+          ++tile;
+          while (b < B && tile >= tb + (ff_item_rows(seg, cnt, m_ptr, M_max, b) + kTQ - 1) / kTQ) {
+            tb += (ff_item_rows(seg, cnt, m_ptr, M_max, b) + kTQ - 1) / kTQ;
+            ++b;
+          }
+        }
+      }
+      if (f0 < f1 && err) atomicExch(err, 9);          // more pieces than kMaxPieces: the host sized the grid wrongly
+    }
+    npiece_s = np;
     tc::mbar_init(&q_full, 1);
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-    tc::mbar_init(&s_ready, 1);
-    tc::mbar_init(&s_free, 128);
-    tc::mbar_init(&p_ready, 128);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 1);
+      tc::mbar_init(&s_ready[s], 1);
+      tc::mbar_init(&s_free[s], kSoftWarps);
+    }
+    tc::mbar_init(&p_ready, kSoftWarps);
     tc::mbar_init(&p_free, 1);
     tc::mbar_init(&o_done, 1);
+    tc::mbar_init(&o_free, kSoftWarps);
     tc::fence_barrier_init();
     tma::prefetch_map(&tmQ);
     tma::prefetch_map(&tmK);
     tma::prefetch_map(&tmV);
   }
+  __syncthreads();
+  const int npiece = npiece_s;
+  if (npiece == 0) return;
   if (warp == 1) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
-  const uint32_t tmem_s = tmem_base_s;            // S: columns [0,128)  (S1 | S2)
-  const uint32_t tmem_o = tmem_base_s + 128u;     // O: columns [128,384) (O1 | O2)
+  const uint32_t tmem_s = tmem_base_s;            // S buffers: columns [0,128) and [128,256)   (each S1 | S2)
+  const uint32_t tmem_o = tmem_base_s + 256u;     // O: columns [256,512) (O1 | O2)
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0 && nb > 0) {      // (nothing may be in flight when the CTA exits: an empty slice loads nothing)
-      tc::mbar_arrive_expect_tx(&q_full, kQBytes);
-      for (int i = 0; i < 4; ++i) ff_tma_load(tc::smem_u32(q_s + i * kQImg), &tmQ, tc::smem_u32(&q_full), i * 64, m0);
-      int it = 0;
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int b = 0; b < nb; ++b, ++it) {
-          const int st = it & 1;
-          tc::mbar_wait(&empty[st], (((uint32_t)(it >> 1)) & 1u) ^ 1u, err, 1);
-          unsigned char* kd = ring + st * kStage;
-          const int t0 = (b_begin + b) * kTB;
-          tc::mbar_arrive_expect_tx(&full[st], pass == 0 ? kKBytes : kStage);
-          for (int i = 0; i < 4; ++i) ff_tma_load(tc::smem_u32(kd + i * kKImg), &tmK, tc::smem_u32(&full[st]), i * 64, t0);
-          if (pass == 1) {
-            ff_tma_load(tc::smem_u32(kd + kKBytes), &tmV, tc::smem_u32(&full[st]), (b_begin + b) * 128, 0);
-            ff_tma_load(tc::smem_u32(kd + kKBytes + kVImg), &tmV, tc::smem_u32(&full[st]), (b_begin + b) * 128 + 64, 0);
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int pc = 0; pc < npiece; ++pc) {
+        const FFPiece p = piece_s[pc];
+        if (pc > 0) tc::mbar_wait(&o_done, (uint32_t)(pc - 1) & 1u, err, 1);      // the previous piece's MMAs are done with Q
+        tc::mbar_arrive_expect_tx(&q_full, kQBytes);
+        for (int i = 0; i < 4; ++i) ff_tma_load(tc::smem_u32(q_s + i * kQImg), &tmQ, tc::smem_u32(&q_full), i * 64, p.row0);
+        const int krow = p.item * Lpad, vrow = p.item * kD;
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int j = 0; j < p.nblk; ++j, ++it) {
+            const int st = it & 1;
+            tc::mbar_wait(&empty[st], ((it >> 1) & 1u) ^ 1u, err, 2);
+            unsigned char* kd = ring + st * kStage;
+            const int blk = p.blk0 + j;
+            const int t0 = krow + blk * kTB;
+            if (pass == 0) {        // q_hi . k_hi^T only: the hi images of both channel chunks
+              tc::mbar_arrive_expect_tx(&full[st], 2 * kKImg);
+              ff_tma_load(tc::smem_u32(kd), &tmK, tc::smem_u32(&full[st]), 0, t0);
+              ff_tma_load(tc::smem_u32(kd + 2 * kKImg), &tmK, tc::smem_u32(&full[st]), 128, t0);
+            } else {
+              tc::mbar_arrive_expect_tx(&full[st], kStage);
+              for (int i = 0; i < 4; ++i) ff_tma_load(tc::smem_u32(kd + i * kKImg), &tmK, tc::smem_u32(&full[st]), i * 64, t0);
+              ff_tma_load(tc::smem_u32(kd + kKBytes), &tmV, tc::smem_u32(&full[st]), blk * 128, vrow);
+              ff_tma_load(tc::smem_u32(kd + kKBytes + kVImg), &tmV, tc::smem_u32(&full[st]), blk * 128 + 64, vrow);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
+    // Warp-uniform issue (operand addresses shuffled from lane 0, MMAs under elect.sync): the compiler then keeps the descriptors in
+    // uniform registers and emits bare UTCHMMA instead of an ELECT / R2UR / branch loop around every instruction.
     constexpr uint32_t id_s2 = ff_idesc(kTQ, 2 * kTB), id_s1 = ff_idesc(kTQ, kTB);       // N = 128 / 64
     constexpr uint32_t id_o2 = ff_idesc(kTQ, 2 * kD), id_o1 = ff_idesc(kTQ, kD);          // N = 256 / 128
-    if (nb > 0) tc::mbar_wait(&q_full, 0u, err, 2);
-    int it = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int b = 0; b < nb; ++b, ++it) {
-        const int st = it & 1;
-        tc::mbar_wait(&full[st], ((uint32_t)(it >> 1)) & 1u, err, 3);
-        tc::mbar_wait(&s_free, ((uint32_t)it & 1u) ^ 1u, err, 4);            // softmax warps have read the previous S
-        tc::tc_fence_after_sync();
-        // issued from `if (lane == 0)` every tcgen05.mma is wrapped by ptxas in an ELECT / R2UR / BRA.U.ANY loop (the same finding as
-        // in sparse_conv_g4.cu); warp-uniform operands + elect.sync give bare UTCHMMAs
-        const uint32_t q0 = __shfl_sync(0xffffffffu, tc::smem_u32(q_s), 0), k0 = __shfl_sync(0xffffffffu, tc::smem_u32(ring + st * kStage), 0);
-        const uint32_t tmem_s_u = __shfl_sync(0xffffffffu, tmem_s, 0);
-        if (tc::elect_one()) {
-#define tmem_s tmem_s_u
+    const uint32_t q0 = __shfl_sync(0xffffffffu, tc::smem_u32(q_s), 0);
+    const uint32_t r0 = __shfl_sync(0xffffffffu, tc::smem_u32(ring), 0);
+    const uint32_t p0 = __shfl_sync(0xffffffffu, tc::smem_u32(p_s), 0);
+    const uint32_t ts = __shfl_sync(0xffffffffu, tmem_s, 0), to = __shfl_sync(0xffffffffu, tmem_o, 0);
+    uint32_t it = 0;       // ring uses consumed
+    uint32_t sit = 0;      // S buffers issued
+    uint32_t pit = 0;      // P blocks consumed
+    auto issue_s = [&](uint32_t st, bool full_product) {
+      const uint32_t sb = sit & 1u;
+      tc::mbar_wait(&s_free[sb], ((sit >> 1) & 1u) ^ 1u, err, 4);            // softmax warps have read this S buffer's previous content
+      tc::tc_fence_after_sync();
+      const uint32_t k0 = r0 + st * kStage;
+      const uint32_t d = ts + sb * 128u;
+      if (tc::elect_one()) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint32_t qhi = q0 + (2 * c) * kQImg, qlo = qhi + kQImg, kb = k0 + (2 * c) * kKImg;     // [Khi_c ; Klo_c] = 128 rows
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t qhi = q0 + (2 * c) * kQImg, qlo = qhi + kQImg, kb = k0 + (2 * c) * kKImg;     // [Khi_c ; Klo_c] = 128 rows
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t o = ks * 32;
-              ff_mma(tmem_s, tc::smem_desc_sw128(qhi + o), tc::smem_desc_sw128(kb + o), id_s2, (c | ks) ? 1u : 0u);
-              ff_mma(tmem_s, tc::smem_desc_sw128(qlo + o), tc::smem_desc_sw128(kb + o), id_s1, 1u);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t o = ks * 32;
+            if (full_product) {
+              ff_mma(d, tc::smem_desc_sw128(qhi + o), tc::smem_desc_sw128(kb + o), id_s2, (c | ks) ? 1u : 0u);
+              ff_mma(d, tc::smem_desc_sw128(qlo + o), tc::smem_desc_sw128(kb + o), id_s1, 1u);
+            } else {
+              ff_mma(d, tc::smem_desc_sw128(qhi + o), tc::smem_desc_sw128(kb + o), id_s1, (c | ks) ? 1u : 0u);
             }
           }
-          tc::mma_commit(&s_ready);
-          if (pass == 0) tc::mma_commit(&empty[st]);
         }
-#undef tmem_s
+        tc::mma_commit(&s_ready[sb]);
+      }
+      __syncwarp();
+      ++sit;
+    };
+    for (int pc = 0; pc < npiece; ++pc) {
+      const int nblk = piece_s[pc].nblk;
+      tc::mbar_wait(&q_full, (uint32_t)pc & 1u, err, 3);
+      // ---- pass 1: approximate scores (hi . hi) for the row maxima ----
+      for (int j = 0; j < nblk; ++j, ++it) {
+        const uint32_t st = it & 1u;
+        tc::mbar_wait(&full[st], (it >> 1) & 1u, err, 5);
+        issue_s(st, false);
+        if (tc::elect_one()) tc::mma_commit(&empty[st]);
         __syncwarp();
-        if (pass == 1) {
-          tc::mbar_wait(&p_ready, (uint32_t)b & 1u, err, 5);                  // P of this block is in shared memory
-          tc::tc_fence_after_sync();
-          const uint32_t p0 = __shfl_sync(0xffffffffu, tc::smem_u32(p_s), 0);
-          const uint32_t v0 = __shfl_sync(0xffffffffu, tc::smem_u32(ring + st * kStage + kKBytes), 0);       // [Vhi ; Vlo] = 256 rows
-          const uint32_t tmem_o_u = __shfl_sync(0xffffffffu, tmem_o, 0);
-          if (tc::elect_one()) {
-#define tmem_o tmem_o_u
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t o = ks * 32;
-              ff_mma(tmem_o, tc::smem_desc_sw128(p0 + o), tc::smem_desc_sw128(v0 + o), id_o2, (b | ks) ? 1u : 0u);
-              ff_mma(tmem_o, tc::smem_desc_sw128(p0 + kQImg + o), tc::smem_desc_sw128(v0 + o), id_o1, 1u);
-            }
-            tc::mma_commit(&empty[st]);
-            tc::mma_commit(&p_free);
-          }
-#undef tmem_o
-          __syncwarp();
+      }
+      // ---- pass 2: S(j + 1) is issued before P(j) . V(j), so the tensor pipe works while the softmax warps handle block j ----
+      tc::mbar_wait(&o_free, ((uint32_t)pc & 1u) ^ 1u, err, 6);                // the previous piece's O has been drained
+      tc::mbar_wait(&full[it & 1u], (it >> 1) & 1u, err, 5);
+      issue_s(it & 1u, true);
+      for (int j = 0; j < nblk; ++j, ++it) {
+        const uint32_t st = it & 1u;
+        if (j + 1 < nblk) {
+          const uint32_t nit = it + 1;
+          tc::mbar_wait(&full[nit & 1u], (nit >> 1) & 1u, err, 5);
+          issue_s(nit & 1u, true);
         }
+        tc::mbar_wait(&p_ready, pit & 1u, err, 7);                              // P of block j is in shared memory
+        tc::tc_fence_after_sync();
+        const uint32_t v0 = r0 + st * kStage + kKBytes;                        // [Vhi ; Vlo] = 256 rows
+        const uint32_t jj = (uint32_t)j;
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t o = ks * 32;
+            ff_mma(to, tc::smem_desc_sw128(p0 + o), tc::smem_desc_sw128(v0 + o), id_o2, (jj | (uint32_t)ks) ? 1u : 0u);
+            ff_mma(to, tc::smem_desc_sw128(p0 + kQImg + o), tc::smem_desc_sw128(v0 + o), id_o1, 1u);
+          }
+          tc::mma_commit(&empty[st]);
+          tc::mma_commit(&p_free);
+          if (j == nblk - 1) tc::mma_commit(&o_done);
+        }
+        __syncwarp();
+        ++pit;
       }
     }
-    if (tc::elect_one()) tc::mma_commit(&o_done);      // same thread as the MMAs above (elect.sync is deterministic per mask)
-    __syncwarp();
   } else {
-    // =========================== softmax (4 warps, one query row per thread) ===========================
-    const int q = warp & 3;                         // TMEM lane quadrant of this warp
+    // =========================== softmax (8 warps: TMEM lane quadrant = warp % 4, token half = (warp - 2) / 4) ===========================
+    const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;                 // 0: tokens [0,32) of a block, 1: tokens [32,64)
     const int r = q * 32 + lane;                    // row inside the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float row_max = -INFINITY, row_sum = 0.f;
-    int it = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int b = 0; b < nb; ++b, ++it) {
-        tc::mbar_wait(&s_ready, (uint32_t)it & 1u, err, 6);
+    float* xch = reinterpret_cast<float*>(p_s);     // [2][128] exchange area between the two halves (P is idle when it is used)
+    uint32_t sct = 0, pct = 0;
+    for (int pc = 0; pc < npiece; ++pc) {
+      const FFPiece p = piece_s[pc];
+      // ---- pass 1: row maximum of the approximate scores ----
+      float row_max = -INFINITY;
+      for (int j = 0; j < p.nblk; ++j, ++sct) {
+        const uint32_t sb = sct & 1u;
+        tc::mbar_wait(&s_ready[sb], (sct >> 1) & 1u, err, 8);
         tc::tc_fence_after_sync();
-        const int t0 = (b_begin + b) * kTB;
-        if (pass == 1) tc::mbar_wait(&p_free, ((uint32_t)b & 1u) ^ 1u, err, 7);    // the previous block's P.V MMAs are done with p_s
-#pragma unroll 1
-        for (int cb = 0; cb < kTB; cb += 16) {
-          float s1[16], s2[16];
-          tc::tmem_ld16(tmem_s + lane_addr + (uint32_t)cb, s1);
-          tc::tmem_ld16(tmem_s + lane_addr + (uint32_t)(kTB + cb), s2);
-          if (pass == 0) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (t0 + cb + i < L) row_max = fmaxf(row_max, s1[i] + s2[i]);
-          } else {
-            __half2 hi[8], lo[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float p0 = (t0 + cb + 2 * i < L) ? expf(s1[2 * i] + s2[2 * i] - row_max) : 0.f;
-              float p1 = (t0 + cb + 2 * i + 1 < L) ? expf(s1[2 * i + 1] + s2[2 * i + 1] - row_max) : 0.f;
-              row_sum += p0 + p1;
-              const __half h0 = __float2half_rn(p0), h1 = __float2half_rn(p1);
-              hi[i] = __halves2half2(h0, h1);
-              lo[i] = __halves2half2(__float2half_rn(p0 - __half2float(h0)), __float2half_rn(p1 - __half2float(h1)));
-            }
-            const int ch = cb >> 3;                 // 16-byte chunk index of token cb inside the 64-token (128-byte) row
-            *reinterpret_cast<FHalf8*>(p_s + tc::sw128_offset(r, ch)) = FHalf8{hi[0], hi[1], hi[2], hi[3]};
-            *reinterpret_cast<FHalf8*>(p_s + tc::sw128_offset(r, ch + 1)) = FHalf8{hi[4], hi[5], hi[6], hi[7]};
-            *reinterpret_cast<FHalf8*>(p_s + kQImg + tc::sw128_offset(r, ch)) = FHalf8{lo[0], lo[1], lo[2], lo[3]};
-            *reinterpret_cast<FHalf8*>(p_s + kQImg + tc::sw128_offset(r, ch + 1)) = FHalf8{lo[4], lo[5], lo[6], lo[7]};
-          }
-        }
+        const int t0 = (p.blk0 + j) * kTB + hf * 32;
+        uint32_t a[32];
+        tc::tmem_ld16_issue(tmem_s + lane_addr + sb * 128u + (uint32_t)(hf * 32), a);
+        tc::tmem_ld16_issue(tmem_s + lane_addr + sb * 128u + (uint32_t)(hf * 32 + 16), a + 16);
+        tc::tmem_ld_wait();
         tc::tc_fence_before_sync();
-        tc::mbar_arrive(&s_free);                   // S may be overwritten by the next block's MMAs
-        if (pass == 1) {
-          tc::fence_proxy_async();
-          tc::mbar_arrive(&p_ready);
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&s_free[sb]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (t0 + i < L) row_max = fmaxf(row_max, __uint_as_float(a[i]));
+      }
+      xch[hf * 128 + r] = row_max;
+      ff_bar(1, kSoftWarps * 32);
+      row_max = fmaxf(xch[r], xch[128 + r]);
+      ff_bar(1, kSoftWarps * 32);                   // everybody has read the exchange area before P is written again
+      // ---- pass 2: exact scores, P = exp2(S - m), row sums ----
+      float row_sum = 0.f;
+      for (int j = 0; j < p.nblk; ++j, ++sct, ++pct) {
+        const uint32_t sb = sct & 1u;
+        tc::mbar_wait(&s_ready[sb], (sct >> 1) & 1u, err, 8);
+        tc::tc_fence_after_sync();
+        const int t0 = (p.blk0 + j) * kTB + hf * 32;
+        uint32_t a[32], b2[32];
+        const uint32_t base = tmem_s + lane_addr + sb * 128u + (uint32_t)(hf * 32);
+        tc::tmem_ld16_issue(base, a);
+        tc::tmem_ld16_issue(base + 16u, a + 16);
+        tc::tmem_ld16_issue(base + (uint32_t)kTB, b2);
+        tc::tmem_ld16_issue(base + (uint32_t)kTB + 16u, b2 + 16);
+        tc::tmem_ld_wait();
+        tc::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&s_free[sb]);
+        __half2 hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float s0 = __uint_as_float(a[2 * i]) + __uint_as_float(b2[2 * i]);
+          const float s1 = __uint_as_float(a[2 * i + 1]) + __uint_as_float(b2[2 * i + 1]);
+          const float p0v = (t0 + 2 * i < L) ? ff_exp2(s0 - row_max) : 0.f;
+          const float p1v = (t0 + 2 * i + 1 < L) ? ff_exp2(s1 - row_max) : 0.f;
+          row_sum += p0v + p1v;
+          hi[i] = __floats2half2_rn(p0v, p1v);
+          const float2 hf2 = __half22float2(hi[i]);
+          lo[i] = __floats2half2_rn(p0v - hf2.x, p1v - hf2.y);
         }
+        tc::mbar_wait(&p_free, (pct & 1u) ^ 1u, err, 9);                      // the previous block's P.V MMAs are done with p_s
+        const int ch = hf * 4;                       // 16-byte chunk index of this half's first token inside the 64-token (128-byte) row
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          *reinterpret_cast<FHalf8*>(p_s + tc::sw128_offset(r, ch + c4)) = FHalf8{hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]};
+          *reinterpret_cast<FHalf8*>(p_s + kQImg + tc::sw128_offset(r, ch + c4)) = FHalf8{lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]};
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&p_ready);
       }
-    }
-    // ---- partial result of this slice: O (un-normalised), row maximum and row sum ----
-    tc::mbar_wait(&o_done, 0u, err, 8);
-    tc::tc_fence_after_sync();
-    const int row = m0 + r;
-    float* op = Opart + ((size_t)split * M_max + row) * kD;
+      // ---- partial result of this piece: O (un-normalised), row maximum and row sum ----
+      tc::mbar_wait(&o_done, (uint32_t)pc & 1u, err, 10);
+      tc::tc_fence_after_sync();
+      xch[hf * 128 + r] = row_sum;                  // (all P.V MMAs are complete: P is idle)
+      float* op = Opart + ((size_t)p.slot * kTQ + r) * kD + hf * 64;
 #pragma unroll 1
-    for (int cb = 0; cb < kD; cb += 16) {          // tcgen05.ld is warp-collective: every lane loads, valid rows store
-      float a[16];
-      if (nb > 0) {
-        float a2[16];
-        tc::tmem_ld16(tmem_o + lane_addr + (uint32_t)cb, a);
-        tc::tmem_ld16(tmem_o + lane_addr + (uint32_t)(kD + cb), a2);
+      for (int cb = 0; cb < 64; cb += 16) {
+        uint32_t a[16], b2[16];
+        tc::tmem_ld16_issue(tmem_o + lane_addr + (uint32_t)(hf * 64 + cb), a);
+        tc::tmem_ld16_issue(tmem_o + lane_addr + (uint32_t)(kD + hf * 64 + cb), b2);
+        tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] += a2[i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a[i] = 0.f;
+        for (int i = 0; i < 4; ++i)
+          reinterpret_cast<float4*>(op + cb)[i] =
+              make_float4(__uint_as_float(a[4 * i]) + __uint_as_float(b2[4 * i]), __uint_as_float(a[4 * i + 1]) + __uint_as_float(b2[4 * i + 1]),
+                          __uint_as_float(a[4 * i + 2]) + __uint_as_float(b2[4 * i + 2]), __uint_as_float(a[4 * i + 3]) + __uint_as_float(b2[4 * i + 3]));
       }
-      if (row < M) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(op + cb)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+      tc::tc_fence_before_sync();
+      ff_bar(1, kSoftWarps * 32);
+      if (hf == 0) {
+        ml[((size_t)p.slot * kTQ + r) * 2] = row_max;
+        ml[((size_t)p.slot * kTQ + r) * 2 + 1] = xch[r] + xch[128 + r];
       }
-    }
-    if (row < M) {
-      ml[((size_t)split * M_max + row) * 2] = row_max;
-      ml[((size_t)split * M_max + row) * 2 + 1] = row_sum;
+      ff_bar(1, kSoftWarps * 32);                   // the exchange area is free again; O is drained
+      if (lane == 0) tc::mbar_arrive(&o_free);
     }
   }
   tc::tc_fence_before_sync();
@@ -280,81 +430,109 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 1) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
-// out[row, :] = sum_s w_s O_s / sum_s w_s l_s,  w_s = exp(m_s - max_s m_s); one thread per (row, 4 channels)
-__global__ void __launch_bounds__(256) k_flash_combine(const float* __restrict__ Opart, const float* __restrict__ ml, int nsplit,
-                                                       const int* __restrict__ m_ptr, int M_max, float* __restrict__ out, int ldo) {
-  int M = M_max;
-  if (m_ptr) { const int v = *m_ptr; M = v < M_max ? v : M_max; }
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= (long long)M * (kD / 4)) return;
-  const int row = (int)(idx / (kD / 4)), c = (int)(idx % (kD / 4)) * 4;
-  float mx = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) mx = fmaxf(mx, ml[((size_t)s * M_max + row) * 2]);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  float den = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const float m = ml[((size_t)s * M_max + row) * 2];
-    if (m == -INFINITY) continue;                  // empty slice
-    const float w = expf(m - mx);
-    den = fmaf(w, ml[((size_t)s * M_max + row) * 2 + 1], den);
-    const float4 o = *reinterpret_cast<const float4*>(Opart + ((size_t)s * M_max + row) * kD + c);
-    acc.x = fmaf(w, o.x, acc.x); acc.y = fmaf(w, o.y, acc.y); acc.z = fmaf(w, o.z, acc.z); acc.w = fmaf(w, o.w, acc.w);
+// out[row, :] = sum_p w_p O_p / sum_p w_p l_p,  w_p = exp2(m_p - max_p m_p), over the pieces p of the row's tile.
+// One CTA per tile of the flat axis; the piece <-> slot mapping is recomputed from the same quantities the attention kernel used.
+__global__ void __launch_bounds__(256) k_flash_combine(const float* __restrict__ Opart, const float* __restrict__ ml, const int* __restrict__ seg,
+                                                       const int* __restrict__ cnt, const int* __restrict__ m_ptr, int B, int M_max, int L,
+                                                       int grid_att, float* __restrict__ out, int ldo) {
+  const int nb = (L + kTB - 1) / kTB;
+  long long T = 0;
+  for (int b = 0; b < B; ++b) T += (ff_item_rows(seg, cnt, m_ptr, M_max, b) + kTQ - 1) / kTQ;
+  const long long tile = blockIdx.x;
+  if (tile >= T) return;
+  const long long total = T * nb;
+  const long long per = (total + grid_att - 1) / grid_att;
+  int b = 0;
+  long long tb = 0;
+  for (;;) {
+    const int tiles_b = (ff_item_rows(seg, cnt, m_ptr, M_max, b) + kTQ - 1) / kTQ;
+    if (tile < tb + tiles_b) break;
+    tb += tiles_b;
+    ++b;
   }
-  const float inv = 1.0f / den;
-  *reinterpret_cast<float4*>(out + (size_t)row * ldo + c) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  const int s0 = seg ? seg[b] : 0;
+  const int row0 = s0 + (int)(tile - tb) * kTQ, row_end = s0 + ff_item_rows(seg, cnt, m_ptr, M_max, b);
+  const int c_first = (int)((tile * nb) / per), c_last = (int)(((tile + 1) * nb - 1) / per);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int r = w; r < kTQ; r += 8) {
+    const int row = row0 + r;
+    if (row >= row_end) break;
+    float mx = -INFINITY;
+    for (int c = c_first; c <= c_last; ++c) mx = fmaxf(mx, ml[((size_t)((int)tile + c) * kTQ + r) * 2]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float den = 0.f;
+    for (int c = c_first; c <= c_last; ++c) {
+      const size_t slot = (size_t)((int)tile + c);
+      const float m = ml[(slot * kTQ + r) * 2];
+      if (m == -INFINITY) continue;                  // a piece whose tokens were all padding
+      const float wgt = ff_exp2(m - mx);
+      den = fmaf(wgt, ml[(slot * kTQ + r) * 2 + 1], den);
+      const float4 o = *reinterpret_cast<const float4*>(Opart + (slot * kTQ + r) * kD + lane * 4);
+      acc.x = fmaf(wgt, o.x, acc.x); acc.y = fmaf(wgt, o.y, acc.y); acc.z = fmaf(wgt, o.z, acc.z); acc.w = fmaf(wgt, o.w, acc.w);
+    }
+    const float inv = 1.0f / den;
+    *reinterpret_cast<float4*>(out + (size_t)row * ldo + lane * 4) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  }
 }
 
 inline int ff_lpad(int L) { return (L + kTB - 1) / kTB * kTB; }
-inline int ff_nsplit(int M_max, int L) {
-  const int tiles = (M_max + kTQ - 1) / kTQ, nblocks = (L + kTB - 1) / kTB;
-  int ns = (2 * imf_sm_count() + tiles - 1) / tiles;          // about two waves of CTAs when every tile is active
-  if (ns > nblocks) ns = nblocks;
-  if (ns > 32) ns = 32;
-  return ns < 1 ? 1 : ns;
+inline int ff_tiles_max(int M_max, int B) { return (M_max + kTQ - 1) / kTQ + B; }
+inline int ff_grid(int M_max, int L, int B) {
+  const long long nb = (L + kTB - 1) / kTB, tmax = ff_tiles_max(M_max, B);
+  long long g = imf_sm_count();
+  if (g > tmax * nb) g = tmax * nb;
+  // a CTA holds at most kMaxPieces pieces (it spans at most ceil(per / nb) + 1 tiles): keep per <= nb * (kMaxPieces - 2)
+  const long long gmin = (tmax + kMaxPieces - 3) / (kMaxPieces - 2);
+  if (g < gmin) g = gmin;
+  return (int)(g < 1 ? 1 : g);
 }
 
 }  // namespace
 
-// sizes of the h2 copies of K and V^T appended to a kv buffer, and of the flash workspace (partials of every slice)
-size_t imf_flash_kv_h2_bytes(int L) { return (size_t)2 * ff_lpad(L) * kD * 2 * sizeof(__half); }
-size_t imf_flash_workspace_bytes(int M_max, int L) {
-  return (size_t)ff_nsplit(M_max, L) * (size_t)(M_max > 0 ? M_max : 1) * (kD + 2) * sizeof(float);
+// sizes of the h2 copies of K and V^T of B images with L tokens each, and of the attention workspace (partials of every piece)
+size_t imf_flash_kv_h2_bytes(int L, int B) { return (size_t)B * 2 * ff_lpad(L) * kD * 2 * sizeof(__half); }
+size_t imf_flash_workspace_bytes(int M_max, int L, int B) {
+  const size_t slots = (size_t)ff_tiles_max(M_max, B) + (size_t)ff_grid(M_max, L, B) + 1;
+  return slots * kTQ * (kD + 2) * sizeof(float);
 }
 
-// K [L,128], V^T [128, ldv] (fp32) -> kvh2 = { Kh2 [Lpad, 256 halves], Vth2 [128, 2*Lpad halves] }
-int imf_flash_pack_kv(const float* K, const float* Vt, int ldv, int L, void* kvh2, cudaStream_t stream) {
+// K / V (fp32) -> kvh2 = { Kh2 [B*Lpad, 256 halves], Vth2 [B*128, 2*Lpad halves] }.
+// v_transposed == 0: K [B*L, ldk] and V [B*L, ldv] row-major (e.g. columns [0,128) and [128,256) of one [B*L, 256] matrix);
+// v_transposed != 0 (B == 1): K [L, ldk] and V^T [128, ldv].
+int imf_flash_pack_kv(const float* K, int ldk, const float* V, int ldv, int v_transposed, int L, int B, void* kvh2, cudaStream_t stream) {
   const int Lpad = ff_lpad(L);
   __half* Kh = reinterpret_cast<__half*>(kvh2);
-  __half* Vh = Kh + (size_t)Lpad * 2 * kD;
-  const long long total = 2LL * Lpad * kD;
-  k_flash_pack_kv<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(K, Vt, ldv, L, Lpad, Kh, Vh);
+  __half* Vh = Kh + (size_t)B * Lpad * 2 * kD;
+  const long long total = 2LL * B * Lpad * kD;
+  k_flash_pack_kv<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(K, ldk, V, ldv, v_transposed, L, Lpad, B, Kh, Vh);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }
 
-// o[M, 128] (fp32, row stride ldo) = softmax(q k^T) v; qh2 = h2 matrix of the (already scaled) queries [M_max, 256 halves]
-int imf_flash_attention(const void* qh2, int M_max, const int* m_dev, const void* kvh2, int L, float* o, int ldo, void* workspace,
-                        size_t workspace_bytes, int* err, cudaStream_t stream) {
-  IMF_CHECK_ARG(qh2 && kvh2 && o && workspace && M_max > 0 && L > 0 && workspace_bytes >= imf_flash_workspace_bytes(M_max, L));
+// o[row, 128] (fp32, row stride ldo) = softmax(q k_b^T) v_b for the rows [seg[b], seg[b] + cnt[b]) of every item b < B;
+// qh2 = h2 matrix of the queries [M_max, 256 halves], already scaled by log2(e) / sqrt(d).  seg / cnt == NULL: one item with
+// *m_dev (or M_max) rows starting at row 0.
+int imf_flash_attention(const void* qh2, int M_max, const int* seg_dev, const int* cnt_dev, const int* m_dev, int B, const void* kvh2, int L,
+                        float* o, int ldo, void* workspace, size_t workspace_bytes, int* err, cudaStream_t stream) {
+  IMF_CHECK_ARG(qh2 && kvh2 && o && workspace && M_max > 0 && L > 0 && B >= 1 && B <= kMaxItems);
+  IMF_CHECK_ARG((seg_dev == nullptr) == (cnt_dev == nullptr) && (cnt_dev != nullptr || B == 1));
+  IMF_CHECK_ARG(workspace_bytes >= imf_flash_workspace_bytes(M_max, L, B));
   const int Lpad = ff_lpad(L);
   const __half* Kh = reinterpret_cast<const __half*>(kvh2);
-  const __half* Vh = Kh + (size_t)Lpad * 2 * kD;
+  const __half* Vh = Kh + (size_t)B * Lpad * 2 * kD;
   CUtensorMap tmQ, tmK, tmV;
   int rc = tma::encode_2d_u16(&tmQ, qh2, (uint64_t)M_max, 2 * kD, 2 * kD, 64, kTQ);
-  if (!rc) rc = tma::encode_2d_u16(&tmK, Kh, (uint64_t)Lpad, 2 * kD, 2 * kD, 64, kTB);
-  if (!rc) rc = tma::encode_2d_u16(&tmV, Vh, (uint64_t)kD, (uint64_t)2 * Lpad, (uint64_t)2 * Lpad, 64, kD);
+  if (!rc) rc = tma::encode_2d_u16(&tmK, Kh, (uint64_t)B * Lpad, 2 * kD, 2 * kD, 64, kTB);
+  if (!rc) rc = tma::encode_2d_u16(&tmV, Vh, (uint64_t)B * kD, (uint64_t)2 * Lpad, (uint64_t)2 * Lpad, 64, kD);
   if (rc) { imf_set_error("cuTensorMapEncodeTiled (flash attention) failed: %d", rc); return IMF_ERR_CUDA; }
-  const int nsplit = ff_nsplit(M_max, L);
-  const int nblocks = (L + kTB - 1) / kTB;
-  const int bps = (nblocks + nsplit - 1) / nsplit;
+  const int grid = ff_grid(M_max, L, B);
+  const size_t slots = (size_t)ff_tiles_max(M_max, B) + (size_t)grid + 1;
   float* Opart = reinterpret_cast<float*>(workspace);
-  float* ml = Opart + (size_t)nsplit * M_max * kD;
+  float* ml = Opart + slots * kTQ * kD;
   IMF_CHECK_CUDA(imf_set_max_smem_once(reinterpret_cast<const void*>(&k_flash_fusion), kSmem + 1024));
-  dim3 grid((M_max + kTQ - 1) / kTQ, nsplit);
-  k_flash_fusion<<<grid, kThreads, kSmem + 1024, stream>>>(tmQ, tmK, tmV, m_dev, M_max, L, bps, Opart, ml, err);
+  k_flash_fusion<<<grid, kThreads, kSmem + 1024, stream>>>(tmQ, tmK, tmV, seg_dev, cnt_dev, m_dev, B, M_max, L, Lpad, Opart, ml, err);
   IMF_CHECK_LAUNCH();
-  const long long total = (long long)M_max * (kD / 4);
-  k_flash_combine<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(Opart, ml, nsplit, m_dev, M_max, o, ldo);
+  k_flash_combine<<<ff_tiles_max(M_max, B), 256, 0, stream>>>(Opart, ml, seg_dev, cnt_dev, m_dev, B, M_max, L, grid, o, ldo);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }

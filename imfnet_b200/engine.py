@@ -371,8 +371,14 @@ class GraphPlan:
     replayed_launches = 0      # kernels of this library launched through graph replays (bench.py adds it to imf_launch_count)
     ROW_SLACK = 4096           # a plan of `rows` voxels only ever serves fragments of more than rows - ROW_SLACK voxels
 
-    def __init__(self, fused: FusedPlan, rows: int, H: int, W: int, cap8: int):
+    ERR_ITEM_CAPACITY = 0x20000      # status bits of imf_batch_segments_n
+    ERR_BATCH_INDEX = 0x40000
+
+    def __init__(self, fused: FusedPlan, rows: int, H: int, W: int, cap8: int, B: int = 1):
+        """rows: voxel capacity (all items together); cap8: token capacity of the fusion module at stride 8 (all items together);
+        B: batch items the coordinates may name (column 0 < B), each with its own image."""
         self.f, self.rows, self.H, self.W, self.cap8 = fused, int(rows), int(H), int(W), int(cap8)
+        self.B = self.num_items = int(B)
         m, dev = fused.m, fused.device
         self.m, self.device = m, dev
         L = _lib.lib()
@@ -383,7 +389,7 @@ class GraphPlan:
         f32 = dict(dtype=torch.float32, device=dev)
         self.coords = {1: torch.zeros((rows, 4), **i32)}
         self.feats = torch.zeros((rows, m.conv1.in_channels), **f32)
-        self.image = torch.zeros((1, 3, self.H, self.W), **f32)
+        self.image = torch.zeros((self.B, 3, self.H, self.W), **f32)
         self.n1 = torch.zeros(1, **i32)
         self.meta = torch.zeros(16, **i32)                  # [0] status, [2] n(stride 2), [3] n(stride 4), [4] n(stride 8)
         self.err = torch.zeros(1, **i32)
@@ -416,16 +422,22 @@ class GraphPlan:
         self.h0, self.h1 = h2(TR[2]), h2(TR[2])
         self.P8, self.fused32 = torch.zeros((self.cap8, CH[4]), **f32), torch.zeros((self.cap8, CH[4]), **f32)
         self.side = torch.cuda.Stream(device=dev)
-        from .model.Img_Encoder import ImagePlan
         with torch.cuda.device(dev):
-            self.image_plan = ImagePlan(m.img_encoder.backbone, self.H, self.W, fused.split_small, err=self.err)     # private buffers: plans run concurrently
-        self.n_tok = self.image_plan.P2                     # image tokens: conv arithmetic, not H/8 * W/8, for odd sizes
+            self.image_plan = self._make_image_plan(m, fused)          # private buffers: plans run concurrently
+        self.n_tok = self.image_plan.P2                     # image tokens per image: conv arithmetic, not H/8 * W/8, for odd sizes
         af = m.attention_fusion
-        self.att_ws_bytes = int(L.imf_attention_workspace_bytes(self.cap8, self.n_tok, af.latent_dim, af.inner))
+        if af.inner != 128:
+            raise NotImplementedError("the captured plans implement the IMFNet fusion head (one cross head of 128 channels)")
+        # fusion module: all items through one chain of launches (imf_attention_fusion_fwd_batched); per-item row ranges stay on the device
+        self.seg = torch.zeros(self.B + 1, **i32)
+        self.cnt = torch.zeros(self.B, **i32)
+        self.kv = torch.empty(int(L.imf_attention_kv_batched_bytes(self.n_tok, self.B)), **u8)
+        self.kv_ws_bytes = int(L.imf_attention_kv_batched_workspace_bytes(self.n_tok, af.dim, af.inner, self.B))
+        self.kv_ws = torch.empty(self.kv_ws_bytes, **u8)
+        self.att_ws_bytes = int(L.imf_attention_batched_workspace_bytes(self.cap8, self.n_tok, af.latent_dim, af.inner, self.B))
         self.att_ws = torch.empty(max(self.att_ws_bytes, 1), **u8)
         self.conv_ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(max(max(CH[1:]), max(TR[1:]))))
         self.conv_ws = torch.zeros(self.conv_ws_bytes, **u8)          # head = arrival counters, zero on entry / left zero
-        self.num_items = 1                                            # batch items the coordinates may name (BatchGraphPlan: B)
         self.cf_ws = None
         if fused.conv1_tc is not None:
             self.cf_ws_bytes = int(L.imf_conv_first_tc_workspace_bytes(rows, m.conv1.kernel_size))
@@ -434,6 +446,12 @@ class GraphPlan:
         self.graph = None
         self.launches_per_replay = 0
         self._tl = None      # layer-timing records while time_layers() runs, else None
+
+    def _make_image_plan(self, m, fused):
+        from .model.Img_Encoder import ImagePlan
+        if self.B != 1:
+            raise NotImplementedError("several images per replay: imfnet_b200.batched.BatchGraphPlan")
+        return ImagePlan(m.img_encoder.backbone, self.H, self.W, fused.split_small, err=self.err)
 
     # -- footprint (the model's plan cache evicts by bytes) ------------------------------------------
     def nbytes(self) -> int:
@@ -578,21 +596,28 @@ class GraphPlan:
                                                1 if m.normalize_feature else 0, None, self.out.data_ptr(), m.out_channels, s))
         self._tl_end(tok)
 
-    # the two steps a batch changes (imfnet_b200/batched.py overrides them): the image branch and the fusion at stride 8
     def _enqueue_image(self, m, main):
-        """Image branch on a forked stream: encoder, then K / V of the image tokens (joined again in _enqueue_fusion)."""
+        """Image branch on a forked stream: encoder over all images of the replay, then K / V of their tokens in one projection
+        (joined again in _enqueue_fusion)."""
+        L = _lib.lib()
         side = main if self._tl is not None else self.side          # (layer timing: nothing runs beside the timed kernels)
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            self.kv = m.attention_fusion.project_context(self.image_plan.enqueue(self.image[0]), False)
+            tokens = self.image_plan.enqueue(self.image if self.B > 1 else self.image[0])
+            _lib.check(L.imf_attention_kv_batched(m.attention_fusion.packed(), tokens.data_ptr(), self.n_tok, self.B, self.kv.data_ptr(),
+                                                  self.kv_ws.data_ptr(), self.kv_ws_bytes, self.err.data_ptr(), side.cuda_stream))
 
     def _enqueue_fusion(self, L, m, C8, k8, main, s):
-        """Attention fusion at stride 8 (fp32 tokens): d2 (h2) -> P8 -> fused32 -> fused (h2)."""
+        """Attention fusion at stride 8 (model/resunet.py:189, 237-273) for all items at once: d2 (h2) -> P8 (fp32) -> fused32 ->
+        fused (h2).  The per-item row ranges (seg, cnt) are computed on the device; item b attends to the tokens of image b."""
         af = m.attention_fusion
+        _lib.check(L.imf_batch_segments_n(self.coords[8].data_ptr(), self._n(8), self.rows, self.B, self.cap8, self.seg.data_ptr(),
+                                          self.cnt.data_ptr(), self.err.data_ptr(), s))
         _lib.check(L.imf_h2_unpack_n(self.d2.data_ptr(), 2 * C8, self.cap8, self._n(8), C8, k8, self.P8.data_ptr(), C8, s))
         main.wait_stream(self.side)
-        _lib.check(L.imf_attention_fusion_fwd_m(af.packed(), self.P8.data_ptr(), C8, self.cap8, self._n(8), self.kv.data_ptr(),
-                                                self.n_tok, self.fused32.data_ptr(), C8, self.att_ws.data_ptr(), self.att_ws_bytes, s))
+        _lib.check(L.imf_attention_fusion_fwd_batched(af.packed(), self.P8.data_ptr(), C8, self.cap8, self._n(8), self.seg.data_ptr(),
+                                                      self.cnt.data_ptr(), self.B, self.kv.data_ptr(), self.n_tok, self.fused32.data_ptr(), C8,
+                                                      self.att_ws.data_ptr(), self.att_ws_bytes, self.err.data_ptr(), s))
         _lib.check(L.imf_h2_pack_n(self.fused32.data_ptr(), C8, self.cap8, self._n(8), C8, k8, self.fused.data_ptr(), 2 * C8,
                                    self.err.data_ptr(), s))
 
@@ -634,7 +659,7 @@ class GraphPlan:
             with torch.cuda.stream(st):
                 self.coords[1][:N].copy_(coords, non_blocking=True)
                 self.feats[:N].copy_(feats, non_blocking=True)
-                self.image.copy_(image.reshape(self.image.shape), non_blocking=True)
+                self.image.copy_(image.reshape(self.image.shape), non_blocking=True)          # (B == 1 here)
                 self.n1.fill_(N)
                 self.graph.replay()
                 GraphPlan.replayed_launches += self.launches_per_replay
@@ -659,11 +684,16 @@ class GraphPlan:
         if mh[0]:
             from .sparse import _raise_status
             _raise_status(mh[0])
-        if mh[4] > self.cap8:
-            raise PlanCapacityError(f"{mh[4]} stride-8 voxels > plan capacity {self.cap8}")
-        FusedPlan._raise_on_status(mh[16])
+        self._check_fusion_status(mh)
         self.levels = {1: N, 2: mh[2], 4: mh[3], 8: mh[4]}
         return out
+
+    def _check_fusion_status(self, mh):
+        if mh[16] & self.ERR_BATCH_INDEX:
+            raise ValueError("coordinates reference more batch items than images were given")
+        if mh[4] > self.cap8 or (mh[16] & self.ERR_ITEM_CAPACITY):
+            raise PlanCapacityError(f"{mh[4]} stride-8 voxels > plan capacity {self.cap8}")
+        FusedPlan._raise_on_status(mh[16] & ~(self.ERR_BATCH_INDEX | self.ERR_ITEM_CAPACITY))
 
     def run(self, coords: torch.Tensor, feats: torch.Tensor, image: torch.Tensor) -> torch.Tensor:
         self.launch(coords, feats, image)

@@ -115,12 +115,7 @@ int imf_batch_segments(const int32_t* coords, const int32_t* n_dev, int32_t n_ma
  * bit 17 when an item has more than cap_item rows and bit 18 when rows carry a batch index >= num_batches.  num_batches <= 255. */
 int imf_batch_segments_n(const int32_t* coords, const int32_t* n_dev, int32_t n_max, int32_t num_batches, int32_t cap_item,
                          int32_t* seg, int32_t* cnt, int32_t* err, imf_stream_t stream);
-/* Rows [*seg_b_dev, *seg_b_dev + min(*cnt_b_dev, cap)) of the h2 matrix H <-> fp32 rows 0.. of X (one batch item's tokens:
- * the `queries_encoder` / result of AttentionFusion.forward, model/resunet.py:262-266).  cap sizes the launch. */
-int imf_h2_unpack_seg(const void* H, int32_t ldh, const int32_t* seg_b_dev, const int32_t* cnt_b_dev, int32_t cap, int32_t C, int32_t KC,
-                      float* X, int32_t ldx, imf_stream_t stream);
-int imf_h2_pack_seg(const float* X, int32_t ldx, const int32_t* seg_b_dev, const int32_t* cnt_b_dev, int32_t cap, int32_t C, int32_t KC,
-                    void* H, int32_t ldh, int32_t* err, imf_stream_t stream);
+
 
 /* ---- sparse convolution: ME.MinkowskiConvolution(+Transpose).forward (model/resunet.py:168-213,
  *      model/residual_block.py:40,44) with BatchNorm(eval)/residual/ReLU fused ------------------------- */
@@ -297,6 +292,23 @@ int imf_nn_search(const float* A, int32_t lda, int32_t na, const float* B, int32
 /* imf_attention_fusion_fwd with an optional device-side token count (min(*m_dev, M) rows; M sizes launches and workspace). */
 int imf_attention_fusion_fwd_m(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const int32_t* m_dev, const float* kv,
                                int32_t L, float* out, int32_t ldo, void* workspace, size_t workspace_bytes, imf_stream_t stream);
+
+/* ---- the same module for ALL batch items in one chain of launches (the batched captured plan) ----------------------------------
+ * ResUNet2.transformer (model/resunet.py:237-273) calls the fusion module once per batch item; everything in it but the attention
+ * core is row-wise, so here the point tokens of all items (rows [seg[b], seg[b] + cnt[b]) of P, imf_batch_segments_n) go through ONE
+ * LayerNorm / projection / feed-forward chain and ONE attention launch in which item b attends to the L tokens of image b.
+ * Requires the IMFNet head (inner == 128).
+ *   imf_attention_kv_batched: tokens [B*L, dim] row-major (image b = rows [b*L, (b+1)*L)) -> kv (opaque: fp16 hi/lo K and V^T per image);
+ *   imf_attention_fusion_fwd_batched: P [M, latent] (M = row capacity, min(*m_dev, M) rows in use) -> out, rows outside every item's
+ *     range untouched.  err (optional device int32): watchdog codes, bit 16 = a query left the fp16 range. */
+size_t imf_attention_kv_batched_bytes(int32_t L, int32_t B);
+size_t imf_attention_kv_batched_workspace_bytes(int32_t L, int32_t dim, int32_t inner, int32_t B);
+int imf_attention_kv_batched(const imf_attn_weights_t* w, const float* tokens, int32_t L, int32_t B, void* kv, void* workspace,
+                             size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+size_t imf_attention_batched_workspace_bytes(int32_t M, int32_t L, int32_t latent, int32_t inner, int32_t B);
+int imf_attention_fusion_fwd_batched(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const int32_t* m_dev,
+                                     const int32_t* seg_dev, const int32_t* cnt_dev, int32_t B, const void* kv, int32_t L, float* out,
+                                     int32_t ldo, void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
 
 #ifdef __cplusplus
 }

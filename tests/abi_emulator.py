@@ -187,14 +187,6 @@ class Emulator:
     def do_imf_h2_pack(self, X, ldx, n, C, KC, H, ldh, err):
         self.do_imf_h2_pack_n(X, ldx, n, None, C, KC, H, ldh, err)
 
-    def do_imf_h2_unpack_seg(self, H, ldh, seg_b, cnt_b, cap, C, KC, X, ldx):
-        s, m = int(vec(seg_b, 1, np.int32)[0]), min(int(vec(cnt_b, 1, np.int32)[0]), cap)
-        mat(X, m, C, ldx)[:] = mat(H, s + m, C, ldh // 2)[s:]
-
-    def do_imf_h2_pack_seg(self, X, ldx, seg_b, cnt_b, cap, C, KC, H, ldh, err):
-        s, m = int(vec(seg_b, 1, np.int32)[0]), min(int(vec(cnt_b, 1, np.int32)[0]), cap)
-        mat(H, s + m, C, ldh // 2)[s:] = mat(X, m, C, ldx)
-
     # ---- convolutions --------------------------------------------------------------------------------------------------
     def do_imf_sparse_conv_h2_pack(self, W, K3, Cin, Cout, kc_in, wmul, packed):
         self.packed[packed] = (vec(W, K3 * Cin * Cout).reshape(K3, Cin, Cout).copy() * np.float32(wmul))
@@ -353,6 +345,26 @@ class Emulator:
         h = layer_norm(x1, vec(w.ln_f_w, lat), vec(w.ln_f_b, lat)) @ vec(w.w1, 8 * lat * lat).reshape(8 * lat, lat).T + vec(w.b1, 8 * lat)
         h = h[:, :4 * lat] * gelu(np.ascontiguousarray(h[:, 4 * lat:]))
         mat(out, m, lat, ldo)[:] = h @ vec(w.w2, lat * 4 * lat).reshape(lat, 4 * lat).T + vec(w.b2, lat) + x1
+
+    def do_imf_attention_kv_batched(self, w, tokens, L, B, kv, ws, ws_bytes, err):
+        t = mat(tokens, B * L, w.dim, w.dim)
+        cn = layer_norm(t, vec(w.ln_c_w, w.dim), vec(w.ln_c_b, w.dim))
+        p = cn @ vec(w.wkv, 2 * w.inner * w.dim).reshape(2 * w.inner, w.dim).T
+        self.kv[kv] = [(p[b * L:(b + 1) * L, :w.inner].copy(), p[b * L:(b + 1) * L, w.inner:].copy()) for b in range(B)]
+
+    def do_imf_attention_fusion_fwd_batched(self, w, P, ldp, M, m_dev, seg_dev, cnt_dev, B, kv, L, out, ldo, ws, ws_bytes, err):
+        seg, cnt = vec(seg_dev, B, np.int32), vec(cnt_dev, B, np.int32)
+        m = count(m_dev, M)
+        saved = self.kv[kv]
+        try:
+            for b in range(B):          # per item: its rows against its image (model/resunet.py:240-271); never past the M rows
+                lo, hi = int(seg[b]), min(int(seg[b]) + int(cnt[b]), m)
+                if hi <= lo:
+                    continue
+                self.kv[kv] = saved[b]
+                self.do_imf_attention_fusion_fwd_m(w, P + 4 * ldp * lo, ldp, hi - lo, None, kv, L, out + 4 * ldo * lo, ldo, ws, ws_bytes)
+        finally:
+            self.kv[kv] = saved
 
     def do_imf_attention_fusion_fwd(self, w, P, ldp, M, kv, L, out, ldo, ws, ws_bytes):
         self.do_imf_attention_fusion_fwd_m(w, P, ldp, M, None, kv, L, out, ldo, ws, ws_bytes)

@@ -132,7 +132,10 @@ def test_single_fragment_graph_plan_sequence(fake_cuda):
     assert per_enqueue == 3                                                  # two warm-ups + the capture
     assert seq.count("imf_sparse_conv_g4_fwd_perm") == 3 * 20               # 6 strided / transposed + 14 block convolutions
     assert seq.count("imf_sparse_conv_g4_fwd") == 3 * 16                    # image encoder: stem + 6 + 9
-    assert seq.count("imf_attention_fusion_fwd_m") == 3 and seq.count("imf_pointwise_tail_h2_fwd") == 3
+    assert seq.count("imf_conv_first_tc_h2_fwd") == 3 and seq.count("imf_conv_first_h2_fwd") == 0      # conv1 on the tensor-core path
+    # the fusion module of the single-fragment plan is the batched chain with B = 1
+    assert seq.count("imf_attention_fusion_fwd_batched") == 3 == seq.count("imf_attention_kv_batched") == seq.count("imf_batch_segments_n")
+    assert seq.count("imf_pointwise_tail_h2_fwd") == 3
 
 
 def test_batched_plan_sequence_and_slices(fake_cuda):
@@ -153,23 +156,24 @@ def test_batched_plan_sequence_and_slices(fake_cuda):
     assert int(g.n1[0]) == n0 + n1 and g.image.shape == (2, 3, 48, 64)
     assert torch.equal(g.image[1], frags[1][2].reshape(3, 48, 64))
     seq = names(fake_cuda)
-    # per enqueue of a batched plan: one image-encoder pass, one segment kernel, B fusion chains
-    enq = seq.count("imf_batch_segments_n")
+    # per enqueue of a batched plan: one image-encoder pass, one segment kernel, ONE fusion chain over all items
+    # (the trailing single fragment goes through a single-fragment plan: 3 more enqueues of the same chain with B = 1)
+    enq = len([a for n, a in fake_cuda.calls if n == "imf_batch_segments_n" and a[3] == 2])
     assert enq == 2 * 3                                                       # two plans x (two warm-ups + capture)
-    assert seq.count("imf_h2_unpack_seg") == enq * 2 == seq.count("imf_h2_pack_seg")
+    assert len([a for n, a in fake_cuda.calls if n == "imf_attention_fusion_fwd_batched" and a[7] == 2]) == enq
+    assert len([a for n, a in fake_cuda.calls if n == "imf_attention_kv_batched" and a[3] == 2]) == enq
     assert seq.count("imf_image_im2col_h2") >= enq * 2 and seq.count("imf_image_maxpool_h2") >= enq * 2
     # the image encoder's batched launches cover B * P rows
     ip = g.image_plan
     stem = [a for n, a in fake_cuda.calls if n == "imf_sparse_conv_g4_fwd" and a[8] == 2 * ip.P0]
     assert stem, "no stem launch over the rows of both images"
     assert ip.col.shape[0] == 2 * ip.P0 and ip.tokens.shape == (2 * ip.P2, 128)
-    # fusion chains: queries of item b come from the level's h2 matrix via that item's segment / count slots
-    unpack = [a for n, a in fake_cuda.calls if n == "imf_h2_unpack_seg" and a[0] == g.d2.data_ptr()][-2:]
-    assert unpack[0][2] == g.seg.data_ptr() and unpack[1][2] == g.seg.data_ptr() + 4
-    assert unpack[0][3] == g.cnt.data_ptr() and unpack[1][3] == g.cnt.data_ptr() + 4
-    att = [a for n, a in fake_cuda.calls if n == "imf_attention_fusion_fwd_m" and a[4] in (g.cnt.data_ptr(), g.cnt.data_ptr() + 4)][-2:]
-    assert att[0][3] == g.item_cap8 and att[0][4] == g.cnt.data_ptr() and att[1][4] == g.cnt.data_ptr() + 4
-    assert att[0][6] == ip.P2                                                 # image tokens per item
+    # fusion chain: the level's rows through one call with the plan's segment / count arrays and the stride-8 row count on the device
+    att = [a for n, a in fake_cuda.calls if n == "imf_attention_fusion_fwd_batched" and a[1] == g.P8.data_ptr()][-1]
+    assert att[3] == g.cap8 == 2 * g.item_cap8 and att[4] == g._n(8) and att[5] == g.seg.data_ptr() and att[6] == g.cnt.data_ptr()
+    assert att[8] == g.kv.data_ptr() and att[9] == ip.P2 and att[10] == g.fused32.data_ptr()          # image tokens per item
+    kvc = [a for n, a in fake_cuda.calls if n == "imf_attention_kv_batched" and a[4] == g.kv.data_ptr()][-1]
+    assert kvc[1] == ip.tokens.data_ptr() and kvc[2] == ip.P2 and kvc[3] == 2
 
 
 def test_batched_plan_errors(fake_cuda):
