@@ -72,6 +72,8 @@ SIGNATURES = {
     "imf_image_conv_table": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p]),
     "imf_image_im2col_h2": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p]),
     "imf_image_maxpool_h2": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p]),
+    "imf_image_im2col_h2_batch": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p]),
+    "imf_image_maxpool_h2_batch": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p]),
     "imf_transpose_tokens": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "imf_nn_search_workspace_bytes": (_sz, [_i32]),
     "imf_nn_search": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),

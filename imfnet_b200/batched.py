@@ -74,13 +74,11 @@ class BatchedImagePlan(ImagePlan):
         s = _lib.cur_stream()
         B = self.B
         k, st, pd = self.stem_geom
-        for b in range(B):
-            _lib.check(L.imf_image_im2col_h2(images[b].data_ptr(), 3, self.H, self.W, k, st, pd, self.STEM_K,
-                                             self.col.data_ptr() + b * self.P0 * self.STEM_K * 4, 2 * self.STEM_K, s))
+        _lib.check(L.imf_image_im2col_h2_batch(images.data_ptr(), 3, self.H, self.W, k, st, pd, self.STEM_K, self.col.data_ptr(),
+                                               2 * self.STEM_K, B, s))                               # all images, one launch
         self._conv(L, self.stem, self.col, self.t_id0, B * self.P0, None, True, self.s0, s)
-        for b in range(B):
-            _lib.check(L.imf_image_maxpool_h2(self.s0.data_ptr() + b * self.P0 * self.C1 * 4, 2 * self.C1, 64, self.C1, self.H1, self.W1,
-                                              3, 2, 1, self.l1[0].data_ptr() + b * self.P1 * self.C1 * 4, 2 * self.C1, s))
+        _lib.check(L.imf_image_maxpool_h2_batch(self.s0.data_ptr(), 2 * self.C1, 64, self.C1, self.H1, self.W1, 3, 2, 1,
+                                                self.l1[0].data_ptr(), 2 * self.C1, B, s))
         n1, n2 = B * self.P1, B * self.P2
         x, tmp, out = self.l1
         for c1, c2 in self.blocks1:

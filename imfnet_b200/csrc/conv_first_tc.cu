@@ -147,57 +147,99 @@ __global__ void __launch_bounds__(256) k_cf_scatter(const float* __restrict__ X,
 }
 
 // E[row, k] = f[nbr(row, k)] as an h2 matrix of KP columns (chunk width 64); identity table + tile masks for the one-offset convolution.
-// One warp per voxel.  Offset k = kx + K ky + K^2 kz (x fastest): the K cells of an x-run are contiguous in the grid, so instruction t
-// lets lane l read offset k = (K * RPI) t + l -- RPI = 32 / K whole runs per instruction.
+// A warp owns 32 consecutive voxels and walks them one by one.  Offset k = kx + K ky + K^2 kz (x fastest): the K cells of an x-run are
+// contiguous in the grid, so in instruction i lane l reads offset k = (K * RPI) i + l -- RPI = 32 / K whole runs per instruction -- and
+// everything that depends only on (lane, i) (the offset's dx, dy, dz) is computed once per warp, not per voxel: per voxel and offset
+// there is one address add, one load, the fp16 hi/lo split and two 2-byte stores into the warp's row buffer in shared memory, from
+// which the row leaves as ONE 512-byte store (a first version issued ~400 warp instructions per voxel and was issue-bound at 850 us
+// for 500 k voxels).  Grid cells are addressed with 32-bit indices (the budget is far below 2^31 cells).
 template <int K>
 __global__ void __launch_bounds__(256) k_cf_expand(const float* __restrict__ X, int ldx, const int4* __restrict__ coords,
                                                    const int* __restrict__ n_ptr, int n_max, int B, const CfMeta* __restrict__ m,
                                                    const float* __restrict__ grid, const ImfSlot* __restrict__ table, unsigned long long mask,
-                                                   __half* __restrict__ E, int KP, int* __restrict__ ident, unsigned* __restrict__ tile_mask,
+                                                   __half* __restrict__ E, int* __restrict__ ident, unsigned* __restrict__ tile_mask,
                                                    int ld_n) {
-  constexpr int K3 = K * K * K, h = K / 2, KR = K * (32 / K);
+  constexpr int K3 = K * K * K, h = K / 2, KR = K * (32 / K), KP = (K3 + 63) / 64 * 64, NI = (KP + KR - 1) / KR;
+  __shared__ __align__(16) __half rowbuf[8][2 * KP];
   const int n = cf_count(n_ptr, n_max);
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= ld_n) return;
-  if (row >= n) {                                       // padding rows of the identity table (up to the 128-row boundary the kernel reads)
-    if (lane == 0 && row < (n + 127) / 128 * 128) ident[row] = -1;
-    if (lane == 0 && (row & 127) == 0 && row >= (n + 127) / 128 * 128) tile_mask[row >> 7] = 0u;
-    return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int chunk0 = (blockIdx.x * 8 + w) * 32;
+  if (chunk0 >= ld_n) return;
+  const int n128 = (n + 127) / 128 * 128;
+  // ---- this lane's voxel of the chunk: identity-table entry, tile mask, grid cell of its centre ----
+  const int myrow = chunk0 + lane;
+  int4 c = make_int4(-1, 0, 0, 0);
+  if (myrow < n) c = coords[myrow];
+  if (myrow < ld_n) {
+    if (myrow < n) ident[myrow] = myrow;
+    else if (myrow < n128) ident[myrow] = -1;           // padding rows up to the 128-row boundary the convolution kernel reads
+    if ((myrow & 127) == 0) tile_mask[myrow >> 7] = myrow < n ? 1u : 0u;
   }
-  const int4 c = coords[row];
-  const bool use_grid = m->use_grid != 0 && (unsigned)c.x < (unsigned)B;
-  int it[kItemInts];
+  const int grid_ok = m->use_grid;
+  int my_ug = 0, my_base = 0, my_dx = 0, my_dxy = 0;
+  if (grid_ok && myrow < n && (unsigned)c.x < (unsigned)B) {
+    const int* it = m->item[c.x];
+    my_ug = 1;
+    my_base = (int)cf_cell(it, c.y, c.z, c.w);
+    my_dx = it[3];
+    my_dxy = it[3] * it[4];
+  }
+  // ---- this lane's offsets ----
+  int odx[NI], ody[NI], odz[NI];
 #pragma unroll
-  for (int i = 0; i < kItemInts; ++i) it[i] = use_grid ? m->item[c.x][i] : 0;
-  if (lane == 0) {
-    ident[row] = row;
-    if ((row & 127) == 0) tile_mask[row >> 7] = 1u;
+  for (int i = 0; i < NI; ++i) {
+    const int k = lane + KR * i;
+    odx[i] = k % K - h;
+    ody[i] = (k / K) % K - h;
+    odz[i] = k / (K * K) - h;
   }
-  __half* e_row = E + (size_t)row * (2 * KP);
-  if (lane < KR) {
-    for (int k = lane; k < KP; k += KR) {
-      float f = 0.f;
-      if (k < K3) {
-        const int x = c.y + (k % K - h), y = c.z + ((k / K) % K - h), z = c.w + (k / (K * K) - h);
-        if (use_grid) {
-          f = __ldg(grid + cf_cell(it, x, y, z));
-        } else if (imf_coord_in_range(c.x, x, y, z)) {
-          const int r = imf_table_lookup(table, mask, imf_pack_key(c.x, x, y, z));
-          if (r >= 0) f = __ldg(X + (size_t)r * ldx);
-        }
-      }
-      const __half hi = __float2half_rn(f);
-      __half* p = e_row + (k >> 6) * 128 + (k & 63);   // chunk k / 64 holds [hi 64 | lo 64]
-      p[0] = hi;
-      p[64] = __float2half_rn(f - __half2float(hi));
+  __half* rb = rowbuf[w];
+  const int vend = min(32, n - chunk0);
+  for (int v = 0; v < vend; ++v) {
+    const int ug = __shfl_sync(0xffffffffu, my_ug, v);
+    const int base = __shfl_sync(0xffffffffu, my_base, v);
+    const int DX = __shfl_sync(0xffffffffu, my_dx, v), DXY = __shfl_sync(0xffffffffu, my_dxy, v);
+    int cb = 0, cx = 0, cy = 0, cz = 0;
+    if (!ug) {                                           // hash-probe path (grid over budget, or a foreign batch index): warp-uniform
+      cb = __shfl_sync(0xffffffffu, c.x, v); cx = __shfl_sync(0xffffffffu, c.y, v);
+      cy = __shfl_sync(0xffffffffu, c.z, v); cz = __shfl_sync(0xffffffffu, c.w, v);
     }
+    if (lane < KR) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int k = lane + KR * i;
+        if (k >= KP) break;
+        float f = 0.f;
+        if (k < K3) {
+          if (ug) {
+            f = __ldg(grid + base + odz[i] * DXY + ody[i] * DX + odx[i]);
+          } else {
+            const int x = cx + odx[i], y = cy + ody[i], z = cz + odz[i];
+            if (imf_coord_in_range(cb, x, y, z)) {
+              const int r = imf_table_lookup(table, mask, imf_pack_key(cb, x, y, z));
+              if (r >= 0) f = __ldg(X + (size_t)r * ldx);
+            }
+          }
+        }
+        const __half hi = __float2half_rn(f);
+        __half* p = rb + (k >> 6) * 128 + (k & 63);     // chunk k / 64 holds [hi 64 | lo 64]
+        p[0] = hi;
+        p[64] = __float2half_rn(f - __half2float(hi));
+      }
+    }
+    __syncwarp();
+    if (lane * 8 < 2 * KP)
+      *reinterpret_cast<uint4*>(E + (size_t)(chunk0 + v) * (2 * KP) + lane * 8) = *reinterpret_cast<const uint4*>(rb + lane * 8);
+    __syncwarp();
   }
 }
 
 inline size_t r256(size_t b) { return (b + 255) / 256 * 256; }
 inline int cf_kp(int K) { return (K * K * K + 63) / 64 * 64; }
-inline long long cf_budget_cells(int n_max) { return 64LL * (n_max > 0 ? n_max : 1) + (1 << 20); }
+inline long long cf_budget_cells(int n_max) {          // 64 cells per voxel, below 2^31 (k_cf_expand addresses cells with 32-bit indices)
+  const long long c = 64LL * (n_max > 0 ? n_max : 1) + (1 << 20);
+  return c < 2000000000LL ? c : 2000000000LL;
+}
 
 struct CfLayout {
   size_t meta, grid, E, ident, mask, conv_ws, total;
@@ -258,10 +300,10 @@ extern "C" int imf_conv_first_tc_h2_fwd(const float* X, int32_t ldx, const void*
   IMF_CHECK_LAUNCH();
   const ImfSlot* tab = reinterpret_cast<const ImfSlot*>(table);
   const unsigned long long hmask = (unsigned long long)capacity - 1;
-  const int eblocks = (L.ld_n + 7) / 8;
-  if (kernel_size == 5) k_cf_expand<5><<<eblocks, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, E, KP, ident, tmask, L.ld_n);
-  else if (kernel_size == 3) k_cf_expand<3><<<eblocks, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, E, KP, ident, tmask, L.ld_n);
-  else k_cf_expand<1><<<eblocks, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, E, KP, ident, tmask, L.ld_n);
+  const int eblocks = (L.ld_n + 255) / 256;          // 8 warps x 32 voxels per block
+  if (kernel_size == 5) k_cf_expand<5><<<eblocks, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, E, ident, tmask, L.ld_n);
+  else if (kernel_size == 3) k_cf_expand<3><<<eblocks, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, E, ident, tmask, L.ld_n);
+  else k_cf_expand<1><<<eblocks, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, E, ident, tmask, L.ld_n);
   IMF_CHECK_LAUNCH();
   return imf_sparse_conv_g4_fwd(E, 2 * KP, 64, packed, ident, L.ld_n, tmask, n_dev, n_max, 1, KP, Cout, scale, shift, nullptr, 0, 0, relu, Y,
                                 ldy, n_max, kc_out, nullptr, 0, err, stream);

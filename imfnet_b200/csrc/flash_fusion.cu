@@ -431,7 +431,9 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 // out[row, :] = sum_p w_p O_p / sum_p w_p l_p,  w_p = exp2(m_p - max_p m_p), over the pieces p of the row's tile.
-// One CTA per tile of the flat axis; the piece <-> slot mapping is recomputed from the same quantities the attention kernel used.
+// grid = (tiles, 16 row groups): one warp per row, eight rows per CTA (a tile of a small problem has ~15 pieces whose loads are
+// dependent: one CTA per tile left 9 CTAs crawling through 128 rows each, 137 us for a single C2 fragment); the piece <-> slot mapping
+// is recomputed from the same quantities the attention kernel used.
 __global__ void __launch_bounds__(256) k_flash_combine(const float* __restrict__ Opart, const float* __restrict__ ml, const int* __restrict__ seg,
                                                        const int* __restrict__ cnt, const int* __restrict__ m_ptr, int B, int M_max, int L,
                                                        int grid_att, float* __restrict__ out, int ldo) {
@@ -454,9 +456,10 @@ __global__ void __launch_bounds__(256) k_flash_combine(const float* __restrict__
   const int row0 = s0 + (int)(tile - tb) * kTQ, row_end = s0 + ff_item_rows(seg, cnt, m_ptr, M_max, b);
   const int c_first = (int)((tile * nb) / per), c_last = (int)(((tile + 1) * nb - 1) / per);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int r = w; r < kTQ; r += 8) {
+  {
+    const int r = blockIdx.y * 8 + w;
     const int row = row0 + r;
-    if (row >= row_end) break;
+    if (row >= row_end) return;
     float mx = -INFINITY;
     for (int c = c_first; c <= c_last; ++c) mx = fmaxf(mx, ml[((size_t)((int)tile + c) * kTQ + r) * 2]);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -532,7 +535,7 @@ int imf_flash_attention(const void* qh2, int M_max, const int* seg_dev, const in
   IMF_CHECK_CUDA(imf_set_max_smem_once(reinterpret_cast<const void*>(&k_flash_fusion), kSmem + 1024));
   k_flash_fusion<<<grid, kThreads, kSmem + 1024, stream>>>(tmQ, tmK, tmV, seg_dev, cnt_dev, m_dev, B, M_max, L, Lpad, Opart, ml, err);
   IMF_CHECK_LAUNCH();
-  k_flash_combine<<<ff_tiles_max(M_max, B), 256, 0, stream>>>(Opart, ml, seg_dev, cnt_dev, m_dev, B, M_max, L, grid, o, ldo);
+  k_flash_combine<<<dim3(ff_tiles_max(M_max, B), kTQ / 8), 256, 0, stream>>>(Opart, ml, seg_dev, cnt_dev, m_dev, B, M_max, L, grid, o, ldo);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }

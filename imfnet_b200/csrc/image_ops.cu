@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(256) k_image_im2col_h2(const float* __restrict
     if (col < C * K * K) { const int c = col % C, t = col / C; o = (c * K + t / K) * PW + t % K; }
     off_s[col] = o;
   }
+  img += (size_t)blockIdx.y * C * H * W;                    // image blockIdx.y of the batch; its rows follow the previous image's
+  Y += (size_t)blockIdx.y * Hout * Wout * ldy;
   const int xblocks = (Wout + 31) / 32;
   const int oy = blockIdx.x / xblocks, ox0 = (blockIdx.x % xblocks) * 32;
   const int iy0 = oy * stride - pad, ix0 = ox0 * stride - pad;
@@ -80,6 +82,8 @@ __global__ void __launch_bounds__(256) k_image_im2col_h2(const float* __restrict
 __global__ void __launch_bounds__(256) k_image_maxpool_h2(const __half* __restrict__ X, int ldx, int kc, int C, int Hin, int Win, int Hout,
                                                           int Wout, int K, int stride, int pad, __half* __restrict__ Y, int ldy) {
   const int groups = C >> 3;
+  X += (size_t)blockIdx.y * Hin * Win * ldx;                // image blockIdx.y of the batch
+  Y += (size_t)blockIdx.y * Hout * Wout * ldy;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)Hout * Wout * groups) return;
   const int o = (int)(idx / groups), c0 = (int)(idx % groups) * 8;
@@ -145,29 +149,45 @@ extern "C" int imf_image_conv_table(int32_t Hin, int32_t Win, int32_t ksize, int
   return IMF_OK;
 }
 
+extern "C" int imf_image_im2col_h2_batch(const float* image, int32_t C, int32_t H, int32_t W, int32_t ksize, int32_t stride, int32_t pad,
+                                         int32_t Kpad, void* Y, int32_t ldy, int32_t num_images, cudaStream_t stream);
 extern "C" int imf_image_im2col_h2(const float* image, int32_t C, int32_t H, int32_t W, int32_t ksize, int32_t stride, int32_t pad,
                                    int32_t Kpad, void* Y, int32_t ldy, cudaStream_t stream) {
-  IMF_CHECK_ARG(image && Y && C > 0 && H > 0 && W > 0 && ksize >= 1 && stride >= 1 && pad >= 0);
+  return imf_image_im2col_h2_batch(image, C, H, W, ksize, stride, pad, Kpad, Y, ldy, 1, stream);
+}
+// num_images contiguous NCHW images -> the rows of image b follow those of image b - 1 in Y: one launch for a whole batch
+extern "C" int imf_image_im2col_h2_batch(const float* image, int32_t C, int32_t H, int32_t W, int32_t ksize, int32_t stride, int32_t pad,
+                                         int32_t Kpad, void* Y, int32_t ldy, int32_t num_images, cudaStream_t stream) {
+  IMF_CHECK_ARG(image && Y && C > 0 && H > 0 && W > 0 && ksize >= 1 && stride >= 1 && pad >= 0 && num_images >= 1 && num_images <= 65535);
   IMF_CHECK_ARG(Kpad % 32 == 0 && Kpad >= C * ksize * ksize && ldy % 8 == 0 && ldy >= 2 * Kpad && ((uintptr_t)Y % 16) == 0);
   const int Hout = (H + 2 * pad - ksize) / stride + 1, Wout = (W + 2 * pad - ksize) / stride + 1;
   IMF_CHECK_ARG(Hout > 0 && Wout > 0);
   const size_t smem = (size_t)C * ksize * (31 * stride + ksize) * sizeof(float) + (size_t)Kpad * sizeof(int);
   IMF_CHECK_ARG(smem <= 48 * 1024);
-  k_image_im2col_h2<<<(unsigned)(Hout * ((Wout + 31) / 32)), 256, smem, stream>>>(image, C, H, W, Hout, Wout, ksize, stride, pad, Kpad,
-                                                                                reinterpret_cast<__half*>(Y), ldy);
+  k_image_im2col_h2<<<dim3((unsigned)(Hout * ((Wout + 31) / 32)), num_images), 256, smem, stream>>>(image, C, H, W, Hout, Wout, ksize, stride,
+                                                                                                   pad, Kpad, reinterpret_cast<__half*>(Y), ldy);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }
 
+extern "C" int imf_image_maxpool_h2_batch(const void* X, int32_t ldx, int32_t kc, int32_t C, int32_t Hin, int32_t Win, int32_t ksize,
+                                          int32_t stride, int32_t pad, void* Y, int32_t ldy, int32_t num_images, cudaStream_t stream);
 extern "C" int imf_image_maxpool_h2(const void* X, int32_t ldx, int32_t kc, int32_t C, int32_t Hin, int32_t Win, int32_t ksize,
                                     int32_t stride, int32_t pad, void* Y, int32_t ldy, cudaStream_t stream) {
+  return imf_image_maxpool_h2_batch(X, ldx, kc, C, Hin, Win, ksize, stride, pad, Y, ldy, 1, stream);
+}
+// num_images pixel-major matrices stacked row-wise (image b = rows [b * Hin*Win, ...) of X and [b * Hout*Wout, ...) of Y)
+extern "C" int imf_image_maxpool_h2_batch(const void* X, int32_t ldx, int32_t kc, int32_t C, int32_t Hin, int32_t Win, int32_t ksize,
+                                          int32_t stride, int32_t pad, void* Y, int32_t ldy, int32_t num_images, cudaStream_t stream) {
+  IMF_CHECK_ARG(num_images >= 1 && num_images <= 65535);
   IMF_CHECK_ARG(X && Y && (kc == 32 || kc == 64) && C % kc == 0 && Hin > 0 && Win > 0 && ksize >= 1 && stride >= 1 && pad >= 0 && pad < ksize);
   IMF_CHECK_ARG(ldx % 8 == 0 && ldx >= 2 * C && ldy % 8 == 0 && ldy >= 2 * C && ((uintptr_t)X % 16) == 0 && ((uintptr_t)Y % 16) == 0);
   const int Hout = (Hin + 2 * pad - ksize) / stride + 1, Wout = (Win + 2 * pad - ksize) / stride + 1;
   IMF_CHECK_ARG(Hout > 0 && Wout > 0);
   const long long total = (long long)Hout * Wout * (C / 8);
-  k_image_maxpool_h2<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(X), ldx, kc, C, Hin, Win, Hout,
-                                                                        Wout, ksize, stride, pad, reinterpret_cast<__half*>(Y), ldy);
+  k_image_maxpool_h2<<<dim3((unsigned)((total + 255) / 256), num_images), 256, 0, stream>>>(reinterpret_cast<const __half*>(X), ldx, kc, C, Hin,
+                                                                                          Win, Hout, Wout, ksize, stride, pad,
+                                                                                          reinterpret_cast<__half*>(Y), ldy);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }

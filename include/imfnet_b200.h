@@ -236,6 +236,12 @@ int imf_image_im2col_h2(const float* image, int32_t C, int32_t H, int32_t W, int
 /* Max pooling (torch semantics: padding never wins) on a pixel-major h2 matrix of C channels, chunk width kc. */
 int imf_image_maxpool_h2(const void* X, int32_t ldx, int32_t kc, int32_t C, int32_t Hin, int32_t Win, int32_t ksize, int32_t stride,
                          int32_t pad, void* Y, int32_t ldy, imf_stream_t stream);
+/* The two kernels above for num_images images in ONE launch: contiguous NCHW images in, the pixel rows of image b following those of
+ * image b - 1 in the input / output matrices (the batched image plan). */
+int imf_image_im2col_h2_batch(const float* image, int32_t C, int32_t H, int32_t W, int32_t ksize, int32_t stride, int32_t pad, int32_t Kpad,
+                              void* Y, int32_t ldy, int32_t num_images, imf_stream_t stream);
+int imf_image_maxpool_h2_batch(const void* X, int32_t ldx, int32_t kc, int32_t C, int32_t Hin, int32_t Win, int32_t ksize, int32_t stride,
+                               int32_t pad, void* Y, int32_t ldy, int32_t num_images, imf_stream_t stream);
 /* Y[C][L] = X[L][C]^T (fp32): token-major result -> the NCHW feature map ImageEncoder.forward returns. */
 int imf_transpose_tokens(const float* X, int32_t L, int32_t C, float* Y, imf_stream_t stream);
 

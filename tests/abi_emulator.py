@@ -321,6 +321,16 @@ class Emulator:
                 m = np.maximum(m, P[ky:ky + stride * Hout:stride, kx:kx + stride * Wout:stride])
         mat(Y, Hout * Wout, C, ldy // 2)[:] = m.reshape(-1, C)
 
+    def do_imf_image_im2col_h2_batch(self, image, C, H, W, K, stride, pad, Kpad, Y, ldy, B):
+        Hout, Wout = (H + 2 * pad - K) // stride + 1, (W + 2 * pad - K) // stride + 1
+        for b in range(B):
+            self.do_imf_image_im2col_h2(image + 4 * b * C * H * W, C, H, W, K, stride, pad, Kpad, Y + 2 * b * Hout * Wout * ldy, ldy)
+
+    def do_imf_image_maxpool_h2_batch(self, X, ldx, kc, C, Hin, Win, K, stride, pad, Y, ldy, B):
+        Hout, Wout = (Hin + 2 * pad - K) // stride + 1, (Win + 2 * pad - K) // stride + 1
+        for b in range(B):
+            self.do_imf_image_maxpool_h2(X + 2 * b * Hin * Win * ldx, ldx, kc, C, Hin, Win, K, stride, pad, Y + 2 * b * Hout * Wout * ldy, ldy)
+
     # ---- attention fusion ----------------------------------------------------------------------------------------------
     def do_imf_attention_kv(self, w, tokens, L, channel_major, kv, ws, ws_bytes):
         assert not channel_major
