@@ -11,14 +11,16 @@
 //      so neighbour reads need no range checks; empty cells hold 0, which contributes nothing): a neighbour's feature becomes one
 //      4-byte load at a computed address -- no hash, no probe chain, no second gather through a row index -- and the K cells of an
 //      x-run are contiguous, so one warp instruction covers 32 / K whole runs (6 cache lines instead of 25 for K = 5).  The grid
-//      lives in the caller's workspace; when the boxes do not fit its budget (sparse outdoor scans at a fine voxel size) the same
-//      kernel probes the hash table and gathers the feature through the row index;
+//      lives in the caller's workspace (budget: 512 cells per voxel -- a 3 m room at 2.5 cm is ~200^3 cells for 50 k voxels; measured
+//      on B200: 341 us for conv1 of 10 x 50 k voxels against 1185 us through the hash); when the boxes do not fit the budget (sparse
+//      outdoor scans at a fine voxel size) the same kernel probes the hash table and gathers the feature through the row index;
 //   2. k_cf_expand writes E as an h2 matrix (fp16 hi/lo, K^3 padded to a multiple of 64 columns) + an identity "neighbour table";
 //   3. the persistent tcgen05 convolution kernel (sparse_conv_g4.cu) runs the product as a one-offset convolution over E, with the
 //      BatchNorm affine in its epilogue -- the accumulation over offsets happens in TMEM, not in a per-voxel loop.
 #include <cuda_fp16.h>
 
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -236,8 +238,9 @@ __global__ void __launch_bounds__(256) k_cf_expand(const float* __restrict__ X, 
 
 inline size_t r256(size_t b) { return (b + 255) / 256 * 256; }
 inline int cf_kp(int K) { return (K * K * K + 63) / 64 * 64; }
-inline long long cf_budget_cells(int n_max) {          // 64 cells per voxel, below 2^31 (k_cf_expand addresses cells with 32-bit indices)
-  const long long c = 64LL * (n_max > 0 ? n_max : 1) + (1 << 20);
+inline long long cf_budget_cells(int n_max) {          // cells per voxel (default 512; IMF_CF_CELLS_PER_VOXEL overrides), below 2^31 (k_cf_expand addresses cells with 32-bit indices)
+  static const long long per = [] { const char* e = getenv("IMF_CF_CELLS_PER_VOXEL"); const long long v = e ? atoll(e) : 0; return v > 0 ? v : 512LL; }();
+  const long long c = per * (n_max > 0 ? n_max : 1) + (1 << 20);
   return c < 2000000000LL ? c : 2000000000LL;
 }
 
@@ -267,7 +270,7 @@ extern "C" size_t imf_conv_first_tc_workspace_bytes(int32_t n_max, int32_t kerne
 // conv1 (+ folded BatchNorm) for ONE input channel through the tensor-core tier.  packed = imf_sparse_conv_h2_pack of the kernel
 // reshaped to ONE offset with K^3 (zero-padded to imf_conv_first_tc_columns) input channels; scale / shift as for imf_sparse_conv_g4_fwd.
 // coords carry the batch index in column 0 (< num_items); table / capacity = the hash table of the same coordinate set (fallback when
-// the items' bounding boxes exceed the workspace's dense-grid budget of 64 cells per voxel).  Y = h2 matrix (ldy halves, chunk kc_out).
+// the items' bounding boxes exceed the workspace's dense-grid budget of 512 cells per voxel).  Y = h2 matrix (ldy halves, chunk kc_out).
 extern "C" int imf_conv_first_tc_h2_fwd(const float* X, int32_t ldx, const void* packed, const int32_t* coords, const int32_t* n_dev,
                                         int32_t n_max, int32_t num_items, const void* table, long long capacity, int32_t kernel_size,
                                         int32_t Cout, const float* scale, const float* shift, int32_t relu, void* Y, int32_t ldy,

@@ -71,7 +71,70 @@ __global__ void __launch_bounds__(256) k_h2_unpack(const __half* __restrict__ H,
   X[(size_t)row * ldx + c] = __half2float(p[0]) + __half2float(p[KC]);
 }
 
+// h2 [n, C] -> fp32 rows, optionally divided by their L2 norm (model/resunet.py:228-231: F / ||F||_2, no epsilon); one warp per row,
+// C <= 128.  out_row (optional) scatters row i to Y[out_row[i]].
+__global__ void __launch_bounds__(256) k_h2_unpack_l2norm(const __half* __restrict__ H, int ldh, int n, int C, int KC, int normalize,
+                                                          const int* __restrict__ out_row, float* __restrict__ Y, int ldy,
+                                                          const int* __restrict__ n_ptr) {
+  if (n_ptr) { const int v = *n_ptr; n = v < n ? v : n; }
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float v[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = 0.f;
+    if (c < C) {
+      const __half* p = H + (size_t)row * ldh + (c / KC) * 2 * KC + (c % KC);
+      v[i] = __half2float(p[0]) + __half2float(p[KC]);
+      ss = fmaf(v[i], v[i], ss);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = normalize ? 1.0f / sqrtf(ss) : 1.0f;
+  float* y = Y + (size_t)(out_row ? __ldg(out_row + row) : row) * ldy;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) y[c] = v[i] * inv;
+  }
+}
+
+// identity "neighbour table" of a one-offset (1x1) convolution for imf_sparse_conv_g4_fwd: nbr_t[i] = i for i < n, -1 up to the next
+// 128-row boundary; tile_mask = 1 for tiles with rows
+__global__ void __launch_bounds__(256) k_identity_table(const int* __restrict__ n_ptr, int n_max, int* __restrict__ nbr_t, int ld_n,
+                                                        unsigned* __restrict__ tile_mask) {
+  int n = n_max;
+  if (n_ptr) { const int v = *n_ptr; n = v < n_max ? v : n_max; }
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= ld_n) return;
+  nbr_t[i] = i < n ? i : -1;
+  if ((i & 127) == 0) tile_mask[i >> 7] = i < n ? 1u : 0u;
+}
+
 }  // namespace
+
+extern "C" int imf_h2_unpack_l2norm(const void* H, int32_t ldh, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, int32_t normalize,
+                                    const int32_t* out_row, float* Y, int32_t ldy, cudaStream_t stream) {
+  IMF_CHECK_ARG(n >= 0 && C > 0 && C <= 128 && (KC == 32 || KC == 64) && C % KC == 0 && ldy >= C && ldh >= 2 * C);
+  if (n == 0) return IMF_OK;
+  IMF_CHECK_ARG(H != nullptr && Y != nullptr);
+  k_h2_unpack_l2norm<<<(n + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const __half*>(H), ldh, n, C, KC, normalize, out_row, Y, ldy, n_dev);
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
+}
+
+extern "C" int imf_identity_table(const int32_t* n_dev, int32_t n_max, int32_t* nbr_t, int32_t ld_n, uint32_t* tile_mask,
+                                  cudaStream_t stream) {
+  IMF_CHECK_ARG(n_max >= 0 && ld_n % 128 == 0 && ld_n >= n_max);
+  if (ld_n == 0) return IMF_OK;
+  IMF_CHECK_ARG(nbr_t != nullptr && tile_mask != nullptr);
+  k_identity_table<<<(ld_n + 255) / 256, 256, 0, stream>>>(n_dev, n_max, nbr_t, ld_n, tile_mask);
+  IMF_CHECK_LAUNCH();
+  return IMF_OK;
+}
 
 extern "C" int imf_h2_pack_n(const float* X, int32_t ldx, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, void* H, int32_t ldh,
                              int32_t* err, cudaStream_t stream);

@@ -97,6 +97,26 @@ class FusedPlan:
                 torch.cuda.current_stream().synchronize()          # w1 is a temporary
                 self.conv1_tc = (buf, (sc / wmul).contiguous(), sh)
         self.final_bias = None if m.final.bias is None else m.final.bias.detach().reshape(-1).contiguous()
+        # tail conv1_tr -> ReLU -> final (+ bias) as two one-offset convolutions on the tensor-core kernel (the captured plans then
+        # write the concatenation [decoder | skip] with 32-channel chunks throughout, so that it is ONE h2 matrix of chunk width 32)
+        self.tail_tc = None
+        c0, c1, c2 = m.conv1_tr.in_channels, m.conv1_tr.out_channels, m.final.out_channels
+        if (m.conv1_tr.kernel_volume == 1 and m.final.kernel_volume == 1 and c0 % 32 == 0 and c1 in (64, 128, 256) and c2 in (32, 64, 128)
+                and m.conv1_tr.bias is None and TR[2] % 32 == 0):
+            with torch.cuda.device(self.device):
+                st = torch.cuda.current_stream().cuda_stream
+                packs = []
+                for W, cin, cout, kci in ((m.conv1_tr.kernel, c0, c1, 32), (m.final.kernel, c1, c2, 64)):
+                    W = W.detach().reshape(1, cin, cout).contiguous()
+                    wmax = float(W.abs().max())
+                    wmul = 2.0 ** math.floor(math.log2(2048.0 / wmax)) if wmax > 0 else 1.0
+                    buf = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(1, cin, cout, kci)), dtype=torch.uint8, device=self.device)
+                    _lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), 1, cin, cout, kci, wmul, buf.data_ptr(), st))
+                    packs.append((buf, torch.full((cout,), 1.0 / wmul, dtype=torch.float32, device=self.device)))
+                torch.cuda.current_stream().synchronize()
+                zero1 = torch.zeros(c1, dtype=torch.float32, device=self.device)
+                bias2 = self.final_bias if self.final_bias is not None else torch.zeros(c2, dtype=torch.float32, device=self.device)
+                self.tail_tc = ((packs[0][0], packs[0][1], zero1), (packs[1][0], packs[1][1], bias2.float().contiguous()))
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         # split-mode workspace of the convolution kernel (its head holds arrival counters that must start, and are left, zero)
@@ -438,6 +458,10 @@ class GraphPlan:
         self.att_ws = torch.empty(max(self.att_ws_bytes, 1), **u8)
         self.conv_ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(max(max(CH[1:]), max(TR[1:]))))
         self.conv_ws = torch.zeros(self.conv_ws_bytes, **u8)          # head = arrival counters, zero on entry / left zero
+        self.ident = self.ident_mask = None
+        if fused.tail_tc is not None:
+            self.ident = torch.zeros(self.ldn, **i32)
+            self.ident_mask = torch.zeros(self.ldn // 128 + 1, **i32)
         self.cf_ws = None
         if fused.conv1_tc is not None:
             self.cf_ws_bytes = int(L.imf_conv_first_tc_workspace_bytes(rows, m.conv1.kernel_size))
@@ -558,6 +582,8 @@ class GraphPlan:
         ld1, ld2, ld4 = 2 * self.cat1.shape[1], 2 * self.cat2.shape[1], 2 * self.cat4.shape[1]
         s1, s2, s4 = self.cat1.data_ptr() + TR[2] * 4, self.cat2.data_ptr() + TR[3] * 4, self.cat4.data_ptr() + TR[4] * 4
         kc1a, kc1b = _kc(TR[2]), _kc(CH[1])
+        if f.tail_tc is not None:
+            kc1a = kc1b = 32          # the tail reads [decoder | skip] as one h2 matrix of chunk width 32
         kc2, kc4, k8 = _kc(TR[3], CH[2]), _kc(TR[4], CH[3]), _kc(CH[4])
         sc, sh = f.norm1
         tok = self._tl_begin("conv1", t_out=1, cin=m.conv1.in_channels, cout=CH[1], K=m.conv1.kernel_size ** 3, residual=False)
@@ -591,9 +617,24 @@ class GraphPlan:
         self._block(L, "block2_tr", self.h0.data_ptr(), 2 * TR[2], _kc(TR[2]), 1, TR[2], self.h1, self.cat1.data_ptr(), ld1, kc1a, s)
         # ---- tail ----
         tok = self._tl_begin("conv1_tr+final", t_out=1, cin=TR[2] + CH[1], mid=TR[1], cout=m.out_channels, K=1, residual=False)
-        _lib.check(L.imf_pointwise_tail_h2_fwd(self.cat1.data_ptr(), ld1, TR[2] + CH[1], TR[2], kc1a, kc1b, m.conv1_tr.kernel.data_ptr(),
-                                               TR[1], m.final.kernel.data_ptr(), _lib.ptr(f.final_bias), m.out_channels, self._n(1), rows,
-                                               1 if m.normalize_feature else 0, None, self.out.data_ptr(), m.out_channels, s))
+        if f.tail_tc is not None:
+            (p1, s1, z1), (p2, s2, b2) = f.tail_tc
+            c0, c1, c2 = TR[2] + CH[1], TR[1], m.out_channels
+            kmid, kout = _kc(c1), _kc(c2)
+            _lib.check(L.imf_identity_table(self._n(1), rows, self.ident.data_ptr(), self.ldn, self.ident_mask.data_ptr(), s))
+            # hidden = relu(cat1 . W1) -> h1 (free after block2_tr);  logits = hidden . W2 + b2 -> h0;  out = logits / ||logits||
+            _lib.check(L.imf_sparse_conv_g4_fwd(self.cat1.data_ptr(), ld1, 32, p1.data_ptr(), self.ident.data_ptr(), self.ldn,
+                                                self.ident_mask.data_ptr(), self._n(1), rows, 1, c0, c1, s1.data_ptr(), z1.data_ptr(), None, 0, 0,
+                                                1, self.h1.data_ptr(), 2 * c1, rows, kmid, None, 0, self.err.data_ptr(), s))
+            _lib.check(L.imf_sparse_conv_g4_fwd(self.h1.data_ptr(), 2 * c1, kmid, p2.data_ptr(), self.ident.data_ptr(), self.ldn,
+                                                self.ident_mask.data_ptr(), self._n(1), rows, 1, c1, c2, s2.data_ptr(), b2.data_ptr(), None, 0, 0,
+                                                0, self.h0.data_ptr(), 2 * c2, rows, kout, None, 0, self.err.data_ptr(), s))
+            _lib.check(L.imf_h2_unpack_l2norm(self.h0.data_ptr(), 2 * c2, rows, self._n(1), c2, kout, 1 if m.normalize_feature else 0, None,
+                                              self.out.data_ptr(), c2, s))
+        else:
+            _lib.check(L.imf_pointwise_tail_h2_fwd(self.cat1.data_ptr(), ld1, TR[2] + CH[1], TR[2], kc1a, kc1b, m.conv1_tr.kernel.data_ptr(),
+                                                   TR[1], m.final.kernel.data_ptr(), _lib.ptr(f.final_bias), m.out_channels, self._n(1), rows,
+                                                   1 if m.normalize_feature else 0, None, self.out.data_ptr(), m.out_channels, s))
         self._tl_end(tok)
 
     def _enqueue_image(self, m, main):

@@ -141,6 +141,15 @@ int imf_h2_pack_n(const float* X, int32_t ldx, int32_t n, const int32_t* n_dev, 
 int imf_h2_unpack_n(const void* H, int32_t ldh, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, float* X, int32_t ldx,
                     imf_stream_t stream);
 
+/* h2 [n, C] (C <= 128) -> fp32 rows, divided by their L2 norm when normalize != 0 (model/resunet.py:228-231, no epsilon); out_row
+ * (optional) scatters row i to Y[out_row[i]]. */
+int imf_h2_unpack_l2norm(const void* H, int32_t ldh, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, int32_t normalize,
+                         const int32_t* out_row, float* Y, int32_t ldy, imf_stream_t stream);
+/* Identity neighbour table (+ tile masks) that turns imf_sparse_conv_g4_fwd with kernel_volume = 1 into a 1x1 convolution / dense
+ * product over the rows [0, min(*n_dev, n_max)): nbr_t[i] = i, -1 from n up to the next 128-row boundary.  ld_n % 128 == 0, >= n_max;
+ * tile_mask holds ld_n / 128 + 1 words. */
+int imf_identity_table(const int32_t* n_dev, int32_t n_max, int32_t* nbr_t, int32_t ld_n, uint32_t* tile_mask, imf_stream_t stream);
+
 /* Weights W[K^3,Cin,Cout] * wmul (a power of two that brings max|W| near 2^11; fold 1/wmul into `scale`) packed for the
  * input chunk width kc_in (consumed by imf_sparse_conv_g4_fwd). */
 size_t imf_sparse_conv_h2_packed_bytes(int32_t kernel_volume, int32_t Cin, int32_t Cout, int32_t kc_in);
@@ -187,7 +196,7 @@ int imf_conv_first_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W,
 
 /* conv1 with ONE input channel on the tensor cores (csrc/conv_first_tc.cu): the K^3 neighbour features of every voxel are laid out as
  * a row of an h2 matrix E[n, KP] (KP = imf_conv_first_tc_columns(K) = K^3 rounded up to 64; neighbours found through a dense row-index
- * grid over every batch item's bounding box, or through the hash table when the boxes exceed the workspace's budget of 64 cells per
+ * grid over every batch item's bounding box, or through the hash table when the boxes exceed the workspace's budget of 512 cells per
  * voxel), then Y = act((E . W) * scale + shift) runs as a one-offset convolution in imf_sparse_conv_g4_fwd.
  * packed = imf_sparse_conv_h2_pack(W', 1, KP, Cout, 64, wmul) with W'[0, k, :] = kernel[k, 0, :] (rows >= K^3 zero); scale already
  * divided by wmul.  coords column 0 = batch item (< num_items <= 256; other rows fall back to the hash probe).  workspace: 256-byte

@@ -187,6 +187,22 @@ class Emulator:
     def do_imf_h2_pack(self, X, ldx, n, C, KC, H, ldh, err):
         self.do_imf_h2_pack_n(X, ldx, n, None, C, KC, H, ldh, err)
 
+    def do_imf_h2_unpack_l2norm(self, H, ldh, n, n_dev, C, KC, normalize, out_row, Y, ldy):
+        m = count(n_dev, n)
+        x = mat(H, m, C, ldh // 2).copy()
+        if normalize:
+            x = x / np.sqrt((x * x).sum(axis=1, keepdims=True))
+        rows = vec(out_row, m, np.int32).astype(np.int64) if out_row else np.arange(m)
+        mat(Y, int(rows.max()) + 1 if m else 0, C, ldy)[rows] = x
+
+    def do_imf_identity_table(self, n_dev, n_max, nbr_t, ld_n, tile_mask):
+        n = count(n_dev, n_max)
+        t = vec(nbr_t, ld_n, np.int32)
+        t[:] = -1
+        t[:n] = np.arange(n, dtype=np.int32)
+        vec(tile_mask, ld_n // 128 + 1, np.uint32)[:] = 0
+        vec(tile_mask, (n + 127) // 128, np.uint32)[:] = 1
+
     # ---- convolutions --------------------------------------------------------------------------------------------------
     def do_imf_sparse_conv_h2_pack(self, W, K3, Cin, Cout, kc_in, wmul, packed):
         self.packed[packed] = (vec(W, K3 * Cin * Cout).reshape(K3, Cin, Cout).copy() * np.float32(wmul))
