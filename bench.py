@@ -256,7 +256,8 @@ def run_ours(args, rank, world, local_rank):
     dev_frags = [(c.to(dev), f.to(dev), im.to(dev)) for c, f, im in frags]
     pin_frags = [(c.pin_memory(), f.pin_memory(), im.pin_memory()) for c, f, im in frags]
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    K = 2 * B                                            # fragments per step: two groups, one captured plan + stream each
+    G = max(2, args.plans)                               # groups per step, one captured plan + stream each
+    K = G * B                                            # fragments per step
     host_outs = [torch.empty((target, 32), dtype=torch.float32).pin_memory() for _ in range(K)]
     match = args.config == "C4"
     gen = torch.Generator().manual_seed(rank)
@@ -284,15 +285,15 @@ def run_ours(args, rank, world, local_rank):
         return out
 
     def step_resident(i):
-        outs = model.forward_batches(pick(dev_frags, i), B, streams=2)
+        outs = model.forward_batches(pick(dev_frags, i), B, streams=args.plans)
         return match_pairs(outs) if match else outs
 
     def step_e2e(i):
         if not match:          # the public end-to-end call: pinned host fragments in, pinned host descriptors out
-            return model.forward_batches(pick(pin_frags, i), B, streams=2, out=host_outs)
+            return model.forward_batches(pick(pin_frags, i), B, streams=args.plans, out=host_outs)
         # pairs: the descriptors are also needed on the device for the matching, so the copies are issued here
         up = [(c.to(dev, non_blocking=True), f.to(dev, non_blocking=True), im.to(dev, non_blocking=True)) for c, f, im in pick(pin_frags, i)]
-        outs = model.forward_batches(up, B, streams=2)
+        outs = model.forward_batches(up, B, streams=args.plans)
         for o, h in zip(outs, host_outs):
             h[: len(o)].copy_(o, non_blocking=True)
         res = match_pairs(outs)
@@ -383,12 +384,12 @@ def run_ours(args, rank, world, local_rank):
     h2d = K * (target * 16 + target * 4 + 3 * H * W * 4)
     d2h = K * target * 32 * 4 + (K // 2 * KEYPOINTS * 4 if match else 0)
     cfg = {"workload": workload_name(args.config, target, W, H), "fragments_per_step": K, "fragments_per_graph_replay": B,
-           "plans_in_flight": 2, "single_fragment_latency_ms": latency_ms, "distinct_fragments_per_rank": N_FRAGMENTS,
+           "plans_in_flight": args.plans, "single_fragment_latency_ms": latency_ms, "distinct_fragments_per_rank": N_FRAGMENTS,
            "l2": "flushed between steps (256 MiB write, outside the per-step CUDA events)",
            "timing": "sum of per-step CUDA-event times on the launching stream, max over ranks",
            "coordinate_maps": "rebuilt every step (cold), as the reference does per SparseTensor",
-           "execution": f"model.forward_batches: one captured CUDA graph replay per group of {B} fragments (device-side sizes), 2 groups per "
-                        "step, 2 plans in flight; the mode tests/test_gpu_batched.py checks against the oracle",
+           "execution": f"model.forward_batches: one captured CUDA graph replay per group of {B} fragments (device-side sizes), {G} groups per "
+                        f"step, {args.plans} plans in flight; the mode tests/test_gpu_batched.py checks against the oracle",
            "library": os.path.basename(_lib.lib_path()),
            "parallelism": f"fragments sharded over {world} GPU(s), no data-path collective",
            "host_cores_of_rank0": getattr(args, "cores", None)}
@@ -416,6 +417,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="fragments per captured-graph replay (0 = the workload's default: C2 10, C3 4, C5 2, C4 8)")
+    ap.add_argument("--plans", type=int, default=2, help="captured plans (CUDA streams) in flight: the copies / latency-bound phases of one group overlap the others")
     ap.add_argument("--profile", action="store_true",
                     help="only warm-up + resident steps, the steps between cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()

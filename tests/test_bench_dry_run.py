@@ -51,7 +51,7 @@ def bench(emu, monkeypatch):  # noqa: F811
 
 
 def run(b, **over):
-    args = types.SimpleNamespace(config="C2", batch=0, steps=1, warmup=1, profile=False, gpus=1)
+    args = types.SimpleNamespace(config="C2", batch=0, steps=1, warmup=1, profile=False, gpus=1, plans=2)
     for k, v in over.items():
         setattr(args, k, v)
     buf = io.StringIO()
