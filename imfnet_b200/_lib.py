@@ -26,6 +26,10 @@ class AttnWeights(C.Structure):
                                   "w1", "b1", "w2", "b2")] + [("latent", _i32), ("dim", _i32), ("inner", _i32)]
 
 
+class AttnPacked(C.Structure):
+    _fields_ = [(n, _p) for n in ("wq", "wkv", "wo", "w1", "w2")] + [(n, _f32) for n in ("mq", "mkv", "mo", "m1", "m2")]
+
+
 # name -> (restype, argtypes); mirrors include/imfnet_b200.h one to one (tests/test_abi.py checks the header).
 SIGNATURES = {
     "imf_last_error": (C.c_char_p, []),
@@ -79,6 +83,8 @@ SIGNATURES = {
     "imf_transpose_tokens": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "imf_nn_search_workspace_bytes": (_sz, [_i32]),
     "imf_nn_search": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
+    "imf_nn_search_tc_workspace_bytes": (_sz, [_i32, _i32]),
+    "imf_nn_search_tc": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
     "imf_linear_fwd": (C.c_int, [_p, _i32, _p, _p, _i32, _i32, _i32, _p, _i32, _p]),
     "imf_tc_gemm_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "imf_tc_gemm": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _i32, _i32, _i32, _f32, _p, _p, _i32, _i32, _p, _sz, _p, _p]),
@@ -88,9 +94,11 @@ SIGNATURES = {
     "imf_attention_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "imf_attention_kv_batched_bytes": (_sz, [_i32, _i32]),
     "imf_attention_kv_batched_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
-    "imf_attention_kv_batched": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _p, _sz, _p, _p]),
+    "imf_attention_kv_batched": (C.c_int, [C.POINTER(AttnWeights), C.POINTER(AttnPacked), _p, _i32, _i32, _p, _p, _sz, _p, _p]),
     "imf_attention_batched_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
-    "imf_attention_fusion_fwd_batched": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _sz, _p, _p]),
+    "imf_attention_fusion_fwd_batched": (C.c_int, [C.POINTER(AttnWeights), C.POINTER(AttnPacked), _p, _i32, _i32, _p, _p, _p, _i32, _p, _i32, _p, _i32,
+                                                   _p, _sz, _p, _p]),
+    "imf_h2_gemm": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _i32, _f32, _p, _p, _i32, _i32, _p, _i32, _p, _p]),
     "imf_attention_fusion_fwd": (C.c_int, [C.POINTER(AttnWeights), _p, _i32, _i32, _p, _i32, _p, _i32, _p, _sz, _p]),
 }
 

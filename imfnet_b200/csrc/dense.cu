@@ -7,6 +7,8 @@
 //   x = W2 . geglu(W1 . LN(x) + b1) + b2 + x
 // Image tokens I arrive channel-major ([C, H*W], the NCHW feature map of the image encoder), so the context
 // LayerNorm also performs the [C,L] -> [L,C] transposition of resunet.py:259-261.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 // fused attention kernel (flash_fusion.cu), used when the head has 128 channels (the IMFNet configuration)
@@ -15,15 +17,22 @@ size_t imf_flash_workspace_bytes(int M_max, int L, int B);
 int imf_flash_pack_kv(const float* K, int ldk, const float* V, int ldv, int v_transposed, int L, int B, void* kvh2, cudaStream_t stream);
 int imf_flash_attention(const void* qh2, int M_max, const int* seg_dev, const int* cnt_dev, const int* m_dev, int B, const void* kvh2, int L,
                         float* o, int ldo, void* workspace, size_t workspace_bytes, int* err, cudaStream_t stream);
+int imf_flash_attention_h2(const void* qh2, int M_max, const int* seg_dev, const int* cnt_dev, const int* m_dev, int B, const void* kvh2, int L,
+                           void* o_h2, int ldo_h, void* workspace, size_t workspace_bytes, int* err, cudaStream_t stream);
 extern "C" int imf_h2_pack_n(const float* X, int32_t ldx, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, void* H, int32_t ldh,
                              int32_t* err, cudaStream_t stream);
+extern "C" int imf_h2_gemm(const void* A, int32_t lda, int32_t M_max, const int32_t* m_dev, const void* Wpacked, int32_t N, int32_t K,
+                           float alpha, const float* bias, const float* R, int32_t ldr, int32_t mode, void* C, int32_t ldc, int32_t* err,
+                           cudaStream_t stream);
 
 namespace {
 
 // ---- LayerNorm over the last dim of row-major rows; one warp per row, C <= 1024, C % 32 == 0 ----
+// Yh (optional): the result is written as an h2 matrix (fp16 hi/lo, chunk width 64, row stride ldy halves) instead of fp32 rows.
 __global__ void __launch_bounds__(256) k_layernorm_rows(const float* __restrict__ X, int ldx, int M, int C,
                                                         const float* __restrict__ g, const float* __restrict__ b, float eps,
-                                                        float* __restrict__ Y, int ldy, const int* __restrict__ m_ptr) {
+                                                        float* __restrict__ Y, int ldy, const int* __restrict__ m_ptr,
+                                                        __half* __restrict__ Yh = nullptr) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m_ptr) { const int v = *m_ptr; M = v < M ? v : M; }
   if (row >= M) return;
@@ -40,6 +49,20 @@ __global__ void __launch_bounds__(256) k_layernorm_rows(const float* __restrict_
   for (int i = 0; i < 32; ++i)
     if (i < per) { const float d = v[i] - mean; q += d * d; }
   const float rstd = 1.0f / sqrtf(imf_warp_sum(q) / (float)C + eps);
+  if (Yh) {
+    __half* yh = Yh + (size_t)row * ldy;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < per) {
+        const int c = i * 32 + lane;
+        const float o = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+        const __half h = __float2half_rn(o);
+        __half* p = yh + (c >> 6) * 128 + (c & 63);
+        p[0] = h;
+        p[64] = __float2half_rn(o - __half2float(h));
+      }
+    return;
+  }
   float* y = Y + (size_t)row * ldy;
 #pragma unroll
   for (int i = 0; i < 32; ++i)
@@ -284,9 +307,43 @@ extern "C" int imf_attention_fusion_fwd(const imf_attn_weights_t* w, const float
   return imf_attention_fusion_fwd_m(w, P, ldp, M, nullptr, kv, L, out, ldo, workspace, workspace_bytes, stream);
 }
 
+// Weights of the fusion module pre-packed for imf_h2_gemm (imf_sparse_conv_h2_pack of W^T as [1, K, N], chunk width 64), with the power-of-two
+// scales they were packed with; w1 with its value / gate rows interleaved per 128-column tile (tile t = [value 64t.. | gate 64t..]).
+struct imf_attn_packed_t {
+  const void *wq, *wkv, *wo, *w1, *w2;
+  float mq, mkv, mo, m1, m2;
+};
+
 namespace {
 
 constexpr float kLog2e = 1.4426950408889634f;
+
+// the h2 tier of the module body: LayerNorm writes fp16 hi/lo, every projection is a TMA-fed tcgen05 GEMM on pre-split operands
+// (h2_gemm.cu), q goes straight into the attention kernel and its output comes back as h2 for to_out
+int attention_body_h2(const imf_attn_weights_t* w, const imf_attn_packed_t* wp, const float* P, int ldp, int M, const int* m_dev,
+                      const int* seg_dev, const int* cnt_dev, int B, const void* kvh2, int L, float* out, int ldo, void* workspace, int* err,
+                      cudaStream_t stream) {
+  const int latent = w->latent, inner = w->inner;
+  char* ws = reinterpret_cast<char*>(workspace);
+  __half* xn = reinterpret_cast<__half*>(ws);  ws += r256((size_t)M * latent * 4);
+  __half* q = reinterpret_cast<__half*>(ws);   ws += r256((size_t)M * inner * 4);
+  __half* o = reinterpret_cast<__half*>(ws);   ws += r256((size_t)M * inner * 4);
+  float* x1 = reinterpret_cast<float*>(ws);    ws += r256((size_t)M * latent * 4);
+  __half* hid = reinterpret_cast<__half*>(ws); ws += r256((size_t)M * latent * 4 * 4);
+  ws += r256(imf_tc_gemm_workspace_bytes(M, latent, 0)) + r256((size_t)M * inner * 4);          // (regions of the 3xTF32 tier, unused here)
+  void* fws = ws;
+  const float sm_scale = 1.0f / sqrtf((float)inner);
+  int rc;
+  k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(P, ldp, M, latent, w->ln_q_w, w->ln_q_b, 1e-5f, nullptr, 2 * latent, m_dev, xn);
+  IMF_CHECK_LAUNCH();
+  if ((rc = imf_h2_gemm(xn, 2 * latent, M, m_dev, wp->wq, inner, latent, sm_scale * kLog2e / wp->mq, nullptr, nullptr, 0, 1, q, 2 * inner, err, stream))) return rc;
+  if ((rc = imf_flash_attention_h2(q, M, seg_dev, cnt_dev, m_dev, B, kvh2, L, o, 2 * inner, fws, imf_flash_workspace_bytes(M, L, B), err, stream))) return rc;
+  if ((rc = imf_h2_gemm(o, 2 * inner, M, m_dev, wp->wo, latent, inner, 1.f / wp->mo, w->bo, P, ldp, 0, x1, latent, err, stream))) return rc;
+  k_layernorm_rows<<<(M + 7) / 8, 256, 0, stream>>>(x1, latent, M, latent, w->ln_f_w, w->ln_f_b, 1e-5f, nullptr, 2 * latent, m_dev, xn);
+  IMF_CHECK_LAUNCH();
+  if ((rc = imf_h2_gemm(xn, 2 * latent, M, m_dev, wp->w1, 8 * latent, latent, 1.f / wp->m1, w->b1, nullptr, 0, 2, hid, 2 * 4 * latent, err, stream))) return rc;
+  return imf_h2_gemm(hid, 2 * 4 * latent, M, m_dev, wp->w2, latent, 4 * latent, 1.f / wp->m2, w->b2, x1, latent, 0, out, ldo, err, stream);
+}
 
 // The module body for M_max rows (min(*m_dev, M_max) of them valid) that belong to B batch items: everything except the attention
 // core is row-wise (LayerNorm, projections, GEGLU feed-forward), so ALL items go through ONE chain of launches; only the attention
@@ -366,18 +423,25 @@ extern "C" size_t imf_attention_kv_batched_workspace_bytes(int32_t L, int32_t di
 }
 // tokens [B*L, dim] row-major (image b = rows [b*L, (b+1)*L)) -> kv = fp16 hi/lo {K, V^T} per image, with
 // [K | V] = LN_c(tokens) . Wkv^T as ONE GEMM over all images.  inner must be 128 (the IMFNet head).
-extern "C" int imf_attention_kv_batched(const imf_attn_weights_t* w, const float* tokens, int32_t L, int32_t B, void* kv, void* workspace,
-                                        size_t workspace_bytes, int32_t* err, cudaStream_t stream) {
+extern "C" int imf_attention_kv_batched(const imf_attn_weights_t* w, const imf_attn_packed_t* wp, const float* tokens, int32_t L, int32_t B,
+                                        void* kv, void* workspace, size_t workspace_bytes, int32_t* err, cudaStream_t stream) {
   IMF_CHECK_ARG(w != nullptr && L >= 1 && B >= 1 && B <= 256 && w->dim % 32 == 0 && w->dim <= 1024 && w->inner == 128);
   IMF_CHECK_ARG(tokens != nullptr && kv != nullptr && workspace != nullptr);
   IMF_CHECK_ARG(workspace_bytes >= imf_attention_kv_batched_workspace_bytes(L, w->dim, w->inner, B));
   const int n = B * L, dim = w->dim, inner = w->inner;
   float* cn = reinterpret_cast<float*>(workspace);
   float* KV = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + r256((size_t)n * dim * 4));
-  k_layernorm_rows<<<(n + 7) / 8, 256, 0, stream>>>(tokens, dim, n, dim, w->ln_c_w, w->ln_c_b, 1e-5f, cn, dim, nullptr);
-  IMF_CHECK_LAUNCH();
   int rc;
-  if ((rc = imf_tc_gemm(cn, dim, w->wkv, dim, KV, 2 * inner, n, 2 * inner, dim, 1.f, nullptr, nullptr, 0, 0, nullptr, 0, err, stream))) return rc;
+  if (wp != nullptr && dim % 64 == 0) {          // h2 tier: LayerNorm writes fp16 hi/lo, the projection is a TMA-fed tcgen05 GEMM
+    k_layernorm_rows<<<(n + 7) / 8, 256, 0, stream>>>(tokens, dim, n, dim, w->ln_c_w, w->ln_c_b, 1e-5f, nullptr, 2 * dim, nullptr,
+                                                      reinterpret_cast<__half*>(cn));
+    IMF_CHECK_LAUNCH();
+    if ((rc = imf_h2_gemm(cn, 2 * dim, n, nullptr, wp->wkv, 2 * inner, dim, 1.f / wp->mkv, nullptr, nullptr, 0, 0, KV, 2 * inner, err, stream))) return rc;
+  } else {
+    k_layernorm_rows<<<(n + 7) / 8, 256, 0, stream>>>(tokens, dim, n, dim, w->ln_c_w, w->ln_c_b, 1e-5f, cn, dim, nullptr);
+    IMF_CHECK_LAUNCH();
+    if ((rc = imf_tc_gemm(cn, dim, w->wkv, dim, KV, 2 * inner, n, 2 * inner, dim, 1.f, nullptr, nullptr, 0, 0, nullptr, 0, err, stream))) return rc;
+  }
   return imf_flash_pack_kv(KV, 2 * inner, KV + inner, 2 * inner, 0, L, B, kv, stream);
 }
 
@@ -389,9 +453,9 @@ extern "C" size_t imf_attention_batched_workspace_bytes(int32_t M, int32_t L, in
 // out[row] for the rows [seg[b], seg[b] + cnt[b]) of every item b < B of P [M, latent] (M = capacity; *m_dev = rows in use = the end of
 // the last item): one LayerNorm / projection / feed-forward chain over all rows + one attention launch over all items.
 // err (optional device int): in-kernel watchdog codes and the fp16-range flag of the query pack (bit 16).
-extern "C" int imf_attention_fusion_fwd_batched(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const int32_t* m_dev,
-                                                const int32_t* seg_dev, const int32_t* cnt_dev, int32_t B, const void* kv, int32_t L,
-                                                float* out, int32_t ldo, void* workspace, size_t workspace_bytes, int32_t* err,
+extern "C" int imf_attention_fusion_fwd_batched(const imf_attn_weights_t* w, const imf_attn_packed_t* wp, const float* P, int32_t ldp, int32_t M,
+                                                const int32_t* m_dev, const int32_t* seg_dev, const int32_t* cnt_dev, int32_t B, const void* kv,
+                                                int32_t L, float* out, int32_t ldo, void* workspace, size_t workspace_bytes, int32_t* err,
                                                 cudaStream_t stream) {
   IMF_CHECK_ARG(w != nullptr && M >= 0 && L >= 1 && B >= 1 && B <= 256);
   IMF_CHECK_ARG(w->latent % 32 == 0 && w->latent <= 1024 && w->inner == 128);
@@ -399,6 +463,8 @@ extern "C" int imf_attention_fusion_fwd_batched(const imf_attn_weights_t* w, con
   IMF_CHECK_ARG(P != nullptr && kv != nullptr && out != nullptr && workspace != nullptr && ldp >= w->latent && ldo >= w->latent);
   IMF_CHECK_ARG(seg_dev != nullptr && cnt_dev != nullptr);
   IMF_CHECK_ARG(workspace_bytes >= imf_attention_batched_workspace_bytes(M, L, w->latent, w->inner, B));
+  if (wp != nullptr && w->latent % 128 == 0 && ldp % 4 == 0 && ldo % 4 == 0)
+    return attention_body_h2(w, wp, P, ldp, M, m_dev, seg_dev, cnt_dev, B, kv, L, out, ldo, workspace, err, stream);
   return attention_body(w, P, ldp, M, m_dev, seg_dev, cnt_dev, B, nullptr, kv, L, out, ldo, workspace, err, stream);
 }
 

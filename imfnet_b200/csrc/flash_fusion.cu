@@ -436,7 +436,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // is recomputed from the same quantities the attention kernel used.
 __global__ void __launch_bounds__(256) k_flash_combine(const float* __restrict__ Opart, const float* __restrict__ ml, const int* __restrict__ seg,
                                                        const int* __restrict__ cnt, const int* __restrict__ m_ptr, int B, int M_max, int L,
-                                                       int grid_att, float* __restrict__ out, int ldo) {
+                                                       int grid_att, float* __restrict__ out, int ldo, __half* __restrict__ out_h) {
   const int nb = (L + kTB - 1) / kTB;
   long long T = 0;
   for (int b = 0; b < B; ++b) T += (ff_item_rows(seg, cnt, m_ptr, M_max, b) + kTQ - 1) / kTQ;
@@ -474,6 +474,17 @@ __global__ void __launch_bounds__(256) k_flash_combine(const float* __restrict__
       acc.x = fmaf(wgt, o.x, acc.x); acc.y = fmaf(wgt, o.y, acc.y); acc.z = fmaf(wgt, o.z, acc.z); acc.w = fmaf(wgt, o.w, acc.w);
     }
     const float inv = 1.0f / den;
+    if (out_h) {          // h2 output (chunk width 64, ldo in halves): the operand of the to_out GEMM
+      const float v[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
+      const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+      const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn(v[0] - b01.x, v[1] - b01.y), l23 = __floats2half2_rn(v[2] - b23.x, v[3] - b23.y);
+      const int c = lane * 4;
+      __half* p = out_h + (size_t)row * ldo + (c >> 6) * 128 + (c & 63);
+      *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const unsigned*>(&h01), *reinterpret_cast<const unsigned*>(&h23));
+      *reinterpret_cast<uint2*>(p + 64) = make_uint2(*reinterpret_cast<const unsigned*>(&l01), *reinterpret_cast<const unsigned*>(&l23));
+      return;
+    }
     *reinterpret_cast<float4*>(out + (size_t)row * ldo + lane * 4) = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
   }
 }
@@ -515,9 +526,21 @@ int imf_flash_pack_kv(const float* K, int ldk, const float* V, int ldv, int v_tr
 // o[row, 128] (fp32, row stride ldo) = softmax(q k_b^T) v_b for the rows [seg[b], seg[b] + cnt[b]) of every item b < B;
 // qh2 = h2 matrix of the queries [M_max, 256 halves], already scaled by log2(e) / sqrt(d).  seg / cnt == NULL: one item with
 // *m_dev (or M_max) rows starting at row 0.
+static int ff_run(const void* qh2, int M_max, const int* seg_dev, const int* cnt_dev, const int* m_dev, int B, const void* kvh2, int L, float* o,
+                  __half* o_h, int ldo, void* workspace, size_t workspace_bytes, int* err, cudaStream_t stream);
 int imf_flash_attention(const void* qh2, int M_max, const int* seg_dev, const int* cnt_dev, const int* m_dev, int B, const void* kvh2, int L,
                         float* o, int ldo, void* workspace, size_t workspace_bytes, int* err, cudaStream_t stream) {
-  IMF_CHECK_ARG(qh2 && kvh2 && o && workspace && M_max > 0 && L > 0 && B >= 1 && B <= kMaxItems);
+  return ff_run(qh2, M_max, seg_dev, cnt_dev, m_dev, B, kvh2, L, o, nullptr, ldo, workspace, workspace_bytes, err, stream);
+}
+// the same with the output written as an h2 matrix (chunk width 64, ldo_h halves)
+int imf_flash_attention_h2(const void* qh2, int M_max, const int* seg_dev, const int* cnt_dev, const int* m_dev, int B, const void* kvh2, int L,
+                           void* o_h2, int ldo_h, void* workspace, size_t workspace_bytes, int* err, cudaStream_t stream) {
+  return ff_run(qh2, M_max, seg_dev, cnt_dev, m_dev, B, kvh2, L, nullptr, reinterpret_cast<__half*>(o_h2), ldo_h, workspace, workspace_bytes, err,
+                stream);
+}
+static int ff_run(const void* qh2, int M_max, const int* seg_dev, const int* cnt_dev, const int* m_dev, int B, const void* kvh2, int L, float* o,
+                  __half* o_h, int ldo, void* workspace, size_t workspace_bytes, int* err, cudaStream_t stream) {
+  IMF_CHECK_ARG(qh2 && kvh2 && (o || o_h) && workspace && M_max > 0 && L > 0 && B >= 1 && B <= kMaxItems);
   IMF_CHECK_ARG((seg_dev == nullptr) == (cnt_dev == nullptr) && (cnt_dev != nullptr || B == 1));
   IMF_CHECK_ARG(workspace_bytes >= imf_flash_workspace_bytes(M_max, L, B));
   const int Lpad = ff_lpad(L);
@@ -535,7 +558,7 @@ int imf_flash_attention(const void* qh2, int M_max, const int* seg_dev, const in
   IMF_CHECK_CUDA(imf_set_max_smem_once(reinterpret_cast<const void*>(&k_flash_fusion), kSmem + 1024));
   k_flash_fusion<<<grid, kThreads, kSmem + 1024, stream>>>(tmQ, tmK, tmV, seg_dev, cnt_dev, m_dev, B, M_max, L, Lpad, Opart, ml, err);
   IMF_CHECK_LAUNCH();
-  k_flash_combine<<<dim3(ff_tiles_max(M_max, B), kTQ / 8), 256, 0, stream>>>(Opart, ml, seg_dev, cnt_dev, m_dev, B, M_max, L, grid, o, ldo);
+  k_flash_combine<<<dim3(ff_tiles_max(M_max, B), kTQ / 8), 256, 0, stream>>>(Opart, ml, seg_dev, cnt_dev, m_dev, B, M_max, L, grid, o, ldo, o_h);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }

@@ -178,7 +178,7 @@ extern "C" size_t imf_sparse_conv_h2_packed_bytes(int32_t kernel_volume, int32_t
 extern "C" int imf_sparse_conv_h2_pack(const float* W, int32_t kernel_volume, int32_t Cin, int32_t Cout, int32_t kc_in, float wmul,
                                        void* packed, cudaStream_t stream) {
   IMF_CHECK_ARG(W != nullptr && packed != nullptr && kernel_volume >= 1 && (kc_in == 32 || kc_in == 64) && Cin > 0 && Cin % kc_in == 0);
-  IMF_CHECK_ARG(Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256);
+  IMF_CHECK_ARG(Cout == 32 || Cout == 64 || (Cout >= 128 && Cout % 128 == 0));          // (tiles of min(Cout, 128) output channels)
   IMF_CHECK_ARG(wmul > 0.f);
   const long long total = (long long)kernel_volume * Cin * Cout;
   k_pack_conv_weights_h2<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(W, kernel_volume, Cin, Cout, kc_in, h2_bn(Cout), wmul,

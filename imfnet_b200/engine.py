@@ -645,7 +645,7 @@ class GraphPlan:
         side.wait_stream(main)
         with torch.cuda.stream(side):
             tokens = self.image_plan.enqueue(self.image if self.B > 1 else self.image[0])
-            _lib.check(L.imf_attention_kv_batched(m.attention_fusion.packed(), tokens.data_ptr(), self.n_tok, self.B, self.kv.data_ptr(),
+            _lib.check(L.imf_attention_kv_batched(m.attention_fusion.packed(), m.attention_fusion.packed_h2(), tokens.data_ptr(), self.n_tok, self.B, self.kv.data_ptr(),
                                                   self.kv_ws.data_ptr(), self.kv_ws_bytes, self.err.data_ptr(), side.cuda_stream))
 
     def _enqueue_fusion(self, L, m, C8, k8, main, s):
@@ -656,7 +656,7 @@ class GraphPlan:
                                           self.cnt.data_ptr(), self.err.data_ptr(), s))
         _lib.check(L.imf_h2_unpack_n(self.d2.data_ptr(), 2 * C8, self.cap8, self._n(8), C8, k8, self.P8.data_ptr(), C8, s))
         main.wait_stream(self.side)
-        _lib.check(L.imf_attention_fusion_fwd_batched(af.packed(), self.P8.data_ptr(), C8, self.cap8, self._n(8), self.seg.data_ptr(),
+        _lib.check(L.imf_attention_fusion_fwd_batched(af.packed(), af.packed_h2(), self.P8.data_ptr(), C8, self.cap8, self._n(8), self.seg.data_ptr(),
                                                       self.cnt.data_ptr(), self.B, self.kv.data_ptr(), self.n_tok, self.fused32.data_ptr(), C8,
                                                       self.att_ws.data_ptr(), self.att_ws_bytes, self.err.data_ptr(), s))
         _lib.check(L.imf_h2_pack_n(self.fused32.data_ptr(), C8, self.cap8, self._n(8), C8, k8, self.fused.data_ptr(), 2 * C8,

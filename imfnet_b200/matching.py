@@ -3,7 +3,9 @@
 Host mirror of the two reference entry points that do nearest-neighbour search in descriptor space:
   find_nn_gpu(F0, F1, nn_max_n=-1, return_distance=False, dist_type='SquareL2')      /root/reference/lib/eval.py:18-48
   mutual_nn(frag1_descs, frag2_descs)    = the two uio.knn_search calls + mutual check  scripts/evaluation_3dmatch.py:207-217
-Both run imf_nn_search (csrc/matching.cu): exact brute force in fp32, first index wins ties.  No CPU fallback.
+Both run imf_nn_search_tc (csrc/matching_tc.cu: the 5000 x 5000 x 32 distance matrix as a tcgen05 product that filters the candidates,
+which are then re-evaluated exactly) for 16- / 32-channel descriptors and imf_nn_search (csrc/matching.cu: brute force in fp32) otherwise;
+both give the same indices and distances bit for bit, first index wins ties.  No CPU fallback.
 """
 from __future__ import annotations
 
@@ -13,8 +15,9 @@ import torch
 from . import _lib
 
 
-def nn_search(A: torch.Tensor, B: torch.Tensor, return_distance: bool = False):
-    """idx[i] = argmin_j ||A[i] - B[j]||^2 (int32 on A's device); optionally the squared distances."""
+def nn_search(A: torch.Tensor, B: torch.Tensor, return_distance: bool = False, tensor_cores: bool = True):
+    """idx[i] = argmin_j ||A[i] - B[j]||^2 (int32 on A's device); optionally the squared distances.
+    tensor_cores=False forces the brute-force kernel (the two are bit-identical; tests compare them)."""
     _lib.require_cuda(A, "descriptors")
     if B.device != A.device:
         raise RuntimeError("both descriptor sets must live on the same CUDA device")
@@ -29,10 +32,12 @@ def nn_search(A: torch.Tensor, B: torch.Tensor, return_distance: bool = False):
     na, nb = A.shape[0], B.shape[0]
     idx = torch.empty(na, dtype=torch.int32, device=A.device)
     d2 = torch.empty(na, dtype=torch.float32, device=A.device) if return_distance else None
-    ws_bytes = int(L.imf_nn_search_workspace_bytes(na))
+    tc = tensor_cores and A.shape[1] in (16, 32)
+    ws_bytes = int(L.imf_nn_search_tc_workspace_bytes(na, nb) if tc else L.imf_nn_search_workspace_bytes(na))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=A.device)
     with torch.cuda.device(A.device):
-        _lib.check(L.imf_nn_search(_lib.ptr(A), A.stride(0) if na else A.shape[1], na, _lib.ptr(B), B.stride(0) if nb else B.shape[1], nb,
+        fn = L.imf_nn_search_tc if tc else L.imf_nn_search
+        _lib.check(fn(_lib.ptr(A), A.stride(0) if na else A.shape[1], na, _lib.ptr(B), B.stride(0) if nb else B.shape[1], nb,
                                    A.shape[1], _lib.ptr(idx), _lib.ptr(d2), _lib.ptr(ws), ws_bytes, _lib.cur_stream()))
     return (idx, d2) if return_distance else idx
 

@@ -75,8 +75,49 @@ class AttentionFusion(nn.Module):
             self._packed = (key, w, keep)
         return self._packed[1]
 
+    def packed_h2(self):
+        """The module's matrices pre-packed for the fp16 hi/lo tensor-core GEMM (imf_h2_gemm): W^T as a one-offset "convolution kernel"
+        [1, K, N] through imf_sparse_conv_h2_pack, scaled by a power of two into fp16 range; net.0 with its value / gate rows interleaved
+        per 128-column tile so that the GEGLU product is an epilogue.  None when the shapes do not fit that kernel."""
+        import math
+        self.packed()
+        key = self._packed[0]
+        hit = getattr(self, "_packed_h2", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        ca, ff = self.cross_attend_blocks
+        lat, inner, dim = self.latent_dim, self.inner, self.dim
+        ok = inner == 128 and lat % 128 == 0 and dim % 64 == 0
+        w = None
+        keep = []
+        if ok:
+            L = _lib.lib()
+            dev = ca.fn.to_q.weight.device
+
+            def pk(Wt):          # Wt [N, K] (a Linear weight) -> packed slabs + scale
+                N, K = Wt.shape
+                W = Wt.detach().float().t().contiguous().reshape(1, K, N)
+                wmax = float(W.abs().max())
+                wmul = 2.0 ** math.floor(math.log2(2048.0 / wmax)) if wmax > 0 else 1.0
+                buf = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(1, K, N, 64)), dtype=torch.uint8, device=dev)
+                with torch.cuda.device(dev):
+                    _lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), 1, K, N, 64, wmul, buf.data_ptr(), _lib.cur_stream()))
+                    torch.cuda.current_stream().synchronize()          # W is a temporary
+                keep.append(buf)
+                return buf.data_ptr(), wmul
+
+            w1 = ff.fn.net[0].weight.detach()
+            half = w1.shape[0] // 2
+            w1i = torch.stack([w1[:half].reshape(half // 64, 64, -1), w1[half:].reshape(half // 64, 64, -1)], dim=1).reshape(2 * half, -1)
+            (q, mq), (kv, mkv), (o, mo), (a1, m1), (a2, m2) = (pk(ca.fn.to_q.weight), pk(ca.fn.to_kv.weight), pk(ca.fn.to_out.weight), pk(w1i),
+                                                                pk(ff.fn.net[2].weight))
+            w = _lib.AttnPacked(q, kv, o, a1, a2, mq, mkv, mo, m1, m2)
+        self._packed_h2 = (key, w, keep)
+        return w
+
     def _apply(self, fn, *a, **k):
         self._packed = None
+        self._packed_h2 = None
         return super()._apply(fn, *a, **k)
 
     # -- kernels ---------------------------------------------------------------------------------

@@ -303,6 +303,13 @@ int imf_attention_fusion_fwd(const imf_attn_weights_t* w, const float* P, int32_
 size_t imf_nn_search_workspace_bytes(int32_t na);
 int imf_nn_search(const float* A, int32_t lda, int32_t na, const float* B, int32_t ldb, int32_t nb, int32_t C, int32_t* idx, float* d2,
                   void* workspace, size_t workspace_bytes, imf_stream_t stream);
+/* The same search with the distance matrix on the tensor cores (csrc/matching_tc.cu): a tcgen05 product on fp16 hi/lo operands
+ * filters, per query, the candidates within a proven error margin of the minimum; those (one or two) are re-evaluated exactly as
+ * imf_nn_search does, so idx / d2 are identical to imf_nn_search bit for bit, ties included.  C in {16, 32}; workspace 256-byte
+ * aligned, imf_nn_search_tc_workspace_bytes(na, nb). */
+size_t imf_nn_search_tc_workspace_bytes(int32_t na, int32_t nb);
+int imf_nn_search_tc(const float* A, int32_t lda, int32_t na, const float* B, int32_t ldb, int32_t nb, int32_t C, int32_t* idx, float* d2,
+                     void* workspace, size_t workspace_bytes, imf_stream_t stream);
 
 /* imf_attention_fusion_fwd with an optional device-side token count (min(*m_dev, M) rows; M sizes launches and workspace). */
 int imf_attention_fusion_fwd_m(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const int32_t* m_dev, const float* kv,
@@ -315,15 +322,30 @@ int imf_attention_fusion_fwd_m(const imf_attn_weights_t* w, const float* P, int3
  * Requires the IMFNet head (inner == 128).
  *   imf_attention_kv_batched: tokens [B*L, dim] row-major (image b = rows [b*L, (b+1)*L)) -> kv (opaque: fp16 hi/lo K and V^T per image);
  *   imf_attention_fusion_fwd_batched: P [M, latent] (M = row capacity, min(*m_dev, M) rows in use) -> out, rows outside every item's
- *     range untouched.  err (optional device int32): watchdog codes, bit 16 = a query left the fp16 range. */
+ *     range untouched.  err (optional device int32): watchdog codes, bit 16 = a query left the fp16 range.
+ *   wp (optional): the module's matrices pre-packed for imf_h2_gemm; with it LayerNorm writes fp16 hi/lo and every projection is a
+ *     TMA-fed tcgen05 GEMM on pre-split operands; NULL = the 3xTF32 GEMMs of imf_tc_gemm (same results to fp32 rounding). */
+typedef struct imf_attn_packed {
+  const void *wq, *wkv, *wo, *w1, *w2; /* imf_sparse_conv_h2_pack(W^T as [1, K, N], 1, K, N, 64, m*); w1: value / gate rows interleaved per
+                                          128-column tile (tile t = [value 64t..64t+63 | gate 64t..64t+63]) */
+  float mq, mkv, mo, m1, m2;           /* the power-of-two scales the matrices were packed with */
+} imf_attn_packed_t;
 size_t imf_attention_kv_batched_bytes(int32_t L, int32_t B);
 size_t imf_attention_kv_batched_workspace_bytes(int32_t L, int32_t dim, int32_t inner, int32_t B);
-int imf_attention_kv_batched(const imf_attn_weights_t* w, const float* tokens, int32_t L, int32_t B, void* kv, void* workspace,
-                             size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+int imf_attention_kv_batched(const imf_attn_weights_t* w, const imf_attn_packed_t* wp, const float* tokens, int32_t L, int32_t B, void* kv,
+                             void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
 size_t imf_attention_batched_workspace_bytes(int32_t M, int32_t L, int32_t latent, int32_t inner, int32_t B);
-int imf_attention_fusion_fwd_batched(const imf_attn_weights_t* w, const float* P, int32_t ldp, int32_t M, const int32_t* m_dev,
-                                     const int32_t* seg_dev, const int32_t* cnt_dev, int32_t B, const void* kv, int32_t L, float* out,
-                                     int32_t ldo, void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+int imf_attention_fusion_fwd_batched(const imf_attn_weights_t* w, const imf_attn_packed_t* wp, const float* P, int32_t ldp, int32_t M,
+                                     const int32_t* m_dev, const int32_t* seg_dev, const int32_t* cnt_dev, int32_t B, const void* kv, int32_t L,
+                                     float* out, int32_t ldo, void* workspace, size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+
+/* Dense GEMM on fp16 hi/lo operands (csrc/h2_gemm.cu): C = alpha * A . W^T (+ bias) (+ R).  A: h2 matrix [M_max, K] (chunk width 64, lda
+ * halves; min(*m_dev, M_max) rows are computed); Wpacked = imf_sparse_conv_h2_pack(W^T as [1, K, N], 1, K, N, 64, wmul), 1 / wmul folded
+ * into alpha by the caller.  K % 64 == 0, N % 128 == 0.  mode 0: fp32 C (ldc floats) + optional fp32 residual R; mode 1: h2 C (ldc halves,
+ * chunk width 64); mode 2: GEGLU h2 C [M, N / 2] (value / gate columns interleaved per 128-column tile by the packing; bias = the
+ * un-permuted [N] vector).  err (optional): watchdog codes, bit 16 = an h2 output left the fp16 range. */
+int imf_h2_gemm(const void* A, int32_t lda, int32_t M_max, const int32_t* m_dev, const void* Wpacked, int32_t N, int32_t K, float alpha,
+                const float* bias, const float* R, int32_t ldr, int32_t mode, void* C, int32_t ldc, int32_t* err, imf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -372,13 +372,13 @@ class Emulator:
         h = h[:, :4 * lat] * gelu(np.ascontiguousarray(h[:, 4 * lat:]))
         mat(out, m, lat, ldo)[:] = h @ vec(w.w2, lat * 4 * lat).reshape(lat, 4 * lat).T + vec(w.b2, lat) + x1
 
-    def do_imf_attention_kv_batched(self, w, tokens, L, B, kv, ws, ws_bytes, err):
+    def do_imf_attention_kv_batched(self, w, wp, tokens, L, B, kv, ws, ws_bytes, err):
         t = mat(tokens, B * L, w.dim, w.dim)
         cn = layer_norm(t, vec(w.ln_c_w, w.dim), vec(w.ln_c_b, w.dim))
         p = cn @ vec(w.wkv, 2 * w.inner * w.dim).reshape(2 * w.inner, w.dim).T
         self.kv[kv] = [(p[b * L:(b + 1) * L, :w.inner].copy(), p[b * L:(b + 1) * L, w.inner:].copy()) for b in range(B)]
 
-    def do_imf_attention_fusion_fwd_batched(self, w, P, ldp, M, m_dev, seg_dev, cnt_dev, B, kv, L, out, ldo, ws, ws_bytes, err):
+    def do_imf_attention_fusion_fwd_batched(self, w, wp, P, ldp, M, m_dev, seg_dev, cnt_dev, B, kv, L, out, ldo, ws, ws_bytes, err):
         seg, cnt = vec(seg_dev, B, np.int32), vec(cnt_dev, B, np.int32)
         m = count(m_dev, M)
         saved = self.kv[kv]

@@ -180,7 +180,8 @@ def test_batched_attention_fusion_all_items_one_launch_vs_oracle(state_dict, cud
     af = cuda_model.attention_fusion
     w = af.packed()
     rng = np.random.default_rng(11)
-    for sizes, Lt in (([300, 0, 77, 1000], 302), ([130, 129], 1001), ([1], 7)):
+    for sizes, Lt, wp in (([300, 0, 77, 1000], 302, af.packed_h2()), ([130, 129], 1001, af.packed_h2()), ([1], 7, af.packed_h2()),
+                          ([300, 0, 77, 1000], 302, None)):          # wp = None: the 3xTF32 GEMM tier
         B, n = len(sizes), sum(sizes)
         cap = n + 200
         P = torch.from_numpy(rng.normal(0, 1, (cap, 256)).astype(np.float32)).cuda()
@@ -191,10 +192,10 @@ def test_batched_attention_fusion_all_items_one_launch_vs_oracle(state_dict, cud
         err = torch.zeros(1, dtype=torch.int32, device="cuda")
         kv = torch.empty(int(L.imf_attention_kv_batched_bytes(Lt, B)), dtype=torch.uint8, device="cuda")
         kws = torch.empty(int(L.imf_attention_kv_batched_workspace_bytes(Lt, 128, 128, B)), dtype=torch.uint8, device="cuda")
-        _lib.check(L.imf_attention_kv_batched(w, tok.data_ptr(), Lt, B, kv.data_ptr(), kws.data_ptr(), kws.numel(), err.data_ptr(), s))
+        _lib.check(L.imf_attention_kv_batched(w, wp, tok.data_ptr(), Lt, B, kv.data_ptr(), kws.data_ptr(), kws.numel(), err.data_ptr(), s))
         ws = torch.empty(int(L.imf_attention_batched_workspace_bytes(cap, Lt, 256, 128, B)), dtype=torch.uint8, device="cuda")
         out = torch.full((cap, 256), float("nan"), device="cuda")
-        _lib.check(L.imf_attention_fusion_fwd_batched(w, P.data_ptr(), 256, cap, m_dev.data_ptr(), seg.data_ptr(), cnt.data_ptr(), B, kv.data_ptr(),
+        _lib.check(L.imf_attention_fusion_fwd_batched(w, wp, P.data_ptr(), 256, cap, m_dev.data_ptr(), seg.data_ptr(), cnt.data_ptr(), B, kv.data_ptr(),
                                                       Lt, out.data_ptr(), 256, ws.data_ptr(), ws.numel(), err.data_ptr(), s))
         torch.cuda.synchronize()
         assert int(err.item()) == 0
@@ -206,3 +207,51 @@ def test_batched_attention_fusion_all_items_one_launch_vs_oracle(state_dict, cud
                 assert rel_rows(o[off:off + m], ref) < TOL, (sizes, Lt, b)
             off += m
         assert bool(torch.isnan(o[n:]).all()), "rows past the last item must stay untouched"
+
+
+@pytest.mark.parametrize("M,N,K,mode", [(1000, 128, 256, 1), (333, 256, 128, 0), (2049, 2048, 256, 2), (700, 256, 1024, 0), (5, 256, 128, 0)])
+def test_h2_gemm_modes_vs_float64(M, N, K, mode):
+    """imf_h2_gemm (TMA-fed tcgen05 GEMM on fp16 hi/lo operands) against a float64 product: fp32 output with bias + residual, h2
+    output, GEGLU h2 output (value / gate rows interleaved per 128-column tile by the packing); a device-side row count below M."""
+    from imfnet_b200 import _lib
+    L = _lib.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    Wt = torch.randn(N, K, device="cuda", generator=g) / np.sqrt(K)
+    bias = torch.randn(N, device="cuda", generator=g)
+    R = torch.randn(M, N, device="cuda", generator=g)
+    Ah = torch.zeros(M, 2 * K, dtype=torch.float16, device="cuda")
+    _lib.check(L.imf_h2_pack(A.data_ptr(), K, M, K, 64, Ah.data_ptr(), 2 * K, None, s))
+    Wsrc = Wt
+    if mode == 2:          # tile t of the packed matrix = [value rows 64t..64t+63 | gate rows 64t..64t+63]
+        h = N // 2
+        Wsrc = torch.stack([Wt[:h].reshape(h // 64, 64, K), Wt[h:].reshape(h // 64, 64, K)], dim=1).reshape(N, K)
+    W1 = Wsrc.t().contiguous().reshape(1, K, N)
+    wmul = 2.0 ** np.floor(np.log2(2048.0 / float(W1.abs().max())))
+    packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(1, K, N, 64)), dtype=torch.uint8, device="cuda")
+    _lib.check(L.imf_sparse_conv_h2_pack(W1.data_ptr(), 1, K, N, 64, wmul, packed.data_ptr(), s))
+    m_eff = M - 3 if M > 10 else M
+    m_dev = torch.tensor([m_eff], dtype=torch.int32, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    alpha = 0.75
+    acc = (A.double() @ Wt.double().t()) * alpha + bias.double()
+    if mode == 0:
+        C = torch.full((M, N), float("nan"), device="cuda")
+        _lib.check(L.imf_h2_gemm(Ah.data_ptr(), 2 * K, M, m_dev.data_ptr(), packed.data_ptr(), N, K, alpha / wmul, bias.data_ptr(), R.data_ptr(), N, 0,
+                                 C.data_ptr(), N, err.data_ptr(), s))
+        ref, out = (acc + R.double()).float(), C
+    else:
+        No = N // 2 if mode == 2 else N
+        Ch = torch.full((M, 2 * No), float("nan"), dtype=torch.float16, device="cuda")
+        _lib.check(L.imf_h2_gemm(Ah.data_ptr(), 2 * K, M, m_dev.data_ptr(), packed.data_ptr(), N, K, alpha / wmul, bias.data_ptr(), None, 0, mode,
+                                 Ch.data_ptr(), 2 * No, err.data_ptr(), s))
+        out = torch.empty(M, No, device="cuda")
+        _lib.check(L.imf_h2_unpack(Ch.data_ptr(), 2 * No, M, No, 64, out.data_ptr(), No, s))
+        ref = acc.float() if mode == 1 else (acc[:, :No] * torch.nn.functional.gelu(acc[:, No:])).float()
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    e = float(((out[:m_eff] - ref[:m_eff]).norm(dim=1) / ref[:m_eff].norm(dim=1)).max())
+    print(f"h2 gemm M={M} N={N} K={K} mode={mode}: max row-wise rel err {e:.2e}")
+    assert e < 2e-6
+    assert bool(torch.isnan(out[m_eff:]).all()), "rows past the device-side count must stay untouched"

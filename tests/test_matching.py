@@ -33,6 +33,29 @@ def test_nn_search_matches_oracle(na, nb, c):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("na,nb,c", [(5000, 5000, 32), (1, 7, 32), (333, 64, 32), (65, 1000, 16), (129, 128, 32)])
+def test_tensor_core_search_is_bit_identical_to_brute_force(na, nb, c):
+    """The tcgen05 distance product only filters candidates; the survivors are re-evaluated like the brute-force kernel: same indices
+    AND the same distance bits, also on near-ties (clusters of almost identical descriptors) and exact ties (duplicated rows)."""
+    from imfnet_b200.matching import nn_search
+    rng = np.random.default_rng(na + nb)
+    a, b = _descs(na, 3, c), _descs(nb, 4, c)
+    if nb >= 64:          # near-ties and exact ties among the candidates
+        b[nb // 2:nb // 2 + 16] = b[:16] + rng.normal(0, 1e-7, (16, c)).astype(np.float32)
+        b[nb // 2 + 16:nb // 2 + 24] = b[:8]
+        a[: min(na, 24)] = b[: min(na, 24)] + rng.normal(0, 1e-3, (min(na, 24), c)).astype(np.float32)
+    A, B = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    i_tc, d_tc = nn_search(A, B, return_distance=True, tensor_cores=True)
+    i_bf, d_bf = nn_search(A, B, return_distance=True, tensor_cores=False)
+    assert torch.equal(i_tc, i_bf) and torch.equal(d_tc, d_bf)
+    # un-normalised descriptors of very different magnitudes (the filter margin scales with the norms)
+    A2, B2 = A * torch.logspace(-2, 2, na, device="cuda")[:, None], B * 30.0
+    i_tc, d_tc = nn_search(A2, B2, return_distance=True, tensor_cores=True)
+    i_bf, d_bf = nn_search(A2, B2, return_distance=True, tensor_cores=False)
+    assert torch.equal(i_tc, i_bf) and torch.equal(d_tc, d_bf)
+
+
+@pytest.mark.gpu
 def test_mutual_nn_5000_keypoints_and_edge_cases():
     """BASELINE config 3 shape: 5000 keypoints per fragment; fragment 2 = noisy permuted copy of half of fragment 1 + outliers."""
     from imfnet_b200.matching import mutual_nn, nn_search

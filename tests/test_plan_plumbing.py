@@ -160,8 +160,8 @@ def test_batched_plan_sequence_and_slices(fake_cuda):
     # (the trailing single fragment goes through a single-fragment plan: 3 more enqueues of the same chain with B = 1)
     enq = len([a for n, a in fake_cuda.calls if n == "imf_batch_segments_n" and a[3] == 2])
     assert enq == 2 * 3                                                       # two plans x (two warm-ups + capture)
-    assert len([a for n, a in fake_cuda.calls if n == "imf_attention_fusion_fwd_batched" and a[7] == 2]) == enq
-    assert len([a for n, a in fake_cuda.calls if n == "imf_attention_kv_batched" and a[3] == 2]) == enq
+    assert len([a for n, a in fake_cuda.calls if n == "imf_attention_fusion_fwd_batched" and a[8] == 2]) == enq
+    assert len([a for n, a in fake_cuda.calls if n == "imf_attention_kv_batched" and a[4] == 2]) == enq
     assert len([a for n, a in fake_cuda.calls if n == "imf_image_im2col_h2_batch" and a[10] == 2]) == enq          # both images, one launch
     assert len([a for n, a in fake_cuda.calls if n == "imf_image_maxpool_h2_batch" and a[11] == 2]) == enq
     # the image encoder's batched launches cover B * P rows
@@ -170,11 +170,11 @@ def test_batched_plan_sequence_and_slices(fake_cuda):
     assert stem, "no stem launch over the rows of both images"
     assert ip.col.shape[0] == 2 * ip.P0 and ip.tokens.shape == (2 * ip.P2, 128)
     # fusion chain: the level's rows through one call with the plan's segment / count arrays and the stride-8 row count on the device
-    att = [a for n, a in fake_cuda.calls if n == "imf_attention_fusion_fwd_batched" and a[1] == g.P8.data_ptr()][-1]
-    assert att[3] == g.cap8 == 2 * g.item_cap8 and att[4] == g._n(8) and att[5] == g.seg.data_ptr() and att[6] == g.cnt.data_ptr()
-    assert att[8] == g.kv.data_ptr() and att[9] == ip.P2 and att[10] == g.fused32.data_ptr()          # image tokens per item
-    kvc = [a for n, a in fake_cuda.calls if n == "imf_attention_kv_batched" and a[4] == g.kv.data_ptr()][-1]
-    assert kvc[1] == ip.tokens.data_ptr() and kvc[2] == ip.P2 and kvc[3] == 2
+    att = [a for n, a in fake_cuda.calls if n == "imf_attention_fusion_fwd_batched" and a[2] == g.P8.data_ptr()][-1]
+    assert att[4] == g.cap8 == 2 * g.item_cap8 and att[5] == g._n(8) and att[6] == g.seg.data_ptr() and att[7] == g.cnt.data_ptr()
+    assert att[9] == g.kv.data_ptr() and att[10] == ip.P2 and att[11] == g.fused32.data_ptr()          # image tokens per item
+    kvc = [a for n, a in fake_cuda.calls if n == "imf_attention_kv_batched" and a[5] == g.kv.data_ptr()][-1]
+    assert kvc[2] == ip.tokens.data_ptr() and kvc[3] == ip.P2 and kvc[4] == 2
 
 
 def test_batched_plan_errors(fake_cuda):

@@ -19,6 +19,7 @@ af = model.eval().cuda().attention_fusion
 L = _lib.lib()
 s = torch.cuda.current_stream().cuda_stream
 w = af.packed()
+wp = None if "--tf32" in sys.argv else af.packed_h2()          # --tf32: the 3xTF32 GEMM tier instead of the h2 GEMMs
 
 
 def timeit(fn, reps=20):
@@ -50,10 +51,10 @@ for sizes, Lt in (([1085], 4800), ([1085] * 10, 4800), ([8192], 4800)):
     out = torch.empty(n, 256, device="cuda")
 
     def kvproj():
-        _lib.check(L.imf_attention_kv_batched(w, tok.data_ptr(), Lt, B, kv.data_ptr(), kws.data_ptr(), kws.numel(), err.data_ptr(), s))
+        _lib.check(L.imf_attention_kv_batched(w, wp, tok.data_ptr(), Lt, B, kv.data_ptr(), kws.data_ptr(), kws.numel(), err.data_ptr(), s))
 
     def module():
-        _lib.check(L.imf_attention_fusion_fwd_batched(w, P.data_ptr(), 256, n, m_dev.data_ptr(), seg.data_ptr(), cnt.data_ptr(), B, kv.data_ptr(), Lt,
+        _lib.check(L.imf_attention_fusion_fwd_batched(w, wp, P.data_ptr(), 256, n, m_dev.data_ptr(), seg.data_ptr(), cnt.data_ptr(), B, kv.data_ptr(), Lt,
                                                       out.data_ptr(), 256, ws.data_ptr(), ws.numel(), err.data_ptr(), s))
 
     kvproj()
