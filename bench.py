@@ -417,7 +417,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="fragments per captured-graph replay (0 = the workload's default: C2 10, C3 4, C5 2, C4 8)")
-    ap.add_argument("--plans", type=int, default=2, help="captured plans (CUDA streams) in flight: the copies / latency-bound phases of one group overlap the others")
+    ap.add_argument("--plans", type=int, default=3, help="captured plans (CUDA streams) in flight: the copies / latency-bound phases of one group overlap the others")
     ap.add_argument("--profile", action="store_true",
                     help="only warm-up + resident steps, the steps between cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()

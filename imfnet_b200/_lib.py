@@ -62,6 +62,8 @@ SIGNATURES = {
     "imf_h2_unpack": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _i32, _p]),
     "imf_h2_pack_n": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p, _p]),
     "imf_h2_unpack_n": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _p]),
+    "imf_h2_pack_scaled_n": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _f32, _p, _i32, _p, _p]),
+    "imf_h2_unpack_scaled_n": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _f32, _p, _i32, _p]),
     "imf_h2_unpack_l2norm": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p, _p, _i32, _p]),
     "imf_identity_table": (C.c_int, [_p, _i32, _p, _i32, _p, _p]),
     "imf_tc_gemm_m": (C.c_int, [_p, _i32, _p, _i32, _p, _i32, _i32, _p, _i32, _i32, _f32, _p, _p, _i32, _i32, _p, _sz, _p, _p]),

@@ -95,7 +95,7 @@ class BatchedImagePlan(ImagePlan):
                 self._conv(L, c1, y, self.t2, n2, None, True, tmp, s)
                 self._conv(L, c2, tmp, self.t2, n2, y, True, out, s)
                 y, out = out, y
-        _lib.check(L.imf_h2_unpack(y.data_ptr(), 2 * self.C2, n2, self.C2, 64, self.tokens.data_ptr(), self.C2, s))
+        _lib.check(L.imf_h2_unpack_scaled_n(y.data_ptr(), 2 * self.C2, n2, None, self.C2, 64, 1.0 / self.act_scale, self.tokens.data_ptr(), self.C2, s))
         return self.tokens
 
 

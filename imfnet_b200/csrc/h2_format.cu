@@ -49,12 +49,12 @@ __global__ void k_pack_conv_weights_h2(const float* __restrict__ W, int K3, int 
 
 // fp32 [n, C] <-> h2
 __global__ void __launch_bounds__(256) k_h2_pack(const float* __restrict__ X, int ldx, int n, int C, int KC, __half* __restrict__ H, int ldh,
-                                                 int* err, const int* __restrict__ n_ptr) {
+                                                 int* err, const int* __restrict__ n_ptr, float mul) {
   if (n_ptr) { const int v = *n_ptr; n = v < n ? v : n; }
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)n * C) return;
   const int row = (int)(idx / C), c = (int)(idx % C);
-  const float x = X[(size_t)row * ldx + c];
+  const float x = X[(size_t)row * ldx + c] * mul;
   const __half h = __float2half_rn(x);
   __half* p = H + (size_t)row * ldh + (c / KC) * 2 * KC + (c % KC);
   p[0] = h;
@@ -62,13 +62,13 @@ __global__ void __launch_bounds__(256) k_h2_pack(const float* __restrict__ X, in
   if (fabsf(x) > 60000.f && err) atomicOr(err, 0x10000);
 }
 __global__ void __launch_bounds__(256) k_h2_unpack(const __half* __restrict__ H, int ldh, int n, int C, int KC, float* __restrict__ X, int ldx,
-                                                   const int* __restrict__ n_ptr) {
+                                                   const int* __restrict__ n_ptr, float mul) {
   if (n_ptr) { const int v = *n_ptr; n = v < n ? v : n; }
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)n * C) return;
   const int row = (int)(idx / C), c = (int)(idx % C);
   const __half* p = H + (size_t)row * ldh + (c / KC) * 2 * KC + (c % KC);
-  X[(size_t)row * ldx + c] = __half2float(p[0]) + __half2float(p[KC]);
+  X[(size_t)row * ldx + c] = (__half2float(p[0]) + __half2float(p[KC])) * mul;
 }
 
 // h2 [n, C] -> fp32 rows, optionally divided by their L2 norm (model/resunet.py:228-231: F / ||F||_2, no epsilon); one warp per row,
@@ -144,13 +144,20 @@ extern "C" int imf_h2_pack(const float* X, int32_t ldx, int32_t n, int32_t C, in
                            cudaStream_t stream) {
   return imf_h2_pack_n(X, ldx, n, nullptr, C, KC, H, ldh, err, stream);
 }
+extern "C" int imf_h2_pack_scaled_n(const float* X, int32_t ldx, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, float mul, void* H,
+                                    int32_t ldh, int32_t* err, cudaStream_t stream);
 extern "C" int imf_h2_pack_n(const float* X, int32_t ldx, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, void* H, int32_t ldh,
                              int32_t* err, cudaStream_t stream) {
+  return imf_h2_pack_scaled_n(X, ldx, n, n_dev, C, KC, 1.f, H, ldh, err, stream);
+}
+// H = h2(X * mul): mul is the (power-of-two) activation scale of the tensor-core tier (stored activations = true values * scale)
+extern "C" int imf_h2_pack_scaled_n(const float* X, int32_t ldx, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, float mul, void* H,
+                                    int32_t ldh, int32_t* err, cudaStream_t stream) {
   IMF_CHECK_ARG(n >= 0 && C > 0 && (KC == 32 || KC == 64) && C % KC == 0 && ldx >= C && ldh >= 2 * C);
   if (n == 0) return IMF_OK;
   IMF_CHECK_ARG(X != nullptr && H != nullptr);
   const long long total = (long long)n * C;
-  k_h2_pack<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(X, ldx, n, C, KC, reinterpret_cast<__half*>(H), ldh, err, n_dev);
+  k_h2_pack<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(X, ldx, n, C, KC, reinterpret_cast<__half*>(H), ldh, err, n_dev, mul);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }
@@ -158,13 +165,20 @@ extern "C" int imf_h2_pack_n(const float* X, int32_t ldx, int32_t n, const int32
 extern "C" int imf_h2_unpack(const void* H, int32_t ldh, int32_t n, int32_t C, int32_t KC, float* X, int32_t ldx, cudaStream_t stream) {
   return imf_h2_unpack_n(H, ldh, n, nullptr, C, KC, X, ldx, stream);
 }
+extern "C" int imf_h2_unpack_scaled_n(const void* H, int32_t ldh, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, float mul, float* X,
+                                      int32_t ldx, cudaStream_t stream);
 extern "C" int imf_h2_unpack_n(const void* H, int32_t ldh, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, float* X, int32_t ldx,
                                cudaStream_t stream) {
+  return imf_h2_unpack_scaled_n(H, ldh, n, n_dev, C, KC, 1.f, X, ldx, stream);
+}
+// X = (hi + lo) * mul
+extern "C" int imf_h2_unpack_scaled_n(const void* H, int32_t ldh, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, float mul, float* X,
+                                      int32_t ldx, cudaStream_t stream) {
   IMF_CHECK_ARG(n >= 0 && C > 0 && (KC == 32 || KC == 64) && C % KC == 0 && ldx >= C && ldh >= 2 * C);
   if (n == 0) return IMF_OK;
   IMF_CHECK_ARG(X != nullptr && H != nullptr);
   const long long total = (long long)n * C;
-  k_h2_unpack<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(H), ldh, n, C, KC, X, ldx, n_dev);
+  k_h2_unpack<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(H), ldh, n, C, KC, X, ldx, n_dev, mul);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }

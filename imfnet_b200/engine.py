@@ -18,6 +18,26 @@ from . import _lib
 from .arena import Arena
 
 
+def act_scale_from_bn(bns) -> float:
+    """Power-of-two scale A under which the h2 activations of a branch are STORED (stored = true * A), chosen so that typical stored
+    magnitudes are O(1): the fp16 hi/lo format keeps 22 mantissa bits only for values between its subnormal range (~6e-5) and its
+    overflow (6e4), whereas the reference computes in fp32.  After an eval-mode BatchNorm an activation is gamma * N(0, 1) + beta, so the
+    geometric mean over the layers of rms_c sqrt(gamma^2 + beta^2) is the typical magnitude; a checkpoint whose BatchNorm parameters
+    sit near 1e-6 or 1e4 is brought back into range.  Because A is a power of two and enters only through the folded BatchNorm shift
+    (and the conversions at the branch's borders), A = 1 reproduces the unscaled arithmetic bit for bit."""
+    logs = []
+    for bn in bns:
+        g = bn.weight.detach().double()
+        b = bn.bias.detach().double()
+        m = float(torch.sqrt((g * g + b * b).mean()))
+        if m > 0 and math.isfinite(m):
+            logs.append(math.log2(m))
+    if not logs:
+        return 1.0
+    e = -round(sum(logs) / len(logs))
+    return float(2.0 ** max(-100, min(100, e)))
+
+
 def _kc(*channels) -> int:
     """Chunk width of an h2 buffer section holding these channel counts (see csrc/sparse_conv_h2.cu)."""
     return 64 if all(c % 64 == 0 for c in channels) else 32
@@ -59,6 +79,9 @@ class FusedPlan:
                 raise TypeError("imfnet_b200 computes in float32; cast the model with .float()")
         mods = dict(m.named_modules())
         CH, TR = self.CH, self.TR
+        # activation scale of the point branch (see act_scale_from_bn); un-normalised outputs would carry it, so it stays 1 then
+        self.act_scale = act_scale_from_bn([mods[b].bn for _c, b in self.CONV_BN] + [m.norm1.bn]) if m.normalize_feature else 1.0
+        A = self.act_scale
         # chunk width of the buffer each convolution reads
         kc_in = {"conv2": _kc(CH[1]), "conv3": _kc(TR[3], CH[2]), "conv4": _kc(TR[4], CH[3]), "conv4_tr": _kc(CH[4]),
                  "conv3_tr": _kc(TR[4], CH[3]), "conv2_tr": _kc(TR[3], CH[2])}
@@ -78,8 +101,9 @@ class FusedPlan:
                 _lib.check(L.imf_sparse_conv_h2_pack(conv.kernel.detach().contiguous().data_ptr(), 27, conv.in_channels,
                                                      conv.out_channels, kci, wmul, buf.data_ptr(), s))
                 scale, shift = bn.folded()
-                self.conv[cname] = (conv, buf, (scale / wmul).contiguous(), shift, kci)
+                self.conv[cname] = (conv, buf, (scale / wmul).contiguous(), (shift * A).contiguous(), kci)          # stored out = A * true out
         sc, sh = m.norm1.folded()
+        sc, sh = (sc * A).contiguous(), (sh * A).contiguous()          # conv1 reads the (unscaled) input features
         self.norm1 = (sc, sh)
         # conv1 with one input channel (the IMFNet configuration: a column of ones, util/misc.py:76-77) runs on the tensor cores as a
         # dense product over the K^3 neighbour features (csrc/conv_first_tc.cu): its kernel packed as ONE offset with K^3 "channels"
@@ -96,7 +120,7 @@ class FusedPlan:
                 _lib.check(L.imf_sparse_conv_h2_pack(w1.data_ptr(), 1, KP, CH[1], 64, wmul, buf.data_ptr(), torch.cuda.current_stream().cuda_stream))
                 torch.cuda.current_stream().synchronize()          # w1 is a temporary
                 self.conv1_tc = (buf, (sc / wmul).contiguous(), sh)
-        self.final_bias = None if m.final.bias is None else m.final.bias.detach().reshape(-1).contiguous()
+        self.final_bias = None if m.final.bias is None else (m.final.bias.detach().reshape(-1) * A).contiguous()          # logits are stored * A
         # tail conv1_tr -> ReLU -> final (+ bias) as two one-offset convolutions on the tensor-core kernel (the captured plans then
         # write the concatenation [decoder | skip] with 32-channel chunks throughout, so that it is ONE h2 matrix of chunk width 32)
         self.tail_tc = None
@@ -144,7 +168,8 @@ class FusedPlan:
 
     def _unpack(self, ptr, ldh, n, C, kc):
         out = torch.empty((n, C), dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib().imf_h2_unpack(ptr, ldh, n, C, kc, out.data_ptr(), C, torch.cuda.current_stream().cuda_stream))
+        _lib.check(_lib.lib().imf_h2_unpack_scaled_n(ptr, ldh, n, None, C, kc, 1.0 / self.act_scale, out.data_ptr(), C,
+                                                     torch.cuda.current_stream().cuda_stream))
         return out
 
     # -- forward -------------------------------------------------------------------------------
@@ -225,7 +250,7 @@ class FusedPlan:
 
             # ---- attention fusion at stride 8 (resunet.py:189, 237-273), fp32 tokens ----
             P8 = buf(n8, CH[4])
-            _lib.check(L.imf_h2_unpack(d2.data_ptr(), 2 * CH[4], n8, CH[4], k8, P8.data_ptr(), CH[4], s))
+            _lib.check(L.imf_h2_unpack_scaled_n(d2.data_ptr(), 2 * CH[4], n8, None, CH[4], k8, 1.0 / self.act_scale, P8.data_ptr(), CH[4], s))
             main.wait_event(ev_img)
             fused32 = buf(n8, CH[4])
             seg = cm.batch_segments(8, B) if B > 1 else [0, n8]
@@ -236,7 +261,8 @@ class FusedPlan:
             if seg[B] != n8:
                 raise ValueError("coordinates reference more batch items than images were given")
             fused = buf(n8, CH[4])
-            _lib.check(L.imf_h2_pack(fused32.data_ptr(), CH[4], n8, CH[4], k8, fused.data_ptr(), 2 * CH[4], self.err.data_ptr(), s))
+            _lib.check(L.imf_h2_pack_scaled_n(fused32.data_ptr(), CH[4], n8, None, CH[4], k8, self.act_scale, fused.data_ptr(), 2 * CH[4],
+                                              self.err.data_ptr(), s))
             if self.debug is not None:
                 self.debug.update(image=img.clone(), out_s1=self._unpack(s1_ptr, ld1, n1, CH[1], kc1b),
                                   out_s2=self._unpack(s2_ptr, ld2, n2, CH[2], kc2), out_s4=self._unpack(s4_ptr, ld4, n4, CH[3], kc4),
@@ -654,13 +680,13 @@ class GraphPlan:
         af = m.attention_fusion
         _lib.check(L.imf_batch_segments_n(self.coords[8].data_ptr(), self._n(8), self.rows, self.B, self.cap8, self.seg.data_ptr(),
                                           self.cnt.data_ptr(), self.err.data_ptr(), s))
-        _lib.check(L.imf_h2_unpack_n(self.d2.data_ptr(), 2 * C8, self.cap8, self._n(8), C8, k8, self.P8.data_ptr(), C8, s))
+        _lib.check(L.imf_h2_unpack_scaled_n(self.d2.data_ptr(), 2 * C8, self.cap8, self._n(8), C8, k8, 1.0 / self.f.act_scale, self.P8.data_ptr(), C8, s))
         main.wait_stream(self.side)
         _lib.check(L.imf_attention_fusion_fwd_batched(af.packed(), af.packed_h2(), self.P8.data_ptr(), C8, self.cap8, self._n(8), self.seg.data_ptr(),
                                                       self.cnt.data_ptr(), self.B, self.kv.data_ptr(), self.n_tok, self.fused32.data_ptr(), C8,
                                                       self.att_ws.data_ptr(), self.att_ws_bytes, self.err.data_ptr(), s))
-        _lib.check(L.imf_h2_pack_n(self.fused32.data_ptr(), C8, self.cap8, self._n(8), C8, k8, self.fused.data_ptr(), 2 * C8,
-                                   self.err.data_ptr(), s))
+        _lib.check(L.imf_h2_pack_scaled_n(self.fused32.data_ptr(), C8, self.cap8, self._n(8), C8, k8, self.f.act_scale, self.fused.data_ptr(), 2 * C8,
+                                          self.err.data_ptr(), s))
 
     def capture(self):
         """Warm the sequence up once (lazy initialisation inside torch / cuDNN must not happen during capture), then record it."""

@@ -23,9 +23,10 @@ def _fold_bn(bn: nn.BatchNorm2d):
 
 
 class _Conv:
-    """One packed convolution: weights W[K, Cin, Cout] in the tensor-core layout + folded BatchNorm."""
+    """One packed convolution: weights W[K, Cin, Cout] in the tensor-core layout + folded BatchNorm.  act_scale: the branch's activation
+    scale A (engine.act_scale_from_bn; stored = true * A): the shift carries it; `first` (a layer reading unscaled input) also the scale."""
 
-    def __init__(self, W: torch.Tensor, bn: nn.BatchNorm2d, kc_in: int):
+    def __init__(self, W: torch.Tensor, bn: nn.BatchNorm2d, kc_in: int, act_scale: float = 1.0, first: bool = False):
         L = _lib.lib()
         K, cin, cout = W.shape
         W = W.contiguous().float()
@@ -34,8 +35,9 @@ class _Conv:
         self.K, self.cin, self.cout, self.kc_in = K, cin, cout, kc_in
         self.packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(K, cin, cout, kc_in)), dtype=torch.uint8, device=W.device)
         _lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), K, cin, cout, kc_in, wmul, self.packed.data_ptr(), _lib.cur_stream()))
-        scale, self.shift = _fold_bn(bn)
-        self.scale = (scale / wmul).contiguous()
+        scale, shift = _fold_bn(bn)
+        self.shift = (shift * act_scale).contiguous()
+        self.scale = (scale * (act_scale if first else 1.0) / wmul).contiguous()
 
 
 def _w3(conv: nn.Conv2d) -> torch.Tensor:
@@ -86,12 +88,15 @@ class ImagePlan:
             # weights
             w0 = torch.zeros((1, self.STEM_K, c1.out_channels), dtype=torch.float32, device=dev)
             w0[0, : c1.in_channels * k * k] = c1.weight.detach().permute(2, 3, 1, 0).reshape(-1, c1.out_channels)
-            self.stem = _Conv(w0, backbone.bn1, 32)
-            self.blocks1 = [(_Conv(_w3(b.conv1), b.bn1, 64), _Conv(_w3(b.conv2), b.bn2, 64)) for b in backbone.layer1]
+            from ..engine import act_scale_from_bn
+            bns = [backbone.bn1] + [bn for b in list(backbone.layer1) + list(backbone.layer2) for bn in (b.bn1, b.bn2)]
+            A = self.act_scale = act_scale_from_bn(bns)          # stored activations of this branch = true * A (power of two)
+            self.stem = _Conv(w0, backbone.bn1, 32, A, first=True)
+            self.blocks1 = [(_Conv(_w3(b.conv1), b.bn1, 64, A), _Conv(_w3(b.conv2), b.bn2, 64, A)) for b in backbone.layer1]
             self.blocks2 = []
             for b in backbone.layer2:
-                down = None if b.downsample is None else _Conv(_w3(b.downsample[0]), b.downsample[1], 64)
-                self.blocks2.append((_Conv(_w3(b.conv1), b.bn1, 64), _Conv(_w3(b.conv2), b.bn2, 64), down))
+                down = None if b.downsample is None else _Conv(_w3(b.downsample[0]), b.downsample[1], 64, A)
+                self.blocks2.append((_Conv(_w3(b.conv1), b.bn1, 64, A), _Conv(_w3(b.conv2), b.bn2, 64, A), down))
             self.C1, self.C2 = backbone.layer1[0].conv1.out_channels, backbone.layer2[0].conv1.out_channels
             if self.C1 % 64 or self.C2 % 64 or backbone.layer1[0].downsample is not None or self.blocks2[0][2] is None:
                 raise NotImplementedError("unexpected ResNet prefix shape")
@@ -138,7 +143,8 @@ class ImagePlan:
                 self._conv(L, c1, y, self.t2, self.P2, None, True, tmp, s)
                 self._conv(L, c2, tmp, self.t2, self.P2, y, True, out, s)
                 y, out = out, y
-        _lib.check(L.imf_h2_unpack(y.data_ptr(), 2 * self.C2, self.P2, self.C2, 64, self.tokens.data_ptr(), self.C2, s))
+        _lib.check(L.imf_h2_unpack_scaled_n(y.data_ptr(), 2 * self.C2, self.P2, None, self.C2, 64, 1.0 / self.act_scale, self.tokens.data_ptr(),
+                                            self.C2, s))
         return self.tokens
 
 

@@ -174,3 +174,34 @@ def make_state_dict(seed: int = 0, model: str = "ResUNetBN2C", in_channels: int 
             raise ValueError(kind)
         sd[name] = torch.from_numpy(np.asarray(v, dtype=np.float32).reshape(shape))
     return sd
+
+
+def scaled_state_dict(sd, s_point: float = 1.0, s_image: float = 1.0):
+    """A checkpoint whose ACTIVATIONS are s_point (point branch) / s_image (image branch) times those of `sd`, layer by layer: every
+    BatchNorm gets gamma, beta times s and -- except the first layer of a branch, whose input is unscaled -- running_mean times s and
+    running_var times s^2; the fusion module's output projections (to_out, net.2) are scaled by s_point so that the fused stride-8
+    features stay at the branch's magnitude.  Used to test the numeric range of the fp16 hi/lo tier (activations near 1e-6 or 1e4)
+    against the fp32 oracle on the same weights."""
+    out = OrderedDict((k, v.clone()) for k, v in sd.items())
+
+    def scale_bn(prefix, s, first):
+        out[prefix + ".weight"] *= s
+        out[prefix + ".bias"] *= s
+        if not first:
+            out[prefix + ".running_mean"] *= s
+            out[prefix + ".running_var"] *= s * s
+
+    for k in sd:
+        if not k.endswith(".running_var"):
+            continue
+        p = k[: -len(".running_var")]
+        if p.startswith("img_encoder.backbone."):
+            if p.startswith("img_encoder.backbone.layer3") or p.startswith("img_encoder.backbone.layer4"):
+                continue                                   # never executed
+            scale_bn(p, s_image, first=(p == "img_encoder.backbone.bn1"))
+        else:
+            scale_bn(p, s_point, first=(p == "norm1.bn"))
+    for k in ("attention_fusion.cross_attend_blocks.0.fn.to_out.weight", "attention_fusion.cross_attend_blocks.0.fn.to_out.bias",
+              "attention_fusion.cross_attend_blocks.1.fn.net.2.weight", "attention_fusion.cross_attend_blocks.1.fn.net.2.bias"):
+        out[k] *= s_point
+    return out

@@ -141,6 +141,12 @@ int imf_h2_pack_n(const float* X, int32_t ldx, int32_t n, const int32_t* n_dev, 
 int imf_h2_unpack_n(const void* H, int32_t ldh, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, float* X, int32_t ldx,
                     imf_stream_t stream);
 
+/* The conversions with a multiplier: H = h2(X * mul), X = (hi + lo) * mul.  The plans store activations times a power-of-two scale chosen
+ * from the BatchNorm affine parameters ("numeric range"); these move values across that boundary. */
+int imf_h2_pack_scaled_n(const float* X, int32_t ldx, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, float mul, void* H, int32_t ldh,
+                         int32_t* err, imf_stream_t stream);
+int imf_h2_unpack_scaled_n(const void* H, int32_t ldh, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, float mul, float* X, int32_t ldx,
+                           imf_stream_t stream);
 /* h2 [n, C] (C <= 128) -> fp32 rows, divided by their L2 norm when normalize != 0 (model/resunet.py:228-231, no epsilon); out_row
  * (optional) scatters row i to Y[out_row[i]]. */
 int imf_h2_unpack_l2norm(const void* H, int32_t ldh, int32_t n, const int32_t* n_dev, int32_t C, int32_t KC, int32_t normalize,

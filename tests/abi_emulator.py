@@ -187,6 +187,14 @@ class Emulator:
     def do_imf_h2_pack(self, X, ldx, n, C, KC, H, ldh, err):
         self.do_imf_h2_pack_n(X, ldx, n, None, C, KC, H, ldh, err)
 
+    def do_imf_h2_unpack_scaled_n(self, H, ldh, n, n_dev, C, KC, mul, X, ldx):
+        m = count(n_dev, n)
+        mat(X, m, C, ldx)[:] = mat(H, m, C, ldh // 2) * np.float32(mul)
+
+    def do_imf_h2_pack_scaled_n(self, X, ldx, n, n_dev, C, KC, mul, H, ldh, err):
+        m = count(n_dev, n)
+        mat(H, m, C, ldh // 2)[:] = mat(X, m, C, ldx) * np.float32(mul)
+
     def do_imf_h2_unpack_l2norm(self, H, ldh, n, n_dev, C, KC, normalize, out_row, Y, ldy):
         m = count(n_dev, n)
         x = mat(H, m, C, ldh // 2).copy()

@@ -67,7 +67,7 @@ def test_bench_line_contract_and_roofline_leg(bench):
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
                 "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert key in d, key
-    assert d["config"]["fragments_per_step"] == 4 and d["config"]["fragments_per_graph_replay"] == 2
+    assert d["config"]["fragments_per_step"] == 4 and d["config"]["fragments_per_graph_replay"] == 2 and d["config"]["plans_in_flight"] == 2
     assert d["value"] == pytest.approx(400 * 4 / 1e-3) and d["ms_per_step"] == pytest.approx(1.0)          # ms_per_step x steps reproduces value
     assert d["e2e"]["h2d_bytes_per_step"] == 4 * (400 * 16 + 400 * 4 + 3 * 48 * 64 * 4) and d["e2e"]["d2h_bytes_per_step"] == 4 * 400 * 32 * 4
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0

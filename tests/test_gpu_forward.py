@@ -306,3 +306,25 @@ def test_reference_call_sequence_on_gpu(state_dict, cuda_model):
     # the evaluation script's keypoint/voxel intersection helper (scripts/evaluation_3dmatch.py:164-168)
     h = ME.utils.fnv_hash_vec(np.floor(xyz[inds] / 0.05))
     assert h.dtype == np.uint64 and h.shape == (len(inds),) and len(np.unique(h)) > 0.99 * len(h)          # (FNV is not injective)
+
+
+@pytest.mark.parametrize("s_point,s_image", [(2.0 ** -20, 1.0), (2.0 ** 13, 1.0), (1.0, 2.0 ** -10), (2.0 ** 7, 2.0 ** 9)])
+def test_activation_range_rescaled_checkpoints_vs_oracle(state_dict, s_point, s_image):
+    """The fp16 hi/lo tier stores activations times a power-of-two scale derived from the BatchNorm affine parameters
+    (engine.act_scale_from_bn), so checkpoints whose activations sit near 1e-6 or 1e4 -- where unscaled fp16 pairs would lose their
+    low halves to subnormals or overflow at 6e4 -- still match the fp32 oracle run on the SAME weights within the 1e-4 bar."""
+    import imfnet_b200.me as ME
+    from imfnet_b200 import load_model
+    sd = synthetic.scaled_state_dict(state_dict, s_point, s_image)
+    model = load_model("ResUNetBN2C")(1, 32, bn_momentum=0.05, normalize_feature=True, conv1_kernel_size=5, D=3, config=None)
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().cuda()
+    coords, _ = synthetic.make_fragment(6000, 0.05, seed=41)
+    c, f, im = torch.from_numpy(coords), torch.ones((6000, 1)), synthetic.make_image(160, 120, seed=41)
+    ref = imfnet_oracle.forward(sd, c, f, im)
+    d = model(ME.SparseTensor(f, coordinates=c, device="cuda"), im.cuda()).F.cpu()
+    assert np.log2(model._plan.act_scale) == round(np.log2(model._plan.act_scale))          # a power of two
+    assert abs(np.log2(model._plan.act_scale * s_point)) <= 2, "the activation scale must undo the checkpoint's magnitude"
+    assert note(f"rescaled_checkpoint_{s_point:g}_{s_image:g}_vs_oracle", rel_rows(d, ref)) < TOL
+    outs = model.forward_batches([(c.cuda(), f.cuda(), im.cuda())] * 2, batch=2)
+    assert all(rel_rows(o.cpu(), ref) < TOL for o in outs)

@@ -18,6 +18,7 @@ METRICS = [
     ("dram__bytes_write.sum", "MB_wr", 1e-6),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%", 1.0),
     ("lts__t_sector_hit_rate.pct", "L2hit%", 1.0),
+    ("lts__t_bytes.sum", "L2_MB", 1e-6),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%", 1.0),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%", 1.0),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps%", 1.0),
@@ -25,7 +26,8 @@ METRICS = [
     ("launch__registers_per_thread", "regs", 1.0),
     ("launch__grid_size", "grid", 1.0),
 ]
-UNIT = {"nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+UNIT = {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9, "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9, "byte": 1.0, "Kbyte": 1e3,
+        "Mbyte": 1e6, "Gbyte": 1e9}
 
 
 def load(path):
