@@ -124,23 +124,34 @@ class FusedPlan:
         # tail conv1_tr -> ReLU -> final (+ bias) as two one-offset convolutions on the tensor-core kernel (the captured plans then
         # write the concatenation [decoder | skip] with 32-channel chunks throughout, so that it is ONE h2 matrix of chunk width 32)
         self.tail_tc = None
+        self.tail_fused = False
         c0, c1, c2 = m.conv1_tr.in_channels, m.conv1_tr.out_channels, m.final.out_channels
         if (m.conv1_tr.kernel_volume == 1 and m.final.kernel_volume == 1 and c0 % 32 == 0 and c1 in (64, 128, 256) and c2 in (32, 64, 128)
                 and m.conv1_tr.bias is None and TR[2] % 32 == 0):
             with torch.cuda.device(self.device):
                 st = torch.cuda.current_stream().cuda_stream
                 packs = []
+                # The logits get their own power-of-two scale A_f: `final` has a bias instead of a BatchNorm, so their magnitude is
+                # sqrt(|bias|^2 + |W2 . hidden|^2) whatever the branch's A is (a checkpoint with tiny activations and an O(1) bias would
+                # overflow under A); the L2 normalisation removes A_f like it removes A.
+                b2 = m.final.bias.detach().double().reshape(-1) if m.final.bias is not None else torch.zeros(1, dtype=torch.float64)
+                est = math.sqrt(float((b2 * b2).mean()) + float((m.final.kernel.detach().double() ** 2).mean()) * c1 / (A * A))
+                self.final_scale = Af = (2.0 ** -round(math.log2(est)) if est > 0 and math.isfinite(est) else A) if m.normalize_feature else 1.0
                 for W, cin, cout, kci in ((m.conv1_tr.kernel, c0, c1, 32), (m.final.kernel, c1, c2, 64)):
                     W = W.detach().reshape(1, cin, cout).contiguous()
                     wmax = float(W.abs().max())
                     wmul = 2.0 ** math.floor(math.log2(2048.0 / wmax)) if wmax > 0 else 1.0
                     buf = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(1, cin, cout, kci)), dtype=torch.uint8, device=self.device)
                     _lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), 1, cin, cout, kci, wmul, buf.data_ptr(), st))
-                    packs.append((buf, torch.full((cout,), 1.0 / wmul, dtype=torch.float32, device=self.device)))
+                    mul = (Af / A) if len(packs) == 1 else 1.0          # (second product) hidden is stored * A, the logits * A_f
+                    packs.append((buf, torch.full((cout,), mul / wmul, dtype=torch.float32, device=self.device)))
                 torch.cuda.current_stream().synchronize()
                 zero1 = torch.zeros(c1, dtype=torch.float32, device=self.device)
-                bias2 = self.final_bias if self.final_bias is not None else torch.zeros(c2, dtype=torch.float32, device=self.device)
+                bias2 = (m.final.bias.detach().reshape(-1) * Af) if m.final.bias is not None else torch.zeros(c2, dtype=torch.float32, device=self.device)
                 self.tail_tc = ((packs[0][0], packs[0][1], zero1), (packs[1][0], packs[1][1], bias2.float().contiguous()))
+                # ... and, for the IMFNet shapes, as ONE kernel (IMFNET_B200_TAIL=split keeps the two-launch form, for comparison)
+                import os
+                self.tail_fused = c0 <= 96 and c1 == 64 and c2 == 32 and os.environ.get("IMFNET_B200_TAIL", "fused") != "split"
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         # split-mode workspace of the convolution kernel (its head holds arrival counters that must start, and are left, zero)
@@ -647,6 +658,12 @@ class GraphPlan:
             (p1, s1, z1), (p2, s2, b2) = f.tail_tc
             c0, c1, c2 = TR[2] + CH[1], TR[1], m.out_channels
             kmid, kout = _kc(c1), _kc(c2)
+            if f.tail_fused:          # one kernel: the hidden layer and the logits stay on the SM (csrc/tail_fused.cu)
+                _lib.check(L.imf_tail_fused_h2_fwd(self.cat1.data_ptr(), ld1, rows, self._n(1), c0, c1, c2, p1.data_ptr(), s1.data_ptr(),
+                                                   z1.data_ptr(), p2.data_ptr(), s2.data_ptr(), b2.data_ptr(), 1 if m.normalize_feature else 0,
+                                                   self.out.data_ptr(), c2, self.err.data_ptr(), s))
+                self._tl_end(tok)
+                return
             _lib.check(L.imf_identity_table(self._n(1), rows, self.ident.data_ptr(), self.ldn, self.ident_mask.data_ptr(), s))
             # hidden = relu(cat1 . W1) -> h1 (free after block2_tr);  logits = hidden . W2 + b2 -> h0;  out = logits / ||logits||
             _lib.check(L.imf_sparse_conv_g4_fwd(self.cat1.data_ptr(), ld1, 32, p1.data_ptr(), self.ident.data_ptr(), self.ldn,

@@ -233,6 +233,16 @@ int imf_pointwise_tail_h2_fwd(const void* X, int32_t ldx, int32_t C0, int32_t Ca
                               const float* W2, const float* b2, int32_t C2, const int32_t* n_dev, int32_t n_max, int32_t normalize,
                               const int32_t* out_row, float* Y, int32_t ldy, imf_stream_t stream);
 
+/* The same tail in ONE tensor-core kernel (csrc/tail_fused.cu): per 128-row tile TMA load -> conv1_tr product -> ReLU -> final
+ * product -> bias -> L2 norm -> TMA store; the hidden layer and the logits never touch HBM.
+ *   out[i, :] = normalize( scale2 * (relu(scale1 * (X[i, :] . W1) + shift1) . W2) + bias2 ),  i < min(*n_dev, n_max)
+ * X: h2 matrix of c0 channels, chunk width 32 (ldx halves); packed1 = imf_sparse_conv_h2_pack(W1 as [1, c0, 64], kc_in 32), packed2 =
+ * (W2 as [1, 64, 32], kc_in 64), their power-of-two multipliers folded into scale1 / scale2; shift1, bias2 optional; out fp32 rows of
+ * ldo floats.  c0 in {32, 64, 96}, c1 == 64, c2 == 32.  Replaces model/resunet.py:216-233 (conv1_tr, MEF.relu, final, L2 norm). */
+int imf_tail_fused_h2_fwd(const void* X, int32_t ldx, int32_t n_max, const int32_t* n_dev, int32_t c0, int32_t c1, int32_t c2,
+                          const void* packed1, const float* scale1, const float* shift1, const void* packed2, const float* scale2,
+                          const float* bias2, int32_t normalize, float* out, int32_t ldo, int32_t* err, imf_stream_t stream);
+
 /* Y = X . W (+ bias): a 1x1 ME.MinkowskiConvolution as a module (kernel [Cin, Cout]). */
 int imf_linear_fwd(const float* X, int32_t ldx, const float* W_kn, const float* bias, int32_t M, int32_t Cin, int32_t Cout,
                    float* Y, int32_t ldy, imf_stream_t stream);

@@ -302,6 +302,19 @@ class Emulator:
         assert not out_row
         mat(Y, n, C2, ldy)[:] = y
 
+    def do_imf_tail_fused_h2_fwd(self, X, ldx, n_max, n_dev, c0, c1, c2, packed1, scale1, shift1, packed2, scale2, bias2, normalize, out, ldo, err):
+        n = count(n_dev, n_max)
+        x = mat(X, n, c0, ldx // 2)
+        h = (x @ self.packed[packed1][0]) * vec(scale1, c1)
+        if shift1:
+            h = h + vec(shift1, c1)
+        y = (np.maximum(h, 0) @ self.packed[packed2][0]) * vec(scale2, c2)
+        if bias2:
+            y = y + vec(bias2, c2)
+        if normalize:
+            y = y / np.sqrt((y * y).sum(axis=1, keepdims=True))
+        mat(out, n, c2, ldo)[:] = y
+
     # ---- image branch --------------------------------------------------------------------------------------------------
     def do_imf_image_conv_table(self, Hin, Win, K, stride, pad, nbr_t, ld_n, tile_mask):
         Hout, Wout = (Hin + 2 * pad - K) // stride + 1, (Win + 2 * pad - K) // stride + 1

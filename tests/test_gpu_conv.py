@@ -368,6 +368,46 @@ def test_pointwise_tail_matches_oracle(normalize):
     close(Y.cpu(), ref)
 
 
+@pytest.mark.parametrize("n,c0,normalize,n_eff", [(1, 96, True, None), (127, 96, True, None), (129, 64, True, None), (3001, 96, False, None),
+                                                  (40000, 96, True, None), (40000, 32, True, 38017), (150 * 128 * 2 + 5, 96, True, None)])
+def test_fused_tail_kernel_matches_fp32(n, c0, normalize, n_eff):
+    """csrc/tail_fused.cu (conv1_tr -> ReLU -> final + bias -> L2 norm in one tcgen05 kernel) against the fp32 formula of
+    model/resunet.py:216-233, at tile-boundary sizes, more tiles than two per SM, a device-side row count and un-normalised output."""
+    g = torch.Generator().manual_seed(n + c0)
+    X = torch.randn(n, c0, generator=g) * 3
+    W1, W2, b2 = torch.randn(c0, 64, generator=g) / 10, torch.randn(64, 32, generator=g) / 8, torch.randn(32, generator=g)
+    sh1 = torch.randn(64, generator=g) * 0.1
+    m = n if n_eff is None else n_eff
+    ref = torch.relu(X[:m].double() @ W1.double() + sh1.double()) @ W2.double() + b2.double()
+    if normalize:
+        ref = ref / torch.norm(ref, p=2, dim=1, keepdim=True)
+    L = _lib.lib()
+    s = _lib.cur_stream()
+    Xd = X.cuda()
+    H = torch.zeros(n, c0, device="cuda")                       # h2 footprint of [n, c0] = fp32 footprint
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(L.imf_h2_pack(Xd.data_ptr(), c0, n, c0, 32, H.data_ptr(), 2 * c0, err.data_ptr(), s))
+    packs = []
+    for W, cin, cout, kci in ((W1, c0, 64, 32), (W2, 64, 32, 64)):
+        Wd = W.reshape(1, cin, cout).contiguous().cuda()
+        wmul = 2.0 ** np.floor(np.log2(2048.0 / float(W.abs().max())))
+        buf = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(1, cin, cout, kci)), dtype=torch.uint8, device="cuda")
+        _lib.check(L.imf_sparse_conv_h2_pack(Wd.data_ptr(), 1, cin, cout, kci, float(wmul), buf.data_ptr(), s))
+        packs.append((buf, torch.full((cout,), 1.0 / wmul, device="cuda"), Wd))
+    out = torch.full((n, 32), float("nan"), device="cuda")
+    n_dev = None if n_eff is None else torch.tensor([n_eff], dtype=torch.int32, device="cuda")
+    sh1_d, b2_d = sh1.cuda(), b2.cuda()
+    for _ in range(2):          # twice: the second launch must not depend on anything the first left behind
+        _lib.check(L.imf_tail_fused_h2_fwd(H.data_ptr(), 2 * c0, n, _lib.ptr(n_dev), c0, 64, 32, packs[0][0].data_ptr(), packs[0][1].data_ptr(),
+                                           sh1_d.data_ptr(), packs[1][0].data_ptr(), packs[1][1].data_ptr(), b2_d.data_ptr(), int(normalize),
+                                           out.data_ptr(), 32, err.data_ptr(), s))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    close(out[:m].cpu().double(), ref, H2_RTOL)
+    tile_end = min(n, (m + 127) // 128 * 128)
+    assert torch.all(out[m:tile_end] == 0) and torch.isnan(out[tile_end:]).all()          # rows past the count: zeros inside the last tile, untouched beyond
+
+
 def test_module_level_layers_match_standin(frag):
     """imfnet_b200.me layers used one by one (the un-fused route) give the oracle's numbers."""
     import imfnet_b200.me as ME

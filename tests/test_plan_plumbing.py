@@ -131,11 +131,12 @@ def test_single_fragment_graph_plan_sequence(fake_cuda):
     per_enqueue = seq.count("imf_hash_build")
     assert per_enqueue == 3                                                  # two warm-ups + the capture
     assert seq.count("imf_sparse_conv_g4_fwd_perm") == 3 * 20               # 6 strided / transposed + 14 block convolutions
-    assert seq.count("imf_sparse_conv_g4_fwd") == 3 * (16 + 2)              # image encoder: stem + 6 + 9; tail: conv1_tr and final as 1x1 products
+    assert seq.count("imf_sparse_conv_g4_fwd") == 3 * 16                    # image encoder: stem + 6 + 9
     assert seq.count("imf_conv_first_tc_h2_fwd") == 3 and seq.count("imf_conv_first_h2_fwd") == 0      # conv1 on the tensor-core path
     # the fusion module of the single-fragment plan is the batched chain with B = 1
     assert seq.count("imf_attention_fusion_fwd_batched") == 3 == seq.count("imf_attention_kv_batched") == seq.count("imf_batch_segments_n")
-    assert seq.count("imf_h2_unpack_l2norm") == 3 == seq.count("imf_identity_table") and seq.count("imf_pointwise_tail_h2_fwd") == 0
+    # tail: conv1_tr -> ReLU -> final -> L2 norm as one fused tensor-core kernel
+    assert seq.count("imf_tail_fused_h2_fwd") == 3 and seq.count("imf_h2_unpack_l2norm") == 0 == seq.count("imf_pointwise_tail_h2_fwd")
 
 
 def test_batched_plan_sequence_and_slices(fake_cuda):
