@@ -176,9 +176,11 @@ def layer_bytes(info, n_out, pairs):
     """Algorithmic bytes and FLOPs of one sparse-convolution layer, SURVEY.md 8(d): gathered inputs + in/out indices + weights once +
     output (+ the residual read of a block's second convolution); activations count 4 bytes per channel."""
     cin, cout, K = info["cin"], info["cout"], info["K"]
-    if K == 1:          # conv1_tr -> ReLU -> final (fused tail kernel): the two 1x1 layers as SURVEY accounts them
+    if K == 1:          # conv1_tr -> ReLU -> final -> L2 norm (fused tail kernel): input rows + both weight matrices + descriptors.  (SURVEY
+        # accounts the two 1x1 layers separately, i.e. adds a write and a read of the hidden layer, 8 * n * mid bytes; the fused kernel
+        # keeps it on the SM, so the conservative figure is used: a fraction above 1 would otherwise appear.)
         mid = info["mid"]
-        b = (4 * n_out * cin + 4 * cin * mid + 4 * n_out * mid) + (4 * n_out * mid + 4 * mid * cout + 4 * n_out * cout)
+        b = 4 * n_out * cin + 4 * cin * mid + 4 * mid * cout + 4 * n_out * cout
         return b, 2 * n_out * (cin * mid + mid * cout)
     b = 4 * pairs * cin + 8 * pairs + 4 * K * cin * cout + 4 * n_out * cout + (4 * n_out * cout if info["residual"] else 0)
     return b, 2 * pairs * cin * cout

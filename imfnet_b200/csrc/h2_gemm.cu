@@ -209,10 +209,10 @@ k_h2_gemm(const __grid_constant__ CUtensorMap tmA, const unsigned char* __restri
             HHalf8 hi[2], lo[2];
             big |= !(hg_split16(a, hi, lo) <= 60000.f);
             __half* yp = reinterpret_cast<__half*>(Cout) + (size_t)m * ldc + (n0 >> 6) * 128 + (n0 & 63);
-            reinterpret_cast<HHalf8*>(yp)[0] = hi[0];
-            reinterpret_cast<HHalf8*>(yp)[1] = hi[1];
-            reinterpret_cast<HHalf8*>(yp + 64)[0] = lo[0];
-            reinterpret_cast<HHalf8*>(yp + 64)[1] = lo[1];
+            tc::st_global_16(yp, hi[0]);
+            tc::st_global_16(yp + 8, hi[1]);
+            tc::st_global_16(yp + 64, lo[0]);
+            tc::st_global_16(yp + 72, lo[1]);
           }
         }
       }

@@ -627,10 +627,10 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
             if (out_row) {        // parity-grouped transposed convolution: table row grow describes output row out_row[grow]
               if (grow < n && grow < row_end) {      // rows past row_end belong to the next CTA's range
                 __half* yp = Yp + (size_t)__ldg(out_row + grow) * ldy + (c / kc_out) * 2 * kc_out + (c % kc_out);
-                reinterpret_cast<Half8*>(yp)[0] = hi[0];
-                reinterpret_cast<Half8*>(yp)[1] = hi[1];
-                reinterpret_cast<Half8*>(yp + kc_out)[0] = lo[0];
-                reinterpret_cast<Half8*>(yp + kc_out)[1] = lo[1];
+                tc::st_global_16(yp, hi[0]);
+                tc::st_global_16(yp + 8, hi[1]);
+                tc::st_global_16(yp + kc_out, lo[0]);
+                tc::st_global_16(yp + kc_out + 8, lo[1]);
               }
               continue;
             }
@@ -732,10 +732,10 @@ __global__ void __launch_bounds__(256) k_conv_g4_reduce(const float* __restrict_
   Half8 hi[2], lo[2];
   const bool big = !(g4_split16(a, hi, lo) <= 60000.f);
   __half* yp = Y + (size_t)(out_row ? __ldg(out_row + row) : row) * ldy + (c / kc_out) * 2 * kc_out + (c % kc_out);
-  reinterpret_cast<Half8*>(yp)[0] = hi[0];
-  reinterpret_cast<Half8*>(yp)[1] = hi[1];
-  reinterpret_cast<Half8*>(yp + kc_out)[0] = lo[0];
-  reinterpret_cast<Half8*>(yp + kc_out)[1] = lo[1];
+  tc::st_global_16(yp, hi[0]);
+  tc::st_global_16(yp + 8, hi[1]);
+  tc::st_global_16(yp + kc_out, lo[0]);
+  tc::st_global_16(yp + kc_out + 8, lo[1]);
   if (big && err) atomicOr(err, 0x10000);
 }
 

@@ -157,6 +157,16 @@ __device__ __forceinline__ void split_tf32(const float4& v, float4& hi, float4& 
   lo.w = v.w - hi.w;
 }
 
+// One 16-byte global store of a struct of four 32-bit members (e.g. four __half2).  Written as PTX because a struct assignment through a
+// reinterpret_cast pointer compiles to FOUR 4-byte STG when the compiler cannot prove the alignment (seen in the scattered-row epilogue of
+// the transposed convolutions: 32 M sector writes instead of 8 M, the launch was bound by them).
+template <class V16>
+__device__ __forceinline__ void st_global_16(void* p, const V16& v) {
+  static_assert(sizeof(V16) == 16, "16-byte value expected");
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
