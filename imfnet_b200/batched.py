@@ -46,7 +46,7 @@ class BatchedImagePlan(ImagePlan):
             self.t12d = self._replicate(self.t12d, self.P1, self.P2)
             self.t2 = self._replicate(self.t2, self.P2, self.P2)
             f32 = dict(dtype=torch.float32, device=dev)
-            self.col = torch.zeros((B * self.P0, self.STEM_K), **f32)
+            self._alloc_stem(B)
             self.s0 = torch.zeros((B * self.P0, self.C1), **f32)
             self.l1 = [torch.zeros((B * self.P1, self.C1), **f32) for _ in range(3)]
             self.l2 = [torch.zeros((B * self.P2, self.C2), **f32) for _ in range(3)]
@@ -73,10 +73,7 @@ class BatchedImagePlan(ImagePlan):
         L = _lib.lib()
         s = _lib.cur_stream()
         B = self.B
-        k, st, pd = self.stem_geom
-        _lib.check(L.imf_image_im2col_h2_batch(images.data_ptr(), 3, self.H, self.W, k, st, pd, self.STEM_K, self.col.data_ptr(),
-                                               2 * self.STEM_K, B, s))                               # all images, one launch
-        self._conv(L, self.stem, self.col, self.t_id0, B * self.P0, None, True, self.s0, s)
+        self._stem(L, images, B, s)
         _lib.check(L.imf_image_maxpool_h2_batch(self.s0.data_ptr(), 2 * self.C1, 64, self.C1, self.H1, self.W1, 3, 2, 1,
                                                 self.l1[0].data_ptr(), 2 * self.C1, B, s))
         n1, n2 = B * self.P1, B * self.P2

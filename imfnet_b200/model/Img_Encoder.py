@@ -92,6 +92,14 @@ class ImagePlan:
             bns = [backbone.bn1] + [bn for b in list(backbone.layer1) + list(backbone.layer2) for bn in (b.bn1, b.bn2)]
             A = self.act_scale = act_scale_from_bn(bns)          # stored activations of this branch = true * A (power of two)
             self.stem = _Conv(w0, backbone.bn1, 32, A, first=True)
+            # the ResNet stem proper (3 channels, 7x7 / 2 / 3 -> 64) as a fused implicit GEMM (csrc/stem_fused.cu): kernel laid out as
+            # [ky][8 columns kx = -1..6 x 4 channels][Cout] with zeros at kx = -1 and channel 3; other stems keep the im2col route
+            import os
+            self.stem_fused = None
+            if (k, s, pd) == (7, 2, 3) and c1.in_channels == 3 and c1.out_channels == 64 and os.environ.get("IMFNET_B200_STEM", "fused") != "im2col":
+                w7 = torch.zeros((7, 8, 4, 64), dtype=torch.float32, device=dev)
+                w7[:, 1:, :3, :] = c1.weight.detach().permute(2, 3, 1, 0)          # [ky, kx, c, o]
+                self.stem_fused = _Conv(w7.reshape(7, 32, 64), backbone.bn1, 32, A, first=True)
             self.blocks1 = [(_Conv(_w3(b.conv1), b.bn1, 64, A), _Conv(_w3(b.conv2), b.bn2, 64, A)) for b in backbone.layer1]
             self.blocks2 = []
             for b in backbone.layer2:
@@ -101,7 +109,7 @@ class ImagePlan:
             if self.C1 % 64 or self.C2 % 64 or backbone.layer1[0].downsample is not None or self.blocks2[0][2] is None:
                 raise NotImplementedError("unexpected ResNet prefix shape")
             f32 = dict(dtype=torch.float32, device=dev)
-            self.col = torch.zeros((self.P0, self.STEM_K), **f32)                 # h2 matrices have the footprint of fp32 [n, C]
+            self._alloc_stem(1)
             self.s0 = torch.zeros((self.P0, self.C1), **f32)
             self.l1 = [torch.zeros((self.P1, self.C1), **f32) for _ in range(3)]
             self.l2 = [torch.zeros((self.P2, self.C2), **f32) for _ in range(3)]
@@ -109,6 +117,28 @@ class ImagePlan:
             self.ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(self.C2))
             self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)        # head = arrival counters (zero)
             self.err = err if err is not None else torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def _alloc_stem(self, B: int):
+        """Scratch of the stem for B images: the pre-split image set (fused stem) or the im2col matrix."""
+        L = _lib.lib()
+        self.col = self.stem_ws = None
+        if self.stem_fused is not None:
+            self.stem_ws_bytes = int(L.imf_image_stem_workspace_bytes(self.H, self.W, B))
+            self.stem_ws = torch.zeros(self.stem_ws_bytes, dtype=torch.uint8, device=self.device)
+        else:
+            self.col = torch.zeros((B * self.P0, self.STEM_K), dtype=torch.float32, device=self.device)   # h2 footprint = fp32 [n, C]
+
+    def _stem(self, L, images, B: int, s):
+        """conv1 -> bn1 -> relu of the ResNet prefix for B images -> self.s0 (h2, pixel-major)."""
+        if self.stem_fused is not None:
+            c = self.stem_fused
+            _lib.check(L.imf_image_stem_h2_fwd(images.data_ptr(), self.H, self.W, B, c.packed.data_ptr(), c.scale.data_ptr(), c.shift.data_ptr(),
+                                               self.stem_ws.data_ptr(), self.stem_ws_bytes, self.s0.data_ptr(), 2 * self.C1, self.err.data_ptr(), s))
+            return
+        k, st, pd = self.stem_geom
+        _lib.check(L.imf_image_im2col_h2_batch(images.data_ptr(), 3, self.H, self.W, k, st, pd, self.STEM_K, self.col.data_ptr(),
+                                               2 * self.STEM_K, B, s))                               # all images, one launch
+        self._conv(L, self.stem, self.col, self.t_id0, B * self.P0, None, True, self.s0, s)
 
     def _conv(self, L, c: _Conv, X, tab, n_out, R, relu, Y, s):
         nbr_t, ld_n, mask = tab
@@ -123,9 +153,7 @@ class ImagePlan:
         """image fp32 [3,H,W] (contiguous, on the plan's device) -> fp32 tokens [H/8*W/8, 128] (a buffer owned by the plan)."""
         L = _lib.lib()
         s = _lib.cur_stream()
-        k, st, pd = self.stem_geom
-        _lib.check(L.imf_image_im2col_h2(image.data_ptr(), 3, self.H, self.W, k, st, pd, self.STEM_K, self.col.data_ptr(), 2 * self.STEM_K, s))
-        self._conv(L, self.stem, self.col, self.t_id0, self.P0, None, True, self.s0, s)
+        self._stem(L, image, 1, s)
         _lib.check(L.imf_image_maxpool_h2(self.s0.data_ptr(), 2 * self.C1, 64, self.C1, self.H1, self.W1, 3, 2, 1, self.l1[0].data_ptr(),
                                           2 * self.C1, s))
         x, tmp, out = self.l1

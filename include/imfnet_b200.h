@@ -258,6 +258,16 @@ int imf_image_conv_table(int32_t Hin, int32_t Win, int32_t ksize, int32_t stride
  * (multiple of 32) columns, written as an h2 matrix with chunk width 32 (ldy in halves). */
 int imf_image_im2col_h2(const float* image, int32_t C, int32_t H, int32_t W, int32_t ksize, int32_t stride, int32_t pad, int32_t Kpad,
                         void* Y, int32_t ldy, imf_stream_t stream);
+/* The ResNet stem (conv 7x7 / stride 2 / padding 3 of the 3-channel frame + BatchNorm + ReLU, model/resnet.py:195-207) as a fused
+ * implicit GEMM (csrc/stem_fused.cu): no im2col matrix in HBM.  image: fp32 [num_images, 3, H, W]; packed =
+ * imf_sparse_conv_h2_pack of the kernel laid out as [7 (ky), 32 (8 columns kx = -1..6 x 4 channels, zeros at kx = -1 and channel 3), 64]
+ * with kc_in 32 (multiplier folded into scale); Y: h2 matrix of 64 channels, chunk width 64, rows = pixels of image 0, then 1, ...;
+ * workspace >= imf_image_stem_workspace_bytes (the pre-split padded image set). */
+size_t imf_image_stem_workspace_bytes(int32_t H, int32_t W, int32_t num_images);
+int imf_image_stem_h2_fwd(const float* image, int32_t H, int32_t W, int32_t num_images, const void* packed, const float* scale,
+                          const float* shift, void* workspace, size_t workspace_bytes, void* Y, int32_t ldy, int32_t* err,
+                          imf_stream_t stream);
+
 /* Max pooling (torch semantics: padding never wins) on a pixel-major h2 matrix of C channels, chunk width kc. */
 int imf_image_maxpool_h2(const void* X, int32_t ldx, int32_t kc, int32_t C, int32_t Hin, int32_t Win, int32_t ksize, int32_t stride,
                          int32_t pad, void* Y, int32_t ldy, imf_stream_t stream);

@@ -347,6 +347,21 @@ class Emulator:
                 col0 = C * (kx + K * ky)
                 out[:, col0:col0 + C] = patch.reshape(C, -1).T
 
+    def do_imf_image_stem_h2_fwd(self, image, H, W, B, packed, scale, shift, ws, ws_bytes, Y, ldy, err):
+        Wk = self.packed[packed].reshape(7, 8, 4, 64)                   # [ky][kx = -1..6][c (4th = 0)][o], already times wmul
+        H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        for b in range(B):
+            img = vec(image + 4 * b * 3 * H * W, 3 * H * W).reshape(3, H, W)
+            P = np.zeros((4, 2 * (H1 - 1) + 7, 2 * (W1 - 1) + 8), dtype=np.float32)      # 3 pad rows on top, 4 pad columns on the left
+            P[:3, 3:3 + H, 4:4 + W] = img
+            acc = np.zeros((H1 * W1, 64), dtype=np.float32)
+            for ky in range(7):
+                for kx in range(8):
+                    patch = P[:, ky:ky + 2 * H1:2, kx:kx + 2 * W1:2]               # [4, H1, W1]
+                    acc += patch.reshape(4, -1).T @ Wk[ky, kx]
+            out = np.maximum(acc * vec(scale, 64) + vec(shift, 64), 0)
+            mat(Y + 2 * b * H1 * W1 * ldy, H1 * W1, 64, ldy // 2)[:] = out
+
     def do_imf_image_maxpool_h2(self, X, ldx, kc, C, Hin, Win, K, stride, pad, Y, ldy):
         Hout, Wout = (Hin + 2 * pad - K) // stride + 1, (Win + 2 * pad - K) // stride + 1
         x = mat(X, Hin * Win, C, ldx // 2).reshape(Hin, Win, C)

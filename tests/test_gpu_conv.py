@@ -408,6 +408,41 @@ def test_fused_tail_kernel_matches_fp32(n, c0, normalize, n_eff):
     assert torch.all(out[m:tile_end] == 0) and torch.isnan(out[tile_end:]).all()          # rows past the count: zeros inside the last tile, untouched beyond
 
 
+@pytest.mark.parametrize("H,W,B", [(48, 64, 1), (37, 53, 3), (120, 160, 2), (480, 640, 2)])
+def test_fused_stem_kernel_matches_conv2d(H, W, B):
+    """csrc/stem_fused.cu (7x7 / 2 / 3 convolution + folded BatchNorm + ReLU as an implicit GEMM on a pre-split image) against
+    torch's conv2d in float64 (model/resnet.py:195-207), odd sizes and several images per launch included."""
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    img = torch.rand(B, 3, H, W, generator=g)
+    Wt = torch.randn(64, 3, 7, 7, generator=g) / 12
+    scale, shift = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.2
+    ref = torch.nn.functional.conv2d(img.double(), Wt.double(), stride=2, padding=3)
+    ref = torch.relu(ref * scale.double().view(1, 64, 1, 1) + shift.double().view(1, 64, 1, 1))
+    H1, W1 = ref.shape[2], ref.shape[3]
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H1 * W1, 64)
+    L = _lib.lib()
+    s = _lib.cur_stream()
+    w7 = torch.zeros(7, 8, 4, 64)
+    w7[:, 1:, :3, :] = Wt.permute(2, 3, 1, 0)
+    w7 = w7.reshape(7, 32, 64).contiguous().cuda()
+    wmul = 2.0 ** np.floor(np.log2(2048.0 / float(Wt.abs().max())))
+    packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(7, 32, 64, 32)), dtype=torch.uint8, device="cuda")
+    _lib.check(L.imf_sparse_conv_h2_pack(w7.data_ptr(), 7, 32, 64, 32, float(wmul), packed.data_ptr(), s))
+    sc_d, sh_d, img_d = (scale / wmul).cuda(), shift.cuda(), img.cuda()
+    ws_bytes = int(L.imf_image_stem_workspace_bytes(H, W, B))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    Y = torch.zeros(B * H1 * W1, 64, device="cuda")                       # h2 footprint
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        _lib.check(L.imf_image_stem_h2_fwd(img_d.data_ptr(), H, W, B, packed.data_ptr(), sc_d.data_ptr(), sh_d.data_ptr(), ws.data_ptr(), ws_bytes,
+                                           Y.data_ptr(), 128, err.data_ptr(), s))
+    out = torch.empty(B * H1 * W1, 64, device="cuda")
+    _lib.check(L.imf_h2_unpack(Y.data_ptr(), 128, B * H1 * W1, 64, 64, out.data_ptr(), 64, s))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    close(out.cpu().double(), ref, H2_RTOL)
+
+
 def test_module_level_layers_match_standin(frag):
     """imfnet_b200.me layers used one by one (the un-fused route) give the oracle's numbers."""
     import imfnet_b200.me as ME
