@@ -305,29 +305,49 @@ __global__ void __launch_bounds__(256) k_parity_hist(const int4* __restrict__ co
   __syncthreads();
   if (threadIdx.x < 8) hist[blockIdx.x * 8 + threadIdx.x] = h[threadIdx.x];
 }
-// offsets[b][c] = rows of classes < c (all blocks) + rows of class c in blocks < b          (one block, 8 warps = 8 classes)
-// Lane l owns a contiguous range of blocks: its loads are independent of each other (the earlier form carried a warp scan -- and a
-// global-load latency -- through every group of 32 blocks: 32 us for 2000 blocks, three times per forward).
+// offsets[b][c] = rows of classes < c (all blocks) + rows of class c in blocks < b.  One block of 256 threads; thread t owns a
+// contiguous range of blocks with all 8 classes (two 16-byte loads per block, all independent), then a block-wide scan per class.
+// (The first form carried a warp scan and a global-load latency through every group of 32 blocks: 32 us for 2000 blocks.)
 __global__ void __launch_bounds__(256) k_parity_scan(const int* __restrict__ hist, int blocks, int* __restrict__ offs) {
-  __shared__ int total[8];
-  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per = (blocks + 31) / 32;
-  const int b0 = min(blocks, lane * per), b1 = min(blocks, b0 + per);
-  int sum = 0;
-#pragma unroll 8
-  for (int b = b0; b < b1; ++b) sum += __ldg(hist + b * 8 + c);
-  int incl = sum;
+  __shared__ int wsum[8][8];      // [warp][class]
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int per = (blocks + 255) / 256;
+  const int b0 = min(blocks, t * per), b1 = min(blocks, b0 + per);
+  int sum[8];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-  if (lane == 31) total[c] = incl;
-  __syncthreads();
-  int run = incl - sum;
-  for (int k = 0; k < c; ++k) run += total[k];
-#pragma unroll 8
+  for (int c = 0; c < 8; ++c) sum[c] = 0;
+#pragma unroll 4
   for (int b = b0; b < b1; ++b) {
-    const int v = __ldg(hist + b * 8 + c);
-    offs[b * 8 + c] = run;
-    run += v;
+    const int4 v0 = __ldg(reinterpret_cast<const int4*>(hist + b * 8)), v1 = __ldg(reinterpret_cast<const int4*>(hist + b * 8 + 4));
+    sum[0] += v0.x; sum[1] += v0.y; sum[2] += v0.z; sum[3] += v0.w;
+    sum[4] += v1.x; sum[5] += v1.y; sum[6] += v1.z; sum[7] += v1.w;
+  }
+  int run[8];                     // exclusive prefix of this thread inside its class
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    int incl = sum[c];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) wsum[w][c] = incl;
+    run[c] = incl - sum[c];
+  }
+  __syncthreads();
+  int base = 0;                   // rows of all lower classes
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    int before = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const int v = wsum[k][c]; total += v; if (k < w) before += v; }
+    run[c] += base + before;
+    base += total;
+  }
+#pragma unroll 4
+  for (int b = b0; b < b1; ++b) {
+    const int4 v0 = __ldg(reinterpret_cast<const int4*>(hist + b * 8)), v1 = __ldg(reinterpret_cast<const int4*>(hist + b * 8 + 4));
+    *reinterpret_cast<int4*>(offs + b * 8) = make_int4(run[0], run[1], run[2], run[3]);
+    *reinterpret_cast<int4*>(offs + b * 8 + 4) = make_int4(run[4], run[5], run[6], run[7]);
+    run[0] += v0.x; run[1] += v0.y; run[2] += v0.z; run[3] += v0.w;
+    run[4] += v1.x; run[5] += v1.y; run[6] += v1.z; run[7] += v1.w;
   }
 }
 __global__ void __launch_bounds__(256) k_parity_scatter(const int4* __restrict__ coords, const int* __restrict__ n_ptr, int n_max, int t,

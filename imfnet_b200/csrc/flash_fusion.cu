@@ -391,8 +391,8 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int ch = hf * 4;                       // 16-byte chunk index of this half's first token inside the 64-token (128-byte) row
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          *reinterpret_cast<FHalf8*>(p_s + tc::sw128_offset(r, ch + c4)) = FHalf8{hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]};
-          *reinterpret_cast<FHalf8*>(p_s + kQImg + tc::sw128_offset(r, ch + c4)) = FHalf8{lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]};
+          tc::st_shared_16(p_s + tc::sw128_offset(r, ch + c4), FHalf8{hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]});
+          tc::st_shared_16(p_s + kQImg + tc::sw128_offset(r, ch + c4), FHalf8{lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]});
         }
         tc::fence_proxy_async();
         __syncwarp();

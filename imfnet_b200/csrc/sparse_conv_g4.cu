@@ -643,10 +643,10 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
             }
             unsigned char* ph = stage + img_hi * kImg;
             unsigned char* pl = stage + img_lo * kImg;
-            *reinterpret_cast<Half8*>(ph + tc::sw128_offset(r_in, ch_hi)) = hi[0];
-            *reinterpret_cast<Half8*>(ph + tc::sw128_offset(r_in, ch_hi + 1)) = hi[1];
-            *reinterpret_cast<Half8*>(pl + tc::sw128_offset(r_in, ch_lo)) = lo[0];
-            *reinterpret_cast<Half8*>(pl + tc::sw128_offset(r_in, ch_lo + 1)) = lo[1];
+            tc::st_shared_16(ph + tc::sw128_offset(r_in, ch_hi), hi[0]);
+            tc::st_shared_16(ph + tc::sw128_offset(r_in, ch_hi + 1), hi[1]);
+            tc::st_shared_16(pl + tc::sw128_offset(r_in, ch_lo), lo[0]);
+            tc::st_shared_16(pl + tc::sw128_offset(r_in, ch_lo + 1), lo[1]);
           }
         }
         if (tid == 0 && j < 8) G4_TRACE(162 + 8 * j);

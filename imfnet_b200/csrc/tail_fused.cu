@@ -217,10 +217,10 @@ k_tail_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         THalf8 hi[2], lo[2];
         big |= !(tf_split16(a, hi, lo) <= 60000.f) && (m0 + r < n);
         const int ch = cb >> 3;
-        *reinterpret_cast<THalf8*>(hg + tc::sw128_offset(r, ch)) = hi[0];
-        *reinterpret_cast<THalf8*>(hg + tc::sw128_offset(r, ch + 1)) = hi[1];
-        *reinterpret_cast<THalf8*>(hg + kImg + tc::sw128_offset(r, ch)) = lo[0];
-        *reinterpret_cast<THalf8*>(hg + kImg + tc::sw128_offset(r, ch + 1)) = lo[1];
+        tc::st_shared_16(hg + tc::sw128_offset(r, ch), hi[0]);
+        tc::st_shared_16(hg + tc::sw128_offset(r, ch + 1), hi[1]);
+        tc::st_shared_16(hg + kImg + tc::sw128_offset(r, ch), lo[0]);
+        tc::st_shared_16(hg + kImg + tc::sw128_offset(r, ch + 1), lo[1]);
       }
       tc::fence_proxy_async();
       tc::tc_fence_before_sync();
@@ -252,7 +252,7 @@ k_tail_fused(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       // MMA 2 has completed (d2_full), so the hidden tile may be overwritten: rows [32 q, 32 q + 32) of the hi image stage this warp's output
 #pragma unroll
       for (int j = 0; j < kC2 / 4; ++j)
-        *reinterpret_cast<float4*>(stage + tc::sw128_offset(lane, j)) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        tc::st_shared_16(stage + tc::sw128_offset(lane, j), make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) {

@@ -167,6 +167,17 @@ __device__ __forceinline__ void st_global_16(void* p, const V16& v) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
 }
 
+// One 16-byte SHARED-memory store (STS.128) of a 16-byte value at a generic pointer into shared memory.  The epilogues' staging pointers
+// are derived from the 1024-aligned dynamic shared base through integer arithmetic, so the compiler only knows them as generic pointers
+// and emits ST.E.128 (generic store: tracked on the long scoreboard, the source registers are released late -- ncu showed the hi/lo
+// conversions of the next 16 channels waiting for them); st.shared is explicit here.
+template <class V16>
+__device__ __forceinline__ void st_shared_16(void* p, const V16& v) {
+  static_assert(sizeof(V16) == 16, "16-byte value expected");
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -93,13 +93,13 @@ class ImagePlan:
             A = self.act_scale = act_scale_from_bn(bns)          # stored activations of this branch = true * A (power of two)
             self.stem = _Conv(w0, backbone.bn1, 32, A, first=True)
             # the ResNet stem proper (3 channels, 7x7 / 2 / 3 -> 64) as a fused implicit GEMM (csrc/stem_fused.cu): kernel laid out as
-            # [ky][8 columns kx = -1..6 x 4 channels][Cout] with zeros at kx = -1 and channel 3; other stems keep the im2col route
+            # [pair of kernel rows][2 x (8 columns kx = -1..6 x 4 channels)][Cout] with zeros at kx = -1 and channel 3; other stems keep the im2col route
             import os
             self.stem_fused = None
             if (k, s, pd) == (7, 2, 3) and c1.in_channels == 3 and c1.out_channels == 64 and os.environ.get("IMFNET_B200_STEM", "fused") != "im2col":
-                w7 = torch.zeros((7, 8, 4, 64), dtype=torch.float32, device=dev)
-                w7[:, 1:, :3, :] = c1.weight.detach().permute(2, 3, 1, 0)          # [ky, kx, c, o]
-                self.stem_fused = _Conv(w7.reshape(7, 32, 64), backbone.bn1, 32, A, first=True)
+                w7 = torch.zeros((8, 8, 4, 64), dtype=torch.float32, device=dev)          # (an 8th, all-zero kernel row completes the last pair)
+                w7[:7, 1:, :3, :] = c1.weight.detach().permute(2, 3, 1, 0)         # [ky, kx, c, o]
+                self.stem_fused = _Conv(w7.reshape(4, 64, 64), backbone.bn1, 64, A, first=True)      # slabs of two kernel rows
             self.blocks1 = [(_Conv(_w3(b.conv1), b.bn1, 64, A), _Conv(_w3(b.conv2), b.bn2, 64, A)) for b in backbone.layer1]
             self.blocks2 = []
             for b in backbone.layer2:

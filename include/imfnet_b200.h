@@ -260,8 +260,8 @@ int imf_image_im2col_h2(const float* image, int32_t C, int32_t H, int32_t W, int
                         void* Y, int32_t ldy, imf_stream_t stream);
 /* The ResNet stem (conv 7x7 / stride 2 / padding 3 of the 3-channel frame + BatchNorm + ReLU, model/resnet.py:195-207) as a fused
  * implicit GEMM (csrc/stem_fused.cu): no im2col matrix in HBM.  image: fp32 [num_images, 3, H, W]; packed =
- * imf_sparse_conv_h2_pack of the kernel laid out as [7 (ky), 32 (8 columns kx = -1..6 x 4 channels, zeros at kx = -1 and channel 3), 64]
- * with kc_in 32 (multiplier folded into scale); Y: h2 matrix of 64 channels, chunk width 64, rows = pixels of image 0, then 1, ...;
+ * imf_sparse_conv_h2_pack of the kernel laid out as [4 (pairs of kernel rows), 64 (per row: 8 columns kx = -1..6 x 4 channels, zeros at
+ * kx = -1, channel 3 and the missing 8th row), 64] with kc_in 64 (multiplier folded into scale); Y: h2 matrix of 64 channels, chunk width 64, rows = pixels of image 0, then 1, ...;
  * workspace >= imf_image_stem_workspace_bytes (the pre-split padded image set). */
 size_t imf_image_stem_workspace_bytes(int32_t H, int32_t W, int32_t num_images);
 int imf_image_stem_h2_fwd(const float* image, int32_t H, int32_t W, int32_t num_images, const void* packed, const float* scale,

@@ -348,7 +348,7 @@ class Emulator:
                 out[:, col0:col0 + C] = patch.reshape(C, -1).T
 
     def do_imf_image_stem_h2_fwd(self, image, H, W, B, packed, scale, shift, ws, ws_bytes, Y, ldy, err):
-        Wk = self.packed[packed].reshape(7, 8, 4, 64)                   # [ky][kx = -1..6][c (4th = 0)][o], already times wmul
+        Wk = self.packed[packed].reshape(8, 8, 4, 64)                   # [ky (8th = 0)][kx = -1..6][c (4th = 0)][o], already times wmul
         H1, W1 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         for b in range(B):
             img = vec(image + 4 * b * 3 * H * W, 3 * H * W).reshape(3, H, W)

@@ -422,12 +422,12 @@ def test_fused_stem_kernel_matches_conv2d(H, W, B):
     ref = ref.permute(0, 2, 3, 1).reshape(B * H1 * W1, 64)
     L = _lib.lib()
     s = _lib.cur_stream()
-    w7 = torch.zeros(7, 8, 4, 64)
-    w7[:, 1:, :3, :] = Wt.permute(2, 3, 1, 0)
-    w7 = w7.reshape(7, 32, 64).contiguous().cuda()
+    w7 = torch.zeros(8, 8, 4, 64)
+    w7[:7, 1:, :3, :] = Wt.permute(2, 3, 1, 0)
+    w7 = w7.reshape(4, 64, 64).contiguous().cuda()
     wmul = 2.0 ** np.floor(np.log2(2048.0 / float(Wt.abs().max())))
-    packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(7, 32, 64, 32)), dtype=torch.uint8, device="cuda")
-    _lib.check(L.imf_sparse_conv_h2_pack(w7.data_ptr(), 7, 32, 64, 32, float(wmul), packed.data_ptr(), s))
+    packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(4, 64, 64, 64)), dtype=torch.uint8, device="cuda")
+    _lib.check(L.imf_sparse_conv_h2_pack(w7.data_ptr(), 4, 64, 64, 64, float(wmul), packed.data_ptr(), s))
     sc_d, sh_d, img_d = (scale / wmul).cuda(), shift.cuda(), img.cuda()
     ws_bytes = int(L.imf_image_stem_workspace_bytes(H, W, B))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
