@@ -179,13 +179,18 @@ class BatchGraphPlan(GraphPlan):
 
 
 @torch.no_grad()
-def forward_batches(model, frags, batch: int, streams: int = 2, out=None):
+def forward_batches(model, frags, batch: int, streams: int = 2, out=None, carry=None):
     """frags = [(coords int32 [N,4], feats fp32 [N,Cin], image fp32 [1,3,H,W]), ...], all on the host (ideally pinned) or all on
     the model's device.  Consecutive groups of `batch` fragments go through one `BatchGraphPlan` replay each, `streams` plans in
     flight (the copies of one group overlap the compute of the other); a trailing group smaller than `batch`, groups with images
     of different sizes and groups that overflow a plan's capacity take `forward_many_host` / `forward_many`.
     Returns the descriptors [N, out_channels] per fragment in order: device tensors for device inputs, pinned host tensors
-    (`out[i]` when given) for host inputs."""
+    (`out[i]` when given) for host inputs.
+
+    carry (a dict the caller keeps, initially empty): streaming use -- the call returns WITHOUT waiting for the groups still in flight,
+    so the next call's host->device copies and first kernels overlap this call's last groups and their device->host copies; the
+    entries of the returned list that belong to such groups are filled in (the same list object) when a later call or
+    `drain_batches(carry)` retires them.  A plan (and with `out` its host buffers) is only reused after its previous group finished."""
     from . import me as ME
     if model.training:
         raise NotImplementedError("imfnet_b200 implements the eval-mode forward")
@@ -199,27 +204,27 @@ def forward_batches(model, frags, batch: int, streams: int = 2, out=None):
         raise ValueError("batch must be in [1, 255]")
     on_device = len(frags) > 0 and frags[0][0].is_cuda
     outs = [None] * len(frags)
-    inflight = []
+    inflight = [] if carry is None else carry.setdefault("inflight", [])
     bucket = model.ROW_BUCKET
 
-    def sequential(idx):
-        if on_device:
-            items = [(ME.SparseTensor(frags[i][1], coordinates=frags[i][0]), frags[i][2]) for i in idx]
-            res = [o.F for o in model.forward_many(items, streams=max(2, streams))]
+    def sequential(idx, fr=frags, dst=outs, o=out):
+        if fr[idx[0]][0].is_cuda:
+            items = [(ME.SparseTensor(fr[i][1], coordinates=fr[i][0]), fr[i][2]) for i in idx]
+            res = [r.F for r in model.forward_many(items, streams=max(2, streams))]
         else:
-            res = model.forward_many_host([frags[i] for i in idx], streams=max(2, streams), out=None if out is None else [out[i] for i in idx])
+            res = model.forward_many_host([fr[i] for i in idx], streams=max(2, streams), out=None if o is None else [o[i] for i in idx])
         for i, r in zip(idx, res):
-            outs[i] = r
+            dst[i] = r
 
     def retire():
-        idx, g = inflight.pop(0)
+        idx, g, fr, dst, o = inflight.pop(0)          # (a group of an earlier streaming call carries its own lists)
         try:
             res = g.finish_batch()
         except PlanCapacityError:
-            sequential(idx)
+            sequential(idx, fr, dst, o)
             return
         for i, r in zip(idx, res):
-            outs[i] = r
+            dst[i] = r
 
     groups = len(frags) // B
     for gi in range(groups):
@@ -250,10 +255,21 @@ def forward_batches(model, frags, batch: int, streams: int = 2, out=None):
                     for j, i in enumerate(idx)]
         g.launch_batch([(frags[i][0], frags[i][1].float(), frags[i][2].float()) for i in idx], g.stream, out_hosts=dsts)
         model._last_batch_plan = g          # (bench.py times this plan's layers in place)
-        inflight.append((idx, g))
-    while inflight:
-        retire()
+        inflight.append((idx, g, frags, outs, out))
     tail = list(range(groups * B, len(frags)))
+    if carry is None or tail:
+        while inflight:
+            retire()
     if tail:
         sequential(tail)
+    if carry is not None:
+        carry["retire"] = retire
     return outs
+
+
+def drain_batches(carry):
+    """Waits for every group a streaming `forward_batches(..., carry=carry)` sequence left in flight (their entries of the lists returned
+    by those calls are filled in)."""
+    inflight = carry.get("inflight", [])
+    while inflight:
+        carry["retire"]()

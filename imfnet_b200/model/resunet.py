@@ -224,10 +224,16 @@ class ResUNet2(ME.MinkowskiNetwork):
             retire()
         return outs
 
-    def forward_batches(self, frags, batch: int, streams: int = 2, out=None):
-        """Throughput form for many fragments: groups of `batch` fragments per captured-graph replay (imfnet_b200/batched.py)."""
+    def forward_batches(self, frags, batch: int, streams: int = 2, out=None, carry=None):
+        """Throughput form for many fragments: groups of `batch` fragments per captured-graph replay (imfnet_b200/batched.py).
+        carry: a dict kept by the caller for streaming use (the call does not wait for its last groups; `drain_batches(carry)` does)."""
         from ..batched import forward_batches
-        return forward_batches(self, frags, batch, streams, out)
+        return forward_batches(self, frags, batch, streams, out, carry)
+
+    @staticmethod
+    def drain_batches(carry):
+        from ..batched import drain_batches
+        drain_batches(carry)
 
     def _forward_graph(self, x, image):
         plan = self._plan

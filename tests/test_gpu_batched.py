@@ -48,6 +48,27 @@ def test_batched_plan_matches_single_forwards(cuda_model, on_device):
         assert torch.equal(o.cpu(), o2.cpu())
 
 
+@pytest.mark.parametrize("on_device", [True, False])
+def test_streaming_calls_give_the_same_descriptors(cuda_model, on_device):
+    """forward_batches(..., carry=state) -- what bench.py times: calls that do not wait for their last groups, drained at the end --
+    returns bit-identical descriptors to the blocking call, for device inputs and for pinned host inputs with caller buffers."""
+    frags = fragments([3000, 5000, 4100, 2500], 160, 120)
+    if on_device:
+        inp = [(c.cuda(), f.cuda(), im.cuda()) for c, f, im in frags]
+    else:
+        inp = [(c.pin_memory(), f.pin_memory(), im.pin_memory()) for c, f, im in frags]
+    ref = [o.cpu().clone() for o in cuda_model.forward_batches(inp, batch=2, streams=2)]
+    carry, results = {}, []
+    for _ in range(3):
+        outs = None if on_device else [torch.empty((len(c), 32)).pin_memory() for c, _f, _im in frags]
+        results.append(cuda_model.forward_batches(inp, batch=2, streams=2, out=outs, carry=carry))
+    assert any(r is None for r in results[-1])          # the last call's groups are still in flight
+    cuda_model.drain_batches(carry)
+    for res in results:
+        for o, r in zip(res, ref):
+            assert o is not None and torch.equal(o.cpu(), r)
+
+
 def test_batched_plan_rejects_wrong_batch_index_capacity(cuda_model):
     """An item with more stride-8 rows than the plan's per-item capacity must fall back, not truncate."""
     frags = fragments([3000, 3000], 160, 120)

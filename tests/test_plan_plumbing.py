@@ -179,6 +179,25 @@ def test_batched_plan_sequence_and_slices(fake_cuda):
     assert kvc[2] == ip.tokens.data_ptr() and kvc[3] == ip.P2 and kvc[4] == 2
 
 
+def test_streaming_calls_leave_groups_in_flight_until_drained(fake_cuda):
+    """forward_batches(..., carry=state): a call does not wait for its last groups (the next call's copies overlap them); a plan is
+    only reused after its previous group retired; drain_batches fills in what is left, in the lists the calls returned."""
+    m = make_model()
+    frags = fragments([700, 900, 650, 800])                                  # two groups of 2
+    carry = {}
+    o1, o2, o3 = ([torch.full((len(c), 32), float("nan")) for c, _f, _im in frags] for _ in range(3))
+    r1 = m.forward_batches(frags, batch=2, streams=2, out=o1, carry=carry)
+    assert r1 == [None] * 4 and len(carry["inflight"]) == 2                  # both groups still in flight
+    r2 = m.forward_batches(frags, batch=2, streams=2, out=o2, carry=carry)   # same plans: the first call's groups are retired one by one
+    assert all(r is not None and tuple(r.shape) == (len(c), 32) for r, (c, _f, _im) in zip(r1, frags))
+    assert r2 == [None] * 4 and len(carry["inflight"]) == 2
+    m.drain_batches(carry)
+    assert not carry["inflight"] and all(tuple(r.shape) == (len(c), 32) for r, (c, _f, _im) in zip(r2, frags))
+    # a call without carry behaves as before (everything retired on return)
+    r3 = m.forward_batches(frags, batch=2, streams=2, out=o3)
+    assert all(r is not None for r in r3)
+
+
 def test_batched_plan_errors(fake_cuda):
     from imfnet_b200.batched import BatchGraphPlan
     from imfnet_b200.engine import PlanCapacityError
