@@ -75,6 +75,9 @@ SIGNATURES = {
     "imf_conv_first_tc_h2_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _sz, _p, _p]),
     "imf_conv_first_h2_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p]),
     "imf_tail_fused_h2_fwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _i32, _p, _p]),
+    "imf_image_p8_bytes": (_sz, [_i32, _i32, _i32]),
+    "imf_image_maxpool_p8": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p]),
+    "imf_image_conv3x3_p8_fwd": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _i32, _p, _i32, _i32, _p, _p]),
     "imf_image_stem_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32]),
     "imf_image_stem_h2_fwd": (C.c_int, [_p, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p, _i32, _p, _p]),
     "imf_pointwise_tail_h2_fwd": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _p, _i32, _p]),

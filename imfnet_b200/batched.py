@@ -48,7 +48,7 @@ class BatchedImagePlan(ImagePlan):
             f32 = dict(dtype=torch.float32, device=dev)
             self._alloc_stem(B)
             self.s0 = torch.zeros((B * self.P0, self.C1), **f32)
-            self.l1 = [torch.zeros((B * self.P1, self.C1), **f32) for _ in range(3)]
+            self._alloc_layer1(B)
             self.l2 = [torch.zeros((B * self.P2, self.C2), **f32) for _ in range(3)]
             self.tokens = torch.zeros((B * self.P2, self.C2), **f32)
 
@@ -74,14 +74,8 @@ class BatchedImagePlan(ImagePlan):
         s = _lib.cur_stream()
         B = self.B
         self._stem(L, images, B, s)
-        _lib.check(L.imf_image_maxpool_h2_batch(self.s0.data_ptr(), 2 * self.C1, 64, self.C1, self.H1, self.W1, 3, 2, 1,
-                                                self.l1[0].data_ptr(), 2 * self.C1, B, s))
-        n1, n2 = B * self.P1, B * self.P2
-        x, tmp, out = self.l1
-        for c1, c2 in self.blocks1:
-            self._conv(L, c1, x, self.t1, n1, None, True, tmp, s)
-            self._conv(L, c2, tmp, self.t1, n1, x, True, out, s)
-            x, out = out, x
+        n2 = B * self.P2
+        x = self._layer1(L, B, s)
         y, tmp, out = self.l2
         for c1, c2, down in self.blocks2:
             if down is not None:

@@ -111,7 +111,10 @@ class ImagePlan:
             f32 = dict(dtype=torch.float32, device=dev)
             self._alloc_stem(1)
             self.s0 = torch.zeros((self.P0, self.C1), **f32)
-            self.l1 = [torch.zeros((self.P1, self.C1), **f32) for _ in range(3)]
+            # layer1 (3x3 / 1, 64 -> 64) on the plane-layout implicit GEMM (csrc/image_conv_p8.cu); IMFNET_B200_LAYER1=g4 keeps the gather route
+            import os
+            self.layer1_p8 = self.C1 == 64 and all(c.K == 9 for pair in self.blocks1 for c in pair) and os.environ.get("IMFNET_B200_LAYER1", "p8") != "g4"
+            self._alloc_layer1(1)
             self.l2 = [torch.zeros((self.P2, self.C2), **f32) for _ in range(3)]
             self.tokens = torch.zeros((self.P2, self.C2), **f32)
             self.ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(self.C2))
@@ -127,6 +130,43 @@ class ImagePlan:
             self.stem_ws = torch.zeros(self.stem_ws_bytes, dtype=torch.uint8, device=self.device)
         else:
             self.col = torch.zeros((B * self.P0, self.STEM_K), dtype=torch.float32, device=self.device)   # h2 footprint = fp32 [n, C]
+
+    def _alloc_layer1(self, B: int):
+        """Activations of layer1 for B images: three P8 plane buffers (zero borders) + the pixel-major output layer2 reads, or three
+        pixel-major h2 matrices (gather route)."""
+        L = _lib.lib()
+        f32 = dict(dtype=torch.float32, device=self.device)
+        if self.layer1_p8:
+            nbytes = int(L.imf_image_p8_bytes(self.H2, self.W2, B))
+            self.l1p = [torch.zeros(nbytes, dtype=torch.uint8, device=self.device) for _ in range(3)]
+            self.l1 = [torch.zeros((B * self.P1, self.C1), **f32)]
+        else:
+            self.l1 = [torch.zeros((B * self.P1, self.C1), **f32) for _ in range(3)]
+
+    def _layer1(self, L, B: int, s):
+        """maxpool + layer1 on self.s0 -> pixel-major h2 matrix [B * P1, C1] (returned)."""
+        n1 = B * self.P1
+        if not self.layer1_p8:
+            _lib.check(L.imf_image_maxpool_h2_batch(self.s0.data_ptr(), 2 * self.C1, 64, self.C1, self.H1, self.W1, 3, 2, 1,
+                                                    self.l1[0].data_ptr(), 2 * self.C1, B, s))
+            x, tmp, out = self.l1
+            for c1, c2 in self.blocks1:
+                self._conv(L, c1, x, self.t1, n1, None, True, tmp, s)
+                self._conv(L, c2, tmp, self.t1, n1, x, True, out, s)
+                x, out = out, x
+            return x
+        _lib.check(L.imf_image_maxpool_p8(self.s0.data_ptr(), 2 * self.C1, 64, self.H1, self.W1, 3, 2, 1, self.l1p[0].data_ptr(), B, s))
+        x, tmp, out = self.l1p
+        err = self.err.data_ptr()
+        for i, (c1, c2) in enumerate(self.blocks1):
+            last = i == len(self.blocks1) - 1
+            _lib.check(L.imf_image_conv3x3_p8_fwd(x.data_ptr(), self.H2, self.W2, B, c1.packed.data_ptr(), c1.scale.data_ptr(), c1.shift.data_ptr(),
+                                                  None, 1, tmp.data_ptr(), 0, 0, err, s))
+            dst = self.l1[0] if last else out          # the last block writes the pixel-major matrix the strided convolutions of layer2 gather from
+            _lib.check(L.imf_image_conv3x3_p8_fwd(tmp.data_ptr(), self.H2, self.W2, B, c2.packed.data_ptr(), c2.scale.data_ptr(), c2.shift.data_ptr(),
+                                                  x.data_ptr(), 1, dst.data_ptr(), 1 if last else 0, 2 * self.C1, err, s))
+            x, out = out, x
+        return self.l1[0]
 
     def _stem(self, L, images, B: int, s):
         """conv1 -> bn1 -> relu of the ResNet prefix for B images -> self.s0 (h2, pixel-major)."""
@@ -154,13 +194,7 @@ class ImagePlan:
         L = _lib.lib()
         s = _lib.cur_stream()
         self._stem(L, image, 1, s)
-        _lib.check(L.imf_image_maxpool_h2(self.s0.data_ptr(), 2 * self.C1, 64, self.C1, self.H1, self.W1, 3, 2, 1, self.l1[0].data_ptr(),
-                                          2 * self.C1, s))
-        x, tmp, out = self.l1
-        for c1, c2 in self.blocks1:
-            self._conv(L, c1, x, self.t1, self.P1, None, True, tmp, s)
-            self._conv(L, c2, tmp, self.t1, self.P1, x, True, out, s)
-            x, out = out, x
+        x = self._layer1(L, 1, s)
         y, tmp, out = self.l2
         for i, (c1, c2, down) in enumerate(self.blocks2):
             if down is not None:          # first block: stride 2, 1x1 projection of the skip path

@@ -258,6 +258,20 @@ int imf_image_conv_table(int32_t Hin, int32_t Win, int32_t ksize, int32_t stride
  * (multiple of 32) columns, written as an h2 matrix with chunk width 32 (ldy in halves). */
 int imf_image_im2col_h2(const float* image, int32_t C, int32_t H, int32_t W, int32_t ksize, int32_t stride, int32_t pad, int32_t Kpad,
                         void* Y, int32_t ldy, imf_stream_t stream);
+/* ResNet layer1 on a plane layout ("P8", csrc/image_conv_p8.cu): a 64-channel activation of num_images H x W images is stored as 16 planes
+ * per image (8 chunks of 8 channels x {hi, lo} fp16 halves) of (H + 2) x (W + 2) zero-bordered pixels, 16 bytes per pixel and plane; a
+ * 3x3 / stride-1 convolution then reads each input pixel once per 16 x 8 tile and forms the nine taps' operands as shifted un-swizzled
+ * views of the same shared-memory patch.  imf_image_p8_bytes: size of such a buffer (zero-initialise it once).  imf_image_maxpool_p8:
+ * model/resnet.py:203 from a pixel-major h2 matrix into P8.  imf_image_conv3x3_p8_fwd: Y = act(conv(X) * scale + shift (+ residual)),
+ * model/resnet.py:60-76; packed = imf_sparse_conv_h2_pack(W as [9 (tap kx + 3 ky), 64, 64], kc_in 64); Y is P8 (y_pixel_major == 0) or a
+ * pixel-major h2 matrix of chunk width 64 with ldy halves. */
+size_t imf_image_p8_bytes(int32_t H, int32_t W, int32_t num_images);
+int imf_image_maxpool_p8(const void* X, int32_t ldx, int32_t kc, int32_t Hin, int32_t Win, int32_t ksize, int32_t stride, int32_t pad, void* Y,
+                         int32_t num_images, imf_stream_t stream);
+int imf_image_conv3x3_p8_fwd(const void* X, int32_t H, int32_t W, int32_t num_images, const void* packed, const float* scale,
+                             const float* shift, const void* residual, int32_t relu, void* Y, int32_t y_pixel_major, int32_t ldy,
+                             int32_t* err, imf_stream_t stream);
+
 /* The ResNet stem (conv 7x7 / stride 2 / padding 3 of the 3-channel frame + BatchNorm + ReLU, model/resnet.py:195-207) as a fused
  * implicit GEMM (csrc/stem_fused.cu): no im2col matrix in HBM.  image: fp32 [num_images, 3, H, W]; packed =
  * imf_sparse_conv_h2_pack of the kernel laid out as [4 (pairs of kernel rows), 64 (per row: 8 columns kx = -1..6 x 4 channels, zeros at

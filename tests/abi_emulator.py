@@ -362,6 +362,44 @@ class Emulator:
             out = np.maximum(acc * vec(scale, 64) + vec(shift, 64), 0)
             mat(Y + 2 * b * H1 * W1 * ldy, H1 * W1, 64, ldy // 2)[:] = out
 
+    # P8 plane layout, emulated as fp32 [B][8 chunks][Hp][Wp][8] in the first half of the buffer (the real one holds hi and lo planes)
+    @staticmethod
+    def _p8(ptr, H, W, B):
+        return vec(ptr, B * 8 * (H + 2) * (W + 2) * 8).reshape(B, 8, H + 2, W + 2, 8)
+
+    def do_imf_image_maxpool_p8(self, X, ldx, kc, Hin, Win, K, stride, pad, Y, B):
+        Hout, Wout = (Hin + 2 * pad - K) // stride + 1, (Win + 2 * pad - K) // stride + 1
+        out = self._p8(Y, Hout, Wout, B)
+        for b in range(B):
+            x = mat(X + 2 * b * Hin * Win * ldx, Hin * Win, 64, ldx // 2).reshape(Hin, Win, 64)
+            P = np.full((Hin + 2 * pad, Win + 2 * pad, 64), -np.inf, dtype=np.float32)
+            P[pad:pad + Hin, pad:pad + Win] = x
+            m = np.full((Hout, Wout, 64), -np.inf, dtype=np.float32)
+            for ky in range(K):
+                for kx in range(K):
+                    m = np.maximum(m, P[ky:ky + stride * Hout:stride, kx:kx + stride * Wout:stride])
+            out[b, :, 1:-1, 1:-1, :] = m.reshape(Hout, Wout, 8, 8).transpose(2, 0, 1, 3)
+
+    def do_imf_image_conv3x3_p8_fwd(self, X, H, W, B, packed, scale, shift, residual, relu, Y, y_pixel_major, ldy, err):
+        Wk = self.packed[packed]                                          # [9, 64, 64], tap kx + 3 ky, already times wmul
+        x = self._p8(X, H, W, B)
+        assert not x[:, :, 0].any() and not x[:, :, -1].any() and not x[:, :, :, 0].any() and not x[:, :, :, -1].any(), "P8 border must be zero"
+        for b in range(B):
+            img = x[b].transpose(1, 2, 0, 3).reshape(H + 2, W + 2, 64)      # padded [Hp, Wp, C]
+            acc = np.zeros((H * W, 64), dtype=np.float32)
+            for ky in range(3):
+                for kx in range(3):
+                    acc += img[ky:ky + H, kx:kx + W].reshape(H * W, 64) @ Wk[kx + 3 * ky]
+            acc = acc * vec(scale, 64) + vec(shift, 64)
+            if residual:
+                acc = acc + self._p8(residual, H, W, B)[b].transpose(1, 2, 0, 3).reshape(H + 2, W + 2, 64)[1:-1, 1:-1].reshape(H * W, 64)
+            if relu:
+                acc = np.maximum(acc, 0)
+            if y_pixel_major:
+                mat(Y + 2 * b * H * W * ldy, H * W, 64, ldy // 2)[:] = acc
+            else:
+                self._p8(Y, H, W, B)[b, :, 1:-1, 1:-1, :] = acc.reshape(H, W, 8, 8).transpose(2, 0, 1, 3)
+
     def do_imf_image_maxpool_h2(self, X, ldx, kc, C, Hin, Win, K, stride, pad, Y, ldy):
         Hout, Wout = (Hin + 2 * pad - K) // stride + 1, (Win + 2 * pad - K) // stride + 1
         x = mat(X, Hin * Win, C, ldx // 2).reshape(Hin, Win, C)

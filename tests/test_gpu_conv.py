@@ -443,6 +443,84 @@ def test_fused_stem_kernel_matches_conv2d(H, W, B):
     close(out.cpu().double(), ref, H2_RTOL)
 
 
+def _p8_pack(x):
+    """fp32 [B, H, W, 64] -> the P8 plane buffer (fp16 [B, 16, H + 2, W + 2, 8], zero border) of csrc/image_conv_p8.cu."""
+    B, H, W, C = x.shape
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    buf = torch.zeros(B, 16, H + 2, W + 2, 8, dtype=torch.float16)
+    buf[:, :8, 1:-1, 1:-1] = hi.reshape(B, H, W, 8, 8).permute(0, 3, 1, 2, 4)
+    buf[:, 8:, 1:-1, 1:-1] = lo.reshape(B, H, W, 8, 8).permute(0, 3, 1, 2, 4)
+    return buf
+
+
+def _p8_unpack(buf):
+    v = buf[:, :8].float() + buf[:, 8:].float()                       # [B, 8, Hp, Wp, 8]
+    assert not v[:, :, 0].any() and not v[:, :, -1].any() and not v[:, :, :, 0].any() and not v[:, :, :, -1].any(), "border written"
+    B, _, Hp, Wp, _ = v.shape
+    return v[:, :, 1:-1, 1:-1].permute(0, 2, 3, 1, 4).reshape(B, Hp - 2, Wp - 2, 64)
+
+
+@pytest.mark.parametrize("H,W,B", [(16, 8, 1), (37, 53, 2), (120, 160, 2), (30, 40, 11)])
+def test_plane_layout_conv3x3_matches_conv2d(H, W, B):
+    """csrc/image_conv_p8.cu: 3x3 / stride 1 / padding 1, 64 -> 64 channels + affine + residual + ReLU on the P8 plane layout against
+    torch's conv2d in float64 (model/resnet.py:60-76), partial tiles and more tiles than SMs included; P8 and pixel-major outputs."""
+    g = torch.Generator().manual_seed(H * 100 + W)
+    x = torch.randn(B, H, W, 64, generator=g)
+    res = torch.randn(B, H, W, 64, generator=g)
+    Wt = torch.randn(64, 64, 3, 3, generator=g) / 24
+    scale, shift = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.2
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), Wt.double(), padding=1).permute(0, 2, 3, 1)
+    ref_plain = ref * scale.double() + shift.double()
+    ref_block = torch.relu(ref_plain + res.double())
+    L = _lib.lib()
+    s = _lib.cur_stream()
+    w9 = Wt.permute(2, 3, 1, 0).reshape(9, 64, 64).contiguous().cuda()
+    wmul = 2.0 ** np.floor(np.log2(2048.0 / float(Wt.abs().max())))
+    packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(9, 64, 64, 64)), dtype=torch.uint8, device="cuda")
+    _lib.check(L.imf_sparse_conv_h2_pack(w9.data_ptr(), 9, 64, 64, 64, float(wmul), packed.data_ptr(), s))
+    sc_d, sh_d = (scale / wmul).cuda(), shift.cuda()
+    nbytes = int(L.imf_image_p8_bytes(H, W, B))
+    xb, rb = _p8_pack(x).cuda(), _p8_pack(res).cuda()
+    assert xb.numel() * 2 == nbytes
+    yb = torch.zeros_like(xb)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    # P8 output, no residual, no ReLU
+    _lib.check(L.imf_image_conv3x3_p8_fwd(xb.data_ptr(), H, W, B, packed.data_ptr(), sc_d.data_ptr(), sh_d.data_ptr(), None, 0, yb.data_ptr(), 0, 0,
+                                          err.data_ptr(), s))
+    torch.cuda.synchronize()
+    close(_p8_unpack(yb.cpu()).double(), ref_plain, H2_RTOL)
+    # pixel-major output with residual + ReLU (what the last block of layer1 does), twice
+    ypm = torch.full((B * H * W, 64), float("nan"), device="cuda")          # h2 footprint
+    for _ in range(2):
+        _lib.check(L.imf_image_conv3x3_p8_fwd(xb.data_ptr(), H, W, B, packed.data_ptr(), sc_d.data_ptr(), sh_d.data_ptr(), rb.data_ptr(), 1,
+                                              ypm.data_ptr(), 1, 128, err.data_ptr(), s))
+    out = torch.empty(B * H * W, 64, device="cuda")
+    _lib.check(L.imf_h2_unpack(ypm.data_ptr(), 128, B * H * W, 64, 64, out.data_ptr(), 64, s))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    close(out.cpu().double().reshape(B, H, W, 64), ref_block, H2_RTOL)
+
+
+def test_plane_layout_maxpool_matches_torch():
+    g = torch.Generator().manual_seed(3)
+    B, Hin, Win = 2, 45, 62
+    x = torch.randn(B, Hin, Win, 64, generator=g)
+    ref = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    L = _lib.lib()
+    s = _lib.cur_stream()
+    xd = x.reshape(-1, 64).contiguous().cuda()
+    X = torch.zeros(B * Hin * Win, 64, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(L.imf_h2_pack(xd.data_ptr(), 64, B * Hin * Win, 64, 64, X.data_ptr(), 128, err.data_ptr(), s))
+    Hout, Wout = ref.shape[1], ref.shape[2]
+    yb = torch.zeros(B, 16, Hout + 2, Wout + 2, 8, dtype=torch.float16, device="cuda")
+    assert yb.numel() * 2 == int(L.imf_image_p8_bytes(Hout, Wout, B))
+    _lib.check(L.imf_image_maxpool_p8(X.data_ptr(), 128, 64, Hin, Win, 3, 2, 1, yb.data_ptr(), B, s))
+    torch.cuda.synchronize()
+    close(_p8_unpack(yb.cpu()), ref, 1e-6)
+
+
 def test_module_level_layers_match_standin(frag):
     """imfnet_b200.me layers used one by one (the un-fused route) give the oracle's numbers."""
     import imfnet_b200.me as ME

@@ -131,7 +131,8 @@ def test_single_fragment_graph_plan_sequence(fake_cuda):
     per_enqueue = seq.count("imf_hash_build")
     assert per_enqueue == 3                                                  # two warm-ups + the capture
     assert seq.count("imf_sparse_conv_g4_fwd_perm") == 3 * 20               # 6 strided / transposed + 14 block convolutions
-    assert seq.count("imf_sparse_conv_g4_fwd") == 3 * 15                    # image encoder: layer1 6 + layer2 9 (the stem is its own fused kernel)
+    assert seq.count("imf_sparse_conv_g4_fwd") == 3 * 9                     # image encoder: layer2 (the stem and layer1 have their own kernels)
+    assert seq.count("imf_image_conv3x3_p8_fwd") == 3 * 6 and seq.count("imf_image_maxpool_p8") == 3          # layer1 on the plane layout
     assert seq.count("imf_image_stem_h2_fwd") == 3 and seq.count("imf_image_im2col_h2_batch") == 0
     assert seq.count("imf_conv_first_tc_h2_fwd") == 3 and seq.count("imf_conv_first_h2_fwd") == 0      # conv1 on the tensor-core path
     # the fusion module of the single-fragment plan is the batched chain with B = 1
@@ -165,11 +166,12 @@ def test_batched_plan_sequence_and_slices(fake_cuda):
     assert len([a for n, a in fake_cuda.calls if n == "imf_attention_fusion_fwd_batched" and a[8] == 2]) == enq
     assert len([a for n, a in fake_cuda.calls if n == "imf_attention_kv_batched" and a[4] == 2]) == enq
     assert len([a for n, a in fake_cuda.calls if n == "imf_image_stem_h2_fwd" and a[3] == 2]) == enq          # both images, one fused stem launch
-    assert len([a for n, a in fake_cuda.calls if n == "imf_image_maxpool_h2_batch" and a[11] == 2]) == enq
+    assert len([a for n, a in fake_cuda.calls if n == "imf_image_maxpool_p8" and a[9] == 2]) == enq
     # the image encoder's batched launches cover B * P rows
     ip = g.image_plan
-    layer1 = [a for n, a in fake_cuda.calls if n == "imf_sparse_conv_g4_fwd" and a[8] == 2 * ip.P1]
-    assert layer1, "no layer1 launch over the rows of both images"
+    layer1 = [a for n, a in fake_cuda.calls if n == "imf_image_conv3x3_p8_fwd" and a[3] == 2]
+    assert len(layer1) == 6 * enq, "layer1: six convolutions over both images per enqueue"
+    assert len([a for n, a in fake_cuda.calls if n == "imf_sparse_conv_g4_fwd" and a[8] == 2 * ip.P2]) == 9 * enq          # layer2 over both images' rows
     assert ip.s0.shape[0] == 2 * ip.P0 and ip.tokens.shape == (2 * ip.P2, 128)
     # fusion chain: the level's rows through one call with the plan's segment / count arrays and the stride-8 row count on the device
     att = [a for n, a in fake_cuda.calls if n == "imf_attention_fusion_fwd_batched" and a[2] == g.P8.data_ptr()][-1]
