@@ -18,7 +18,8 @@ _p, _i32, _i64, _sz, _f32, _f64 = C.c_void_p, C.c_int32, C.c_longlong, C.c_size_
 
 
 class KmapJob(C.Structure):
-    _fields_ = [("out_coords", _p), ("n_out_dev", _p), ("table_in", _p), ("nbr_t", _p), ("tile_mask", _p), ("perm", _p), ("scale", _i32)]
+    _fields_ = [("out_coords", _p), ("n_out_dev", _p), ("table_in", _p), ("nbr_t", _p), ("tile_mask", _p), ("perm", _p), ("scale", _i32),
+                ("dense_meta", _p), ("dense_cells", _p)]
 
 
 class AttnWeights(C.Structure):
@@ -73,6 +74,9 @@ SIGNATURES = {
     "imf_conv_first_tc_columns": (_i32, [_i32]),
     "imf_conv_first_tc_workspace_bytes": (_sz, [_i32, _i32]),
     "imf_conv_first_tc_h2_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _sz, _p, _p]),
+    "imf_conv_first_tc_h2_fwd_keep": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _sz, _p, _p]),
+    "imf_conv_first_tc_release": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _sz, _p]),
+    "imf_conv_first_tc_grid": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "imf_conv_first_h2_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p]),
     "imf_tail_fused_h2_fwd": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _i32, _p, _i32, _p, _p]),
     "imf_image_p8_bytes": (_sz, [_i32, _i32, _i32]),

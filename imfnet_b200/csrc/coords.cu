@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "dense_grid.cuh"
 #include <stdarg.h>
 #include <atomic>
 
@@ -249,6 +250,8 @@ struct KmapJob {
   const int* perm;       // optional: table row o describes output row perm[o] (parity-grouped transposed convolution)
   int scale;
   int pad;
+  const imf_dense::CfMeta* dense_meta;      // optional: dense row-index grid over the INPUT coordinate set (see below)
+  const int* dense_cells;
 };
 struct KmapJobs {
   KmapJob j[16];
@@ -268,6 +271,18 @@ __global__ void __launch_bounds__(128) k_kernel_map_t(const __grid_constant__ Km
   if (o < n) c = jb.out_coords[jb.perm ? jb.perm[o] : o];
   const bool transposed = jb.perm != nullptr && jb.scale < 0 && K == 3;      // parity-grouped tables are stride-2 transposed by contract
   const int pc = transposed ? imf_parity_class(c, -jb.scale) : 0;
+  // Dense path: when the input set's row-index grid exists (conv_first_tc.cu built it for conv1 and left it populated), a neighbour is
+  // ONE 4-byte load at a computed cell -- x-neighbours share a 32-byte sector -- instead of a hash probe chain of 16-byte slots
+  // (two thirds of a forward's ~25 M probes look up the stride-1 table; the launch was bound by L2 sectors).  A cell outside the
+  // item's box (boxes include a halo of 2) has no voxel; rows with a batch index the grid does not know take the hash path.
+  const bool dense = jb.dense_meta != nullptr && jb.dense_meta->use_grid && o < n && (unsigned)c.x < (unsigned)jb.dense_meta->pad[2];
+  int gx0 = 0, gy0 = 0, gz0 = 0, gdx = 0, gdy = 0, gdz = 0;
+  long long gbase = 0;
+  if (dense) {
+    const int* it = jb.dense_meta->item[c.x];
+    gx0 = it[0]; gy0 = it[1]; gz0 = it[2]; gdx = it[3]; gdy = it[4]; gdz = it[5];
+    gbase = ((long long)(unsigned)it[6]) | ((long long)it[7] << 32);
+  }
   unsigned mine = 0u;
   for (int k = 0; k < K3; ++k) {
     int r = -1;
@@ -277,7 +292,13 @@ __global__ void __launch_bounds__(128) k_kernel_map_t(const __grid_constant__ Km
       const bool possible = !transposed || (((kx != 0) == ((pc & 1) != 0)) && ((ky != 0) == ((pc & 2) != 0)) && ((kz != 0) == ((pc & 4) != 0)));
       if (possible) {
         const int x = c.y + kx * jb.scale, y = c.z + ky * jb.scale, z = c.w + kz * jb.scale;
-        if (imf_coord_in_range(c.x, x, y, z)) r = imf_table_lookup(jb.table, mask, imf_pack_key(c.x, x, y, z));
+        if (dense) {
+          const int lx = x - gx0, ly = y - gy0, lz = z - gz0;
+          if ((unsigned)lx < (unsigned)gdx && (unsigned)ly < (unsigned)gdy && (unsigned)lz < (unsigned)gdz)
+            r = __ldg(jb.dense_cells + gbase + ((long long)lz * gdy + ly) * gdx + lx) - 1;
+        } else if (imf_coord_in_range(c.x, x, y, z)) {
+          r = imf_table_lookup(jb.table, mask, imf_pack_key(c.x, x, y, z));
+        }
       }
     }
     if (o < ld_n) jb.nbr_t[(size_t)k * ld_n + o] = r;
@@ -500,6 +521,8 @@ struct imf_kmap_job_t {      // mirrors include/imfnet_b200.h
   uint32_t* tile_mask;
   const int32_t* perm;
   int32_t scale;
+  const void* dense_meta;
+  const void* dense_cells;
 };
 
 extern "C" int imf_kernel_map_t_batch(const imf_kmap_job_t* jobs, int32_t njobs, int32_t n_out_max, long long capacity, int32_t kernel_size,
@@ -519,6 +542,9 @@ extern "C" int imf_kernel_map_t_batch(const imf_kmap_job_t* jobs, int32_t njobs,
     kj.j[i].perm = jobs[i].perm;
     kj.j[i].scale = jobs[i].scale;
     kj.j[i].pad = 0;
+    IMF_CHECK_ARG((jobs[i].dense_meta == nullptr) == (jobs[i].dense_cells == nullptr));
+    kj.j[i].dense_meta = reinterpret_cast<const imf_dense::CfMeta*>(jobs[i].dense_meta);
+    kj.j[i].dense_cells = reinterpret_cast<const int*>(jobs[i].dense_cells);
   }
   const int tiles = (n_out_max + 127) / 128;
   dim3 grid(tiles + 1, njobs);          // + 1: the mask entry past the last tile is written (zero) too
@@ -530,7 +556,7 @@ extern "C" int imf_kernel_map_t_batch(const imf_kmap_job_t* jobs, int32_t njobs,
 extern "C" int imf_kernel_map_t(const int32_t* out_coords, const int32_t* n_out_dev, int32_t n_out_max, const void* table_in,
                                 long long capacity, int32_t kernel_size, int32_t scale, int32_t* nbr_t, int32_t ld_n,
                                 uint32_t* tile_mask, cudaStream_t stream) {
-  imf_kmap_job_t job{out_coords, n_out_dev, table_in, nbr_t, tile_mask, nullptr, scale};
+  imf_kmap_job_t job{out_coords, n_out_dev, table_in, nbr_t, tile_mask, nullptr, scale, nullptr, nullptr};
   return imf_kernel_map_t_batch(&job, 1, n_out_max, capacity, kernel_size, ld_n, stream);
 }
 

@@ -499,10 +499,15 @@ class GraphPlan:
         if fused.tail_tc is not None:
             self.ident = torch.zeros(self.ldn, **i32)
             self.ident_mask = torch.zeros(self.ldn // 128 + 1, **i32)
-        self.cf_ws = None
+        self.cf_ws = self.cf_grid = None
         if fused.conv1_tc is not None:
             self.cf_ws_bytes = int(L.imf_conv_first_tc_workspace_bytes(rows, m.conv1.kernel_size))
-            self.cf_ws = torch.empty(self.cf_ws_bytes, **u8)
+            # zero once: the plan never clears the dense grid, it un-scatters the occupied cells after every use (imf_conv_first_tc_release)
+            self.cf_ws = torch.zeros(self.cf_ws_bytes, **u8)
+            import ctypes as C
+            gm, gc = C.c_void_p(), C.c_void_p()
+            _lib.check(L.imf_conv_first_tc_grid(self.cf_ws.data_ptr(), rows, m.conv1.kernel_size, C.byref(gm), C.byref(gc)))
+            self.cf_grid = (gm.value, gc.value)          # header / cells of the stride-1 row-index grid (also read by the neighbour tables)
         self.out = torch.zeros((rows, m.out_channels), **f32)
         self.graph = None
         self.launches_per_replay = 0
@@ -610,11 +615,6 @@ class GraphPlan:
         for t in (1, 2, 4):
             _lib.check(L.imf_parity_perm(self.coords[t].data_ptr(), self._n(t), rows, t, self.perm[t].data_ptr(), self.perm_ws.data_ptr(),
                                          self.perm_ws_bytes, s))
-        jobs = (_lib.KmapJob * len(self.nbr))()
-        for i, ((t_in, t_out, tr), (nbr_t, ld_n, mask)) in enumerate(self.nbr.items()):
-            jobs[i] = _lib.KmapJob(self.coords[t_out].data_ptr(), self._n(t_out), self.tables[t_in].data_ptr(), nbr_t.data_ptr(),
-                                   mask.data_ptr(), self.perm[t_out].data_ptr() if tr else None, -t_out if tr else t_in)
-        _lib.check(L.imf_kernel_map_t_batch(jobs, len(self.nbr), rows, self.cap, 3, self.ldn, s))       # all 10 tables, one launch
         # ---- encoder ----
         ld1, ld2, ld4 = 2 * self.cat1.shape[1], 2 * self.cat2.shape[1], 2 * self.cat4.shape[1]
         s1, s2, s4 = self.cat1.data_ptr() + TR[2] * 4, self.cat2.data_ptr() + TR[3] * 4, self.cat4.data_ptr() + TR[4] * 4
@@ -624,18 +624,28 @@ class GraphPlan:
         kc2, kc4, k8 = _kc(TR[3], CH[2]), _kc(TR[4], CH[3]), _kc(CH[4])
         sc, sh = f.norm1
         tok = self._tl_begin("conv1", t_out=1, cin=m.conv1.in_channels, cout=CH[1], K=m.conv1.kernel_size ** 3, residual=False)
-        if self.cf_ws is not None:
+        if self.cf_ws is not None:          # leaves the stride-1 dense grid populated for the neighbour tables below
             packed1, sc1, sh1 = f.conv1_tc
-            _lib.check(L.imf_conv_first_tc_h2_fwd(self.feats.data_ptr(), self.feats.shape[1], packed1.data_ptr(), self.coords[1].data_ptr(),
-                                                  self._n(1), rows, self.num_items, self.tables[1].data_ptr(), self.cap, m.conv1.kernel_size,
-                                                  CH[1], sc1.data_ptr(), sh1.data_ptr(), 0, self.a0.data_ptr(), 2 * CH[1], _kc(CH[1]),
-                                                  self.cf_ws.data_ptr(), self.cf_ws_bytes, self.err.data_ptr(), s))
+            _lib.check(L.imf_conv_first_tc_h2_fwd_keep(self.feats.data_ptr(), self.feats.shape[1], packed1.data_ptr(), self.coords[1].data_ptr(),
+                                                       self._n(1), rows, self.num_items, self.tables[1].data_ptr(), self.cap, m.conv1.kernel_size,
+                                                       CH[1], sc1.data_ptr(), sh1.data_ptr(), 0, self.a0.data_ptr(), 2 * CH[1], _kc(CH[1]),
+                                                       self.cf_ws.data_ptr(), self.cf_ws_bytes, self.err.data_ptr(), s))
         else:
             _lib.check(L.imf_conv_first_h2_fwd(self.feats.data_ptr(), self.feats.shape[1], m.conv1.in_channels, m.conv1.kernel.data_ptr(),
                                                self.coords[1].data_ptr(), self._n(1), rows, self.tables[1].data_ptr(), self.cap,
                                                m.conv1.kernel_size, 1, CH[1], sc.data_ptr(), sh.data_ptr(), 0, self.a0.data_ptr(),
                                                2 * CH[1], _kc(CH[1]), s))
         self._tl_end(tok)
+        # ---- neighbour tables: all 10 in one launch; those over the stride-1 set read the dense grid conv1 left behind ----
+        jobs = (_lib.KmapJob * len(self.nbr))()
+        for i, ((t_in, t_out, tr), (nbr_t, ld_n, mask)) in enumerate(self.nbr.items()):
+            gm, gc = self.cf_grid if (self.cf_grid is not None and t_in == 1 and not tr) else (None, None)
+            jobs[i] = _lib.KmapJob(self.coords[t_out].data_ptr(), self._n(t_out), self.tables[t_in].data_ptr(), nbr_t.data_ptr(),
+                                   mask.data_ptr(), self.perm[t_out].data_ptr() if tr else None, -t_out if tr else t_in, gm, gc)
+        _lib.check(L.imf_kernel_map_t_batch(jobs, len(self.nbr), rows, self.cap, 3, self.ldn, s))
+        if self.cf_ws is not None:
+            _lib.check(L.imf_conv_first_tc_release(self.coords[1].data_ptr(), self._n(1), rows, self.num_items, m.conv1.kernel_size,
+                                                   self.cf_ws.data_ptr(), self.cf_ws_bytes, s))
         self._block(L, "block1", self.a0.data_ptr(), 2 * CH[1], _kc(CH[1]), 1, CH[1], self.a1, s1, ld1, kc1b, s)
         self._conv(L, "conv2", s1, ld1, (1, 2, False), 2, None, 0, 0, False, self.b0.data_ptr(), 2 * CH[2], _kc(CH[2]), s)
         self._block(L, "block2", self.b0.data_ptr(), 2 * CH[2], _kc(CH[2]), 2, CH[2], self.b1, s2, ld2, kc2, s)

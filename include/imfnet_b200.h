@@ -87,6 +87,9 @@ typedef struct {
   const int32_t* perm; /* optional: table row o describes output row perm[o] (see imf_parity_perm); only for the STRIDE-2 transposed
                           convolution (scale = -fine stride): offsets impossible for the row's parity class are not probed */
   int32_t scale;
+  const void* dense_meta;  /* optional (both or neither): header and cells of the dense row-index grid over the INPUT coordinate set of */
+  const void* dense_cells; /* this table (imf_conv_first_tc_grid of a workspace populated by imf_conv_first_tc_h2_fwd_keep): neighbours are
+                              then read from the grid (one 4-byte load) instead of probing table_in; same result */
 } imf_kmap_job_t;
 int imf_kernel_map_t_batch(const imf_kmap_job_t* jobs, int32_t njobs, int32_t n_out_max, long long capacity, int32_t kernel_size,
                            int32_t ld_n, imf_stream_t stream);
@@ -213,6 +216,16 @@ int imf_conv_first_tc_h2_fwd(const float* X, int32_t ldx, const void* packed, co
                              int32_t num_items, const void* table, long long capacity, int32_t kernel_size, int32_t Cout,
                              const float* scale, const float* shift, int32_t relu, void* Y, int32_t ldy, int32_t kc_out, void* workspace,
                              size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+/* The captured plans' form of the same call: the workspace was zero-initialised ONCE by the caller and every use is followed by
+ * imf_conv_first_tc_release, so the ~200 MB grid is never cleared; between the two calls the populated grid (cell = row + 1) also
+ * serves imf_kernel_map_t_batch (imf_kmap_job_t.dense_meta / dense_cells from imf_conv_first_tc_grid). */
+int imf_conv_first_tc_h2_fwd_keep(const float* X, int32_t ldx, const void* packed, const int32_t* coords, const int32_t* n_dev, int32_t n_max,
+                             int32_t num_items, const void* table, long long capacity, int32_t kernel_size, int32_t Cout,
+                             const float* scale, const float* shift, int32_t relu, void* Y, int32_t ldy, int32_t kc_out, void* workspace,
+                             size_t workspace_bytes, int32_t* err, imf_stream_t stream);
+int imf_conv_first_tc_release(const int32_t* coords, const int32_t* n_dev, int32_t n_max, int32_t num_items, int32_t kernel_size,
+                              void* workspace, size_t workspace_bytes, imf_stream_t stream);
+int imf_conv_first_tc_grid(void* workspace, int32_t n_max, int32_t kernel_size, const void** meta, const void** cells);
 
 /* imf_conv_first_fwd writing an h2 matrix (ldy in halves, chunk width kc_out). */
 int imf_conv_first_h2_fwd(const float* X, int32_t ldx, int32_t Cin, const float* W, const int32_t* coords, const int32_t* n_dev,

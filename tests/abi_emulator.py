@@ -16,7 +16,7 @@ from numpy.lib.stride_tricks import as_strided
 
 from imfnet_b200 import _lib
 
-HOST_ONLY = {"imf_conv_first_tc_columns", "imf_last_error", "imf_version", "imf_launch_count", "imf_hash_capacity", "imf_hash_bytes", "imf_device_sm_count"}
+HOST_ONLY = {"imf_conv_first_tc_columns", "imf_conv_first_tc_grid", "imf_last_error", "imf_version", "imf_launch_count", "imf_hash_capacity", "imf_hash_bytes", "imf_device_sm_count"}
 
 
 def vec(ptr, n, dtype=np.float32):
@@ -151,7 +151,7 @@ class Emulator:
                 mask[tile] = bits
 
     def do_imf_kernel_map_t(self, out_coords, n_out_dev, n_out_max, table_in, cap, K, scale, nbr_t, ld_n, tile_mask):
-        job = _lib.KmapJob(out_coords, n_out_dev, table_in, nbr_t, tile_mask, None, scale)
+        job = _lib.KmapJob(out_coords, n_out_dev, table_in, nbr_t, tile_mask, None, scale, None, None)
         self.do_imf_kernel_map_t_batch([job], 1, n_out_max, cap, K, ld_n)
 
     def do_imf_batch_segments(self, coords, n_dev, n_max, B, seg):
@@ -252,6 +252,13 @@ class Emulator:
         if relu:
             acc = np.maximum(acc, 0)
         mat(Y, n, Cout, ldy // 2)[:] = acc
+
+    def do_imf_conv_first_tc_h2_fwd_keep(self, X, ldx, packed, coords, n_dev, n_max, num_items, table, cap, K, Cout, scale, shift, relu, Y, ldy,
+                                    kc_out, ws, ws_bytes, err):
+        self.do_imf_conv_first_tc_h2_fwd(X, ldx, packed, coords, n_dev, n_max, num_items, table, cap, K, Cout, scale, shift, relu, Y, ldy, kc_out, ws, ws_bytes, err)
+
+    def do_imf_conv_first_tc_release(self, coords, n_dev, n_max, num_items, K, ws, ws_bytes):
+        pass          # (the emulated conv1 does not use the grid)
 
     def do_imf_sparse_conv_g4_fwd_perm(self, X, ldx, kc_in, packed, nbr_t, ld_n, tile_mask, n_out_dev, n_out_max, K3, Cin, Cout, scale,
                                        shift, R, ldr, kc_r, relu, Y, ldy, n_y_rows, kc_out, out_row, ws, ws_bytes, err):

@@ -350,6 +350,77 @@ def test_first_conv_tensor_core_path_batches_fallback_and_device_count():
     check(a, 1, 1, n_dev=n_dev, n_eff=2100)
 
 
+def test_neighbour_tables_from_the_dense_grid_equal_the_hash_tables():
+    """imf_conv_first_tc_h2_fwd_keep leaves the stride-1 row-index grid populated; imf_kernel_map_t_batch with dense_meta / dense_cells
+    must give bit-identical tables and tile masks to the hash probes -- same-level (1 -> 1) and strided (1 -> 2) maps, two batch items,
+    a row with a foreign batch index (hash fallback) -- and imf_conv_first_tc_release must leave the grid all-empty again."""
+    import ctypes as C
+    from imfnet_b200.sparse import CoordinateManager
+    a, _ = synthetic.make_fragment(5000, 0.05, seed=11)
+    b, _ = synthetic.make_fragment(3000, 0.05, seed=12)
+    b = b.copy(); b[:, 0] = 1; b[:, 1:] += np.array([40, -25, 7], dtype=np.int32)
+    coords = np.concatenate([a, b])
+    coords[-3:, 0] = 5                                           # foreign batch index (num_items = 2)
+    n = len(coords)
+    L = _lib.lib()
+    s = _lib.cur_stream()
+    cm = CoordinateManager(torch.from_numpy(coords).cuda(), check=False)
+    cm.build_pyramid([2])
+    l1, l2 = cm.level(1), cm.level(2)
+    K, cout = 5, 32
+    g = torch.Generator().manual_seed(1)
+    W = torch.randn(125, 1, cout, generator=g) / 11
+    KP = int(L.imf_conv_first_tc_columns(K))
+    w1 = torch.zeros((1, KP, cout), device="cuda")
+    w1[0, :125] = W[:, 0, :].cuda()
+    packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(1, KP, cout, 64)), dtype=torch.uint8, device="cuda")
+    _lib.check(L.imf_sparse_conv_h2_pack(w1.data_ptr(), 1, KP, cout, 64, 1024.0, packed.data_ptr(), s))
+    ws_bytes = int(L.imf_conv_first_tc_workspace_bytes(n, K))
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device="cuda")          # zero once, as the plans do
+    X = torch.ones(n, 1, device="cuda")
+    sc, sh = torch.full((cout,), 1.0 / 1024, device="cuda"), torch.zeros(cout, device="cuda")
+    Yh = torch.zeros((n, 2 * cout), dtype=torch.float16, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    gm, gc = C.c_void_p(), C.c_void_p()
+    _lib.check(L.imf_conv_first_tc_grid(ws.data_ptr(), n, K, C.byref(gm), C.byref(gc)))
+    ld_n = (n + 127) // 128 * 128
+
+    def tables(dense):
+        out = []
+        jobs = (_lib.KmapJob * 2)()
+        for i, (dst, scale) in enumerate(((l1, 1), (l2, 1))):
+            nbr_t = torch.full((27, ld_n), -9, dtype=torch.int32, device="cuda")
+            mask = torch.full((ld_n // 128 + 2,), -9, dtype=torch.int32, device="cuda")
+            jobs[i] = _lib.KmapJob(dst.coords.data_ptr(), None if i == 0 else None, l1.table.data_ptr(), nbr_t.data_ptr(), mask.data_ptr(), None, scale,
+                                   gm.value if dense else None, gc.value if dense else None)
+            out.append((nbr_t, mask, dst.n))
+        # (both jobs share n_out_max = n; the stride-2 level has fewer rows: its count is passed on the device)
+        n2 = torch.tensor([l2.n], dtype=torch.int32, device="cuda")
+        jobs[1].n_out_dev = n2.data_ptr()
+        _lib.check(L.imf_kernel_map_t_batch(jobs, 2, n, l1.capacity, 3, ld_n, s))
+        torch.cuda.synchronize()
+        return out
+
+    for rep in range(2):                                         # twice: the second use relies on the release of the first
+        _lib.check(L.imf_conv_first_tc_h2_fwd_keep(X.data_ptr(), 1, packed.data_ptr(), l1.coords.data_ptr(), None, n, 2, l1.table.data_ptr(), l1.capacity,
+                                                   K, cout, sc.data_ptr(), sh.data_ptr(), 0, Yh.data_ptr(), 2 * cout, 32, ws.data_ptr(), ws_bytes,
+                                                   err.data_ptr(), s))
+        torch.cuda.synchronize()
+        assert int(ws[:4].view(torch.int32).item()) == 1, "the two boxes must fit the grid budget"
+        dense, plain = tables(True), tables(False)
+        for (nd, md, cnt), (nh, mh, _c) in zip(dense, plain):
+            npad = (cnt + 127) // 128 * 128
+            assert torch.equal(nd[:, :npad], nh[:, :npad]) and torch.equal(md[: npad // 128 + 1], mh[: npad // 128 + 1])
+            assert int((nh[:, :cnt] >= 0).sum()) > 5 * cnt          # (a real table: ~12 neighbours per row)
+        _lib.check(L.imf_conv_first_tc_release(l1.coords.data_ptr(), None, n, 2, K, ws.data_ptr(), ws_bytes, s))
+        torch.cuda.synchronize()
+        off = gc.value - ws.data_ptr()
+        cells = ws[off:off + 4 * (512 * n)].view(torch.int32)
+        feats = ws[gm.value - ws.data_ptr() + 14592:off].view(torch.int32)          # the feature grid lies between the header and the row grid
+        assert int(cells.abs().max()) == 0 and int(feats.abs().max()) == 0, "release must leave both grids empty"
+    assert int(err.item()) == 0
+
+
 @pytest.mark.parametrize("normalize", [True, False])
 def test_pointwise_tail_matches_oracle(normalize):
     g = torch.Generator().manual_seed(5)
@@ -580,7 +651,7 @@ def test_parity_grouped_transposed_conv_matches_oracle(frag, t_in, t_out, cin, c
     nbr_t = torch.empty((27, ld_n), dtype=torch.int32, device="cuda")
     mask = torch.empty(ld_n // 128 + 1, dtype=torch.int32, device="cuda")
     job = (_lib.KmapJob * 1)(_lib.KmapJob(fine.coords.data_ptr(), None, coarse.table.data_ptr(), nbr_t.data_ptr(), mask.data_ptr(),
-                                          perm.data_ptr(), -t_out))
+                                          perm.data_ptr(), -t_out, None, None))
     _lib.check(L.imf_kernel_map_t_batch(job, 1, n, coarse.capacity, 3, ld_n, s))
     onbr = ocm.table(t_in, t_out, 3, True)
     assert np.array_equal(nbr_t.cpu().numpy()[:, :n], onbr[p].T)
