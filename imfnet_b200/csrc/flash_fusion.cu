@@ -15,10 +15,14 @@
 // a tile (log-sum-exp weights).  Every CTA therefore does the same number of blocks (no wave quantisation, no per-item launches),
 // and all sizes are read on the device (seg / cnt), which keeps the launch capturable.
 //
-// CTA = 10 warps:
-//   warp 0    TMA producer: Q of the piece, then the K (pass 1: its hi halves only) / K + V blocks into a 2-stage ring
+// CTA = 19 warps:
+//   warp 0    TMA producer of Q and K: Q of the piece, then the K blocks (pass 1: their hi halves only) into a 2-stage ring
+//   warp 18   TMA producer of V (pass 2) into its own 2-stage ring.  K and V were ONE stage at first: a stage was then released only
+//             by the P.V MMAs of its block, so the loads of block j + 2 started after P.V(j) and S(j + 2) waited for their whole
+//             latency (ncu, 8192 x 4800: the softmax warps waited 43 % of the time for S, ~8 k cycles per block for ~2 k of MMAs);
+//             with separate rings K(j + 2) is fetched as soon as S(j) has completed, V(j + 2) as soon as P.V(j) has
 //   warp 1    MMA issuer + TMEM owner: S double-buffered (2 x 128 columns), O (256 columns)
-//   warps 2-9 softmax, two warps per TMEM lane quadrant (32 of a block's 64 tokens each): pass 1 finds the row maximum of the piece
+//   warps 2-17 softmax, four warps per TMEM lane quadrant (16 of a block's 64 tokens each): pass 1 finds the row maximum of the piece
 //             from the CHEAP product q_hi . k_hi^T (any m close to the maximum serves: it only has to keep exp2(S - m) in range, and
 //             the pieces are merged with exact weights exp2(m_piece - m)); pass 2 recomputes S with all three products, writes
 //             P = exp2(S - m) (hi/lo) to shared memory for the P.V MMAs and sums the row -- O is never rescaled.
@@ -41,11 +45,10 @@ constexpr int kVImg = kD * 128;         // 16 KB: 128 dims x 64 tokens
 constexpr int kQBytes = 4 * kQImg;      // hi0 lo0 hi1 lo1
 constexpr int kKBytes = 4 * kKImg;
 constexpr int kVBytes = 2 * kVImg;      // Vhi Vlo
-constexpr int kStage = kKBytes + kVBytes;
 constexpr int kPBytes = 2 * kQImg;      // Phi Plo (128 rows x 64 tokens)
-constexpr int kSmem = kQBytes + 2 * kStage + kPBytes;
-constexpr int kThreads = 320;
-constexpr int kSoftWarps = 8;
+constexpr int kSmem = kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes;
+constexpr int kThreads = 608;
+constexpr int kSoftWarps = 16;
 constexpr int kMaxPieces = 16;          // pieces a CTA may hold (the host sizes the grid so that this suffices)
 constexpr int kMaxItems = 256;
 
@@ -135,9 +138,10 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* q_s = smem;
-  unsigned char* ring = smem + kQBytes;
-  unsigned char* p_s = ring + 2 * kStage;
-  __shared__ __align__(8) uint64_t q_full, full[2], empty[2], s_ready[2], s_free[2], p_ready, p_free, o_done, o_free;
+  unsigned char* kring = smem + kQBytes;
+  unsigned char* vring = kring + 2 * kKBytes;
+  unsigned char* p_s = vring + 2 * kVBytes;
+  __shared__ __align__(8) uint64_t q_full, kfull[2], kempty[2], vfull[2], vempty[2], s_ready[2], s_free[2], p_ready, p_free, o_done, o_free;
   __shared__ uint32_t tmem_base_s;
   __shared__ FFPiece piece_s[kMaxPieces];
   __shared__ int npiece_s;
@@ -191,8 +195,10 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     npiece_s = np;
     tc::mbar_init(&q_full, 1);
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&full[s], 1);
-      tc::mbar_init(&empty[s], 1);
+      tc::mbar_init(&kfull[s], 1);
+      tc::mbar_init(&kempty[s], 1);
+      tc::mbar_init(&vfull[s], 1);
+      tc::mbar_init(&vempty[s], 1);
       tc::mbar_init(&s_ready[s], 1);
       tc::mbar_init(&s_free[s], kSoftWarps);
     }
@@ -216,7 +222,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_o = tmem_base_s + 256u;     // O: columns [256,512) (O1 | O2)
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer: Q and K ===========================
     if (lane == 0) {
       uint32_t it = 0;
       for (int pc = 0; pc < npiece; ++pc) {
@@ -224,25 +230,40 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (pc > 0) tc::mbar_wait(&o_done, (uint32_t)(pc - 1) & 1u, err, 1);      // the previous piece's MMAs are done with Q
         tc::mbar_arrive_expect_tx(&q_full, kQBytes);
         for (int i = 0; i < 4; ++i) ff_tma_load(tc::smem_u32(q_s + i * kQImg), &tmQ, tc::smem_u32(&q_full), i * 64, p.row0);
-        const int krow = p.item * Lpad, vrow = p.item * kD;
+        const int krow = p.item * Lpad;
         for (int pass = 0; pass < 2; ++pass) {
           for (int j = 0; j < p.nblk; ++j, ++it) {
             const int st = it & 1;
-            tc::mbar_wait(&empty[st], ((it >> 1) & 1u) ^ 1u, err, 2);
-            unsigned char* kd = ring + st * kStage;
-            const int blk = p.blk0 + j;
-            const int t0 = krow + blk * kTB;
+            tc::mbar_wait(&kempty[st], ((it >> 1) & 1u) ^ 1u, err, 2);
+            unsigned char* kd = kring + st * kKBytes;
+            const int t0 = krow + (p.blk0 + j) * kTB;
             if (pass == 0) {        // q_hi . k_hi^T only: the hi images of both channel chunks
-              tc::mbar_arrive_expect_tx(&full[st], 2 * kKImg);
-              ff_tma_load(tc::smem_u32(kd), &tmK, tc::smem_u32(&full[st]), 0, t0);
-              ff_tma_load(tc::smem_u32(kd + 2 * kKImg), &tmK, tc::smem_u32(&full[st]), 128, t0);
+              tc::mbar_arrive_expect_tx(&kfull[st], 2 * kKImg);
+              ff_tma_load(tc::smem_u32(kd), &tmK, tc::smem_u32(&kfull[st]), 0, t0);
+              ff_tma_load(tc::smem_u32(kd + 2 * kKImg), &tmK, tc::smem_u32(&kfull[st]), 128, t0);
             } else {
-              tc::mbar_arrive_expect_tx(&full[st], kStage);
-              for (int i = 0; i < 4; ++i) ff_tma_load(tc::smem_u32(kd + i * kKImg), &tmK, tc::smem_u32(&full[st]), i * 64, t0);
-              ff_tma_load(tc::smem_u32(kd + kKBytes), &tmV, tc::smem_u32(&full[st]), blk * 128, vrow);
-              ff_tma_load(tc::smem_u32(kd + kKBytes + kVImg), &tmV, tc::smem_u32(&full[st]), blk * 128 + 64, vrow);
+              tc::mbar_arrive_expect_tx(&kfull[st], kKBytes);
+              for (int i = 0; i < 4; ++i) ff_tma_load(tc::smem_u32(kd + i * kKImg), &tmK, tc::smem_u32(&kfull[st]), i * 64, t0);
             }
           }
+        }
+      }
+    }
+  } else if (warp == 2 + kSoftWarps) {
+    // =========================== TMA producer: V (pass 2 only) ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int pc = 0; pc < npiece; ++pc) {
+        const FFPiece p = piece_s[pc];
+        const int vrow = p.item * kD;
+        for (int j = 0; j < p.nblk; ++j, ++it) {
+          const int st = it & 1;
+          tc::mbar_wait(&vempty[st], ((it >> 1) & 1u) ^ 1u, err, 11);
+          unsigned char* vd = vring + st * kVBytes;
+          const int blk = p.blk0 + j;
+          tc::mbar_arrive_expect_tx(&vfull[st], kVBytes);
+          ff_tma_load(tc::smem_u32(vd), &tmV, tc::smem_u32(&vfull[st]), blk * 128, vrow);
+          ff_tma_load(tc::smem_u32(vd + kVImg), &tmV, tc::smem_u32(&vfull[st]), blk * 128 + 64, vrow);
         }
       }
     }
@@ -253,17 +274,19 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     constexpr uint32_t id_s2 = ff_idesc(kTQ, 2 * kTB), id_s1 = ff_idesc(kTQ, kTB);       // N = 128 / 64
     constexpr uint32_t id_o2 = ff_idesc(kTQ, 2 * kD), id_o1 = ff_idesc(kTQ, kD);          // N = 256 / 128
     const uint32_t q0 = __shfl_sync(0xffffffffu, tc::smem_u32(q_s), 0);
-    const uint32_t r0 = __shfl_sync(0xffffffffu, tc::smem_u32(ring), 0);
+    const uint32_t kr0 = __shfl_sync(0xffffffffu, tc::smem_u32(kring), 0);
+    const uint32_t vr0 = __shfl_sync(0xffffffffu, tc::smem_u32(vring), 0);
     const uint32_t p0 = __shfl_sync(0xffffffffu, tc::smem_u32(p_s), 0);
     const uint32_t ts = __shfl_sync(0xffffffffu, tmem_s, 0), to = __shfl_sync(0xffffffffu, tmem_o, 0);
-    uint32_t it = 0;       // ring uses consumed
+    uint32_t it = 0;       // K ring uses consumed
+    uint32_t vit = 0;      // V ring uses consumed
     uint32_t sit = 0;      // S buffers issued
     uint32_t pit = 0;      // P blocks consumed
     auto issue_s = [&](uint32_t st, bool full_product) {
       const uint32_t sb = sit & 1u;
       tc::mbar_wait(&s_free[sb], ((sit >> 1) & 1u) ^ 1u, err, 4);            // softmax warps have read this S buffer's previous content
       tc::tc_fence_after_sync();
-      const uint32_t k0 = r0 + st * kStage;
+      const uint32_t k0 = kr0 + st * kKBytes;
       const uint32_t d = ts + sb * 128u;
       if (tc::elect_one()) {
 #pragma unroll
@@ -281,6 +304,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
         tc::mma_commit(&s_ready[sb]);
+        tc::mma_commit(&kempty[st]);              // the K block is only needed by this product
       }
       __syncwarp();
       ++sit;
@@ -291,25 +315,25 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ---- pass 1: approximate scores (hi . hi) for the row maxima ----
       for (int j = 0; j < nblk; ++j, ++it) {
         const uint32_t st = it & 1u;
-        tc::mbar_wait(&full[st], (it >> 1) & 1u, err, 5);
+        tc::mbar_wait(&kfull[st], (it >> 1) & 1u, err, 5);
         issue_s(st, false);
-        if (tc::elect_one()) tc::mma_commit(&empty[st]);
-        __syncwarp();
       }
       // ---- pass 2: S(j + 1) is issued before P(j) . V(j), so the tensor pipe works while the softmax warps handle block j ----
       tc::mbar_wait(&o_free, ((uint32_t)pc & 1u) ^ 1u, err, 6);                // the previous piece's O has been drained
-      tc::mbar_wait(&full[it & 1u], (it >> 1) & 1u, err, 5);
+      tc::mbar_wait(&kfull[it & 1u], (it >> 1) & 1u, err, 5);
       issue_s(it & 1u, true);
-      for (int j = 0; j < nblk; ++j, ++it) {
-        const uint32_t st = it & 1u;
+      ++it;
+      for (int j = 0; j < nblk; ++j, ++vit) {
         if (j + 1 < nblk) {
-          const uint32_t nit = it + 1;
-          tc::mbar_wait(&full[nit & 1u], (nit >> 1) & 1u, err, 5);
-          issue_s(nit & 1u, true);
+          tc::mbar_wait(&kfull[it & 1u], (it >> 1) & 1u, err, 5);
+          issue_s(it & 1u, true);
+          ++it;
         }
+        const uint32_t st = vit & 1u;
         tc::mbar_wait(&p_ready, pit & 1u, err, 7);                              // P of block j is in shared memory
+        tc::mbar_wait(&vfull[st], (vit >> 1) & 1u, err, 12);
         tc::tc_fence_after_sync();
-        const uint32_t v0 = r0 + st * kStage + kKBytes;                        // [Vhi ; Vlo] = 256 rows
+        const uint32_t v0 = vr0 + st * kVBytes;                                // [Vhi ; Vlo] = 256 rows
         const uint32_t jj = (uint32_t)j;
         if (tc::elect_one()) {
 #pragma unroll
@@ -318,7 +342,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             ff_mma(to, tc::smem_desc_sw128(p0 + o), tc::smem_desc_sw128(v0 + o), id_o2, (jj | (uint32_t)ks) ? 1u : 0u);
             ff_mma(to, tc::smem_desc_sw128(p0 + kQImg + o), tc::smem_desc_sw128(v0 + o), id_o1, 1u);
           }
-          tc::mma_commit(&empty[st]);
+          tc::mma_commit(&vempty[st]);
           tc::mma_commit(&p_free);
           if (j == nblk - 1) tc::mma_commit(&o_done);
         }
@@ -327,12 +351,14 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     }
   } else {
-    // =========================== softmax (8 warps: TMEM lane quadrant = warp % 4, token half = (warp - 2) / 4) ===========================
+    // =========================== softmax (16 warps: TMEM lane quadrant = warp % 4, token quarter = (warp - 2) / 4) ===========================
+    // Four warps per lane quadrant, 16 of a block's 64 tokens each: with eight warps (32 tokens per thread) the softmax of a block --
+    // TMEM loads, 32 exponentials, the hi/lo split, the swizzled stores -- took longer than the block's MMAs and the tensor pipe idled.
     const int q = warp & 3;
-    const int hf = (warp - 2) >> 2;                 // 0: tokens [0,32) of a block, 1: tokens [32,64)
+    const int qt = (warp - 2) >> 2;                 // tokens [16 qt, 16 qt + 16) of a block
     const int r = q * 32 + lane;                    // row inside the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float* xch = reinterpret_cast<float*>(p_s);     // [2][128] exchange area between the two halves (P is idle when it is used)
+    float* xch = reinterpret_cast<float*>(p_s);     // [4][128] exchange area between the quarters (P is idle when it is used)
     uint32_t sct = 0, pct = 0;
     for (int pc = 0; pc < npiece; ++pc) {
       const FFPiece p = piece_s[pc];
@@ -342,21 +368,20 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t sb = sct & 1u;
         tc::mbar_wait(&s_ready[sb], (sct >> 1) & 1u, err, 8);
         tc::tc_fence_after_sync();
-        const int t0 = (p.blk0 + j) * kTB + hf * 32;
-        uint32_t a[32];
-        tc::tmem_ld16_issue(tmem_s + lane_addr + sb * 128u + (uint32_t)(hf * 32), a);
-        tc::tmem_ld16_issue(tmem_s + lane_addr + sb * 128u + (uint32_t)(hf * 32 + 16), a + 16);
+        const int t0 = (p.blk0 + j) * kTB + qt * 16;
+        uint32_t a[16];
+        tc::tmem_ld16_issue(tmem_s + lane_addr + sb * 128u + (uint32_t)(qt * 16), a);
         tc::tmem_ld_wait();
         tc::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s_free[sb]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
+        for (int i = 0; i < 16; ++i)
           if (t0 + i < L) row_max = fmaxf(row_max, __uint_as_float(a[i]));
       }
-      xch[hf * 128 + r] = row_max;
+      xch[qt * 128 + r] = row_max;
       ff_bar(1, kSoftWarps * 32);
-      row_max = fmaxf(xch[r], xch[128 + r]);
+      row_max = fmaxf(fmaxf(xch[r], xch[128 + r]), fmaxf(xch[256 + r], xch[384 + r]));
       ff_bar(1, kSoftWarps * 32);                   // everybody has read the exchange area before P is written again
       // ---- pass 2: exact scores, P = exp2(S - m), row sums ----
       float row_sum = 0.f;
@@ -364,20 +389,18 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t sb = sct & 1u;
         tc::mbar_wait(&s_ready[sb], (sct >> 1) & 1u, err, 8);
         tc::tc_fence_after_sync();
-        const int t0 = (p.blk0 + j) * kTB + hf * 32;
-        uint32_t a[32], b2[32];
-        const uint32_t base = tmem_s + lane_addr + sb * 128u + (uint32_t)(hf * 32);
+        const int t0 = (p.blk0 + j) * kTB + qt * 16;
+        uint32_t a[16], b2[16];
+        const uint32_t base = tmem_s + lane_addr + sb * 128u + (uint32_t)(qt * 16);
         tc::tmem_ld16_issue(base, a);
-        tc::tmem_ld16_issue(base + 16u, a + 16);
         tc::tmem_ld16_issue(base + (uint32_t)kTB, b2);
-        tc::tmem_ld16_issue(base + (uint32_t)kTB + 16u, b2 + 16);
         tc::tmem_ld_wait();
         tc::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s_free[sb]);
-        __half2 hi[16], lo[16];
+        __half2 hi[8], lo[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           const float s0 = __uint_as_float(a[2 * i]) + __uint_as_float(b2[2 * i]);
           const float s1 = __uint_as_float(a[2 * i + 1]) + __uint_as_float(b2[2 * i + 1]);
           const float p0v = (t0 + 2 * i < L) ? ff_exp2(s0 - row_max) : 0.f;
@@ -388,9 +411,9 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           lo[i] = __floats2half2_rn(p0v - hf2.x, p1v - hf2.y);
         }
         tc::mbar_wait(&p_free, (pct & 1u) ^ 1u, err, 9);                      // the previous block's P.V MMAs are done with p_s
-        const int ch = hf * 4;                       // 16-byte chunk index of this half's first token inside the 64-token (128-byte) row
+        const int ch = qt * 2;                       // 16-byte chunk index of this quarter's first token inside the 64-token (128-byte) row
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
+        for (int c4 = 0; c4 < 2; ++c4) {
           tc::st_shared_16(p_s + tc::sw128_offset(r, ch + c4), FHalf8{hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]});
           tc::st_shared_16(p_s + kQImg + tc::sw128_offset(r, ch + c4), FHalf8{lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]});
         }
@@ -401,13 +424,13 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ---- partial result of this piece: O (un-normalised), row maximum and row sum ----
       tc::mbar_wait(&o_done, (uint32_t)pc & 1u, err, 10);
       tc::tc_fence_after_sync();
-      xch[hf * 128 + r] = row_sum;                  // (all P.V MMAs are complete: P is idle)
-      float* op = Opart + ((size_t)p.slot * kTQ + r) * kD + hf * 64;
+      xch[qt * 128 + r] = row_sum;                  // (all P.V MMAs are complete: P is idle)
+      float* op = Opart + ((size_t)p.slot * kTQ + r) * kD + qt * 32;
 #pragma unroll 1
-      for (int cb = 0; cb < 64; cb += 16) {
+      for (int cb = 0; cb < 32; cb += 16) {
         uint32_t a[16], b2[16];
-        tc::tmem_ld16_issue(tmem_o + lane_addr + (uint32_t)(hf * 64 + cb), a);
-        tc::tmem_ld16_issue(tmem_o + lane_addr + (uint32_t)(kD + hf * 64 + cb), b2);
+        tc::tmem_ld16_issue(tmem_o + lane_addr + (uint32_t)(qt * 32 + cb), a);
+        tc::tmem_ld16_issue(tmem_o + lane_addr + (uint32_t)(kD + qt * 32 + cb), b2);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -417,9 +440,9 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       tc::tc_fence_before_sync();
       ff_bar(1, kSoftWarps * 32);
-      if (hf == 0) {
+      if (qt == 0) {
         ml[((size_t)p.slot * kTQ + r) * 2] = row_max;
-        ml[((size_t)p.slot * kTQ + r) * 2 + 1] = xch[r] + xch[128 + r];
+        ml[((size_t)p.slot * kTQ + r) * 2 + 1] = (xch[r] + xch[128 + r]) + (xch[256 + r] + xch[384 + r]);
       }
       ff_bar(1, kSoftWarps * 32);                   // the exchange area is free again; O is drained
       if (lane == 0) tc::mbar_arrive(&o_free);
