@@ -199,8 +199,8 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   __shared__ int klist_s[32];
   __shared__ unsigned jmask_s[32];
   __shared__ int nk_s;
-  __shared__ int ring_s[5];
-  __shared__ int turn_s;                                 // next stage (running count) whose MMAs may be issued
+  __shared__ int ring_s[6];
+  __shared__ int slot_turn_s[NA];                        // per ring slot: uses of the slot whose stage has been seen full by its MMA warp
   __shared__ __align__(16) float sc_s[BN], sh_s[BN];
   __shared__ __align__(16) int idx_s[NPROD][2][HROWS]; // neighbour indices of each producer warp's current / next stage
 
@@ -264,7 +264,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
     for (int s = 0; s < NA; ++s) { tc::mbar_init(&full_a[s], 32 * HALVES); tc::mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < kNW; ++s) { tc::mbar_init(&full_w[s], 1); tc::mbar_init(&empty_w[s], kNMW); }
     tc::mbar_init(&acc_bar, kNMW);
-    turn_s = 0;
+    for (int s = 0; s < NA; ++s) slot_turn_s[s] = 0;
     tc::fence_barrier_init();
     tma::prefetch_map(&tmY);
   }
@@ -291,7 +291,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   if (tid == 0) G4_TRACE(1);
 
   // running ring positions (the producers and the MMA warps advance them identically)
-  int ac = 0, a_slot = 0, w_slot = 0;
+  int ac = 0, a_slot = 0, w_slot = 0, a_use = 0;       // a_use: how often the ring has wrapped (= use index of a slot, a_phase = a_use & 1)
   uint32_t a_phase = 0u, w_phase = 0u;
   int passes_done = 0;                                  // executed passes (parity of the accumulator barrier)
   for (int pass = 0; pass < npass; ++pass) {
@@ -367,8 +367,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       // tracked by the stage's mbarrier (cp.async.mbarrier.arrive.noinc), i.e. no thread ever waits for its own row copies.
       // A ring slot (= every NA-th stage) belongs to HALVES warps, each copying 128 / HALVES rows of the stage: their per-stage
       // barrier / walk / issue time (~1000 cycles for 64 instructions per lane) overlaps the other slots' copies, and with two
-      // warps per slot the slot's turnaround fits the MMA rate.  The neighbour indices of a warp's NEXT stage are prefetched into
-      // shared memory (one 16-byte cp.async per lane) while it copies the current one.
+      // warps per slot the slot's turnaround fits the MMA rate.
       // KC = 64: 16 lanes per row (hi 8 x 16 B | lo 8 x 16 B): instruction i covers rows 4*(2*(i/4) + lane/16) + i%4;
       // KC = 32:  8 lanes per row: instruction i covers rows 4*(4*(i/4) + lane/8) + i%4  -> whole rows per instruction.
       constexpr int LPR = (KC == 64) ? 16 : 8;           // lanes per row
@@ -381,13 +380,17 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       const char* xthr = reinterpret_cast<const char*>(X) + part * 128 + c16 * 16;
       const unsigned ldx_bytes = (unsigned)ldx * 2u;
       int* my_idx = &idx_s[pw][0][0];
-      auto prefetch = [&](const G4It& it, int slot) {    // lane l: neighbour rows of output rows 4l..4l+3 of this warp's half
+      // The neighbour indices of a warp's NEXT stage are loaded into registers (plain 16-byte load) while it handles the current one
+      // and written to shared memory when their stage begins.  (They used to be prefetched with cp.async: the stage's
+      // cp.async.mbarrier.arrive.noinc then also waited for the prefetch issued just before it -- a cold read of the 54 MB table --
+      // so a slot took ~1300 cycles from "free" to "full" even with the row copies disabled: clock64 trace, profiles/r02/call31.)
+      auto load_idx = [&](const G4It& it) {              // lane l: neighbour rows of output rows 4l..4l+3 of this warp's half
+        int4 v = make_int4(-1, -1, -1, -1);
         if (lane < HROWS / 4) {
           const int row = prow + it.j * kBM + half * HROWS + 4 * lane;
-          int* dst = my_idx + slot * HROWS + 4 * lane;
-          if (row < row_end) g4_cp_async16_row(tc::smem_u32(dst), nbr_t + (size_t)it.k * ld_n + row, 0);
-          else *reinterpret_cast<int4*>(dst) = make_int4(-1, -1, -1, -1);
+          if (row < row_end) v = __ldg(reinterpret_cast<const int4*>(nbr_t + (size_t)it.k * ld_n + row));
         }
+        return v;
       };
       // Stage s lives in ring slot s % NA: the producers of a slot take part in every use of it, so none can run two phases
       // ahead of the slot's consumer (which the parity wait could not tell apart from "free").
@@ -406,19 +409,18 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       for (int i = 0; i < 4; ++i) dstq[i] = ring_base + pslot * Cfg::A_BYTES + tc::sw128_offset(half * HROWS + 4 * hw + i, c16);
 #define G4_DST(i4, i) (dstq[i] + (uint32_t)((i4) * (RPI / 2) * 1024))
 #define G4_SRC(r) reinterpret_cast<const char*>(xb + (unsigned long long)((unsigned)max((r), 0)) * ldx_bytes)
-      if (it.w < w_end) prefetch(it, 0);
-      g4_cp_async_commit();
-      g4_cp_async_commit();                                               // (empty) keeps the group arithmetic uniform
+      int4 cur_idx = make_int4(-1, -1, -1, -1);
+      if (it.w < w_end) cur_idx = load_idx(it);
       while (it.w < w_end) {
         G4It nxt = it;
         for (int i = 0; i < NA && nxt.w < w_end; ++i) advance(nxt);
-        if (nxt.w < w_end) prefetch(nxt, slot ^ 1);
-        g4_cp_async_commit();
+        if (lane < HROWS / 4) *reinterpret_cast<int4*>(my_idx + slot * HROWS + 4 * lane) = cur_idx;
+        int4 nxt_idx = make_int4(-1, -1, -1, -1);
+        if (nxt.w < w_end) nxt_idx = load_idx(nxt);                       // in flight during this stage's wait and copies
         if (trace && lane == 0 && half == 0 && my_ac < 36) trace[16 + 4 * my_ac] = clock64();
         tc::mbar_wait(&empty_a[pslot], my_phase ^ 1u, err, 2);
         if (trace && lane == 0 && half == 0 && my_ac < 36) trace[17 + 4 * my_ac] = clock64();
-        g4_cp_async_wait<2>();             // pending at most: the previous stage's rows and the prefetch just issued
-        __syncwarp();
+        __syncwarp();                      // the index slot written above is visible to the whole warp
         const int4* idx4p = reinterpret_cast<const int4*>(my_idx + slot * HROWS);
         unsigned long long xb = reinterpret_cast<unsigned long long>(xthr + it.chunk * (4 * KC));
         asm volatile("" : "+l"(xb));        // keep base + chunk offset in one register pair (one IMAD.WIDE per copy)
@@ -440,8 +442,8 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
         my_ac += NA;
         my_phase ^= 1u;
         it = nxt;
+        cur_idx = nxt_idx;
         slot ^= 1;
-        __syncwarp();                      // every lane is done reading the index slot the next prefetch overwrites
       }
       g4_cp_async_wait<0>();
     } else if (warp == kNPW + kNMW) {
@@ -469,10 +471,14 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       // tcgen05.mma execute in issue order.  Feeding an accumulator from several threads is not ordered by the tensor pipe even
       // when the issue order is (measured: last-bit differences from launch to launch, tools/conv_g4_check.py), so this
       // ownership is what makes the sums bit-reproducible.  With >= 2 sub-tiles consecutive stages fall to different warps, whose
-      // per-stage bookkeeping (~600 cycles) then stays off the issue chain.  The warps take turns in walk order (turn_s): a warp
-      // reaches stage s only after every earlier stage was issued, i.e. after the previous use of the same ring slot was
-      // consumed, which keeps the parity wait on full_a unambiguous.  The accumulators are zeroed here (each MMA warp clears
-      // one TMEM lane quadrant) so that every MMA accumulates.
+      // per-stage bookkeeping (~600 cycles) then stays off the issue chain.  Hand-off PER RING SLOT (slot_turn_s): a warp waits on a
+      // stage's full_a only after the previous use of the SAME slot has been seen full by its owner -- the barrier is then at most one
+      // phase behind, which keeps the parity wait unambiguous (tests/test_g4_protocol_model.py shows what happens without it).  The
+      // first form passed ONE turn through all stages in walk order: every stage then paid the hand-off chain (shared-memory poll,
+      // barrier try_wait, turn store: ~380 cycles) serially, and with gathers, weight copies and MMAs disabled the 64 -> 64 launch
+      // still took 171 of 327 us, the 32 -> 32 launch 138 of 187 us (profiles/r02/call28_conv_g4_bench_*).  Stages on different slots
+      // now proceed independently; every accumulator still has ONE issuing thread, whose MMAs execute in issue order.  The
+      // accumulators are zeroed here (each MMA warp clears one TMEM lane quadrant) so that every MMA accumulates.
       {
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         for (int col = 0; col < nsub * Cfg::ACC_COLS; col += 16) g4_tmem_zero16(tmem_d + lane_base + (uint32_t)col);
@@ -493,22 +499,18 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
         }
         const int owner = (dbg & 8) ? 0 : (dbg & 16) ? (ac & (kNMW - 1)) : (cur.j & (kNMW - 1));
         if (owner == mw) {
-          // The slot barriers are WAITED ON in walk order whichever warp owns the stage (a turn counter in shared memory): every
-          // earlier stage's slot has been seen full by then, so a waiter is never more than one phase off.
-          // The hand-off chain between the MMA warps is what a stage costs when nothing else stalls.  The descriptors do not
-          // depend on the turn, and the turn only has to order the WAITS on the ring (parity), not the MMAs (every accumulator
-          // has one issuing thread): the descriptors are built first (warp-uniform values shuffled from lane 0, so the compiler
-          // keeps them in uniform registers and emits bare UTCHMMA instructions) and the turn is passed on as soon as this
-          // stage's slot has been seen full, before issuing.
+          // The descriptors do not depend on the hand-off (warp-uniform values shuffled from lane 0, so the compiler keeps them in
+          // uniform registers and emits bare UTCHMMA instructions): they are built first; the slot's turn is passed on as soon as
+          // this stage's slot has been seen full, before issuing.
           const uint32_t a0 = __shfl_sync(0xffffffffu, tc::smem_u32(a_ring + a_slot * Cfg::A_BYTES), 0);
           const uint32_t w0 = __shfl_sync(0xffffffffu, tc::smem_u32(w_ring + ws * Cfg::W_BYTES), 0);
           const uint32_t d = __shfl_sync(0xffffffffu, tmem_d + (uint32_t)(cur.j * Cfg::ACC_COLS), 0);
           const uint64_t da = tc::smem_desc_sw128(a0), dw = tc::smem_desc_sw128(w0);
-          while (*reinterpret_cast<volatile int*>(&turn_s) != ac) {}
+          while (*reinterpret_cast<volatile int*>(&slot_turn_s[a_slot]) != a_use) {}
           tc::mbar_wait(&full_a[a_slot], a_phase, err, 4);
           if (trace && lane == 0 && ac < 36) trace[18 + 4 * ac] = clock64();
           if (tc::elect_one()) {
-            *reinterpret_cast<volatile int*>(&turn_s) = ac + 1;
+            *reinterpret_cast<volatile int*>(&slot_turn_s[a_slot]) = a_use + 1;
             if (dbg & 4) {
             } else if (KC == 64) {
               // (descriptor start-address field = byte address >> 4: the hi image is at +0, the lo image at +kImg)
@@ -531,14 +533,14 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
           __syncwarp();
         }
         ++ac;
-        if (++a_slot == NA) { a_slot = 0; a_phase ^= 1u; }
+        if (++a_slot == NA) { a_slot = 0; a_phase ^= 1u; ++a_use; }
         advance(cur);
       }
       if (tc::elect_one()) {                 // the thread that issued this warp's MMAs (elect.sync is deterministic per mask)
         if (last_w >= 0) tc::mma_commit(&empty_w[ws]);
         tc::mma_commit(&acc_bar);
         if (mw == 0) {                     // ring positions after this pass, for everybody (the producers skip through theirs)
-          ring_s[0] = ac; ring_s[1] = a_slot; ring_s[2] = (int)a_phase; ring_s[3] = w_slot; ring_s[4] = (int)w_phase;
+          ring_s[0] = ac; ring_s[1] = a_slot; ring_s[2] = (int)a_phase; ring_s[3] = w_slot; ring_s[4] = (int)w_phase; ring_s[5] = a_use;
         }
       }
       __syncwarp();
@@ -675,7 +677,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
     tc::tc_fence_before_sync();
     __syncthreads();                       // pass boundary: TMEM drained, staging reads done, ring reusable
     tc::tc_fence_after_sync();
-    ac = ring_s[0]; a_slot = ring_s[1]; a_phase = (uint32_t)ring_s[2]; w_slot = ring_s[3]; w_phase = (uint32_t)ring_s[4];
+    ac = ring_s[0]; a_slot = ring_s[1]; a_phase = (uint32_t)ring_s[2]; w_slot = ring_s[3]; w_phase = (uint32_t)ring_s[4]; a_use = ring_s[5];
     ++passes_done;
   }
   if (warp == kNPW) tc::tmem_dealloc(tmem_d, tmem_cols);

@@ -1,6 +1,7 @@
-"""CPU: randomized model check of the operand-ring protocol of csrc/sparse_conv_g4.cu (producers, MMA warps taking turns, parity
-waits on mbarriers, asynchronous MMA completion) -- for the production hand-off (turn passed on after the MMAs were issued) and for
-the variant libraries' early hand-off (-DIMF_G4_EARLY_TURN: turn passed on as soon as the stage's slot was seen full).
+"""CPU: randomized model check of the operand-ring protocol of csrc/sparse_conv_g4.cu (producers, MMA warps, parity waits on mbarriers,
+asynchronous MMA completion) -- for the production hand-off (ONE turn counter PER RING SLOT: a stage waits until the previous use of
+its slot has been seen full, so the parity wait is unambiguous while stages on different slots do not wait for each other) and for
+the earlier global hand-offs (one turn counter over all stages, passed on after issuing / as soon as the slot was seen full).
 
 What is modelled (one CTA, one pass):
   * stage s lives in ring slot s % NA with phase parity (s / NA) & 1; full[slot] counts the producers' arrivals, empty[slot] the
@@ -31,13 +32,14 @@ class MBar:
         return self.parity != parity
 
 
-def simulate(n_stages, n_slots, n_sub, early_turn, seed, halves=2, n_mma_warps=4, producers_wait_for_empty=True):
+def simulate(n_stages, n_slots, n_sub, early_turn, seed, halves=2, n_mma_warps=4, producers_wait_for_empty=True, turn="global"):
     rng = random.Random(seed)
     full = [MBar(halves) for _ in range(n_slots)]
     empty = [MBar(1) for _ in range(n_slots)]
     slot_tag = [None] * n_slots          # stage whose rows the slot currently holds (None = garbage)
     slot_fill = [0] * n_slots            # producers that have finished copying the current stage
     state = {"turn": 0}
+    slot_turn = [0] * n_slots            # turn == "slot": uses of the slot that have been seen full
     executed = []
     queues = [[] for _ in range(n_mma_warps)]          # issued, not yet executed MMAs per issuing warp
 
@@ -61,9 +63,19 @@ def simulate(n_stages, n_slots, n_sub, early_turn, seed, halves=2, n_mma_warps=4
                 continue
             for _ in range(rng.randint(0, 2)):          # per-stage bookkeeping (iterator, descriptors)
                 yield
-            while state["turn"] != s:
-                yield
+            if turn == "slot":
+                while slot_turn[slot] != s // n_slots:
+                    yield
+            elif turn == "global":
+                while state["turn"] != s:
+                    yield
             while not full[slot].try_wait(phase):
+                if turn == "none":
+                    yield
+                    continue
+                yield
+            if turn == "slot":
+                slot_turn[slot] = s // n_slots + 1
                 yield
             if early_turn:
                 state["turn"] = s + 1
@@ -116,3 +128,22 @@ def test_the_model_detects_a_broken_protocol():
         except AssertionError:
             caught += 1
     assert caught >= 15
+
+
+@pytest.mark.parametrize("n_slots,n_sub", [(5, 3), (5, 1), (4, 2), (8, 8), (5, 4), (8, 5), (6, 7)])
+def test_per_slot_turn_counters_under_random_interleavings(n_slots, n_sub):
+    """The production hand-off: a stage only waits for the previous use of ITS slot."""
+    for seed in range(60):
+        simulate(n_stages=37 + seed % 23, n_slots=n_slots, n_sub=n_sub, early_turn=False, seed=seed, turn="slot")
+
+
+def test_without_any_turn_the_parity_wait_is_ambiguous():
+    """Why a hand-off is needed at all: a warp that reaches a later use of a slot while an earlier use is still pending sees the
+    barrier's stale parity and issues on rows that are not there yet."""
+    caught = 0
+    for seed in range(30):
+        try:
+            simulate(n_stages=60, n_slots=5, n_sub=3, early_turn=False, seed=seed, turn="none", n_mma_warps=4)
+        except AssertionError:
+            caught += 1
+    assert caught >= 20
