@@ -23,8 +23,9 @@
 //   * small levels (fewer tiles than SMs) run one CTA per tile, or -- when the caller passes a workspace -- split a tile's stage
 //     list over several CTAs into fp32 partials + a reduce kernel (shorter latency, more SM time).
 //
-// CTA = 13 or 15 warps: warps 0-7 = gather producers, then the epilogue; warps 8-11 = MMA issuers (warp 8 also owns the TMEM
-// allocation); warp 12 = weight-slab loader (bulk TMA copies); warps 13-14 = two more gather producers when the ring has 5 slots.
+// CTA = 13 to 17 warps: warps 0-7 = gather producers, then the epilogue; warps 8-11 = MMA issuers (warp 8 also owns the TMEM
+// allocation); warp 12 = weight-slab loader (bulk TMA copies, residual prefetch); warps 13-16 = further gather producers when two
+// warps share a ring slot (5 or 6 slots of 32 KB).
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -39,7 +40,7 @@ constexpr int kBM = 128;
 constexpr int kImg = kBM * 128;          // one 128-row x 128-byte operand image (16 KB)
 constexpr int kNPW = 8;                  // gather producer warps that also run the epilogue (warps 0-7)
 constexpr int kNMW = 4;                  // MMA issuing warps (8-11)
-constexpr int kNXW = 2;                  // extra gather producer warps (13-14) for the 5-slot configurations
+constexpr int kNXW = 4;                  // extra gather producer warps (13-16) for the configurations with two warps per ring slot
 constexpr int kNW = 2;                   // weight-slab ring depth
 constexpr int kMaxSubAll = 8;            // 512 TMEM columns / (2 * 32)
 
@@ -48,10 +49,13 @@ struct G4Cfg {
   static constexpr int A_BYTES = (KC == 64 ? 2 : 1) * kImg;
   static constexpr int W_IMG = BN * 128;
   static constexpr int W_BYTES = 2 * W_IMG;
-  static constexpr int BUDGET = 200 * 1024;
+  // Rings: everything the 227 KB of a CTA allow next to ~1.5 KB of static shared memory and the 1 KB alignment slack (the pipeline is
+  // latency-bound -- no unit above 60 % in ncu, profiles/r02/call28 -- so every further stage in flight counts: 64 -> 64 runs with 6
+  // slots of 32 KB, 128-wide output tiles with 5; the neighbour indices of a stage travel through registers, not shared memory).
+  static constexpr int BUDGET = 224 * 1024;
   static constexpr int NA_FIT = (BUDGET - kNW * W_BYTES) / A_BYTES;
   static constexpr int NA = NA_FIT > 8 ? 8 : NA_FIT;
-  static constexpr int HALVES = NA <= 5 ? 2 : 1;         // producer warps per ring slot (each copies 128 / HALVES rows of a stage)
+  static constexpr int HALVES = NA <= 6 ? 2 : 1;         // producer warps per ring slot (each copies 128 / HALVES rows of a stage)
   static constexpr int NPROD = NA * HALVES;
   static_assert(NPROD <= kNPW + kNXW, "not enough producer warps");
   static constexpr int THREADS = (kNPW + kNMW + 1 + (NPROD > kNPW ? NPROD - kNPW : 0)) * 32;   // warp 12 = weight-slab loader
@@ -59,6 +63,12 @@ struct G4Cfg {
   static constexpr int MAXSUB = 512 / ACC_COLS;
   static constexpr int OUT_BYTES = kBM * BN * 4;       // one staged output sub-tile (BN/32 images)
   static constexpr int RING_BYTES = NA * A_BYTES;
+  // Neighbour indices of a stage: through shared memory where it is not scarce (KC = 32: 128 KB ring), by shuffle otherwise (KC = 64:
+  // the 5 KB of staging are what the last ring slot needs; the four shuffles per row group cost the 32 -> 32 layers 5 %, call 33).
+  static constexpr bool IDX_SMEM = (KC == 32);
+  // Residual sub-tiles are copied (coalesced cp.async) into the ring slots the epilogue's staging double buffer leaves free.
+  static constexpr int NRB_FIT = (RING_BYTES - 2 * (kBM * BN * 4)) / (kBM * BN * 4);
+  static constexpr int NRB = NRB_FIT > 8 ? 8 : (NRB_FIT < 0 ? 0 : NRB_FIT);
   static_assert(2 * OUT_BYTES <= RING_BYTES, "the epilogue double buffer lives in the operand ring");
 };
 
@@ -149,6 +159,24 @@ __device__ __forceinline__ float g4_split16(const float* x, Half8* hi, Half8* lo
   lo[1] = Half8{l[4], l[5], l[6], l[7]};
   return m;
 }
+// 8 + 8 halves (hi, lo) -> 8 floats
+__device__ __forceinline__ void g4_unpack8_h2(const int4& h4, const int4& l4, float* x) {
+  Half8 h, l;
+  *reinterpret_cast<int4*>(&h) = h4;
+  *reinterpret_cast<int4*>(&l) = l4;
+  const __half2 hv[4] = {h.a, h.b, h.c, h.d}, lv[4] = {l.a, l.b, l.c, l.d};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 hf = __half22float2(hv[i]), lf = __half22float2(lv[i]);
+    x[2 * i] = hf.x + lf.x;
+    x[2 * i + 1] = hf.y + lf.y;
+  }
+}
+__device__ __forceinline__ int4 g4_lds16(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void g4_load16_h2(const __half* hi_src, const __half* lo_src, float* x) {
   const Half8* hs = reinterpret_cast<const Half8*>(hi_src);
   const Half8* ls = reinterpret_cast<const Half8*>(lo_src);
@@ -202,7 +230,8 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   __shared__ int ring_s[6];
   __shared__ int slot_turn_s[NA];                        // per ring slot: uses of the slot whose stage has been seen full by its MMA warp
   __shared__ __align__(16) float sc_s[BN], sh_s[BN];
-  __shared__ __align__(16) int idx_s[NPROD][2][HROWS]; // neighbour indices of each producer warp's current / next stage
+  __shared__ __align__(8) uint64_t res_bar[Cfg::NRB > 0 ? Cfg::NRB : 1];     // residual sub-tile landed in its buffer (256 cp.async arrivals)
+  __shared__ __align__(16) int idx_s[Cfg::IDX_SMEM ? NPROD : 1][2][Cfg::IDX_SMEM ? HROWS : 4];   // KC = 32: indices of a producer warp's current / next stage
 
 #if !defined(IMF_G4_TRACE)
   trace = nullptr;      // the clock64 trace hooks only exist in a -DIMF_G4_TRACE build (tools/conv_g4_bench.py --trace)
@@ -264,6 +293,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
     for (int s = 0; s < NA; ++s) { tc::mbar_init(&full_a[s], 32 * HALVES); tc::mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < kNW; ++s) { tc::mbar_init(&full_w[s], 1); tc::mbar_init(&empty_w[s], kNMW); }
     tc::mbar_init(&acc_bar, kNMW);
+    for (int s = 0; s < Cfg::NRB; ++s) tc::mbar_init(&res_bar[s], 256);
     for (int s = 0; s < NA; ++s) slot_turn_s[s] = 0;
     tc::fence_barrier_init();
     tma::prefetch_map(&tmY);
@@ -294,6 +324,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
   int ac = 0, a_slot = 0, w_slot = 0, a_use = 0;       // a_use: how often the ring has wrapped (= use index of a slot, a_phase = a_use & 1)
   uint32_t a_phase = 0u, w_phase = 0u;
   int passes_done = 0;                                  // executed passes (parity of the accumulator barrier)
+  uint32_t res_phase = 0u;                              // bit b: parity of residual buffer b's next completion
   for (int pass = 0; pass < npass; ++pass) {
     int prow, row_end;                                  // first row of this pass, end of this CTA's rows in it
     const int nsub = pass_rows(pass, prow, row_end);
@@ -379,11 +410,11 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       const uint32_t ring_base = tc::smem_u32(a_ring) + part * kImg;
       const char* xthr = reinterpret_cast<const char*>(X) + part * 128 + c16 * 16;
       const unsigned ldx_bytes = (unsigned)ldx * 2u;
-      int* my_idx = &idx_s[pw][0][0];
-      // The neighbour indices of a warp's NEXT stage are loaded into registers (plain 16-byte load) while it handles the current one
-      // and written to shared memory when their stage begins.  (They used to be prefetched with cp.async: the stage's
-      // cp.async.mbarrier.arrive.noinc then also waited for the prefetch issued just before it -- a cold read of the 54 MB table --
-      // so a slot took ~1300 cycles from "free" to "full" even with the row copies disabled: clock64 trace, profiles/r02/call31.)
+      // The neighbour indices of a warp's NEXT stage are loaded into registers (plain 16-byte load) while it handles the current one;
+      // the copy instructions fetch theirs from the owning lane by shuffle (no shared-memory staging: those 5 KB pay for a ring slot).
+      // (They used to be prefetched with cp.async: the stage's cp.async.mbarrier.arrive.noinc then also waited for the prefetch
+      // issued just before it -- a cold read of the 54 MB table -- so a slot took ~1300 cycles from "free" to "full" even with the
+      // row copies disabled: clock64 trace, profiles/r02/experiments/call31_*.)
       auto load_idx = [&](const G4It& it) {              // lane l: neighbour rows of output rows 4l..4l+3 of this warp's half
         int4 v = make_int4(-1, -1, -1, -1);
         if (lane < HROWS / 4) {
@@ -399,7 +430,6 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       for (int i = 0; i < first_i && it.w < w_end; ++i) advance(it);               // first stage of this warp
       int my_ac = ac + first_i;
       uint32_t my_phase = pslot >= a_slot ? a_phase : a_phase ^ 1u;                // phase of slot `pslot` at its next use
-      int slot = 0;
       // The swizzled shared-memory address of a copy is not recomputed per LDGSTS (that cost ~12 ALU instructions per copy and made
       // the producers issue-bound): row half*HROWS + 4*RPI*i4 + q of instruction group i4 (q = 4*hw + i) has the swizzled offset
       // i4 * (RPI/2) * 1024 + a per-lane constant, so four destination registers per lane are enough and the i4 term is an
@@ -411,16 +441,18 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
 #define G4_SRC(r) reinterpret_cast<const char*>(xb + (unsigned long long)((unsigned)max((r), 0)) * ldx_bytes)
       int4 cur_idx = make_int4(-1, -1, -1, -1);
       if (it.w < w_end) cur_idx = load_idx(it);
+      int* my_idx = &idx_s[Cfg::IDX_SMEM ? pw : 0][0][0];
+      int slot = 0;
       while (it.w < w_end) {
         G4It nxt = it;
         for (int i = 0; i < NA && nxt.w < w_end; ++i) advance(nxt);
-        if (lane < HROWS / 4) *reinterpret_cast<int4*>(my_idx + slot * HROWS + 4 * lane) = cur_idx;
+        if (Cfg::IDX_SMEM && lane < HROWS / 4) *reinterpret_cast<int4*>(my_idx + slot * HROWS + 4 * lane) = cur_idx;
         int4 nxt_idx = make_int4(-1, -1, -1, -1);
         if (nxt.w < w_end) nxt_idx = load_idx(nxt);                       // in flight during this stage's wait and copies
         if (trace && lane == 0 && half == 0 && my_ac < 36) trace[16 + 4 * my_ac] = clock64();
         tc::mbar_wait(&empty_a[pslot], my_phase ^ 1u, err, 2);
         if (trace && lane == 0 && half == 0 && my_ac < 36) trace[17 + 4 * my_ac] = clock64();
-        __syncwarp();                      // the index slot written above is visible to the whole warp
+        if (Cfg::IDX_SMEM) __syncwarp();     // the index slot written above is visible to the whole warp (double-buffered: no WAR)
         const int4* idx4p = reinterpret_cast<const int4*>(my_idx + slot * HROWS);
         unsigned long long xb = reinterpret_cast<unsigned long long>(xthr + it.chunk * (4 * KC));
         asm volatile("" : "+l"(xb));        // keep base + chunk offset in one register pair (one IMAD.WIDE per copy)
@@ -428,7 +460,13 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
 #pragma unroll
           for (int i4 = 0; i4 < NINS / 4; ++i4) {
             const int m = RPI * i4 + hw;                                  // row group (of this warp's half) for these 4 instructions
-            const int4 r = idx4p[m];
+            int4 r;
+            if (Cfg::IDX_SMEM) {
+              r = idx4p[m];
+            } else {
+              r = make_int4(__shfl_sync(0xffffffffu, cur_idx.x, m), __shfl_sync(0xffffffffu, cur_idx.y, m),
+                            __shfl_sync(0xffffffffu, cur_idx.z, m), __shfl_sync(0xffffffffu, cur_idx.w, m));
+            }
             const int r4[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)      // absent neighbour: the (valid) address of row 0 is passed but ignored (zero fill)
@@ -556,6 +594,30 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
       constexpr int CW = BN / 2;
       const bool partial = (P != nullptr) && !part.row_mode && part.S > 1;
       bool big = false;
+      // Residual rows: each thread reading its own row from global memory (32 rows = 32 cache lines per warp instruction, issued when
+      // the sub-tile is due) cost block2_tr.conv2 63 us on top of conv1's 321 -- and prefetching the rows into the L2 changed nothing
+      // (call 33: the cost is LSU wavefronts and exposed latency, not DRAM).  The ring is idle during the epilogue: the slots behind
+      // the staging double buffer receive whole residual sub-tiles by coalesced cp.async (same swizzled image layout as the operands),
+      // all of them issued when the accumulators are ready, completion per buffer on an mbarrier; a thread then reads its row's
+      // channels with conflict-free 16-byte shared-memory loads.
+      const bool res_smem = Cfg::NRB > 0 && R != nullptr && !partial && !out_row && (BN % kc_r) == 0 && !(dbg & 32);
+      const int res_b0 = ((zt * BN) / kc_r) * 4 * kc_r;                  // byte offset of this CTA's channels in a residual row
+      auto issue_res = [&](int j) {                                       // sub-tile j -> buffer j % NRB (256 threads, 16 B each per round)
+        constexpr int PPR = BN / 4;                                       // 16-byte pieces per row ([hi | lo] chunks of BN channels)
+        const uint32_t base = tc::smem_u32(a_ring) + (uint32_t)((2 + j % Cfg::NRB) * Cfg::OUT_BYTES);
+        const char* rb = reinterpret_cast<const char*>(R) + res_b0;
+#pragma unroll
+        for (int i = 0; i < PPR / 2; ++i) {
+          const int idx = tid + 256 * i, r = idx / PPR, pc = idx % PPR;
+          const int gr = prow + j * kBM + r;
+          const bool ok = gr < n;
+          g4_cp_async16_row(base + (uint32_t)((pc >> 3) * kImg) + tc::sw128_offset(r, pc & 7),
+                            rb + (size_t)(ok ? gr : 0) * ldr * 2 + pc * 16, ok ? 0 : -1);
+        }
+        g4_cp_async_arrive_noinc(&res_bar[j % Cfg::NRB]);
+      };
+      if (res_smem)
+        for (int j = 0; j < nsub && j < Cfg::NRB; ++j) issue_res(j);
       for (int j = 0; j < nsub; ++j) {
         const int r_in = q * 32 + lane;
         const int grow = prow + j * kBM + r_in;
@@ -569,10 +631,29 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
         constexpr int NB = CW >= 32 ? 2 : 1;
         const bool has_r = !partial && (R != nullptr) && grow < n;
         const float act_floor = relu ? 0.f : -INFINITY;
+        uint32_t res_base = 0u;
+        if (res_smem) {
+          const int b = j % Cfg::NRB;
+          tc::mbar_wait(&res_bar[b], (res_phase >> b) & 1u, err, 6);
+          res_phase ^= 1u << b;
+          res_base = tc::smem_u32(a_ring) + (uint32_t)((2 + b) * Cfg::OUT_BYTES);
+        }
 #pragma unroll 1
         for (int cb = 0; cb < CW; cb += 16 * NB) {
           float r16[NB][16];
-          if (has_r) {
+          if (has_r && res_smem) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+              const int cl = h * CW + cb + 16 * b;                       // 16 channels inside this CTA's BN-wide tile
+              const int ph = ((cl / kc_r) * 4 * kc_r + 2 * (cl % kc_r)) >> 4, pl = ph + (kc_r >> 3);      // 16-byte pieces: hi, lo
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int4 h4 = g4_lds16(res_base + (uint32_t)(((ph + u) >> 3) * kImg) + tc::sw128_offset(r_in, (ph + u) & 7));
+                const int4 l4 = g4_lds16(res_base + (uint32_t)(((pl + u) >> 3) * kImg) + tc::sw128_offset(r_in, (pl + u) & 7));
+                g4_unpack8_h2(h4, l4, r16[b] + 8 * u);
+              }
+            }
+          } else if (has_r) {
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
               const int c = zt * BN + h * CW + cb + 16 * b;
@@ -657,6 +738,7 @@ k_sparse_conv_g4(const __half* __restrict__ X, int ldx, const __grid_constant__ 
           if (tid == 0 && j < 8) G4_TRACE(163 + 8 * j);
           named_barrier(1, 256);
           if (tid == 0 && j < 8) G4_TRACE(164 + 8 * j);
+          if (res_smem && j + Cfg::NRB < nsub) issue_res(j + Cfg::NRB);      // (every thread is done reading buffer j % NRB)
           // warp (q, h) stores the 32-row box q of images h, h + 2, ...: eight issuing threads instead of one
           const int r0 = prow + j * kBM + q * 32;
           if (lane == 0) {
@@ -742,7 +824,8 @@ __global__ void __launch_bounds__(256) k_conv_g4_reduce(const float* __restrict_
 }
 
 long long* g_g4_trace = nullptr;
-int g_g4_dbg = 0;       // profiling hook: bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs (results meaningless)
+int g_g4_dbg = 0;       // profiling hook: bit 0 skips the weight copies, bit 1 the gathers, bit 2 the MMAs (results meaningless);
+                        // bits 3/4 change the MMA warp that owns a stage; bit 5 (32): the epilogue reads residual rows straight from global memory
 int g_g4_sps = 4;         // stages per split CTA at least (profiling hook can change it)
 int g_g4_grid = 0;        // profiling hook: overrides the number of CTAs per output-channel tile (0 = one per SM)
 int g4_split_param() {    // experiment knob: IMF_G4_MAX_SPLITS caps the split factor of the small levels (default 32)

@@ -89,7 +89,7 @@ def test_h2_pack_unpack_roundtrip_keeps_22_bits():
     assert bool(((back - X).abs() <= torch.maximum(X.abs() * 2.0 ** -21, torch.tensor(6.1e-8, device="cuda"))).all())
 
 
-def run_conv_g4(X, W, tab, n_out, scale, shift, R=None, relu=False, split=True, kc_out=None, n_dev=None, extra_rows=0):
+def run_conv_g4(X, W, tab, n_out, scale, shift, R=None, relu=False, split=True, kc_out=None, n_dev=None, extra_rows=0, kc_r=None):
     """fp32 in/out wrapper of the TMA-gather kernel: pack -> conv -> unpack.  tab = CoordinateManager.table_t(...)."""
     L = _lib.lib()
     nbr_t, ld_n, tile_mask = tab
@@ -100,7 +100,8 @@ def run_conv_g4(X, W, tab, n_out, scale, shift, R=None, relu=False, split=True, 
     packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(K3, cin, cout, kc_in)), dtype=torch.uint8, device="cuda")
     _lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), K3, cin, cout, kc_in, wmul, packed.data_ptr(), _lib.cur_stream()))
     Xh = h2_pack(X, kc_in, ld_extra=8)
-    Rh = None if R is None else h2_pack(R, kc_out, ld_extra=16)
+    kc_r = kc_r or kc_out
+    Rh = None if R is None else h2_pack(R, kc_r, ld_extra=16)
     Yh = torch.full((n_out + extra_rows, 2 * cout + 8), float("nan"), dtype=torch.float16, device="cuda")
     ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(cout)) if split else 0
     ws = torch.zeros(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
@@ -108,7 +109,7 @@ def run_conv_g4(X, W, tab, n_out, scale, shift, R=None, relu=False, split=True, 
     sc = (scale / wmul).contiguous()
     _lib.check(L.imf_sparse_conv_g4_fwd(Xh.data_ptr(), Xh.stride(0), kc_in, packed.data_ptr(), nbr_t.data_ptr(), ld_n,
                                         tile_mask.data_ptr(), _lib.ptr(n_dev), n_out, K3, cin, cout, sc.data_ptr(), shift.data_ptr(),
-                                        _lib.ptr(Rh), 0 if Rh is None else Rh.stride(0), kc_out, int(relu), Yh.data_ptr(), Yh.stride(0),
+                                        _lib.ptr(Rh), 0 if Rh is None else Rh.stride(0), kc_r, int(relu), Yh.data_ptr(), Yh.stride(0),
                                         Yh.shape[0], kc_out, ws.data_ptr() if split else None, ws_bytes, err.data_ptr(),
                                         _lib.cur_stream()))
     torch.cuda.synchronize()
@@ -273,8 +274,9 @@ def test_first_conv_matches_oracle(frag, cin, cout, K):
     close(Y.cpu(), ref)
 
 
-def run_conv_first_tc(coords_np, X, W, scale, shift, K, num_items, n_dev=None):
-    """imf_conv_first_tc_h2_fwd (dense-grid / hash-probe neighbour expansion + one-offset tensor-core convolution), fp32 in/out."""
+def run_conv_first_tc(coords_np, X, W, scale, shift, K, num_items, n_dev=None, direct=False):
+    """imf_conv_first_tc_h2_fwd (dense-grid / hash-probe neighbour expansion + one-offset tensor-core convolution), fp32 in/out;
+    direct: imf_conv_first_direct_h2_fwd (32 output channels: fp32 weights in registers, no expanded operand)."""
     from imfnet_b200.sparse import CoordinateManager
     L = _lib.lib()
     n, cout = len(coords_np), W.shape[2]
@@ -292,18 +294,25 @@ def run_conv_first_tc(coords_np, X, W, scale, shift, K, num_items, n_dev=None):
     Yh = torch.full((n, 2 * cout), float("nan"), dtype=torch.float16, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     X_d, sc_d, sh_d = X.cuda().contiguous(), (scale / wmul).cuda().contiguous(), shift.cuda().contiguous()
-    _lib.check(L.imf_conv_first_tc_h2_fwd(X_d.data_ptr(), X_d.stride(0), packed.data_ptr(), lvl.coords.data_ptr(), _lib.ptr(n_dev), n, num_items,
-                                          lvl.table.data_ptr(), lvl.capacity, K, cout, sc_d.data_ptr(), sh_d.data_ptr(), 0, Yh.data_ptr(),
-                                          2 * cout, kco, ws.data_ptr(), ws_bytes, err.data_ptr(), _lib.cur_stream()))
+    if direct:
+        W_d, sc_d = W[:, 0, :].cuda().contiguous(), scale.cuda().contiguous()
+        _lib.check(L.imf_conv_first_direct_h2_fwd(X_d.data_ptr(), X_d.stride(0), W_d.data_ptr(), lvl.coords.data_ptr(), _lib.ptr(n_dev), n,
+                                                  num_items, lvl.table.data_ptr(), lvl.capacity, K, cout, sc_d.data_ptr(), sh_d.data_ptr(), 0,
+                                                  Yh.data_ptr(), 2 * cout, kco, ws.data_ptr(), ws_bytes, err.data_ptr(), _lib.cur_stream()))
+    else:
+        _lib.check(L.imf_conv_first_tc_h2_fwd(X_d.data_ptr(), X_d.stride(0), packed.data_ptr(), lvl.coords.data_ptr(), _lib.ptr(n_dev), n,
+                                              num_items, lvl.table.data_ptr(), lvl.capacity, K, cout, sc_d.data_ptr(), sh_d.data_ptr(), 0,
+                                              Yh.data_ptr(), 2 * cout, kco, ws.data_ptr(), ws_bytes, err.data_ptr(), _lib.cur_stream()))
     torch.cuda.synchronize()
     assert int(err.item()) == 0
     use_grid = int(ws[:4].view(torch.int32).item())
     return h2_unpack(Yh, cout, kco).cpu(), use_grid
 
 
-@pytest.mark.parametrize("cout,K", [(32, 5), (32, 3), (64, 5), (32, 1)])
-def test_first_conv_tensor_core_path_matches_oracle(frag, cout, K):
-    """conv1 with one input channel as neighbour expansion (dense row-index grid) + tcgen05 product, against the oracle's convolution."""
+@pytest.mark.parametrize("cout,K,direct", [(32, 5, False), (32, 3, False), (64, 5, False), (32, 1, False), (32, 5, True), (32, 3, True), (32, 1, True)])
+def test_first_conv_tensor_core_path_matches_oracle(frag, cout, K, direct):
+    """conv1 with one input channel as neighbour expansion (dense row-index grid) + tcgen05 product, or as the direct fp32 kernel for 32
+    output channels (tolerance of an fp32 sum there), against the oracle's convolution."""
     coords, ocm, cm = frag
     g = torch.Generator().manual_seed(cout + K)
     n = len(coords)
@@ -311,12 +320,13 @@ def test_first_conv_tensor_core_path_matches_oracle(frag, cout, K):
     W = torch.randn(K ** 3, 1, cout, generator=g) / np.sqrt(K ** 3)
     scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
     ref = sparse_ops.conv_forward(X, W, ocm.table(1, 1, K, False)) * scale + shift
-    out, use_grid = run_conv_first_tc(coords, X, W, scale, shift, K, 1)
+    out, use_grid = run_conv_first_tc(coords, X, W, scale, shift, K, 1, direct=direct)
     assert use_grid == 1
     close(out, ref, H2_RTOL)
 
 
-def test_first_conv_tensor_core_path_batches_fallback_and_device_count():
+@pytest.mark.parametrize("direct", [False, True])
+def test_first_conv_tensor_core_path_batches_fallback_and_device_count(direct):
     """(a) three batch items with different bounding boxes (one of them empty) share the grid; (b) scattered voxels whose boxes exceed
     the grid budget take the hash-probe fallback; (c) a foreign batch index falls back per voxel; (d) a device-side row count."""
     g = torch.Generator().manual_seed(9)
@@ -331,7 +341,7 @@ def test_first_conv_tensor_core_path_batches_fallback_and_device_count():
         m = n if n_eff is None else n_eff
         ocm = sparse_ops.CoordinateManager(coords[:m])
         ref = sparse_ops.conv_forward(X[:m], W, ocm.table(1, 1, K, False)) * scale + shift
-        out, use_grid = run_conv_first_tc(coords, X, W, scale, shift, K, num_items, n_dev)
+        out, use_grid = run_conv_first_tc(coords, X, W, scale, shift, K, num_items, n_dev, direct=direct)
         assert use_grid == expect_grid
         close(out[:m], ref, H2_RTOL)
 
@@ -610,6 +620,26 @@ def test_module_level_layers_match_standin(frag):
     close(z.F.cpu(), ref_z)
     assert z.coordinate_map_key == x.coordinate_map_key and len(z) == len(x)
     assert ME.cat(x, z).F.shape == (len(coords), 64)
+
+
+@pytest.mark.parametrize("n,cin,cout,kc_r", [(50000, 64, 64, 64), (50000, 64, 64, 32), (140000, 32, 32, 32), (60000, 32, 64, 64), (50000, 64, 32, 32),
+                                             (30000, 64, 128, 64)])
+def test_g4_row_mode_residual_matches_simt_conv(n, cin, cout, kc_r):
+    """Row mode with a residual: the epilogue takes the residual sub-tiles through the free ring slots (coalesced cp.async, one mbarrier
+    per buffer; 140 000 rows at 32 -> 32 = 8 sub-tiles per CTA on 6 buffers, i.e. buffers are re-filled inside a pass), several passes,
+    residual chunk width different from the output's, a ragged last tile; 64 -> 128 keeps the direct global-memory reads."""
+    coords, _ = synthetic.make_fragment(n, 0.025, 1)
+    from imfnet_b200.sparse import CoordinateManager
+    cm = CoordinateManager(torch.from_numpy(coords).cuda())
+    n = n - 37
+    g = torch.Generator(device="cuda").manual_seed(2)
+    X = torch.randn(len(coords), cin, device="cuda", generator=g)
+    W = torch.randn(27, cin, cout, device="cuda", generator=g) / 40
+    R = torch.randn(n, cout, device="cuda", generator=g)
+    scale, shift = torch.rand(cout, device="cuda", generator=g) + 0.5, torch.randn(cout, device="cuda", generator=g) * 0.1
+    a = run_conv(X, W, cm.table(1, 1, 3, False), n, scale, shift, R, True)
+    b = run_conv_g4(X, W, cm.table_t(1, 1, 3, False), n, scale, shift, R, True, split=True, kc_r=kc_r)
+    close(b, a, H2_RTOL)
 
 
 @pytest.fixture(scope="module")

@@ -23,6 +23,7 @@ ap.add_argument("--grid", type=int, default=0)
 ap.add_argument("--trace", action="store_true")
 ap.add_argument("--npw", type=int, default=0, help="minimum stages per split CTA (profiling hook)")
 ap.add_argument("--flags", default="0", help="comma list of profiling flags: 1 no W copies, 2 no gathers, 4 no MMAs")
+ap.add_argument("--residual", action="store_true", help="with a residual input (the second convolution of a block); flag 32 = no L2 prefetch of it")
 ap.add_argument("--frags", type=int, default=1, help="fragments of --n voxels in one launch (batch index in column 0), as the batched plan runs it")
 args = ap.parse_args()
 
@@ -47,6 +48,8 @@ packed = torch.empty(int(L.imf_sparse_conv_h2_packed_bytes(27, cin, cout, kci)),
 _lib.check(L.imf_sparse_conv_h2_pack(W.data_ptr(), 27, cin, cout, kci, 1024.0, packed.data_ptr(), s))
 Yh = torch.zeros(n, 2 * cout, dtype=torch.float16, device="cuda")
 one, zero = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
+Rh = torch.zeros(n, 2 * cout, dtype=torch.float16, device="cuda")
+_lib.check(L.imf_h2_pack(torch.randn(n, cout, device="cuda", generator=g).data_ptr(), cout, n, cout, kco, Rh.data_ptr(), 2 * cout, None, s))
 err = torch.zeros(1, dtype=torch.int32, device="cuda")
 ws_bytes = int(L.imf_sparse_conv_g4_workspace_bytes(cout))
 ws = torch.zeros(ws_bytes, dtype=torch.uint8, device="cuda")
@@ -57,7 +60,7 @@ alg = 4 * pairs * cin + 8 * pairs + 4 * 27 * cin * cout + 4 * n * cout
 
 def g4():
     _lib.check(L.imf_sparse_conv_g4_fwd(Xh.data_ptr(), 2 * cin, kci, packed.data_ptr(), nbr_t.data_ptr(), ld_n, tile_mask.data_ptr(), None, n,
-                                        27, cin, cout, one.data_ptr(), zero.data_ptr(), None, 0, 0, 1, Yh.data_ptr(), 2 * cout, n, kco,
+                                        27, cin, cout, one.data_ptr(), zero.data_ptr(), Rh.data_ptr() if args.residual else None, 2 * cout, kco, 1, Yh.data_ptr(), 2 * cout, n, kco,
                                         ws.data_ptr(), ws_bytes, err.data_ptr(), s))
 
 
@@ -80,7 +83,7 @@ def timeit(fn, label):
 for fl in [int(f) for f in args.flags.split(",")]:
     L.imf_debug_conv_g4_trace(None, args.grid, args.npw, fl)
     timeit(g4, f"g4 grid={args.grid or 148} npw={args.npw or 8} flags={fl}")
-    if fl == 0:
+    if fl in (0, 32):
         assert int(err.item()) == 0, int(err.item())
     err.zero_()          # (with profiling flags the results are meaningless and may leave the fp16 range)
 L.imf_debug_conv_g4_trace(None, args.grid, args.npw, 0)
