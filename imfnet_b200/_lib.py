@@ -75,8 +75,6 @@ SIGNATURES = {
     "imf_conv_first_tc_workspace_bytes": (_sz, [_i32, _i32]),
     "imf_conv_first_tc_h2_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _sz, _p, _p]),
     "imf_conv_first_tc_h2_fwd_keep": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _sz, _p, _p]),
-    "imf_conv_first_direct_h2_fwd": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _sz, _p, _p]),
-    "imf_conv_first_direct_h2_fwd_keep": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _sz, _p, _p]),
     "imf_conv_first_tc_release": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _sz, _p]),
     "imf_conv_first_tc_grid": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "imf_conv_first_h2_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _i32, _p]),

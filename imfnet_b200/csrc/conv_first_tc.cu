@@ -232,125 +232,6 @@ __global__ void __launch_bounds__(256) k_cf_expand(const float* __restrict__ X, 
   }
 }
 
-// Direct form for 32 output channels (the IMFNet configuration): no E matrix at all.  Lane = output channel, the K^3 weights of that
-// channel live in REGISTERS (128 for K = 5), a warp owns 32 consecutive voxels and handles them four at a time: the neighbour features
-// of the four voxels (one 4-byte grid load per lane and 32 offsets, issued one group ahead so that their latency hides behind the
-// previous group's arithmetic) go through a 2 KB shared-memory buffer, from which every lane reads them back as broadcast 16-byte
-// loads -- per voxel 32 LDS.128 + 128 FFMA, fp32 accumulation in offset order (deterministic), BatchNorm affine / ReLU / fp16 hi/lo
-// split in registers, one 64 + 64-byte row store.  Against expansion + tensor-core product this removes the 256 MB E matrix
-// (written, then read) and its 250 two-byte shared-memory stores per voxel: 231 us -> see profiles/r02 (call 35) per 500 k voxels.
-template <int K>
-__global__ void __launch_bounds__(256, 1) k_cf_direct(const float* __restrict__ X, int ldx, const int4* __restrict__ coords,
-                                                      const int* __restrict__ n_ptr, int n_max, int B, const CfMeta* __restrict__ m,
-                                                      const float* __restrict__ grid, const ImfSlot* __restrict__ table, unsigned long long mask,
-                                                      const float* __restrict__ W, const float* __restrict__ scale,
-                                                      const float* __restrict__ shift, int relu, __half* __restrict__ Y, int ldy, int* err) {
-  constexpr int K3 = K * K * K, h = K / 2, NI = (K3 + 31) / 32, KP = NI * 32, V = 4;
-  __shared__ __align__(16) float fbuf[8][V][KP];
-  const int n = cf_count(n_ptr, n_max);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float wreg[KP];
-#pragma unroll
-  for (int k = 0; k < KP; ++k) wreg[k] = k < K3 ? __ldg(W + k * 32 + lane) : 0.f;
-  const float sc = __ldg(scale + lane), sh = __ldg(shift + lane);
-  const float act_floor = relu ? 0.f : -INFINITY;
-  int odx[NI], ody[NI], odz[NI];
-#pragma unroll
-  for (int i = 0; i < NI; ++i) {
-    const int k = lane + 32 * i;
-    odx[i] = k % K - h;
-    ody[i] = (k / K) % K - h;
-    odz[i] = k / (K * K) - h;
-  }
-  const int grid_ok = m->use_grid;
-  const int nchunks = (n + 31) / 32;
-  bool big = false;
-  for (int chunk = blockIdx.x * 8 + w; chunk < nchunks; chunk += gridDim.x * 8) {
-    const int chunk0 = chunk * 32;
-    const int myrow = chunk0 + lane;
-    int4 c = make_int4(-1, 0, 0, 0);
-    if (myrow < n) c = coords[myrow];
-    int my_ug = 0, my_base = 0, my_dx = 0, my_dxy = 0;
-    if (grid_ok && myrow < n && (unsigned)c.x < (unsigned)B) {
-      const int* it = m->item[c.x];
-      my_ug = 1;
-      my_base = (int)cf_cell(it, c.y, c.z, c.w);
-      my_dx = it[3];
-      my_dxy = it[3] * it[4];
-    }
-    const int vend = min(32, n - chunk0), ngr = (vend + V - 1) / V;
-    float f[V][NI];
-    auto gather = [&](int g) {
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const int vv = g * V + v;                         // (< 32)
-        const int ug = __shfl_sync(0xffffffffu, my_ug, vv);
-        const int base = __shfl_sync(0xffffffffu, my_base, vv);
-        const int DX = __shfl_sync(0xffffffffu, my_dx, vv), DXY = __shfl_sync(0xffffffffu, my_dxy, vv);
-        int cb = 0, cx = 0, cy = 0, cz = 0;
-        if (!ug) {                                         // hash-probe path (grid over budget, or a foreign batch index): warp-uniform
-          cb = __shfl_sync(0xffffffffu, c.x, vv); cx = __shfl_sync(0xffffffffu, c.y, vv);
-          cy = __shfl_sync(0xffffffffu, c.z, vv); cz = __shfl_sync(0xffffffffu, c.w, vv);
-        }
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          const int k = lane + 32 * i;
-          float x = 0.f;
-          if (k < K3 && vv < vend) {
-            if (ug) {
-              x = __ldg(grid + base + odz[i] * DXY + ody[i] * DX + odx[i]);
-            } else {
-              const int xx = cx + odx[i], yy = cy + ody[i], zz = cz + odz[i];
-              if (imf_coord_in_range(cb, xx, yy, zz)) {
-                const int r = imf_table_lookup(table, mask, imf_pack_key(cb, xx, yy, zz));
-                if (r >= 0) x = __ldg(X + (size_t)r * ldx);
-              }
-            }
-          }
-          f[v][i] = x;
-        }
-      }
-    };
-    gather(0);
-    for (int g = 0; g < ngr; ++g) {
-      __syncwarp();                                        // the previous group's reads of the buffer are done
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int i = 0; i < NI; ++i) fbuf[w][v][lane + 32 * i] = f[v][i];
-      __syncwarp();
-      if (g + 1 < ngr) gather(g + 1);                      // in flight during the arithmetic below
-      float acc[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] = 0.f;
-#pragma unroll
-      for (int k4 = 0; k4 < KP / 4; ++k4) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const float4 f4 = *reinterpret_cast<const float4*>(&fbuf[w][v][4 * k4]);
-          acc[v] = fmaf(f4.x, wreg[4 * k4], acc[v]);
-          acc[v] = fmaf(f4.y, wreg[4 * k4 + 1], acc[v]);
-          acc[v] = fmaf(f4.z, wreg[4 * k4 + 2], acc[v]);
-          acc[v] = fmaf(f4.w, wreg[4 * k4 + 3], acc[v]);
-        }
-      }
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const int row = chunk0 + g * V + v;
-        if (row < n) {
-          const float y = fmaxf(fmaf(acc[v], sc, sh), act_floor);
-          big |= !(fabsf(y) <= 60000.f);
-          const __half hi = __float2half_rn(y);
-          __half* yp = Y + (size_t)row * ldy + lane;       // h2 row of 32 channels: [hi 32 | lo 32]
-          yp[0] = hi;
-          yp[32] = __float2half_rn(y - __half2float(hi));
-        }
-      }
-    }
-  }
-  if (big && err) atomicOr(err, 0x10000);
-}
-
 inline size_t r256(size_t b) { return (b + 255) / 256 * 256; }
 inline int cf_kp(int K) { return (K * K * K + 63) / 64 * 64; }
 inline long long cf_budget_cells(int n_max) {          // cells per voxel (default 512; IMF_CF_CELLS_PER_VOXEL overrides), below 2^31 (k_cf_expand addresses cells with 32-bit indices)
@@ -387,12 +268,12 @@ namespace {
 int conv_first_tc_run(const float* X, int32_t ldx, const void* packed, const int32_t* coords, const int32_t* n_dev, int32_t n_max,
                       int32_t num_items, const void* table, long long capacity, int32_t kernel_size, int32_t Cout, const float* scale,
                       const float* shift, int32_t relu, void* Y, int32_t ldy, int32_t kc_out, void* workspace, size_t workspace_bytes,
-                      int32_t* err, cudaStream_t stream, bool clear_first, const float* W_direct = nullptr) {
+                      int32_t* err, cudaStream_t stream, bool clear_first) {
   IMF_CHECK_ARG(n_max >= 0 && (kernel_size == 1 || kernel_size == 3 || kernel_size == 5) && num_items >= 1 && num_items <= kMaxItems);
   IMF_CHECK_ARG(ldx >= 1 && (Cout == 32 || Cout == 64 || Cout == 128) && scale != nullptr && shift != nullptr);
   IMF_CHECK_ARG(capacity > 0 && (capacity & (capacity - 1)) == 0);
   if (n_max == 0) return IMF_OK;
-  IMF_CHECK_ARG(X != nullptr && (packed != nullptr || W_direct != nullptr) && coords != nullptr && table != nullptr && Y != nullptr && workspace != nullptr);
+  IMF_CHECK_ARG(X != nullptr && packed != nullptr && coords != nullptr && table != nullptr && Y != nullptr && workspace != nullptr);
   const CfLayout L = cf_layout(n_max, kernel_size);
   IMF_CHECK_ARG(workspace_bytes >= L.total && ((uintptr_t)workspace % 256) == 0);
   char* ws = reinterpret_cast<char*>(workspace);
@@ -421,16 +302,6 @@ int conv_first_tc_run(const float* X, int32_t ldx, const void* packed, const int
   IMF_CHECK_LAUNCH();
   const ImfSlot* tab = reinterpret_cast<const ImfSlot*>(table);
   const unsigned long long hmask = (unsigned long long)capacity - 1;
-  if (W_direct != nullptr) {                          // 32 output channels: no E matrix, no tensor-core product (k_cf_direct)
-    IMF_CHECK_ARG(Cout == 32 && kc_out == 32 && ldy >= 64);
-    __half* Yh = reinterpret_cast<__half*>(Y);
-    const int g = imf_sm_count();
-    if (kernel_size == 5) k_cf_direct<5><<<g, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, W_direct, scale, shift, relu, Yh, ldy, err);
-    else if (kernel_size == 3) k_cf_direct<3><<<g, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, W_direct, scale, shift, relu, Yh, ldy, err);
-    else k_cf_direct<1><<<g, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, W_direct, scale, shift, relu, Yh, ldy, err);
-    IMF_CHECK_LAUNCH();
-    return IMF_OK;
-  }
   const int eblocks = (L.ld_n + 255) / 256;          // 8 warps x 32 voxels per block
   if (kernel_size == 5) k_cf_expand<5><<<eblocks, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, E, ident, tmask, L.ld_n);
   else if (kernel_size == 3) k_cf_expand<3><<<eblocks, 256, 0, stream>>>(X, ldx, c4, n_dev, n_max, num_items, meta, grid, tab, hmask, E, ident, tmask, L.ld_n);
@@ -463,25 +334,6 @@ extern "C" int imf_conv_first_tc_h2_fwd_keep(const float* X, int32_t ldx, const 
                                              int32_t kc_out, void* workspace, size_t workspace_bytes, int32_t* err, cudaStream_t stream) {
   return conv_first_tc_run(X, ldx, packed, coords, n_dev, n_max, num_items, table, capacity, kernel_size, Cout, scale, shift, relu, Y, ldy, kc_out,
                            workspace, workspace_bytes, err, stream, false);
-}
-
-// The same two calls for 32 output channels WITHOUT the tensor-core detour: W = the layer's fp32 kernel [K^3, 32] (ME layout, one input
-// channel), scale / shift = the folded BatchNorm as they are (no weight multiplier); same workspace, grid and release contract.
-extern "C" int imf_conv_first_direct_h2_fwd(const float* X, int32_t ldx, const float* W, const int32_t* coords, const int32_t* n_dev,
-                                            int32_t n_max, int32_t num_items, const void* table, long long capacity, int32_t kernel_size,
-                                            int32_t Cout, const float* scale, const float* shift, int32_t relu, void* Y, int32_t ldy,
-                                            int32_t kc_out, void* workspace, size_t workspace_bytes, int32_t* err, cudaStream_t stream) {
-  IMF_CHECK_ARG(W != nullptr);
-  return conv_first_tc_run(X, ldx, nullptr, coords, n_dev, n_max, num_items, table, capacity, kernel_size, Cout, scale, shift, relu, Y, ldy, kc_out,
-                           workspace, workspace_bytes, err, stream, true, W);
-}
-extern "C" int imf_conv_first_direct_h2_fwd_keep(const float* X, int32_t ldx, const float* W, const int32_t* coords, const int32_t* n_dev,
-                                                 int32_t n_max, int32_t num_items, const void* table, long long capacity, int32_t kernel_size,
-                                                 int32_t Cout, const float* scale, const float* shift, int32_t relu, void* Y, int32_t ldy,
-                                                 int32_t kc_out, void* workspace, size_t workspace_bytes, int32_t* err, cudaStream_t stream) {
-  IMF_CHECK_ARG(W != nullptr);
-  return conv_first_tc_run(X, ldx, nullptr, coords, n_dev, n_max, num_items, table, capacity, kernel_size, Cout, scale, shift, relu, Y, ldy, kc_out,
-                           workspace, workspace_bytes, err, stream, false, W);
 }
 
 // empties the cells the coordinates occupy (same coords / counts / num_items / workspace as the _keep call before)

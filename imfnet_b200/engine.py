@@ -120,11 +120,6 @@ class FusedPlan:
                 _lib.check(L.imf_sparse_conv_h2_pack(w1.data_ptr(), 1, KP, CH[1], 64, wmul, buf.data_ptr(), torch.cuda.current_stream().cuda_stream))
                 torch.cuda.current_stream().synchronize()          # w1 is a temporary
                 self.conv1_tc = (buf, (sc / wmul).contiguous(), sh)
-        # ... and for 32 output channels (ResUNetBN2C) without the expanded operand at all: fp32 weights in registers, one lane per
-        # output channel (k_cf_direct); the tensor-core form stays for the wider first layers
-        self.conv1_direct = None
-        if self.conv1_tc is not None and CH[1] == 32:
-            self.conv1_direct = (m.conv1.kernel.detach().reshape(-1, CH[1]).to(torch.float32).contiguous(), sc, sh)
         self.final_bias = None if m.final.bias is None else (m.final.bias.detach().reshape(-1) * A).contiguous()          # logits are stored * A
         # tail conv1_tr -> ReLU -> final (+ bias) as two one-offset convolutions on the tensor-core kernel (the captured plans then
         # write the concatenation [decoder | skip] with 32-channel chunks throughout, so that it is ONE h2 matrix of chunk width 32)
@@ -630,14 +625,11 @@ class GraphPlan:
         sc, sh = f.norm1
         tok = self._tl_begin("conv1", t_out=1, cin=m.conv1.in_channels, cout=CH[1], K=m.conv1.kernel_size ** 3, residual=False)
         if self.cf_ws is not None:          # leaves the stride-1 dense grid populated for the neighbour tables below
-            if f.conv1_direct is not None:
-                fn, (packed1, sc1, sh1) = L.imf_conv_first_direct_h2_fwd_keep, f.conv1_direct
-            else:
-                fn, (packed1, sc1, sh1) = L.imf_conv_first_tc_h2_fwd_keep, f.conv1_tc
-            _lib.check(fn(self.feats.data_ptr(), self.feats.shape[1], packed1.data_ptr(), self.coords[1].data_ptr(),
-                          self._n(1), rows, self.num_items, self.tables[1].data_ptr(), self.cap, m.conv1.kernel_size,
-                          CH[1], sc1.data_ptr(), sh1.data_ptr(), 0, self.a0.data_ptr(), 2 * CH[1], _kc(CH[1]),
-                          self.cf_ws.data_ptr(), self.cf_ws_bytes, self.err.data_ptr(), s))
+            packed1, sc1, sh1 = f.conv1_tc
+            _lib.check(L.imf_conv_first_tc_h2_fwd_keep(self.feats.data_ptr(), self.feats.shape[1], packed1.data_ptr(), self.coords[1].data_ptr(),
+                                                       self._n(1), rows, self.num_items, self.tables[1].data_ptr(), self.cap, m.conv1.kernel_size,
+                                                       CH[1], sc1.data_ptr(), sh1.data_ptr(), 0, self.a0.data_ptr(), 2 * CH[1], _kc(CH[1]),
+                                                       self.cf_ws.data_ptr(), self.cf_ws_bytes, self.err.data_ptr(), s))
         else:
             _lib.check(L.imf_conv_first_h2_fwd(self.feats.data_ptr(), self.feats.shape[1], m.conv1.in_channels, m.conv1.kernel.data_ptr(),
                                                self.coords[1].data_ptr(), self._n(1), rows, self.tables[1].data_ptr(), self.cap,

@@ -223,17 +223,6 @@ int imf_conv_first_tc_h2_fwd_keep(const float* X, int32_t ldx, const void* packe
                              int32_t num_items, const void* table, long long capacity, int32_t kernel_size, int32_t Cout,
                              const float* scale, const float* shift, int32_t relu, void* Y, int32_t ldy, int32_t kc_out, void* workspace,
                              size_t workspace_bytes, int32_t* err, imf_stream_t stream);
-/* The same two calls for Cout = 32 (kc_out = 32) WITHOUT the E matrix and the tensor-core product: W = the layer's fp32 kernel
- * [K^3, 1, 32] (ME layout; /root/reference/model/resunet.py:42-49), scale / shift = the folded BatchNorm as they are; every lane keeps
- * one output channel's K^3 weights in registers and accumulates in fp32 in offset order.  Same workspace, grid and release contract. */
-int imf_conv_first_direct_h2_fwd(const float* X, int32_t ldx, const float* W, const int32_t* coords, const int32_t* n_dev, int32_t n_max,
-                                 int32_t num_items, const void* table, long long capacity, int32_t kernel_size, int32_t Cout,
-                                 const float* scale, const float* shift, int32_t relu, void* Y, int32_t ldy, int32_t kc_out, void* workspace,
-                                 size_t workspace_bytes, int32_t* err, imf_stream_t stream);
-int imf_conv_first_direct_h2_fwd_keep(const float* X, int32_t ldx, const float* W, const int32_t* coords, const int32_t* n_dev, int32_t n_max,
-                                 int32_t num_items, const void* table, long long capacity, int32_t kernel_size, int32_t Cout,
-                                 const float* scale, const float* shift, int32_t relu, void* Y, int32_t ldy, int32_t kc_out, void* workspace,
-                                 size_t workspace_bytes, int32_t* err, imf_stream_t stream);
 int imf_conv_first_tc_release(const int32_t* coords, const int32_t* n_dev, int32_t n_max, int32_t num_items, int32_t kernel_size,
                               void* workspace, size_t workspace_bytes, imf_stream_t stream);
 int imf_conv_first_tc_grid(void* workspace, int32_t n_max, int32_t kernel_size, const void** meta, const void** cells);

@@ -257,29 +257,6 @@ class Emulator:
                                     kc_out, ws, ws_bytes, err):
         self.do_imf_conv_first_tc_h2_fwd(X, ldx, packed, coords, n_dev, n_max, num_items, table, cap, K, Cout, scale, shift, relu, Y, ldy, kc_out, ws, ws_bytes, err)
 
-    def do_imf_conv_first_direct_h2_fwd(self, X, ldx, W, coords, n_dev, n_max, num_items, table, cap, K, Cout, scale, shift, relu, Y, ldy,
-                                        kc_out, ws, ws_bytes, err):
-        assert Cout == 32 and kc_out == 32
-        n = count(n_dev, n_max)
-        C = mat(coords, n, 4, 4, np.int32).tolist()
-        x = mat(X, n, 1, ldx)
-        Wk = mat(W, K ** 3, Cout, Cout)
-        t = self.tables[table]
-        acc = np.zeros((n, Cout), dtype=np.float32)
-        for k, (dx, dy, dz) in enumerate(offsets(K).tolist()):
-            idx = np.fromiter((t.get((b, x_ + dx, y_ + dy, z_ + dz), -1) for b, x_, y_, z_ in C), dtype=np.int64, count=n)
-            ok = idx >= 0
-            if ok.any():
-                acc[ok] += x[idx[ok]] @ Wk[k:k + 1]
-        acc = acc * vec(scale, Cout) + vec(shift, Cout)
-        if relu:
-            acc = np.maximum(acc, 0)
-        mat(Y, n, Cout, ldy // 2)[:] = acc
-
-    def do_imf_conv_first_direct_h2_fwd_keep(self, X, ldx, W, coords, n_dev, n_max, num_items, table, cap, K, Cout, scale, shift, relu, Y, ldy,
-                                             kc_out, ws, ws_bytes, err):
-        self.do_imf_conv_first_direct_h2_fwd(X, ldx, W, coords, n_dev, n_max, num_items, table, cap, K, Cout, scale, shift, relu, Y, ldy, kc_out, ws, ws_bytes, err)
-
     def do_imf_conv_first_tc_release(self, coords, n_dev, n_max, num_items, K, ws, ws_bytes):
         pass          # (the emulated conv1 does not use the grid)
 

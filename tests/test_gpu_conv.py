@@ -274,9 +274,8 @@ def test_first_conv_matches_oracle(frag, cin, cout, K):
     close(Y.cpu(), ref)
 
 
-def run_conv_first_tc(coords_np, X, W, scale, shift, K, num_items, n_dev=None, direct=False):
-    """imf_conv_first_tc_h2_fwd (dense-grid / hash-probe neighbour expansion + one-offset tensor-core convolution), fp32 in/out;
-    direct: imf_conv_first_direct_h2_fwd (32 output channels: fp32 weights in registers, no expanded operand)."""
+def run_conv_first_tc(coords_np, X, W, scale, shift, K, num_items, n_dev=None):
+    """imf_conv_first_tc_h2_fwd (dense-grid / hash-probe neighbour expansion + one-offset tensor-core convolution), fp32 in/out."""
     from imfnet_b200.sparse import CoordinateManager
     L = _lib.lib()
     n, cout = len(coords_np), W.shape[2]
@@ -294,25 +293,18 @@ def run_conv_first_tc(coords_np, X, W, scale, shift, K, num_items, n_dev=None, d
     Yh = torch.full((n, 2 * cout), float("nan"), dtype=torch.float16, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     X_d, sc_d, sh_d = X.cuda().contiguous(), (scale / wmul).cuda().contiguous(), shift.cuda().contiguous()
-    if direct:
-        W_d, sc_d = W[:, 0, :].cuda().contiguous(), scale.cuda().contiguous()
-        _lib.check(L.imf_conv_first_direct_h2_fwd(X_d.data_ptr(), X_d.stride(0), W_d.data_ptr(), lvl.coords.data_ptr(), _lib.ptr(n_dev), n,
-                                                  num_items, lvl.table.data_ptr(), lvl.capacity, K, cout, sc_d.data_ptr(), sh_d.data_ptr(), 0,
-                                                  Yh.data_ptr(), 2 * cout, kco, ws.data_ptr(), ws_bytes, err.data_ptr(), _lib.cur_stream()))
-    else:
-        _lib.check(L.imf_conv_first_tc_h2_fwd(X_d.data_ptr(), X_d.stride(0), packed.data_ptr(), lvl.coords.data_ptr(), _lib.ptr(n_dev), n,
-                                              num_items, lvl.table.data_ptr(), lvl.capacity, K, cout, sc_d.data_ptr(), sh_d.data_ptr(), 0,
-                                              Yh.data_ptr(), 2 * cout, kco, ws.data_ptr(), ws_bytes, err.data_ptr(), _lib.cur_stream()))
+    _lib.check(L.imf_conv_first_tc_h2_fwd(X_d.data_ptr(), X_d.stride(0), packed.data_ptr(), lvl.coords.data_ptr(), _lib.ptr(n_dev), n, num_items,
+                                          lvl.table.data_ptr(), lvl.capacity, K, cout, sc_d.data_ptr(), sh_d.data_ptr(), 0, Yh.data_ptr(),
+                                          2 * cout, kco, ws.data_ptr(), ws_bytes, err.data_ptr(), _lib.cur_stream()))
     torch.cuda.synchronize()
     assert int(err.item()) == 0
     use_grid = int(ws[:4].view(torch.int32).item())
     return h2_unpack(Yh, cout, kco).cpu(), use_grid
 
 
-@pytest.mark.parametrize("cout,K,direct", [(32, 5, False), (32, 3, False), (64, 5, False), (32, 1, False), (32, 5, True), (32, 3, True), (32, 1, True)])
-def test_first_conv_tensor_core_path_matches_oracle(frag, cout, K, direct):
-    """conv1 with one input channel as neighbour expansion (dense row-index grid) + tcgen05 product, or as the direct fp32 kernel for 32
-    output channels (tolerance of an fp32 sum there), against the oracle's convolution."""
+@pytest.mark.parametrize("cout,K", [(32, 5), (32, 3), (64, 5), (32, 1)])
+def test_first_conv_tensor_core_path_matches_oracle(frag, cout, K):
+    """conv1 with one input channel as neighbour expansion (dense row-index grid) + tcgen05 product, against the oracle's convolution."""
     coords, ocm, cm = frag
     g = torch.Generator().manual_seed(cout + K)
     n = len(coords)
@@ -320,13 +312,12 @@ def test_first_conv_tensor_core_path_matches_oracle(frag, cout, K, direct):
     W = torch.randn(K ** 3, 1, cout, generator=g) / np.sqrt(K ** 3)
     scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
     ref = sparse_ops.conv_forward(X, W, ocm.table(1, 1, K, False)) * scale + shift
-    out, use_grid = run_conv_first_tc(coords, X, W, scale, shift, K, 1, direct=direct)
+    out, use_grid = run_conv_first_tc(coords, X, W, scale, shift, K, 1)
     assert use_grid == 1
     close(out, ref, H2_RTOL)
 
 
-@pytest.mark.parametrize("direct", [False, True])
-def test_first_conv_tensor_core_path_batches_fallback_and_device_count(direct):
+def test_first_conv_tensor_core_path_batches_fallback_and_device_count():
     """(a) three batch items with different bounding boxes (one of them empty) share the grid; (b) scattered voxels whose boxes exceed
     the grid budget take the hash-probe fallback; (c) a foreign batch index falls back per voxel; (d) a device-side row count."""
     g = torch.Generator().manual_seed(9)
@@ -341,7 +332,7 @@ def test_first_conv_tensor_core_path_batches_fallback_and_device_count(direct):
         m = n if n_eff is None else n_eff
         ocm = sparse_ops.CoordinateManager(coords[:m])
         ref = sparse_ops.conv_forward(X[:m], W, ocm.table(1, 1, K, False)) * scale + shift
-        out, use_grid = run_conv_first_tc(coords, X, W, scale, shift, K, num_items, n_dev, direct=direct)
+        out, use_grid = run_conv_first_tc(coords, X, W, scale, shift, K, num_items, n_dev)
         assert use_grid == expect_grid
         close(out[:m], ref, H2_RTOL)
 

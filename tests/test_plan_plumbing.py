@@ -134,11 +134,10 @@ def test_single_fragment_graph_plan_sequence(fake_cuda):
     assert seq.count("imf_sparse_conv_g4_fwd") == 3 * 9                     # image encoder: layer2 (the stem and layer1 have their own kernels)
     assert seq.count("imf_image_conv3x3_p8_fwd") == 3 * 6 and seq.count("imf_image_maxpool_p8") == 3          # layer1 on the plane layout
     assert seq.count("imf_image_stem_h2_fwd") == 3 and seq.count("imf_image_im2col_h2_batch") == 0
-    # conv1 (32 output channels) on the dense-grid direct kernel, not the hash-probe one, not the expanded tensor-core form
-    assert seq.count("imf_conv_first_direct_h2_fwd_keep") == 3 and seq.count("imf_conv_first_h2_fwd") == 0 == seq.count("imf_conv_first_tc_h2_fwd_keep")
+    assert seq.count("imf_conv_first_tc_h2_fwd_keep") == 3 and seq.count("imf_conv_first_h2_fwd") == 0      # conv1 on the tensor-core path
     # ... whose dense grid the neighbour tables read before it is released: conv1, tables, release, in that order, per enqueue
-    order = [n for n in seq if n in ("imf_conv_first_direct_h2_fwd_keep", "imf_kernel_map_t_batch", "imf_conv_first_tc_release")]
-    assert order == ["imf_conv_first_direct_h2_fwd_keep", "imf_kernel_map_t_batch", "imf_conv_first_tc_release"] * 3
+    order = [n for n in seq if n in ("imf_conv_first_tc_h2_fwd_keep", "imf_kernel_map_t_batch", "imf_conv_first_tc_release")]
+    assert order == ["imf_conv_first_tc_h2_fwd_keep", "imf_kernel_map_t_batch", "imf_conv_first_tc_release"] * 3
     # the fusion module of the single-fragment plan is the batched chain with B = 1
     assert seq.count("imf_attention_fusion_fwd_batched") == 3 == seq.count("imf_attention_kv_batched") == seq.count("imf_batch_segments_n")
     # tail: conv1_tr -> ReLU -> final -> L2 norm as one fused tensor-core kernel
