@@ -25,10 +25,13 @@
 //   warps 2-17 softmax, four warps per TMEM lane quadrant (16 of a block's 64 tokens each): pass 1 finds the row maximum of the piece
 //             from the CHEAP product q_hi . k_hi^T (any m close to the maximum serves: it only has to keep exp2(S - m) in range, and
 //             the pieces are merged with exact weights exp2(m_piece - m)); pass 2 recomputes S with all three products, writes
-//             P = exp2(S - m) (hi/lo) to shared memory for the P.V MMAs and sums the row -- O is never rescaled.
+//             P = exp2(S - m) (hi/lo) back into the TENSOR-MEMORY columns it has just read -- the P.V MMAs take their A operand from
+//             there (tcgen05.mma with a tensor-memory A), so P never touches shared memory -- and sums the row; O is never rescaled.
 //             While the softmax warps work on block j the tensor pipe already computes S of block j + 1 (second S buffer).
 // The queries arrive scaled by log2(e) / sqrt(d) (dense.cu), so the exponentials are bare ex2.approx.
 #include <cuda_fp16.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -45,7 +48,7 @@ constexpr int kVImg = kD * 128;         // 16 KB: 128 dims x 64 tokens
 constexpr int kQBytes = 4 * kQImg;      // hi0 lo0 hi1 lo1
 constexpr int kKBytes = 4 * kKImg;
 constexpr int kVBytes = 2 * kVImg;      // Vhi Vlo
-constexpr int kPBytes = 2 * kQImg;      // Phi Plo (128 rows x 64 tokens)
+constexpr int kPBytes = 2048;           // exchange area of the softmax quarters ([4][128] floats); P itself lives in tensor memory
 constexpr int kSmem = kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes;
 constexpr int kThreads = 608;
 constexpr int kSoftWarps = 16;
@@ -70,6 +73,24 @@ __device__ __forceinline__ void ff_tma_load(uint32_t dst, const CUtensorMap* map
                "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(col), "r"(row)
                : "memory");
 }
+// A operand from tensor memory (M = 128: lane = row, one 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void ff_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d),
+      "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// 8 consecutive TMEM columns of this warp's 32 lanes <- 8 registers per lane
+__device__ __forceinline__ void ff_tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void ff_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ff_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -78,6 +99,13 @@ __device__ __forceinline__ float ff_exp2(float x) {
 __device__ __forceinline__ void ff_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 struct __align__(16) FHalf8 { __half2 a, b, c, d; };
+
+#ifdef IMF_FF_TRACE      // clock64 timeline of CTA 0 (profiling build only: IMFNET_B200_NVCC_FLAGS=-DIMF_FF_TRACE, tools/flash_trace.py)
+__device__ long long g_ff_trace[8 * 256];
+#define FF_TRACE(cond, idx, slot) do { if (blockIdx.x == 0 && (cond) && (idx) < 256) g_ff_trace[(idx) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define FF_TRACE(cond, idx, slot) do { } while (0)
+#endif
 
 struct FFPiece {
   int item;        // batch item
@@ -141,7 +169,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   unsigned char* kring = smem + kQBytes;
   unsigned char* vring = kring + 2 * kKBytes;
   unsigned char* p_s = vring + 2 * kVBytes;
-  __shared__ __align__(8) uint64_t q_full, kfull[2], kempty[2], vfull[2], vempty[2], s_ready[2], s_free[2], p_ready, p_free, o_done, o_free;
+  __shared__ __align__(8) uint64_t q_full, kfull[2], kempty[2], vfull[2], vempty[2], s_ready[2], s_free[2], p_ready, o_done, o_free;
   __shared__ uint32_t tmem_base_s;
   __shared__ FFPiece piece_s[kMaxPieces];
   __shared__ int npiece_s;
@@ -203,7 +231,6 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::mbar_init(&s_free[s], kSoftWarps);
     }
     tc::mbar_init(&p_ready, kSoftWarps);
-    tc::mbar_init(&p_free, 1);
     tc::mbar_init(&o_done, 1);
     tc::mbar_init(&o_free, kSoftWarps);
     tc::fence_barrier_init();
@@ -276,16 +303,17 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t q0 = __shfl_sync(0xffffffffu, tc::smem_u32(q_s), 0);
     const uint32_t kr0 = __shfl_sync(0xffffffffu, tc::smem_u32(kring), 0);
     const uint32_t vr0 = __shfl_sync(0xffffffffu, tc::smem_u32(vring), 0);
-    const uint32_t p0 = __shfl_sync(0xffffffffu, tc::smem_u32(p_s), 0);
     const uint32_t ts = __shfl_sync(0xffffffffu, tmem_s, 0), to = __shfl_sync(0xffffffffu, tmem_o, 0);
     uint32_t it = 0;       // K ring uses consumed
     uint32_t vit = 0;      // V ring uses consumed
     uint32_t sit = 0;      // S buffers issued
     uint32_t pit = 0;      // P blocks consumed
+    uint32_t pbuf = 0;     // S buffer that holds P of the next block (running count, as sit)
     auto issue_s = [&](uint32_t st, bool full_product) {
       const uint32_t sb = sit & 1u;
       tc::mbar_wait(&s_free[sb], ((sit >> 1) & 1u) ^ 1u, err, 4);            // softmax warps have read this S buffer's previous content
       tc::tc_fence_after_sync();
+      FF_TRACE(lane == 0, sit, 0);
       const uint32_t k0 = kr0 + st * kKBytes;
       const uint32_t d = ts + sb * 128u;
       if (tc::elect_one()) {
@@ -307,6 +335,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc::mma_commit(&kempty[st]);              // the K block is only needed by this product
       }
       __syncwarp();
+      FF_TRACE(lane == 0, sit, 1);
       ++sit;
     };
     for (int pc = 0; pc < npiece; ++pc) {
@@ -321,32 +350,38 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ---- pass 2: S(j + 1) is issued before P(j) . V(j), so the tensor pipe works while the softmax warps handle block j ----
       tc::mbar_wait(&o_free, ((uint32_t)pc & 1u) ^ 1u, err, 6);                // the previous piece's O has been drained
       tc::mbar_wait(&kfull[it & 1u], (it >> 1) & 1u, err, 5);
+      pbuf = sit;                                                               // block 0 of pass 2 goes to this S buffer
       issue_s(it & 1u, true);
       ++it;
-      for (int j = 0; j < nblk; ++j, ++vit) {
+      for (int j = 0; j < nblk; ++j, ++vit, ++pbuf) {
         if (j + 1 < nblk) {
           tc::mbar_wait(&kfull[it & 1u], (it >> 1) & 1u, err, 5);
           issue_s(it & 1u, true);
           ++it;
         }
         const uint32_t st = vit & 1u;
-        tc::mbar_wait(&p_ready, pit & 1u, err, 7);                              // P of block j is in shared memory
+        tc::mbar_wait(&p_ready, pit & 1u, err, 7);                              // P of block j is in tensor memory (in S(j)'s buffer)
         tc::mbar_wait(&vfull[st], (vit >> 1) & 1u, err, 12);
         tc::tc_fence_after_sync();
+        FF_TRACE(lane == 0, pbuf, 2);
         const uint32_t v0 = vr0 + st * kVBytes;                                // [Vhi ; Vlo] = 256 rows
         const uint32_t jj = (uint32_t)j;
+        // P is the A operand FROM TENSOR MEMORY: K step ks = the 16 tokens of softmax quarter ks, whose hi halves sit in columns
+        // [16 ks, 16 ks + 8) of S(j)'s buffer and whose lo halves in [16 ks + 8, 16 ks + 16) (written in place by the warps that read
+        // those columns).  S(j + 2) re-uses the buffer: it is issued after these MMAs by the same thread, i.e. executes after them.
+        const uint32_t pa = ts + (pbuf & 1u) * 128u;
         if (tc::elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t o = ks * 32;
-            ff_mma(to, tc::smem_desc_sw128(p0 + o), tc::smem_desc_sw128(v0 + o), id_o2, (jj | (uint32_t)ks) ? 1u : 0u);
-            ff_mma(to, tc::smem_desc_sw128(p0 + kQImg + o), tc::smem_desc_sw128(v0 + o), id_o1, 1u);
+            ff_mma_ts(to, pa + (uint32_t)(16 * ks), tc::smem_desc_sw128(v0 + o), id_o2, (jj | (uint32_t)ks) ? 1u : 0u);
+            ff_mma_ts(to, pa + (uint32_t)(16 * ks + 8), tc::smem_desc_sw128(v0 + o), id_o1, 1u);
           }
           tc::mma_commit(&vempty[st]);
-          tc::mma_commit(&p_free);
           if (j == nblk - 1) tc::mma_commit(&o_done);
         }
         __syncwarp();
+        FF_TRACE(lane == 0, pbuf, 3);
         ++pit;
       }
     }
@@ -358,8 +393,8 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int qt = (warp - 2) >> 2;                 // tokens [16 qt, 16 qt + 16) of a block
     const int r = q * 32 + lane;                    // row inside the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float* xch = reinterpret_cast<float*>(p_s);     // [4][128] exchange area between the quarters (P is idle when it is used)
-    uint32_t sct = 0, pct = 0;
+    float* xch = reinterpret_cast<float*>(p_s);     // [4][128] exchange area between the quarters
+    uint32_t sct = 0;
     for (int pc = 0; pc < npiece; ++pc) {
       const FFPiece p = piece_s[pc];
       // ---- pass 1: row maximum of the approximate scores ----
@@ -368,6 +403,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t sb = sct & 1u;
         tc::mbar_wait(&s_ready[sb], (sct >> 1) & 1u, err, 8);
         tc::tc_fence_after_sync();
+        FF_TRACE(tid == 64, sct, 4);
         const int t0 = (p.blk0 + j) * kTB + qt * 16;
         uint32_t a[16];
         tc::tmem_ld16_issue(tmem_s + lane_addr + sb * 128u + (uint32_t)(qt * 16), a);
@@ -375,6 +411,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s_free[sb]);
+        FF_TRACE(tid == 64, sct, 5);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           if (t0 + i < L) row_max = fmaxf(row_max, __uint_as_float(a[i]));
@@ -385,10 +422,11 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       ff_bar(1, kSoftWarps * 32);                   // everybody has read the exchange area before P is written again
       // ---- pass 2: exact scores, P = exp2(S - m), row sums ----
       float row_sum = 0.f;
-      for (int j = 0; j < p.nblk; ++j, ++sct, ++pct) {
+      for (int j = 0; j < p.nblk; ++j, ++sct) {
         const uint32_t sb = sct & 1u;
         tc::mbar_wait(&s_ready[sb], (sct >> 1) & 1u, err, 8);
         tc::tc_fence_after_sync();
+        FF_TRACE(tid == 64, sct, 4);
         const int t0 = (p.blk0 + j) * kTB + qt * 16;
         uint32_t a[16], b2[16];
         const uint32_t base = tmem_s + lane_addr + sb * 128u + (uint32_t)(qt * 16);
@@ -398,6 +436,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s_free[sb]);
+        FF_TRACE(tid == 64, sct, 5);
         __half2 hi[8], lo[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -410,16 +449,16 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const float2 hf2 = __half22float2(hi[i]);
           lo[i] = __floats2half2_rn(p0v - hf2.x, p1v - hf2.y);
         }
-        tc::mbar_wait(&p_free, (pct & 1u) ^ 1u, err, 9);                      // the previous block's P.V MMAs are done with p_s
-        const int ch = qt * 2;                       // 16-byte chunk index of this quarter's first token inside the 64-token (128-byte) row
-#pragma unroll
-        for (int c4 = 0; c4 < 2; ++c4) {
-          tc::st_shared_16(p_s + tc::sw128_offset(r, ch + c4), FHalf8{hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]});
-          tc::st_shared_16(p_s + kQImg + tc::sw128_offset(r, ch + c4), FHalf8{lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]});
-        }
-        tc::fence_proxy_async();
+        // P (hi | lo, 8 + 8 columns) goes back into the columns this warp has just read: the P.V MMAs take it from tensor memory, so
+        // the 32 KB P tile is neither written to nor (three times per block) read from shared memory
+        ff_tmem_st8(base, reinterpret_cast<const uint32_t*>(hi));
+        ff_tmem_st8(base + 8u, reinterpret_cast<const uint32_t*>(lo));
+        ff_tmem_st_wait();
+        tc::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&p_ready);
+        FF_TRACE(tid == 64, sct, 6);
+        FF_TRACE(tid == 64 + 15 * 32, sct, 7);
       }
       // ---- partial result of this piece: O (un-normalised), row maximum and row sum ----
       tc::mbar_wait(&o_done, (uint32_t)pc & 1u, err, 10);
@@ -512,6 +551,13 @@ __global__ void __launch_bounds__(256) k_flash_combine(const float* __restrict__
   }
 }
 
+}  // namespace
+#ifdef IMF_FF_TRACE
+extern "C" int imf_debug_flash_trace(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_ff_trace, sizeof(long long) * (size_t)(n < 8 * 256 ? n : 8 * 256)) == cudaSuccess ? IMF_OK : IMF_ERR_CUDA;
+}
+#endif
+namespace {
 inline int ff_lpad(int L) { return (L + kTB - 1) / kTB * kTB; }
 inline int ff_tiles_max(int M_max, int B) { return (M_max + kTQ - 1) / kTQ + B; }
 inline int ff_grid(int M_max, int L, int B) {
