@@ -3,7 +3,7 @@ registers, shared memory -- the numbers DESIGN.md / bench.py quote.  Runs where 
 
     python tools/ncu_summary.py gpurun_out/<tag>/g4.ncu-rep [--traffic-key 'k_sparse_conv_g4<64,64>@batched' --pick longest:k_sparse_conv_g4<64, 64>]
 
---traffic-key K --pick longest:<kernel substring>: also records dram bytes of the longest launch whose name contains the substring
+--traffic-key K --pick longest:<kernel substring> | rank:<n>:<kernel substring>: also records dram bytes of the (n-th) longest launch whose name contains the substring
 in profiles/ncu_traffic.json under key K (bench.py's roofline.traffic reads that file)."""
 import csv
 import io
@@ -68,15 +68,16 @@ def main():
         print("  " + " ".join(vals) + "  " + d["Kernel Name"].split("(")[0][-60:])
     if "--traffic-key" in sys.argv:
         key = sys.argv[sys.argv.index("--traffic-key") + 1]
-        sub = sys.argv[sys.argv.index("--pick") + 1].split(":", 1)[1]
-        cand = [d for d in recs if sub in d["Kernel Name"]]
-        best = max(cand, key=lambda d: d.get("gpu__time_duration.sum", 0))
+        pick = sys.argv[sys.argv.index("--pick") + 1]          # longest:<substring> | rank:<n>:<substring> (n-th longest, 1-based)
+        rank, sub = (1, pick.split(":", 1)[1]) if pick.startswith("longest:") else (int(pick.split(":", 2)[1]), pick.split(":", 2)[2])
+        cand = sorted((d for d in recs if sub in d["Kernel Name"]), key=lambda d: -d.get("gpu__time_duration.sum", 0))
+        best = cand[rank - 1]
         p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "ncu_traffic.json")
         cur = json.load(open(p)) if os.path.exists(p) else {}
         cur[key] = {"dram_bytes_per_launch": int(best["dram__bytes_read.sum"] + best["dram__bytes_write.sum"]),
                     "ncu_duration_us": best["gpu__time_duration.sum"] * 1e-3,
                     "tensor_pipe_pct": best.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
-                    "source": f"dram__bytes_read.sum + dram__bytes_write.sum of the longest {sub} launch in one ncu --set full capture of "
+                    "source": f"dram__bytes_read.sum + dram__bytes_write.sum of the {'longest' if rank == 1 else f'number-{rank} (by duration)'} {sub} launch in one ncu --set full capture of "
                               f"`bench.py --profile` ({os.path.basename(path)}; summary under profiles/)"}
         json.dump(cur, open(p, "w"), indent=1)
         print(f"recorded {key}: {cur[key]}")
