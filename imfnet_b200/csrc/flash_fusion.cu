@@ -259,15 +259,22 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int i = 0; i < 4; ++i) ff_tma_load(tc::smem_u32(q_s + i * kQImg), &tmQ, tc::smem_u32(&q_full), i * 64, p.row0);
         const int krow = p.item * Lpad;
         for (int pass = 0; pass < 2; ++pass) {
-          for (int j = 0; j < p.nblk; ++j, ++it) {
+          // pass 1 (q_hi . k_hi^T only) takes the blocks in PAIRS: the hi images of blocks a and a + 1 fill one ring stage in the place
+          // of [K_hi ; K_lo] of one block, so a pair is ONE N = 128 product, one barrier round trip and one TMEM read instead of two
+          for (int j = 0; j < p.nblk; j += (pass == 0 ? 2 : 1), ++it) {
             const int st = it & 1;
             tc::mbar_wait(&kempty[st], ((it >> 1) & 1u) ^ 1u, err, 2);
             unsigned char* kd = kring + st * kKBytes;
             const int t0 = krow + (p.blk0 + j) * kTB;
-            if (pass == 0) {        // q_hi . k_hi^T only: the hi images of both channel chunks
-              tc::mbar_arrive_expect_tx(&kfull[st], 2 * kKImg);
+            if (pass == 0) {        // hi images of both channel chunks (columns 0 and 128 of the h2 rows), of one or two blocks
+              const bool pair = j + 1 < p.nblk;
+              tc::mbar_arrive_expect_tx(&kfull[st], (pair ? 4 : 2) * kKImg);
               ff_tma_load(tc::smem_u32(kd), &tmK, tc::smem_u32(&kfull[st]), 0, t0);
               ff_tma_load(tc::smem_u32(kd + 2 * kKImg), &tmK, tc::smem_u32(&kfull[st]), 128, t0);
+              if (pair) {
+                ff_tma_load(tc::smem_u32(kd + kKImg), &tmK, tc::smem_u32(&kfull[st]), 0, t0 + kTB);
+                ff_tma_load(tc::smem_u32(kd + 3 * kKImg), &tmK, tc::smem_u32(&kfull[st]), 128, t0 + kTB);
+              }
             } else {
               tc::mbar_arrive_expect_tx(&kfull[st], kKBytes);
               for (int i = 0; i < 4; ++i) ff_tma_load(tc::smem_u32(kd + i * kKImg), &tmK, tc::smem_u32(&kfull[st]), i * 64, t0);
@@ -309,7 +316,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint32_t sit = 0;      // S buffers issued
     uint32_t pit = 0;      // P blocks consumed
     uint32_t pbuf = 0;     // S buffer that holds P of the next block (running count, as sit)
-    auto issue_s = [&](uint32_t st, bool full_product) {
+    auto issue_s = [&](uint32_t st, bool full_product, bool pair) {      // pair (pass 1): the stage holds K_hi of two blocks -> N = 128
       const uint32_t sb = sit & 1u;
       tc::mbar_wait(&s_free[sb], ((sit >> 1) & 1u) ^ 1u, err, 4);            // softmax warps have read this S buffer's previous content
       tc::tc_fence_after_sync();
@@ -327,7 +334,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               ff_mma(d, tc::smem_desc_sw128(qhi + o), tc::smem_desc_sw128(kb + o), id_s2, (c | ks) ? 1u : 0u);
               ff_mma(d, tc::smem_desc_sw128(qlo + o), tc::smem_desc_sw128(kb + o), id_s1, 1u);
             } else {
-              ff_mma(d, tc::smem_desc_sw128(qhi + o), tc::smem_desc_sw128(kb + o), id_s1, (c | ks) ? 1u : 0u);
+              ff_mma(d, tc::smem_desc_sw128(qhi + o), tc::smem_desc_sw128(kb + o), pair ? id_s2 : id_s1, (c | ks) ? 1u : 0u);
             }
           }
         }
@@ -342,21 +349,21 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int nblk = piece_s[pc].nblk;
       tc::mbar_wait(&q_full, (uint32_t)pc & 1u, err, 3);
       // ---- pass 1: approximate scores (hi . hi) for the row maxima ----
-      for (int j = 0; j < nblk; ++j, ++it) {
+      for (int j = 0; j < nblk; j += 2, ++it) {
         const uint32_t st = it & 1u;
         tc::mbar_wait(&kfull[st], (it >> 1) & 1u, err, 5);
-        issue_s(st, false);
+        issue_s(st, false, j + 1 < nblk);
       }
       // ---- pass 2: S(j + 1) is issued before P(j) . V(j), so the tensor pipe works while the softmax warps handle block j ----
       tc::mbar_wait(&o_free, ((uint32_t)pc & 1u) ^ 1u, err, 6);                // the previous piece's O has been drained
       tc::mbar_wait(&kfull[it & 1u], (it >> 1) & 1u, err, 5);
       pbuf = sit;                                                               // block 0 of pass 2 goes to this S buffer
-      issue_s(it & 1u, true);
+      issue_s(it & 1u, true, false);
       ++it;
       for (int j = 0; j < nblk; ++j, ++vit, ++pbuf) {
         if (j + 1 < nblk) {
           tc::mbar_wait(&kfull[it & 1u], (it >> 1) & 1u, err, 5);
-          issue_s(it & 1u, true);
+          issue_s(it & 1u, true, false);
           ++it;
         }
         const uint32_t st = vit & 1u;
@@ -399,22 +406,27 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const FFPiece p = piece_s[pc];
       // ---- pass 1: row maximum of the approximate scores ----
       float row_max = -INFINITY;
-      for (int j = 0; j < p.nblk; ++j, ++sct) {
+      for (int j = 0; j < p.nblk; j += 2, ++sct) {          // block pairs: columns [0, 64) = block j, [64, 128) = block j + 1
         const uint32_t sb = sct & 1u;
+        const bool pair = j + 1 < p.nblk;
         tc::mbar_wait(&s_ready[sb], (sct >> 1) & 1u, err, 8);
         tc::tc_fence_after_sync();
         FF_TRACE(tid == 64, sct, 4);
         const int t0 = (p.blk0 + j) * kTB + qt * 16;
-        uint32_t a[16];
-        tc::tmem_ld16_issue(tmem_s + lane_addr + sb * 128u + (uint32_t)(qt * 16), a);
+        uint32_t a[16], b2[16];
+        const uint32_t base = tmem_s + lane_addr + sb * 128u + (uint32_t)(qt * 16);
+        tc::tmem_ld16_issue(base, a);
+        if (pair) tc::tmem_ld16_issue(base + (uint32_t)kTB, b2);
         tc::tmem_ld_wait();
         tc::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&s_free[sb]);
         FF_TRACE(tid == 64, sct, 5);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
+        for (int i = 0; i < 16; ++i) {
           if (t0 + i < L) row_max = fmaxf(row_max, __uint_as_float(a[i]));
+          if (pair && t0 + kTB + i < L) row_max = fmaxf(row_max, __uint_as_float(b2[i]));
+        }
       }
       xch[qt * 128 + r] = row_max;
       ff_bar(1, kSoftWarps * 32);
