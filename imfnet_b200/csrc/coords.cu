@@ -256,7 +256,12 @@ struct KmapJob {
 struct KmapJobs {
   KmapJob j[16];
 };
-__global__ void __launch_bounds__(128) k_kernel_map_t(const __grid_constant__ KmapJobs jobs, int n_max, unsigned long long mask, int K, int ld_n) {
+// KT = kernel size as a compile-time constant (3: every 3x3x3 geometry of the network; 0: read K at run time).  With a run-time K
+// the offset decomposition costs three integer divisions per neighbour and the loop cannot be unrolled: the launch (10 tables, ~25 M
+// lookups per batch of ten fragments) was bound by ALU issue (sm 75 %, 182 us: profiles/r02/call43_ncu_other_kernels.txt).
+template <int KT>
+__global__ void __launch_bounds__(128) k_kernel_map_t(const __grid_constant__ KmapJobs jobs, int n_max, unsigned long long mask, int K_rt, int ld_n) {
+  const int K = KT ? KT : K_rt;
   __shared__ unsigned wmask[4];
   const KmapJob& jb = jobs.j[blockIdx.y];
   const int n = imf_count(jb.n_ptr, n_max);
@@ -283,8 +288,13 @@ __global__ void __launch_bounds__(128) k_kernel_map_t(const __grid_constant__ Km
     gx0 = it[0]; gy0 = it[1]; gz0 = it[2]; gdx = it[3]; gdy = it[4]; gdz = it[5];
     gbase = ((long long)(unsigned)it[6]) | ((long long)it[7] << 32);
   }
+  // centre cell of the dense grid (cells are addressed with 32-bit offsets relative to it: the grid budget is far below 2^31 cells)
+  const int lx0 = c.y - gx0, ly0 = c.z - gy0, lz0 = c.w - gz0;
+  const int* cell0 = dense ? jb.dense_cells + gbase + ((long long)lz0 * gdy + ly0) * gdx + lx0 : nullptr;
+  const int sx = jb.scale, sy = jb.scale * gdx, sz = jb.scale * gdx * gdy;
   unsigned mine = 0u;
-  for (int k = 0; k < K3; ++k) {
+#pragma unroll
+  for (int k = 0; k < (KT ? KT * KT * KT : K3); ++k) {
     int r = -1;
     if (o < n) {
       const int kx = k % K - h, ky = (k / K) % K - h, kz = k / (K * K) - h;
@@ -295,7 +305,7 @@ __global__ void __launch_bounds__(128) k_kernel_map_t(const __grid_constant__ Km
         if (dense) {
           const int lx = x - gx0, ly = y - gy0, lz = z - gz0;
           if ((unsigned)lx < (unsigned)gdx && (unsigned)ly < (unsigned)gdy && (unsigned)lz < (unsigned)gdz)
-            r = __ldg(jb.dense_cells + gbase + ((long long)lz * gdy + ly) * gdx + lx) - 1;
+            r = __ldg(cell0 + (kz * sz + ky * sy + kx * sx)) - 1;
         } else if (imf_coord_in_range(c.x, x, y, z)) {
           r = imf_table_lookup(jb.table, mask, imf_pack_key(c.x, x, y, z));
         }
@@ -548,7 +558,8 @@ extern "C" int imf_kernel_map_t_batch(const imf_kmap_job_t* jobs, int32_t njobs,
   }
   const int tiles = (n_out_max + 127) / 128;
   dim3 grid(tiles + 1, njobs);          // + 1: the mask entry past the last tile is written (zero) too
-  k_kernel_map_t<<<grid, 128, 0, stream>>>(kj, n_out_max, (unsigned long long)capacity - 1, kernel_size, ld_n);
+  if (kernel_size == 3) k_kernel_map_t<3><<<grid, 128, 0, stream>>>(kj, n_out_max, (unsigned long long)capacity - 1, kernel_size, ld_n);
+  else k_kernel_map_t<0><<<grid, 128, 0, stream>>>(kj, n_out_max, (unsigned long long)capacity - 1, kernel_size, ld_n);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }
