@@ -37,6 +37,41 @@ __global__ void __launch_bounds__(256) k_layernorm_rows(const float* __restrict_
   if (m_ptr) { const int v = *m_ptr; M = v < M ? v : M; }
   if (row >= M) return;
   const float* x = X + (size_t)row * ldx;
+  const bool aligned8 = ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b) |
+                          reinterpret_cast<uintptr_t>(Y)) & 7) == 0 && (reinterpret_cast<uintptr_t>(Yh) & 3) == 0;
+  if ((C & 63) == 0 && C <= 512 && (ldx & 1) == 0 && (ldy & 1) == 0 && aligned8) {
+    // two adjacent channels per lane: 8-byte loads, 4-byte (half2) / 8-byte stores -- the 2-byte stores of the one-channel form made
+    // the h2 output LSU-bound (77 % LSU, 22 us for 48 k x 128 tokens: profiles/r02/call43_ncu_other_kernels.txt)
+    float2 w2[8];
+    const int per2 = C >> 6;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < per2) { w2[i] = *reinterpret_cast<const float2*>(x + i * 64 + 2 * lane); s += w2[i].x + w2[i].y; }
+    const float mean = imf_warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < per2) { const float d0 = w2[i].x - mean, d1 = w2[i].y - mean; q += d0 * d0 + d1 * d1; }
+    const float rstd = 1.0f / sqrtf(imf_warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < per2) {
+        const int c = i * 64 + 2 * lane;
+        const float2 g2 = __ldg(reinterpret_cast<const float2*>(g + c)), b2 = __ldg(reinterpret_cast<const float2*>(b + c));
+        const float o0 = (w2[i].x - mean) * rstd * g2.x + b2.x, o1 = (w2[i].y - mean) * rstd * g2.y + b2.y;
+        if (Yh) {
+          const __half2 h = __floats2half2_rn(o0, o1);
+          const float2 hf = __half22float2(h);
+          __half* p = Yh + (size_t)row * ldy + i * 128 + 2 * lane;          // chunk i = channels [64 i, 64 i + 64): [hi 64 | lo 64]
+          *reinterpret_cast<__half2*>(p) = h;
+          *reinterpret_cast<__half2*>(p + 64) = __floats2half2_rn(o0 - hf.x, o1 - hf.y);
+        } else {
+          *reinterpret_cast<float2*>(Y + (size_t)row * ldy + c) = make_float2(o0, o1);
+        }
+      }
+    return;
+  }
   float v[32];
   const int per = C / 32;
   float s = 0.f;

@@ -25,8 +25,10 @@
 //   warps 2-17 softmax, four warps per TMEM lane quadrant (16 of a block's 64 tokens each): pass 1 finds the row maximum of the piece
 //             from the CHEAP product q_hi . k_hi^T (any m close to the maximum serves: it only has to keep exp2(S - m) in range, and
 //             the pieces are merged with exact weights exp2(m_piece - m)); pass 2 recomputes S with all three products, writes
-//             P = exp2(S - m) (hi/lo) back into the TENSOR-MEMORY columns it has just read -- the P.V MMAs take their A operand from
-//             there (tcgen05.mma with a tensor-memory A), so P never touches shared memory -- and sums the row; O is never rescaled.
+//             P = exp2(S - m) (hi/lo) to shared memory for the P.V MMAs and sums the row -- O is never rescaled.
+//             (P as a tensor-memory A operand, written in place over S, was tried in calls 36-51: parity tests green, but the bench's
+//             streaming steps then failed intermittently -- S(j + 2) is issued right behind P.V(j) into the columns P.V(j) still reads
+//             its A operand from, and issue order alone does not protect that read; profiles/r02/experiments/call36-54_attention.txt.)
 //             While the softmax warps work on block j the tensor pipe already computes S of block j + 1 (second S buffer).
 // The queries arrive scaled by log2(e) / sqrt(d) (dense.cu), so the exponentials are bare ex2.approx.
 #include <cuda_fp16.h>
@@ -48,7 +50,7 @@ constexpr int kVImg = kD * 128;         // 16 KB: 128 dims x 64 tokens
 constexpr int kQBytes = 4 * kQImg;      // hi0 lo0 hi1 lo1
 constexpr int kKBytes = 4 * kKImg;
 constexpr int kVBytes = 2 * kVImg;      // Vhi Vlo
-constexpr int kPBytes = 2048;           // exchange area of the softmax quarters ([4][128] floats); P itself lives in tensor memory
+constexpr int kPBytes = 2 * kQImg;      // Phi Plo (128 rows x 64 tokens)
 constexpr int kSmem = kQBytes + 2 * kKBytes + 2 * kVBytes + kPBytes;
 constexpr int kThreads = 608;
 constexpr int kSoftWarps = 16;
@@ -73,24 +75,6 @@ __device__ __forceinline__ void ff_tma_load(uint32_t dst, const CUtensorMap* map
                "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(col), "r"(row)
                : "memory");
 }
-// A operand from tensor memory (M = 128: lane = row, one 32-bit column = two consecutive K elements)
-__device__ __forceinline__ void ff_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d),
-      "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// 8 consecutive TMEM columns of this warp's 32 lanes <- 8 registers per lane
-__device__ __forceinline__ void ff_tmem_st8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
-               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-__device__ __forceinline__ void ff_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ff_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -119,31 +103,52 @@ struct FFPiece {
 
 // K [B*L, ldk] fp32 (columns 0..127 of row b*L + t) -> h2 [B*Lpad, 256 halves] (chunk width 64); V [B*L, ldv] -> V^T as h2 over the token
 // axis [B*128, 2*Lpad halves]; padding tokens = 0.  v_transposed != 0: V is given as V^T [128, ldv] (single item, the old kv layout).
+// grid = (Lpad / 64, B, 2): z = 0 packs a 64-token block of K (two channels per thread: 8-byte loads, half2 stores), z = 1 transposes
+// the block of V through shared memory (coalesced token rows in, one h2 chunk [hi 64 | lo 64] per dimension out).  The first form used
+// one thread per element: 2-byte stores everywhere and, for V, a read stride of a whole token row per thread (56 us per batch of ten
+// images, profiles/r02/call43_ncu_other_kernels.txt).
 __global__ void __launch_bounds__(256) k_flash_pack_kv(const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
                                                        int v_transposed, int L, int Lpad, int B, __half* __restrict__ Kh,
                                                        __half* __restrict__ Vh) {
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long nk = (long long)B * Lpad * kD;
-  if (idx < nk) {
-    const int c = (int)(idx % kD);
-    const long long bt = idx / kD;
-    const int t = (int)(bt % Lpad), b = (int)(bt / Lpad);
-    const float v = t < L ? K[((size_t)b * L + t) * ldk + c] : 0.f;
-    const __half h = __float2half_rn(v);
-    __half* p = Kh + (size_t)bt * (2 * kD) + (c >> 6) * 128 + (c & 63);
-    p[0] = h;
-    p[64] = __float2half_rn(v - __half2float(h));
-  } else if (idx < 2 * nk) {
-    const long long j = idx - nk;
-    const int t = (int)(j % Lpad);
-    const long long bd = j / Lpad;
-    const int d = (int)(bd % kD), b = (int)(bd / kD);
+  __shared__ float tile[64][kD + 1];
+  const int t0 = blockIdx.x * kTB, b = blockIdx.y, tid = threadIdx.x;
+  if (blockIdx.z == 0) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(K) & 7) == 0) && (ldk & 1) == 0;
+#pragma unroll 4
+    for (int e = tid; e < kTB * (kD / 2); e += 256) {          // (token, channel pair)
+      const int r = e / (kD / 2), c = 2 * (e % (kD / 2));
+      const int t = t0 + r;
+      float2 v = make_float2(0.f, 0.f);
+      if (t < L) {
+        const float* src = K + ((size_t)b * L + t) * ldk + c;
+        v = vec ? *reinterpret_cast<const float2*>(src) : make_float2(src[0], src[1]);
+      }
+      const __half2 h = __floats2half2_rn(v.x, v.y);
+      const float2 hf = __half22float2(h);
+      __half* p = Kh + ((size_t)b * Lpad + t) * (2 * kD) + (c >> 6) * 128 + (c & 63);
+      *reinterpret_cast<__half2*>(p) = h;
+      *reinterpret_cast<__half2*>(p + 64) = __floats2half2_rn(v.x - hf.x, v.y - hf.y);
+    }
+    return;
+  }
+  // V: tile[token][dim]
+  for (int e = tid; e < kTB * kD; e += 256) {
+    const int r = v_transposed ? e % kTB : e / kD, d = v_transposed ? e / kTB : e % kD;
+    const int t = t0 + r;
     float v = 0.f;
     if (t < L) v = v_transposed ? V[(size_t)d * ldv + t] : V[((size_t)b * L + t) * ldv + d];
-    const __half h = __float2half_rn(v);
-    __half* p = Vh + (size_t)bd * (2 * Lpad) + (t >> 6) * 128 + (t & 63);
-    p[0] = h;
-    p[64] = __float2half_rn(v - __half2float(h));
+    tile[r][d] = v;
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int e = tid; e < kD * (kTB / 2); e += 256) {            // (dim, token pair)
+    const int d = e / (kTB / 2), r = 2 * (e % (kTB / 2));
+    const float v0 = tile[r][d], v1 = tile[r + 1][d];
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    __half* p = Vh + ((size_t)b * kD + d) * (2 * Lpad) + (size_t)blockIdx.x * 128 + r;
+    *reinterpret_cast<__half2*>(p) = h;
+    *reinterpret_cast<__half2*>(p + 64) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
   }
 }
 
@@ -169,7 +174,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   unsigned char* kring = smem + kQBytes;
   unsigned char* vring = kring + 2 * kKBytes;
   unsigned char* p_s = vring + 2 * kVBytes;
-  __shared__ __align__(8) uint64_t q_full, kfull[2], kempty[2], vfull[2], vempty[2], s_ready[2], s_free[2], p_ready, o_done, o_free;
+  __shared__ __align__(8) uint64_t q_full, kfull[2], kempty[2], vfull[2], vempty[2], s_ready[2], s_free[2], p_ready, p_free, o_done, o_free;
   __shared__ uint32_t tmem_base_s;
   __shared__ FFPiece piece_s[kMaxPieces];
   __shared__ int npiece_s;
@@ -231,6 +236,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::mbar_init(&s_free[s], kSoftWarps);
     }
     tc::mbar_init(&p_ready, kSoftWarps);
+    tc::mbar_init(&p_free, 1);
     tc::mbar_init(&o_done, 1);
     tc::mbar_init(&o_free, kSoftWarps);
     tc::fence_barrier_init();
@@ -310,12 +316,13 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t q0 = __shfl_sync(0xffffffffu, tc::smem_u32(q_s), 0);
     const uint32_t kr0 = __shfl_sync(0xffffffffu, tc::smem_u32(kring), 0);
     const uint32_t vr0 = __shfl_sync(0xffffffffu, tc::smem_u32(vring), 0);
+    const uint32_t p0 = __shfl_sync(0xffffffffu, tc::smem_u32(p_s), 0);
     const uint32_t ts = __shfl_sync(0xffffffffu, tmem_s, 0), to = __shfl_sync(0xffffffffu, tmem_o, 0);
     uint32_t it = 0;       // K ring uses consumed
     uint32_t vit = 0;      // V ring uses consumed
     uint32_t sit = 0;      // S buffers issued
     uint32_t pit = 0;      // P blocks consumed
-    uint32_t pbuf = 0;     // S buffer that holds P of the next block (running count, as sit)
+    uint32_t pbuf = 0;     // running S count of the block whose P.V product is issued next (trace index)
     auto issue_s = [&](uint32_t st, bool full_product, bool pair) {      // pair (pass 1): the stage holds K_hi of two blocks -> N = 128
       const uint32_t sb = sit & 1u;
       tc::mbar_wait(&s_free[sb], ((sit >> 1) & 1u) ^ 1u, err, 4);            // softmax warps have read this S buffer's previous content
@@ -357,7 +364,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // ---- pass 2: S(j + 1) is issued before P(j) . V(j), so the tensor pipe works while the softmax warps handle block j ----
       tc::mbar_wait(&o_free, ((uint32_t)pc & 1u) ^ 1u, err, 6);                // the previous piece's O has been drained
       tc::mbar_wait(&kfull[it & 1u], (it >> 1) & 1u, err, 5);
-      pbuf = sit;                                                               // block 0 of pass 2 goes to this S buffer
+      pbuf = sit;
       issue_s(it & 1u, true, false);
       ++it;
       for (int j = 0; j < nblk; ++j, ++vit, ++pbuf) {
@@ -367,24 +374,21 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           ++it;
         }
         const uint32_t st = vit & 1u;
-        tc::mbar_wait(&p_ready, pit & 1u, err, 7);                              // P of block j is in tensor memory (in S(j)'s buffer)
+        tc::mbar_wait(&p_ready, pit & 1u, err, 7);                              // P of block j is in shared memory
         tc::mbar_wait(&vfull[st], (vit >> 1) & 1u, err, 12);
         tc::tc_fence_after_sync();
         FF_TRACE(lane == 0, pbuf, 2);
         const uint32_t v0 = vr0 + st * kVBytes;                                // [Vhi ; Vlo] = 256 rows
         const uint32_t jj = (uint32_t)j;
-        // P is the A operand FROM TENSOR MEMORY: K step ks = the 16 tokens of softmax quarter ks, whose hi halves sit in columns
-        // [16 ks, 16 ks + 8) of S(j)'s buffer and whose lo halves in [16 ks + 8, 16 ks + 16) (written in place by the warps that read
-        // those columns).  S(j + 2) re-uses the buffer: it is issued after these MMAs by the same thread, i.e. executes after them.
-        const uint32_t pa = ts + (pbuf & 1u) * 128u;
         if (tc::elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t o = ks * 32;
-            ff_mma_ts(to, pa + (uint32_t)(16 * ks), tc::smem_desc_sw128(v0 + o), id_o2, (jj | (uint32_t)ks) ? 1u : 0u);
-            ff_mma_ts(to, pa + (uint32_t)(16 * ks + 8), tc::smem_desc_sw128(v0 + o), id_o1, 1u);
+            ff_mma(to, tc::smem_desc_sw128(p0 + o), tc::smem_desc_sw128(v0 + o), id_o2, (jj | (uint32_t)ks) ? 1u : 0u);
+            ff_mma(to, tc::smem_desc_sw128(p0 + kQImg + o), tc::smem_desc_sw128(v0 + o), id_o1, 1u);
           }
           tc::mma_commit(&vempty[st]);
+          tc::mma_commit(&p_free);
           if (j == nblk - 1) tc::mma_commit(&o_done);
         }
         __syncwarp();
@@ -400,8 +404,8 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int qt = (warp - 2) >> 2;                 // tokens [16 qt, 16 qt + 16) of a block
     const int r = q * 32 + lane;                    // row inside the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float* xch = reinterpret_cast<float*>(p_s);     // [4][128] exchange area between the quarters
-    uint32_t sct = 0;
+    float* xch = reinterpret_cast<float*>(p_s);     // [4][128] exchange area between the quarters (P is idle when it is used)
+    uint32_t sct = 0, pct = 0;
     for (int pc = 0; pc < npiece; ++pc) {
       const FFPiece p = piece_s[pc];
       // ---- pass 1: row maximum of the approximate scores ----
@@ -434,7 +438,7 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       ff_bar(1, kSoftWarps * 32);                   // everybody has read the exchange area before P is written again
       // ---- pass 2: exact scores, P = exp2(S - m), row sums ----
       float row_sum = 0.f;
-      for (int j = 0; j < p.nblk; ++j, ++sct) {
+      for (int j = 0; j < p.nblk; ++j, ++sct, ++pct) {
         const uint32_t sb = sct & 1u;
         tc::mbar_wait(&s_ready[sb], (sct >> 1) & 1u, err, 8);
         tc::tc_fence_after_sync();
@@ -461,12 +465,14 @@ k_flash_fusion(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const float2 hf2 = __half22float2(hi[i]);
           lo[i] = __floats2half2_rn(p0v - hf2.x, p1v - hf2.y);
         }
-        // P (hi | lo, 8 + 8 columns) goes back into the columns this warp has just read: the P.V MMAs take it from tensor memory, so
-        // the 32 KB P tile is neither written to nor (three times per block) read from shared memory
-        ff_tmem_st8(base, reinterpret_cast<const uint32_t*>(hi));
-        ff_tmem_st8(base + 8u, reinterpret_cast<const uint32_t*>(lo));
-        ff_tmem_st_wait();
-        tc::tc_fence_before_sync();
+        tc::mbar_wait(&p_free, (pct & 1u) ^ 1u, err, 9);                      // the previous block's P.V MMAs are done with p_s
+        const int ch = qt * 2;                       // 16-byte chunk index of this quarter's first token inside the 64-token (128-byte) row
+#pragma unroll
+        for (int c4 = 0; c4 < 2; ++c4) {
+          tc::st_shared_16(p_s + tc::sw128_offset(r, ch + c4), FHalf8{hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]});
+          tc::st_shared_16(p_s + kQImg + tc::sw128_offset(r, ch + c4), FHalf8{lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]});
+        }
+        tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&p_ready);
         FF_TRACE(tid == 64, sct, 6);
@@ -598,8 +604,7 @@ int imf_flash_pack_kv(const float* K, int ldk, const float* V, int ldv, int v_tr
   const int Lpad = ff_lpad(L);
   __half* Kh = reinterpret_cast<__half*>(kvh2);
   __half* Vh = Kh + (size_t)B * Lpad * 2 * kD;
-  const long long total = 2LL * B * Lpad * kD;
-  k_flash_pack_kv<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(K, ldk, V, ldv, v_transposed, L, Lpad, B, Kh, Vh);
+  k_flash_pack_kv<<<dim3(Lpad / kTB, B, 2), 256, 0, stream>>>(K, ldk, V, ldv, v_transposed, L, Lpad, B, Kh, Vh);
   IMF_CHECK_LAUNCH();
   return IMF_OK;
 }
