@@ -175,6 +175,44 @@ def test_batched_plan_matches_reference_goldens(golden_dir, cuda_model):
         assert rel_rows(o.cpu(), it[3]) < TOL
 
 
+def test_streaming_steps_at_the_bench_shape_are_bit_stable(cuda_model):
+    """What bench.py times, as a regression test: C2 fragments (50 k voxels + 640x480 image), 10 fragments per replay, three plans in
+    flight, streaming calls (carry) of 30 fragments each -- every descriptor of every step must equal the blocking result of the same
+    group of ten bit for bit, and no step may raise.  (A tensor-memory P operand written in place over S passed every other test and made
+    exactly this pattern fail in about half of the bench runs -- garbage descriptors or a launch failure, profiles/r02/experiments;
+    with the L2 flush between the steps this test caught that library in one of four runs of 40 steps, hence 100 steps.)"""
+    nfrag, per_step, steps = 8, 30, 100
+    frags = []
+    for i in range(nfrag):
+        c, _ = synthetic.make_fragment(50000, 0.025, seed=60 + i)
+        frags.append((torch.from_numpy(c).cuda(), torch.ones((len(c), 1), device="cuda"), synthetic.make_image(640, 480, seed=60 + i).cuda()))
+    # (bits depend on a replay's composition -- the attention kernel's stream-K pieces are cut along the flat (tile, block) axis of
+    # the whole batch --, so the reference is the blocking result of the SAME group of ten: groups start at fragment 0, 2, 4 or 6)
+    ref = {}
+    for first in (0, 2, 4, 6):
+        group = [frags[(first + j) % nfrag] for j in range(10)]
+        ref[first] = [o.clone() for o in cuda_model.forward_batches(group, batch=10, streams=1)]
+
+    def check(step, idx, outs):
+        for g in range(per_step // 10):
+            want = ref[idx[10 * g]]
+            for j in range(10):
+                o = outs[10 * g + j]
+                assert o is not None and torch.equal(o, want[j]), f"step {step}, group {g}, fragment {idx[10 * g + j]} differs"
+
+    carry, prev = {}, None
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")          # bench.py flushes the L2 before every step: the fill runs
+    for s in range(steps):                                                     # next to the previous step's tail on another stream
+        flush.fill_(s & 1)
+        idx = [(s * per_step + j) % nfrag for j in range(per_step)]
+        outs = cuda_model.forward_batches([frags[i] for i in idx], batch=10, streams=3, carry=carry)
+        if prev is not None:          # a plan is only re-used after its previous group finished: step s - 1 is complete by now
+            check(s - 1, *prev)
+        prev = (idx, outs)
+    cuda_model.drain_batches(carry)
+    check(steps - 1, *prev)
+
+
 def test_batched_plan_bit_reproducible_over_100_replays(cuda_model):
     """The convolution kernel's MMA warps pass their turn on before issuing (early hand-off); every accumulator still has one
     issuing thread, so replays must give the same bits.  100 replays of a batch of 4 fragments at 20 k voxels (row mode at level 1,
