@@ -35,6 +35,8 @@ for _ in range(3):
                                                   out.data_ptr(), 256, ws.data_ptr(), ws.numel(), err.data_ptr(), s))
 torch.cuda.synchronize()
 t = np.zeros(8 * 256, dtype=np.int64)
+if not hasattr(raw, "imf_debug_flash_trace"):
+    sys.exit('this library has no trace hooks: rebuild with IMFNET_B200_NVCC_FLAGS="-DIMF_FF_TRACE" python -m imfnet_b200.build --force')
 fn = raw.imf_debug_flash_trace
 fn.argtypes = [C.c_void_p, C.c_int]
 assert fn(t.ctypes.data, t.size) == 0
