@@ -308,8 +308,14 @@ def run_ours(args, rank, world, local_rank):
         return res
 
     def timed(step_fn):
+        # warm-up = the timed pattern (streaming calls, drained at the end): the resident arm clones its descriptors on the device, and
+        # the caching allocator only settles once the streaming depth has been seen -- blocking warm-up steps left cudaMalloc calls
+        # (implicit device synchronisations) inside the first timed steps: `value` scattered 105-118 M while `e2e`, which writes into
+        # preallocated pinned buffers, stayed at 117-118 M (profiles/r02/call61_bench_x8_stress.txt)
+        wc = {}
         for i in range(args.warmup):
-            step_fn(i)
+            step_fn(i, wc)
+        model.drain_batches(wc)
         barrier()
         sampler = None
         if local_rank == 0:
